@@ -1,0 +1,160 @@
+/*
+ * nvqa.h -- C ABI of the B200-native (sm_100a) arch1 VQA training / eval step.
+ *
+ * This is the drop-in boundary for the ONE hot path of srama2512/novel-vqa: the body of
+ * JdJ() + optim.rmsprop in 002_train_vqa_arch1/002_train_baseline.lua:272-335,408 and of
+ * forward() in 002_train_vqa_arch1/004_eval_model.lua:202-218.  The reference has no FFI of
+ * its own (it is pure Torch7 Lua); these are the entry points a LuaJIT `ffi.cdef` of this very
+ * file binds (see INTEGRATION.md and lua/nvqa_ffi.lua).  The header is restricted to the C
+ * subset accepted by LuaJIT's ffi.cdef and by Python cffi/ctypes: no macros in declarations,
+ * plain pointers and sizes, no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; it never throws and never
+ *     aborts.  nvqa_last_error() returns the message of the last failure on this thread.
+ *   - all device work is enqueued on the model's stream; the host blocks only in *_get,
+ *     nvqa_loss, nvqa_train_step_host and nvqa_sync.
+ *   - "Torch flat layout" = the layout of the reference's getParameters() vectors
+ *     (SURVEY.md App. B): encoder = per layer i2h.weight[4H x in], i2h.bias, h2h.weight[4H x H],
+ *     h2h.bias; embedding = Linear.weight[E x V], bias[E]; multimodal = Wq[C x 2LH], bq,
+ *     Wi[C x I], bi, Wc[O x C], bc.  These are exactly the three tensors of the reference's
+ *     .t7 checkpoint {encoder_w_q, embedding_w_q, multimodal_w} (002_train_baseline.lua:401-402).
+ *   - token ids and labels are 1-based as in the reference's HDF5 files; 0 = padding.
+ *   - there is NO CPU fallback: every compute entry point fails if no sm_100 device is present.
+ */
+#ifndef NVQA_H
+#define NVQA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nvqa_model nvqa_model;
+
+/* precision of the dense contractions (element-wise math is always fp32) */
+enum {
+  NVQA_PREC_FP32_SIMT = 0, /* fp32 FFMA kernels (exact-fp32 cross-check path)                        */
+  NVQA_PREC_BF16X3    = 1, /* tcgen05, fp32 operands split into 3 bf16 planes, 6 MMAs, fp32 accum:
+                              fp32-equivalent (1e-4 parity mode on tensor cores)                    */
+  NVQA_PREC_BF16      = 2, /* tcgen05, single bf16 plane (the 1e-2 "bf16-operand" mode)             */
+  NVQA_PREC_BF16X2    = 3  /* tcgen05, 2 bf16 planes, 3 MMAs (~1e-5 relative per product)            */
+};
+
+enum { NVQA_BLOCK_ENCODER = 0, NVQA_BLOCK_EMBEDDING = 1, NVQA_BLOCK_MULTIMODAL = 2 };
+enum { NVQA_MODE_EVAL = 0, NVQA_MODE_TRAIN = 1 };
+/* backward phases, in gradient-readiness order (what the data-parallel host overlaps with NCCL) */
+enum { NVQA_PHASE_HEAD = 0, NVQA_PHASE_LSTM = 1, NVQA_PHASE_EMBED = 2, NVQA_PHASE_ALL = 3 };
+
+/* mirrors the cmd:option block of 002_train_baseline.lua:22-48 */
+typedef struct nvqa_config {
+  int32_t arch;       /* 1 = 002_train_vqa_arch1                                          */
+  int32_t V;          /* vocabulary size (count of ix_to_word)            :126-127         */
+  int32_t E;          /* -input_encoding_size  (200)                      :34              */
+  int32_t H;          /* -rnn_size             (512)                      :35              */
+  int32_t L;          /* -rnn_layer            (2)                        :36              */
+  int32_t I;          /* -nhimage              (4096)                     :33              */
+  int32_t C;          /* -common_embedding_size(1024)                     :37              */
+  int32_t O;          /* -num_output           (1000)                     :38              */
+  int32_t T;          /* question matrix width (buffer_size_q)            :136             */
+  int32_t B;          /* max rows per step (-batch_size, 500)             :31              */
+  int32_t precision;  /* NVQA_PREC_*                                                       */
+  int32_t img_norm;   /* -img_norm: 1 = L2-normalise fc7 rows inside the step  :117-123    */
+  int32_t device;     /* CUDA device ordinal (-gpuid)                                      */
+  float   dropout;    /* 0.5 at every Dropout site of the path                             */
+} nvqa_config;
+
+const char* nvqa_last_error(void);
+int nvqa_version(void);
+/* number of CUDA devices of compute capability 10.x; 0 if none (then every compute call fails) */
+int nvqa_device_count(void);
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int nvqa_model_create(const nvqa_config* cfg, nvqa_model** out);
+int nvqa_model_destroy(nvqa_model* m);
+int nvqa_set_stream(nvqa_model* m, void* cuda_stream);      /* cudaStream_t; NULL = own stream  */
+int nvqa_sync(nvqa_model* m);
+
+/* ---- parameters: module:getParameters() / torch.save table (002_train_baseline.lua:174-181,401) */
+int nvqa_param_count(const nvqa_model* m, int block, int64_t* n);
+int nvqa_params_set(nvqa_model* m, int block, const float* host_src);   /* Torch flat layout     */
+int nvqa_params_get(nvqa_model* m, int block, float* host_dst);
+int nvqa_grads_get(nvqa_model* m, int block, float* host_dst);          /* raw (unclamped) grads */
+int nvqa_rms_get(nvqa_model* m, int block, float* host_dst);            /* optim state.m         */
+int nvqa_rms_set(nvqa_model* m, int block, const float* host_src);
+/* flat device vectors [encoder | embedding | multimodal] in the optimiser's order (:183,190), for
+ * the host's all-reduce plumbing.  Element order inside a block is the library's internal one
+ * (embedding weight is kept [V x E]); every op applied through these views must be element-wise. */
+int nvqa_device_views(nvqa_model* m, float** params, float** grads, int64_t* block_offsets4);
+
+/* ---- integer preprocessing on the host: misc/RNNUtils.lua:54-61 and :84-125 (bit-exact) ---- */
+int nvqa_right_align(const int32_t* seq, const int32_t* lengths, int32_t nq, int32_t T, int32_t* out);
+/* words[sum(len)], batch_sizes[max len], 1-based sort_index[B] / sort_index_inverse[B] (stable
+ * descending sort), as returned by sort_encoding_onehot_right_align minus the one-hot expansion */
+int nvqa_pack_batch(const int32_t* q_right_aligned, const int32_t* lengths, int32_t B, int32_t T,
+                    int32_t* words, int32_t* batch_sizes, int32_t* sort_index,
+                    int32_t* sort_index_inverse, int32_t* n_words, int32_t* n_steps);
+
+/* ---- one step, piecewise (device pointers; rows in ORIGINAL batch order, no sort needed) --- */
+/* q: [B x T] right-aligned token ids, len: [B], fc7: [B x I], labels: [B] 1-based (may be NULL
+ * for eval).  Pointers must stay valid until the step's last kernel has run. */
+int nvqa_set_batch(nvqa_model* m, const int32_t* q_dev, const int32_t* len_dev, const float* fc7_dev,
+                   const int32_t* labels_dev, int32_t B);
+/* same from host memory (pinned for async): copies into the model's staging buffers */
+int nvqa_set_batch_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
+                        const int32_t* labels, int32_t B);
+/* explicit Dropout multipliers (0 or 1/(1-p)) in the padded layout, device pointers, any NULL:
+ * emb [T x B x E], lstm [(L-1) x T x B x H], q [B x 2LH], i [B x I], z [B x C].  While unset,
+ * training mode draws masks from the counter hash shared with oracle/rng.py. */
+int nvqa_set_masks(nvqa_model* m, const float* emb, const float* lstm, const float* q, const float* i,
+                   const float* z);
+int nvqa_forward(nvqa_model* m, int mode, uint64_t seed);        /* embedding .. scores           */
+int nvqa_loss(nvqa_model* m, float* loss_host);                  /* criterion:forward (blocks)    */
+int nvqa_backward(nvqa_model* m, int phase);                     /* criterion/multimodal/rnn/embedding backward */
+/* gradients *= grad_scale; clamp(-clamp, clamp); optim.rmsprop (misc/rmsprop_lrscale.lua:14-34) */
+int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps, float wd, float clamp,
+                      float grad_scale);
+int nvqa_scores_get(nvqa_model* m, float* host_dst);             /* [B x O]                       */
+int nvqa_argmax_get(nvqa_model* m, int32_t* host_dst);           /* torch.max(scores,2), 1-based  */
+int nvqa_state_get(nvqa_model* m, float* host_dst);              /* final LSTM state tv_q [B x 2LH] */
+
+/* ---- one step, fused convenience (what bench.py's e2e number calls) ------------------------ */
+/* JdJ + clamp + rmsprop from HOST buffers: H2D copies, all kernels, D2H of the loss. */
+int nvqa_train_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
+                         const int32_t* labels, int32_t B, float lr, uint64_t seed, float* loss_out);
+/* forward() + argmax from HOST buffers */
+int nvqa_eval_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
+                        int32_t B, int32_t* answers_out);
+
+/* ---- module-level pieces behind the reference's nn.Module calls (device pointers, fp32) ---- */
+/* LSTM.lstm_conventional():forward({state,x}) for one timestep (misc/LSTM.lua:12-73):
+ * state/state_out [n x 2LH], x [n x E]; masks [(L-1) x n x H] or NULL (evaluate mode). */
+int nvqa_lstm_cell_forward(nvqa_model* m, const float* state, const float* x, const float* masks,
+                           int32_t n, float* state_out);
+/* nn.CrossEntropyCriterion forward+backward on device scores [n x O] (labels 1-based) */
+int nvqa_cross_entropy(nvqa_model* m, const float* scores, const int32_t* labels, int32_t n,
+                       float* loss_host, float* dscores);
+
+/* ---- utilities ------------------------------------------------------------------------------ */
+int nvqa_host_alloc(void** p, int64_t bytes);     /* pinned host memory */
+int nvqa_host_free(void* p);
+int nvqa_device_alloc(void** p, int64_t bytes);
+int nvqa_device_free(void* p);
+int nvqa_memcpy_h2d(nvqa_model* m, void* dst, const void* src, int64_t bytes);
+int nvqa_memcpy_d2h(nvqa_model* m, void* dst, const void* src, int64_t bytes);
+/* live timing of the GEMM kernel classes with CUDA events on the model's stream: enable, run steps,
+ * then fetch a JSON array [{"kernel","launches","ms","flops"}...] (blocks). */
+int nvqa_profile(nvqa_model* m, int enable);
+int nvqa_profile_report(nvqa_model* m, char* json_out, int32_t capacity);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t nvqa_launch_count(void);
+/* stand-alone GEMM for tests: C[M x N] = A (.) B with A stored [M x K] (a_kmajor) or [K x M],
+ * B stored [N x K] (b_kmajor) or [K x N]; fp32 device pointers; precision = NVQA_PREC_* */
+int nvqa_gemm_test(int precision, int a_kmajor, int b_kmajor, int32_t M, int32_t N, int32_t K,
+                   const float* A, const float* B, float* C, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVQA_H */

@@ -1,0 +1,266 @@
+"""Host-side API of the B200-native arch1 step (Python stand-in for the Lua host).
+
+``Arch1Model`` holds what 002_train_vqa_arch1/002_train_baseline.lua keeps in its globals
+(embedding_net_q / encoder_net_q / multimodal_net parameters, RMSprop state) and exposes the
+step pieces JdJ is made of.  Everything here is plumbing: all arithmetic happens in libnvqa.so.
+"""
+import ctypes as C
+from dataclasses import dataclass, asdict
+
+import numpy as np
+
+from . import _lib
+from ._lib import (PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_BF16X2, BLOCK_ENCODER, BLOCK_EMBEDDING,  # noqa: F401
+                   BLOCK_MULTIMODAL, MODE_EVAL, MODE_TRAIN, PHASE_HEAD, PHASE_LSTM, PHASE_EMBED, PHASE_ALL,
+                   NvqaError)
+
+__all__ = ["Arch1Config", "Arch1Model", "DeviceBuffer", "right_align", "pack_batch", "synth_batch", "synth_params",
+           "device_count", "launch_count", "PREC_FP32_SIMT", "PREC_BF16X3", "PREC_BF16", "PREC_BF16X2",
+           "BLOCK_ENCODER", "BLOCK_EMBEDDING", "BLOCK_MULTIMODAL", "MODE_EVAL", "MODE_TRAIN", "PHASE_HEAD",
+           "PHASE_LSTM", "PHASE_EMBED", "PHASE_ALL", "NvqaError", "DECAY_FACTOR"]
+
+DECAY_FACTOR = 0.99997592083      # 002_train_baseline.lua:78
+
+
+@dataclass
+class Arch1Config:
+    """Defaults = the cmd:option defaults of 002_train_baseline.lua:22-48 + vocab_oracle.json size."""
+    V: int = 14773
+    E: int = 200
+    H: int = 512
+    L: int = 2
+    I: int = 4096
+    C: int = 1024
+    O: int = 1000
+    T: int = 26
+    B: int = 500
+    dropout: float = 0.5
+    img_norm: int = 1
+
+    @property
+    def S(self):
+        return 2 * self.L * self.H
+
+
+def device_count():
+    return _lib.load().nvqa_device_count()
+
+
+def launch_count():
+    return int(_lib.load().nvqa_launch_count())
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def right_align(seq, lengths):
+    """misc/RNNUtils.lua:54-61 via the C ABI."""
+    seq, lengths = _i32(seq), _i32(lengths)
+    out = np.empty_like(seq)
+    _lib.check(_lib.load().nvqa_right_align(seq.ctypes.data_as(_lib.c_i32p), lengths.ctypes.data_as(_lib.c_i32p),
+                                            seq.shape[0], seq.shape[1], out.ctypes.data_as(_lib.c_i32p)))
+    return out
+
+
+def pack_batch(q_ra, lengths):
+    """sort_encoding_onehot_right_align (misc/RNNUtils.lua:84-125) minus the one-hot: returns
+    (words, batch_sizes, sort_index, sort_index_inverse), permutations 1-based like Torch."""
+    q_ra, lengths = _i32(q_ra), _i32(lengths)
+    B, T = q_ra.shape
+    words = np.zeros(B * T, dtype=np.int32)
+    sizes = np.zeros(T, dtype=np.int32)
+    sidx = np.zeros(B, dtype=np.int32)
+    inv = np.zeros(B, dtype=np.int32)
+    nw, ns = C.c_int32(0), C.c_int32(0)
+    p = lambda a: a.ctypes.data_as(_lib.c_i32p)
+    _lib.check(_lib.load().nvqa_pack_batch(p(q_ra), p(lengths), B, T, p(words), p(sizes), p(sidx), p(inv),
+                                           C.byref(nw), C.byref(ns)))
+    return words[:nw.value].copy(), sizes[:ns.value].copy(), sidx, inv
+
+
+class DeviceBuffer:
+    """A cudaMalloc'ed array owned by Python (plumbing for tests / bench)."""
+
+    def __init__(self, model, array):
+        self.model = model
+        self.array = np.ascontiguousarray(array)
+        self.ptr = C.c_void_p()
+        _lib.check(_lib.load().nvqa_device_alloc(C.byref(self.ptr), self.array.nbytes))
+        _lib.check(_lib.load().nvqa_memcpy_h2d(model.handle, self.ptr, _ptr(self.array), self.array.nbytes))
+
+    def get(self):
+        out = np.empty_like(self.array)
+        _lib.check(_lib.load().nvqa_memcpy_d2h(self.model.handle, _ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            _lib.load().nvqa_device_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Arch1Model:
+    def __init__(self, cfg: Arch1Config = None, precision=PREC_FP32_SIMT, device=0, **overrides):
+        self.lib = _lib.load()
+        cfg = cfg or Arch1Config()
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.precision = precision
+        c = _lib.nvqa_config(arch=1, precision=precision, device=device, **{k: v for k, v in asdict(cfg).items()})
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.nvqa_model_create(C.byref(c), C.byref(self.handle)))
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.nvqa_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters (Torch flat layout on the host side) ----
+    def param_count(self, block):
+        n = C.c_int64(0)
+        _lib.check(self.lib.nvqa_param_count(self.handle, block, C.byref(n)))
+        return n.value
+
+    def _get(self, fn, block):
+        out = np.empty(self.param_count(block), dtype=np.float32)
+        _lib.check(fn(self.handle, block, out.ctypes.data_as(_lib.c_f32p)))
+        return out
+
+    def set_params(self, block, w):
+        w = _f32(w)
+        assert w.size == self.param_count(block)
+        _lib.check(self.lib.nvqa_params_set(self.handle, block, w.ctypes.data_as(_lib.c_f32p)))
+
+    def get_params(self, block):
+        return self._get(self.lib.nvqa_params_get, block)
+
+    def get_grads(self, block):
+        return self._get(self.lib.nvqa_grads_get, block)
+
+    def get_rms(self, block):
+        return self._get(self.lib.nvqa_rms_get, block)
+
+    def device_views(self):
+        p, g = C.c_void_p(), C.c_void_p()
+        off = (C.c_int64 * 4)()
+        _lib.check(self.lib.nvqa_device_views(self.handle, C.byref(p), C.byref(g), off))
+        return p.value, g.value, list(off)
+
+    # ---- batch ----
+    def set_batch_host(self, q_ra, lengths, fc7, labels=None):
+        q_ra, lengths, fc7 = _i32(q_ra), _i32(lengths), _f32(fc7)
+        labels = None if labels is None else _i32(labels)
+        self._keep = [q_ra, lengths, fc7, labels]
+        _lib.check(self.lib.nvqa_set_batch_host(self.handle, _ptr(q_ra), _ptr(lengths), _ptr(fc7),
+                                                None if labels is None else _ptr(labels), q_ra.shape[0]))
+        self.sync()
+
+    def set_batch_device(self, q, lengths, fc7, labels, B):
+        """q, lengths, fc7, labels: DeviceBuffer (labels may be None)."""
+        self._keep = [q, lengths, fc7, labels]
+        _lib.check(self.lib.nvqa_set_batch(self.handle, q.ptr, lengths.ptr, fc7.ptr,
+                                           None if labels is None else labels.ptr, B))
+
+    def set_masks(self, emb=None, lstm=None, q=None, i=None, z=None):
+        """Explicit Dropout multipliers in the padded layout (see include/nvqa.h); None clears."""
+        bufs = [None if a is None else DeviceBuffer(self, _f32(a)) for a in (emb, lstm, q, i, z)]
+        self._masks = bufs
+        _lib.check(self.lib.nvqa_set_masks(self.handle, *[None if b is None else b.ptr for b in bufs]))
+
+    # ---- step pieces ----
+    def forward(self, mode=MODE_EVAL, seed=0):
+        _lib.check(self.lib.nvqa_forward(self.handle, mode, seed))
+
+    def loss(self):
+        out = C.c_float(0)
+        _lib.check(self.lib.nvqa_loss(self.handle, C.byref(out)))
+        return out.value
+
+    def backward(self, phase=PHASE_ALL):
+        _lib.check(self.lib.nvqa_backward(self.handle, phase))
+
+    def rmsprop_step(self, lr, alpha=0.99, eps=1e-8, wd=0.0, clamp=10.0, grad_scale=1.0):
+        _lib.check(self.lib.nvqa_rmsprop_step(self.handle, lr, alpha, eps, wd, clamp, grad_scale))
+
+    def scores(self, B):
+        out = np.empty((B, self.cfg.O), dtype=np.float32)
+        _lib.check(self.lib.nvqa_scores_get(self.handle, out.ctypes.data_as(_lib.c_f32p)))
+        return out
+
+    def argmax(self, B):
+        out = np.empty(B, dtype=np.int32)
+        _lib.check(self.lib.nvqa_argmax_get(self.handle, out.ctypes.data_as(_lib.c_i32p)))
+        return out
+
+    def state(self, B):
+        out = np.empty((B, self.cfg.S), dtype=np.float32)
+        _lib.check(self.lib.nvqa_state_get(self.handle, out.ctypes.data_as(_lib.c_f32p)))
+        return out
+
+    def sync(self):
+        _lib.check(self.lib.nvqa_sync(self.handle))
+
+    # ---- fused convenience (host buffers in, scalar out) ----
+    def train_step_host(self, q_ra, lengths, fc7, labels, lr, seed):
+        out = C.c_float(0)
+        _lib.check(self.lib.nvqa_train_step_host(self.handle, _ptr(q_ra), _ptr(lengths), _ptr(fc7), _ptr(labels),
+                                                 q_ra.shape[0], lr, seed, C.byref(out)))
+        return out.value
+
+    def eval_step_host(self, q_ra, lengths, fc7):
+        ans = np.empty(q_ra.shape[0], dtype=np.int32)
+        _lib.check(self.lib.nvqa_eval_step_host(self.handle, _ptr(q_ra), _ptr(lengths), _ptr(fc7), q_ra.shape[0],
+                                                _ptr(ans)))
+        return ans
+
+
+# ---- synthetic data of the BASELINE.json shape ----------------------------------------
+def synth_params(cfg, seed=123):
+    """uniform(-0.08, 0.08) over the flat blocks in the order embedding, encoder, multimodal
+    (002_train_baseline.lua:174-181).  Returns (enc_w, emb_w, mm_w) in Torch flat layout."""
+    r = np.random.default_rng(seed)
+    n_enc = sum(4 * cfg.H * ((cfg.E if l == 0 else cfg.H) + cfg.H + 2) for l in range(cfg.L))
+    n_emb = cfg.V * cfg.E + cfg.E
+    n_mm = cfg.C * cfg.S + cfg.C + cfg.C * cfg.I + cfg.C + cfg.O * cfg.C + cfg.O
+    emb = r.uniform(-0.08, 0.08, n_emb).astype(np.float32)
+    enc = r.uniform(-0.08, 0.08, n_enc).astype(np.float32)
+    mm = r.uniform(-0.08, 0.08, n_mm).astype(np.float32)
+    return enc, emb, mm
+
+
+def synth_batch(cfg, B, seed=123, min_len=None):
+    """Random question tokens U{1..V}, lengths = T (or U{min_len..T}), fc7 = max(0, N(0,1)) (post-ReLU
+    like VGG fc7), labels U{1..O}.  Returns (q_right_aligned, lengths, fc7_raw, labels)."""
+    r = np.random.default_rng(seed)
+    T = cfg.T
+    lengths = np.full(B, T, dtype=np.int32) if min_len is None else r.integers(min_len, T + 1, B).astype(np.int32)
+    q = np.zeros((B, T), dtype=np.int32)
+    tok = r.integers(1, cfg.V + 1, (B, T)).astype(np.int32)
+    for b in range(B):
+        q[b, T - lengths[b]:] = tok[b, :lengths[b]]
+    fc7 = np.maximum(0.0, r.standard_normal((B, cfg.I))).astype(np.float32)
+    labels = r.integers(1, cfg.O + 1, B).astype(np.int32)
+    return q, lengths, fc7, labels

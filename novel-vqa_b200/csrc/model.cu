@@ -1,0 +1,690 @@
+// libnvqa: the arch1 VQA training / eval step of srama2512/novel-vqa as hand-written sm_100a CUDA
+// behind a C ABI (include/nvqa.h).  This file owns device memory, the parameter layout and the
+// per-step kernel schedule; kernels live in pointwise.cu, simt_gemm.cu and umma_gemm.cu.
+//
+// Path restated: JdJ + optim.rmsprop (002_train_vqa_arch1/002_train_baseline.lua:272-335,408) and
+// forward() (004_eval_model.lua:202-218).  Differences in *schedule* (never in math):
+//   - the one-hot nn.Linear embedding (:141-144) is a gather (K2) / scatter-add (K11);
+//   - the LSTM is processed layer by layer: the input projection x.Wi^T of ALL timesteps is one
+//     batched GEMM, only h.Wh^T is serial in t (the reference runs 4 small GEMMs per timestep clone,
+//     misc/LSTM.lua:41-43); weights are shared across timesteps instead of 26 cloned copies
+//     (misc/RNNUtils.lua:66-81), dW is accumulated by one GEMM over all (t,b) rows instead of a sum
+//     over clones (:323-326);
+//   - rows stay in original batch order; activity masks replace the length sort (see pointwise.cu);
+//   - d fc7 (computed and discarded by the reference) is not computed.
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/nvqa.h"
+#include "pointwise.cuh"
+
+namespace nvqa {
+static thread_local std::string g_err;
+int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace nvqa
+
+using namespace nvqa;
+
+struct LayerPtrs { float *Wi, *bi, *Wh, *bh; };
+
+// live per-kernel-class timing with CUDA events on the model's stream (bench.py's roofline leg)
+enum GemmCat { CAT_INPROJ = 0, CAT_REC_FWD, CAT_HEAD_FWD, CAT_HEAD_BWD, CAT_REC_BWD, CAT_WGRAD, CAT_DGRAD, CAT_OTHER, CAT_COUNT };
+static const char* kCatName[CAT_COUNT] = {"lstm_inproj_gemm", "lstm_recurrent_fwd_gemm", "head_fwd_gemm", "head_bwd_gemm",
+                                          "lstm_recurrent_bwd_gemm", "lstm_wgrad_gemm", "lstm_dgrad_gemm", "other_gemm"};
+struct ProfCat {
+  double ms = 0, flops = 0;
+  int64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct nvqa_model {
+  nvqa_config cfg;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int S = 0;
+  int64_t n_blk[3] = {0, 0, 0};
+  int64_t off_blk[4] = {0, 0, 0, 0};
+  int64_t P = 0;
+  float *params = nullptr, *grads = nullptr, *rms = nullptr;
+  LayerPtrs lw[4], lg[4];
+  float *WeT, *be, *gWeT, *gbe;
+  float *Wq, *bq, *Wv, *bv, *Wc, *bc, *gWq, *gbq, *gWv, *gbv, *gWc, *gbc;
+  // activations (sized for cfg.B rows)
+  float* y = nullptr;
+  float *pre[4] = {}, *c[4] = {}, *h[4] = {}, *xdrop[4] = {};
+  float *state = nullptr, *qd = nullptr, *vd = nullptr, *qc = nullptr, *ic = nullptr, *zd = nullptr;
+  float *scores = nullptr, *dscores = nullptr, *rowloss = nullptr, *loss = nullptr;
+  int32_t* argmax = nullptr;
+  float *dzd = nullptr, *dqpre = nullptr, *dipre = nullptr, *dqd = nullptr;
+  float *da = nullptr, *dxbuf = nullptr, *dh_carry = nullptr, *dc_carry = nullptr;
+  // batch
+  const int32_t *q = nullptr, *len = nullptr, *labels = nullptr;
+  const float* fc7 = nullptr;
+  int B = 0;
+  int32_t *q_stage = nullptr, *len_stage = nullptr, *lab_stage = nullptr;
+  float* fc7_stage = nullptr;
+  float* loss_host = nullptr;      // pinned
+  int32_t* ans_host = nullptr;     // pinned
+  // dropout
+  const float *mk_emb = nullptr, *mk_lstm = nullptr, *mk_q = nullptr, *mk_i = nullptr, *mk_z = nullptr;
+  int mode = NVQA_MODE_EVAL;
+  uint64_t seed = 0;
+  bool fwd_done = false;
+  UmmaWorkspace* ws = nullptr;
+  std::vector<void*> allocs;
+  bool profiling = false;
+  ProfCat prof[CAT_COUNT];
+};
+
+static int dalloc(nvqa_model* m, void** p, size_t bytes) {
+  NVQA_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  m->allocs.push_back(*p);
+  return 0;
+}
+template <typename T>
+static int dallocT(nvqa_model* m, T** p, size_t count) { return dalloc(m, reinterpret_cast<void**>(p), count * sizeof(T)); }
+
+static Drop make_drop(const nvqa_model* m, const float* mask, uint32_t stream) {
+  Drop d;
+  d.mask = mask;
+  d.key = stream_key(m->seed, stream);
+  d.thresh = (uint32_t)(m->cfg.dropout * 256.0f + 0.5f);
+  d.scale = 1.0f / (1.0f - m->cfg.dropout);
+  d.mode = (m->mode == NVQA_MODE_TRAIN && m->cfg.dropout > 0.f) ? (mask ? 1 : 2) : 0;
+  return d;
+}
+
+static int gemm_raw(nvqa_model* m, bool ak, bool bk, int M, int N, int K, const float* A, int lda, const float* B,
+                    int ldb, float* C, int ldc, bool beta, const float* b0, const float* b1);
+
+static int gemm(nvqa_model* m, int cat, bool ak, bool bk, int M, int N, int K, const float* A, int lda, const float* B,
+                int ldb, float* C, int ldc, bool beta, const float* b0 = nullptr, const float* b1 = nullptr) {
+  if (!m->profiling) return gemm_raw(m, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1);
+  cudaEvent_t e0, e1;
+  NVQA_CUDA(cudaEventCreate(&e0));
+  NVQA_CUDA(cudaEventCreate(&e1));
+  NVQA_CUDA(cudaEventRecord(e0, m->stream));
+  int r = gemm_raw(m, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1);
+  NVQA_CUDA(cudaEventRecord(e1, m->stream));
+  ProfCat& pc = m->prof[cat];
+  pc.pending.emplace_back(e0, e1);
+  pc.flops += 2.0 * M * N * K;
+  pc.launches += 1;
+  return r;
+}
+
+static int gemm_raw(nvqa_model* m, bool ak, bool bk, int M, int N, int K, const float* A, int lda, const float* B,
+                    int ldb, float* C, int ldc, bool beta, const float* b0, const float* b1) {
+  switch (m->cfg.precision) {
+    case NVQA_PREC_FP32_SIMT:
+      return simt_gemm(m->stream, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1);
+    case NVQA_PREC_BF16X3:
+      return umma_gemm(m->stream, 3, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws);
+    case NVQA_PREC_BF16X2:
+      return umma_gemm(m->stream, 2, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws);
+    case NVQA_PREC_BF16:
+      return umma_gemm(m->stream, 1, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws);
+  }
+  set_error("unknown precision");
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* nvqa_last_error(void) { return g_err.c_str(); }
+extern "C" int nvqa_version(void) { return 100; }
+extern "C" int64_t nvqa_launch_count(void) { return g_launches; }
+
+extern "C" int nvqa_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+static int require_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    set_error("no CUDA device: libnvqa has no CPU fallback (sm_100a kernels only)");
+    return 1;
+  }
+  NVQA_CHECK(device >= 0 && device < n, "device ordinal out of range");
+  cudaDeviceProp p;
+  NVQA_CUDA(cudaGetDeviceProperties(&p, device));
+  NVQA_CHECK(p.major == 10, "libnvqa is built for sm_100a only; this device is not compute capability 10.x");
+  NVQA_CUDA(cudaSetDevice(device));
+  return 0;
+}
+
+extern "C" int nvqa_model_destroy(nvqa_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->cfg.device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (void* p : m->allocs) cudaFree(p);
+  if (m->loss_host) cudaFreeHost(m->loss_host);
+  if (m->ans_host) cudaFreeHost(m->ans_host);
+  if (m->ws) umma_workspace_destroy(m->ws);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+  return 0;
+}
+
+static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
+  m->cfg = *cfg;
+  const int V = cfg->V, E = cfg->E, H = cfg->H, L = cfg->L, I = cfg->I, C = cfg->C, O = cfg->O, T = cfg->T, B = cfg->B;
+  NVQA_CHECK(cfg->arch == 1, "only arch 1 (002_train_vqa_arch1) is built in this round");
+  NVQA_CHECK(V > 0 && E > 0 && H > 0 && L >= 1 && L <= 4 && I > 0 && C > 0 && O > 0 && T > 0 && B > 0, "bad config");
+  NVQA_CHECK(E % 4 == 0 && H % 4 == 0 && I % 4 == 0 && C % 4 == 0, "E, H, I, C must be multiples of 4 (128-bit rows)");
+  NVQA_CHECK(cfg->dropout >= 0.f && cfg->dropout < 1.f, "dropout must be in [0,1)");
+  NVQA_CHECK(cfg->precision >= 0 && cfg->precision <= 3, "unknown precision");
+  NVQA_TRY(require_device(cfg->device));
+  NVQA_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  m->stream = m->own_stream;
+  const int S = 2 * L * H;
+  m->S = S;
+  // optimiser order: encoder, embedding, multimodal (002_train_baseline.lua:183,190)
+  int64_t n_enc = 0;
+  for (int l = 0; l < L; ++l) n_enc += (int64_t)4 * H * (l == 0 ? E : H) + 4 * H + (int64_t)4 * H * H + 4 * H;
+  m->n_blk[0] = n_enc;
+  m->n_blk[1] = (int64_t)V * E + E;
+  m->n_blk[2] = (int64_t)C * S + C + (int64_t)C * I + C + (int64_t)O * C + O;
+  for (int i = 0; i < 3; ++i) m->off_blk[i + 1] = m->off_blk[i] + ((m->n_blk[i] + 3) / 4) * 4;
+  m->P = m->off_blk[3];
+  NVQA_TRY(dallocT(m, &m->params, m->P));
+  NVQA_TRY(dallocT(m, &m->grads, m->P));
+  NVQA_TRY(dallocT(m, &m->rms, m->P));
+  NVQA_CUDA(cudaMemsetAsync(m->params, 0, m->P * 4, m->stream));
+  NVQA_CUDA(cudaMemsetAsync(m->grads, 0, m->P * 4, m->stream));
+  NVQA_CUDA(cudaMemsetAsync(m->rms, 0, m->P * 4, m->stream));   // optim.rmsprop: state.m = 0
+  auto carve = [&](float* base, LayerPtrs* lp, float** We, float** be_, float** q6) {
+    float* p = base + m->off_blk[0];
+    for (int l = 0; l < L; ++l) {
+      int in = l == 0 ? E : H;
+      lp[l].Wi = p; p += (int64_t)4 * H * in;
+      lp[l].bi = p; p += 4 * H;
+      lp[l].Wh = p; p += (int64_t)4 * H * H;
+      lp[l].bh = p; p += 4 * H;
+    }
+    p = base + m->off_blk[1];
+    *We = p; p += (int64_t)V * E;
+    *be_ = p;
+    p = base + m->off_blk[2];
+    q6[0] = p; p += (int64_t)C * S;
+    q6[1] = p; p += C;
+    q6[2] = p; p += (int64_t)C * I;
+    q6[3] = p; p += C;
+    q6[4] = p; p += (int64_t)O * C;
+    q6[5] = p;
+  };
+  float* w6[6];
+  float* g6[6];
+  carve(m->params, m->lw, &m->WeT, &m->be, w6);
+  carve(m->grads, m->lg, &m->gWeT, &m->gbe, g6);
+  m->Wq = w6[0]; m->bq = w6[1]; m->Wv = w6[2]; m->bv = w6[3]; m->Wc = w6[4]; m->bc = w6[5];
+  m->gWq = g6[0]; m->gbq = g6[1]; m->gWv = g6[2]; m->gbv = g6[3]; m->gWc = g6[4]; m->gbc = g6[5];
+
+  const int64_t N = (int64_t)T * B;
+  NVQA_TRY(dallocT(m, &m->y, N * E));
+  for (int l = 0; l < L; ++l) {
+    NVQA_TRY(dallocT(m, &m->pre[l], N * 4 * H));
+    NVQA_TRY(dallocT(m, &m->c[l], (N + B) * H));
+    NVQA_TRY(dallocT(m, &m->h[l], (N + B) * H));
+    NVQA_CUDA(cudaMemsetAsync(m->c[l], 0, (N + B) * H * 4, m->stream));
+    NVQA_CUDA(cudaMemsetAsync(m->h[l], 0, (N + B) * H * 4, m->stream));
+    if (l > 0) NVQA_TRY(dallocT(m, &m->xdrop[l], N * H));
+  }
+  NVQA_TRY(dallocT(m, &m->state, (int64_t)B * S));
+  NVQA_TRY(dallocT(m, &m->qd, (int64_t)B * S));
+  NVQA_TRY(dallocT(m, &m->vd, (int64_t)B * I));
+  NVQA_TRY(dallocT(m, &m->qc, (int64_t)B * C));
+  NVQA_TRY(dallocT(m, &m->ic, (int64_t)B * C));
+  NVQA_TRY(dallocT(m, &m->zd, (int64_t)B * C));
+  NVQA_TRY(dallocT(m, &m->scores, (int64_t)B * O));
+  NVQA_TRY(dallocT(m, &m->dscores, (int64_t)B * O));
+  NVQA_TRY(dallocT(m, &m->rowloss, (int64_t)B));
+  NVQA_TRY(dallocT(m, &m->loss, 4));
+  NVQA_TRY(dallocT(m, &m->argmax, (int64_t)B));
+  NVQA_TRY(dallocT(m, &m->dzd, (int64_t)B * C));
+  NVQA_TRY(dallocT(m, &m->dqpre, (int64_t)B * C));
+  NVQA_TRY(dallocT(m, &m->dipre, (int64_t)B * C));
+  NVQA_TRY(dallocT(m, &m->dqd, (int64_t)B * S));
+  NVQA_TRY(dallocT(m, &m->da, N * 4 * H));
+  NVQA_TRY(dallocT(m, &m->dxbuf, N * (H > E ? H : E)));
+  NVQA_TRY(dallocT(m, &m->dh_carry, (int64_t)B * H));
+  NVQA_TRY(dallocT(m, &m->dc_carry, (int64_t)B * H));
+  NVQA_TRY(dallocT(m, &m->q_stage, (int64_t)B * T));
+  NVQA_TRY(dallocT(m, &m->len_stage, (int64_t)B));
+  NVQA_TRY(dallocT(m, &m->lab_stage, (int64_t)B));
+  NVQA_TRY(dallocT(m, &m->fc7_stage, (int64_t)B * I));
+  NVQA_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->loss_host), 64));
+  NVQA_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->ans_host), (size_t)B * 4));
+  if (cfg->precision != NVQA_PREC_FP32_SIMT) {
+    // operand planes of the largest GEMM: A = da [N x 4H], B = x [N x H]  (3 bf16 planes each)
+    size_t elems = (size_t)N * 4 * H + (size_t)N * (H > E ? H : E) + (size_t)C * I + (1 << 20);
+    NVQA_TRY(umma_workspace_create(&m->ws, elems * 3 * 2 + (8 << 20)));
+  }
+  NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+extern "C" int nvqa_model_create(const nvqa_config* cfg, nvqa_model** out) {
+  if (!cfg || !out) { set_error("nvqa_model_create: null argument"); return 1; }
+  *out = nullptr;
+  nvqa_model* m = new (std::nothrow) nvqa_model();
+  if (!m) { set_error("out of host memory"); return 1; }
+  int r = model_create_impl(cfg, m);
+  if (r != 0) {
+    std::string keep = g_err;
+    nvqa_model_destroy(m);
+    g_err = keep;
+    return r;
+  }
+  *out = m;
+  return 0;
+}
+
+extern "C" int nvqa_set_stream(nvqa_model* m, void* s) {
+  NVQA_CHECK(m, "null model");
+  m->stream = s ? reinterpret_cast<cudaStream_t>(s) : m->own_stream;
+  return 0;
+}
+
+extern "C" int nvqa_sync(nvqa_model* m) {
+  NVQA_CHECK(m, "null model");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+// ---- parameters ----------------------------------------------------------------------------------
+extern "C" int nvqa_param_count(const nvqa_model* m, int block, int64_t* n) {
+  NVQA_CHECK(m && n && block >= 0 && block < 3, "bad argument");
+  *n = m->n_blk[block];
+  return 0;
+}
+
+// Torch flat layout <-> internal layout.  Only the embedding differs: Linear.weight is [E x V] in the
+// checkpoint (002_train_baseline.lua:142,174) and [V x E] on the device (coalesced row gather).
+static int block_copy(nvqa_model* m, float* dev_base, int block, float* host, bool to_device) {
+  NVQA_CHECK(m && host && block >= 0 && block < 3, "bad argument");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  float* d = dev_base + m->off_blk[block];
+  const int64_t n = m->n_blk[block];
+  if (block != NVQA_BLOCK_EMBEDDING) {
+    if (to_device) NVQA_CUDA(cudaMemcpyAsync(d, host, n * 4, cudaMemcpyHostToDevice, m->stream));
+    else NVQA_CUDA(cudaMemcpyAsync(host, d, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    NVQA_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+  }
+  const int V = m->cfg.V, E = m->cfg.E;
+  std::vector<float> tmp((size_t)n);
+  if (to_device) {
+    for (int e = 0; e < E; ++e)
+      for (int v = 0; v < V; ++v) tmp[(size_t)v * E + e] = host[(size_t)e * V + v];
+    std::memcpy(tmp.data() + (size_t)V * E, host + (size_t)V * E, (size_t)E * 4);
+    NVQA_CUDA(cudaMemcpyAsync(d, tmp.data(), n * 4, cudaMemcpyHostToDevice, m->stream));
+    NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  } else {
+    NVQA_CUDA(cudaMemcpyAsync(tmp.data(), d, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    NVQA_CUDA(cudaStreamSynchronize(m->stream));
+    for (int v = 0; v < V; ++v)
+      for (int e = 0; e < E; ++e) host[(size_t)e * V + v] = tmp[(size_t)v * E + e];
+    std::memcpy(host + (size_t)V * E, tmp.data() + (size_t)V * E, (size_t)E * 4);
+  }
+  return 0;
+}
+
+extern "C" int nvqa_params_set(nvqa_model* m, int block, const float* src) {
+  return block_copy(m, m ? m->params : nullptr, block, const_cast<float*>(src), true);
+}
+extern "C" int nvqa_params_get(nvqa_model* m, int block, float* dst) { return block_copy(m, m ? m->params : nullptr, block, dst, false); }
+extern "C" int nvqa_grads_get(nvqa_model* m, int block, float* dst) { return block_copy(m, m ? m->grads : nullptr, block, dst, false); }
+extern "C" int nvqa_rms_get(nvqa_model* m, int block, float* dst) { return block_copy(m, m ? m->rms : nullptr, block, dst, false); }
+extern "C" int nvqa_rms_set(nvqa_model* m, int block, const float* src) {
+  return block_copy(m, m ? m->rms : nullptr, block, const_cast<float*>(src), true);
+}
+
+extern "C" int nvqa_device_views(nvqa_model* m, float** params, float** grads, int64_t* off4) {
+  NVQA_CHECK(m, "null model");
+  if (params) *params = m->params;
+  if (grads) *grads = m->grads;
+  if (off4) for (int i = 0; i < 4; ++i) off4[i] = m->off_blk[i];
+  return 0;
+}
+
+// ---- batch ---------------------------------------------------------------------------------------
+extern "C" int nvqa_set_batch(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
+                              const int32_t* labels, int32_t B) {
+  NVQA_CHECK(m && q && len && fc7, "null argument");
+  NVQA_CHECK(B > 0 && B <= m->cfg.B, "batch size out of range");
+  m->q = q; m->len = len; m->fc7 = fc7; m->labels = labels; m->B = B;
+  m->fwd_done = false;
+  return 0;
+}
+
+extern "C" int nvqa_set_batch_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
+                                   const int32_t* labels, int32_t B) {
+  NVQA_CHECK(m && q && len && fc7, "null argument");
+  NVQA_CHECK(B > 0 && B <= m->cfg.B, "batch size out of range");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_CUDA(cudaMemcpyAsync(m->q_stage, q, (size_t)B * m->cfg.T * 4, cudaMemcpyHostToDevice, m->stream));
+  NVQA_CUDA(cudaMemcpyAsync(m->len_stage, len, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
+  NVQA_CUDA(cudaMemcpyAsync(m->fc7_stage, fc7, (size_t)B * m->cfg.I * 4, cudaMemcpyHostToDevice, m->stream));
+  if (labels) NVQA_CUDA(cudaMemcpyAsync(m->lab_stage, labels, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
+  return nvqa_set_batch(m, m->q_stage, m->len_stage, m->fc7_stage, labels ? m->lab_stage : nullptr, B);
+}
+
+extern "C" int nvqa_set_masks(nvqa_model* m, const float* emb, const float* lstm, const float* q, const float* i,
+                              const float* z) {
+  NVQA_CHECK(m, "null model");
+  m->mk_emb = emb; m->mk_lstm = lstm; m->mk_q = q; m->mk_i = i; m->mk_z = z;
+  return 0;
+}
+
+// ---- forward -------------------------------------------------------------------------------------
+static Drop lstm_drop(const nvqa_model* m, int l /* between layer l and l+1 */) {
+  const int64_t per = (int64_t)m->cfg.T * m->B * m->cfg.H;
+  return make_drop(m, m->mk_lstm ? m->mk_lstm + per * l : nullptr, STREAM_LSTM0 + l);
+}
+
+extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
+  NVQA_CHECK(m && m->q, "nvqa_forward: no batch set");
+  NVQA_CHECK(mode == NVQA_MODE_EVAL || mode == NVQA_MODE_TRAIN, "bad mode");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  m->mode = mode; m->seed = seed;
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, T = c.T, E = c.E, H = c.H, L = c.L, S = m->S;
+  const int64_t BH = (int64_t)B * H;
+  cudaStream_t s = m->stream;
+  // embedding_net_q:forward   (:300)
+  NVQA_TRY(embed_fwd(s, m->q, m->len, m->WeT, m->be, m->y, make_drop(m, m->mk_emb, STREAM_EMB), B, T, E, c.V));
+  // rnn_forward (:303), layer-major
+  for (int l = 0; l < L; ++l) {
+    const float* X = l == 0 ? m->y : m->xdrop[l];
+    const int in = l == 0 ? E : H;
+    NVQA_TRY(gemm(m, CAT_INPROJ, true, true, T * B, 4 * H, in, X, in, m->lw[l].Wi, in, m->pre[l], 4 * H, false, m->lw[l].bi,
+                  m->lw[l].bh));
+    for (int t = 0; t < T; ++t) {
+      float* pre_t = m->pre[l] + (int64_t)t * B * 4 * H;
+      if (t > 0)   // h_0 == 0: the recurrent term of the first step vanishes
+        NVQA_TRY(gemm(m, CAT_REC_FWD, true, true, B, 4 * H, H, m->h[l] + t * BH, H, m->lw[l].Wh, H, pre_t, 4 * H, true));
+      NVQA_TRY(lstm_gates_fwd(s, pre_t, m->c[l] + t * BH, H, m->c[l] + (t + 1) * BH, m->h[l] + (t + 1) * BH, H,
+                              l + 1 < L ? m->xdrop[l + 1] + t * BH : nullptr, m->len, lstm_drop(m, l), t, T, B, H));
+    }
+  }
+  // tv_q (:306) and multimodal_net:forward (:307)
+  const float* cf[4];
+  const float* hf[4];
+  for (int l = 0; l < L; ++l) { cf[l] = m->c[l] + T * BH; hf[l] = m->h[l] + T * BH; }
+  NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L));
+  NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), B, c.I, c.img_norm));
+  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
+  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
+  NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C));
+  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.O, c.C, m->zd, c.C, m->Wc, c.C, m->scores, c.O, false, m->bc));
+  // criterion forward/backward (:308-310) + torch.max (004_eval_model.lua:233)
+  NVQA_TRY(softmax_ce(s, m->scores, m->labels, m->labels ? m->dscores : nullptr, m->rowloss, m->argmax, B, c.O,
+                      1.0f / (float)B));
+  if (m->labels) NVQA_TRY(loss_reduce(s, m->rowloss, m->loss, B));
+  m->fwd_done = true;
+  return 0;
+}
+
+extern "C" int nvqa_loss(nvqa_model* m, float* out) {
+  NVQA_CHECK(m && out && m->fwd_done && m->labels, "nvqa_loss: forward with labels has not run");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_CUDA(cudaMemcpyAsync(m->loss_host, m->loss, 4, cudaMemcpyDeviceToHost, m->stream));
+  NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  *out = m->loss_host[0];
+  return 0;
+}
+
+// ---- backward ------------------------------------------------------------------------------------
+static int backward_head(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, S = m->S, C = c.C, O = c.O, I = c.I;
+  cudaStream_t s = m->stream;
+  // bias gradients and the embedding scatter accumulate with atomics: clear them (weight gradients
+  // are written with beta = 0 by exactly one GEMM each)
+  NVQA_CUDA(cudaMemsetAsync(m->gbc, 0, (size_t)O * 4, s));
+  NVQA_CUDA(cudaMemsetAsync(m->gbq, 0, (size_t)C * 4, s));
+  NVQA_CUDA(cudaMemsetAsync(m->gbv, 0, (size_t)C * 4, s));
+  // Linear(C,O) backward
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, O, C, B, m->dscores, O, m->zd, C, m->gWc, C, false));
+  NVQA_TRY(colsum(s, m->dscores, B, O, O, m->gbc, nullptr));
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, C, O, m->dscores, O, m->Wc, C, m->dzd, C, false));
+  // Dropout, CMulTable, Tanh backward
+  NVQA_TRY(fuse_bwd(s, m->dzd, m->qc, m->ic, m->dqpre, m->dipre, make_drop(m, m->mk_z, STREAM_HEAD), B, C));
+  // AxB Linear backward (no d fc7)
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, S, B, m->dqpre, C, m->qd, S, m->gWq, S, false));
+  NVQA_TRY(colsum(s, m->dqpre, B, C, C, m->gbq, nullptr));
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, I, B, m->dipre, C, m->vd, I, m->gWv, I, false));
+  NVQA_TRY(colsum(s, m->dipre, B, C, C, m->gbv, nullptr));
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, S, C, m->dqpre, C, m->Wq, S, m->dqd, S, false));
+  NVQA_TRY(mask_inplace(s, m->dqd, make_drop(m, m->mk_q, STREAM_AXB_Q), (int64_t)B * S));
+  return 0;
+}
+
+static int backward_lstm(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, T = c.T, E = c.E, H = c.H, L = c.L, S = m->S;
+  const int64_t BH = (int64_t)B * H;
+  cudaStream_t s = m->stream;
+  for (int l = L - 1; l >= 0; --l) {
+    const float* dh_in = m->dqd + (2 * l + 1) * H;
+    const float* dc_in = m->dqd + (2 * l) * H;
+    int ld = S;
+    for (int t = T - 1; t >= 0; --t) {
+      NVQA_TRY(lstm_gates_bwd(s, m->pre[l] + (int64_t)t * B * 4 * H, m->c[l] + t * BH, m->c[l] + (t + 1) * BH, dh_in, ld,
+                              l + 1 < L ? m->dxbuf + t * BH : nullptr, dc_in, ld, m->da + (int64_t)t * B * 4 * H,
+                              m->dc_carry, m->len, lstm_drop(m, l), t, T, B, H));
+      if (t > 0)   // dh_{t-1} = da_t . Wh
+        NVQA_TRY(gemm(m, CAT_REC_BWD, true, false, B, H, 4 * H, m->da + (int64_t)t * B * 4 * H, 4 * H, m->lw[l].Wh, H, m->dh_carry, H,
+                      false));
+      dh_in = m->dh_carry; dc_in = m->dc_carry; ld = H;
+    }
+    const float* X = l == 0 ? m->y : m->xdrop[l];
+    const int in = l == 0 ? E : H;
+    NVQA_CUDA(cudaMemsetAsync(m->lg[l].bi, 0, (size_t)4 * H * 4, s));
+    NVQA_CUDA(cudaMemsetAsync(m->lg[l].bh, 0, (size_t)4 * H * 4, s));
+    // sum over timestep clones of accGradParameters (:323-326) as one GEMM over all (t,b) rows
+    NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, in, T * B, m->da, 4 * H, X, in, m->lg[l].Wi, in, false));
+    NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, H, T * B, m->da, 4 * H, m->h[l], H, m->lg[l].Wh, H, false));
+    NVQA_TRY(colsum(s, m->da, T * B, 4 * H, 4 * H, m->lg[l].bi, m->lg[l].bh));
+    // dX = da . Wi  (layer l-1's dh contribution, or the embedding gradient for l = 0)
+    NVQA_TRY(gemm(m, CAT_DGRAD, true, false, T * B, in, 4 * H, m->da, 4 * H, m->lw[l].Wi, in, m->dxbuf, in, false));
+  }
+  return 0;
+}
+
+static int backward_embed(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  cudaStream_t s = m->stream;
+  NVQA_CUDA(cudaMemsetAsync(m->gWeT, 0, (size_t)m->n_blk[1] * 4, s));
+  NVQA_TRY(embed_bwd(s, m->q, m->len, m->y, m->dxbuf, m->gWeT, make_drop(m, m->mk_emb, STREAM_EMB), m->B, c.T, c.E, c.V));
+  NVQA_TRY(colsum(s, m->dxbuf, c.T * m->B, c.E, c.E, m->gbe, nullptr));
+  return 0;
+}
+
+extern "C" int nvqa_backward(nvqa_model* m, int phase) {
+  NVQA_CHECK(m && m->fwd_done && m->labels, "nvqa_backward: forward with labels has not run");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  if (phase == NVQA_PHASE_HEAD || phase == NVQA_PHASE_ALL) NVQA_TRY(backward_head(m));
+  if (phase == NVQA_PHASE_LSTM || phase == NVQA_PHASE_ALL) NVQA_TRY(backward_lstm(m));
+  if (phase == NVQA_PHASE_EMBED || phase == NVQA_PHASE_ALL) NVQA_TRY(backward_embed(m));
+  NVQA_CHECK(phase >= 0 && phase <= 3, "bad phase");
+  return 0;
+}
+
+extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps, float wd, float clamp, float gscale) {
+  NVQA_CHECK(m, "null model");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  return clamp_rmsprop(m->stream, m->params, m->grads, m->rms, m->P, lr, alpha, eps, wd, clamp, gscale);
+}
+
+// ---- results -------------------------------------------------------------------------------------
+static int d2h(nvqa_model* m, void* dst, const void* src, size_t bytes) {
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, m->stream));
+  NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+extern "C" int nvqa_scores_get(nvqa_model* m, float* dst) {
+  NVQA_CHECK(m && dst && m->fwd_done, "forward has not run");
+  return d2h(m, dst, m->scores, (size_t)m->B * m->cfg.O * 4);
+}
+extern "C" int nvqa_argmax_get(nvqa_model* m, int32_t* dst) {
+  NVQA_CHECK(m && dst && m->fwd_done, "forward has not run");
+  return d2h(m, dst, m->argmax, (size_t)m->B * 4);
+}
+extern "C" int nvqa_state_get(nvqa_model* m, float* dst) {
+  NVQA_CHECK(m && dst && m->fwd_done, "forward has not run");
+  return d2h(m, dst, m->state, (size_t)m->B * m->S * 4);
+}
+
+// ---- fused convenience -----------------------------------------------------------------------------
+extern "C" int nvqa_train_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
+                                    const int32_t* labels, int32_t B, float lr, uint64_t seed, float* loss_out) {
+  NVQA_CHECK(labels, "labels required");
+  NVQA_TRY(nvqa_set_batch_host(m, q, len, fc7, labels, B));
+  NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
+  NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
+  // clamp(-10,10) (:329) and optim.rmsprop defaults alpha=.99, eps=1e-8 (:408)
+  NVQA_TRY(nvqa_rmsprop_step(m, lr, 0.99f, 1e-8f, 0.f, 10.f, 1.f));
+  if (loss_out) NVQA_TRY(nvqa_loss(m, loss_out));
+  return 0;
+}
+
+extern "C" int nvqa_eval_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7, int32_t B,
+                                   int32_t* answers_out) {
+  NVQA_CHECK(answers_out, "null output");
+  NVQA_TRY(nvqa_set_batch_host(m, q, len, fc7, nullptr, B));
+  NVQA_TRY(nvqa_forward(m, NVQA_MODE_EVAL, 0));
+  NVQA_CUDA(cudaMemcpyAsync(m->ans_host, m->argmax, (size_t)B * 4, cudaMemcpyDeviceToHost, m->stream));
+  NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  std::memcpy(answers_out, m->ans_host, (size_t)B * 4);
+  return 0;
+}
+
+// ---- module-level pieces ---------------------------------------------------------------------------
+extern "C" int nvqa_lstm_cell_forward(nvqa_model* m, const float* state, const float* x, const float* masks, int32_t n,
+                                      float* state_out) {
+  NVQA_CHECK(m && state && x && state_out, "null argument");
+  const nvqa_config& c = m->cfg;
+  NVQA_CHECK(n > 0 && (int64_t)n <= (int64_t)c.B * c.T, "row count out of range");
+  NVQA_CUDA(cudaSetDevice(c.device));
+  const int E = c.E, H = c.H, L = c.L, S = m->S;
+  cudaStream_t s = m->stream;
+  float* pre = m->da;                     // scratch [n x 4H]
+  float* xin = m->dxbuf;                  // scratch [n x H] (dropped h of the layer below)
+  Drop d;
+  d.mask = masks; d.key = 0; d.thresh = 0; d.scale = 1.f; d.mode = masks ? 1 : 0;
+  for (int l = 0; l < L; ++l) {
+    const float* X = l == 0 ? x : xin;
+    const int in = l == 0 ? E : H;
+    NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, 4 * H, in, X, in, m->lw[l].Wi, in, pre, 4 * H, false, m->lw[l].bi, m->lw[l].bh));
+    NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, 4 * H, H, state + (2 * l + 1) * H, S, m->lw[l].Wh, H, pre, 4 * H, true));
+    Drop dl = d;
+    if (masks) dl.mask = masks + (int64_t)l * n * H;
+    NVQA_TRY(lstm_gates_fwd(s, pre, state + 2 * l * H, S, state_out + 2 * l * H, state_out + (2 * l + 1) * H, S,
+                            l + 1 < L ? xin : nullptr, nullptr, dl, 0, 1, n, H));
+  }
+  return 0;
+}
+
+extern "C" int nvqa_cross_entropy(nvqa_model* m, const float* scores, const int32_t* labels, int32_t n, float* loss_host,
+                                  float* dscores) {
+  NVQA_CHECK(m && scores && labels, "null argument");
+  NVQA_CHECK(n > 0 && n <= m->cfg.B, "row count out of range");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_TRY(softmax_ce(m->stream, scores, labels, dscores, m->rowloss, nullptr, n, m->cfg.O, 1.0f / (float)n));
+  NVQA_TRY(loss_reduce(m->stream, m->rowloss, m->loss, n));
+  if (loss_host) {
+    NVQA_CUDA(cudaMemcpyAsync(m->loss_host, m->loss, 4, cudaMemcpyDeviceToHost, m->stream));
+    NVQA_CUDA(cudaStreamSynchronize(m->stream));
+    *loss_host = m->loss_host[0];
+  }
+  return 0;
+}
+
+// ---- live profile ------------------------------------------------------------------------------------
+extern "C" int nvqa_profile(nvqa_model* m, int enable) {
+  NVQA_CHECK(m, "null model");
+  m->profiling = enable != 0;
+  if (enable) for (auto& pc : m->prof) { pc.ms = 0; pc.flops = 0; pc.launches = 0; }
+  return 0;
+}
+
+extern "C" int nvqa_profile_report(nvqa_model* m, char* buf, int32_t cap) {
+  NVQA_CHECK(m && buf && cap > 0, "bad argument");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  std::string out = "[";
+  for (int c = 0; c < CAT_COUNT; ++c) {
+    ProfCat& pc = m->prof[c];
+    for (auto& ev : pc.pending) {
+      float ms = 0.f;
+      NVQA_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+      pc.ms += ms;
+      cudaEventDestroy(ev.first);
+      cudaEventDestroy(ev.second);
+    }
+    pc.pending.clear();
+    char line[256];
+    snprintf(line, sizeof line, "%s{\"kernel\": \"%s\", \"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e}",
+             c ? ", " : "", kCatName[c], (long long)pc.launches, pc.ms, pc.flops);
+    out += line;
+  }
+  out += "]";
+  NVQA_CHECK((int)out.size() + 1 <= cap, "report buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
+// ---- utilities ---------------------------------------------------------------------------------------
+extern "C" int nvqa_host_alloc(void** p, int64_t bytes) {
+  NVQA_CHECK(p && bytes >= 0, "bad argument");
+  NVQA_CUDA(cudaMallocHost(p, (size_t)(bytes ? bytes : 16)));
+  return 0;
+}
+extern "C" int nvqa_host_free(void* p) { if (p) NVQA_CUDA(cudaFreeHost(p)); return 0; }
+extern "C" int nvqa_device_alloc(void** p, int64_t bytes) {
+  NVQA_CHECK(p && bytes >= 0, "bad argument");
+  NVQA_CUDA(cudaMalloc(p, (size_t)(bytes ? bytes : 16)));
+  return 0;
+}
+extern "C" int nvqa_device_free(void* p) { if (p) NVQA_CUDA(cudaFree(p)); return 0; }
+extern "C" int nvqa_memcpy_h2d(nvqa_model* m, void* dst, const void* src, int64_t bytes) {
+  NVQA_CHECK(m && dst && src, "null argument");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, m->stream));
+  NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+extern "C" int nvqa_memcpy_d2h(nvqa_model* m, void* dst, const void* src, int64_t bytes) {
+  NVQA_CHECK(m && dst && src, "null argument");
+  return d2h(m, dst, src, (size_t)bytes);
+}
+
+extern "C" int nvqa_gemm_test(int precision, int a_kmajor, int b_kmajor, int32_t M, int32_t N, int32_t K, const float* A,
+                              const float* B, float* C, void* stream) {
+  NVQA_CHECK(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int lda = a_kmajor ? K : M, ldb = b_kmajor ? K : N;
+  if (precision == NVQA_PREC_FP32_SIMT)
+    return simt_gemm(s, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, N, false, nullptr, nullptr);
+  int planes = precision == NVQA_PREC_BF16X3 ? 3 : precision == NVQA_PREC_BF16X2 ? 2 : 1;
+  UmmaWorkspace* ws = nullptr;
+  NVQA_TRY(umma_workspace_create(&ws, ((size_t)M * K + (size_t)N * K) * 2 * 3 + (8 << 20)));
+  int r = umma_gemm(s, planes, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, N, false, nullptr, nullptr, ws);
+  cudaStreamSynchronize(s);
+  umma_workspace_destroy(ws);
+  return r;
+}

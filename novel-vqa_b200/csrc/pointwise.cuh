@@ -1,0 +1,40 @@
+// Launchers of the bandwidth-bound kernels of the arch1 step (pointwise.cu).
+#pragma once
+#include "common.cuh"
+
+namespace nvqa {
+
+// K2: one-hot Linear + Dropout + Tanh as a gather (002_train_baseline.lua:141-144).  y [T x B x E]
+int embed_fwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* WeT, const float* be, float* y,
+              Drop d, int B, int T, int E, int V);
+// fc7 L2 row norm (002_train_baseline.lua:117-123) fused with AxB's Dropout on i (misc/netdef.lua:11)
+int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm);
+// gate math + cell update of one LSTM layer at time t (misc/LSTM.lua:45-59); pre -> gates in place
+int lstm_gates_fwd(cudaStream_t s, float* pre_t, const float* c_prev, int ldp, float* c_new, float* h_new, int ldn,
+                   float* xdrop_next_t, const int32_t* len, Drop d, int t, int T, int B, int H);
+// final state -> question vector with AxB's Dropout on q  (002_train_baseline.lua:306, misc/netdef.lua:10)
+int qvec_fwd(cudaStream_t s, const float* const* c_fin, const float* const* h_fin, float* state, float* qd,
+             Drop d, int B, int H, int L);
+// qc = tanh(qpre), ic = tanh(ipre) (in place), zd = mz * qc * ic   (misc/netdef.lua:10-12, 002_train_baseline.lua:153)
+int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C);
+// nn.CrossEntropyCriterion fwd+bwd + torch.max argmax (002_train_baseline.lua:308-310, 004_eval_model.lua:233)
+int softmax_ce(cudaStream_t s, const float* scores, const int32_t* labels, float* dscores, float* rowloss,
+               int32_t* argmax, int n, int O, float inv_n);
+int loss_reduce(cudaStream_t s, const float* rowloss, float* loss, int n);
+int fuse_bwd(cudaStream_t s, const float* dzd, const float* qc, const float* ic, float* dqpre, float* dipre,
+             Drop d, int B, int C);
+int mask_inplace(cudaStream_t s, float* x, Drop d, int64_t n);
+// cell backward at time t: writes da_t [B x 4H] and the dc carry
+int lstm_gates_bwd(cudaStream_t s, const float* gates_t, const float* c_prev, const float* c_new,
+                   const float* dh_in, int dh_ld, const float* dh_above_t, const float* dc_in, int dc_ld,
+                   float* da_t, float* dc_out, const int32_t* len, Drop d_above, int t, int T, int B, int H);
+// out0[n] (and out1[n]) = sum_r A[r][n]   (bias gradients)
+int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* out0, float* out1);
+// Tanh/Dropout backward + scatter-add into dWeT [V x E]  (002_train_baseline.lua:320)
+int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* y, float* dx, float* dWeT,
+              Drop d, int B, int T, int E, int V);
+// gradients*scale -> clamp -> optim.rmsprop, one pass (002_train_baseline.lua:329,408; misc/rmsprop_lrscale.lua:26-34)
+int clamp_rmsprop(cudaStream_t s, float* x, float* g, float* m, int64_t n, float lr, float alpha, float eps,
+                  float wd, float clamp, float gscale);
+
+}  // namespace nvqa

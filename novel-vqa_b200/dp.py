@@ -1,0 +1,61 @@
+"""Data-parallel plumbing for the arch1 step (new functionality: the reference is single-GPU,
+SURVEY 2.2).  One process per GPU; the batch is sharded (500 rows per rank, weak scaling); the flat
+fp32 gradient is all-reduced (sum) in three buckets in gradient-readiness order -- multimodal
+(ready after the head backward), encoder (after the LSTM backward), embedding (after the scatter) --
+each issued asynchronously so that NCCL overlaps the next backward phase; 1/n_ranks is folded into
+the clamp+RMSprop kernel (scale -> clamp -> update, i.e. single-process semantics at the global batch).
+
+torch.distributed is plumbing only (rendezvous + ncclAllReduce on the library's device memory).
+"""
+import numpy as np
+
+from . import api
+
+# (phase to run, parameter block whose gradient becomes final in that phase)
+PHASES = ((api.PHASE_HEAD, api.BLOCK_MULTIMODAL), (api.PHASE_LSTM, api.BLOCK_ENCODER),
+          (api.PHASE_EMBED, api.BLOCK_EMBEDDING))
+
+
+class _CudaArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def grad_bucket_views(model, device):
+    """torch views (no copy) of the three gradient blocks of the library's flat gradient vector."""
+    import torch
+    _, g, off = model.device_views()
+    views = {}
+    for blk in (api.BLOCK_ENCODER, api.BLOCK_EMBEDDING, api.BLOCK_MULTIMODAL):
+        n = model.param_count(blk)
+        views[blk] = torch.as_tensor(_CudaArray(g + 4 * off[blk], n), device=f"cuda:{device}")
+    return views
+
+
+def backward_allreduce(model, views, dist, world):
+    """backward in three phases; after each, all-reduce the bucket that just became final.
+    ``dist`` is torch.distributed (or a stand-in with all_reduce(tensor, async_op=True))."""
+    if world == 1:
+        model.backward(api.PHASE_ALL)
+        return
+    works = []
+    for phase, blk in PHASES:
+        model.backward(phase)
+        works.append(dist.all_reduce(views[blk], async_op=True))
+    for w in works:
+        w.wait()
+
+
+def train_step(model, views, dist, world, lr, seed):
+    """JdJ + all-reduce + clamp + RMSprop on an already-set batch."""
+    model.forward(api.MODE_TRAIN, seed)
+    backward_allreduce(model, views, dist, world)
+    model.rmsprop_step(lr, grad_scale=1.0 / world)
+
+
+def average_then_update_reference(grads_per_rank, clamp=10.0):
+    """What the collective + optimizer kernel compute, stated on host arrays (used by the gloo test):
+    sum over ranks, scale 1/n, clamp."""
+    n = len(grads_per_rank)
+    s = np.sum(np.stack(grads_per_rank), axis=0, dtype=np.float32)
+    return np.clip(s * np.float32(1.0 / n), -clamp, clamp)

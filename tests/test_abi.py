@@ -1,0 +1,45 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/nvqa.h declares, and refuses
+to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nvqa.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nvqa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from novel_vqa_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/nvqa.h but not exported by libnvqa.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_error_string(lib):
+    assert lib.nvqa_version() >= 100
+    assert isinstance(lib.nvqa_last_error(), bytes)
+
+
+def test_fails_loudly_without_gpu(lib):
+    from novel_vqa_b200 import Arch1Model, Arch1Config, NvqaError, device_count
+    if device_count() > 0:
+        pytest.skip("a B200 is present")
+    with pytest.raises(NvqaError, match="no CUDA device|not compute capability"):
+        Arch1Model(Arch1Config(V=10, E=4, H=4, L=1, I=4, C=4, O=3, T=2, B=2))
+
+
+def test_bad_arguments_return_errors_not_crashes(lib):
+    assert lib.nvqa_model_create(None, None) != 0
+    assert lib.nvqa_right_align(None, None, 1, 1, None) != 0
+    assert b"bad argument" in lib.nvqa_last_error()
+    assert lib.nvqa_forward(None, 0, 0) != 0

@@ -1,0 +1,238 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle and the
+committed golden vectors.  Tolerances: integer outputs bit-exact; fp32 within 1e-4 relative
+(per-tensor rel-L2 and rel-max); bf16-operand mode within 1e-2."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_close, rel_err
+from oracle import arch1 as A
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "arch1_small.npz")
+FP32_TOL = 1e-4
+BF16_TOL = 1e-2
+
+
+def nv():
+    import novel_vqa_b200 as nv_
+    if nv_.device_count() == 0:
+        pytest.fail("no sm_100 device visible: GPU tests must run on the B200 box (no CPU fallback)")
+    return nv_
+
+
+def ocfg(cfg):
+    return A.Arch1Config(V=cfg.V, E=cfg.E, H=cfg.H, L=cfg.L, I=cfg.I, C=cfg.C, O=cfg.O, T=cfg.T, p=cfg.dropout)
+
+
+def make_model(nvm, cfg, enc, emb, mm, precision):
+    m = nvm.Arch1Model(cfg, precision=precision)
+    m.set_params(nvm.BLOCK_ENCODER, enc)
+    m.set_params(nvm.BLOCK_EMBEDDING, emb)
+    m.set_params(nvm.BLOCK_MULTIMODAL, mm)
+    return m
+
+
+def small_cfg(nvm, g):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden
+    c = make_golden.CFG
+    return nvm.Arch1Config(B=make_golden.B, **c), make_golden
+
+
+PRECISIONS = [("fp32_simt", 0, FP32_TOL), ("bf16x3", 1, FP32_TOL), ("bf16", 2, BF16_TOL)]
+
+
+@pytest.mark.parametrize("name,prec,tol", PRECISIONS)
+@pytest.mark.parametrize("tag", ["eval", "train"])
+def test_small_step_against_golden(name, prec, tol, tag):
+    nvm = nv()
+    g = np.load(GOLD)
+    cfg, mg = small_cfg(nvm, g)
+    m = make_model(nvm, cfg, g["enc"], g["emb"], g["mm"], prec)
+    # parameter round trip through the Torch flat layout (embedding is transposed on the device)
+    assert np.array_equal(m.get_params(nvm.BLOCK_EMBEDDING), g["emb"])
+    assert np.array_equal(m.get_params(nvm.BLOCK_ENCODER), g["enc"])
+    m.set_batch_host(g["q_ra"], g["lengths"], g["fc7"], g["labels"])
+    if tag == "eval":
+        m.forward(nvm.MODE_EVAL, 0)
+    else:
+        m.forward(nvm.MODE_TRAIN, mg.SEED_DROP)
+    B = g["q_ra"].shape[0]
+    for ref in ("f32", "f64"):
+        assert_close(m.scores(B), g[f"{tag}_{ref}_scores"], tol, f"{name} scores vs {ref}")
+        assert_close(m.state(B), g[f"{tag}_{ref}_state"], tol, f"{name} state vs {ref}")
+        assert abs(m.loss() - float(g[f"{tag}_{ref}_loss"])) <= tol * abs(float(g[f"{tag}_{ref}_loss"]))
+    if tag == "eval" and tol == FP32_TOL:
+        assert np.array_equal(m.argmax(B), g["eval_f32_argmax"])          # bit-exact answers
+    m.backward()
+    for blk, key in ((nvm.BLOCK_ENCODER, "genc"), (nvm.BLOCK_EMBEDDING, "gemb"), (nvm.BLOCK_MULTIMODAL, "gmm")):
+        got = np.clip(m.get_grads(blk), -10, 10)
+        assert_close(got, g[f"{tag}_f32_{key}"], tol, f"{name} {tag} {key} vs f32")
+        assert_close(got, g[f"{tag}_f64_{key}"], tol, f"{name} {tag} {key} vs f64")
+    m.close()
+
+
+@pytest.mark.parametrize("name,prec,tol", PRECISIONS[:2])
+def test_training_trajectory_against_golden(name, prec, tol):
+    """three iterations of optim.rmsprop(JdJ, ...) + lr decay (002_train_baseline.lua:408-410)"""
+    nvm = nv()
+    g = np.load(GOLD)
+    cfg, mg = small_cfg(nvm, g)
+    m = make_model(nvm, cfg, g["enc"], g["emb"], g["mm"], prec)
+    lr = 3e-4
+    q, ln, fc7, lab = (np.ascontiguousarray(g[k]) for k in ("q_ra", "lengths", "fc7", "labels"))
+    for it in range(3):
+        f = m.train_step_host(q, ln, fc7, lab, lr, mg.SEED_DROP + it)
+        assert abs(f - g["traj_losses"][it]) <= tol * abs(g["traj_losses"][it])
+        lr *= nvm.DECAY_FACTOR
+    # RMSprop's first steps move every weight by ~lr: compare the *updates*, not the weights
+    for blk, k0, k1 in ((nvm.BLOCK_ENCODER, "enc", "traj_enc"), (nvm.BLOCK_EMBEDDING, "emb", "traj_emb"),
+                        (nvm.BLOCK_MULTIMODAL, "mm", "traj_mm")):
+        assert_close(m.get_params(blk), g[k1], 1e-5, f"{name} weights {k0}")
+        upd_ref = g[k1].astype(np.float64) - g[k0]
+        upd = m.get_params(blk).astype(np.float64) - g[k0]
+        e2, _ = rel_err(upd, upd_ref)
+        assert e2 <= 5e-3, f"{name} update {k0}: rel-l2 {e2:.3e}"
+    m.close()
+
+
+def test_explicit_masks_match_oracle():
+    nvm = nv()
+    g = np.load(GOLD)
+    cfg, mg = small_cfg(nvm, g)
+    oc = ocfg(cfg)
+    B, T = g["q_ra"].shape
+    r = np.random.default_rng(11)
+    bern = lambda *s: (r.integers(0, 2, s) * 2).astype(np.float32)
+    padded = dict(emb=bern(T, B, cfg.E), lstm=bern(cfg.L - 1, T, B, cfg.H), q=bern(B, cfg.S), i=bern(B, cfg.I),
+                  z=bern(B, cfg.C))
+    words, sizes, sidx, inv = A.sort_encoding_right_align(g["q_ra"], g["lengths"])
+    pm = A.pack_masks(oc, padded, B, sizes, sidx)
+    f, grads, scores, _ = A.jdj(oc, g["enc"], g["emb"], g["mm"], g["q_ra"], g["lengths"],
+                                A.l2_normalize_rows(g["fc7"]), g["labels"], masks=pm)
+    m = make_model(nvm, cfg, g["enc"], g["emb"], g["mm"], 0)
+    m.set_batch_host(g["q_ra"], g["lengths"], g["fc7"], g["labels"])
+    m.set_masks(**padded)
+    m.forward(nvm.MODE_TRAIN, 0)
+    assert_close(m.scores(B), scores, FP32_TOL, "scores")
+    m.backward()
+    for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
+        assert_close(np.clip(m.get_grads(blk), -10, 10), gw, FP32_TOL, f"grads {blk}")
+    m.close()
+
+
+@pytest.mark.parametrize("name,prec,tol", PRECISIONS)
+def test_medium_ragged_batch_live_oracle(name, prec, tol):
+    """Ragged lengths (1..T), one empty-ish edge (length 1), odd sizes that do not fill GEMM tiles."""
+    nvm = nv()
+    cfg = nvm.Arch1Config(V=300, E=20, H=64, L=2, I=72, C=48, O=37, T=9, B=45)
+    oc = ocfg(cfg)
+    enc, emb, mm = nvm.synth_params(cfg, seed=5)
+    enc, emb, mm = enc * 3, emb * 3, mm * 3
+    q, ln, fc7, lab = nvm.synth_batch(cfg, 45, seed=6, min_len=1)
+    ln[0], ln[1] = 1, cfg.T
+    q[0, :cfg.T - 1] = 0
+    m = make_model(nvm, cfg, enc, emb, mm, prec)
+    m.set_batch_host(q, ln, fc7, lab)
+    for mode, seed in ((nvm.MODE_EVAL, None), (nvm.MODE_TRAIN, 99)):
+        f, grads, scores, ctx = A.jdj(oc, enc, emb, mm, q, ln, A.l2_normalize_rows(fc7), lab, seed=seed)
+        m.forward(mode, seed or 0)
+        assert_close(m.scores(45), scores, tol, f"{name} scores")
+        assert_close(m.state(45), ctx["tv_q"], tol, f"{name} state")
+        assert abs(m.loss() - f) <= tol * abs(f)
+        m.backward()
+        for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
+            assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, f"{name} grads {blk}")
+    m.close()
+
+
+@pytest.mark.parametrize("prec", [0, 1, 2])
+@pytest.mark.parametrize("ak,bk", [(1, 1), (1, 0), (0, 0), (0, 1)])
+def test_gemm_engines(prec, ak, bk):
+    """The GEMM engines behind nn.Linear fwd (K-major x K-major), dgrad (x MN-major) and wgrad (both
+    MN-major), on sizes that exercise partial tiles and K tails."""
+    nvm = nv()
+    lib = nvm._lib.load()
+    m = nvm.Arch1Model(nvm.Arch1Config(V=8, E=4, H=4, L=1, I=4, C=4, O=3, T=2, B=2))
+    r = np.random.default_rng(7)
+    for (M, N, K) in ((500, 2048, 512), (130, 72, 200), (2048, 200, 1300), (37, 1000, 1024)):
+        a = r.standard_normal((M, K)).astype(np.float32)
+        b = r.standard_normal((N, K)).astype(np.float32)
+        ref = a.astype(np.float64) @ b.astype(np.float64).T
+        A_ = nvm.DeviceBuffer(m, a if ak else a.T.copy())
+        B_ = nvm.DeviceBuffer(m, b if bk else b.T.copy())
+        C_ = nvm.DeviceBuffer(m, np.zeros((M, N), np.float32))
+        nvm._lib.check(lib.nvqa_gemm_test(prec, ak, bk, M, N, K, A_.ptr, B_.ptr, C_.ptr, None))
+        e2, em = rel_err(C_.get(), ref)
+        tol = 2e-6 if prec in (0, 1) else 6e-3
+        assert e2 <= tol, f"prec {prec} {ak}{bk} {M}x{N}x{K}: rel-l2 {e2:.3e}"
+    m.close()
+
+
+def test_module_level_cell_and_criterion():
+    """LSTM.lstm_conventional():forward and nn.CrossEntropyCriterion through their C-ABI entry points."""
+    nvm = nv()
+    cfg = nvm.Arch1Config(V=30, E=12, H=16, L=2, I=8, C=8, O=21, T=3, B=10)
+    oc = ocfg(cfg)
+    enc, emb, mm = nvm.synth_params(cfg, seed=8)
+    m = make_model(nvm, cfg, enc * 4, emb, mm, 0)
+    r = np.random.default_rng(9)
+    n = 10
+    state = r.standard_normal((n, cfg.S)).astype(np.float32)
+    x = r.standard_normal((n, cfg.E)).astype(np.float32)
+    masks = (r.integers(0, 2, (cfg.L - 1, n, cfg.H)) * 2).astype(np.float32)
+    lib = nvm._lib.load()
+    for mk in (None, masks):
+        ref, _ = A.lstm_cell_forward(oc, A.split_flat(enc * 4, oc.enc_layout()), state, x,
+                                     None if mk is None else [mk[l] for l in range(cfg.L - 1)])
+        S_, X_, O_ = nvm.DeviceBuffer(m, state), nvm.DeviceBuffer(m, x), nvm.DeviceBuffer(m, np.zeros_like(state))
+        M_ = None if mk is None else nvm.DeviceBuffer(m, mk)
+        nvm._lib.check(lib.nvqa_lstm_cell_forward(m.handle, S_.ptr, X_.ptr, None if mk is None else M_.ptr, n, O_.ptr))
+        assert_close(O_.get(), ref, FP32_TOL, "cell forward")
+    scores = r.standard_normal((n, cfg.O)).astype(np.float32) * 3
+    labels = r.integers(1, cfg.O + 1, n).astype(np.int32)
+    f, d = A.cross_entropy(scores, labels)
+    import ctypes as C
+    S_, L_, D_ = nvm.DeviceBuffer(m, scores), nvm.DeviceBuffer(m, labels), nvm.DeviceBuffer(m, np.zeros_like(scores))
+    out = C.c_float(0)
+    nvm._lib.check(lib.nvqa_cross_entropy(m.handle, S_.ptr, L_.ptr, n, C.byref(out), D_.ptr))
+    assert abs(out.value - f) <= 1e-5 * abs(f)
+    assert_close(D_.get(), d, 1e-5, "dscores")
+    m.close()
+
+
+def test_full_size_config1_step():
+    """BASELINE config 1 (B=500, T=26, V=14773, E=200, H=512, L=2, I=4096, C=1024, O=1000): one evaluate-mode
+    JdJ against the fp32 oracle, plus size-independent properties."""
+    nvm = nv()
+    cfg = nvm.Arch1Config()
+    oc = ocfg(cfg)
+    enc, emb, mm = nvm.synth_params(cfg, seed=123)
+    q, ln, fc7, lab = nvm.synth_batch(cfg, 500, seed=123)
+    f, grads, scores, ctx = A.jdj(oc, enc, emb, mm, q, ln, A.l2_normalize_rows(fc7), lab, seed=None)
+    margin = np.sort(scores, axis=1)
+    margin = margin[:, -1] - margin[:, -2]
+    for prec, tol in ((0, FP32_TOL), (1, FP32_TOL)):
+        m = make_model(nvm, cfg, enc, emb, mm, prec)
+        m.set_batch_host(q, ln, fc7, lab)
+        m.forward(nvm.MODE_EVAL, 0)
+        assert_close(m.scores(500), scores, tol, f"prec {prec} scores")
+        assert abs(m.loss() - f) <= tol * abs(f)
+        assert abs(m.loss() - np.log(1000.0)) < 0.05                  # random init: loss ~ ln(O)
+        am = m.argmax(500)
+        safe = margin > 1e-5 * np.abs(scores).max()                   # ties below fp32 noise are not pinned
+        assert np.array_equal(am[safe], A.argmax_first(scores)[safe])
+        assert safe.mean() > 0.99
+        m.backward()
+        for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
+            assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, f"prec {prec} grads {blk}")
+        # determinism of the forward: same inputs -> bit-identical scores
+        s1 = m.scores(500)
+        m.forward(nvm.MODE_EVAL, 0)
+        assert np.array_equal(s1, m.scores(500))
+        # eval_step_host == forward + argmax
+        assert np.array_equal(m.eval_step_host(q, ln, fc7), am)
+        m.close()
