@@ -117,15 +117,17 @@ static int gemm(nvqa_model* m, int cat, bool ak, bool bk, int M, int N, int K, c
 
 static int gemm_raw(nvqa_model* m, bool ak, bool bk, int M, int N, int K, const float* A, int lda, const float* B,
                     int ldb, float* C, int ldc, bool beta, const float* b0, const float* b1) {
+  // weights (anything inside the flat parameter vector) keep their bf16 planes cached for the whole step
+  const bool as = A >= m->params && A < m->params + m->P, bs = B >= m->params && B < m->params + m->P;
   switch (m->cfg.precision) {
     case NVQA_PREC_FP32_SIMT:
       return simt_gemm(m->stream, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1);
     case NVQA_PREC_BF16X3:
-      return umma_gemm(m->stream, 3, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws);
+      return umma_gemm(m->stream, 3, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws, as, bs);
     case NVQA_PREC_BF16X2:
-      return umma_gemm(m->stream, 2, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws);
+      return umma_gemm(m->stream, 2, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws, as, bs);
     case NVQA_PREC_BF16:
-      return umma_gemm(m->stream, 1, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws);
+      return umma_gemm(m->stream, 1, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1, m->ws, as, bs);
   }
   set_error("unknown precision");
   return 1;
@@ -266,9 +268,11 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->loss_host), 64));
   NVQA_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->ans_host), (size_t)B * 4));
   if (cfg->precision != NVQA_PREC_FP32_SIMT) {
-    // operand planes of the largest GEMM: A = da [N x 4H], B = x [N x H]  (3 bf16 planes each)
-    size_t elems = (size_t)N * 4 * H + (size_t)N * (H > E ? H : E) + (size_t)C * I + (1 << 20);
-    NVQA_TRY(umma_workspace_create(&m->ws, elems * 3 * 2 + (8 << 20)));
+    // transient operand planes of the largest GEMM (wgrad: da^T [4H x TB] and x^T [H x TB], 3 bf16 planes each);
+    // static region: every weight matrix in both orientations
+    size_t elems = (size_t)(N + 64) * 4 * H + (size_t)(N + 64) * (H > E ? H : E) + (size_t)(B + 64) * (I + S + 2 * C);
+    size_t stat = (size_t)(m->n_blk[0] + m->n_blk[2]) * 2 * 6 + (16 << 20);
+    NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (16 << 20), stat));
   }
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
   return 0;
@@ -342,6 +346,7 @@ static int block_copy(nvqa_model* m, float* dev_base, int block, float* host, bo
 }
 
 extern "C" int nvqa_params_set(nvqa_model* m, int block, const float* src) {
+  if (m) umma_workspace_invalidate(m->ws);
   return block_copy(m, m ? m->params : nullptr, block, const_cast<float*>(src), true);
 }
 extern "C" int nvqa_params_get(nvqa_model* m, int block, float* dst) { return block_copy(m, m ? m->params : nullptr, block, dst, false); }
@@ -526,6 +531,7 @@ extern "C" int nvqa_backward(nvqa_model* m, int phase) {
 extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps, float wd, float clamp, float gscale) {
   NVQA_CHECK(m, "null model");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  umma_workspace_invalidate(m->ws);     // the weights change: their cached bf16 planes are stale
   return clamp_rmsprop(m->stream, m->params, m->grads, m->rms, m->P, lr, alpha, eps, wd, clamp, gscale);
 }
 
@@ -678,12 +684,15 @@ extern "C" int nvqa_gemm_test(int precision, int a_kmajor, int b_kmajor, int32_t
   NVQA_CHECK(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int lda = a_kmajor ? K : M, ldb = b_kmajor ? K : N;
-  if (precision == NVQA_PREC_FP32_SIMT)
-    return simt_gemm(s, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, N, false, nullptr, nullptr);
+  if (precision == NVQA_PREC_FP32_SIMT) {
+    NVQA_TRY(simt_gemm(s, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, N, false, nullptr, nullptr));
+    NVQA_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
   int planes = precision == NVQA_PREC_BF16X3 ? 3 : precision == NVQA_PREC_BF16X2 ? 2 : 1;
   UmmaWorkspace* ws = nullptr;
-  NVQA_TRY(umma_workspace_create(&ws, ((size_t)M * K + (size_t)N * K) * 2 * 3 + (8 << 20)));
-  int r = umma_gemm(s, planes, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, N, false, nullptr, nullptr, ws);
+  NVQA_TRY(umma_workspace_create(&ws, ((size_t)(M + 64) * (K + 64) + (size_t)(N + 64) * (K + 64)) * 2 * 3 + (8 << 20), 0));
+  int r = umma_gemm(s, planes, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, N, false, nullptr, nullptr, ws, false, false);
   cudaStreamSynchronize(s);
   umma_workspace_destroy(ws);
   return r;

@@ -1,9 +1,535 @@
-// placeholder until the tcgen05 engine lands
+// tcgen05 / TMEM / TMA GEMM engine for sm_100a (hand-written PTX, no CUTLASS, no cuBLAS).
+//
+//   C[M x N] (fp32) = (beta ? C : 0) + A . B^T + bias0 + bias1        A: [M x K], B: [N x K]
+//
+// Operands are bf16 "planes": an fp32 value x is split as x = p0 + p1 + p2 (+ O(2^-24 |x|)) with
+// p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1).  With P planes per operand the kernel issues
+//   P = 1:  (0,0)                                   -> plain bf16-operand GEMM (1e-2 mode)
+//   P = 2:  (0,0) (0,1) (1,0)                       -> ~2^-16 relative per product
+//   P = 3:  (0,0) (0,1) (1,0) (1,1) (0,2) (2,0)     -> fp32-equivalent (dropped terms <= 2^-25)
+// tcgen05.mma kind::f16 instructions per K step, all accumulating in fp32 in the same TMEM tile.
+// This is the "fp32 parity on tensor cores" mode of the arch1 step: the reference's nn.Linear GEMMs
+// (misc/LSTM.lua:41-42, misc/netdef.lua:10-11, 002_train_baseline.lua:154) are fp32 SGEMMs.
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer   - cp.async.bulk.tensor.3d (SWIZZLE_128B boxes of 64 bf16 x rows x 1 plane)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
+//   warps 2-5: epilogue       - tcgen05.ld (32 lanes x 32 columns per warp), bias / beta, fp32 stores
+// smem: STAGES x { P A-planes [128 x 64] , P B-planes [BN x 64] } ring with full/empty mbarriers.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <unordered_map>
+#include <vector>
+
 #include "common.cuh"
+
 namespace nvqa {
-struct UmmaWorkspace { int dummy; };
-int umma_gemm(cudaStream_t, int, bool, bool, int, int, int, const float*, int, const float*, int, float*, int, bool,
-              const float*, const float*, UmmaWorkspace*) { set_error("tcgen05 GEMM engine not built"); return 1; }
-int umma_workspace_create(UmmaWorkspace** ws, size_t) { *ws = new UmmaWorkspace(); return 0; }
-void umma_workspace_destroy(UmmaWorkspace* ws) { delete ws; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// spin on try_wait with a watchdog: a broken pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("umma_gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, issued by ONE thread on behalf of the CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane_base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand tile [rows x 64 bf16] written by TMA with SWIZZLE_128B:
+// 8-row groups of 1024 B (SBO), 128 B rows; LBO unused for swizzled K-major; version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (ignored)  [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset        [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version        [46,48)
+  d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B      [61,64)
+  return d;
+}
+// Instruction descriptor, kind::f16: D = F32, A = B = BF16, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int UG_BM = 128;
+constexpr int UG_BK = 64;                  // bf16 elements per 128-byte swizzle row
+constexpr int UG_THREADS = 192;
+
+template <int BN, int P>
+struct UgCfg {
+  static constexpr int A_PLANE = UG_BM * UG_BK * 2;           // 16 KB
+  static constexpr int B_PLANE = BN * UG_BK * 2;
+  static constexpr int STAGE = P * (A_PLANE + B_PLANE);
+  static constexpr int MAX_STAGES = (227 * 1024 - 2048) / STAGE;
+  static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static_assert(STAGES >= 2, "pipeline needs two stages");
+};
+
+template <int BN, int P>
+__global__ void __launch_bounds__(UG_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N,
+                 int K, float* __restrict__ C, int ldc, int beta, const float* __restrict__ bias0,
+                 const float* __restrict__ bias1) {
+  using Cfg = UgCfg<BN, P>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* gen = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + Cfg::STAGES * Cfg::STAGE);
+  const uint32_t full0 = base + Cfg::STAGES * Cfg::STAGE;            // full[s]  at full0 + 8 s
+  const uint32_t empty0 = full0 + 8 * Cfg::STAGES;                   // empty[s]
+  const uint32_t tfull = empty0 + 8 * Cfg::STAGES;                   // accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * UG_BM, n0 = blockIdx.x * BN;
+  const int nkb = (K + UG_BK - 1) / UG_BK;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      mbar_init(tfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        mbar_expect_tx(full0 + 8 * s, Cfg::STAGE);
+        const uint32_t sa = base + s * Cfg::STAGE;
+        const uint32_t sb = sa + P * Cfg::A_PLANE;
+#pragma unroll
+        for (int p = 0; p < P; ++p) tma_load_3d(sa + p * Cfg::A_PLANE, &mapA, full0 + 8 * s, kb * UG_BK, m0, p);
+#pragma unroll
+        for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::B_PLANE, &mapB, full0 + 8 * s, kb * UG_BK, n0, p);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN);
+      uint32_t acc = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * Cfg::STAGE;
+        const uint32_t sb = sa + P * Cfg::A_PLANE;
+#pragma unroll
+        for (int k = 0; k < UG_BK / 16; ++k) {
+          // K advance inside the 128 B swizzle atom: +32 bytes per UMMA_K = 16 bf16
+          uint64_t da[P], db[P];
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            da[p] = make_kmajor_sw128_desc(sa + p * Cfg::A_PLANE + k * 32);
+            db[p] = make_kmajor_sw128_desc(sb + p * Cfg::B_PLANE + k * 32);
+          }
+          // smallest terms first
+          if (P == 3) {
+            umma_f16(tmem_base, da[0], db[2], idesc, acc); acc = 1;
+            umma_f16(tmem_base, da[2], db[0], idesc, acc);
+            umma_f16(tmem_base, da[1], db[1], idesc, acc);
+          }
+          if (P >= 2) {
+            umma_f16(tmem_base, da[0], db[1], idesc, acc); acc = 1;
+            umma_f16(tmem_base, da[1], db[0], idesc, acc);
+          }
+          umma_f16(tmem_base, da[0], db[0], idesc, acc); acc = 1;
+        }
+        umma_commit(empty0 + 8 * s);          // smem slot free once these MMAs have read it
+      }
+      umma_commit(tfull);                     // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+      if (row < M) {
+        float* crow = C + (size_t)row * ldc;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = n0 + cc * 32 + j;
+          if (col >= N) break;
+          float r[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (col + t < N) {
+              if (bias0) r[t] += __ldg(bias0 + col + t);
+              if (bias1) r[t] += __ldg(bias1 + col + t);
+            }
+          }
+          if (vec && col + 3 < N) {
+            if (beta) {
+              float4 o = *reinterpret_cast<const float4*>(crow + col);
+              r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w;
+            }
+            *reinterpret_cast<float4*>(crow + col) = make_float4(r[0], r[1], r[2], r[3]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (col + t < N) crow[col + t] = (beta ? crow[col + t] : 0.f) + r[t];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation: fp32 -> P bf16 planes, K-major [P][rows][Kp]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
+  p0 = __float2bfloat16_rn(x);
+  float r1 = x - __bfloat162float(p0);
+  p1 = __float2bfloat16_rn(r1);
+  float r2 = r1 - __bfloat162float(p1);
+  p2 = __float2bfloat16_rn(r2);
+}
+
+// source is K-major: src[row * ld + k]
+template <int P>
+__global__ void __launch_bounds__(256)
+split_kmajor_kernel(const float* __restrict__ src, int rows, int K, int ld, int Kp, __nv_bfloat16* __restrict__ dst) {
+  const int K4 = Kp >> 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * K4) return;
+  const int k = (int)(i % K4) * 4;
+  const int64_t row = i / K4;
+  const float* s = src + row * ld + k;
+  float x[4];
+  if (k + 3 < K && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+    float4 t = *reinterpret_cast<const float4*>(s);
+    x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = (k + j < K) ? s[j] : 0.f;
+  }
+  __nv_bfloat16 p[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split3(x[j], p[0][j], p[1][j], p[2][j]);
+  const int64_t plane = (int64_t)rows * Kp;
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    uint2 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(p[q][0]) | ((uint32_t)__bfloat16_as_ushort(p[q][1]) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(p[q][2]) | ((uint32_t)__bfloat16_as_ushort(p[q][3]) << 16);
+    *reinterpret_cast<uint2*>(dst + q * plane + row * Kp + k) = o;
+  }
+}
+
+// source is MN-major: src[k * ld + row]; transposed through shared memory so that both the fp32 reads
+// and the bf16 writes are coalesced.  Tile: 64 k x 32 rows, 256 threads.
+template <int P>
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ src, int rows, int K, int ld, int Kp, __nv_bfloat16* __restrict__ dst) {
+  __shared__ float tile[64][33];
+  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int k = k0 + ty + 8 * j, r = r0 + tx;
+    tile[ty + 8 * j][tx] = (k < K && r < rows) ? src[(int64_t)k * ld + r] : 0.f;
+  }
+  __syncthreads();
+  const int64_t plane = (int64_t)rows * Kp;
+  // each thread writes two consecutive k (one 32-bit store per plane): 32 threads cover 64 k of one row
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int r = r0 + ty + 8 * j, k = k0 + 2 * tx;
+    if (r < rows && k < Kp) {
+      __nv_bfloat16 a[3], b[3];
+      split3(tile[2 * tx][ty + 8 * j], a[0], a[1], a[2]);
+      split3(tile[2 * tx + 1][ty + 8 * j], b[0], b[1], b[2]);
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        uint32_t o = (uint32_t)__bfloat16_as_ushort(a[q]) | ((uint32_t)__bfloat16_as_ushort(b[q]) << 16);
+        *reinterpret_cast<uint32_t*>(dst + q * plane + (int64_t)r * Kp + k) = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct PlaneKey {
+  const void* src; int rows, K, ld, kmajor, P;
+  bool operator==(const PlaneKey& o) const {
+    return src == o.src && rows == o.rows && K == o.K && ld == o.ld && kmajor == o.kmajor && P == o.P;
+  }
+};
+struct PlaneKeyHash {
+  size_t operator()(const PlaneKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.src);
+    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.K; h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)(k.kmajor * 8 + k.P);
+    return h;
+  }
+};
+struct MapKey {
+  const void* planes; int rows, Kp, P, box;
+  bool operator==(const MapKey& o) const { return planes == o.planes && rows == o.rows && Kp == o.Kp && P == o.P && box == o.box; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.planes);
+    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.Kp; h = h * 1000003u ^ (size_t)(k.P * 1024 + k.box);
+    return h;
+  }
+};
+
+struct UmmaWorkspace {
+  uint8_t* base = nullptr;
+  size_t bytes = 0;
+  size_t static_bytes = 0;      // [0, static_bytes): cached planes of static operands (weights)
+  size_t static_top = 0;
+  size_t trans_top = 0;         // transient planes live in [static_bytes, bytes), reset per GEMM
+  std::unordered_map<PlaneKey, __nv_bfloat16*, PlaneKeyHash> cache;
+  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
+};
+
+int umma_workspace_create(UmmaWorkspace** out, size_t transient_bytes, size_t static_bytes) {
+  UmmaWorkspace* ws = new UmmaWorkspace();
+  ws->static_bytes = (static_bytes + 1023) & ~(size_t)1023;
+  ws->bytes = ws->static_bytes + transient_bytes;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws->base), ws->bytes);
+  if (e != cudaSuccess) {
+    set_error(std::string("umma workspace cudaMalloc: ") + cudaGetErrorString(e));
+    delete ws;
+    return 1;
+  }
+  *out = ws;
+  return 0;
+}
+void umma_workspace_destroy(UmmaWorkspace* ws) {
+  if (!ws) return;
+  cudaFree(ws->base);
+  delete ws;
+}
+// the static operands (weights) changed: drop their cached planes
+void umma_workspace_invalidate(UmmaWorkspace* ws) {
+  if (!ws) return;
+  ws->cache.clear();
+  ws->static_top = 0;
+}
+
+static int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, bool kmajor, int rows, int K,
+                          int ld, bool is_static, __nv_bfloat16** out, int* Kp_out) {
+  const int Kp = (K + 7) & ~7;
+  *Kp_out = Kp;
+  PlaneKey key{src, rows, K, ld, kmajor ? 1 : 0, P};
+  if (is_static) {
+    auto it = ws->cache.find(key);
+    if (it != ws->cache.end()) { *out = it->second; return 0; }
+  }
+  const size_t need = ((size_t)P * rows * Kp * 2 + 1023) & ~(size_t)1023;
+  __nv_bfloat16* dst;
+  if (is_static && ws->static_top + need <= ws->static_bytes) {
+    dst = reinterpret_cast<__nv_bfloat16*>(ws->base + ws->static_top);
+    ws->static_top += need;
+    ws->cache[key] = dst;
+  } else {
+    NVQA_CHECK(ws->static_bytes + ws->trans_top + need <= ws->bytes, "umma workspace too small");
+    dst = reinterpret_cast<__nv_bfloat16*>(ws->base + ws->static_bytes + ws->trans_top);
+    ws->trans_top += need;
+  }
+  if (kmajor) {
+    int64_t n = (int64_t)rows * (Kp / 4);
+    if (P == 1) split_kmajor_kernel<1><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+    else if (P == 2) split_kmajor_kernel<2><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+    else split_kmajor_kernel<3><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+  } else {
+    dim3 grid(ceil_div(rows, 32), ceil_div(Kp, 64));
+    if (P == 1) split_transpose_kernel<1><<<grid, 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+    else if (P == 2) split_transpose_kernel<2><<<grid, 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+    else split_transpose_kernel<3><<<grid, 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+  }
+  NVQA_LAUNCHED();
+  *out = dst;
+  return 0;
+}
+
+static int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, int P, int box_rows, CUtensorMap* out) {
+  MapKey key{planes, rows, Kp, P, box_rows};
+  auto it = ws->maps.find(key);
+  if (it != ws->maps.end()) { *out = it->second; return 0; }
+  EncodeTiledFn enc = get_encode();
+  NVQA_CHECK(enc, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)P};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
+  cuuint32_t box[3] = {(cuuint32_t)UG_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(planes), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return 1;
+  }
+  if (ws->maps.size() > 4096) ws->maps.clear();
+  ws->maps[key] = m;
+  *out = m;
+  return 0;
+}
+
+template <int BN, int P>
+static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int Kp, float* C,
+                       int ldc, bool beta, const float* b0, const float* b1) {
+  using Cfg = UgCfg<BN, P>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NVQA_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, UG_BM));
+  umma_gemm_kernel<BN, P><<<grid, UG_THREADS, Cfg::SMEM, s>>>(ma, mb, M, N, Kp, C, ldc, beta ? 1 : 0, b0, b1);
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+int umma_gemm(cudaStream_t s, int planes, bool a_kmajor, bool b_kmajor, int M, int N, int K, const float* A, int lda,
+              const float* B, int ldb, float* C, int ldc, bool beta, const float* bias0, const float* bias1,
+              UmmaWorkspace* ws, bool a_static, bool b_static) {
+  NVQA_CHECK(ws, "umma_gemm: no workspace");
+  NVQA_CHECK(planes >= 1 && planes <= 3, "umma_gemm: planes must be 1..3");
+  if (M <= 0 || N <= 0) return 0;
+  ws->trans_top = 0;                      // stream order makes the previous GEMM's transient planes reusable
+  __nv_bfloat16 *pa = nullptr, *pb = nullptr;
+  int Kpa = 0, Kpb = 0;
+  NVQA_TRY(prepare_planes(ws, s, planes, A, a_kmajor, M, K, lda, a_static, &pa, &Kpa));
+  NVQA_TRY(prepare_planes(ws, s, planes, B, b_kmajor, N, K, ldb, b_static, &pb, &Kpb));
+  // 128 x 128 tiles when they fill the machine, else 128 x 64 for more CTAs
+  const long tiles128 = (long)ceil_div(M, UG_BM) * ceil_div(N, 128);
+  const int BN = tiles128 >= 148 ? 128 : 64;
+  CUtensorMap ma, mb;
+  NVQA_TRY(get_map(ws, pa, M, Kpa, planes, UG_BM, &ma));
+  NVQA_TRY(get_map(ws, pb, N, Kpb, planes, BN, &mb));
+#define NVQA_UG(BN_, P_) return launch_umma<BN_, P_>(s, ma, mb, M, N, Kpa, C, ldc, beta, bias0, bias1)
+  if (BN == 128) {
+    if (planes == 1) NVQA_UG(128, 1);
+    if (planes == 2) NVQA_UG(128, 2);
+    NVQA_UG(128, 3);
+  } else {
+    if (planes == 1) NVQA_UG(64, 1);
+    if (planes == 2) NVQA_UG(64, 2);
+    NVQA_UG(64, 3);
+  }
+#undef NVQA_UG
+}
+
+}  // namespace nvqa
