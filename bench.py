@@ -26,7 +26,7 @@ METRIC = "arch1_train_samples_per_s"
 UNIT = "samples/s"
 FLOPS_PER_SAMPLE = 590.1e6     # SURVEY 8(d) / BASELINE.md section 3: algorithmic FLOPs of one training sample
 PREC_NAMES = {"fp32_simt": 0, "bf16x3": 1, "bf16": 2, "bf16x2": 3}
-DEFAULT_PRECISION = "bf16x3"
+DEFAULT_PRECISION = "bf16x2"
 
 
 def peaks():

@@ -113,9 +113,21 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B      [61,64)
   return d;
 }
-// Instruction descriptor, kind::f16: D = F32, A = B = BF16, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand tile: [64 k-rows x 64 mn] boxes (128 B rows, SWIZZLE_128B), one box per 64-wide MN chunk:
+// LBO = byte stride between MN chunks (one 8 KB box), SBO = stride between 8-row k groups (1024 B).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D = F32, A = B = BF16, M x N tile; bit 15 / 16 = A / B is MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -137,7 +149,7 @@ struct UgCfg {
   static_assert(STAGES >= 2, "pipeline needs two stages");
 };
 
-template <int BN, int P>
+template <int BN, int P, bool AMN, bool BMN>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N,
                  int K, float* __restrict__ C, int ldc, int beta, const float* __restrict__ bias0,
@@ -186,15 +198,31 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const uint32_t sa = base + s * Cfg::STAGE;
         const uint32_t sb = sa + P * Cfg::A_PLANE;
 #pragma unroll
-        for (int p = 0; p < P; ++p) tma_load_3d(sa + p * Cfg::A_PLANE, &mapA, full0 + 8 * s, kb * UG_BK, m0, p);
+        for (int p = 0; p < P; ++p) {
+          if (!AMN) {
+            tma_load_3d(sa + p * Cfg::A_PLANE, &mapA, full0 + 8 * s, kb * UG_BK, m0, p);
+          } else {
 #pragma unroll
-        for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::B_PLANE, &mapB, full0 + 8 * s, kb * UG_BK, n0, p);
+            for (int c = 0; c < UG_BM / 64; ++c)
+              tma_load_3d(sa + p * Cfg::A_PLANE + c * 8192, &mapA, full0 + 8 * s, m0 + 64 * c, kb * UG_BK, p);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          if (!BMN) {
+            tma_load_3d(sb + p * Cfg::B_PLANE, &mapB, full0 + 8 * s, kb * UG_BK, n0, p);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_3d(sb + p * Cfg::B_PLANE + c * 8192, &mapB, full0 + 8 * s, n0 + 64 * c, kb * UG_BK, p);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN, AMN, BMN);
       uint32_t acc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % Cfg::STAGES;
@@ -205,12 +233,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const uint32_t sb = sa + P * Cfg::A_PLANE;
 #pragma unroll
         for (int k = 0; k < UG_BK / 16; ++k) {
-          // K advance inside the 128 B swizzle atom: +32 bytes per UMMA_K = 16 bf16
+          // K advance per UMMA_K = 16 bf16: +32 bytes inside the 128 B swizzle row (K-major), or 16 k-rows of
+          // 128 B = +2048 bytes (MN-major)
           uint64_t da[P], db[P];
 #pragma unroll
           for (int p = 0; p < P; ++p) {
-            da[p] = make_kmajor_sw128_desc(sa + p * Cfg::A_PLANE + k * 32);
-            db[p] = make_kmajor_sw128_desc(sb + p * Cfg::B_PLANE + k * 32);
+            da[p] = AMN ? make_mnmajor_sw128_desc(sa + p * Cfg::A_PLANE + k * 2048)
+                        : make_kmajor_sw128_desc(sa + p * Cfg::A_PLANE + k * 32);
+            db[p] = BMN ? make_mnmajor_sw128_desc(sb + p * Cfg::B_PLANE + k * 2048)
+                        : make_kmajor_sw128_desc(sb + p * Cfg::B_PLANE + k * 32);
           }
           // smallest terms first
           if (P == 3) {
@@ -427,11 +458,14 @@ void umma_workspace_invalidate(UmmaWorkspace* ws) {
   ws->static_top = 0;
 }
 
-static int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, bool kmajor, int rows, int K,
+// fp32 row-major [rows x cols] (ld) -> bf16 planes [P][rows][colsp]; no transposition: an MN-major operand is
+// consumed as such through MN-major shared-memory descriptors
+static int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int K,
                           int ld, bool is_static, __nv_bfloat16** out, int* Kp_out) {
+  const bool kmajor = true;
   const int Kp = (K + 7) & ~7;
   *Kp_out = Kp;
-  PlaneKey key{src, rows, K, ld, kmajor ? 1 : 0, P};
+  PlaneKey key{src, rows, K, ld, 1, P};
   if (is_static) {
     auto it = ws->cache.find(key);
     if (it != ws->cache.end()) { *out = it->second; return 0; }
@@ -463,6 +497,7 @@ static int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float*
   return 0;
 }
 
+// tensor map over planes [P][rows][colsp]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
 static int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, int P, int box_rows, CUtensorMap* out) {
   MapKey key{planes, rows, Kp, P, box_rows};
   auto it = ws->maps.find(key);
@@ -487,19 +522,29 @@ static int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int
   return 0;
 }
 
-template <int BN, int P>
-static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int Kp, float* C,
+template <int BN, int P, bool AMN, bool BMN>
+static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, float* C,
                        int ldc, bool beta, const float* b0, const float* b1) {
   using Cfg = UgCfg<BN, P>;
   static bool attr_set = false;
   if (!attr_set) {
-    NVQA_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    NVQA_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, P, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::SMEM));
     attr_set = true;
   }
   dim3 grid(ceil_div(N, BN), ceil_div(M, UG_BM));
-  umma_gemm_kernel<BN, P><<<grid, UG_THREADS, Cfg::SMEM, s>>>(ma, mb, M, N, Kp, C, ldc, beta ? 1 : 0, b0, b1);
+  umma_gemm_kernel<BN, P, AMN, BMN><<<grid, UG_THREADS, Cfg::SMEM, s>>>(ma, mb, M, N, K, C, ldc, beta ? 1 : 0, b0, b1);
   NVQA_LAUNCHED();
   return 0;
+}
+
+template <int BN, int P>
+static int launch_umma_major(bool amn, bool bmn, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, int M,
+                             int N, int K, float* C, int ldc, bool beta, const float* b0, const float* b1) {
+  if (!amn && !bmn) return launch_umma<BN, P, false, false>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1);
+  if (!amn && bmn) return launch_umma<BN, P, false, true>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1);
+  if (amn && !bmn) return launch_umma<BN, P, true, false>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1);
+  return launch_umma<BN, P, true, true>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1);
 }
 
 int umma_gemm(cudaStream_t s, int planes, bool a_kmajor, bool b_kmajor, int M, int N, int K, const float* A, int lda,
@@ -511,15 +556,19 @@ int umma_gemm(cudaStream_t s, int planes, bool a_kmajor, bool b_kmajor, int M, i
   ws->trans_top = 0;                      // stream order makes the previous GEMM's transient planes reusable
   __nv_bfloat16 *pa = nullptr, *pb = nullptr;
   int Kpa = 0, Kpb = 0;
-  NVQA_TRY(prepare_planes(ws, s, planes, A, a_kmajor, M, K, lda, a_static, &pa, &Kpa));
-  NVQA_TRY(prepare_planes(ws, s, planes, B, b_kmajor, N, K, ldb, b_static, &pb, &Kpb));
+  // planes keep the source's row-major shape: [M x K] / [N x K] when K-major, [K x M] / [K x N] when MN-major
+  int pitch_a = 0, pitch_b = 0;
+  NVQA_TRY(prepare_planes(ws, s, planes, A, a_kmajor ? M : K, a_kmajor ? K : M, lda, a_static, &pa, &pitch_a));
+  NVQA_TRY(prepare_planes(ws, s, planes, B, b_kmajor ? N : K, b_kmajor ? K : N, ldb, b_static, &pb, &pitch_b));
+  (void)Kpa; (void)Kpb;
   // 128 x 128 tiles when they fill the machine, else 128 x 64 for more CTAs
   const long tiles128 = (long)ceil_div(M, UG_BM) * ceil_div(N, 128);
   const int BN = tiles128 >= 148 ? 128 : 64;
   CUtensorMap ma, mb;
-  NVQA_TRY(get_map(ws, pa, M, Kpa, planes, UG_BM, &ma));
-  NVQA_TRY(get_map(ws, pb, N, Kpb, planes, BN, &mb));
-#define NVQA_UG(BN_, P_) return launch_umma<BN_, P_>(s, ma, mb, M, N, Kpa, C, ldc, beta, bias0, bias1)
+  NVQA_TRY(get_map(ws, pa, a_kmajor ? M : K, pitch_a, planes, a_kmajor ? UG_BM : 64, &ma));
+  NVQA_TRY(get_map(ws, pb, b_kmajor ? N : K, pitch_b, planes, b_kmajor ? BN : 64, &mb));
+#define NVQA_UG(BN_, P_) \
+  return launch_umma_major<BN_, P_>(!a_kmajor, !b_kmajor, s, ma, mb, M, N, K, C, ldc, beta, bias0, bias1)
   if (BN == 128) {
     if (planes == 1) NVQA_UG(128, 1);
     if (planes == 2) NVQA_UG(128, 2);

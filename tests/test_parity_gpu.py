@@ -42,7 +42,9 @@ def small_cfg(nvm, g):
     return nvm.Arch1Config(B=make_golden.B, **c), make_golden
 
 
-PRECISIONS = [("fp32_simt", 0, FP32_TOL), ("bf16x3", 1, FP32_TOL), ("bf16", 2, BF16_TOL)]
+# precision modes of the dense contractions (include/nvqa.h): exact-fp32 SIMT, split-bf16 x2 (the default fp32-parity
+# mode on tensor cores), split-bf16 x3, and the optional single-plane bf16-operand mode (1e-2)
+PRECISIONS = [("fp32_simt", 0, FP32_TOL), ("bf16x2", 3, FP32_TOL), ("bf16x3", 1, FP32_TOL), ("bf16", 2, BF16_TOL)]
 
 
 @pytest.mark.parametrize("name,prec,tol", PRECISIONS)
@@ -75,7 +77,7 @@ def test_small_step_against_golden(name, prec, tol, tag):
     m.close()
 
 
-@pytest.mark.parametrize("name,prec,tol", PRECISIONS[:2])
+@pytest.mark.parametrize("name,prec,tol", PRECISIONS[:3])
 def test_training_trajectory_against_golden(name, prec, tol):
     """three iterations of optim.rmsprop(JdJ, ...) + lr decay (002_train_baseline.lua:408-410)"""
     nvm = nv()
@@ -150,7 +152,7 @@ def test_medium_ragged_batch_live_oracle(name, prec, tol):
     m.close()
 
 
-@pytest.mark.parametrize("prec", [0, 1, 2])
+@pytest.mark.parametrize("prec", [0, 1, 2, 3])
 @pytest.mark.parametrize("ak,bk", [(1, 1), (1, 0), (0, 0), (0, 1)])
 def test_gemm_engines(prec, ak, bk):
     """The GEMM engines behind nn.Linear fwd (K-major x K-major), dgrad (x MN-major) and wgrad (both
@@ -168,7 +170,7 @@ def test_gemm_engines(prec, ak, bk):
         C_ = nvm.DeviceBuffer(m, np.zeros((M, N), np.float32))
         nvm._lib.check(lib.nvqa_gemm_test(prec, ak, bk, M, N, K, A_.ptr, B_.ptr, C_.ptr, None))
         e2, em = rel_err(C_.get(), ref)
-        tol = {0: 2e-6, 1: 1e-5, 2: 6e-3}[prec]      # bf16x3: fp32-equivalent operands, tensor-core accumulation
+        tol = {0: 2e-6, 1: 1e-5, 2: 6e-3, 3: 1e-5}[prec]      # bf16x3: fp32-equivalent operands, tensor-core accumulation
         assert e2 <= tol, f"prec {prec} {ak}{bk} {M}x{N}x{K}: rel-l2 {e2:.3e}"
     m.close()
 
@@ -216,7 +218,7 @@ def test_full_size_config1_step():
     f, grads, scores, ctx = A.jdj(oc, enc, emb, mm, q, ln, A.l2_normalize_rows(fc7), lab, seed=None)
     margin = np.sort(scores, axis=1)
     margin = margin[:, -1] - margin[:, -2]
-    for prec, tol in ((0, FP32_TOL), (1, FP32_TOL)):
+    for prec, tol in ((0, FP32_TOL), (3, FP32_TOL), (1, FP32_TOL)):
         m = make_model(nvm, cfg, enc, emb, mm, prec)
         m.set_batch_host(q, ln, fc7, lab)
         m.forward(nvm.MODE_EVAL, 0)
