@@ -1,0 +1,583 @@
+// Persistent multi-timestep LSTM layer kernels (sm_100a): ONE cooperative launch runs all T steps of a layer.
+//
+// Forward (K4): replaces, per layer, T x { h2h nn.Linear + CAddTable + 2 Narrow/Sigmoid/Tanh chains + 3 CMulTable +
+// CAddTable } of the reference cell (002_train_vqa_arch1/misc/LSTM.lua:42-59) and the rnn_forward driver loop
+// (misc/RNNUtils.lua:128-154).
+//
+//   grid  = (H/16 hidden-unit slices) x (ceil(B/128) batch tiles), one CTA per SM, all co-resident
+//   smem  = the CTA's slice of W_hh (4 gates x 16 units = 64 rows x H, P bf16 planes) RESIDENT for all T steps
+//           + a ring of A stages (h_{t-1} tile: 128 rows x 64 k x P planes) filled by TMA
+//   TMEM  = one 128 x 64 fp32 accumulator: columns ordered [i f o g] x 8 units, twice -> every epilogue thread
+//           (= one batch row) holds all four gates of its units: the gate math is thread-local
+//   per step: TMA(h_{t-1}) -> tcgen05.mma (P=2: 3 MMAs per k16) -> tcgen05.ld -> + input projection -> sigmoid/tanh,
+//           cell update -> gates, c_t, h_t (fp32), h_t as bf16 planes (next step's A operand, and the wgrad operand),
+//           Dropout(h_t) for the layer above -> grid barrier (one release-add per CTA, acquire-spin by the
+//           TMA producer thread only).
+#include <cstdlib>
+#include <vector>
+
+#include "lstm_persistent.cuh"
+#include "umma_ptx.cuh"
+
+namespace nvqa {
+
+constexpr int LP_THREADS = 320;          // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+constexpr int LP_EPI_THREADS = 256;
+constexpr int LP_MAX_STAGES = 4;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void grid_arrive(unsigned int* counter) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+// one thread per CTA polls (relaxed loads with back-off so that 128 pollers do not starve the arriving atomics),
+// then a single acquire fence orders everything after the barrier
+__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int target) {
+  long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= target) break;
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("lstm_persistent: grid barrier timed out (block %d,%d,%d, have %u want %u)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, v, target);
+      __trap();
+    }
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+// exp-based activations for the fused epilogue: ex2.approx + fast division, absolute error ~1e-7
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+template <int P>
+__global__ void __launch_bounds__(LP_THREADS, 1)
+lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
+                           float* __restrict__ pre, float* __restrict__ c, float* __restrict__ h,
+                           __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
+                           const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, int S,
+                           unsigned int* counter, long long* dbg) {
+#define LP_STAMP(t_, k_) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0) dbg[(t_) * 8 + (k_)] = clock64(); } while (0)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t W_TILE = 64 * 128;                 // 64 rows x 128 B, one plane, one k-block
+  constexpr uint32_t A_PLANE = 128 * 128;               // 128 rows x 128 B
+  const uint32_t w0 = base;                             // W: [(kb * P + p)] tiles
+  const uint32_t a0 = w0 + (uint32_t)KB * P * W_TILE;   // A ring: [s][p]
+  const uint32_t bar0 = a0 + (uint32_t)S * P * A_PLANE;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * LP_MAX_STAGES, wfull = bar0 + 16 * LP_MAX_STAGES,
+                 tfull = wfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * LP_MAX_STAGES + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * 16, m0 = blockIdx.y * 128;
+  const unsigned int G = gridDim.x * gridDim.y;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      mbar_init(wfull, 1);
+      mbar_init(tfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 64);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      // resident W_hh slice: smem row (cc*32 + g*8 + j) <- W row g*H + u0 + 8*cc + j
+      mbar_expect_tx(wfull, (uint32_t)KB * P * W_TILE);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int p = 0; p < P; ++p)
+          for (int cc = 0; cc < 2; ++cc)
+            for (int g = 0; g < 4; ++g)
+              tma_load_3d(w0 + (uint32_t)(kb * P + p) * W_TILE + (uint32_t)(cc * 4 + g) * 1024, &mapW, wfull, kb * 64,
+                          g * H + u0 + 8 * cc, p);
+      int it = 0;
+      for (int t = 0; t < T; ++t) {
+        LP_STAMP(t, 0);
+        if (t > 0) {
+          grid_wait(counter, (unsigned int)t * G);       // every CTA has published h_{t-1}
+          fence_proxy_async();
+        }
+        LP_STAMP(t, 1);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          mbar_expect_tx(full0 + 8 * s, P * A_PLANE);
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            tma_load_3d(a0 + (uint32_t)(s * P + p) * A_PLANE, &mapH, full0 + 8 * s, kb * 64, t * B + m0, p);
+        }
+        LP_STAMP(t, 2);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+      mbar_wait(wfull, 0);
+      int it = 0;
+      for (int t = 0; t < T; ++t) {
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          if (kb == 0) LP_STAMP(t, 3);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint64_t da[P], db[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              da[p] = make_kmajor_sw128_desc(a0 + (uint32_t)(s * P + p) * A_PLANE + k * 32);
+              db[p] = make_kmajor_sw128_desc(w0 + (uint32_t)(kb * P + p) * W_TILE + k * 32);
+            }
+            if (P >= 2) {
+              umma_f16(tmem_base, da[0], db[1], idesc, acc); acc = 1;
+              umma_f16(tmem_base, da[1], db[0], idesc, acc);
+            }
+            umma_f16(tmem_base, da[0], db[0], idesc, acc); acc = 1;
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+        LP_STAMP(t, 4);
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps; thread = (batch row, half of the CTA's 16 hidden units) =====
+    const int q = warp & 3;                       // TMEM lane quarter of this warp
+    const int cc = (warp - 2) >> 2;               // which 32-column half: units u0 + 8 cc .. + 8
+    const int b = m0 + q * 32 + lane;
+    const bool rowok = b < B;
+    const int mylen = rowok ? len[b] : 0;
+    const int uo = u0 + 8 * cc;
+    for (int t = 0; t < T; ++t) {
+      const bool active = rowok && (t >= T - mylen);
+      const size_t rin = (size_t)t * B + b, rout = (size_t)(t + 1) * B + b;
+      // prefetch the input projection and c_{t-1} while the MMAs run
+      float4 pv[4][2], cv[2];
+      if (active) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float* src = pre + rin * 4 * H + (size_t)g * H + uo;
+          pv[g][0] = *reinterpret_cast<const float4*>(src);
+          pv[g][1] = *reinterpret_cast<const float4*>(src + 4);
+        }
+        const float* cs = c + rin * H + uo;
+        cv[0] = *reinterpret_cast<const float4*>(cs);
+        cv[1] = *reinterpret_cast<const float4*>(cs + 4);
+      }
+      mbar_wait(tfull, (uint32_t)t & 1u);
+      tc_fence_after();
+      if (threadIdx.x == 64) LP_STAMP(t, 5);
+      float acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), acc);
+      if (rowok) {
+        float gi[8], gf[8], go[8], gg[8], cn[8], hn[8];
+        if (active) {
+          const float* pi = reinterpret_cast<const float*>(&pv[0][0]);
+          const float* pf = reinterpret_cast<const float*>(&pv[1][0]);
+          const float* po = reinterpret_cast<const float*>(&pv[2][0]);
+          const float* pg = reinterpret_cast<const float*>(&pv[3][0]);
+          const float* cp = reinterpret_cast<const float*>(&cv[0]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            gi[j] = fast_sigmoid(acc[j] + pi[j]);
+            gf[j] = fast_sigmoid(acc[8 + j] + pf[j]);
+            go[j] = fast_sigmoid(acc[16 + j] + po[j]);
+            gg[j] = fast_tanh(acc[24 + j] + pg[j]);
+            cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
+            hn[j] = go[j] * fast_tanh(cn[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { gi[j] = gf[j] = go[j] = gg[j] = cn[j] = hn[j] = 0.f; }
+        }
+        float* gdst = pre + rin * 4 * H + uo;
+#define ST8(ptr, a)                                                                          \
+        *reinterpret_cast<float4*>(ptr) = make_float4(a[0], a[1], a[2], a[3]);               \
+        *reinterpret_cast<float4*>((ptr) + 4) = make_float4(a[4], a[5], a[6], a[7]);
+        ST8(gdst, gi) ST8(gdst + H, gf) ST8(gdst + 2 * H, go) ST8(gdst + 3 * H, gg)
+        ST8(c + rout * H + uo, cn) ST8(h + rout * H + uo, hn)
+        if (xdrop) {
+          float xd[8];
+          const uint64_t mi = (uint64_t)rin * H + uo;
+          float4 ma = drop_at4(drop, mi), mb = drop_at4(drop, mi + 4);
+          xd[0] = hn[0] * ma.x; xd[1] = hn[1] * ma.y; xd[2] = hn[2] * ma.z; xd[3] = hn[3] * ma.w;
+          xd[4] = hn[4] * mb.x; xd[5] = hn[5] * mb.y; xd[6] = hn[6] * mb.z; xd[7] = hn[7] * mb.w;
+          ST8(xdrop + rin * H + uo, xd)
+        }
+#undef ST8
+        // h_t as bf16 planes: row (t+1)*B + b of the [P][(T+1)B][H] plane array
+        __nv_bfloat16 pl[3][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split3(hn[j], pl[0][j], pl[1][j], pl[2][j]);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          uint4 o;
+          o.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+          o.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+          o.z = (uint32_t)__bfloat16_as_ushort(pl[p][4]) | ((uint32_t)__bfloat16_as_ushort(pl[p][5]) << 16);
+          o.w = (uint32_t)__bfloat16_as_ushort(pl[p][6]) | ((uint32_t)__bfloat16_as_ushort(pl[p][7]) << 16);
+          *reinterpret_cast<uint4*>(hp + (size_t)p * hp_plane + rout * H + uo) = o;
+        }
+      }
+      // publish: this CTA's slice of h_t is complete.  Every writer orders its generic-proxy stores before later
+      // async-proxy (TMA) reads; the CTA barrier then makes one thread's gpu-scope release cumulative over all.
+      if (threadIdx.x == 64) LP_STAMP(t, 6);
+      tc_fence_before();
+      fence_proxy_async();
+      named_bar_sync(1, LP_EPI_THREADS);
+      if (threadIdx.x == 64) {
+        __threadfence();
+        grid_arrive(counter);
+        LP_STAMP(t, 7);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward (K9): all T steps of rnn_backward for one layer (misc/RNNUtils.lua:181-210; cell math SURVEY App. A).
+//
+//   grid = (H/64 column tiles of dh) x (4 K-splits = the four gate blocks of da) x (ceil(B/128) batch tiles)
+//   per step t = T-1 .. 0, two phases separated by grid barriers:
+//     A. element-wise, spread over all epilogue threads of the grid: da_t = f(dh_t, dc_t, gates_t, c_{t-1}, c_t),
+//        written as fp32 and as bf16 planes (the TMA / wgrad / dgrad operand); dc carry; zero the dh accumulator
+//     B. dh_{t-1} += da_t[:, gate block] . W_hh[gate block, :]   with the CTA's [512 x 64] slice of W_hh RESIDENT
+//        in shared memory (MN-major B operand: no transposed weight copy), split-K partial sums reduced with
+//        fp32 red.global.add into the double-buffered dh accumulator.
+template <int P>
+__global__ void __launch_bounds__(LP_THREADS, 1)
+lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
+                           const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ dh0,
+                           const float* __restrict__ dc0, int ld0, const float* __restrict__ dh_above, Drop drop,
+                           float* __restrict__ da, __nv_bfloat16* __restrict__ dap, long long dap_plane,
+                           float* __restrict__ dhbuf, float* __restrict__ dcbuf, const int32_t* __restrict__ len, int T,
+                           int B, int H, int KB, int S, unsigned int* counter) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t W_TILE = 64 * 128;
+  constexpr uint32_t A_PLANE = 128 * 128;
+  const uint32_t w0 = base;
+  const uint32_t a0 = w0 + (uint32_t)KB * P * W_TILE;
+  const uint32_t bar0 = a0 + (uint32_t)S * P * A_PLANE;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * LP_MAX_STAGES, wfull = bar0 + 16 * LP_MAX_STAGES,
+                 tfull = wfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * LP_MAX_STAGES + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * 64, ks = blockIdx.y, m0 = blockIdx.z * 128;
+  const unsigned int G = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int k_base = ks * H;                 // this split's gate block inside the 4H contraction dimension
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapDA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      mbar_init(wfull, 1);
+      mbar_init(tfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 64);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(wfull, (uint32_t)KB * P * W_TILE);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int p = 0; p < P; ++p)
+          tma_load_3d(w0 + (uint32_t)(kb * P + p) * W_TILE, &mapW, wfull, n0, k_base + kb * 64, p);
+      int it = 0;
+      for (int t = T - 1; t >= 1; --t) {
+        const unsigned int k = (unsigned int)(T - 1 - t);
+        grid_wait(counter, (2 * k + 1) * G);             // da_t is complete everywhere
+        fence_proxy_async();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          mbar_expect_tx(full0 + 8 * s, P * A_PLANE);
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            tma_load_3d(a0 + (uint32_t)(s * P + p) * A_PLANE, &mapDA, full0 + 8 * s, k_base + kb * 64, t * B + m0, p);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);      // B = W_hh slice, MN-major
+      mbar_wait(wfull, 0);
+      int it = 0;
+      for (int t = T - 1; t >= 1; --t) {
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint64_t dA[P], dB[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              dA[p] = make_kmajor_sw128_desc(a0 + (uint32_t)(s * P + p) * A_PLANE + k * 32);
+              dB[p] = make_mnmajor_sw128_desc(w0 + (uint32_t)(kb * P + p) * W_TILE + k * 2048);
+            }
+            if (P >= 2) {
+              umma_f16(tmem_base, dA[0], dB[1], idesc, acc); acc = 1;
+              umma_f16(tmem_base, dA[1], dB[0], idesc, acc);
+            }
+            umma_f16(tmem_base, dA[0], dB[0], idesc, acc); acc = 1;
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else {
+    // ===== 8 element-wise / epilogue warps =====
+    const int et = threadIdx.x - 64;                         // 0..255
+    const int q = warp & 3, cc = (warp - 2) >> 2;
+    const int brow = m0 + q * 32 + lane;
+    const int H4 = H >> 2;
+    const long long items = (long long)B * H4;
+    const long long gthreads = (long long)G * LP_EPI_THREADS;
+    for (int t = T - 1; t >= 0; --t) {
+      const unsigned int k = (unsigned int)(T - 1 - t);
+      if (t < T - 1) {                                       // dh_t (split-K sums of step t+1) complete everywhere
+        if (et == 0) grid_wait(counter, (2 * k) * G);
+        named_bar_sync(2, LP_EPI_THREADS);
+      }
+      // ---- phase A: cell backward, element-wise ----
+      const float* dh_src = dhbuf + (size_t)((t + 1) & 1) * B * H;
+      float* dh_zero = dhbuf + (size_t)(t & 1) * B * H;
+      for (long long i = (long long)cta * LP_EPI_THREADS + et; i < items; i += gthreads) {
+        const int b = (int)(i / H4), u = (int)(i % H4) * 4;
+        const size_t row = (size_t)t * B + b, o = (size_t)b * H + u;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 dai = z, daf = z, dao = z, dag = z, dcp = z;
+        if (t >= T - len[b]) {
+          const float* g = gates + row * 4 * H + u;
+          float4 gi = *reinterpret_cast<const float4*>(g), gf = *reinterpret_cast<const float4*>(g + H),
+                 go = *reinterpret_cast<const float4*>(g + 2 * H), gg = *reinterpret_cast<const float4*>(g + 3 * H);
+          float4 cp = *reinterpret_cast<const float4*>(c + row * H + u);
+          float4 cn = *reinterpret_cast<const float4*>(c + (row + B) * H + u);
+          float4 dh, dc;
+          if (t == T - 1) {
+            dh = *reinterpret_cast<const float4*>(dh0 + (size_t)b * ld0 + u);
+            dc = *reinterpret_cast<const float4*>(dc0 + (size_t)b * ld0 + u);
+          } else {
+            dh = *reinterpret_cast<const float4*>(dh_src + o);
+            dc = *reinterpret_cast<const float4*>(dcbuf + o);
+          }
+          if (dh_above) {
+            float4 ua = *reinterpret_cast<const float4*>(dh_above + row * H + u), mk = drop_at4(drop, (uint64_t)row * H + u);
+            dh.x += ua.x * mk.x; dh.y += ua.y * mk.y; dh.z += ua.z * mk.z; dh.w += ua.w * mk.w;
+          }
+#define LB(kk)                                                   \
+          { float tc = tanhf(cn.kk);                               \
+            float dct = dc.kk + dh.kk * go.kk * (1.0f - tc * tc);  \
+            dao.kk = dh.kk * tc * go.kk * (1.0f - go.kk);          \
+            dai.kk = dct * gg.kk * gi.kk * (1.0f - gi.kk);         \
+            daf.kk = dct * cp.kk * gf.kk * (1.0f - gf.kk);         \
+            dag.kk = dct * gi.kk * (1.0f - gg.kk * gg.kk);         \
+            dcp.kk = dct * gf.kk; }
+          LB(x) LB(y) LB(z) LB(w)
+#undef LB
+        }
+        float* dr = da + row * 4 * H + u;
+        *reinterpret_cast<float4*>(dr) = dai;
+        *reinterpret_cast<float4*>(dr + H) = daf;
+        *reinterpret_cast<float4*>(dr + 2 * H) = dao;
+        *reinterpret_cast<float4*>(dr + 3 * H) = dag;
+        *reinterpret_cast<float4*>(dcbuf + o) = dcp;
+        *reinterpret_cast<float4*>(dh_zero + o) = z;
+        const float4 gsrc[4] = {dai, daf, dao, dag};
+#pragma unroll
+        for (int gI = 0; gI < 4; ++gI) {
+          __nv_bfloat16 pl[3][4];
+          split3(gsrc[gI].x, pl[0][0], pl[1][0], pl[2][0]);
+          split3(gsrc[gI].y, pl[0][1], pl[1][1], pl[2][1]);
+          split3(gsrc[gI].z, pl[0][2], pl[1][2], pl[2][2]);
+          split3(gsrc[gI].w, pl[0][3], pl[1][3], pl[2][3]);
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            uint2 ov;
+            ov.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+            ov.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+            *reinterpret_cast<uint2*>(dap + (size_t)p * dap_plane + row * 4 * H + (size_t)gI * H + u) = ov;
+          }
+        }
+      }
+      // publish da_t (barrier 2k+1)
+      fence_proxy_async();
+      named_bar_sync(1, LP_EPI_THREADS);
+      if (et == 0) { __threadfence(); grid_arrive(counter); }
+      if (t == 0) break;
+      // ---- phase B epilogue: split-K partial of dh_{t-1} ----
+      mbar_wait(tfull, k & 1u);
+      tc_fence_after();
+      float acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), acc);
+      if (brow < B) {
+        float* dst = dh_zero + (size_t)brow * H + n0 + cc * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, acc[j]);
+      }
+      tc_fence_before();
+      named_bar_sync(1, LP_EPI_THREADS);
+      if (et == 0) { __threadfence(); grid_arrive(counter); }      // barrier 2k+2
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+static int persistent_limits(int* num_sms, int* max_smem) {
+  static int sms = 0, smem = 0;
+  if (!sms) {
+    int dev = 0;
+    NVQA_CUDA(cudaGetDevice(&dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  *num_sms = sms; *max_smem = smem;
+  return 0;
+}
+
+int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
+                        const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* da,
+                        __nv_bfloat16* dap, float* dhbuf, float* dcbuf, const int32_t* len, int T, int B, int H,
+                        unsigned int* counter) {
+  if (P < 1 || P > 2) return -1;
+  if (H % 64 != 0 || H < 64) return -1;
+  int num_sms = 0, max_smem = 0;
+  NVQA_TRY(persistent_limits(&num_sms, &max_smem));
+  const int KB = H / 64;
+  dim3 grid(H / 64, 4, ceil_div(B, 128));
+  if ((int)(grid.x * grid.y * grid.z) > num_sms) return -1;
+  const size_t wbytes = (size_t)KB * P * 8192, misc = 1024 + 256;
+  if ((size_t)max_smem < misc + wbytes + 2 * (size_t)P * 16384) return -1;
+  int S = (int)(((size_t)max_smem - misc - wbytes) / ((size_t)P * 16384));
+  if (S > LP_MAX_STAGES) S = LP_MAX_STAGES;
+  const size_t smem = wbytes + (size_t)S * P * 16384 + misc;
+
+  __nv_bfloat16* wp = nullptr;
+  int pitch = 0;
+  NVQA_TRY(prepare_planes(ws, s, P, Wh, 4 * H, H, H, true, &wp, &pitch));
+  CUtensorMap mapW, mapDA;
+  NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 64, &mapW));             // MN-major B: 64 k-rows x 64 columns
+  NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 128, &mapDA));
+  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+  long long dap_plane = (long long)T * B * 4 * H;
+  int KBv = KB, Sv = S;
+  void* args[] = {&mapDA, &mapW, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &da, &dap, &dap_plane, &dhbuf, &dcbuf,
+                  &len, &T, &B, &H, &KBv, &Sv, &counter};
+  const void* fn = P == 1 ? (const void*)lstm_bwd_persistent_kernel<1> : (const void*)lstm_bwd_persistent_kernel<2>;
+  static bool attr[3] = {false, false, false};
+  if (!attr[P]) {
+    NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr[P] = true;
+  }
+  NVQA_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(LP_THREADS), args, smem, s));
+  ++g_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
+                        __nv_bfloat16* hp, float* xdrop_next, const int32_t* len, Drop d, int T, int B, int H,
+                        unsigned int* counter) {
+  if (P < 1 || P > 2) return -1;                 // P = 3: W_hh does not fit in shared memory next to the A ring
+  if (H % 64 != 0 || H < 64) return -1;
+  static int num_sms = 0, max_smem = 0;
+  if (!num_sms) {
+    int dev = 0;
+    NVQA_CUDA(cudaGetDevice(&dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  const int KB = H / 64;
+  dim3 grid(H / 16, ceil_div(B, 128));
+  if ((int)(grid.x * grid.y) > num_sms) return -1;
+  const size_t wbytes = (size_t)KB * P * 8192, misc = 1024 + 256;
+  int S = (int)(((size_t)max_smem - misc - wbytes) / ((size_t)P * 16384));
+  if ((size_t)max_smem < misc + wbytes + 2 * (size_t)P * 16384) return -1;
+  if (S > LP_MAX_STAGES) S = LP_MAX_STAGES;
+  const size_t smem = wbytes + (size_t)S * P * 16384 + misc;
+
+  __nv_bfloat16* wp = nullptr;
+  int pitch = 0;
+  NVQA_TRY(prepare_planes(ws, s, P, Wh, 4 * H, H, H, true, &wp, &pitch));
+  CUtensorMap mapW, mapH;
+  NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 8, &mapW));
+  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 128, &mapH));
+  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+  long long hp_plane = (long long)(T + 1) * B * H;
+  int KBv = KB, Sv = S;
+  long long* dbg = nullptr;
+  static const bool want_dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
+  if (want_dbg) {
+    NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbg), (size_t)T * 8 * sizeof(long long)));
+    NVQA_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(long long), s));
+  }
+  void* args[] = {&mapH, &mapW, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &Sv, &counter, &dbg};
+  const void* fn = P == 1 ? (const void*)lstm_fwd_persistent_kernel<1> : (const void*)lstm_fwd_persistent_kernel<2>;
+  static bool attr[3] = {false, false, false};
+  if (!attr[P]) {
+    NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr[P] = true;
+  }
+  NVQA_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(LP_THREADS), args, smem, s));
+  ++g_launches;
+  if (want_dbg) {   // per-step timeline of CTA (0,0) in SM cycles, relative to the step's first stamp
+    std::vector<long long> hbuf((size_t)T * 8);
+    NVQA_CUDA(cudaStreamSynchronize(s));
+    NVQA_CUDA(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    fprintf(stderr, "lstm_fwd_persistent timeline (cycles): t | wait_bar tma_issued first_data mma_done epi_start epi_stored arrived | step\n");
+    for (int t = 1; t < T; ++t) {
+      const long long* e = &hbuf[(size_t)t * 8];
+      fprintf(stderr, "%2d | %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", t, e[1] - e[0], e[2] - e[0], e[3] - e[0],
+              e[4] - e[0], e[5] - e[0], e[6] - e[0], e[7] - e[0], e[0] - hbuf[(size_t)(t - 1) * 8]);
+    }
+  }
+  return 0;
+}
+
+}  // namespace nvqa

@@ -1,0 +1,27 @@
+// Persistent multi-timestep LSTM layer kernels (lstm_persistent.cu).
+#pragma once
+#include "umma_engine.cuh"
+
+namespace nvqa {
+
+// All T steps of one LSTM layer's recurrence in one cooperative launch (see lstm_persistent.cu).
+//   pre  [T][B][4H]   in: x.Wi^T + bi + bh (batched input projection)   out: gates i,f,o,g (post-activation)
+//   c,h  [(T+1)][B][H] fp32 states, slot 0 = zeros, slot t+1 written by step t
+//   hp   [P][(T+1)B][H] bf16 planes of h (slot 0 zeros): A operand of the next step and of the wgrad GEMM
+//   xdrop_next [T][B][H] = Dropout(h_t) for the layer above (nullptr for the top layer)
+// Returns 0 on success, -1 when the shape/precision is not supported (caller falls back to per-step kernels),
+// > 0 on error.
+int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
+                        __nv_bfloat16* hp, float* xdrop_next, const int32_t* len, Drop d, int T, int B, int H,
+                        unsigned int* counter);
+
+// All T steps of one layer's backward recurrence (see lstm_persistent.cu).
+//   gates [T][B][4H] post-activation, c [(T+1)][B][H]; dh0/dc0 (leading dim ld0): d(final state) of this layer;
+//   dh_above [T][B][H]: dX of the layer above (masked by its input Dropout) or nullptr;
+//   out: da [T*B][4H] fp32 and dap [P][T*B][4H] bf16 planes; scratch dhbuf [2][B][H], dcbuf [B][H].
+int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
+                        const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* da,
+                        __nv_bfloat16* dap, float* dhbuf, float* dcbuf, const int32_t* len, int T, int B, int H,
+                        unsigned int* counter);
+
+}  // namespace nvqa

@@ -12,11 +12,13 @@
 //     over clones (:323-326);
 //   - rows stay in original batch order; activity masks replace the length sort (see pointwise.cu);
 //   - d fc7 (computed and discarded by the reference) is not computed.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
 
 #include "../../include/nvqa.h"
+#include "lstm_persistent.cuh"
 #include "pointwise.cuh"
 
 namespace nvqa {
@@ -59,6 +61,12 @@ struct nvqa_model {
   int32_t* argmax = nullptr;
   float *dzd = nullptr, *dqpre = nullptr, *dipre = nullptr, *dqd = nullptr;
   float *da = nullptr, *dxbuf = nullptr, *dh_carry = nullptr, *dc_carry = nullptr;
+  __nv_bfloat16* hp[4] = {};        // bf16 planes of h per layer [P][(T+1)B][H] (persistent recurrent kernels)
+  __nv_bfloat16* dap = nullptr;     // bf16 planes of da [P][T*B][4H] (persistent backward kernel)
+  float* dhbuf = nullptr;           // [2][B][H] split-K accumulator of dh
+  unsigned int* grid_counter = nullptr;
+  int planes = 0;                   // bf16 planes per operand of the tensor-core modes (0 = SIMT)
+  bool use_persistent = true;
   // batch
   const int32_t *q = nullptr, *len = nullptr, *labels = nullptr;
   const float* fc7 = nullptr;
@@ -267,6 +275,20 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_TRY(dallocT(m, &m->fc7_stage, (int64_t)B * I));
   NVQA_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->loss_host), 64));
   NVQA_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->ans_host), (size_t)B * 4));
+  m->planes = cfg->precision == NVQA_PREC_BF16X3 ? 3 : cfg->precision == NVQA_PREC_BF16X2 ? 2
+              : cfg->precision == NVQA_PREC_BF16 ? 1 : 0;
+  NVQA_TRY(dallocT(m, &m->grid_counter, 4));
+  if (m->planes) {
+    for (int l = 0; l < L; ++l) {
+      NVQA_TRY(dallocT(m, &m->hp[l], (size_t)m->planes * (N + B) * H));
+      NVQA_CUDA(cudaMemsetAsync(m->hp[l], 0, (size_t)m->planes * (N + B) * H * 2, m->stream));
+    }
+  }
+  if (m->planes) {
+    NVQA_TRY(dallocT(m, &m->dap, (size_t)m->planes * N * 4 * H));
+    NVQA_TRY(dallocT(m, &m->dhbuf, (size_t)2 * B * H));
+  }
+  if (getenv("NVQA_NO_PERSISTENT")) m->use_persistent = false;
   if (cfg->precision != NVQA_PREC_FP32_SIMT) {
     // transient operand planes of the largest GEMM (wgrad: da^T [4H x TB] and x^T [H x TB], 3 bf16 planes each);
     // static region: every weight matrix in both orientations
@@ -416,6 +438,14 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
     const int in = l == 0 ? E : H;
     NVQA_TRY(gemm(m, CAT_INPROJ, true, true, T * B, 4 * H, in, X, in, m->lw[l].Wi, in, m->pre[l], 4 * H, false, m->lw[l].bi,
                   m->lw[l].bh));
+    if (m->planes && m->use_persistent) {
+      // K4: all T steps in one persistent cooperative kernel (W_hh slice resident in shared memory)
+      int rc = lstm_fwd_persistent(s, m->ws, m->planes, m->lw[l].Wh, m->pre[l], m->c[l], m->h[l], m->hp[l],
+                                   l + 1 < L ? m->xdrop[l + 1] : nullptr, m->len, lstm_drop(m, l), T, B, H,
+                                   m->grid_counter);
+      if (rc > 0) return rc;
+      if (rc == 0) continue;
+    }
     for (int t = 0; t < T; ++t) {
       float* pre_t = m->pre[l] + (int64_t)t * B * 4 * H;
       if (t > 0)   // h_0 == 0: the recurrent term of the first step vanishes
@@ -486,7 +516,15 @@ static int backward_lstm(nvqa_model* m) {
     const float* dh_in = m->dqd + (2 * l + 1) * H;
     const float* dc_in = m->dqd + (2 * l) * H;
     int ld = S;
-    for (int t = T - 1; t >= 0; --t) {
+    int rc = -1;
+    if (m->planes && m->use_persistent) {
+      // K9: the whole backward recurrence of this layer in one persistent cooperative kernel
+      rc = lstm_bwd_persistent(s, m->ws, m->planes, m->lw[l].Wh, m->pre[l], m->c[l], dh_in, dc_in, ld,
+                               l + 1 < L ? m->dxbuf : nullptr, lstm_drop(m, l), m->da, m->dap, m->dhbuf, m->dc_carry,
+                               m->len, T, B, H, m->grid_counter);
+      if (rc > 0) return rc;
+    }
+    for (int t = T - 1; t >= 0 && rc != 0; --t) {
       NVQA_TRY(lstm_gates_bwd(s, m->pre[l] + (int64_t)t * B * 4 * H, m->c[l] + t * BH, m->c[l] + (t + 1) * BH, dh_in, ld,
                               l + 1 < L ? m->dxbuf + t * BH : nullptr, dc_in, ld, m->da + (int64_t)t * B * 4 * H,
                               m->dc_carry, m->len, lstm_drop(m, l), t, T, B, H));

@@ -1,0 +1,56 @@
+// Host-side state of the tcgen05 GEMM engine: bf16 operand planes (arena + per-step cache of weight planes) and
+// cached TMA tensor maps.  Shared by umma_gemm.cu and the persistent LSTM kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace nvqa {
+
+struct PlaneKey {
+  const void* src; int rows, K, ld, kmajor, P;
+  bool operator==(const PlaneKey& o) const {
+    return src == o.src && rows == o.rows && K == o.K && ld == o.ld && kmajor == o.kmajor && P == o.P;
+  }
+};
+struct PlaneKeyHash {
+  size_t operator()(const PlaneKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.src);
+    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.K; h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)(k.kmajor * 8 + k.P);
+    return h;
+  }
+};
+struct MapKey {
+  const void* planes; int rows, Kp, P, box;
+  bool operator==(const MapKey& o) const { return planes == o.planes && rows == o.rows && Kp == o.Kp && P == o.P && box == o.box; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.planes);
+    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.Kp; h = h * 1000003u ^ (size_t)(k.P * 1024 + k.box);
+    return h;
+  }
+};
+
+struct UmmaWorkspace {
+  uint8_t* base = nullptr;
+  size_t bytes = 0;
+  size_t static_bytes = 0;      // [0, static_bytes): cached planes of static operands (weights)
+  size_t static_top = 0;
+  size_t trans_top = 0;         // transient planes live in [static_bytes, bytes), reset per GEMM
+  std::unordered_map<PlaneKey, __nv_bfloat16*, PlaneKeyHash> cache;
+  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
+};
+
+
+// fp32 row-major [rows x cols] (ld) -> bf16 planes [P][rows][pitch], pitch = cols rounded up to 8
+int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int cols, int ld,
+                   bool is_static, __nv_bfloat16** out, int* pitch_out);
+// tensor map over planes [P][rows][pitch]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
+int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int pitch, int P, int box_rows, CUtensorMap* out);
+
+}  // namespace nvqa

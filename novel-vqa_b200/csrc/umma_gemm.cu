@@ -16,119 +16,13 @@
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
 //   warps 2-5: epilogue       - tcgen05.ld (32 lanes x 32 columns per warp), bias / beta, fp32 stores
 // smem: STAGES x { P A-planes [128 x 64] , P B-planes [BN x 64] } ring with full/empty mbarriers.
-#include <cuda.h>
-#include <cuda_bf16.h>
-
 #include <unordered_map>
 #include <vector>
 
-#include "common.cuh"
+#include "umma_engine.cuh"
+#include "umma_ptx.cuh"
 
 namespace nvqa {
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// spin on try_wait with a watchdog: a broken pipeline traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (clock64() - t0 > 4000000000LL) {
-      printf("umma_gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, issued by ONE thread on behalf of the CTA
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane_base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor, K-major operand tile [rows x 64 bf16] written by TMA with SWIZZLE_128B:
-// 8-row groups of 1024 B (SBO), 128 B rows; LBO unused for swizzled K-major; version 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address            bits [0,14)
-  d |= (uint64_t)1 << 16;                             // leading byte offset (ignored)  [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset        [32,46)
-  d |= (uint64_t)1 << 46;                             // descriptor version        [46,48)
-  d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B      [61,64)
-  return d;
-}
-// MN-major operand tile: [64 k-rows x 64 mn] boxes (128 B rows, SWIZZLE_128B), one box per 64-wide MN chunk:
-// LBO = byte stride between MN chunks (one 8 KB box), SBO = stride between 8-row k groups (1024 B).
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(8192 >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// Instruction descriptor, kind::f16: D = F32, A = B = BF16, M x N tile; bit 15 / 16 = A / B is MN-major.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------------------
 // the GEMM kernel
@@ -307,18 +201,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // operand preparation: fp32 -> P bf16 planes, K-major [P][rows][Kp]
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
-  p0 = __float2bfloat16_rn(x);
-  float r1 = x - __bfloat162float(p0);
-  p1 = __float2bfloat16_rn(r1);
-  float r2 = r1 - __bfloat162float(p1);
-  p2 = __float2bfloat16_rn(r2);
-}
-
-// source is K-major: src[row * ld + k]
+// row-major fp32 [rows x K] (ld) -> planes [P][rows][Kp]
 template <int P>
 __global__ void __launch_bounds__(256)
-split_kmajor_kernel(const float* __restrict__ src, int rows, int K, int ld, int Kp, __nv_bfloat16* __restrict__ dst) {
+split_planes_kernel(const float* __restrict__ src, int rows, int K, int ld, int Kp, __nv_bfloat16* __restrict__ dst) {
   const int K4 = Kp >> 2;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * K4) return;
@@ -346,38 +232,6 @@ split_kmajor_kernel(const float* __restrict__ src, int rows, int K, int ld, int 
   }
 }
 
-// source is MN-major: src[k * ld + row]; transposed through shared memory so that both the fp32 reads
-// and the bf16 writes are coalesced.  Tile: 64 k x 32 rows, 256 threads.
-template <int P>
-__global__ void __launch_bounds__(256)
-split_transpose_kernel(const float* __restrict__ src, int rows, int K, int ld, int Kp, __nv_bfloat16* __restrict__ dst) {
-  __shared__ float tile[64][33];
-  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int k = k0 + ty + 8 * j, r = r0 + tx;
-    tile[ty + 8 * j][tx] = (k < K && r < rows) ? src[(int64_t)k * ld + r] : 0.f;
-  }
-  __syncthreads();
-  const int64_t plane = (int64_t)rows * Kp;
-  // each thread writes two consecutive k (one 32-bit store per plane): 32 threads cover 64 k of one row
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int r = r0 + ty + 8 * j, k = k0 + 2 * tx;
-    if (r < rows && k < Kp) {
-      __nv_bfloat16 a[3], b[3];
-      split3(tile[2 * tx][ty + 8 * j], a[0], a[1], a[2]);
-      split3(tile[2 * tx + 1][ty + 8 * j], b[0], b[1], b[2]);
-#pragma unroll
-      for (int q = 0; q < P; ++q) {
-        uint32_t o = (uint32_t)__bfloat16_as_ushort(a[q]) | ((uint32_t)__bfloat16_as_ushort(b[q]) << 16);
-        *reinterpret_cast<uint32_t*>(dst + q * plane + (int64_t)r * Kp + k) = o;
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -396,42 +250,6 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-
-struct PlaneKey {
-  const void* src; int rows, K, ld, kmajor, P;
-  bool operator==(const PlaneKey& o) const {
-    return src == o.src && rows == o.rows && K == o.K && ld == o.ld && kmajor == o.kmajor && P == o.P;
-  }
-};
-struct PlaneKeyHash {
-  size_t operator()(const PlaneKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.src);
-    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.K; h = h * 1000003u ^ (size_t)k.ld;
-    h = h * 1000003u ^ (size_t)(k.kmajor * 8 + k.P);
-    return h;
-  }
-};
-struct MapKey {
-  const void* planes; int rows, Kp, P, box;
-  bool operator==(const MapKey& o) const { return planes == o.planes && rows == o.rows && Kp == o.Kp && P == o.P && box == o.box; }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.planes);
-    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.Kp; h = h * 1000003u ^ (size_t)(k.P * 1024 + k.box);
-    return h;
-  }
-};
-
-struct UmmaWorkspace {
-  uint8_t* base = nullptr;
-  size_t bytes = 0;
-  size_t static_bytes = 0;      // [0, static_bytes): cached planes of static operands (weights)
-  size_t static_top = 0;
-  size_t trans_top = 0;         // transient planes live in [static_bytes, bytes), reset per GEMM
-  std::unordered_map<PlaneKey, __nv_bfloat16*, PlaneKeyHash> cache;
-  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
-};
 
 int umma_workspace_create(UmmaWorkspace** out, size_t transient_bytes, size_t static_bytes) {
   UmmaWorkspace* ws = new UmmaWorkspace();
@@ -460,9 +278,8 @@ void umma_workspace_invalidate(UmmaWorkspace* ws) {
 
 // fp32 row-major [rows x cols] (ld) -> bf16 planes [P][rows][colsp]; no transposition: an MN-major operand is
 // consumed as such through MN-major shared-memory descriptors
-static int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int K,
+int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int K,
                           int ld, bool is_static, __nv_bfloat16** out, int* Kp_out) {
-  const bool kmajor = true;
   const int Kp = (K + 7) & ~7;
   *Kp_out = Kp;
   PlaneKey key{src, rows, K, ld, 1, P};
@@ -481,24 +298,17 @@ static int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float*
     dst = reinterpret_cast<__nv_bfloat16*>(ws->base + ws->static_bytes + ws->trans_top);
     ws->trans_top += need;
   }
-  if (kmajor) {
-    int64_t n = (int64_t)rows * (Kp / 4);
-    if (P == 1) split_kmajor_kernel<1><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
-    else if (P == 2) split_kmajor_kernel<2><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
-    else split_kmajor_kernel<3><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
-  } else {
-    dim3 grid(ceil_div(rows, 32), ceil_div(Kp, 64));
-    if (P == 1) split_transpose_kernel<1><<<grid, 256, 0, s>>>(src, rows, K, ld, Kp, dst);
-    else if (P == 2) split_transpose_kernel<2><<<grid, 256, 0, s>>>(src, rows, K, ld, Kp, dst);
-    else split_transpose_kernel<3><<<grid, 256, 0, s>>>(src, rows, K, ld, Kp, dst);
-  }
+  int64_t n = (int64_t)rows * (Kp / 4);
+  if (P == 1) split_planes_kernel<1><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+  else if (P == 2) split_planes_kernel<2><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+  else split_planes_kernel<3><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
   NVQA_LAUNCHED();
   *out = dst;
   return 0;
 }
 
 // tensor map over planes [P][rows][colsp]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
-static int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, int P, int box_rows, CUtensorMap* out) {
+int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, int P, int box_rows, CUtensorMap* out) {
   MapKey key{planes, rows, Kp, P, box_rows};
   auto it = ws->maps.find(key);
   if (it != ws->maps.end()) { *out = it->second; return 0; }
