@@ -24,6 +24,8 @@ namespace nvqa {
 constexpr int LP_THREADS = 320;          // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 constexpr int LP_EPI_THREADS = 256;
 constexpr int LP_MAX_STAGES = 4;
+#define LP_STAMP(t_, k_) \
+  do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) dbg[(t_) * 8 + (k_)] = clock64(); } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -33,13 +35,14 @@ __device__ __forceinline__ void grid_arrive(unsigned int* counter) {
 }
 // one thread per CTA polls (relaxed loads with back-off so that 128 pollers do not starve the arriving atomics),
 // then a single acquire fence orders everything after the barrier
+__device__ int g_poll_ns = 40;
 __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int target) {
   long long t0 = clock64();
   while (true) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
     if (v >= target) break;
-    __nanosleep(40);
+    __nanosleep(g_poll_ns);
     if (clock64() - t0 > 4000000000LL) {
       printf("lstm_persistent: grid barrier timed out (block %d,%d,%d, have %u want %u)\n", blockIdx.x, blockIdx.y,
              blockIdx.z, v, target);
@@ -60,7 +63,6 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
                            __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
                            const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, int S,
                            unsigned int* counter, long long* dbg) {
-#define LP_STAMP(t_, k_) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0) dbg[(t_) * 8 + (k_)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -124,7 +126,6 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
           for (int p = 0; p < P; ++p)
             tma_load_3d(a0 + (uint32_t)(s * P + p) * A_PLANE, &mapH, full0 + 8 * s, kb * 64, t * B + m0, p);
         }
-        LP_STAMP(t, 2);
       }
     }
   } else if (warp == 1) {
@@ -169,11 +170,14 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
     const bool rowok = b < B;
     const int mylen = rowok ? len[b] : 0;
     const int uo = u0 + 8 * cc;
+    float ccarry[8];                               // c_{t-1} of this thread's (row, 8 units): never leaves registers
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ccarry[j] = 0.f;
     for (int t = 0; t < T; ++t) {
       const bool active = rowok && (t >= T - mylen);
       const size_t rin = (size_t)t * B + b, rout = (size_t)(t + 1) * B + b;
-      // prefetch the input projection and c_{t-1} while the MMAs run
-      float4 pv[4][2], cv[2];
+      // prefetch the input projection while the MMAs run
+      float4 pv[4][2];
       if (active) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -181,9 +185,6 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
           pv[g][0] = *reinterpret_cast<const float4*>(src);
           pv[g][1] = *reinterpret_cast<const float4*>(src + 4);
         }
-        const float* cs = c + rin * H + uo;
-        cv[0] = *reinterpret_cast<const float4*>(cs);
-        cv[1] = *reinterpret_cast<const float4*>(cs + 4);
       }
       mbar_wait(tfull, (uint32_t)t & 1u);
       tc_fence_after();
@@ -197,15 +198,15 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
           const float* pf = reinterpret_cast<const float*>(&pv[1][0]);
           const float* po = reinterpret_cast<const float*>(&pv[2][0]);
           const float* pg = reinterpret_cast<const float*>(&pv[3][0]);
-          const float* cp = reinterpret_cast<const float*>(&cv[0]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             gi[j] = fast_sigmoid(acc[j] + pi[j]);
             gf[j] = fast_sigmoid(acc[8 + j] + pf[j]);
             go[j] = fast_sigmoid(acc[16 + j] + po[j]);
             gg[j] = fast_tanh(acc[24 + j] + pg[j]);
-            cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
+            cn[j] = gf[j] * ccarry[j] + gi[j] * gg[j];
             hn[j] = go[j] * fast_tanh(cn[j]);
+            ccarry[j] = cn[j];
           }
         } else {
 #pragma unroll
@@ -247,10 +248,14 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
       fence_proxy_async();
       named_bar_sync(1, LP_EPI_THREADS);
       if (threadIdx.x == 64) {
+        LP_STAMP(t, 2);      // (debug) reuse slot 2: all epilogue warps done
         __threadfence();
         grid_arrive(counter);
         LP_STAMP(t, 7);
       }
+      // hold the other warps until the release is out: their prefetch loads for step t+1 would otherwise sit in
+      // front of the membar in the SM's memory pipeline (measured: +3.4k cycles per step)
+      named_bar_sync(3, LP_EPI_THREADS);
     }
   }
   tc_fence_before();
@@ -266,8 +271,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
 //     A. element-wise, spread over all epilogue threads of the grid: da_t = f(dh_t, dc_t, gates_t, c_{t-1}, c_t),
 //        written as fp32 and as bf16 planes (the TMA / wgrad / dgrad operand); dc carry; zero the dh accumulator
 //     B. dh_{t-1} += da_t[:, gate block] . W_hh[gate block, :]   with the CTA's [512 x 64] slice of W_hh RESIDENT
-//        in shared memory (MN-major B operand: no transposed weight copy), split-K partial sums reduced with
-//        fp32 red.global.add into the double-buffered dh accumulator.
+//        in shared memory (MN-major B operand: no transposed weight copy); the four split-K partials go to a
+//        double-buffered [4][B][H] scratch and are summed (fixed order, deterministic) by the next phase A.
 template <int P>
 __global__ void __launch_bounds__(LP_THREADS, 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
@@ -275,7 +280,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
                            const float* __restrict__ dc0, int ld0, const float* __restrict__ dh_above, Drop drop,
                            float* __restrict__ da, __nv_bfloat16* __restrict__ dap, long long dap_plane,
                            float* __restrict__ dhbuf, float* __restrict__ dcbuf, const int32_t* __restrict__ len, int T,
-                           int B, int H, int KB, int S, unsigned int* counter) {
+                           int B, int H, int KB, int S, unsigned int* counter, long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -378,89 +383,120 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
     const long long gthreads = (long long)G * LP_EPI_THREADS;
     for (int t = T - 1; t >= 0; --t) {
       const unsigned int k = (unsigned int)(T - 1 - t);
+      if (et == 0) LP_STAMP(t, 0);
       if (t < T - 1) {                                       // dh_t (split-K sums of step t+1) complete everywhere
         if (et == 0) grid_wait(counter, (2 * k) * G);
         named_bar_sync(2, LP_EPI_THREADS);
       }
+      if (et == 0) LP_STAMP(t, 1);
       // ---- phase A: cell backward, element-wise ----
-      const float* dh_src = dhbuf + (size_t)((t + 1) & 1) * B * H;
-      float* dh_zero = dhbuf + (size_t)(t & 1) * B * H;
-      for (long long i = (long long)cta * LP_EPI_THREADS + et; i < items; i += gthreads) {
-        const int b = (int)(i / H4), u = (int)(i % H4) * 4;
-        const size_t row = (size_t)t * B + b, o = (size_t)b * H + u;
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 dai = z, daf = z, dao = z, dag = z, dcp = z;
-        if (t >= T - len[b]) {
-          const float* g = gates + row * 4 * H + u;
-          float4 gi = *reinterpret_cast<const float4*>(g), gf = *reinterpret_cast<const float4*>(g + H),
-                 go = *reinterpret_cast<const float4*>(g + 2 * H), gg = *reinterpret_cast<const float4*>(g + 3 * H);
-          float4 cp = *reinterpret_cast<const float4*>(c + row * H + u);
-          float4 cn = *reinterpret_cast<const float4*>(c + (row + B) * H + u);
-          float4 dh, dc;
-          if (t == T - 1) {
-            dh = *reinterpret_cast<const float4*>(dh0 + (size_t)b * ld0 + u);
-            dc = *reinterpret_cast<const float4*>(dc0 + (size_t)b * ld0 + u);
-          } else {
-            dh = *reinterpret_cast<const float4*>(dh_src + o);
-            dc = *reinterpret_cast<const float4*>(dcbuf + o);
+      const size_t BHs = (size_t)B * H;
+      const float* dh_src = dhbuf + (size_t)((t + 1) & 1) * 4 * BHs;      // 4 split-K partials of dh_t
+      float* dh_part = dhbuf + ((size_t)(t & 1) * 4 + ks) * BHs;          // this split's partial of dh_{t-1}
+      // two items per pass with all loads issued up front (the phase is latency-bound, not bandwidth-bound)
+      for (long long i0 = (long long)cta * LP_EPI_THREADS + et; i0 < items; i0 += 2 * gthreads) {
+        constexpr int NI = 2;
+        bool valid[NI], act[NI];
+        size_t row[NI], o[NI];
+        int ucol[NI];
+        float4 gi[NI], gf[NI], go[NI], gg[NI], cp[NI], cn[NI], dh[NI], dc[NI];
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+          const long long i = i0 + (long long)n * gthreads;
+          valid[n] = i < items;
+          const int b = valid[n] ? (int)(i / H4) : 0;
+          ucol[n] = valid[n] ? (int)(i % H4) * 4 : 0;
+          row[n] = (size_t)t * B + b;
+          o[n] = (size_t)b * H + ucol[n];
+          act[n] = valid[n] && (t >= T - len[b]);
+          gi[n] = gf[n] = go[n] = gg[n] = cp[n] = cn[n] = dh[n] = dc[n] = z;
+          if (act[n]) {
+            const float* g = gates + row[n] * 4 * H + ucol[n];
+            gi[n] = *reinterpret_cast<const float4*>(g);
+            gf[n] = *reinterpret_cast<const float4*>(g + H);
+            go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+            gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+            cp[n] = *reinterpret_cast<const float4*>(c + row[n] * H + ucol[n]);
+            cn[n] = *reinterpret_cast<const float4*>(c + (row[n] + B) * H + ucol[n]);
+            if (t == T - 1) {
+              dh[n] = *reinterpret_cast<const float4*>(dh0 + (size_t)b * ld0 + ucol[n]);
+              dc[n] = *reinterpret_cast<const float4*>(dc0 + (size_t)b * ld0 + ucol[n]);
+            } else {
+              const float* ds = dh_src + o[n];
+              float4 d0 = *reinterpret_cast<const float4*>(ds), d1 = *reinterpret_cast<const float4*>(ds + BHs),
+                     d2 = *reinterpret_cast<const float4*>(ds + 2 * BHs), d3 = *reinterpret_cast<const float4*>(ds + 3 * BHs);
+              dh[n] = make_float4((d0.x + d1.x) + (d2.x + d3.x), (d0.y + d1.y) + (d2.y + d3.y),
+                                  (d0.z + d1.z) + (d2.z + d3.z), (d0.w + d1.w) + (d2.w + d3.w));
+              dc[n] = *reinterpret_cast<const float4*>(dcbuf + o[n]);
+            }
+            if (dh_above) {
+              float4 ua = *reinterpret_cast<const float4*>(dh_above + row[n] * H + ucol[n]);
+              float4 mk = drop_at4(drop, (uint64_t)row[n] * H + ucol[n]);
+              dh[n].x += ua.x * mk.x; dh[n].y += ua.y * mk.y; dh[n].z += ua.z * mk.z; dh[n].w += ua.w * mk.w;
+            }
           }
-          if (dh_above) {
-            float4 ua = *reinterpret_cast<const float4*>(dh_above + row * H + u), mk = drop_at4(drop, (uint64_t)row * H + u);
-            dh.x += ua.x * mk.x; dh.y += ua.y * mk.y; dh.z += ua.z * mk.z; dh.w += ua.w * mk.w;
-          }
-#define LB(kk)                                                   \
-          { float tc = tanhf(cn.kk);                               \
-            float dct = dc.kk + dh.kk * go.kk * (1.0f - tc * tc);  \
-            dao.kk = dh.kk * tc * go.kk * (1.0f - go.kk);          \
-            dai.kk = dct * gg.kk * gi.kk * (1.0f - gi.kk);         \
-            daf.kk = dct * cp.kk * gf.kk * (1.0f - gf.kk);         \
-            dag.kk = dct * gi.kk * (1.0f - gg.kk * gg.kk);         \
-            dcp.kk = dct * gf.kk; }
-          LB(x) LB(y) LB(z) LB(w)
-#undef LB
         }
-        float* dr = da + row * 4 * H + u;
-        *reinterpret_cast<float4*>(dr) = dai;
-        *reinterpret_cast<float4*>(dr + H) = daf;
-        *reinterpret_cast<float4*>(dr + 2 * H) = dao;
-        *reinterpret_cast<float4*>(dr + 3 * H) = dag;
-        *reinterpret_cast<float4*>(dcbuf + o) = dcp;
-        *reinterpret_cast<float4*>(dh_zero + o) = z;
-        const float4 gsrc[4] = {dai, daf, dao, dag};
 #pragma unroll
-        for (int gI = 0; gI < 4; ++gI) {
-          __nv_bfloat16 pl[3][4];
-          split3(gsrc[gI].x, pl[0][0], pl[1][0], pl[2][0]);
-          split3(gsrc[gI].y, pl[0][1], pl[1][1], pl[2][1]);
-          split3(gsrc[gI].z, pl[0][2], pl[1][2], pl[2][2]);
-          split3(gsrc[gI].w, pl[0][3], pl[1][3], pl[2][3]);
+        for (int n = 0; n < NI; ++n) {
+          if (!valid[n]) continue;
+          float4 dai = z, daf = z, dao = z, dag = z, dcp = z;
+          if (act[n]) {
+#define LB(kk)                                                                   \
+            { float tc = fast_tanh(cn[n].kk);                                      \
+              float dct = dc[n].kk + dh[n].kk * go[n].kk * (1.0f - tc * tc);       \
+              dao.kk = dh[n].kk * tc * go[n].kk * (1.0f - go[n].kk);               \
+              dai.kk = dct * gg[n].kk * gi[n].kk * (1.0f - gi[n].kk);              \
+              daf.kk = dct * cp[n].kk * gf[n].kk * (1.0f - gf[n].kk);              \
+              dag.kk = dct * gi[n].kk * (1.0f - gg[n].kk * gg[n].kk);              \
+              dcp.kk = dct * gf[n].kk; }
+            LB(x) LB(y) LB(z) LB(w)
+#undef LB
+          }
+          float* dr = da + row[n] * 4 * H + ucol[n];
+          *reinterpret_cast<float4*>(dr) = dai;
+          *reinterpret_cast<float4*>(dr + H) = daf;
+          *reinterpret_cast<float4*>(dr + 2 * H) = dao;
+          *reinterpret_cast<float4*>(dr + 3 * H) = dag;
+          *reinterpret_cast<float4*>(dcbuf + o[n]) = dcp;
+          const float4 gsrc[4] = {dai, daf, dao, dag};
 #pragma unroll
-          for (int p = 0; p < P; ++p) {
-            uint2 ov;
-            ov.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
-            ov.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
-            *reinterpret_cast<uint2*>(dap + (size_t)p * dap_plane + row * 4 * H + (size_t)gI * H + u) = ov;
+          for (int gI = 0; gI < 4; ++gI) {
+            __nv_bfloat16 pl[3][4];
+            split3(gsrc[gI].x, pl[0][0], pl[1][0], pl[2][0]);
+            split3(gsrc[gI].y, pl[0][1], pl[1][1], pl[2][1]);
+            split3(gsrc[gI].z, pl[0][2], pl[1][2], pl[2][2]);
+            split3(gsrc[gI].w, pl[0][3], pl[1][3], pl[2][3]);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              uint2 ov;
+              ov.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+              ov.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+              *reinterpret_cast<uint2*>(dap + (size_t)p * dap_plane + row[n] * 4 * H + (size_t)gI * H + ucol[n]) = ov;
+            }
           }
         }
       }
       // publish da_t (barrier 2k+1)
+      if (et == 0) LP_STAMP(t, 2);
       fence_proxy_async();
       named_bar_sync(1, LP_EPI_THREADS);
-      if (et == 0) { __threadfence(); grid_arrive(counter); }
+      if (et == 0) { LP_STAMP(t, 3); __threadfence(); grid_arrive(counter); LP_STAMP(t, 4); }
       if (t == 0) break;
       // ---- phase B epilogue: split-K partial of dh_{t-1} ----
       mbar_wait(tfull, k & 1u);
       tc_fence_after();
+      if (et == 0) LP_STAMP(t, 5);
       float acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), acc);
-      if (brow < B) {
-        float* dst = dh_zero + (size_t)brow * H + n0 + cc * 32;
+      if (brow < B) {                                          // one full 128 B line per thread, deterministic
+        float* dst = dh_part + (size_t)brow * H + n0 + cc * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, acc[j]);
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
       tc_fence_before();
       named_bar_sync(1, LP_EPI_THREADS);
-      if (et == 0) { __threadfence(); grid_arrive(counter); }      // barrier 2k+2
+      if (et == 0) { LP_STAMP(t, 6); __threadfence(); grid_arrive(counter); LP_STAMP(t, 7); }      // barrier 2k+2
     }
   }
   tc_fence_before();
@@ -506,8 +542,14 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
   long long dap_plane = (long long)T * B * 4 * H;
   int KBv = KB, Sv = S;
+  long long* dbg = nullptr;
+  static const bool want_dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
+  if (want_dbg) {
+    NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbg), (size_t)T * 8 * sizeof(long long)));
+    NVQA_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(long long), s));
+  }
   void* args[] = {&mapDA, &mapW, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &da, &dap, &dap_plane, &dhbuf, &dcbuf,
-                  &len, &T, &B, &H, &KBv, &Sv, &counter};
+                  &len, &T, &B, &H, &KBv, &Sv, &counter, &dbg};
   const void* fn = P == 1 ? (const void*)lstm_bwd_persistent_kernel<1> : (const void*)lstm_bwd_persistent_kernel<2>;
   static bool attr[3] = {false, false, false};
   if (!attr[P]) {
@@ -516,6 +558,18 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   }
   NVQA_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(LP_THREADS), args, smem, s));
   ++g_launches;
+  if (want_dbg) {
+    std::vector<long long> hbuf((size_t)T * 8);
+    NVQA_CUDA(cudaStreamSynchronize(s));
+    NVQA_CUDA(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    fprintf(stderr, "lstm_bwd_persistent timeline (cycles): t | bar2_passed phaseA_done A_alldone A_arrived mma_done B_alldone B_arrived | step\n");
+    for (int t = T - 2; t >= 1; --t) {
+      const long long* e = &hbuf[(size_t)t * 8];
+      fprintf(stderr, "%2d | %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", t, e[1] - e[0], e[2] - e[0], e[3] - e[0],
+              e[4] - e[0], e[5] - e[0], e[6] - e[0], e[7] - e[0], e[0] - hbuf[(size_t)(t + 1) * 8]);
+    }
+  }
   return 0;
 }
 
@@ -552,6 +606,10 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   int KBv = KB, Sv = S;
   long long* dbg = nullptr;
   static const bool want_dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
+  if (getenv("NVQA_POLL_NS")) {
+    int ns = atoi(getenv("NVQA_POLL_NS"));
+    NVQA_CUDA(cudaMemcpyToSymbol(g_poll_ns, &ns, sizeof(int)));
+  }
   if (want_dbg) {
     NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbg), (size_t)T * 8 * sizeof(long long)));
     NVQA_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(long long), s));
@@ -570,7 +628,7 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
     NVQA_CUDA(cudaStreamSynchronize(s));
     NVQA_CUDA(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(dbg);
-    fprintf(stderr, "lstm_fwd_persistent timeline (cycles): t | wait_bar tma_issued first_data mma_done epi_start epi_stored arrived | step\n");
+    fprintf(stderr, "lstm_fwd_persistent timeline (cycles): t | wait_bar epi_alldone first_data mma_done epi_start epi_stored arrived | step\n");
     for (int t = 1; t < T; ++t) {
       const long long* e = &hbuf[(size_t)t * 8];
       fprintf(stderr, "%2d | %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", t, e[1] - e[0], e[2] - e[0], e[3] - e[0],

@@ -18,7 +18,7 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
 // All T steps of one layer's backward recurrence (see lstm_persistent.cu).
 //   gates [T][B][4H] post-activation, c [(T+1)][B][H]; dh0/dc0 (leading dim ld0): d(final state) of this layer;
 //   dh_above [T][B][H]: dX of the layer above (masked by its input Dropout) or nullptr;
-//   out: da [T*B][4H] fp32 and dap [P][T*B][4H] bf16 planes; scratch dhbuf [2][B][H], dcbuf [B][H].
+//   out: da [T*B][4H] fp32 and dap [P][T*B][4H] bf16 planes; scratch dhbuf [2][4][B][H], dcbuf [B][H].
 int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
                         const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* da,
                         __nv_bfloat16* dap, float* dhbuf, float* dcbuf, const int32_t* len, int T, int B, int H,

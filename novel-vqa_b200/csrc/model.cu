@@ -32,9 +32,11 @@ using namespace nvqa;
 struct LayerPtrs { float *Wi, *bi, *Wh, *bh; };
 
 // live per-kernel-class timing with CUDA events on the model's stream (bench.py's roofline leg)
-enum GemmCat { CAT_INPROJ = 0, CAT_REC_FWD, CAT_HEAD_FWD, CAT_HEAD_BWD, CAT_REC_BWD, CAT_WGRAD, CAT_DGRAD, CAT_OTHER, CAT_COUNT };
-static const char* kCatName[CAT_COUNT] = {"lstm_inproj_gemm", "lstm_recurrent_fwd_gemm", "head_fwd_gemm", "head_bwd_gemm",
-                                          "lstm_recurrent_bwd_gemm", "lstm_wgrad_gemm", "lstm_dgrad_gemm", "other_gemm"};
+enum GemmCat { CAT_INPROJ = 0, CAT_REC_FWD, CAT_HEAD_FWD, CAT_HEAD_BWD, CAT_REC_BWD, CAT_WGRAD, CAT_DGRAD, CAT_OTHER,
+               CAT_PW_FWD, CAT_PW_BWD, CAT_OPT, CAT_COUNT };
+static const char* kCatName[CAT_COUNT] = {"lstm_inproj_gemm", "lstm_recurrent_fwd", "head_fwd_gemm", "head_bwd_gemm",
+                                          "lstm_recurrent_bwd", "lstm_wgrad_gemm", "lstm_dgrad_gemm", "other_gemm",
+                                          "pointwise_fwd", "pointwise_bwd", "clamp_rmsprop"};
 struct ProfCat {
   double ms = 0, flops = 0;
   int64_t launches = 0;
@@ -63,10 +65,12 @@ struct nvqa_model {
   float *da = nullptr, *dxbuf = nullptr, *dh_carry = nullptr, *dc_carry = nullptr;
   __nv_bfloat16* hp[4] = {};        // bf16 planes of h per layer [P][(T+1)B][H] (persistent recurrent kernels)
   __nv_bfloat16* dap = nullptr;     // bf16 planes of da [P][T*B][4H] (persistent backward kernel)
-  float* dhbuf = nullptr;           // [2][B][H] split-K accumulator of dh
+  float* dhbuf = nullptr;           // [2][4][B][H] split-K partials of dh
   unsigned int* grid_counter = nullptr;
   int planes = 0;                   // bf16 planes per operand of the tensor-core modes (0 = SIMT)
   bool use_persistent = true;
+  bool hp_valid[4] = {false, false, false, false};   // hp[l] holds this step's h planes (persistent forward ran)
+  bool dap_valid = false;                            // dap holds the current layer's da planes
   // batch
   const int32_t *q = nullptr, *len = nullptr, *labels = nullptr;
   const float* fc7 = nullptr;
@@ -107,6 +111,22 @@ static Drop make_drop(const nvqa_model* m, const float* mask, uint32_t stream) {
 static int gemm_raw(nvqa_model* m, bool ak, bool bk, int M, int N, int K, const float* A, int lda, const float* B,
                     int ldb, float* C, int ldc, bool beta, const float* b0, const float* b1);
 
+// event bracket around any stretch of work on the model's stream (no-ops unless profiling)
+struct ProfScope {
+  nvqa_model* m; int cat; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(nvqa_model* m_, int cat_, double flops) : m(m_), cat(cat_) {
+    if (!m->profiling) return;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, m->stream);
+    m->prof[cat].flops += flops; m->prof[cat].launches += 1;
+  }
+  ~ProfScope() {
+    if (!e0) return;
+    cudaEventRecord(e1, m->stream);
+    m->prof[cat].pending.emplace_back(e0, e1);
+  }
+};
+
 static int gemm(nvqa_model* m, int cat, bool ak, bool bk, int M, int N, int K, const float* A, int lda, const float* B,
                 int ldb, float* C, int ldc, bool beta, const float* b0 = nullptr, const float* b1 = nullptr) {
   if (!m->profiling) return gemm_raw(m, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1);
@@ -139,6 +159,24 @@ static int gemm_raw(nvqa_model* m, bool ak, bool bk, int M, int N, int K, const 
   }
   set_error("unknown precision");
   return 1;
+}
+
+// tensor-core GEMM whose operands may be ready-made bf16 planes (written by the persistent LSTM kernels)
+static int gemm_ops(nvqa_model* m, int cat, const UmmaOperand& A, const UmmaOperand& B, int M, int N, int K, float* C,
+                    int ldc, bool beta, const float* b0 = nullptr, const float* b1 = nullptr) {
+  ProfScope ps(m, cat, 2.0 * M * N * K);
+  return umma_gemm_ops(m->stream, m->planes, A, B, M, N, K, C, ldc, beta, b0, b1, m->ws);
+}
+static UmmaOperand op_f32(const nvqa_model* m, const float* src, int ld, bool kmajor) {
+  UmmaOperand o;
+  o.src = src; o.ld = ld; o.kmajor = kmajor;
+  o.is_static = src >= m->params && src < m->params + m->P;
+  return o;
+}
+static UmmaOperand op_planes(const __nv_bfloat16* planes, int plane_rows, int pitch, int row_offset, bool kmajor) {
+  UmmaOperand o;
+  o.planes = planes; o.plane_rows = plane_rows; o.pitch = pitch; o.row_offset = row_offset; o.kmajor = kmajor;
+  return o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -286,7 +324,7 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   }
   if (m->planes) {
     NVQA_TRY(dallocT(m, &m->dap, (size_t)m->planes * N * 4 * H));
-    NVQA_TRY(dallocT(m, &m->dhbuf, (size_t)2 * B * H));
+    NVQA_TRY(dallocT(m, &m->dhbuf, (size_t)2 * 4 * B * H));
   }
   if (getenv("NVQA_NO_PERSISTENT")) m->use_persistent = false;
   if (cfg->precision != NVQA_PREC_FP32_SIMT) {
@@ -294,7 +332,7 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
     // static region: every weight matrix in both orientations
     size_t elems = (size_t)(N + 64) * 4 * H + (size_t)(N + 64) * (H > E ? H : E) + (size_t)(B + 64) * (I + S + 2 * C);
     size_t stat = (size_t)(m->n_blk[0] + m->n_blk[2]) * 2 * 6 + (16 << 20);
-    NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (16 << 20), stat));
+    NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (96 << 20), stat));
   }
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
   return 0;
@@ -431,7 +469,10 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   const int64_t BH = (int64_t)B * H;
   cudaStream_t s = m->stream;
   // embedding_net_q:forward   (:300)
-  NVQA_TRY(embed_fwd(s, m->q, m->len, m->WeT, m->be, m->y, make_drop(m, m->mk_emb, STREAM_EMB), B, T, E, c.V));
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(embed_fwd(s, m->q, m->len, m->WeT, m->be, m->y, make_drop(m, m->mk_emb, STREAM_EMB), B, T, E, c.V));
+  }
   // rnn_forward (:303), layer-major
   for (int l = 0; l < L; ++l) {
     const float* X = l == 0 ? m->y : m->xdrop[l];
@@ -440,16 +481,20 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
                   m->lw[l].bh));
     if (m->planes && m->use_persistent) {
       // K4: all T steps in one persistent cooperative kernel (W_hh slice resident in shared memory)
+      ProfScope ps(m, CAT_REC_FWD, 2.0 * (T - 1) * B * 4.0 * H * H);
       int rc = lstm_fwd_persistent(s, m->ws, m->planes, m->lw[l].Wh, m->pre[l], m->c[l], m->h[l], m->hp[l],
                                    l + 1 < L ? m->xdrop[l + 1] : nullptr, m->len, lstm_drop(m, l), T, B, H,
                                    m->grid_counter);
       if (rc > 0) return rc;
+      m->hp_valid[l] = rc == 0;
       if (rc == 0) continue;
     }
+    m->hp_valid[l] = false;
     for (int t = 0; t < T; ++t) {
       float* pre_t = m->pre[l] + (int64_t)t * B * 4 * H;
       if (t > 0)   // h_0 == 0: the recurrent term of the first step vanishes
         NVQA_TRY(gemm(m, CAT_REC_FWD, true, true, B, 4 * H, H, m->h[l] + t * BH, H, m->lw[l].Wh, H, pre_t, 4 * H, true));
+      ProfScope ps(m, CAT_PW_FWD, 0);
       NVQA_TRY(lstm_gates_fwd(s, pre_t, m->c[l] + t * BH, H, m->c[l] + (t + 1) * BH, m->h[l] + (t + 1) * BH, H,
                               l + 1 < L ? m->xdrop[l + 1] + t * BH : nullptr, m->len, lstm_drop(m, l), t, T, B, H));
     }
@@ -458,16 +503,25 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   const float* cf[4];
   const float* hf[4];
   for (int l = 0; l < L; ++l) { cf[l] = m->c[l] + T * BH; hf[l] = m->h[l] + T * BH; }
-  NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L));
-  NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), B, c.I, c.img_norm));
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L));
+    NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), B, c.I, c.img_norm));
+  }
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
-  NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C));
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C));
+  }
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.O, c.C, m->zd, c.C, m->Wc, c.C, m->scores, c.O, false, m->bc));
   // criterion forward/backward (:308-310) + torch.max (004_eval_model.lua:233)
-  NVQA_TRY(softmax_ce(s, m->scores, m->labels, m->labels ? m->dscores : nullptr, m->rowloss, m->argmax, B, c.O,
-                      1.0f / (float)B));
-  if (m->labels) NVQA_TRY(loss_reduce(s, m->rowloss, m->loss, B));
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(softmax_ce(s, m->scores, m->labels, m->labels ? m->dscores : nullptr, m->rowloss, m->argmax, B, c.O,
+                        1.0f / (float)B));
+    if (m->labels) NVQA_TRY(loss_reduce(s, m->rowloss, m->loss, B));
+  }
   m->fwd_done = true;
   return 0;
 }
@@ -519,11 +573,13 @@ static int backward_lstm(nvqa_model* m) {
     int rc = -1;
     if (m->planes && m->use_persistent) {
       // K9: the whole backward recurrence of this layer in one persistent cooperative kernel
+      ProfScope ps(m, CAT_REC_BWD, 2.0 * (T - 1) * B * 4.0 * H * H);
       rc = lstm_bwd_persistent(s, m->ws, m->planes, m->lw[l].Wh, m->pre[l], m->c[l], dh_in, dc_in, ld,
                                l + 1 < L ? m->dxbuf : nullptr, lstm_drop(m, l), m->da, m->dap, m->dhbuf, m->dc_carry,
                                m->len, T, B, H, m->grid_counter);
       if (rc > 0) return rc;
     }
+    m->dap_valid = rc == 0;
     for (int t = T - 1; t >= 0 && rc != 0; --t) {
       NVQA_TRY(lstm_gates_bwd(s, m->pre[l] + (int64_t)t * B * 4 * H, m->c[l] + t * BH, m->c[l] + (t + 1) * BH, dh_in, ld,
                               l + 1 < L ? m->dxbuf + t * BH : nullptr, dc_in, ld, m->da + (int64_t)t * B * 4 * H,
@@ -538,11 +594,26 @@ static int backward_lstm(nvqa_model* m) {
     NVQA_CUDA(cudaMemsetAsync(m->lg[l].bi, 0, (size_t)4 * H * 4, s));
     NVQA_CUDA(cudaMemsetAsync(m->lg[l].bh, 0, (size_t)4 * H * 4, s));
     // sum over timestep clones of accGradParameters (:323-326) as one GEMM over all (t,b) rows
-    NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, in, T * B, m->da, 4 * H, X, in, m->lg[l].Wi, in, false));
-    NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, H, T * B, m->da, 4 * H, m->h[l], H, m->lg[l].Wh, H, false));
-    NVQA_TRY(colsum(s, m->da, T * B, 4 * H, 4 * H, m->lg[l].bi, m->lg[l].bh));
+    if (m->dap_valid) {
+      // da (and h_prev) already exist as bf16 planes: no split passes, the GEMMs read them through MN-major TMA maps
+      UmmaOperand da_mn = op_planes(m->dap, T * B, 4 * H, 0, false);
+      NVQA_TRY(gemm_ops(m, CAT_WGRAD, da_mn, op_f32(m, X, in, false), 4 * H, in, T * B, m->lg[l].Wi, in, false));
+      UmmaOperand hprev = m->hp_valid[l] ? op_planes(m->hp[l], (T + 1) * B, H, 0, false) : op_f32(m, m->h[l], H, false);
+      NVQA_TRY(gemm_ops(m, CAT_WGRAD, da_mn, hprev, 4 * H, H, T * B, m->lg[l].Wh, H, false));
+    } else {
+      NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, in, T * B, m->da, 4 * H, X, in, m->lg[l].Wi, in, false));
+      NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, H, T * B, m->da, 4 * H, m->h[l], H, m->lg[l].Wh, H, false));
+    }
+    {
+      ProfScope ps(m, CAT_PW_BWD, 0);
+      NVQA_TRY(colsum(s, m->da, T * B, 4 * H, 4 * H, m->lg[l].bi, m->lg[l].bh));
+    }
     // dX = da . Wi  (layer l-1's dh contribution, or the embedding gradient for l = 0)
-    NVQA_TRY(gemm(m, CAT_DGRAD, true, false, T * B, in, 4 * H, m->da, 4 * H, m->lw[l].Wi, in, m->dxbuf, in, false));
+    if (m->dap_valid)
+      NVQA_TRY(gemm_ops(m, CAT_DGRAD, op_planes(m->dap, T * B, 4 * H, 0, true), op_f32(m, m->lw[l].Wi, in, false), T * B, in,
+                        4 * H, m->dxbuf, in, false));
+    else
+      NVQA_TRY(gemm(m, CAT_DGRAD, true, false, T * B, in, 4 * H, m->da, 4 * H, m->lw[l].Wi, in, m->dxbuf, in, false));
   }
   return 0;
 }
@@ -550,6 +621,7 @@ static int backward_lstm(nvqa_model* m) {
 static int backward_embed(nvqa_model* m) {
   const nvqa_config& c = m->cfg;
   cudaStream_t s = m->stream;
+  ProfScope ps(m, CAT_PW_BWD, 0);
   NVQA_CUDA(cudaMemsetAsync(m->gWeT, 0, (size_t)m->n_blk[1] * 4, s));
   NVQA_TRY(embed_bwd(s, m->q, m->len, m->y, m->dxbuf, m->gWeT, make_drop(m, m->mk_emb, STREAM_EMB), m->B, c.T, c.E, c.V));
   NVQA_TRY(colsum(s, m->dxbuf, c.T * m->B, c.E, c.E, m->gbe, nullptr));
@@ -570,6 +642,7 @@ extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps
   NVQA_CHECK(m, "null model");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   umma_workspace_invalidate(m->ws);     // the weights change: their cached bf16 planes are stale
+  ProfScope ps(m, CAT_OPT, 0);
   return clamp_rmsprop(m->stream, m->params, m->grads, m->rms, m->P, lr, alpha, eps, wd, clamp, gscale);
 }
 

@@ -25,8 +25,10 @@ struct PlaneKeyHash {
   }
 };
 struct MapKey {
-  const void* planes; int rows, Kp, P, box;
-  bool operator==(const MapKey& o) const { return planes == o.planes && rows == o.rows && Kp == o.Kp && P == o.P && box == o.box; }
+  const void* planes; int rows, Kp, P, box; long long plane_stride;
+  bool operator==(const MapKey& o) const {
+    return planes == o.planes && rows == o.rows && Kp == o.Kp && P == o.P && box == o.box && plane_stride == o.plane_stride;
+  }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
@@ -51,6 +53,21 @@ struct UmmaWorkspace {
 int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int cols, int ld,
                    bool is_static, __nv_bfloat16** out, int* pitch_out);
 // tensor map over planes [P][rows][pitch]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
-int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int pitch, int P, int box_rows, CUtensorMap* out);
+// (rows = bound of the row coordinate; plane_stride in elements, 0 = rows * pitch)
+int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int pitch, int P, int box_rows, CUtensorMap* out,
+            long long plane_stride = 0);
+
+// A GEMM operand: either an fp32 row-major source (split into planes by the engine) or planes made upstream.
+struct UmmaOperand {
+  const float* src = nullptr;             // fp32 [rows x cols], leading dimension ld
+  int ld = 0;
+  bool is_static = false;                 // weight: cache the planes until umma_workspace_invalidate()
+  const __nv_bfloat16* planes = nullptr;  // ready-made planes [P][plane_rows][pitch] ...
+  int plane_rows = 0, pitch = 0;
+  int row_offset = 0;                     // ... of which this operand starts at row row_offset
+  bool kmajor = true;                     // contraction index is the contiguous one
+};
+int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOperand& B, int M, int N, int K, float* C,
+                  int ldc, bool beta, const float* bias0, const float* bias1, UmmaWorkspace* ws);
 
 }  // namespace nvqa

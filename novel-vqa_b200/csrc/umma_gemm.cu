@@ -47,7 +47,7 @@ template <int BN, int P, bool AMN, bool BMN>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N,
                  int K, float* __restrict__ C, int ldc, int beta, const float* __restrict__ bias0,
-                 const float* __restrict__ bias1) {
+                 const float* __restrict__ bias1, int a_row0, int b_row0, int kb_per_split, long long c_split_stride) {
   using Cfg = UgCfg<BN, P>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -61,7 +61,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * UG_BM, n0 = blockIdx.x * BN;
-  const int nkb = (K + UG_BK - 1) / UG_BK;
+  const int nkb_all = (K + UG_BK - 1) / UG_BK;
+  const int kb0 = blockIdx.z * kb_per_split;                          // split-K: this CTA's k-block range
+  const int nkb = min(nkb_all, kb0 + kb_per_split) - kb0;
+  C += (size_t)blockIdx.z * c_split_stride;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -94,21 +97,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           if (!AMN) {
-            tma_load_3d(sa + p * Cfg::A_PLANE, &mapA, full0 + 8 * s, kb * UG_BK, m0, p);
+            tma_load_3d(sa + p * Cfg::A_PLANE, &mapA, full0 + 8 * s, (kb0 + kb) * UG_BK, a_row0 + m0, p);
           } else {
 #pragma unroll
             for (int c = 0; c < UG_BM / 64; ++c)
-              tma_load_3d(sa + p * Cfg::A_PLANE + c * 8192, &mapA, full0 + 8 * s, m0 + 64 * c, kb * UG_BK, p);
+              tma_load_3d(sa + p * Cfg::A_PLANE + c * 8192, &mapA, full0 + 8 * s, m0 + 64 * c,
+                          a_row0 + (kb0 + kb) * UG_BK, p);
           }
         }
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           if (!BMN) {
-            tma_load_3d(sb + p * Cfg::B_PLANE, &mapB, full0 + 8 * s, kb * UG_BK, n0, p);
+            tma_load_3d(sb + p * Cfg::B_PLANE, &mapB, full0 + 8 * s, (kb0 + kb) * UG_BK, b_row0 + n0, p);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_3d(sb + p * Cfg::B_PLANE + c * 8192, &mapB, full0 + 8 * s, n0 + 64 * c, kb * UG_BK, p);
+              tma_load_3d(sb + p * Cfg::B_PLANE + c * 8192, &mapB, full0 + 8 * s, n0 + 64 * c,
+                          b_row0 + (kb0 + kb) * UG_BK, p);
           }
         }
       }
@@ -308,14 +313,16 @@ int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, i
 }
 
 // tensor map over planes [P][rows][colsp]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
-int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, int P, int box_rows, CUtensorMap* out) {
-  MapKey key{planes, rows, Kp, P, box_rows};
+int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, int P, int box_rows, CUtensorMap* out,
+            long long plane_stride) {
+  if (plane_stride <= 0) plane_stride = (long long)rows * Kp;
+  MapKey key{planes, rows, Kp, P, box_rows, plane_stride};
   auto it = ws->maps.find(key);
   if (it != ws->maps.end()) { *out = it->second; return 0; }
   EncodeTiledFn enc = get_encode();
   NVQA_CHECK(enc, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)P};
-  cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)plane_stride * 2};
   cuuint32_t box[3] = {(cuuint32_t)UG_BK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
@@ -332,9 +339,14 @@ int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, in
   return 0;
 }
 
+struct UgLaunch {
+  int a_row0 = 0, b_row0 = 0, splits = 1, kb_per_split = 1 << 30;
+  long long c_split_stride = 0;
+};
+
 template <int BN, int P, bool AMN, bool BMN>
 static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, float* C,
-                       int ldc, bool beta, const float* b0, const float* b1) {
+                       int ldc, bool beta, const float* b0, const float* b1, const UgLaunch& L) {
   using Cfg = UgCfg<BN, P>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -342,53 +354,131 @@ static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap&
                                    Cfg::SMEM));
     attr_set = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, UG_BM));
-  umma_gemm_kernel<BN, P, AMN, BMN><<<grid, UG_THREADS, Cfg::SMEM, s>>>(ma, mb, M, N, K, C, ldc, beta ? 1 : 0, b0, b1);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, UG_BM), L.splits);
+  umma_gemm_kernel<BN, P, AMN, BMN><<<grid, UG_THREADS, Cfg::SMEM, s>>>(ma, mb, M, N, K, C, ldc, beta ? 1 : 0, b0, b1,
+                                                                        L.a_row0, L.b_row0, L.kb_per_split,
+                                                                        L.c_split_stride);
   NVQA_LAUNCHED();
   return 0;
 }
 
 template <int BN, int P>
 static int launch_umma_major(bool amn, bool bmn, cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, int M,
-                             int N, int K, float* C, int ldc, bool beta, const float* b0, const float* b1) {
-  if (!amn && !bmn) return launch_umma<BN, P, false, false>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1);
-  if (!amn && bmn) return launch_umma<BN, P, false, true>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1);
-  if (amn && !bmn) return launch_umma<BN, P, true, false>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1);
-  return launch_umma<BN, P, true, true>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1);
+                             int N, int K, float* C, int ldc, bool beta, const float* b0, const float* b1,
+                             const UgLaunch& L) {
+  if (!amn && !bmn) return launch_umma<BN, P, false, false>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1, L);
+  if (!amn && bmn) return launch_umma<BN, P, false, true>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1, L);
+  if (amn && !bmn) return launch_umma<BN, P, true, false>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1, L);
+  return launch_umma<BN, P, true, true>(s, ma, mb, M, N, K, C, ldc, beta, b0, b1, L);
+}
+
+// C[m][n] = (beta ? C : 0) + sum_z part[z][m][n] + bias0[n] + bias1[n]   (fixed summation order: deterministic)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, int splits, long long stride, int M, int N, int ldp,
+                     float* __restrict__ C, int ldc, int beta, const float* __restrict__ bias0,
+                     const float* __restrict__ bias1) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int n = (int)(i % N);
+  const long long m = i / N;
+  float acc = 0.f;
+  for (int z = 0; z < splits; ++z) acc += part[(size_t)z * stride + m * ldp + n];
+  if (bias0) acc += bias0[n];
+  if (bias1) acc += bias1[n];
+  float* dst = C + m * ldc + n;
+  *dst = (beta ? *dst : 0.f) + acc;
+}
+
+// operand = fp32 source to be split into planes here, or ready-made planes produced by an upstream kernel
+static int resolve_operand(UmmaWorkspace* ws, cudaStream_t s, int P, const UmmaOperand& op, int rows, int cols,
+                           const __nv_bfloat16** planes, int* pitch, long long* plane_stride, int* row0, int* bound) {
+  if (op.planes) {
+    *planes = op.planes; *pitch = op.pitch; *plane_stride = (long long)op.plane_rows * op.pitch;
+    *row0 = op.row_offset; *bound = op.row_offset + rows;
+    return 0;
+  }
+  __nv_bfloat16* p = nullptr;
+  NVQA_TRY(prepare_planes(ws, s, P, op.src, rows, cols, op.ld, op.is_static, &p, pitch));
+  *planes = p; *plane_stride = (long long)rows * *pitch; *row0 = 0; *bound = rows;
+  return 0;
+}
+
+int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOperand& B, int M, int N, int K, float* C,
+                  int ldc, bool beta, const float* bias0, const float* bias1, UmmaWorkspace* ws) {
+  NVQA_CHECK(ws, "umma_gemm: no workspace");
+  NVQA_CHECK(planes >= 1 && planes <= 3, "umma_gemm: planes must be 1..3");
+  if (M <= 0 || N <= 0) return 0;
+  ws->trans_top = 0;                      // stream order makes the previous GEMM's transient planes reusable
+  // planes keep the source's row-major shape: [M x K] / [N x K] when K-major, [K x M] / [K x N] when MN-major
+  const __nv_bfloat16 *pa = nullptr, *pb = nullptr;
+  int pitch_a = 0, pitch_b = 0, bound_a = 0, bound_b = 0;
+  long long ps_a = 0, ps_b = 0;
+  UgLaunch L;
+  NVQA_TRY(resolve_operand(ws, s, planes, A, A.kmajor ? M : K, A.kmajor ? K : M, &pa, &pitch_a, &ps_a, &L.a_row0, &bound_a));
+  NVQA_TRY(resolve_operand(ws, s, planes, B, B.kmajor ? N : K, B.kmajor ? K : N, &pb, &pitch_b, &ps_b, &L.b_row0, &bound_b));
+  // tile shape: the widest N tile that still gives every SM a CTA; split K when the grid would be too small
+  int num_sms = 148;
+  const int mt = ceil_div(M, UG_BM);
+  int BN = 64;
+  if (planes <= 2 && N >= 256 && (long)mt * ceil_div(N, 256) >= num_sms / 2) BN = 256;
+  else if ((long)mt * ceil_div(N, 128) >= num_sms / 2) BN = 128;
+  else if (planes <= 2 && N >= 256 && K >= 2048) BN = 256;        // few tiles but a long K: wide tiles + split-K
+  else if (N >= 128 && K >= 2048) BN = 128;
+  const int tiles = mt * ceil_div(N, BN);
+  const int nkb = ceil_div(K, UG_BK);
+  int splits = 1;
+  if (tiles < num_sms / 2 && nkb >= 16) {
+    splits = num_sms / tiles;
+    if (splits > 8) splits = 8;
+    if (splits > nkb / 8) splits = nkb / 8;
+    if (splits < 1) splits = 1;
+  }
+  float* Cout = C;
+  int ldo = ldc;
+  bool beta_k = beta;
+  const float *b0k = bias0, *b1k = bias1;
+  if (splits > 1) {
+    L.kb_per_split = ceil_div(nkb, splits);
+    splits = ceil_div(nkb, L.kb_per_split);                       // no empty split
+    L.splits = splits;
+    const size_t need = (size_t)splits * M * N * sizeof(float);
+    NVQA_CHECK(ws->static_bytes + ws->trans_top + need <= ws->bytes, "umma workspace too small for split-K partials");
+    Cout = reinterpret_cast<float*>(ws->base + ws->static_bytes + ws->trans_top);
+    ws->trans_top += (need + 1023) & ~(size_t)1023;
+    ldo = N;
+    L.c_split_stride = (long long)M * N;
+    beta_k = false; b0k = b1k = nullptr;
+  }
+  CUtensorMap ma, mb;
+  NVQA_TRY(get_map(ws, pa, bound_a, pitch_a, planes, A.kmajor ? UG_BM : 64, &ma, ps_a));
+  NVQA_TRY(get_map(ws, pb, bound_b, pitch_b, planes, B.kmajor ? BN : 64, &mb, ps_b));
+  int rc = 1;
+#define NVQA_UG(BN_, P_) \
+  rc = launch_umma_major<BN_, P_>(!A.kmajor, !B.kmajor, s, ma, mb, M, N, K, Cout, ldo, beta_k, b0k, b1k, L)
+  if (BN == 256) {
+    if (planes == 1) NVQA_UG(256, 1); else NVQA_UG(256, 2);
+  } else if (BN == 128) {
+    if (planes == 1) NVQA_UG(128, 1); else if (planes == 2) NVQA_UG(128, 2); else NVQA_UG(128, 3);
+  } else {
+    if (planes == 1) NVQA_UG(64, 1); else if (planes == 2) NVQA_UG(64, 2); else NVQA_UG(64, 3);
+  }
+#undef NVQA_UG
+  if (rc) return rc;
+  if (splits > 1) {
+    splitk_reduce_kernel<<<ceil_div((long long)M * N, 256), 256, 0, s>>>(Cout, splits, L.c_split_stride, M, N, N, C, ldc,
+                                                                        beta ? 1 : 0, bias0, bias1);
+    NVQA_LAUNCHED();
+  }
+  return 0;
 }
 
 int umma_gemm(cudaStream_t s, int planes, bool a_kmajor, bool b_kmajor, int M, int N, int K, const float* A, int lda,
               const float* B, int ldb, float* C, int ldc, bool beta, const float* bias0, const float* bias1,
               UmmaWorkspace* ws, bool a_static, bool b_static) {
-  NVQA_CHECK(ws, "umma_gemm: no workspace");
-  NVQA_CHECK(planes >= 1 && planes <= 3, "umma_gemm: planes must be 1..3");
-  if (M <= 0 || N <= 0) return 0;
-  ws->trans_top = 0;                      // stream order makes the previous GEMM's transient planes reusable
-  __nv_bfloat16 *pa = nullptr, *pb = nullptr;
-  int Kpa = 0, Kpb = 0;
-  // planes keep the source's row-major shape: [M x K] / [N x K] when K-major, [K x M] / [K x N] when MN-major
-  int pitch_a = 0, pitch_b = 0;
-  NVQA_TRY(prepare_planes(ws, s, planes, A, a_kmajor ? M : K, a_kmajor ? K : M, lda, a_static, &pa, &pitch_a));
-  NVQA_TRY(prepare_planes(ws, s, planes, B, b_kmajor ? N : K, b_kmajor ? K : N, ldb, b_static, &pb, &pitch_b));
-  (void)Kpa; (void)Kpb;
-  // 128 x 128 tiles when they fill the machine, else 128 x 64 for more CTAs
-  const long tiles128 = (long)ceil_div(M, UG_BM) * ceil_div(N, 128);
-  const int BN = tiles128 >= 148 ? 128 : 64;
-  CUtensorMap ma, mb;
-  NVQA_TRY(get_map(ws, pa, a_kmajor ? M : K, pitch_a, planes, a_kmajor ? UG_BM : 64, &ma));
-  NVQA_TRY(get_map(ws, pb, b_kmajor ? N : K, pitch_b, planes, b_kmajor ? BN : 64, &mb));
-#define NVQA_UG(BN_, P_) \
-  return launch_umma_major<BN_, P_>(!a_kmajor, !b_kmajor, s, ma, mb, M, N, K, C, ldc, beta, bias0, bias1)
-  if (BN == 128) {
-    if (planes == 1) NVQA_UG(128, 1);
-    if (planes == 2) NVQA_UG(128, 2);
-    NVQA_UG(128, 3);
-  } else {
-    if (planes == 1) NVQA_UG(64, 1);
-    if (planes == 2) NVQA_UG(64, 2);
-    NVQA_UG(64, 3);
-  }
-#undef NVQA_UG
+  UmmaOperand a, b;
+  a.src = A; a.ld = lda; a.kmajor = a_kmajor; a.is_static = a_static;
+  b.src = B; b.ld = ldb; b.kmajor = b_kmajor; b.is_static = b_static;
+  return umma_gemm_ops(s, planes, a, b, M, N, K, C, ldc, beta, bias0, bias1, ws);
 }
 
 }  // namespace nvqa
