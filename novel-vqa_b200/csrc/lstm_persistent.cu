@@ -13,6 +13,7 @@
 //           cell update -> gates, c_t, h_t (fp32), h_t as bf16 planes (next step's A operand, and the wgrad operand),
 //           Dropout(h_t) for the layer above -> grid barrier (one release-add per CTA, acquire-spin by the
 //           TMA producer thread only).
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -24,23 +25,35 @@ namespace nvqa {
 constexpr int LP_THREADS = 320;          // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 constexpr int LP_EPI_THREADS = 256;
 constexpr int LP_MAX_STAGES = 4;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// (debug) per-CTA wall-clock stamps at steps 10 and 11: dbg2[cta*4 + {0: barrier seen open t=10, 1: arrived t=10, 2: open t=11, 3: arrived t=11}]
+#define LP_GSTAMP(t_, k_) \
+  do { if (dbg && ((t_) == 10 || (t_) == 11)) dbg[T * 8 + (blockIdx.y * gridDim.x + blockIdx.x) * 4 + ((t_) - 10) * 2 + (k_)] = (long long)gtimer(); } while (0)
+#define LP_XSTAMP(t_, k_, v_) \
+  do { if (dbg && (t_) == 10) dbg[T * 8 + 1024 + (blockIdx.y * gridDim.x + blockIdx.x) * 4 + (k_)] = (long long)(v_); } while (0)
 #define LP_STAMP(t_, k_) \
   do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) dbg[(t_) * 8 + (k_)] = clock64(); } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// Grid-wide counter barrier (backward kernel).  See group_arrive / group_wait below for why the arrive is a blocking
+// atom.release and the poll an atom.acquire rather than plain loads + fences.
+__device__ int g_poll_ns = 64;
 __device__ __forceinline__ void grid_arrive(unsigned int* counter) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+  unsigned int old;
+  asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+  if (old == 0xFFFFFFFFu) __trap();
 }
-// one thread per CTA polls (relaxed loads with back-off so that 128 pollers do not starve the arriving atomics),
-// then a single acquire fence orders everything after the barrier
-__device__ int g_poll_ns = 40;
-__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int target) {
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int target) {
   long long t0 = clock64();
   while (true) {
     unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    asm volatile("atom.acquire.gpu.global.add.u32 %0, [%1], 0;" : "=r"(v) : "l"(counter) : "memory");
     if (v >= target) break;
     __nanosleep(g_poll_ns);
     if (clock64() - t0 > 4000000000LL) {
@@ -49,14 +62,65 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
       __trap();
     }
   }
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 // exp-based activations for the fused epilogue: ex2.approx + fast division, absolute error ~1e-7
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
-template <int P>
+// Flag barrier among the CTAs of one group (here: the CTAs that share a batch tile).  Each member publishes its step
+// count with a release store to its OWN word (no same-address atomic serialisation: measured 5 us of skew with a
+// single counter and 128 arrivals); one warp polls all members' words with coalesced relaxed loads.
+__device__ __forceinline__ void flag_arrive(unsigned int* flag, unsigned int value) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+// Group counter barrier.  Arrive = one release-add per CTA; the poller reads the counter WITH AN ATOMIC: plain (even
+// .acquire.gpu) loads were measured to observe a remote SM's store up to 4 us late on some SMs, atomics execute at the
+// line's home L2 slice and see it within ~0.3 us.
+// returns only after the add has been performed at L2 (the returned value is consumed), so that the caller can then
+// let other warps flood the memory pipeline without delaying the release
+__device__ __forceinline__ void group_arrive(unsigned int* ctr) {
+  unsigned int old;
+  asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+  if (old == 0xFFFFFFFFu) __trap();
+}
+__device__ __forceinline__ void group_wait(unsigned int* ctr, unsigned int target) {
+  long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    // acquire on the polling atomic itself: a trailing fence.acq_rel would also carry release semantics and was
+    // measured to wait ~4 us for the SM's queued (unrelated) epilogue stores to drain
+    asm volatile("atom.acquire.gpu.global.add.u32 %0, [%1], 0;" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= target) break;
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("lstm_persistent: group barrier timed out (block %d,%d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, v, target);
+      __trap();
+    }
+  }
+}
+// called by a full warp; returns when every member's flag >= target
+__device__ __forceinline__ void flag_wait_warp(const unsigned int* flags, int members, unsigned int target) {
+  const int lane = threadIdx.x & 31;
+  long long t0 = clock64();
+  while (true) {
+    bool ok = true;
+    for (int i = lane; i < members; i += 32) {
+      unsigned int v;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+      ok = ok && (v >= target);
+    }
+    if (__all_sync(0xffffffffu, ok)) break;
+    if (clock64() - t0 > 4000000000LL) {
+      if (lane == 0) printf("lstm_persistent: flag barrier timed out (block %d,%d,%d want %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, target);
+      __trap();
+    }
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  __syncwarp();
+}
+
+template <int P, int CL>
 __global__ void __launch_bounds__(LP_THREADS, 1)
 lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
                            float* __restrict__ pre, float* __restrict__ c, float* __restrict__ h,
@@ -85,7 +149,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      // with a cluster of CL CTAs sharing the A tile, a stage is free only when all CL consumers have released it
+      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CL); }
       mbar_init(wfull, 1);
       mbar_init(tfull, 1);
       fence_barrier_init();
@@ -95,11 +160,14 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();           // peers' barriers exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (lane 0 issues; the whole warp polls the batch tile's flags) =====
     if (lane == 0) {
       // resident W_hh slice: smem row (cc*32 + g*8 + j) <- W row g*H + u0 + 8*cc + j
       mbar_expect_tx(wfull, (uint32_t)KB * P * W_TILE);
@@ -109,24 +177,39 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
             for (int g = 0; g < 4; ++g)
               tma_load_3d(w0 + (uint32_t)(kb * P + p) * W_TILE + (uint32_t)(cc * 4 + g) * 1024, &mapW, wfull, kb * 64,
                           g * H + u0 + 8 * cc, p);
-      int it = 0;
-      for (int t = 0; t < T; ++t) {
-        LP_STAMP(t, 0);
-        if (t > 0) {
-          grid_wait(counter, (unsigned int)t * G);       // every CTA has published h_{t-1}
+    }
+    int it = 0;
+    for (int t = 0; t < T; ++t) {
+      if (t > 0) {
+        // h_{t-1} rows of THIS batch tile are complete once the gridDim.x CTAs sharing it have published step t
+        if (lane == 0) {
+          group_wait(counter + 32 * blockIdx.y, (unsigned int)t * gridDim.x);      // one counter (own 128 B line) per batch tile
           fence_proxy_async();
         }
+        __syncwarp();
+      }
+      if (lane == 0) {
         LP_STAMP(t, 1);
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
+        LP_GSTAMP(t, 0);
+        for (int kb = 0; kb < KB; ++kb) {
+          const int s = (it + kb) % S;
+          const uint32_t ph = (uint32_t)((it + kb) / S) & 1u;
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           mbar_expect_tx(full0 + 8 * s, P * A_PLANE);
 #pragma unroll
-          for (int p = 0; p < P; ++p)
-            tma_load_3d(a0 + (uint32_t)(s * P + p) * A_PLANE, &mapH, full0 + 8 * s, kb * 64, t * B + m0, p);
+          for (int p = 0; p < P; ++p) {
+            if (CL == 1) {
+              tma_load_3d(a0 + (uint32_t)(s * P + p) * A_PLANE, &mapH, full0 + 8 * s, kb * 64, t * B + m0, p);
+            } else {   // this CTA fetches rows [128/CL * rank, +128/CL) of the shared tile for the whole cluster
+              constexpr uint32_t SL = 128 / CL;
+              tma_load_3d_mc(a0 + (uint32_t)(s * P + p) * A_PLANE + crank * SL * 128, &mapH, full0 + 8 * s, kb * 64,
+                             t * B + m0 + (int)(crank * SL), p, kMask);
+            }
+          }
         }
       }
+      it += KB;
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -141,7 +224,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
           const uint32_t ph = (uint32_t)(it / S) & 1u;
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          if (kb == 0) LP_STAMP(t, 3);
+          if (kb == 0) { LP_STAMP(t, 3); LP_XSTAMP(t, 0, gtimer()); }
+          if (kb == KB - 1) { LP_STAMP(t, 0); LP_XSTAMP(t, 1, gtimer()); }   // last k-block's data has landed
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint64_t da[P], db[P];
@@ -156,10 +240,11 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
             }
             umma_f16(tmem_base, da[0], db[0], idesc, acc); acc = 1;
           }
-          umma_commit(empty0 + 8 * s);
+          if (CL == 1) umma_commit(empty0 + 8 * s); else umma_commit_mc(empty0 + 8 * s, kMask);
         }
         umma_commit(tfull);
         LP_STAMP(t, 4);
+        { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); LP_XSTAMP(t, 2, smid); }
       }
     }
   } else {
@@ -188,30 +273,62 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
       }
       mbar_wait(tfull, (uint32_t)t & 1u);
       tc_fence_after();
-      if (threadIdx.x == 64) LP_STAMP(t, 5);
+      if (threadIdx.x == 64) { LP_STAMP(t, 5); LP_XSTAMP(t, 3, gtimer()); }
       float acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), acc);
-      if (rowok) {
-        float gi[8], gf[8], go[8], gg[8], cn[8], hn[8];
-        if (active) {
-          const float* pi = reinterpret_cast<const float*>(&pv[0][0]);
-          const float* pf = reinterpret_cast<const float*>(&pv[1][0]);
-          const float* po = reinterpret_cast<const float*>(&pv[2][0]);
-          const float* pg = reinterpret_cast<const float*>(&pv[3][0]);
+      float gi[8], gf[8], go[8], gg[8], cn[8], hn[8];
+      if (active) {
+        const float* pi = reinterpret_cast<const float*>(&pv[0][0]);
+        const float* pf = reinterpret_cast<const float*>(&pv[1][0]);
+        const float* po = reinterpret_cast<const float*>(&pv[2][0]);
+        const float* pg = reinterpret_cast<const float*>(&pv[3][0]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            gi[j] = fast_sigmoid(acc[j] + pi[j]);
-            gf[j] = fast_sigmoid(acc[8 + j] + pf[j]);
-            go[j] = fast_sigmoid(acc[16 + j] + po[j]);
-            gg[j] = fast_tanh(acc[24 + j] + pg[j]);
-            cn[j] = gf[j] * ccarry[j] + gi[j] * gg[j];
-            hn[j] = go[j] * fast_tanh(cn[j]);
-            ccarry[j] = cn[j];
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { gi[j] = gf[j] = go[j] = gg[j] = cn[j] = hn[j] = 0.f; }
+        for (int j = 0; j < 8; ++j) {
+          gi[j] = fast_sigmoid(acc[j] + pi[j]);
+          gf[j] = fast_sigmoid(acc[8 + j] + pf[j]);
+          go[j] = fast_sigmoid(acc[16 + j] + po[j]);
+          gg[j] = fast_tanh(acc[24 + j] + pg[j]);
+          cn[j] = gf[j] * ccarry[j] + gi[j] * gg[j];
+          hn[j] = go[j] * fast_tanh(cn[j]);
+          ccarry[j] = cn[j];
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gi[j] = gf[j] = go[j] = gg[j] = cn[j] = hn[j] = 0.f; }
+      }
+      // (1) the only output the NEXT step depends on: h_t as bf16 planes, row (t+1)*B + b of [P][(T+1)B][H]
+      if (rowok) {
+        __nv_bfloat16 pl[3][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split3(hn[j], pl[0][j], pl[1][j], pl[2][j]);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          uint4 o;
+          o.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+          o.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+          o.z = (uint32_t)__bfloat16_as_ushort(pl[p][4]) | ((uint32_t)__bfloat16_as_ushort(pl[p][5]) << 16);
+          o.w = (uint32_t)__bfloat16_as_ushort(pl[p][6]) | ((uint32_t)__bfloat16_as_ushort(pl[p][7]) << 16);
+          *reinterpret_cast<uint4*>(hp + (size_t)p * hp_plane + rout * H + uo) = o;
+        }
+      }
+      // (2) publish it.  Every writer orders its generic-proxy stores before later async-proxy (TMA) reads; the CTA
+      // barrier then makes one thread's gpu-scope release cumulative over all.
+      if (threadIdx.x == 64) LP_STAMP(t, 6);
+      tc_fence_before();
+      fence_proxy_async();
+      named_bar_sync(1, LP_EPI_THREADS);
+      if (threadIdx.x == 64) {
+        LP_STAMP(t, 2);      // (debug) reuse slot 2: all epilogue warps done
+        group_arrive(counter + 32 * blockIdx.y);
+        LP_STAMP(t, 7);
+        LP_GSTAMP(t, 1);
+      }
+      // hold the other warps until the release is out: their stores / prefetch loads would otherwise sit in front of
+      // the membar in the SM's memory pipeline (measured: +3.4k cycles per step)
+      named_bar_sync(3, LP_EPI_THREADS);
+      // (3) everything only the backward pass needs goes out OFF the critical path, overlapping the grid barrier
+      // and the next step's TMA loads and MMAs
+      if (rowok) {
         float* gdst = pre + rin * 4 * H + uo;
 #define ST8(ptr, a)                                                                          \
         *reinterpret_cast<float4*>(ptr) = make_float4(a[0], a[1], a[2], a[3]);               \
@@ -227,39 +344,12 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
           ST8(xdrop + rin * H + uo, xd)
         }
 #undef ST8
-        // h_t as bf16 planes: row (t+1)*B + b of the [P][(T+1)B][H] plane array
-        __nv_bfloat16 pl[3][8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) split3(hn[j], pl[0][j], pl[1][j], pl[2][j]);
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          uint4 o;
-          o.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
-          o.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
-          o.z = (uint32_t)__bfloat16_as_ushort(pl[p][4]) | ((uint32_t)__bfloat16_as_ushort(pl[p][5]) << 16);
-          o.w = (uint32_t)__bfloat16_as_ushort(pl[p][6]) | ((uint32_t)__bfloat16_as_ushort(pl[p][7]) << 16);
-          *reinterpret_cast<uint4*>(hp + (size_t)p * hp_plane + rout * H + uo) = o;
-        }
       }
-      // publish: this CTA's slice of h_t is complete.  Every writer orders its generic-proxy stores before later
-      // async-proxy (TMA) reads; the CTA barrier then makes one thread's gpu-scope release cumulative over all.
-      if (threadIdx.x == 64) LP_STAMP(t, 6);
-      tc_fence_before();
-      fence_proxy_async();
-      named_bar_sync(1, LP_EPI_THREADS);
-      if (threadIdx.x == 64) {
-        LP_STAMP(t, 2);      // (debug) reuse slot 2: all epilogue warps done
-        __threadfence();
-        grid_arrive(counter);
-        LP_STAMP(t, 7);
-      }
-      // hold the other warps until the release is out: their prefetch loads for step t+1 would otherwise sit in
-      // front of the membar in the SM's memory pipeline (measured: +3.4k cycles per step)
-      named_bar_sync(3, LP_EPI_THREADS);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();           // no CTA leaves while a peer can still multicast into it / signal it
   if (warp == 1) tmem_dealloc(tmem_base, 64);
 }
 
@@ -273,7 +363,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
 //     B. dh_{t-1} += da_t[:, gate block] . W_hh[gate block, :]   with the CTA's [512 x 64] slice of W_hh RESIDENT
 //        in shared memory (MN-major B operand: no transposed weight copy); the four split-K partials go to a
 //        double-buffered [4][B][H] scratch and are summed (fixed order, deterministic) by the next phase A.
-template <int P>
+template <int P, int CL>
 __global__ void __launch_bounds__(LP_THREADS, 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
                            const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ dh0,
@@ -305,7 +395,8 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      // with a cluster of CL CTAs sharing the A tile, a stage is free only when all CL consumers have released it
+      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CL); }
       mbar_init(wfull, 1);
       mbar_init(tfull, 1);
       fence_barrier_init();
@@ -315,8 +406,11 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();           // peers' barriers exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -336,8 +430,15 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           mbar_expect_tx(full0 + 8 * s, P * A_PLANE);
 #pragma unroll
-          for (int p = 0; p < P; ++p)
-            tma_load_3d(a0 + (uint32_t)(s * P + p) * A_PLANE, &mapDA, full0 + 8 * s, k_base + kb * 64, t * B + m0, p);
+          for (int p = 0; p < P; ++p) {
+            if (CL == 1) {
+              tma_load_3d(a0 + (uint32_t)(s * P + p) * A_PLANE, &mapDA, full0 + 8 * s, k_base + kb * 64, t * B + m0, p);
+            } else {
+              constexpr uint32_t SL = 128 / CL;
+              tma_load_3d_mc(a0 + (uint32_t)(s * P + p) * A_PLANE + crank * SL * 128, &mapDA, full0 + 8 * s,
+                             k_base + kb * 64, t * B + m0 + (int)(crank * SL), p, kMask);
+            }
+          }
         }
       }
     }
@@ -368,7 +469,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
             }
             umma_f16(tmem_base, dA[0], dB[0], idesc, acc); acc = 1;
           }
-          umma_commit(empty0 + 8 * s);
+          if (CL == 1) umma_commit(empty0 + 8 * s); else umma_commit_mc(empty0 + 8 * s, kMask);
         }
         umma_commit(tfull);
       }
@@ -481,7 +582,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       if (et == 0) LP_STAMP(t, 2);
       fence_proxy_async();
       named_bar_sync(1, LP_EPI_THREADS);
-      if (et == 0) { LP_STAMP(t, 3); __threadfence(); grid_arrive(counter); LP_STAMP(t, 4); }
+      if (et == 0) { LP_STAMP(t, 3); grid_arrive(counter); LP_STAMP(t, 4); }
       if (t == 0) break;
       // ---- phase B epilogue: split-K partial of dh_{t-1} ----
       mbar_wait(tfull, k & 1u);
@@ -496,12 +597,37 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       }
       tc_fence_before();
       named_bar_sync(1, LP_EPI_THREADS);
-      if (et == 0) { LP_STAMP(t, 6); __threadfence(); grid_arrive(counter); LP_STAMP(t, 7); }      // barrier 2k+2
+      if (et == 0) { LP_STAMP(t, 6); grid_arrive(counter); LP_STAMP(t, 7); }      // barrier 2k+2
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();           // no CTA leaves while a peer can still multicast into it / signal it
   if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+// cooperative launch (all CTAs co-resident: the kernels spin on grid barriers), optionally with thread-block clusters
+static cudaError_t launch_coop(const void* fn, dim3 grid, int cluster_x, void** args, size_t smem, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(LP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attrs[2];
+  int n = 0;
+  attrs[n].id = cudaLaunchAttributeCooperative; attrs[n].val.cooperative = 1; ++n;
+  if (cluster_x > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = cluster_x; attrs[n].val.clusterDim.y = 1; attrs[n].val.clusterDim.z = 1; ++n;
+  }
+  cfg.attrs = attrs; cfg.numAttrs = n;
+  return cudaLaunchKernelExC(&cfg, fn, args);
+}
+static int g_cluster = -1;                    // A-tile multicast cluster size (NVQA_LSTM_CLUSTER=1 disables)
+static int cluster_pref() {
+  if (g_cluster < 0) {
+    const char* e = getenv("NVQA_LSTM_CLUSTER");
+    g_cluster = e ? atoi(e) : 1;   // measured on B200: multicast does not shorten the load phase (SM ingest-bound)
+    if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4 && g_cluster != 8) g_cluster = 1;
+  }
+  return g_cluster;
 }
 
 static int persistent_limits(int* num_sms, int* max_smem) {
@@ -538,7 +664,9 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   NVQA_TRY(prepare_planes(ws, s, P, Wh, 4 * H, H, H, true, &wp, &pitch));
   CUtensorMap mapW, mapDA;
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 64, &mapW));             // MN-major B: 64 k-rows x 64 columns
-  NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 128, &mapDA));
+  int CL = cluster_pref();
+  if ((int)grid.x % CL != 0) CL = 1;
+  NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 128 / CL, &mapDA));
   NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
   long long dap_plane = (long long)T * B * 4 * H;
   int KBv = KB, Sv = S;
@@ -550,13 +678,20 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   }
   void* args[] = {&mapDA, &mapW, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &da, &dap, &dap_plane, &dhbuf, &dcbuf,
                   &len, &T, &B, &H, &KBv, &Sv, &counter, &dbg};
-  const void* fn = P == 1 ? (const void*)lstm_bwd_persistent_kernel<1> : (const void*)lstm_bwd_persistent_kernel<2>;
-  static bool attr[3] = {false, false, false};
-  if (!attr[P]) {
-    NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr[P] = true;
+  const void* fn = nullptr;
+#define LP_PICK(P_, CL_) if (P == P_ && CL == CL_) fn = (const void*)lstm_bwd_persistent_kernel<P_, CL_>
+  LP_PICK(1, 1); LP_PICK(1, 2); LP_PICK(1, 4); LP_PICK(1, 8); LP_PICK(2, 1); LP_PICK(2, 2); LP_PICK(2, 4); LP_PICK(2, 8);
+#undef LP_PICK
+  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  if (CL > 4) NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaError_t le = launch_coop(fn, grid, CL, args, smem, s);
+  if (le != cudaSuccess && CL > 1) {          // clusters could not be made co-resident: fall back to unicast loads
+    (void)cudaGetLastError();
+    g_cluster = 1;
+    return lstm_bwd_persistent(s, ws, P, Wh, gates, c, dh0, dc0, ld0, dh_above, d, da, dap, dhbuf, dcbuf, len, T, B, H,
+                               counter);
   }
-  NVQA_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(LP_THREADS), args, smem, s));
+  NVQA_CUDA(le);
   ++g_launches;
   if (want_dbg) {
     std::vector<long long> hbuf((size_t)T * 8);
@@ -600,8 +735,10 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   NVQA_TRY(prepare_planes(ws, s, P, Wh, 4 * H, H, H, true, &wp, &pitch));
   CUtensorMap mapW, mapH;
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 8, &mapW));
-  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 128, &mapH));
-  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+  int CL = cluster_pref();
+  if ((int)grid.x % CL != 0) CL = 1;
+  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 128 / CL, &mapH));
+  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));      // one counter line per batch tile
   long long hp_plane = (long long)(T + 1) * B * H;
   int KBv = KB, Sv = S;
   long long* dbg = nullptr;
@@ -610,29 +747,75 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
     int ns = atoi(getenv("NVQA_POLL_NS"));
     NVQA_CUDA(cudaMemcpyToSymbol(g_poll_ns, &ns, sizeof(int)));
   }
+  const size_t dbg_n = (size_t)T * 8 + 1024 + 1024;
   if (want_dbg) {
-    NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbg), (size_t)T * 8 * sizeof(long long)));
-    NVQA_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(long long), s));
+    NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbg), dbg_n * sizeof(long long)));
+    NVQA_CUDA(cudaMemsetAsync(dbg, 0, dbg_n * sizeof(long long), s));
   }
   void* args[] = {&mapH, &mapW, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &Sv, &counter, &dbg};
-  const void* fn = P == 1 ? (const void*)lstm_fwd_persistent_kernel<1> : (const void*)lstm_fwd_persistent_kernel<2>;
-  static bool attr[3] = {false, false, false};
-  if (!attr[P]) {
-    NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr[P] = true;
+  const void* fn = nullptr;
+#define LP_PICK(P_, CL_) if (P == P_ && CL == CL_) fn = (const void*)lstm_fwd_persistent_kernel<P_, CL_>
+  LP_PICK(1, 1); LP_PICK(1, 2); LP_PICK(1, 4); LP_PICK(1, 8); LP_PICK(2, 1); LP_PICK(2, 2); LP_PICK(2, 4); LP_PICK(2, 8);
+#undef LP_PICK
+  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  if (CL > 4) NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaError_t le = launch_coop(fn, grid, CL, args, smem, s);
+  if (le != cudaSuccess && CL > 1) {          // clusters could not be made co-resident: fall back to unicast loads
+    (void)cudaGetLastError();
+    g_cluster = 1;
+    return lstm_fwd_persistent(s, ws, P, Wh, pre, c, h, hp, xdrop_next, len, d, T, B, H, counter);
   }
-  NVQA_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(LP_THREADS), args, smem, s));
+  NVQA_CUDA(le);
   ++g_launches;
   if (want_dbg) {   // per-step timeline of CTA (0,0) in SM cycles, relative to the step's first stamp
-    std::vector<long long> hbuf((size_t)T * 8);
+    std::vector<long long> hbuf(dbg_n);
     NVQA_CUDA(cudaStreamSynchronize(s));
     NVQA_CUDA(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(dbg);
-    fprintf(stderr, "lstm_fwd_persistent timeline (cycles): t | wait_bar epi_alldone first_data mma_done epi_start epi_stored arrived | step\n");
+    fprintf(stderr, "lstm_fwd_persistent timeline (cycles after the grid barrier opened): t | first_data last_data mma_done epi_start epi_stored epi_alldone arrived | step\n");
     for (int t = 1; t < T; ++t) {
       const long long* e = &hbuf[(size_t)t * 8];
-      fprintf(stderr, "%2d | %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", t, e[1] - e[0], e[2] - e[0], e[3] - e[0],
-              e[4] - e[0], e[5] - e[0], e[6] - e[0], e[7] - e[0], e[0] - hbuf[(size_t)(t - 1) * 8]);
+      fprintf(stderr, "%2d | %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", t, e[3] - e[1], e[0] - e[1], e[4] - e[1],
+              e[5] - e[1], e[6] - e[1], e[2] - e[1], e[7] - e[1], e[1] - hbuf[(size_t)(t - 1) * 8 + 1]);
+    }
+    {   // wall-clock (globaltimer, ns) spread over all CTAs at step 10 -> 11
+      const int G = grid.x * grid.y;
+      const long long* g = &hbuf[(size_t)T * 8];
+      long long open10_min = 1LL << 62, open10_max = 0, arr10_min = 1LL << 62, arr10_max = 0, open11_min = 1LL << 62, open11_max = 0;
+      int slowest = 0;
+      for (int i = 0; i < G; ++i) {
+        open10_min = std::min(open10_min, g[i * 4]); open10_max = std::max(open10_max, g[i * 4]);
+        arr10_min = std::min(arr10_min, g[i * 4 + 1]);
+        if (g[i * 4 + 1] > arr10_max) { arr10_max = g[i * 4 + 1]; slowest = i; }
+        open11_min = std::min(open11_min, g[i * 4 + 2]); open11_max = std::max(open11_max, g[i * 4 + 2]);
+      }
+      fprintf(stderr, "step 10 wall clock (ns, relative to first CTA seeing the barrier open): open %lld..%lld | arrive %lld..%lld "
+              "(slowest CTA %d = n-slice %d, m-tile %d) | next open %lld..%lld\n", 0LL, open10_max - open10_min,
+              arr10_min - open10_min, arr10_max - open10_min, slowest, slowest % (int)grid.x, slowest / (int)grid.x,
+              open11_min - open10_min, open11_max - open10_min);
+      for (int y = 0; y < (int)grid.y; y += 3) {
+        std::vector<long long> o10, a10, o11;
+        long long base = 1LL << 62;
+        for (int x = 0; x < (int)grid.x; ++x) base = std::min(base, g[(y * grid.x + x) * 4]);
+        for (int x = 0; x < (int)grid.x; ++x) {
+          o10.push_back(g[(y * grid.x + x) * 4] - base); a10.push_back(g[(y * grid.x + x) * 4 + 1] - base);
+          o11.push_back(g[(y * grid.x + x) * 4 + 2] - base);
+        }
+        fprintf(stderr, "m-tile %d per n-slice: smid | open10 first_data last_data tfull arrive10 | open11 (ns)\n", y);
+        const long long* x3 = &hbuf[(size_t)T * 8 + 1024];
+        for (int x = 0; x < (int)grid.x; ++x) {
+          const long long* e = &x3[(y * grid.x + x) * 4];
+          fprintf(stderr, "  n%02d sm%3lld | %5lld %5lld %5lld %5lld %5lld | %5lld\n", x, e[2], o10[x], e[0] - base, e[1] - base,
+                  e[3] - base, a10[x], o11[x]);
+        }
+      }
+      fprintf(stderr, "arrive(ns) by m-tile:");
+      for (int y = 0; y < (int)grid.y; ++y) {
+        long long mn = 1LL << 62, mx = 0;
+        for (int x = 0; x < (int)grid.x; ++x) { long long v = g[(y * grid.x + x) * 4 + 1] - open10_min; mn = std::min(mn, v); mx = std::max(mx, v); }
+        fprintf(stderr, "  m%d: %lld..%lld", y, mn, mx);
+      }
+      fprintf(stderr, "\n");
     }
   }
   return 0;

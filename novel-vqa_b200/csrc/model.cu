@@ -315,7 +315,7 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->ans_host), (size_t)B * 4));
   m->planes = cfg->precision == NVQA_PREC_BF16X3 ? 3 : cfg->precision == NVQA_PREC_BF16X2 ? 2
               : cfg->precision == NVQA_PREC_BF16 ? 1 : 0;
-  NVQA_TRY(dallocT(m, &m->grid_counter, 4));
+  NVQA_TRY(dallocT(m, &m->grid_counter, 1024));    // per-CTA barrier flags of the persistent kernels
   if (m->planes) {
     for (int l = 0; l < L; ++l) {
       NVQA_TRY(dallocT(m, &m->hp[l], (size_t)m->planes * (N + B) * H));

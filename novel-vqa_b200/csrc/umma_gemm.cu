@@ -38,7 +38,7 @@ struct UgCfg {
   static constexpr int STAGE = P * (A_PLANE + B_PLANE);
   static constexpr int MAX_STAGES = (227 * 1024 - 2048) / STAGE;
   static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias tile*/;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static_assert(STAGES >= 2, "pipeline needs two stages");
 };
@@ -58,6 +58,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const uint32_t empty0 = full0 + 8 * Cfg::STAGES;                   // empty[s]
   const uint32_t tfull = empty0 + 8 * Cfg::STAGES;                   // accumulator ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+  float* bias_s = reinterpret_cast<float*>(gen + Cfg::STAGES * Cfg::STAGE + 256);      // bias0 + bias1 of this tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * UG_BM, n0 = blockIdx.x * BN;
@@ -69,6 +70,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp >= 2) {      // stage the tile's bias row once (the epilogue then reads it as a shared-memory broadcast)
+    for (int j = threadIdx.x - 64; j < BN; j += 128) {
+      float bsum = 0.f;
+      if (n0 + j < N) {
+        if (bias0) bsum += __ldg(bias0 + n0 + j);
+        if (bias1) bsum += __ldg(bias1 + n0 + j);
+      }
+      bias_s[j] = bsum;
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -175,14 +186,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int j = 0; j < 32; j += 4) {
           const int col = n0 + cc * 32 + j;
           if (col >= N) break;
-          float r[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            if (col + t < N) {
-              if (bias0) r[t] += __ldg(bias0 + col + t);
-              if (bias1) r[t] += __ldg(bias1 + col + t);
-            }
-          }
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j);
+          float r[4] = {v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w};
           if (vec && col + 3 < N) {
             if (beta) {
               float4 o = *reinterpret_cast<const float4*>(crow + col);
