@@ -49,7 +49,10 @@ enum { NVQA_PHASE_HEAD = 0, NVQA_PHASE_LSTM = 1, NVQA_PHASE_EMBED = 2, NVQA_PHAS
 
 /* mirrors the cmd:option block of 002_train_baseline.lua:22-48 */
 typedef struct nvqa_config {
-  int32_t arch;       /* 1 = 002_train_vqa_arch1                                          */
+  int32_t arch;       /* 1 = 002_train_vqa_arch1, 2 = 003_train_vqa_arch2 (image + START + words through a
+                         LookupTable LSTM encoder; E = -input_encoding_size, L = -num_layers, C unused;
+                         blocks: 0 = cnn_w, 1 = encoder_w_q (LSTM core then LookupTable), 2 = multimodal_w;
+                         q is the question matrix as stored, NOT right-aligned)                 */
   int32_t V;          /* vocabulary size (count of ix_to_word)            :126-127         */
   int32_t E;          /* -input_encoding_size  (200)                      :34              */
   int32_t H;          /* -rnn_size             (512)                      :35              */
@@ -107,6 +110,9 @@ int nvqa_set_batch_host(nvqa_model* m, const int32_t* q, const int32_t* len, con
 /* explicit Dropout multipliers (0 or 1/(1-p)) in the padded layout, device pointers, any NULL:
  * emb [T x B x E], lstm [(L-1) x T x B x H], q [B x 2LH], i [B x I], z [B x C].  While unset,
  * training mode draws masks from the counter hash shared with oracle/rng.py. */
+/* arch 2 with device-resident batches: number of LSTM steps to execute = 2 + longest question of the batch
+ * (misc/Encoder_lstm.lua:185-189,219); nvqa_set_batch resets it to T + 2, nvqa_set_batch_host derives it from len. */
+int nvqa_set_steps(nvqa_model* m, int32_t steps);
 int nvqa_set_masks(nvqa_model* m, const float* emb, const float* lstm, const float* q, const float* i,
                    const float* z);
 int nvqa_forward(nvqa_model* m, int mode, uint64_t seed);        /* embedding .. scores           */

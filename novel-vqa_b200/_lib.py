@@ -42,6 +42,7 @@ SIGNATURES = {
     "nvqa_pack_batch": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
     "nvqa_set_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "nvqa_set_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "nvqa_set_steps": (C.c_int, [C.c_void_p, C.c_int32]),
     "nvqa_set_masks": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "nvqa_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64]),
     "nvqa_loss": (C.c_int, [C.c_void_p, c_f32p]),

@@ -14,12 +14,13 @@ from ._lib import (PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_BF16X2, BLOCK_EN
                    BLOCK_MULTIMODAL, MODE_EVAL, MODE_TRAIN, PHASE_HEAD, PHASE_LSTM, PHASE_EMBED, PHASE_ALL,
                    NvqaError)
 
-__all__ = ["Arch1Config", "Arch1Model", "DeviceBuffer", "right_align", "pack_batch", "synth_batch", "synth_params",
+__all__ = ["Arch1Config", "Arch1Model", "Arch2Config", "Arch2Model", "synth_params2", "synth_batch2", "BLOCK_CNN", "DeviceBuffer", "right_align", "pack_batch", "synth_batch", "synth_params",
            "device_count", "launch_count", "PREC_FP32_SIMT", "PREC_BF16X3", "PREC_BF16", "PREC_BF16X2",
            "BLOCK_ENCODER", "BLOCK_EMBEDDING", "BLOCK_MULTIMODAL", "MODE_EVAL", "MODE_TRAIN", "PHASE_HEAD",
            "PHASE_LSTM", "PHASE_EMBED", "PHASE_ALL", "NvqaError", "DECAY_FACTOR"]
 
 DECAY_FACTOR = 0.99997592083      # 002_train_baseline.lua:78
+BLOCK_CNN = 0                     # arch2 blocks: cnn_w, encoder_w_q (LSTM core + LookupTable), multimodal_w
 
 
 @dataclass
@@ -40,6 +41,27 @@ class Arch1Config:
     @property
     def S(self):
         return 2 * self.L * self.H
+
+
+@dataclass
+class Arch2Config:
+    """Defaults = the cmd:option defaults of 003_train_vqa_arch2/002_train_baseline.lua:30-43 (I = 2048 for the
+    Inception features of BASELINE config 4)."""
+    V: int = 14773
+    E: int = 512
+    H: int = 512
+    L: int = 1
+    I: int = 4096
+    O: int = 1000
+    T: int = 26
+    B: int = 500
+    dropout: float = 0.5
+    img_norm: int = 1
+    C: int = 0
+
+    @property
+    def S(self):
+        return self.H
 
 
 def device_count():
@@ -115,14 +137,17 @@ class DeviceBuffer:
 
 
 class Arch1Model:
-    def __init__(self, cfg: Arch1Config = None, precision=PREC_FP32_SIMT, device=0, **overrides):
+    ARCH = 1
+    CONFIG = Arch1Config
+
+    def __init__(self, cfg=None, precision=PREC_FP32_SIMT, device=0, **overrides):
         self.lib = _lib.load()
-        cfg = cfg or Arch1Config()
+        cfg = cfg or self.CONFIG()
         for k, v in overrides.items():
             setattr(cfg, k, v)
         self.cfg = cfg
         self.precision = precision
-        c = _lib.nvqa_config(arch=1, precision=precision, device=device, **{k: v for k, v in asdict(cfg).items()})
+        c = _lib.nvqa_config(arch=self.ARCH, precision=precision, device=device, **{k: v for k, v in asdict(cfg).items()})
         self.handle = C.c_void_p()
         _lib.check(self.lib.nvqa_model_create(C.byref(c), C.byref(self.handle)))
         self._keep = []
@@ -235,6 +260,42 @@ class Arch1Model:
         _lib.check(self.lib.nvqa_eval_step_host(self.handle, _ptr(q_ra), _ptr(lengths), _ptr(fc7), q_ra.shape[0],
                                                 _ptr(ans)))
         return ans
+
+
+class Arch2Model(Arch1Model):
+    """003_train_vqa_arch2: cnn_projection + nn.Encoder (image, START, words through a LookupTable LSTM) + head.
+    Blocks: BLOCK_CNN (0), BLOCK_EMBEDDING slot = encoder_w_q (1), BLOCK_MULTIMODAL (2).  Questions are passed as
+    stored (left-aligned, zero-padded)."""
+    ARCH = 2
+    CONFIG = Arch2Config
+
+    def set_steps(self, steps):
+        _lib.check(self.lib.nvqa_set_steps(self.handle, steps))
+
+    def set_masks(self, lstm=None, z=None):
+        super().set_masks(emb=None, lstm=lstm, q=None, i=None, z=z)
+
+
+def synth_params2(cfg, seed=123):
+    """uniform(-0.08, 0.08) over cnn_w, encoder_w_q, multimodal_w (003_train_vqa_arch2/002_train_baseline.lua:182-189)."""
+    r = np.random.default_rng(seed)
+    n_enc = sum(4 * cfg.H * ((cfg.E if l == 0 else cfg.H) + cfg.H + 2) for l in range(cfg.L)) + (cfg.V + 1) * cfg.E
+    cnn = r.uniform(-0.08, 0.08, cfg.E * cfg.I + cfg.E).astype(np.float32)
+    enc = r.uniform(-0.08, 0.08, n_enc).astype(np.float32)
+    mm = r.uniform(-0.08, 0.08, cfg.O * cfg.H + cfg.O).astype(np.float32)
+    return cnn, enc, mm
+
+
+def synth_batch2(cfg, B, seed=123, min_len=None):
+    """arch2 batch: questions left-aligned and zero-padded as in data_prepro.h5 (no right_align)."""
+    r = np.random.default_rng(seed)
+    T = cfg.T
+    lengths = np.full(B, T, dtype=np.int32) if min_len is None else r.integers(min_len, T + 1, B).astype(np.int32)
+    tok = r.integers(1, cfg.V + 1, (B, T)).astype(np.int32)
+    q = np.where(np.arange(T)[None, :] < lengths[:, None], tok, 0).astype(np.int32)
+    fc7 = np.maximum(0.0, r.standard_normal((B, cfg.I))).astype(np.float32)
+    labels = r.integers(1, cfg.O + 1, B).astype(np.int32)
+    return q, lengths, fc7, labels
 
 
 # ---- synthetic data of the BASELINE.json shape (SURVEY 8d) ----------------------------------------

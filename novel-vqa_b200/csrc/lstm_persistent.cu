@@ -253,7 +253,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
     const int cc = (warp - 2) >> 2;               // which 32-column half: units u0 + 8 cc .. + 8
     const int b = m0 + q * 32 + lane;
     const bool rowok = b < B;
-    const int mylen = rowok ? len[b] : 0;
+    const int mylen = rowok ? (len ? len[b] : T) : 0;
     const int uo = u0 + 8 * cc;
     float ccarry[8];                               // c_{t-1} of this thread's (row, 8 units): never leaves registers
 #pragma unroll
@@ -510,7 +510,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
           ucol[n] = valid[n] ? (int)(i % H4) * 4 : 0;
           row[n] = (size_t)t * B + b;
           o[n] = (size_t)b * H + ucol[n];
-          act[n] = valid[n] && (t >= T - len[b]);
+          act[n] = valid[n] && (!len || t >= T - len[b]);
           gi[n] = gf[n] = go[n] = gg[n] = cp[n] = cn[n] = dh[n] = dc[n] = z;
           if (act[n]) {
             const float* g = gates + row[n] * 4 * H + ucol[n];

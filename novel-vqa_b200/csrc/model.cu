@@ -69,6 +69,11 @@ struct nvqa_model {
   unsigned int* grid_counter = nullptr;
   int planes = 0;                   // bf16 planes per operand of the tensor-core modes (0 = SIMT)
   bool use_persistent = true;
+  // arch2 (003_train_vqa_arch2): image projection, LookupTable, head on the top-layer h
+  int TS = 0;                       // time-step capacity of the activation buffers (T for arch1, T + 2 for arch2)
+  int steps = 0;                    // arch2: executed steps tmax = 2 + longest question of the batch
+  float *Wcnn = nullptr, *bcnn = nullptr, *gWcnn = nullptr, *gbcnn = nullptr, *lookup = nullptr, *glookup = nullptr;
+  float* zeros = nullptr;           // [B x H] zeros (initial dc / dh of the arch2 backward)
   bool hp_valid[4] = {false, false, false, false};   // hp[l] holds this step's h planes (persistent forward ran)
   bool dap_valid = false;                            // dap holds the current layer's da planes
   // batch
@@ -227,22 +232,34 @@ extern "C" int nvqa_model_destroy(nvqa_model* m) {
 static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   m->cfg = *cfg;
   const int V = cfg->V, E = cfg->E, H = cfg->H, L = cfg->L, I = cfg->I, C = cfg->C, O = cfg->O, T = cfg->T, B = cfg->B;
-  NVQA_CHECK(cfg->arch == 1, "only arch 1 (002_train_vqa_arch1) is built in this round");
-  NVQA_CHECK(V > 0 && E > 0 && H > 0 && L >= 1 && L <= 4 && I > 0 && C > 0 && O > 0 && T > 0 && B > 0, "bad config");
+  NVQA_CHECK(cfg->arch == 1 || cfg->arch == 2, "arch must be 1 (002_train_vqa_arch1) or 2 (003_train_vqa_arch2)");
+  const bool a2 = cfg->arch == 2;
+  if (a2) m->cfg.C = cfg->H;        // arch2 has no common embedding: the head reads the H-wide encoder output
+  NVQA_CHECK(V > 0 && E > 0 && H > 0 && L >= 1 && L <= 4 && I > 0 && (a2 || C > 0) && O > 0 && T > 0 && B > 0, "bad config");
   NVQA_CHECK(E % 4 == 0 && H % 4 == 0 && I % 4 == 0 && C % 4 == 0, "E, H, I, C must be multiples of 4 (128-bit rows)");
   NVQA_CHECK(cfg->dropout >= 0.f && cfg->dropout < 1.f, "dropout must be in [0,1)");
   NVQA_CHECK(cfg->precision >= 0 && cfg->precision <= 3, "unknown precision");
   NVQA_TRY(require_device(cfg->device));
   NVQA_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
-  const int S = 2 * L * H;
+  const int S = a2 ? H : 2 * L * H;
   m->S = S;
-  // optimiser order: encoder, embedding, multimodal (002_train_baseline.lua:183,190)
+  m->TS = a2 ? T + 2 : T;
+  m->steps = m->TS;
   int64_t n_enc = 0;
   for (int l = 0; l < L; ++l) n_enc += (int64_t)4 * H * (l == 0 ? E : H) + 4 * H + (int64_t)4 * H * H + 4 * H;
-  m->n_blk[0] = n_enc;
-  m->n_blk[1] = (int64_t)V * E + E;
-  m->n_blk[2] = (int64_t)C * S + C + (int64_t)C * I + C + (int64_t)O * C + O;
+  if (!a2) {
+    // optimiser order: encoder, embedding, multimodal (002_train_baseline.lua:183,190)
+    m->n_blk[0] = n_enc;
+    m->n_blk[1] = (int64_t)V * E + E;
+    m->n_blk[2] = (int64_t)C * S + C + (int64_t)C * I + C + (int64_t)O * C + O;
+  } else {
+    // optimiser / checkpoint order: cnn_w, encoder_w_q (LSTM then LookupTable), multimodal_w
+    // (003_train_vqa_arch2/002_train_baseline.lua:192,198; misc/Encoder_lstm.lua:66-83)
+    m->n_blk[0] = (int64_t)E * I + E;
+    m->n_blk[1] = n_enc + (int64_t)(V + 1) * E;
+    m->n_blk[2] = (int64_t)O * H + O;
+  }
   for (int i = 0; i < 3; ++i) m->off_blk[i + 1] = m->off_blk[i] + ((m->n_blk[i] + 3) / 4) * 4;
   m->P = m->off_blk[3];
   NVQA_TRY(dallocT(m, &m->params, m->P));
@@ -252,13 +269,23 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_CUDA(cudaMemsetAsync(m->grads, 0, m->P * 4, m->stream));
   NVQA_CUDA(cudaMemsetAsync(m->rms, 0, m->P * 4, m->stream));   // optim.rmsprop: state.m = 0
   auto carve = [&](float* base, LayerPtrs* lp, float** We, float** be_, float** q6) {
-    float* p = base + m->off_blk[0];
+    float* p = base + m->off_blk[a2 ? 1 : 0];
     for (int l = 0; l < L; ++l) {
       int in = l == 0 ? E : H;
       lp[l].Wi = p; p += (int64_t)4 * H * in;
       lp[l].bi = p; p += 4 * H;
       lp[l].Wh = p; p += (int64_t)4 * H * H;
       lp[l].bh = p; p += 4 * H;
+    }
+    if (a2) {
+      *We = p;                                   // LookupTable.weight [(V+1) x E] follows the LSTM core
+      *be_ = nullptr;
+      q6[0] = base + m->off_blk[0];              // cnn_projection: W [E x I], b [E]
+      q6[1] = q6[0] + (int64_t)E * I;
+      q6[2] = q6[3] = nullptr;
+      q6[4] = base + m->off_blk[2];              // head: W [O x H], b [O]
+      q6[5] = q6[4] + (int64_t)O * H;
+      return;
     }
     p = base + m->off_blk[1];
     *We = p; p += (int64_t)V * E;
@@ -277,8 +304,15 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   carve(m->grads, m->lg, &m->gWeT, &m->gbe, g6);
   m->Wq = w6[0]; m->bq = w6[1]; m->Wv = w6[2]; m->bv = w6[3]; m->Wc = w6[4]; m->bc = w6[5];
   m->gWq = g6[0]; m->gbq = g6[1]; m->gWv = g6[2]; m->gbv = g6[3]; m->gWc = g6[4]; m->gbc = g6[5];
+  if (a2) {
+    m->Wcnn = w6[0]; m->bcnn = w6[1]; m->gWcnn = g6[0]; m->gbcnn = g6[1];
+    m->lookup = m->WeT; m->glookup = m->gWeT;
+    NVQA_TRY(dallocT(m, &m->zeros, (size_t)B * H));
+    NVQA_CUDA(cudaMemsetAsync(m->zeros, 0, (size_t)B * H * 4, m->stream));
+  }
+  const int C2 = m->cfg.C;
 
-  const int64_t N = (int64_t)T * B;
+  const int64_t N = (int64_t)m->TS * B;
   NVQA_TRY(dallocT(m, &m->y, N * E));
   for (int l = 0; l < L; ++l) {
     NVQA_TRY(dallocT(m, &m->pre[l], N * 4 * H));
@@ -291,17 +325,17 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_TRY(dallocT(m, &m->state, (int64_t)B * S));
   NVQA_TRY(dallocT(m, &m->qd, (int64_t)B * S));
   NVQA_TRY(dallocT(m, &m->vd, (int64_t)B * I));
-  NVQA_TRY(dallocT(m, &m->qc, (int64_t)B * C));
-  NVQA_TRY(dallocT(m, &m->ic, (int64_t)B * C));
-  NVQA_TRY(dallocT(m, &m->zd, (int64_t)B * C));
+  NVQA_TRY(dallocT(m, &m->qc, (int64_t)B * C2));
+  NVQA_TRY(dallocT(m, &m->ic, (int64_t)B * C2));
+  NVQA_TRY(dallocT(m, &m->zd, (int64_t)B * C2));
   NVQA_TRY(dallocT(m, &m->scores, (int64_t)B * O));
   NVQA_TRY(dallocT(m, &m->dscores, (int64_t)B * O));
   NVQA_TRY(dallocT(m, &m->rowloss, (int64_t)B));
   NVQA_TRY(dallocT(m, &m->loss, 4));
   NVQA_TRY(dallocT(m, &m->argmax, (int64_t)B));
-  NVQA_TRY(dallocT(m, &m->dzd, (int64_t)B * C));
-  NVQA_TRY(dallocT(m, &m->dqpre, (int64_t)B * C));
-  NVQA_TRY(dallocT(m, &m->dipre, (int64_t)B * C));
+  NVQA_TRY(dallocT(m, &m->dzd, (int64_t)B * C2));
+  NVQA_TRY(dallocT(m, &m->dqpre, (int64_t)B * C2));
+  NVQA_TRY(dallocT(m, &m->dipre, (int64_t)B * C2));
   NVQA_TRY(dallocT(m, &m->dqd, (int64_t)B * S));
   NVQA_TRY(dallocT(m, &m->da, N * 4 * H));
   NVQA_TRY(dallocT(m, &m->dxbuf, N * (H > E ? H : E)));
@@ -330,8 +364,8 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   if (cfg->precision != NVQA_PREC_FP32_SIMT) {
     // transient operand planes of the largest GEMM (wgrad: da^T [4H x TB] and x^T [H x TB], 3 bf16 planes each);
     // static region: every weight matrix in both orientations
-    size_t elems = (size_t)(N + 64) * 4 * H + (size_t)(N + 64) * (H > E ? H : E) + (size_t)(B + 64) * (I + S + 2 * C);
-    size_t stat = (size_t)(m->n_blk[0] + m->n_blk[2]) * 2 * 6 + (16 << 20);
+    size_t elems = (size_t)(N + 64) * 4 * H + (size_t)(N + 64) * (H > E ? H : E) + (size_t)(B + 64) * (I + S + 2 * C2);
+    size_t stat = (size_t)(n_enc + m->n_blk[2] + (a2 ? m->n_blk[0] : 0)) * 2 * 6 + (16 << 20);
     NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (96 << 20), stat));
   }
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
@@ -381,7 +415,7 @@ static int block_copy(nvqa_model* m, float* dev_base, int block, float* host, bo
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   float* d = dev_base + m->off_blk[block];
   const int64_t n = m->n_blk[block];
-  if (block != NVQA_BLOCK_EMBEDDING) {
+  if (block != NVQA_BLOCK_EMBEDDING || m->cfg.arch == 2) {
     if (to_device) NVQA_CUDA(cudaMemcpyAsync(d, host, n * 4, cudaMemcpyHostToDevice, m->stream));
     else NVQA_CUDA(cudaMemcpyAsync(host, d, n * 4, cudaMemcpyDeviceToHost, m->stream));
     NVQA_CUDA(cudaStreamSynchronize(m->stream));
@@ -431,6 +465,14 @@ extern "C" int nvqa_set_batch(nvqa_model* m, const int32_t* q, const int32_t* le
   NVQA_CHECK(B > 0 && B <= m->cfg.B, "batch size out of range");
   m->q = q; m->len = len; m->fc7 = fc7; m->labels = labels; m->B = B;
   m->fwd_done = false;
+  m->steps = m->TS;
+  return 0;
+}
+
+extern "C" int nvqa_set_steps(nvqa_model* m, int32_t steps) {
+  NVQA_CHECK(m && m->cfg.arch == 2, "nvqa_set_steps applies to arch 2 models");
+  NVQA_CHECK(steps >= 2 && steps <= m->TS, "steps out of range");
+  m->steps = steps;
   return 0;
 }
 
@@ -443,7 +485,14 @@ extern "C" int nvqa_set_batch_host(nvqa_model* m, const int32_t* q, const int32_
   NVQA_CUDA(cudaMemcpyAsync(m->len_stage, len, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
   NVQA_CUDA(cudaMemcpyAsync(m->fc7_stage, fc7, (size_t)B * m->cfg.I * 4, cudaMemcpyHostToDevice, m->stream));
   if (labels) NVQA_CUDA(cudaMemcpyAsync(m->lab_stage, labels, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
-  return nvqa_set_batch(m, m->q_stage, m->len_stage, m->fc7_stage, labels ? m->lab_stage : nullptr, B);
+  NVQA_TRY(nvqa_set_batch(m, m->q_stage, m->len_stage, m->fc7_stage, labels ? m->lab_stage : nullptr, B));
+  if (m->cfg.arch == 2) {   // executed steps tmax = image + START + longest question (Encoder_lstm.lua:185-189,219)
+    int mx = 0;
+    for (int b = 0; b < B; ++b) mx = len[b] > mx ? len[b] : mx;
+    NVQA_CHECK(mx >= 0 && mx <= m->cfg.T, "question length out of range");
+    m->steps = 2 + mx;
+  }
+  return 0;
 }
 
 extern "C" int nvqa_set_masks(nvqa_model* m, const float* emb, const float* lstm, const float* q, const float* i,
@@ -454,26 +503,21 @@ extern "C" int nvqa_set_masks(nvqa_model* m, const float* emb, const float* lstm
 }
 
 // ---- forward -------------------------------------------------------------------------------------
+
 static Drop lstm_drop(const nvqa_model* m, int l /* between layer l and l+1 */) {
-  const int64_t per = (int64_t)m->cfg.T * m->B * m->cfg.H;
+  const int64_t per = (int64_t)(m->cfg.arch == 2 ? m->steps : m->cfg.T) * m->B * m->cfg.H;
   return make_drop(m, m->mk_lstm ? m->mk_lstm + per * l : nullptr, STREAM_LSTM0 + l);
 }
 
-extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
-  NVQA_CHECK(m && m->q, "nvqa_forward: no batch set");
-  NVQA_CHECK(mode == NVQA_MODE_EVAL || mode == NVQA_MODE_TRAIN, "bad mode");
-  NVQA_CUDA(cudaSetDevice(m->cfg.device));
-  m->mode = mode; m->seed = seed;
+static int lstm_layers_backward(nvqa_model* m, int T, const int32_t* len, const float* const* dh0, const float* const* dc0, int ld0);
+
+// All LSTM layers over T steps, layer-major: batched input projection (K3), then the recurrence (K4 persistent kernel,
+// or per-step GEMM + gate kernel as the generic fallback).  len == nullptr: every row is active at every step.
+static int lstm_layers_forward(nvqa_model* m, int T, const int32_t* len) {
   const nvqa_config& c = m->cfg;
-  const int B = m->B, T = c.T, E = c.E, H = c.H, L = c.L, S = m->S;
+  const int B = m->B, E = c.E, H = c.H, L = c.L;
   const int64_t BH = (int64_t)B * H;
   cudaStream_t s = m->stream;
-  // embedding_net_q:forward   (:300)
-  {
-    ProfScope ps(m, CAT_PW_FWD, 0);
-    NVQA_TRY(embed_fwd(s, m->q, m->len, m->WeT, m->be, m->y, make_drop(m, m->mk_emb, STREAM_EMB), B, T, E, c.V));
-  }
-  // rnn_forward (:303), layer-major
   for (int l = 0; l < L; ++l) {
     const float* X = l == 0 ? m->y : m->xdrop[l];
     const int in = l == 0 ? E : H;
@@ -483,7 +527,7 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
       // K4: all T steps in one persistent cooperative kernel (W_hh slice resident in shared memory)
       ProfScope ps(m, CAT_REC_FWD, 2.0 * (T - 1) * B * 4.0 * H * H);
       int rc = lstm_fwd_persistent(s, m->ws, m->planes, m->lw[l].Wh, m->pre[l], m->c[l], m->h[l], m->hp[l],
-                                   l + 1 < L ? m->xdrop[l + 1] : nullptr, m->len, lstm_drop(m, l), T, B, H,
+                                   l + 1 < L ? m->xdrop[l + 1] : nullptr, len, lstm_drop(m, l), T, B, H,
                                    m->grid_counter);
       if (rc > 0) return rc;
       m->hp_valid[l] = rc == 0;
@@ -496,9 +540,59 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
         NVQA_TRY(gemm(m, CAT_REC_FWD, true, true, B, 4 * H, H, m->h[l] + t * BH, H, m->lw[l].Wh, H, pre_t, 4 * H, true));
       ProfScope ps(m, CAT_PW_FWD, 0);
       NVQA_TRY(lstm_gates_fwd(s, pre_t, m->c[l] + t * BH, H, m->c[l] + (t + 1) * BH, m->h[l] + (t + 1) * BH, H,
-                              l + 1 < L ? m->xdrop[l + 1] + t * BH : nullptr, m->len, lstm_drop(m, l), t, T, B, H));
+                              l + 1 < L ? m->xdrop[l + 1] + t * BH : nullptr, len, lstm_drop(m, l), t, T, B, H));
     }
   }
+  return 0;
+}
+
+// arch2 forward: 003_train_vqa_arch2/002_train_baseline.lua:308-314 + misc/Encoder_lstm.lua:152-227
+static int forward_arch2(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, T = c.T, E = c.E, H = c.H, L = c.L, steps = m->steps;
+  cudaStream_t s = m->stream;
+  Drop none = make_drop(m, nullptr, 0);
+  none.mode = 0;
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, none, B, c.I, c.img_norm));
+    NVQA_TRY(lookup_fwd(s, m->q, m->lookup, m->y, B, T, E, c.V, steps));
+  }
+  // step 1: cnn_projection = Linear(I, E) on the (normalised) image feature, written as rows [0, B) of the LSTM input
+  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, E, c.I, m->vd, c.I, m->Wcnn, c.I, m->y, E, false, m->bcnn));
+  NVQA_TRY(lstm_layers_forward(m, steps, nullptr));
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(mask_copy(s, m->h[L - 1] + (int64_t)steps * B * H, H, m->state, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, H));
+  }
+  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.O, H, m->zd, H, m->Wc, H, m->scores, c.O, false, m->bc));
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(softmax_ce(s, m->scores, m->labels, m->labels ? m->dscores : nullptr, m->rowloss, m->argmax, B, c.O,
+                        1.0f / (float)B));
+    if (m->labels) NVQA_TRY(loss_reduce(s, m->rowloss, m->loss, B));
+  }
+  m->fwd_done = true;
+  return 0;
+}
+
+extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
+  NVQA_CHECK(m && m->q, "nvqa_forward: no batch set");
+  NVQA_CHECK(mode == NVQA_MODE_EVAL || mode == NVQA_MODE_TRAIN, "bad mode");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  m->mode = mode; m->seed = seed;
+  if (m->cfg.arch == 2) return forward_arch2(m);
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, T = c.T, E = c.E, H = c.H, L = c.L, S = m->S;
+  const int64_t BH = (int64_t)B * H;
+  cudaStream_t s = m->stream;
+  // embedding_net_q:forward   (:300)
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(embed_fwd(s, m->q, m->len, m->WeT, m->be, m->y, make_drop(m, m->mk_emb, STREAM_EMB), B, T, E, c.V));
+  }
+  // rnn_forward (:303), layer-major
+  NVQA_TRY(lstm_layers_forward(m, T, m->len));
   // tv_q (:306) and multimodal_net:forward (:307)
   const float* cf[4];
   const float* hf[4];
@@ -536,7 +630,35 @@ extern "C" int nvqa_loss(nvqa_model* m, float* out) {
 }
 
 // ---- backward ------------------------------------------------------------------------------------
+// arch2: Linear(H,O) + Dropout backward (003_train_vqa_arch2/002_train_baseline.lua:316-318)
+static int backward_head_arch2(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, H = c.H, O = c.O;
+  cudaStream_t s = m->stream;
+  NVQA_CUDA(cudaMemsetAsync(m->gbc, 0, (size_t)O * 4, s));
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, O, H, B, m->dscores, O, m->zd, H, m->gWc, H, false));
+  NVQA_TRY(colsum(s, m->dscores, B, O, O, m->gbc, nullptr));
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, H, O, m->dscores, O, m->Wc, H, m->dzd, H, false));
+  NVQA_TRY(mask_inplace(s, m->dzd, make_drop(m, m->mk_z, STREAM_HEAD), (int64_t)B * H));
+  return 0;
+}
+
+// arch2: d(step-1 input) -> cnn_projection:backward (:322); d(steps 2..) -> LookupTable accGradParameters
+static int backward_embed_arch2(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, E = c.E;
+  cudaStream_t s = m->stream;
+  ProfScope ps(m, CAT_PW_BWD, 0);
+  NVQA_CUDA(cudaMemsetAsync(m->glookup, 0, (size_t)(c.V + 1) * E * 4, s));
+  NVQA_CUDA(cudaMemsetAsync(m->gbcnn, 0, (size_t)E * 4, s));
+  NVQA_TRY(lookup_bwd(s, m->q, m->dxbuf, m->glookup, B, c.T, E, c.V, m->steps));
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, E, c.I, B, m->dxbuf, E, m->vd, c.I, m->gWcnn, c.I, false));
+  NVQA_TRY(colsum(s, m->dxbuf, B, E, E, m->gbcnn, nullptr));
+  return 0;
+}
+
 static int backward_head(nvqa_model* m) {
+  if (m->cfg.arch == 2) return backward_head_arch2(m);
   const nvqa_config& c = m->cfg;
   const int B = m->B, S = m->S, C = c.C, O = c.O, I = c.I;
   cudaStream_t s = m->stream;
@@ -561,29 +683,31 @@ static int backward_head(nvqa_model* m) {
   return 0;
 }
 
-static int backward_lstm(nvqa_model* m) {
+// rnn_backward for all layers (top first).  dh0[l] / dc0[l]: gradient of the loss w.r.t. layer l's final h / c
+// (leading dimension ld0); len == nullptr: every row active at every step.
+static int lstm_layers_backward(nvqa_model* m, int T, const int32_t* len, const float* const* dh0, const float* const* dc0, int ld0) {
   const nvqa_config& c = m->cfg;
-  const int B = m->B, T = c.T, E = c.E, H = c.H, L = c.L, S = m->S;
+  const int B = m->B, E = c.E, H = c.H, L = c.L;
   const int64_t BH = (int64_t)B * H;
   cudaStream_t s = m->stream;
   for (int l = L - 1; l >= 0; --l) {
-    const float* dh_in = m->dqd + (2 * l + 1) * H;
-    const float* dc_in = m->dqd + (2 * l) * H;
-    int ld = S;
+    const float* dh_in = dh0[l];
+    const float* dc_in = dc0[l];
+    int ld = ld0;
     int rc = -1;
     if (m->planes && m->use_persistent) {
       // K9: the whole backward recurrence of this layer in one persistent cooperative kernel
       ProfScope ps(m, CAT_REC_BWD, 2.0 * (T - 1) * B * 4.0 * H * H);
       rc = lstm_bwd_persistent(s, m->ws, m->planes, m->lw[l].Wh, m->pre[l], m->c[l], dh_in, dc_in, ld,
                                l + 1 < L ? m->dxbuf : nullptr, lstm_drop(m, l), m->da, m->dap, m->dhbuf, m->dc_carry,
-                               m->len, T, B, H, m->grid_counter);
+                               len, T, B, H, m->grid_counter);
       if (rc > 0) return rc;
     }
     m->dap_valid = rc == 0;
     for (int t = T - 1; t >= 0 && rc != 0; --t) {
       NVQA_TRY(lstm_gates_bwd(s, m->pre[l] + (int64_t)t * B * 4 * H, m->c[l] + t * BH, m->c[l] + (t + 1) * BH, dh_in, ld,
                               l + 1 < L ? m->dxbuf + t * BH : nullptr, dc_in, ld, m->da + (int64_t)t * B * 4 * H,
-                              m->dc_carry, m->len, lstm_drop(m, l), t, T, B, H));
+                              m->dc_carry, len, lstm_drop(m, l), t, T, B, H));
       if (t > 0)   // dh_{t-1} = da_t . Wh
         NVQA_TRY(gemm(m, CAT_REC_BWD, true, false, B, H, 4 * H, m->da + (int64_t)t * B * 4 * H, 4 * H, m->lw[l].Wh, H, m->dh_carry, H,
                       false));
@@ -618,7 +742,20 @@ static int backward_lstm(nvqa_model* m) {
   return 0;
 }
 
+static int backward_lstm(nvqa_model* m) {
+  const int H = m->cfg.H, L = m->cfg.L;
+  const float *dh0[4], *dc0[4];
+  if (m->cfg.arch == 2) {   // only the top layer's final h receives a gradient (Encoder_lstm.lua:238-239)
+    for (int l = 0; l < L; ++l) { dh0[l] = l == L - 1 ? m->dzd : m->zeros; dc0[l] = m->zeros; }
+    return lstm_layers_backward(m, m->steps, nullptr, dh0, dc0, H);
+  }
+  // arch1: d tv_q = d[c1 h1 c2 h2 ...] (002_train_baseline.lua:306,313)
+  for (int l = 0; l < L; ++l) { dh0[l] = m->dqd + (2 * l + 1) * H; dc0[l] = m->dqd + (2 * l) * H; }
+  return lstm_layers_backward(m, m->cfg.T, m->len, dh0, dc0, m->S);
+}
+
 static int backward_embed(nvqa_model* m) {
+  if (m->cfg.arch == 2) return backward_embed_arch2(m);
   const nvqa_config& c = m->cfg;
   cudaStream_t s = m->stream;
   ProfScope ps(m, CAT_PW_BWD, 0);
@@ -674,7 +811,8 @@ extern "C" int nvqa_train_step_host(nvqa_model* m, const int32_t* q, const int32
   NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
   NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
   // clamp(-10,10) (:329) and optim.rmsprop defaults alpha=.99, eps=1e-8 (:408)
-  NVQA_TRY(nvqa_rmsprop_step(m, lr, 0.99f, 1e-8f, 0.f, 10.f, 1.f));
+  // arch2 trains with optimize.weightDecay = 1e-4 (003_train_vqa_arch2/002_train_baseline.lua:197)
+  NVQA_TRY(nvqa_rmsprop_step(m, lr, 0.99f, 1e-8f, m->cfg.arch == 2 ? 1e-4f : 0.f, 10.f, 1.f));
   if (loss_out) NVQA_TRY(nvqa_loss(m, loss_out));
   return 0;
 }

@@ -283,7 +283,7 @@ lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__
   float* a = da + (int64_t)b * 4 * H;
   float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 dai = z, daf = z, dao = z, dag = z, dcp = z;
-  if (t >= T - len[b]) {
+  if (!len || t >= T - len[b]) {
     const float* g = gates + (int64_t)b * 4 * H;
     float4 gi = LD4(g + j), gf = LD4(g + H + j), go = LD4(g + 2 * H + j), gg = LD4(g + 3 * H + j);
     float4 cp = LD4(c_prev + o), cn = LD4(c_new + o);
@@ -378,6 +378,74 @@ int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float*
               Drop d, int B, int T, int E, int V) {
   int64_t total = (int64_t)T * B * (E / 4);
   embed_bwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(q, len, y, dx, dWeT, d, B, T, E, V);
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// arch2 (003_train_vqa_arch2/misc/Encoder_lstm.lua:177-203): x[t] = LookupTable row of the START token (t = 1) or of
+// word t-2 (zeros -> token 1); t = 0 is the projected image and is written by a GEMM.  seq is [B x T], NOT right-aligned.
+__global__ void __launch_bounds__(256)
+lookup_fwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ table, float* __restrict__ x, int B, int T,
+                  int E, int V, int steps) {
+  const int E4 = E >> 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)(steps - 1) * B * E4) return;
+  int e = (int)(i % E4) * 4;
+  int64_t n = i / E4 + B;                        // row t*B + b, t >= 1
+  int b = (int)(n % B), t = (int)(n / B);
+  int tok = t == 1 ? V + 1 : seq[(int64_t)b * T + (t - 2)];
+  if (tok < 1 || tok > V + 1) tok = 1;
+  ST4(x + n * E + e, LD4(table + (int64_t)(tok - 1) * E + e));
+}
+
+int lookup_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* x, int B, int T, int E, int V, int steps) {
+  int64_t total = (int64_t)(steps - 1) * B * (E / 4);
+  if (total <= 0) return 0;
+  lookup_fwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(seq, table, x, B, T, E, V, steps);
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+// LookupTable accGradParameters for steps 1.. (Encoder_lstm.lua:256): dtable[token] += dx[t,b]
+__global__ void __launch_bounds__(256)
+lookup_bwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ dx, float* __restrict__ dtable, int B, int T,
+                  int E, int V, int steps) {
+  const int E4 = E >> 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)(steps - 1) * B * E4) return;
+  int e = (int)(i % E4) * 4;
+  int64_t n = i / E4 + B;
+  int b = (int)(n % B), t = (int)(n / B);
+  int tok = t == 1 ? V + 1 : seq[(int64_t)b * T + (t - 2)];
+  if (tok < 1 || tok > V + 1) tok = 1;
+  float4 g = LD4(dx + n * E + e);
+  float* dst = dtable + (int64_t)(tok - 1) * E + e;
+  atomicAdd(dst + 0, g.x); atomicAdd(dst + 1, g.y); atomicAdd(dst + 2, g.z); atomicAdd(dst + 3, g.w);
+}
+
+int lookup_bwd(cudaStream_t s, const int32_t* seq, const float* dx, float* dtable, int B, int T, int E, int V, int steps) {
+  int64_t total = (int64_t)(steps - 1) * B * (E / 4);
+  if (total <= 0) return 0;
+  lookup_bwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(seq, dx, dtable, B, T, E, V, steps);
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+// dst[b][j] = drop(b*W + j) * src[b*ld + j]   (head Dropout on the encoder output; also saves the raw state)
+__global__ void __launch_bounds__(256)
+mask_copy_kernel(const float* __restrict__ src, int ld, float* __restrict__ raw, float* __restrict__ dst, Drop d, int B, int W) {
+  const int W4 = W >> 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * W4) return;
+  int j = (i % W4) * 4, b = i / W4;
+  float4 v = LD4(src + (int64_t)b * ld + j), m = drop_at4(d, (uint64_t)b * W + j);
+  if (raw) ST4(raw + (int64_t)b * W + j, v);
+  ST4(dst + (int64_t)b * W + j, make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w));
+}
+
+int mask_copy(cudaStream_t s, const float* src, int ld, float* raw, float* dst, Drop d, int B, int W) {
+  mask_copy_kernel<<<ceil_div((int64_t)B * W / 4, 256), 256, 0, s>>>(src, ld, raw, dst, d, B, W);
   NVQA_LAUNCHED();
   return 0;
 }

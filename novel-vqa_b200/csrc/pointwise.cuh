@@ -33,6 +33,10 @@ int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* o
 // Tanh/Dropout backward + scatter-add into dWeT [V x E]  (002_train_baseline.lua:320)
 int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* y, float* dx, float* dWeT,
               Drop d, int B, int T, int E, int V);
+// arch2 LookupTable gather / scatter-add (003_train_vqa_arch2/misc/Encoder_lstm.lua:177-203,256) and head Dropout
+int lookup_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* x, int B, int T, int E, int V, int steps);
+int lookup_bwd(cudaStream_t s, const int32_t* seq, const float* dx, float* dtable, int B, int T, int E, int V, int steps);
+int mask_copy(cudaStream_t s, const float* src, int ld, float* raw, float* dst, Drop d, int B, int W);
 // gradients*scale -> clamp -> optim.rmsprop, one pass (002_train_baseline.lua:329,408; misc/rmsprop_lrscale.lua:26-34)
 int clamp_rmsprop(cudaStream_t s, float* x, float* g, float* m, int64_t n, float lr, float alpha, float eps,
                   float wd, float clamp, float gscale);

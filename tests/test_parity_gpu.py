@@ -239,3 +239,87 @@ def test_full_size_config1_step():
         # eval_step_host == forward + argmax
         assert np.array_equal(m.eval_step_host(q, ln, fc7), am)
         m.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# arch2 (003_train_vqa_arch2): cnn projection + LookupTable LSTM encoder + head   (BASELINE config 4)
+# ------------------------------------------------------------------------------------------------
+def ocfg2(cfg):
+    from oracle import arch2 as A2
+    return A2.Arch2Config(V=cfg.V, E=cfg.E, H=cfg.H, L=cfg.L, I=cfg.I, O=cfg.O, T=cfg.T, p=cfg.dropout)
+
+
+def make_model2(nvm, cfg, cnn, enc, mm, precision):
+    m = nvm.Arch2Model(cfg, precision=precision)
+    m.set_params(nvm.BLOCK_CNN, cnn)
+    m.set_params(nvm.BLOCK_EMBEDDING, enc)
+    m.set_params(nvm.BLOCK_MULTIMODAL, mm)
+    return m
+
+
+@pytest.mark.parametrize("name,prec,tol", PRECISIONS)
+def test_arch2_ragged_batch_live_oracle(name, prec, tol):
+    from oracle import arch2 as A2
+    nvm = nv()
+    cfg = nvm.Arch2Config(V=200, E=24, H=64, L=2, I=40, O=31, T=9, B=37)
+    oc = ocfg2(cfg)
+    cnn, enc, mm = nvm.synth_params2(cfg, seed=5)
+    cnn, enc, mm = cnn * 3, enc * 3, mm * 3
+    q, ln, fc7, lab = nvm.synth_batch2(cfg, 37, seed=6, min_len=1)
+    ln[0] = 1
+    q[0, 1:] = 0
+    ln[:] = np.minimum(ln, 7)                                       # longest question 7 < T: tmax = 9 < T + 2
+    q[:, 7:] = 0
+    m = make_model2(nvm, cfg, cnn, enc, mm, prec)
+    assert np.array_equal(m.get_params(nvm.BLOCK_EMBEDDING), enc)    # LSTM core + LookupTable round trip
+    m.set_batch_host(q, ln, fc7, lab)
+    for mode, seed in ((nvm.MODE_EVAL, None), (nvm.MODE_TRAIN, 99)):
+        f, grads, scores, ctx = A2.jdj(oc, cnn, enc, mm, q, A.l2_normalize_rows(fc7), lab, seed=seed)
+        assert ctx["tmax"] == 9
+        m.forward(mode, seed or 0)
+        assert_close(m.scores(37), scores, tol, f"{name} arch2 scores")
+        assert_close(m.state(37), ctx["out"], tol, f"{name} arch2 encoder output")
+        assert abs(m.loss() - f) <= tol * abs(f)
+        if mode == nvm.MODE_EVAL and tol == FP32_TOL:
+            assert np.array_equal(m.argmax(37), A.argmax_first(scores))
+        m.backward()
+        for blk, gw in zip((nvm.BLOCK_CNN, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
+            assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, f"{name} arch2 grads {blk}")
+    m.close()
+
+
+def test_arch2_full_size_config4_step_and_update():
+    """BASELINE config 4: E=H=512, 1 layer, I=2048 (Inception), 28 steps, B=500; one training-mode JdJ + RMSprop with
+    weight decay 1e-4 against the fp32 oracle."""
+    from oracle import arch2 as A2
+    nvm = nv()
+    cfg = nvm.Arch2Config(I=2048)
+    oc = ocfg2(cfg)
+    cnn, enc, mm = nvm.synth_params2(cfg, seed=123)
+    q, ln, fc7, lab = nvm.synth_batch2(cfg, 500, seed=123)
+    fv = A.l2_normalize_rows(fc7)
+    w = [cnn.copy(), enc.copy(), mm.copy()]
+    ms = [np.zeros_like(x) for x in w]
+    f_ref, _ = A2.train_step(oc, w[0], w[1], w[2], ms, (q, fv, lab), 3e-4, seed=7)
+    f0, grads, scores, _ = A2.jdj(oc, cnn, enc, mm, q, fv, lab, seed=7)
+    for prec in (3, 0):
+        m = make_model2(nvm, cfg, cnn, enc, mm, prec)
+        m.set_batch_host(q, ln, fc7, lab)
+        m.forward(nvm.MODE_TRAIN, 7)
+        assert_close(m.scores(500), scores, FP32_TOL, f"prec {prec} arch2 scores")
+        m.backward()
+        for blk, gw in zip((0, 1, 2), grads):
+            assert_close(np.clip(m.get_grads(blk), -10, 10), gw, FP32_TOL, f"prec {prec} arch2 grads {blk}")
+        m.close()
+        m = make_model2(nvm, cfg, cnn, enc, mm, prec)
+        f = m.train_step_host(np.ascontiguousarray(q), np.ascontiguousarray(ln), np.ascontiguousarray(fc7),
+                              np.ascontiguousarray(lab), 3e-4, 7)
+        assert abs(f - f_ref) <= FP32_TOL * abs(f_ref)
+        for blk, k in zip((0, 1, 2), range(3)):
+            # RMSprop's first step moves every touched weight by ~10*lr*sign(g): near-zero gradients make single
+            # elements sensitive, so the weights are compared in rel-L2 and with an absolute bound of 5% of a step
+            got = m.get_params(blk)
+            e2, _ = rel_err(got, w[k])
+            assert e2 <= 1e-5, f"prec {prec} arch2 weights after the update, block {blk}: rel-l2 {e2:.3e}"
+            assert np.max(np.abs(got - w[k])) <= 0.05 * 10 * 3e-4
+        m.close()
