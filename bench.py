@@ -248,6 +248,55 @@ def run_ours(args):
                 "note": "algorithmic FLOPs (2*M*N*K) / CUDA-event time per GEMM class inside the training step; "
                         "bf16x3 issues 6 MMAs per algorithmic product, fp32_simt runs on the FFMA pipe"}
 
+    # ---- other BASELINE.json configs, device-timed (parity-tested in tests/; reported as extras, not the headline) ----
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = {}
+        # config 3: arch1 eval / inference, forward-only scoring + top-1000 argmax of 100k synthetic questions
+        nv._lib.check(model.lib.nvqa_set_batch(model.handle, dq.ptr, dl.ptr, df.ptr, None, B))
+        nb = 200
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                model.forward(nv.MODE_EVAL, 0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(nb):
+                model.forward(nv.MODE_EVAL, 0)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        extras["arch1_eval_questions_per_s"] = {"value": nb * B / (e0.elapsed_time(e1) / 1e3), "questions": nb * B,
+                                                "config": "BASELINE configs[2]: forward + argmax, batches of 500, device-resident"}
+        # config 4: arch2 training step (E=H=512, 1 layer, 2048-d Inception features, 28 LSTM steps)
+        cfg2 = nv.Arch2Config(I=2048, B=B)
+        m2 = nv.Arch2Model(cfg2, precision=prec, device=local)
+        for blk, w in zip((0, 1, 2), nv.synth_params2(cfg2, seed=123)):
+            m2.set_params(blk, w)
+        q2, l2, f2, y2 = nv.synth_batch2(cfg2, B, seed=123)
+        nv._lib.check(m2.lib.nvqa_set_stream(m2.handle, ctypes.c_void_p(stream.cuda_stream)))
+        bufs2 = [nv.DeviceBuffer(m2, a) for a in (q2, l2, f2, y2)]
+        m2.set_batch_device(bufs2[0], bufs2[1], bufs2[2], bufs2[3], B)
+
+        def step2(i):
+            m2.forward(nv.MODE_TRAIN, 100 + i)
+            m2.backward()
+            m2.rmsprop_step(lr0, wd=1e-4)
+
+        with torch.cuda.stream(stream):
+            for i in range(3):
+                step2(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(args.steps):
+                step2(3 + i)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        extras["arch2_train_samples_per_s"] = {"value": args.steps * B / (e0.elapsed_time(e1) / 1e3),
+                                               "ms_per_step": e0.elapsed_time(e1) / args.steps,
+                                               "config": "BASELINE configs[3]: arch2, E=H=512, L=1, I=2048, 28 steps, B=500, RMSprop wd 1e-4"}
+        m2.close()
+
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -275,7 +324,7 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / args.steps, "last_loss": losses[-1]},
                 "gpu_launches": int(launches),
                 "tflops_algorithmic": value * FLOPS_PER_SAMPLE / 1e12,
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "extras": extras}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -291,6 +340,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("NVQA_PRECISION", DEFAULT_PRECISION), choices=sorted(PREC_NAMES))
     ap.add_argument("--batch", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -323,3 +323,43 @@ def test_arch2_full_size_config4_step_and_update():
             assert e2 <= 1e-5, f"prec {prec} arch2 weights after the update, block {blk}: rel-l2 {e2:.3e}"
             assert np.max(np.abs(got - w[k])) <= 0.05 * 10 * 3e-4
         m.close()
+
+
+def test_eval_100k_questions_properties():
+    """BASELINE config 3: forward-only scoring of 100 000 synthetic questions (200 batches of 500, 10 000 distinct fc7
+    rows indexed by an img_list), top-1000 argmax.  Oracle-checked on three batches; size-independent properties on
+    all: answers in 1..1000, idempotence (a second pass gives bit-identical answers), batch-order independence."""
+    nvm = nv()
+    cfg = nvm.Arch1Config()
+    oc = ocfg(cfg)
+    enc, emb, mm = nvm.synth_params(cfg, seed=123)
+    r = np.random.default_rng(9)
+    nq, nimg = 100_000, 10_000
+    lengths = r.integers(3, cfg.T + 1, nq).astype(np.int32)
+    tok = r.integers(1, cfg.V + 1, (nq, cfg.T)).astype(np.int32)
+    q = np.where(np.arange(cfg.T)[None, :] < lengths[:, None], tok, 0).astype(np.int32)
+    q_ra = nvm.right_align(q, lengths)                                   # 004_eval_model.lua:92
+    fc7_all = np.maximum(0, r.standard_normal((nimg, cfg.I))).astype(np.float32)
+    img_list = r.integers(0, nimg, nq)
+    m = make_model(nvm, cfg, enc, emb, mm, nvm.PREC_BF16X2)
+    answers = np.zeros(nq, dtype=np.int32)
+    for s in range(0, nq, 500):
+        sl = slice(s, s + 500)
+        answers[sl] = m.eval_step_host(np.ascontiguousarray(q_ra[sl]), np.ascontiguousarray(lengths[sl]),
+                                       np.ascontiguousarray(fc7_all[img_list[sl]]))
+    assert answers.min() >= 1 and answers.max() <= cfg.O
+    for s in (0, 49_500, 99_500):                                        # oracle on three batches
+        sl = slice(s, s + 500)
+        scores, _ = A.forward(oc, enc, emb, mm, q_ra[sl], lengths[sl], A.l2_normalize_rows(fc7_all[img_list[sl]]))
+        srt = np.sort(scores, axis=1)
+        safe = (srt[:, -1] - srt[:, -2]) > 1e-4 * np.abs(scores).max()   # top-2 margin above the fp32-parity noise
+        assert safe.mean() > 0.9
+        assert np.array_equal(answers[sl][safe], A.argmax_first(scores)[safe])
+    again = np.zeros(1000, dtype=np.int32)
+    perm = np.r_[np.arange(500, 1000), np.arange(0, 500)]                # second pass, batches swapped
+    for k, s in enumerate((500, 0)):
+        sl = slice(s, s + 500)
+        again[sl] = m.eval_step_host(np.ascontiguousarray(q_ra[sl]), np.ascontiguousarray(lengths[sl]),
+                                     np.ascontiguousarray(fc7_all[img_list[sl]]))
+    assert np.array_equal(again, answers[:1000])
+    m.close()
