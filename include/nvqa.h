@@ -138,6 +138,12 @@ int nvqa_eval_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, con
  * state/state_out [n x 2LH], x [n x E]; masks [(L-1) x n x H] or NULL (evaluate mode). */
 int nvqa_lstm_cell_forward(nvqa_model* m, const float* state, const float* x, const float* masks,
                            int32_t n, float* state_out);
+/* netdef.AxB():forward({q, i}) (misc/netdef.lua:6-14): q [n x 2LH], i [n x I] -> out [n x C]; masks NULL = evaluate */
+int nvqa_axb_forward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
+                     int32_t n, float* out);
+/* optim.rmsprop update (misc/rmsprop_lrscale.lua:26-34) on arbitrary device vectors of length n */
+int nvqa_rmsprop_vector(nvqa_model* m, float* x, const float* g, float* state_m, int64_t n, float lr, float alpha,
+                        float eps, float wd, float clamp, float grad_scale);
 /* nn.CrossEntropyCriterion forward+backward on device scores [n x O] (labels 1-based) */
 int nvqa_cross_entropy(nvqa_model* m, const float* scores, const int32_t* labels, int32_t n,
                        float* loss_host, float* dscores);

@@ -55,6 +55,8 @@ SIGNATURES = {
                                        C.c_float, C.c_uint64, c_f32p]),
     "nvqa_eval_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "nvqa_lstm_cell_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "nvqa_axb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "nvqa_rmsprop_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_float] * 6),
     "nvqa_cross_entropy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, c_f32p, C.c_void_p]),
     "nvqa_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "nvqa_host_free": (C.c_int, [C.c_void_p]),

@@ -854,6 +854,38 @@ extern "C" int nvqa_lstm_cell_forward(nvqa_model* m, const float* state, const f
   return 0;
 }
 
+// netdef.AxB():forward({q, i}) (misc/netdef.lua:6-14) on device pointers: q [n x 2LH], i [n x I] -> out [n x C].
+// masks_q / masks_i: explicit Dropout multipliers or NULL (evaluate mode).
+extern "C" int nvqa_axb_forward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
+                                int32_t n, float* out) {
+  NVQA_CHECK(m && q && i && out, "null argument");
+  NVQA_CHECK(m->cfg.arch == 1, "AxB belongs to arch 1");
+  NVQA_CHECK(n > 0 && n <= m->cfg.B, "row count out of range");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  const nvqa_config& c = m->cfg;
+  const int S = m->S;
+  cudaStream_t s = m->stream;
+  Drop dq, di, none;
+  dq.mask = masks_q; dq.key = 0; dq.thresh = 0; dq.scale = 1.f; dq.mode = masks_q ? 1 : 0;
+  di = dq; di.mask = masks_i; di.mode = masks_i ? 1 : 0;
+  none = dq; none.mask = nullptr; none.mode = 0;
+  NVQA_TRY(mask_copy(s, q, S, nullptr, m->qd, dq, n, S));
+  NVQA_TRY(mask_copy(s, i, c.I, nullptr, m->vd, di, n, c.I));
+  NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
+  NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
+  NVQA_TRY(fuse_fwd(s, m->qc, m->ic, out, none, n, c.C));
+  return 0;
+}
+
+// optim.rmsprop's update (misc/rmsprop_lrscale.lua:26-34, lrs = 1) on arbitrary device vectors:
+// g' = clamp(g * grad_scale) + wd * x;  m = alpha m + (1 - alpha) g'^2;  x -= lr g' / (sqrt(m) + eps)
+extern "C" int nvqa_rmsprop_vector(nvqa_model* m, float* x, const float* g, float* state_m, int64_t n, float lr, float alpha,
+                                   float eps, float wd, float clamp, float grad_scale) {
+  NVQA_CHECK(m && x && g && state_m && n > 0, "bad argument");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  return clamp_rmsprop(m->stream, x, const_cast<float*>(g), state_m, n, lr, alpha, eps, wd, clamp, grad_scale);
+}
+
 extern "C" int nvqa_cross_entropy(nvqa_model* m, const float* scores, const int32_t* labels, int32_t n, float* loss_host,
                                   float* dscores) {
   NVQA_CHECK(m && scores && labels, "null argument");
