@@ -482,6 +482,35 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
     const int H4 = H >> 2;
     const long long items = (long long)B * H4;
     const long long gthreads = (long long)G * LP_EPI_THREADS;
+    // Every thread owns the same <= 2 items (batch row b, 4 hidden units) at every step, so the dc carry lives in
+    // registers and the step-invariant operands (gates_t, c_{t-1}) of the NEXT step are prefetched from HBM while the
+    // tensor cores run this step's phase B.
+    constexpr int NI = 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool valid[NI];
+    int bq[NI], ucol[NI], first_t[NI];
+    float4 gi[NI], gf[NI], go[NI], gg[NI], cp[NI], cn[NI], dcr[NI];
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      const long long i = (long long)cta * LP_EPI_THREADS + et + (long long)n * gthreads;
+      valid[n] = i < items;
+      bq[n] = valid[n] ? (int)(i / H4) : 0;
+      ucol[n] = valid[n] ? (int)(i % H4) * 4 : 0;
+      first_t[n] = valid[n] ? (len ? T - len[bq[n]] : 0) : T;          // row active iff t >= first_t
+      gi[n] = gf[n] = go[n] = gg[n] = cp[n] = cn[n] = dcr[n] = z;
+      if (T - 1 >= first_t[n]) {
+        const size_t row = (size_t)(T - 1) * B + bq[n];
+        const float* g = gates + row * 4 * H + ucol[n];
+        gi[n] = *reinterpret_cast<const float4*>(g);
+        gf[n] = *reinterpret_cast<const float4*>(g + H);
+        go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+        gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+        cp[n] = *reinterpret_cast<const float4*>(c + row * H + ucol[n]);
+        cn[n] = *reinterpret_cast<const float4*>(c + (row + B) * H + ucol[n]);
+        dcr[n] = *reinterpret_cast<const float4*>(dc0 + (size_t)bq[n] * ld0 + ucol[n]);
+      }
+    }
+    const size_t BHs = (size_t)B * H;
     for (int t = T - 1; t >= 0; --t) {
       const unsigned int k = (unsigned int)(T - 1 - t);
       if (et == 0) LP_STAMP(t, 0);
@@ -491,98 +520,89 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       }
       if (et == 0) LP_STAMP(t, 1);
       // ---- phase A: cell backward, element-wise ----
-      const size_t BHs = (size_t)B * H;
       const float* dh_src = dhbuf + (size_t)((t + 1) & 1) * 4 * BHs;      // 4 split-K partials of dh_t
       float* dh_part = dhbuf + ((size_t)(t & 1) * 4 + ks) * BHs;          // this split's partial of dh_{t-1}
-      // two items per pass with all loads issued up front (the phase is latency-bound, not bandwidth-bound)
-      for (long long i0 = (long long)cta * LP_EPI_THREADS + et; i0 < items; i0 += 2 * gthreads) {
-        constexpr int NI = 2;
-        bool valid[NI], act[NI];
-        size_t row[NI], o[NI];
-        int ucol[NI];
-        float4 gi[NI], gf[NI], go[NI], gg[NI], cp[NI], cn[NI], dh[NI], dc[NI];
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 dai[NI], daf[NI], dao[NI], dag[NI];
+      size_t row[NI];
 #pragma unroll
-        for (int n = 0; n < NI; ++n) {
-          const long long i = i0 + (long long)n * gthreads;
-          valid[n] = i < items;
-          const int b = valid[n] ? (int)(i / H4) : 0;
-          ucol[n] = valid[n] ? (int)(i % H4) * 4 : 0;
-          row[n] = (size_t)t * B + b;
-          o[n] = (size_t)b * H + ucol[n];
-          act[n] = valid[n] && (!len || t >= T - len[b]);
-          gi[n] = gf[n] = go[n] = gg[n] = cp[n] = cn[n] = dh[n] = dc[n] = z;
-          if (act[n]) {
-            const float* g = gates + row[n] * 4 * H + ucol[n];
-            gi[n] = *reinterpret_cast<const float4*>(g);
-            gf[n] = *reinterpret_cast<const float4*>(g + H);
-            go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
-            gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
-            cp[n] = *reinterpret_cast<const float4*>(c + row[n] * H + ucol[n]);
-            cn[n] = *reinterpret_cast<const float4*>(c + (row[n] + B) * H + ucol[n]);
-            if (t == T - 1) {
-              dh[n] = *reinterpret_cast<const float4*>(dh0 + (size_t)b * ld0 + ucol[n]);
-              dc[n] = *reinterpret_cast<const float4*>(dc0 + (size_t)b * ld0 + ucol[n]);
-            } else {
-              const float* ds = dh_src + o[n];
-              float4 d0 = *reinterpret_cast<const float4*>(ds), d1 = *reinterpret_cast<const float4*>(ds + BHs),
-                     d2 = *reinterpret_cast<const float4*>(ds + 2 * BHs), d3 = *reinterpret_cast<const float4*>(ds + 3 * BHs);
-              dh[n] = make_float4((d0.x + d1.x) + (d2.x + d3.x), (d0.y + d1.y) + (d2.y + d3.y),
-                                  (d0.z + d1.z) + (d2.z + d3.z), (d0.w + d1.w) + (d2.w + d3.w));
-              dc[n] = *reinterpret_cast<const float4*>(dcbuf + o[n]);
-            }
-            if (dh_above) {
-              float4 ua = *reinterpret_cast<const float4*>(dh_above + row[n] * H + ucol[n]);
-              float4 mk = drop_at4(drop, (uint64_t)row[n] * H + ucol[n]);
-              dh[n].x += ua.x * mk.x; dh[n].y += ua.y * mk.y; dh[n].z += ua.z * mk.z; dh[n].w += ua.w * mk.w;
-            }
+      for (int n = 0; n < NI; ++n) {
+        row[n] = (size_t)t * B + bq[n];
+        dai[n] = daf[n] = dao[n] = dag[n] = z;
+        if (!valid[n]) continue;
+        if (t >= first_t[n]) {
+          const size_t o = (size_t)bq[n] * H + ucol[n];
+          float4 dh;
+          if (t == T - 1) {
+            dh = *reinterpret_cast<const float4*>(dh0 + (size_t)bq[n] * ld0 + ucol[n]);
+          } else {
+            const float* ds = dh_src + o;
+            float4 d0 = *reinterpret_cast<const float4*>(ds), d1 = *reinterpret_cast<const float4*>(ds + BHs),
+                   d2 = *reinterpret_cast<const float4*>(ds + 2 * BHs), d3 = *reinterpret_cast<const float4*>(ds + 3 * BHs);
+            dh = make_float4((d0.x + d1.x) + (d2.x + d3.x), (d0.y + d1.y) + (d2.y + d3.y), (d0.z + d1.z) + (d2.z + d3.z),
+                             (d0.w + d1.w) + (d2.w + d3.w));
           }
-        }
-#pragma unroll
-        for (int n = 0; n < NI; ++n) {
-          if (!valid[n]) continue;
-          float4 dai = z, daf = z, dao = z, dag = z, dcp = z;
-          if (act[n]) {
-#define LB(kk)                                                                   \
-            { float tc = fast_tanh(cn[n].kk);                                      \
-              float dct = dc[n].kk + dh[n].kk * go[n].kk * (1.0f - tc * tc);       \
-              dao.kk = dh[n].kk * tc * go[n].kk * (1.0f - go[n].kk);               \
-              dai.kk = dct * gg[n].kk * gi[n].kk * (1.0f - gi[n].kk);              \
-              daf.kk = dct * cp[n].kk * gf[n].kk * (1.0f - gf[n].kk);              \
-              dag.kk = dct * gi[n].kk * (1.0f - gg[n].kk * gg[n].kk);              \
-              dcp.kk = dct * gf[n].kk; }
-            LB(x) LB(y) LB(z) LB(w)
+          if (dh_above) {
+            float4 ua = *reinterpret_cast<const float4*>(dh_above + row[n] * H + ucol[n]);
+            float4 mk = drop_at4(drop, (uint64_t)row[n] * H + ucol[n]);
+            dh.x += ua.x * mk.x; dh.y += ua.y * mk.y; dh.z += ua.z * mk.z; dh.w += ua.w * mk.w;
+          }
+#define LB(kk)                                                                     \
+          { float tc = fast_tanh(cn[n].kk);                                          \
+            float dct = dcr[n].kk + dh.kk * go[n].kk * (1.0f - tc * tc);             \
+            dao[n].kk = dh.kk * tc * go[n].kk * (1.0f - go[n].kk);                   \
+            dai[n].kk = dct * gg[n].kk * gi[n].kk * (1.0f - gi[n].kk);               \
+            daf[n].kk = dct * cp[n].kk * gf[n].kk * (1.0f - gf[n].kk);               \
+            dag[n].kk = dct * gi[n].kk * (1.0f - gg[n].kk * gg[n].kk);               \
+            dcr[n].kk = dct * gf[n].kk; }
+          LB(x) LB(y) LB(z) LB(w)
 #undef LB
-          }
-          float* dr = da + row[n] * 4 * H + ucol[n];
-          *reinterpret_cast<float4*>(dr) = dai;
-          *reinterpret_cast<float4*>(dr + H) = daf;
-          *reinterpret_cast<float4*>(dr + 2 * H) = dao;
-          *reinterpret_cast<float4*>(dr + 3 * H) = dag;
-          *reinterpret_cast<float4*>(dcbuf + o[n]) = dcp;
-          const float4 gsrc[4] = {dai, daf, dao, dag};
+        }
+        // (1) what phase B consumes through TMA: da_t as bf16 planes
+        const float4 gsrc[4] = {dai[n], daf[n], dao[n], dag[n]};
 #pragma unroll
-          for (int gI = 0; gI < 4; ++gI) {
-            __nv_bfloat16 pl[3][4];
-            split3(gsrc[gI].x, pl[0][0], pl[1][0], pl[2][0]);
-            split3(gsrc[gI].y, pl[0][1], pl[1][1], pl[2][1]);
-            split3(gsrc[gI].z, pl[0][2], pl[1][2], pl[2][2]);
-            split3(gsrc[gI].w, pl[0][3], pl[1][3], pl[2][3]);
+        for (int gI = 0; gI < 4; ++gI) {
+          __nv_bfloat16 pl[3][4];
+          split3(gsrc[gI].x, pl[0][0], pl[1][0], pl[2][0]);
+          split3(gsrc[gI].y, pl[0][1], pl[1][1], pl[2][1]);
+          split3(gsrc[gI].z, pl[0][2], pl[1][2], pl[2][2]);
+          split3(gsrc[gI].w, pl[0][3], pl[1][3], pl[2][3]);
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-              uint2 ov;
-              ov.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
-              ov.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
-              *reinterpret_cast<uint2*>(dap + (size_t)p * dap_plane + row[n] * 4 * H + (size_t)gI * H + ucol[n]) = ov;
-            }
+          for (int p = 0; p < P; ++p) {
+            uint2 ov;
+            ov.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+            ov.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+            *reinterpret_cast<uint2*>(dap + (size_t)p * dap_plane + row[n] * 4 * H + (size_t)gI * H + ucol[n]) = ov;
           }
         }
       }
-      // publish da_t (barrier 2k+1)
+      // (2) publish da_t (barrier 2k+1)
       if (et == 0) LP_STAMP(t, 2);
       fence_proxy_async();
       named_bar_sync(1, LP_EPI_THREADS);
       if (et == 0) { LP_STAMP(t, 3); grid_arrive(counter); LP_STAMP(t, 4); }
+      named_bar_sync(3, LP_EPI_THREADS);          // keep the SM's memory pipeline clear until the release is out
+      // (3) off the critical path: fp32 da_t (bias column sums), and the prefetch of step t-1's gates / cell states
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        if (!valid[n]) continue;
+        float* dr = da + row[n] * 4 * H + ucol[n];
+        *reinterpret_cast<float4*>(dr) = dai[n];
+        *reinterpret_cast<float4*>(dr + H) = daf[n];
+        *reinterpret_cast<float4*>(dr + 2 * H) = dao[n];
+        *reinterpret_cast<float4*>(dr + 3 * H) = dag[n];
+        if (t > 0) {
+          cn[n] = cp[n];                                               // c_{t-1} becomes the "new" cell of step t-1
+          if (t - 1 >= first_t[n]) {
+            const size_t rp = row[n] - B;
+            const float* g = gates + rp * 4 * H + ucol[n];
+            gi[n] = *reinterpret_cast<const float4*>(g);
+            gf[n] = *reinterpret_cast<const float4*>(g + H);
+            go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+            gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+            cp[n] = *reinterpret_cast<const float4*>(c + rp * H + ucol[n]);
+          }
+        }
+      }
       if (t == 0) break;
       // ---- phase B epilogue: split-K partial of dh_{t-1} ----
       mbar_wait(tfull, k & 1u);
