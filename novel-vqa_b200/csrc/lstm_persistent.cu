@@ -136,7 +136,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
   const uint32_t a0 = w0 + (uint32_t)KB * P * W_TILE;   // A ring: [s][p]
   const uint32_t bar0 = a0 + (uint32_t)S * P * A_PLANE;
   const uint32_t full0 = bar0, empty0 = bar0 + 8 * LP_MAX_STAGES, wfull = bar0 + 16 * LP_MAX_STAGES,
-                 tfull = wfull + 8;
+                 tfull = wfull + 8, gobar = wfull + 24;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * LP_MAX_STAGES + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,6 +153,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
       for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CL); }
       mbar_init(wfull, 1);
       mbar_init(tfull, 1);
+      mbar_init(gobar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -179,6 +180,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
                           g * H + u0 + 8 * cc, p);
     }
     int it = 0;
+    const int gokb = (S < KB ? S : KB) - 1;
     for (int t = 0; t < T; ++t) {
       if (t > 0) {
         // h_{t-1} rows of THIS batch tile are complete once the gridDim.x CTAs sharing it have published step t
@@ -206,6 +208,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
                              t * B + m0 + (int)(crank * SL), p, kMask);
             }
           }
+          if (kb == gokb) mbar_arrive(gobar);     // this step's first loads are out: the epilogue may use the memory pipe
         }
       }
       it += KB;
@@ -326,8 +329,11 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
       // hold the other warps until the release is out: their stores / prefetch loads would otherwise sit in front of
       // the membar in the SM's memory pipeline (measured: +3.4k cycles per step)
       named_bar_sync(3, LP_EPI_THREADS);
-      // (3) everything only the backward pass needs goes out OFF the critical path, overlapping the grid barrier
-      // and the next step's TMA loads and MMAs
+      // ... and until the producer thread has seen the barrier open and issued the next step's first TMA loads: its
+      // polling atomics share the SM's memory pipeline with the stores below (measured: each poll took ~2.5 us)
+      if (t + 1 < T) mbar_wait(gobar, (uint32_t)(t + 1) & 1u);
+      // (3) everything only the backward pass needs goes out OFF the critical path, overlapping the next step's TMA
+      // loads and MMAs
       if (rowok) {
         float* gdst = pre + rin * 4 * H + uo;
 #define ST8(ptr, a)                                                                          \
@@ -380,7 +386,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
   const uint32_t a0 = w0 + (uint32_t)KB * P * W_TILE;
   const uint32_t bar0 = a0 + (uint32_t)S * P * A_PLANE;
   const uint32_t full0 = bar0, empty0 = bar0 + 8 * LP_MAX_STAGES, wfull = bar0 + 16 * LP_MAX_STAGES,
-                 tfull = wfull + 8;
+                 tfull = wfull + 8, gobar = wfull + 24;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * LP_MAX_STAGES + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -399,6 +405,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CL); }
       mbar_init(wfull, 1);
       mbar_init(tfull, 1);
+      mbar_init(gobar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -420,6 +427,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
         for (int p = 0; p < P; ++p)
           tma_load_3d(w0 + (uint32_t)(kb * P + p) * W_TILE, &mapW, wfull, n0, k_base + kb * 64, p);
       int it = 0;
+      const int gokb = (S < KB ? S : KB) - 1;
       for (int t = T - 1; t >= 1; --t) {
         const unsigned int k = (unsigned int)(T - 1 - t);
         grid_wait(counter, (2 * k + 1) * G);             // da_t is complete everywhere
@@ -439,6 +447,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
                              k_base + kb * 64, t * B + m0 + (int)(crank * SL), p, kMask);
             }
           }
+          if (kb == gokb) mbar_arrive(gobar);
         }
       }
     }
@@ -581,6 +590,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       named_bar_sync(1, LP_EPI_THREADS);
       if (et == 0) { LP_STAMP(t, 3); grid_arrive(counter); LP_STAMP(t, 4); }
       named_bar_sync(3, LP_EPI_THREADS);          // keep the SM's memory pipeline clear until the release is out
+      if (t >= 1) mbar_wait(gobar, k & 1u);          // ... and until the producer has seen da_t complete and issued its loads
       // (3) off the critical path: fp32 da_t (bias column sums), and the prefetch of step t-1's gates / cell states
 #pragma unroll
       for (int n = 0; n < NI; ++n) {
