@@ -49,7 +49,10 @@ enum { NVQA_PHASE_HEAD = 0, NVQA_PHASE_LSTM = 1, NVQA_PHASE_EMBED = 2, NVQA_PHAS
 
 /* mirrors the cmd:option block of 002_train_baseline.lua:22-48 */
 typedef struct nvqa_config {
-  int32_t arch;       /* 1 = 002_train_vqa_arch1, 2 = 003_train_vqa_arch2 (image + START + words through a
+  int32_t arch;       /* 3 = 001_train_autoencoder text autoencoder (misc/AutoEncoder_text_nostart.lua): blocks
+                         0 = encoder LSTM core, 1 = decoder LSTM core then Linear(H, V+1), 2 = LookupTable [(V+1) x E]
+                         (nn.AutoEncoder:parameters() order, :86-105); q = seq [B x T] zero-padded right; I, C, O unused;
+                         1 = 002_train_vqa_arch1, 2 = 003_train_vqa_arch2 (image + START + words through a
                          LookupTable LSTM encoder; E = -input_encoding_size, L = -num_layers, C unused;
                          blocks: 0 = cnn_w, 1 = encoder_w_q (LSTM core then LookupTable), 2 = multimodal_w;
                          q is the question matrix as stored, NOT right-aligned)                 */
@@ -111,7 +114,8 @@ int nvqa_set_batch_host(nvqa_model* m, const int32_t* q, const int32_t* len, con
  * emb [T x B x E], lstm [(L-1) x T x B x H], q [B x 2LH], i [B x I], z [B x C].  While unset,
  * training mode draws masks from the counter hash shared with oracle/rng.py. */
 /* arch 2 with device-resident batches: number of LSTM steps to execute = 2 + longest question of the batch
- * (misc/Encoder_lstm.lua:185-189,219); nvqa_set_batch resets it to T + 2, nvqa_set_batch_host derives it from len. */
+ * (misc/Encoder_lstm.lua:185-189,219); nvqa_set_batch resets it to T + 2, nvqa_set_batch_host derives it from len.
+ * arch 3: steps = tmax = longest sequence of the batch (AutoEncoder_text_nostart.lua:281); reset to T / derived from len. */
 int nvqa_set_steps(nvqa_model* m, int32_t steps);
 int nvqa_set_masks(nvqa_model* m, const float* emb, const float* lstm, const float* q, const float* i,
                    const float* z);
@@ -121,6 +125,13 @@ int nvqa_backward(nvqa_model* m, int phase);                     /* criterion/mu
 /* gradients *= grad_scale; clamp(-clamp, clamp); optim.rmsprop (misc/rmsprop_lrscale.lua:14-34) */
 int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps, float wd, float clamp,
                       float grad_scale);
+/* arch 3: grad_params:clamp(-clamp, clamp); grad_params:add(wd, params); adam(...)
+ * (001_train_autoencoder/001_train_arch1_text_autoencoder.lua:237-243, misc/optim_updates.lua:78-111) */
+int nvqa_adam_step(nvqa_model* m, float lr, float beta1, float beta2, float eps, float wd, float clamp,
+                   float grad_scale);
+/* arch 3: log-probabilities [B x (V+1)] of decoder step `step` (0-based; self.output_dec[step+1],
+ * AutoEncoder_text_nostart.lua:334); valid after nvqa_forward until nvqa_backward consumes them in place */
+int nvqa_logprobs_get(nvqa_model* m, int32_t step, float* host_dst);
 int nvqa_scores_get(nvqa_model* m, float* host_dst);             /* [B x O]                       */
 int nvqa_argmax_get(nvqa_model* m, int32_t* host_dst);           /* torch.max(scores,2), 1-based  */
 int nvqa_state_get(nvqa_model* m, float* host_dst);              /* final LSTM state tv_q [B x 2LH] */

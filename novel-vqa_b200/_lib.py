@@ -48,6 +48,8 @@ SIGNATURES = {
     "nvqa_loss": (C.c_int, [C.c_void_p, c_f32p]),
     "nvqa_backward": (C.c_int, [C.c_void_p, C.c_int]),
     "nvqa_rmsprop_step": (C.c_int, [C.c_void_p] + [C.c_float] * 6),
+    "nvqa_adam_step": (C.c_int, [C.c_void_p] + [C.c_float] * 7),
+    "nvqa_logprobs_get": (C.c_int, [C.c_void_p, C.c_int32, c_f32p]),
     "nvqa_scores_get": (C.c_int, [C.c_void_p, c_f32p]),
     "nvqa_argmax_get": (C.c_int, [C.c_void_p, c_i32p]),
     "nvqa_state_get": (C.c_int, [C.c_void_p, c_f32p]),

@@ -14,13 +14,15 @@ from ._lib import (PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_BF16X2, BLOCK_EN
                    BLOCK_MULTIMODAL, MODE_EVAL, MODE_TRAIN, PHASE_HEAD, PHASE_LSTM, PHASE_EMBED, PHASE_ALL,
                    NvqaError)
 
-__all__ = ["Arch1Config", "Arch1Model", "Arch2Config", "Arch2Model", "synth_params2", "synth_batch2", "BLOCK_CNN", "DeviceBuffer", "right_align", "pack_batch", "synth_batch", "synth_params",
+__all__ = ["Arch1Config", "Arch1Model", "Arch2Config", "Arch2Model", "synth_params2", "synth_batch2", "BLOCK_CNN",
+           "AEConfig", "AEModel", "synth_params_ae", "synth_batch_ae", "BLOCK_AE_ENCODER", "BLOCK_AE_DECODER", "BLOCK_AE_LOOKUP", "DeviceBuffer", "right_align", "pack_batch", "synth_batch", "synth_params",
            "device_count", "launch_count", "PREC_FP32_SIMT", "PREC_BF16X3", "PREC_BF16", "PREC_BF16X2",
            "BLOCK_ENCODER", "BLOCK_EMBEDDING", "BLOCK_MULTIMODAL", "MODE_EVAL", "MODE_TRAIN", "PHASE_HEAD",
            "PHASE_LSTM", "PHASE_EMBED", "PHASE_ALL", "NvqaError", "DECAY_FACTOR"]
 
 DECAY_FACTOR = 0.99997592083      # 002_train_baseline.lua:78
 BLOCK_CNN = 0                     # arch2 blocks: cnn_w, encoder_w_q (LSTM core + LookupTable), multimodal_w
+BLOCK_AE_ENCODER, BLOCK_AE_DECODER, BLOCK_AE_LOOKUP = 0, 1, 2   # nn.AutoEncoder:parameters() order
 
 
 @dataclass
@@ -274,6 +276,82 @@ class Arch2Model(Arch1Model):
 
     def set_masks(self, lstm=None, z=None):
         super().set_masks(emb=None, lstm=lstm, q=None, i=None, z=z)
+
+
+@dataclass
+class AEConfig:
+    """Defaults = cmd:option defaults of 001_train_autoencoder/001_train_arch1_text_autoencoder.lua:27-37 and the
+    prepro defaults (000_prepro_book_corpus.py:265,270): V = 20000 (+1), seq_length 16, batch 1000."""
+    V: int = 20000
+    E: int = 512
+    H: int = 512
+    L: int = 1
+    T: int = 16
+    B: int = 1000
+    dropout: float = 0.5
+    I: int = 4
+    C: int = 0
+    O: int = 4
+    img_norm: int = 0
+
+    @property
+    def S(self):
+        return 2 * self.L * self.H
+
+
+class AEModel(Arch1Model):
+    """001_train_autoencoder: nn.AutoEncoder (LSTM encoder -> LSTM decoder over a shared LookupTable) +
+    nn.LanguageModelCriterion + clamp / weight decay / adam.  Blocks: BLOCK_AE_ENCODER, BLOCK_AE_DECODER (LSTM core then
+    Linear(H, V+1)), BLOCK_AE_LOOKUP.  seq is [B x T], zero-padded on the right (the reference's [T x B] transposed)."""
+    ARCH = 3
+    CONFIG = AEConfig
+
+    def set_batch_host(self, seq, lengths=None):
+        seq = _i32(seq)
+        lengths = _i32((seq != 0).sum(axis=1) if lengths is None else lengths)
+        self._keep = [seq, lengths]
+        _lib.check(self.lib.nvqa_set_batch_host(self.handle, _ptr(seq), _ptr(lengths), None, None, seq.shape[0]))
+        self.sync()
+
+    def set_batch_device(self, seq, B, tmax):
+        self._keep = [seq]
+        _lib.check(self.lib.nvqa_set_batch(self.handle, seq.ptr, None, None, None, B))
+        _lib.check(self.lib.nvqa_set_steps(self.handle, tmax))
+
+    def adam_step(self, lr=1e-5, beta1=0.8, beta2=0.999, eps=1e-8, wd=1e-6, clamp=0.1, grad_scale=1.0):
+        _lib.check(self.lib.nvqa_adam_step(self.handle, lr, beta1, beta2, eps, wd, clamp, grad_scale))
+
+    def logprobs(self, step, B):
+        out = np.empty((B, self.cfg.V + 1), dtype=np.float32)
+        _lib.check(self.lib.nvqa_logprobs_get(self.handle, step, out.ctypes.data_as(_lib.c_f32p)))
+        return out
+
+    def train_step_host(self, seq, lengths, lr, seed):
+        out = C.c_float(0)
+        seq, lengths = _i32(seq), _i32(lengths)
+        _lib.check(self.lib.nvqa_train_step_host(self.handle, _ptr(seq), _ptr(lengths), None, None, seq.shape[0], lr, seed,
+                                                 C.byref(out)))
+        return out.value
+
+
+def synth_params_ae(cfg, seed=123):
+    """uniform(-0.08, 0.08) over encoder, decoder, lookup_table (flat parameter order of nn.AutoEncoder)."""
+    r = np.random.default_rng(seed)
+    n_core = sum(4 * cfg.H * ((cfg.E if l == 0 else cfg.H) + cfg.H + 2) for l in range(cfg.L))
+    enc = r.uniform(-0.08, 0.08, n_core).astype(np.float32)
+    dec = r.uniform(-0.08, 0.08, n_core + (cfg.V + 1) * cfg.H + cfg.V + 1).astype(np.float32)
+    lut = r.uniform(-0.08, 0.08, (cfg.V + 1) * cfg.E).astype(np.float32)
+    return enc, dec, lut
+
+
+def synth_batch_ae(cfg, B, seed=123, min_len=4):
+    """book-corpus-shaped token sequences: U{1..V} tokens, lengths U{min_len..T}, zero-padded right."""
+    r = np.random.default_rng(seed)
+    T = cfg.T
+    lengths = r.integers(min_len, T + 1, B).astype(np.int32)
+    tok = r.integers(1, cfg.V + 1, (B, T)).astype(np.int32)
+    seq = np.where(np.arange(T)[None, :] < lengths[:, None], tok, 0).astype(np.int32)
+    return seq, lengths
 
 
 def synth_params2(cfg, seed=123):

@@ -261,6 +261,12 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
     float ccarry[8];                               // c_{t-1} of this thread's (row, 8 units): never leaves registers
 #pragma unroll
     for (int j = 0; j < 8; ++j) ccarry[j] = 0.f;
+    if (rowok) {                                   // slot 0 of c: zeros, or the initial state handed over by a previous segment
+      const float4 c0a = *reinterpret_cast<const float4*>(c + (size_t)b * H + uo);
+      const float4 c0b = *reinterpret_cast<const float4*>(c + (size_t)b * H + uo + 4);
+      ccarry[0] = c0a.x; ccarry[1] = c0a.y; ccarry[2] = c0a.z; ccarry[3] = c0a.w;
+      ccarry[4] = c0b.x; ccarry[5] = c0b.y; ccarry[6] = c0b.z; ccarry[7] = c0b.w;
+    }
     for (int t = 0; t < T; ++t) {
       const bool active = rowok && (t >= T - mylen);
       const size_t rin = (size_t)t * B + b, rout = (size_t)(t + 1) * B + b;
@@ -375,7 +381,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
                            const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ dh0,
                            const float* __restrict__ dc0, int ld0, const float* __restrict__ dh_above, Drop drop,
                            float* __restrict__ da, __nv_bfloat16* __restrict__ dap, long long dap_plane,
-                           float* __restrict__ dhbuf, float* __restrict__ dcbuf, const int32_t* __restrict__ len, int T,
+                           float* __restrict__ dhbuf, float* __restrict__ dc_init, const int32_t* __restrict__ len, int T,
                            int B, int H, int KB, int S, unsigned int* counter, long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -394,6 +400,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
   const unsigned int G = gridDim.x * gridDim.y * gridDim.z;
   const unsigned int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const int k_base = ks * H;                 // this split's gate block inside the 4H contraction dimension
+  const int tlast = dc_init ? 0 : 1;         // with dc_init: also produce d(initial state) (dh partials of step 0 + dc)
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapDA) : "memory");
@@ -428,7 +435,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
           tma_load_3d(w0 + (uint32_t)(kb * P + p) * W_TILE, &mapW, wfull, n0, k_base + kb * 64, p);
       int it = 0;
       const int gokb = (S < KB ? S : KB) - 1;
-      for (int t = T - 1; t >= 1; --t) {
+      for (int t = T - 1; t >= tlast; --t) {
         const unsigned int k = (unsigned int)(T - 1 - t);
         grid_wait(counter, (2 * k + 1) * G);             // da_t is complete everywhere
         fence_proxy_async();
@@ -457,7 +464,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);      // B = W_hh slice, MN-major
       mbar_wait(wfull, 0);
       int it = 0;
-      for (int t = T - 1; t >= 1; --t) {
+      for (int t = T - 1; t >= tlast; --t) {
         uint32_t acc = 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % S;
@@ -590,7 +597,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       named_bar_sync(1, LP_EPI_THREADS);
       if (et == 0) { LP_STAMP(t, 3); grid_arrive(counter); LP_STAMP(t, 4); }
       named_bar_sync(3, LP_EPI_THREADS);          // keep the SM's memory pipeline clear until the release is out
-      if (t >= 1) mbar_wait(gobar, k & 1u);          // ... and until the producer has seen da_t complete and issued its loads
+      if (t >= tlast) mbar_wait(gobar, k & 1u);      // ... and until the producer has seen da_t complete and issued its loads
       // (3) off the critical path: fp32 da_t (bias column sums), and the prefetch of step t-1's gates / cell states
 #pragma unroll
       for (int n = 0; n < NI; ++n) {
@@ -600,6 +607,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
         *reinterpret_cast<float4*>(dr + H) = daf[n];
         *reinterpret_cast<float4*>(dr + 2 * H) = dao[n];
         *reinterpret_cast<float4*>(dr + 3 * H) = dag[n];
+        if (t == 0 && dc_init) *reinterpret_cast<float4*>(dc_init + (size_t)bq[n] * H + ucol[n]) = dcr[n];
         if (t > 0) {
           cn[n] = cp[n];                                               // c_{t-1} becomes the "new" cell of step t-1
           if (t - 1 >= first_t[n]) {
@@ -613,7 +621,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
           }
         }
       }
-      if (t == 0) break;
+      if (t < tlast) break;
       // ---- phase B epilogue: split-K partial of dh_{t-1} ----
       mbar_wait(tfull, k & 1u);
       tc_fence_after();
@@ -672,10 +680,21 @@ static int persistent_limits(int* num_sms, int* max_smem) {
   return 0;
 }
 
+// dh_init[b][u] = sum of the four split-K partials of d h_{-1} left in dhbuf slot 0 by step 0 (fixed order)
+__global__ void __launch_bounds__(256) sum4_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4* p = reinterpret_cast<const float4*>(part);
+  float4 a = p[i], b = p[i + n4], c = p[i + 2 * n4], d = p[i + 3 * n4];
+  reinterpret_cast<float4*>(out)[i] = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z),
+                                                  (a.w + b.w) + (c.w + d.w));
+}
+
 int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
                         const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* da,
-                        __nv_bfloat16* dap, float* dhbuf, float* dcbuf, const int32_t* len, int T, int B, int H,
-                        unsigned int* counter) {
+                        __nv_bfloat16* dap, long long dap_plane_rows, float* dhbuf, float* dh_init, float* dc_init,
+                        const int32_t* len, int T, int B, int H, unsigned int* counter) {
+  if ((dh_init == nullptr) != (dc_init == nullptr)) return -1;
   if (P < 1 || P > 2) return -1;
   if (H % 64 != 0 || H < 64) return -1;
   int num_sms = 0, max_smem = 0;
@@ -696,9 +715,10 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 64, &mapW));             // MN-major B: 64 k-rows x 64 columns
   int CL = cluster_pref();
   if ((int)grid.x % CL != 0) CL = 1;
-  NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 128 / CL, &mapDA));
+  if (dap_plane_rows <= 0) dap_plane_rows = (long long)T * B;
+  NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 128 / CL, &mapDA, dap_plane_rows * 4 * H));
   NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
-  long long dap_plane = (long long)T * B * 4 * H;
+  long long dap_plane = dap_plane_rows * 4 * H;
   int KBv = KB, Sv = S;
   long long* dbg = nullptr;
   static const bool want_dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
@@ -706,7 +726,7 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
     NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbg), (size_t)T * 8 * sizeof(long long)));
     NVQA_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(long long), s));
   }
-  void* args[] = {&mapDA, &mapW, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &da, &dap, &dap_plane, &dhbuf, &dcbuf,
+  void* args[] = {&mapDA, &mapW, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &da, &dap, &dap_plane, &dhbuf, &dc_init,
                   &len, &T, &B, &H, &KBv, &Sv, &counter, &dbg};
   const void* fn = nullptr;
 #define LP_PICK(P_, CL_) if (P == P_ && CL == CL_) fn = (const void*)lstm_bwd_persistent_kernel<P_, CL_>
@@ -718,11 +738,16 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   if (le != cudaSuccess && CL > 1) {          // clusters could not be made co-resident: fall back to unicast loads
     (void)cudaGetLastError();
     g_cluster = 1;
-    return lstm_bwd_persistent(s, ws, P, Wh, gates, c, dh0, dc0, ld0, dh_above, d, da, dap, dhbuf, dcbuf, len, T, B, H,
-                               counter);
+    return lstm_bwd_persistent(s, ws, P, Wh, gates, c, dh0, dc0, ld0, dh_above, d, da, dap, dap_plane_rows, dhbuf, dh_init,
+                               dc_init, len, T, B, H, counter);
   }
   NVQA_CUDA(le);
   ++g_launches;
+  if (dh_init) {
+    const long long n4 = (long long)B * H / 4;
+    sum4_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(dhbuf, dh_init, n4);
+    NVQA_LAUNCHED();
+  }
   if (want_dbg) {
     std::vector<long long> hbuf((size_t)T * 8);
     NVQA_CUDA(cudaStreamSynchronize(s));
@@ -740,8 +765,8 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
 
 // ------------------------------------------------------------------------------------------------
 int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
-                        __nv_bfloat16* hp, float* xdrop_next, const int32_t* len, Drop d, int T, int B, int H,
-                        unsigned int* counter) {
+                        __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
+                        int B, int H, unsigned int* counter) {
   if (P < 1 || P > 2) return -1;                 // P = 3: W_hh does not fit in shared memory next to the A ring
   if (H % 64 != 0 || H < 64) return -1;
   static int num_sms = 0, max_smem = 0;
@@ -767,9 +792,10 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 8, &mapW));
   int CL = cluster_pref();
   if ((int)grid.x % CL != 0) CL = 1;
-  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 128 / CL, &mapH));
+  if (hp_plane_rows <= 0) hp_plane_rows = (long long)(T + 1) * B;
+  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 128 / CL, &mapH, hp_plane_rows * H));
   NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));      // one counter line per batch tile
-  long long hp_plane = (long long)(T + 1) * B * H;
+  long long hp_plane = hp_plane_rows * H;
   int KBv = KB, Sv = S;
   long long* dbg = nullptr;
   static const bool want_dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
@@ -793,7 +819,7 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   if (le != cudaSuccess && CL > 1) {          // clusters could not be made co-resident: fall back to unicast loads
     (void)cudaGetLastError();
     g_cluster = 1;
-    return lstm_fwd_persistent(s, ws, P, Wh, pre, c, h, hp, xdrop_next, len, d, T, B, H, counter);
+    return lstm_fwd_persistent(s, ws, P, Wh, pre, c, h, hp, hp_plane_rows, xdrop_next, len, d, T, B, H, counter);
   }
   NVQA_CUDA(le);
   ++g_launches;

@@ -11,17 +11,20 @@ namespace nvqa {
 //   xdrop_next [T][B][H] = Dropout(h_t) for the layer above (nullptr for the top layer)
 // Returns 0 on success, -1 when the shape/precision is not supported (caller falls back to per-step kernels),
 // > 0 on error.
+// c slot 0 / hp slot 0 hold the INITIAL state (zeros, or the last slot of a preceding segment of the same buffers);
+// hp_plane_rows = rows between consecutive planes of hp (0: (T+1)*B).
 int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
-                        __nv_bfloat16* hp, float* xdrop_next, const int32_t* len, Drop d, int T, int B, int H,
-                        unsigned int* counter);
+                        __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
+                        int B, int H, unsigned int* counter);
 
 // All T steps of one layer's backward recurrence (see lstm_persistent.cu).
 //   gates [T][B][4H] post-activation, c [(T+1)][B][H]; dh0/dc0 (leading dim ld0): d(final state) of this layer;
 //   dh_above [T][B][H]: dX of the layer above (masked by its input Dropout) or nullptr;
-//   out: da [T*B][4H] fp32 and dap [P][T*B][4H] bf16 planes; scratch dhbuf [2][4][B][H], dcbuf [B][H].
+//   out: da [T*B][4H] fp32 and dap [P][T*B][4H] bf16 planes (dap_plane_rows rows between planes, 0: T*B);
+//   scratch dhbuf [2][4][B][H]; dh_init / dc_init [B][H] (both or neither): gradient w.r.t. the initial state.
 int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
                         const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* da,
-                        __nv_bfloat16* dap, float* dhbuf, float* dcbuf, const int32_t* len, int T, int B, int H,
-                        unsigned int* counter);
+                        __nv_bfloat16* dap, long long dap_plane_rows, float* dhbuf, float* dh_init, float* dc_init,
+                        const int32_t* len, int T, int B, int H, unsigned int* counter);
 
 }  // namespace nvqa

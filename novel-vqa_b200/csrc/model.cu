@@ -12,6 +12,7 @@
 //     over clones (:323-326);
 //   - rows stay in original batch order; activity masks replace the length sort (see pointwise.cu);
 //   - d fc7 (computed and discarded by the reference) is not computed.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -74,6 +75,17 @@ struct nvqa_model {
   int steps = 0;                    // arch2: executed steps tmax = 2 + longest question of the batch
   float *Wcnn = nullptr, *bcnn = nullptr, *gWcnn = nullptr, *gbcnn = nullptr, *lookup = nullptr, *glookup = nullptr;
   float* zeros = nullptr;           // [B x H] zeros (initial dc / dh of the arch2 backward)
+  // arch3 (001_train_autoencoder text autoencoder): encoder core = lw/lg, decoder core = lw2/lg2, decoder projection, lookup
+  LayerPtrs lw2[4], lg2[4];
+  float *Wd = nullptr, *bd = nullptr, *gWd = nullptr, *gbd = nullptr;
+  float *logits = nullptr;          // [(T+1) B x ldl] logits -> log-probs -> d logits, in place
+  int ldl = 0;                      // row pitch of logits: V+1 rounded up to 4
+  float *hd = nullptr, *dhd = nullptr;   // Dropout(top h) of the decoder steps and its gradient [(T+1) B x H]
+  float *dh_init = nullptr, *dc_init = nullptr;   // d(decoder initial state) = d(encoder final state) [B x H]
+  int32_t *targets = nullptr, *n_pred = nullptr;
+  float *adam_m = nullptr;          // Adam first moment (second moment lives in rms)
+  int64_t adam_t = 0;
+  bool logp_valid = false;          // logits holds this forward's log-probs (backward overwrites them with d logits)
   bool hp_valid[4] = {false, false, false, false};   // hp[l] holds this step's h planes (persistent forward ran)
   bool dap_valid = false;                            // dap holds the current layer's da planes
   // batch
@@ -231,10 +243,17 @@ extern "C" int nvqa_model_destroy(nvqa_model* m) {
 
 static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   m->cfg = *cfg;
-  const int V = cfg->V, E = cfg->E, H = cfg->H, L = cfg->L, I = cfg->I, C = cfg->C, O = cfg->O, T = cfg->T, B = cfg->B;
-  NVQA_CHECK(cfg->arch == 1 || cfg->arch == 2, "arch must be 1 (002_train_vqa_arch1) or 2 (003_train_vqa_arch2)");
-  const bool a2 = cfg->arch == 2;
+  const int V = cfg->V, E = cfg->E, H = cfg->H, L = cfg->L, C = cfg->C, T = cfg->T, B = cfg->B;
+  const int I = cfg->arch == 3 ? 4 : cfg->I, O = cfg->arch == 3 ? 4 : cfg->O;
+  NVQA_CHECK(cfg->arch >= 1 && cfg->arch <= 3,
+             "arch must be 1 (002_train_vqa_arch1), 2 (003_train_vqa_arch2) or 3 (001_train_autoencoder text autoencoder)");
+  const bool a3 = cfg->arch == 3;
+  const bool a2 = cfg->arch == 2 || a3;   // arch3 shares arch2's "no multimodal block" buffer shapes
   if (a2) m->cfg.C = cfg->H;        // arch2 has no common embedding: the head reads the H-wide encoder output
+  if (a3) {                         // no image, no answer classifier: keep the shared buffers minimal
+    m->cfg.I = 4; m->cfg.O = 4;
+    NVQA_CHECK(cfg->L == 1, "arch 3 restates the reference default num_layers = 1");
+  }
   NVQA_CHECK(V > 0 && E > 0 && H > 0 && L >= 1 && L <= 4 && I > 0 && (a2 || C > 0) && O > 0 && T > 0 && B > 0, "bad config");
   NVQA_CHECK(E % 4 == 0 && H % 4 == 0 && I % 4 == 0 && C % 4 == 0, "E, H, I, C must be multiples of 4 (128-bit rows)");
   NVQA_CHECK(cfg->dropout >= 0.f && cfg->dropout < 1.f, "dropout must be in [0,1)");
@@ -242,13 +261,19 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_TRY(require_device(cfg->device));
   NVQA_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
-  const int S = a2 ? H : 2 * L * H;
+  const int S = (a2 && !a3) ? H : 2 * L * H;
   m->S = S;
-  m->TS = a2 ? T + 2 : T;
-  m->steps = m->TS;
+  m->TS = a3 ? 2 * T + 1 : a2 ? T + 2 : T;
+  m->steps = a3 ? T : m->TS;
   int64_t n_enc = 0;
   for (int l = 0; l < L; ++l) n_enc += (int64_t)4 * H * (l == 0 ? E : H) + 4 * H + (int64_t)4 * H * H + 4 * H;
-  if (!a2) {
+  if (a3) {
+    // getParameters order: encoder, decoder (LSTM core then Linear(H, V+1)), lookup_table
+    // (001_train_autoencoder/misc/AutoEncoder_text_nostart.lua:86-105)
+    m->n_blk[0] = n_enc;
+    m->n_blk[1] = n_enc + (int64_t)(V + 1) * H + (V + 1);
+    m->n_blk[2] = (int64_t)(V + 1) * E;
+  } else if (!a2) {
     // optimiser order: encoder, embedding, multimodal (002_train_baseline.lua:183,190)
     m->n_blk[0] = n_enc;
     m->n_blk[1] = (int64_t)V * E + E;
@@ -269,13 +294,19 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_CUDA(cudaMemsetAsync(m->grads, 0, m->P * 4, m->stream));
   NVQA_CUDA(cudaMemsetAsync(m->rms, 0, m->P * 4, m->stream));   // optim.rmsprop: state.m = 0
   auto carve = [&](float* base, LayerPtrs* lp, float** We, float** be_, float** q6) {
-    float* p = base + m->off_blk[a2 ? 1 : 0];
+    float* p = base + m->off_blk[(a2 && !a3) ? 1 : 0];
     for (int l = 0; l < L; ++l) {
       int in = l == 0 ? E : H;
       lp[l].Wi = p; p += (int64_t)4 * H * in;
       lp[l].bi = p; p += 4 * H;
       lp[l].Wh = p; p += (int64_t)4 * H * H;
       lp[l].bh = p; p += 4 * H;
+    }
+    if (a3) {
+      *We = base + m->off_blk[2];
+      *be_ = nullptr;
+      for (int k = 0; k < 6; ++k) q6[k] = nullptr;
+      return;
     }
     if (a2) {
       *We = p;                                   // LookupTable.weight [(V+1) x E] follows the LSTM core
@@ -304,6 +335,33 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   carve(m->grads, m->lg, &m->gWeT, &m->gbe, g6);
   m->Wq = w6[0]; m->bq = w6[1]; m->Wv = w6[2]; m->bv = w6[3]; m->Wc = w6[4]; m->bc = w6[5];
   m->gWq = g6[0]; m->gbq = g6[1]; m->gWv = g6[2]; m->gbv = g6[3]; m->gWc = g6[4]; m->gbc = g6[5];
+  if (a3) {
+    auto carve2 = [&](float* base, LayerPtrs* lp, float** W, float** b) {
+      float* p = base + m->off_blk[1];
+      for (int l = 0; l < L; ++l) {
+        int in = l == 0 ? E : H;
+        lp[l].Wi = p; p += (int64_t)4 * H * in;
+        lp[l].bi = p; p += 4 * H;
+        lp[l].Wh = p; p += (int64_t)4 * H * H;
+        lp[l].bh = p; p += 4 * H;
+      }
+      *W = p; p += (int64_t)(V + 1) * H;
+      *b = p;
+    };
+    carve2(m->params, m->lw2, &m->Wd, &m->bd);
+    carve2(m->grads, m->lg2, &m->gWd, &m->gbd);
+    m->ldl = ((V + 1 + 3) / 4) * 4;
+    const int64_t rows = (int64_t)(T + 1) * B;
+    NVQA_TRY(dallocT(m, &m->logits, rows * m->ldl));
+    NVQA_TRY(dallocT(m, &m->hd, rows * H));
+    NVQA_TRY(dallocT(m, &m->dhd, rows * H));
+    NVQA_TRY(dallocT(m, &m->dh_init, (size_t)B * H));
+    NVQA_TRY(dallocT(m, &m->dc_init, (size_t)B * H));
+    NVQA_TRY(dallocT(m, &m->targets, rows));
+    NVQA_TRY(dallocT(m, &m->n_pred, 4));
+    NVQA_TRY(dallocT(m, &m->adam_m, m->P));
+    NVQA_CUDA(cudaMemsetAsync(m->adam_m, 0, m->P * 4, m->stream));
+  }
   if (a2) {
     m->Wcnn = w6[0]; m->bcnn = w6[1]; m->gWcnn = g6[0]; m->gbcnn = g6[1];
     m->lookup = m->WeT; m->glookup = m->gWeT;
@@ -330,7 +388,7 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_TRY(dallocT(m, &m->zd, (int64_t)B * C2));
   NVQA_TRY(dallocT(m, &m->scores, (int64_t)B * O));
   NVQA_TRY(dallocT(m, &m->dscores, (int64_t)B * O));
-  NVQA_TRY(dallocT(m, &m->rowloss, (int64_t)B));
+  NVQA_TRY(dallocT(m, &m->rowloss, a3 ? (int64_t)(T + 1) * B : (int64_t)B));
   NVQA_TRY(dallocT(m, &m->loss, 4));
   NVQA_TRY(dallocT(m, &m->argmax, (int64_t)B));
   NVQA_TRY(dallocT(m, &m->dzd, (int64_t)B * C2));
@@ -365,7 +423,8 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
     // transient operand planes of the largest GEMM (wgrad: da^T [4H x TB] and x^T [H x TB], 3 bf16 planes each);
     // static region: every weight matrix in both orientations
     size_t elems = (size_t)(N + 64) * 4 * H + (size_t)(N + 64) * (H > E ? H : E) + (size_t)(B + 64) * (I + S + 2 * C2);
-    size_t stat = (size_t)(n_enc + m->n_blk[2] + (a2 ? m->n_blk[0] : 0)) * 2 * 6 + (16 << 20);
+    if (a3) elems = std::max(elems, (size_t)((T + 1) * (size_t)B + 64) * (m->ldl + 8 + H + 8));   // d logits + hd planes
+    size_t stat = (size_t)(n_enc + m->n_blk[2] + (a2 ? m->n_blk[0] : 0) + (a3 ? m->n_blk[1] : 0)) * 2 * 6 + (16 << 20);
     NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (96 << 20), stat));
   }
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
@@ -415,7 +474,7 @@ static int block_copy(nvqa_model* m, float* dev_base, int block, float* host, bo
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   float* d = dev_base + m->off_blk[block];
   const int64_t n = m->n_blk[block];
-  if (block != NVQA_BLOCK_EMBEDDING || m->cfg.arch == 2) {
+  if (block != NVQA_BLOCK_EMBEDDING || m->cfg.arch != 1) {
     if (to_device) NVQA_CUDA(cudaMemcpyAsync(d, host, n * 4, cudaMemcpyHostToDevice, m->stream));
     else NVQA_CUDA(cudaMemcpyAsync(host, d, n * 4, cudaMemcpyDeviceToHost, m->stream));
     NVQA_CUDA(cudaStreamSynchronize(m->stream));
@@ -461,29 +520,30 @@ extern "C" int nvqa_device_views(nvqa_model* m, float** params, float** grads, i
 // ---- batch ---------------------------------------------------------------------------------------
 extern "C" int nvqa_set_batch(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
                               const int32_t* labels, int32_t B) {
-  NVQA_CHECK(m && q && len && fc7, "null argument");
+  NVQA_CHECK(m && q && (m->cfg.arch == 3 || (len && fc7)), "null argument");
   NVQA_CHECK(B > 0 && B <= m->cfg.B, "batch size out of range");
   m->q = q; m->len = len; m->fc7 = fc7; m->labels = labels; m->B = B;
   m->fwd_done = false;
-  m->steps = m->TS;
+  m->steps = m->cfg.arch == 3 ? m->cfg.T : m->TS;
   return 0;
 }
 
 extern "C" int nvqa_set_steps(nvqa_model* m, int32_t steps) {
-  NVQA_CHECK(m && m->cfg.arch == 2, "nvqa_set_steps applies to arch 2 models");
-  NVQA_CHECK(steps >= 2 && steps <= m->TS, "steps out of range");
+  NVQA_CHECK(m && m->cfg.arch >= 2, "nvqa_set_steps applies to arch 2 and arch 3 models");
+  if (m->cfg.arch == 3) NVQA_CHECK(steps >= 1 && steps <= m->cfg.T, "steps (tmax) out of range");
+  else NVQA_CHECK(steps >= 2 && steps <= m->TS, "steps out of range");
   m->steps = steps;
   return 0;
 }
 
 extern "C" int nvqa_set_batch_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
                                    const int32_t* labels, int32_t B) {
-  NVQA_CHECK(m && q && len && fc7, "null argument");
+  NVQA_CHECK(m && q && len && (fc7 || m->cfg.arch == 3), "null argument");
   NVQA_CHECK(B > 0 && B <= m->cfg.B, "batch size out of range");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   NVQA_CUDA(cudaMemcpyAsync(m->q_stage, q, (size_t)B * m->cfg.T * 4, cudaMemcpyHostToDevice, m->stream));
   NVQA_CUDA(cudaMemcpyAsync(m->len_stage, len, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
-  NVQA_CUDA(cudaMemcpyAsync(m->fc7_stage, fc7, (size_t)B * m->cfg.I * 4, cudaMemcpyHostToDevice, m->stream));
+  if (m->cfg.arch != 3) NVQA_CUDA(cudaMemcpyAsync(m->fc7_stage, fc7, (size_t)B * m->cfg.I * 4, cudaMemcpyHostToDevice, m->stream));
   if (labels) NVQA_CUDA(cudaMemcpyAsync(m->lab_stage, labels, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
   NVQA_TRY(nvqa_set_batch(m, m->q_stage, m->len_stage, m->fc7_stage, labels ? m->lab_stage : nullptr, B));
   if (m->cfg.arch == 2) {   // executed steps tmax = image + START + longest question (Encoder_lstm.lua:185-189,219)
@@ -491,6 +551,12 @@ extern "C" int nvqa_set_batch_host(nvqa_model* m, const int32_t* q, const int32_
     for (int b = 0; b < B; ++b) mx = len[b] > mx ? len[b] : mx;
     NVQA_CHECK(mx >= 0 && mx <= m->cfg.T, "question length out of range");
     m->steps = 2 + mx;
+  }
+  if (m->cfg.arch == 3) {   // tmax = longest sequence of the batch (AutoEncoder_text_nostart.lua:249-256,281)
+    int mx = 0;
+    for (int b = 0; b < B; ++b) mx = len[b] > mx ? len[b] : mx;
+    NVQA_CHECK(mx >= 1 && mx <= m->cfg.T, "sequence length out of range");
+    m->steps = mx;
   }
   return 0;
 }
@@ -509,41 +575,60 @@ static Drop lstm_drop(const nvqa_model* m, int l /* between layer l and l+1 */) 
   return make_drop(m, m->mk_lstm ? m->mk_lstm + per * l : nullptr, STREAM_LSTM0 + l);
 }
 
-static int lstm_layers_backward(nvqa_model* m, int T, const int32_t* len, const float* const* dh0, const float* const* dc0, int ld0);
+// A run of consecutive time slots [t0, t0 + T) of the activation buffers processed with one set of LSTM weights.
+// arch1 / arch2 use a single segment starting at slot 0; the autoencoder runs the encoder in [0, tmax) and the decoder
+// in [tmax, 2 tmax + 1): the decoder's slot 0 IS the encoder's last slot, i.e. its initial state (has_init).
+struct LstmSeg {
+  int t0 = 0, T = 0;
+  const LayerPtrs* w = nullptr;
+  LayerPtrs* g = nullptr;
+  bool has_init = false;
+};
 
-// All LSTM layers over T steps, layer-major: batched input projection (K3), then the recurrence (K4 persistent kernel,
-// or per-step GEMM + gate kernel as the generic fallback).  len == nullptr: every row is active at every step.
-static int lstm_layers_forward(nvqa_model* m, int T, const int32_t* len) {
+static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t* len, const float* const* dh0,
+                                const float* const* dc0, int ld0, const float* dh_top, Drop dh_top_drop, bool want_init);
+
+// All LSTM layers over the segment's steps, layer-major: batched input projection (K3), then the recurrence (K4 persistent
+// kernel, or per-step GEMM + gate kernel as the generic fallback).  len == nullptr: every row is active at every step.
+static int lstm_layers_forward(nvqa_model* m, const LstmSeg& sg, const int32_t* len) {
   const nvqa_config& c = m->cfg;
-  const int B = m->B, E = c.E, H = c.H, L = c.L;
-  const int64_t BH = (int64_t)B * H;
+  const int B = m->B, E = c.E, H = c.H, L = c.L, T = sg.T;
+  const int64_t BH = (int64_t)B * H, r0 = (int64_t)sg.t0 * B;
   cudaStream_t s = m->stream;
   for (int l = 0; l < L; ++l) {
-    const float* X = l == 0 ? m->y : m->xdrop[l];
     const int in = l == 0 ? E : H;
-    NVQA_TRY(gemm(m, CAT_INPROJ, true, true, T * B, 4 * H, in, X, in, m->lw[l].Wi, in, m->pre[l], 4 * H, false, m->lw[l].bi,
-                  m->lw[l].bh));
+    const float* X = (l == 0 ? m->y : m->xdrop[l]) + r0 * in;
+    float* pre = m->pre[l] + r0 * 4 * H;
+    float* cb = m->c[l] + r0 * H;
+    float* hb = m->h[l] + r0 * H;
+    float* xnext = l + 1 < L ? m->xdrop[l + 1] + r0 * H : nullptr;
+    NVQA_TRY(gemm(m, CAT_INPROJ, true, true, T * B, 4 * H, in, X, in, sg.w[l].Wi, in, pre, 4 * H, false, sg.w[l].bi,
+                  sg.w[l].bh));
     if (m->planes && m->use_persistent) {
       // K4: all T steps in one persistent cooperative kernel (W_hh slice resident in shared memory)
-      ProfScope ps(m, CAT_REC_FWD, 2.0 * (T - 1) * B * 4.0 * H * H);
-      int rc = lstm_fwd_persistent(s, m->ws, m->planes, m->lw[l].Wh, m->pre[l], m->c[l], m->h[l], m->hp[l],
-                                   l + 1 < L ? m->xdrop[l + 1] : nullptr, len, lstm_drop(m, l), T, B, H,
-                                   m->grid_counter);
+      ProfScope ps(m, CAT_REC_FWD, 2.0 * (T - (sg.has_init ? 0 : 1)) * B * 4.0 * H * H);
+      int rc = lstm_fwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
+                                   (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter);
       if (rc > 0) return rc;
       m->hp_valid[l] = rc == 0;
       if (rc == 0) continue;
     }
     m->hp_valid[l] = false;
     for (int t = 0; t < T; ++t) {
-      float* pre_t = m->pre[l] + (int64_t)t * B * 4 * H;
-      if (t > 0)   // h_0 == 0: the recurrent term of the first step vanishes
-        NVQA_TRY(gemm(m, CAT_REC_FWD, true, true, B, 4 * H, H, m->h[l] + t * BH, H, m->lw[l].Wh, H, pre_t, 4 * H, true));
+      float* pre_t = pre + (int64_t)t * B * 4 * H;
+      if (t > 0 || sg.has_init)   // h_0 == 0 without an initial state: the recurrent term of the first step vanishes
+        NVQA_TRY(gemm(m, CAT_REC_FWD, true, true, B, 4 * H, H, hb + t * BH, H, sg.w[l].Wh, H, pre_t, 4 * H, true));
       ProfScope ps(m, CAT_PW_FWD, 0);
-      NVQA_TRY(lstm_gates_fwd(s, pre_t, m->c[l] + t * BH, H, m->c[l] + (t + 1) * BH, m->h[l] + (t + 1) * BH, H,
-                              l + 1 < L ? m->xdrop[l + 1] + t * BH : nullptr, len, lstm_drop(m, l), t, T, B, H));
+      NVQA_TRY(lstm_gates_fwd(s, pre_t, cb + t * BH, H, cb + (t + 1) * BH, hb + (t + 1) * BH, H,
+                              xnext ? xnext + t * BH : nullptr, len, lstm_drop(m, l), t, T, B, H));
     }
   }
   return 0;
+}
+static int lstm_layers_forward(nvqa_model* m, int T, const int32_t* len) {
+  LstmSeg sg;
+  sg.T = T; sg.w = m->lw; sg.g = m->lg;
+  return lstm_layers_forward(m, sg, len);
 }
 
 // arch2 forward: 003_train_vqa_arch2/002_train_baseline.lua:308-314 + misc/Encoder_lstm.lua:152-227
@@ -576,11 +661,65 @@ static int forward_arch2(nvqa_model* m) {
   return 0;
 }
 
+// arch3 forward: nn.AutoEncoder:updateOutput + nn.LanguageModelCriterion:updateOutput
+// (001_train_autoencoder/misc/AutoEncoder_text_nostart.lua:222-339, 427-449)
+enum : uint32_t { STREAM_AE_ENC_EMB = 32, STREAM_AE_DEC_EMB = 33, STREAM_AE_OUT = 34 };
+static Drop ae_drop(const nvqa_model* m, uint32_t stream, float p) {
+  Drop d = make_drop(m, nullptr, stream);
+  d.thresh = (uint32_t)(p * 256.0f + 0.5f);
+  d.scale = 1.0f / (1.0f - p);
+  d.mode = (m->mode == NVQA_MODE_TRAIN && p > 0.f) ? 2 : 0;
+  return d;
+}
+static void ae_segments(nvqa_model* m, LstmSeg* enc, LstmSeg* dec) {
+  enc->t0 = 0; enc->T = m->steps; enc->w = m->lw; enc->g = m->lg; enc->has_init = false;
+  dec->t0 = m->steps; dec->T = m->steps + 1; dec->w = m->lw2; dec->g = m->lg2; dec->has_init = true;
+}
+static int forward_arch3(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, T = c.T, E = c.E, H = c.H, L = c.L, tmax = m->steps, V1 = c.V + 1;
+  const int64_t BH = (int64_t)B * H;
+  cudaStream_t s = m->stream;
+  LstmSeg enc, dec;
+  ae_segments(m, &enc, &dec);
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    // the lookup Dropout is a hard-coded 0.5 (:31); one mask per timestep clone
+    NVQA_TRY(ae_embed_fwd(s, m->q, m->lookup, m->y, ae_drop(m, STREAM_AE_ENC_EMB, 0.5f), ae_drop(m, STREAM_AE_DEC_EMB, 0.5f), B, T,
+                          E, c.V, tmax));
+    NVQA_TRY(lm_targets(s, m->q, m->targets, m->n_pred, B, T, c.V));
+  }
+  NVQA_TRY(lstm_layers_forward(m, enc, nullptr));
+  NVQA_TRY(lstm_layers_forward(m, dec, nullptr));          // initial state = encoder state at tmax (:287-288)
+  const int rows = dec.T * B;
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    // encoder output state [c | h] (self.output_enc, :286) for nvqa_state_get
+    NVQA_CUDA(cudaMemcpy2DAsync(m->state, (size_t)2 * H * 4, m->c[L - 1] + (int64_t)tmax * BH, (size_t)H * 4, (size_t)H * 4, B,
+                                cudaMemcpyDeviceToDevice, s));
+    NVQA_CUDA(cudaMemcpy2DAsync(m->state + H, (size_t)2 * H * 4, m->h[L - 1] + (int64_t)tmax * BH, (size_t)H * 4, (size_t)H * 4, B,
+                                cudaMemcpyDeviceToDevice, s));
+    // 'drop_final' on the decoder's top h of every step (003_train_vqa_arch2/misc/LSTM_decoder.lua:56)
+    NVQA_TRY(mask_copy(s, m->h[L - 1] + (int64_t)(dec.t0 + 1) * BH, H, nullptr, m->hd, ae_drop(m, STREAM_AE_OUT, c.dropout), rows, H));
+  }
+  // 'decoder' Linear(H, V+1) (:57) for all steps at once
+  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, rows, V1, H, m->hd, H, m->Wd, H, m->logits, m->ldl, false, m->bd));
+  {
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(logsoftmax_lm(s, m->logits, rows, m->ldl, V1, m->targets, m->rowloss));
+    NVQA_TRY(lm_loss_reduce(s, m->rowloss, rows, m->n_pred, m->loss));
+  }
+  m->fwd_done = true;
+  m->logp_valid = true;
+  return 0;
+}
+
 extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   NVQA_CHECK(m && m->q, "nvqa_forward: no batch set");
   NVQA_CHECK(mode == NVQA_MODE_EVAL || mode == NVQA_MODE_TRAIN, "bad mode");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   m->mode = mode; m->seed = seed;
+  if (m->cfg.arch == 3) return forward_arch3(m);
   if (m->cfg.arch == 2) return forward_arch2(m);
   const nvqa_config& c = m->cfg;
   const int B = m->B, T = c.T, E = c.E, H = c.H, L = c.L, S = m->S;
@@ -621,7 +760,7 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
 }
 
 extern "C" int nvqa_loss(nvqa_model* m, float* out) {
-  NVQA_CHECK(m && out && m->fwd_done && m->labels, "nvqa_loss: forward with labels has not run");
+  NVQA_CHECK(m && out && m->fwd_done && (m->labels || m->cfg.arch == 3), "nvqa_loss: forward with labels has not run");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   NVQA_CUDA(cudaMemcpyAsync(m->loss_host, m->loss, 4, cudaMemcpyDeviceToHost, m->stream));
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
@@ -657,7 +796,46 @@ static int backward_embed_arch2(nvqa_model* m) {
   return 0;
 }
 
+// arch3: criterion + LogSoftMax + 'decoder' Linear + 'drop_final' backward for all decoder steps
+// (AutoEncoder_text_nostart.lua:444-450, 351-356; 003_train_vqa_arch2/misc/LSTM_decoder.lua:56-59)
+static int backward_head_arch3(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, H = c.H, V1 = c.V + 1, rows = (m->steps + 1) * B;
+  cudaStream_t s = m->stream;
+  {
+    ProfScope ps(m, CAT_PW_BWD, 0);
+    NVQA_TRY(lm_grad(s, m->logits, rows, m->ldl, V1, m->targets, m->n_pred, 1.0f));
+    NVQA_CUDA(cudaMemsetAsync(m->gbd, 0, (size_t)V1 * 4, s));
+    NVQA_TRY(colsum(s, m->logits, rows, V1, m->ldl, m->gbd, nullptr));
+  }
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, V1, H, rows, m->logits, m->ldl, m->hd, H, m->gWd, H, false));
+  NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, rows, H, V1, m->logits, m->ldl, m->Wd, H, m->dhd, H, false));
+  return 0;
+}
+// arch3: decoder steps tmax+1..1 from zero state gradients, then encoder steps tmax..1 from d(decoder initial state)
+static int backward_lstm_arch3(nvqa_model* m) {
+  const int H = m->cfg.H;
+  LstmSeg enc, dec;
+  ae_segments(m, &enc, &dec);
+  Drop none = make_drop(m, nullptr, 0);
+  none.mode = 0;
+  const float* z[4] = {m->zeros, m->zeros, m->zeros, m->zeros};
+  NVQA_TRY(lstm_layers_backward(m, dec, nullptr, z, z, H, m->dhd, ae_drop(m, STREAM_AE_OUT, m->cfg.dropout), true));
+  const float* dh0[4] = {m->dh_init, nullptr, nullptr, nullptr};
+  const float* dc0[4] = {m->dc_init, nullptr, nullptr, nullptr};
+  return lstm_layers_backward(m, enc, nullptr, dh0, dc0, H, nullptr, none, false);
+}
+static int backward_embed_arch3(nvqa_model* m) {
+  const nvqa_config& c = m->cfg;
+  cudaStream_t s = m->stream;
+  ProfScope ps(m, CAT_PW_BWD, 0);
+  NVQA_CUDA(cudaMemsetAsync(m->glookup, 0, (size_t)(c.V + 1) * c.E * 4, s));
+  return ae_embed_bwd(s, m->q, m->y, m->dxbuf, m->glookup, ae_drop(m, STREAM_AE_ENC_EMB, 0.5f), ae_drop(m, STREAM_AE_DEC_EMB, 0.5f),
+                      m->B, c.T, c.E, c.V, m->steps);
+}
+
 static int backward_head(nvqa_model* m) {
+  if (m->cfg.arch == 3) return backward_head_arch3(m);
   if (m->cfg.arch == 2) return backward_head_arch2(m);
   const nvqa_config& c = m->cfg;
   const int B = m->B, S = m->S, C = c.C, O = c.O, I = c.I;
@@ -683,66 +861,89 @@ static int backward_head(nvqa_model* m) {
   return 0;
 }
 
-// rnn_backward for all layers (top first).  dh0[l] / dc0[l]: gradient of the loss w.r.t. layer l's final h / c
-// (leading dimension ld0); len == nullptr: every row active at every step.
-static int lstm_layers_backward(nvqa_model* m, int T, const int32_t* len, const float* const* dh0, const float* const* dc0, int ld0) {
+// rnn_backward for all layers (top first) over one segment.  dh0[l] / dc0[l]: gradient of the loss w.r.t. layer l's
+// final h / c (leading dimension ld0); dh_top [T][B][H] (optional): extra gradient of every step's top-layer h, multiplied
+// by dh_top_drop (the consumer's input Dropout); len == nullptr: every row active at every step; want_init: also produce
+// the gradient w.r.t. the segment's initial state of layer 0 in m->dh_init / m->dc_init.
+static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t* len, const float* const* dh0,
+                                const float* const* dc0, int ld0, const float* dh_top, Drop dh_top_drop, bool want_init) {
   const nvqa_config& c = m->cfg;
-  const int B = m->B, E = c.E, H = c.H, L = c.L;
-  const int64_t BH = (int64_t)B * H;
+  const int B = m->B, E = c.E, H = c.H, L = c.L, T = sg.T;
+  const int64_t BH = (int64_t)B * H, r0 = (int64_t)sg.t0 * B;
   cudaStream_t s = m->stream;
+  NVQA_CHECK(!want_init || L == 1, "initial-state gradients are implemented for single-layer segments");
   for (int l = L - 1; l >= 0; --l) {
     const float* dh_in = dh0[l];
     const float* dc_in = dc0[l];
     int ld = ld0;
     int rc = -1;
+    const int in = l == 0 ? E : H;
+    const float* gates = m->pre[l] + r0 * 4 * H;
+    const float* cb = m->c[l] + r0 * H;
+    float* da = m->da + r0 * 4 * H;
+    float* dx = m->dxbuf + r0 * in;
+    const float* dh_above = l + 1 < L ? m->dxbuf + r0 * H : dh_top;
+    const Drop dabove = l + 1 < L ? lstm_drop(m, l) : dh_top_drop;
     if (m->planes && m->use_persistent) {
       // K9: the whole backward recurrence of this layer in one persistent cooperative kernel
-      ProfScope ps(m, CAT_REC_BWD, 2.0 * (T - 1) * B * 4.0 * H * H);
-      rc = lstm_bwd_persistent(s, m->ws, m->planes, m->lw[l].Wh, m->pre[l], m->c[l], dh_in, dc_in, ld,
-                               l + 1 < L ? m->dxbuf : nullptr, lstm_drop(m, l), m->da, m->dap, m->dhbuf, m->dc_carry,
-                               len, T, B, H, m->grid_counter);
+      ProfScope ps(m, CAT_REC_BWD, 2.0 * (T - (want_init ? 0 : 1)) * B * 4.0 * H * H);
+      rc = lstm_bwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, gates, cb, dh_in, dc_in, ld, dh_above, dabove, da,
+                               m->dap + r0 * 4 * H, (long long)m->TS * c.B, m->dhbuf, want_init ? m->dh_init : nullptr,
+                               want_init ? m->dc_init : nullptr, len, T, B, H, m->grid_counter);
       if (rc > 0) return rc;
     }
     m->dap_valid = rc == 0;
     for (int t = T - 1; t >= 0 && rc != 0; --t) {
-      NVQA_TRY(lstm_gates_bwd(s, m->pre[l] + (int64_t)t * B * 4 * H, m->c[l] + t * BH, m->c[l] + (t + 1) * BH, dh_in, ld,
-                              l + 1 < L ? m->dxbuf + t * BH : nullptr, dc_in, ld, m->da + (int64_t)t * B * 4 * H,
-                              m->dc_carry, len, lstm_drop(m, l), t, T, B, H));
-      if (t > 0)   // dh_{t-1} = da_t . Wh
-        NVQA_TRY(gemm(m, CAT_REC_BWD, true, false, B, H, 4 * H, m->da + (int64_t)t * B * 4 * H, 4 * H, m->lw[l].Wh, H, m->dh_carry, H,
+      NVQA_TRY(lstm_gates_bwd(s, gates + (int64_t)t * B * 4 * H, cb + t * BH, cb + (t + 1) * BH, dh_in, ld,
+                              dh_above ? dh_above + t * BH : nullptr, dc_in, ld, da + (int64_t)t * B * 4 * H,
+                              m->dc_carry, len, dabove, t, T, B, H));
+      if (t > 0 || want_init)   // dh_{t-1} = da_t . Wh
+        NVQA_TRY(gemm(m, CAT_REC_BWD, true, false, B, H, 4 * H, da + (int64_t)t * B * 4 * H, 4 * H, sg.w[l].Wh, H, m->dh_carry, H,
                       false));
       dh_in = m->dh_carry; dc_in = m->dc_carry; ld = H;
     }
-    const float* X = l == 0 ? m->y : m->xdrop[l];
-    const int in = l == 0 ? E : H;
-    NVQA_CUDA(cudaMemsetAsync(m->lg[l].bi, 0, (size_t)4 * H * 4, s));
-    NVQA_CUDA(cudaMemsetAsync(m->lg[l].bh, 0, (size_t)4 * H * 4, s));
+    if (want_init && rc != 0) {
+      NVQA_CUDA(cudaMemcpyAsync(m->dh_init, m->dh_carry, (size_t)BH * 4, cudaMemcpyDeviceToDevice, s));
+      NVQA_CUDA(cudaMemcpyAsync(m->dc_init, m->dc_carry, (size_t)BH * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    const float* X = (l == 0 ? m->y : m->xdrop[l]) + r0 * in;
+    NVQA_CUDA(cudaMemsetAsync(sg.g[l].bi, 0, (size_t)4 * H * 4, s));
+    NVQA_CUDA(cudaMemsetAsync(sg.g[l].bh, 0, (size_t)4 * H * 4, s));
     // sum over timestep clones of accGradParameters (:323-326) as one GEMM over all (t,b) rows
     if (m->dap_valid) {
       // da (and h_prev) already exist as bf16 planes: no split passes, the GEMMs read them through MN-major TMA maps
-      UmmaOperand da_mn = op_planes(m->dap, T * B, 4 * H, 0, false);
-      NVQA_TRY(gemm_ops(m, CAT_WGRAD, da_mn, op_f32(m, X, in, false), 4 * H, in, T * B, m->lg[l].Wi, in, false));
-      UmmaOperand hprev = m->hp_valid[l] ? op_planes(m->hp[l], (T + 1) * B, H, 0, false) : op_f32(m, m->h[l], H, false);
-      NVQA_TRY(gemm_ops(m, CAT_WGRAD, da_mn, hprev, 4 * H, H, T * B, m->lg[l].Wh, H, false));
+      UmmaOperand da_mn = op_planes(m->dap, m->TS * c.B, 4 * H, (int)r0, false);
+      NVQA_TRY(gemm_ops(m, CAT_WGRAD, da_mn, op_f32(m, X, in, false), 4 * H, in, T * B, sg.g[l].Wi, in, false));
+      UmmaOperand hprev = m->hp_valid[l] ? op_planes(m->hp[l], (m->TS + 1) * c.B, H, (int)r0, false)
+                                         : op_f32(m, m->h[l] + r0 * H, H, false);
+      NVQA_TRY(gemm_ops(m, CAT_WGRAD, da_mn, hprev, 4 * H, H, T * B, sg.g[l].Wh, H, false));
     } else {
-      NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, in, T * B, m->da, 4 * H, X, in, m->lg[l].Wi, in, false));
-      NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, H, T * B, m->da, 4 * H, m->h[l], H, m->lg[l].Wh, H, false));
+      NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, in, T * B, da, 4 * H, X, in, sg.g[l].Wi, in, false));
+      NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, H, T * B, da, 4 * H, m->h[l] + r0 * H, H, sg.g[l].Wh, H, false));
     }
     {
       ProfScope ps(m, CAT_PW_BWD, 0);
-      NVQA_TRY(colsum(s, m->da, T * B, 4 * H, 4 * H, m->lg[l].bi, m->lg[l].bh));
+      NVQA_TRY(colsum(s, da, T * B, 4 * H, 4 * H, sg.g[l].bi, sg.g[l].bh));
     }
     // dX = da . Wi  (layer l-1's dh contribution, or the embedding gradient for l = 0)
     if (m->dap_valid)
-      NVQA_TRY(gemm_ops(m, CAT_DGRAD, op_planes(m->dap, T * B, 4 * H, 0, true), op_f32(m, m->lw[l].Wi, in, false), T * B, in,
-                        4 * H, m->dxbuf, in, false));
+      NVQA_TRY(gemm_ops(m, CAT_DGRAD, op_planes(m->dap, m->TS * c.B, 4 * H, (int)r0, true), op_f32(m, sg.w[l].Wi, in, false), T * B, in,
+                        4 * H, dx, in, false));
     else
-      NVQA_TRY(gemm(m, CAT_DGRAD, true, false, T * B, in, 4 * H, m->da, 4 * H, m->lw[l].Wi, in, m->dxbuf, in, false));
+      NVQA_TRY(gemm(m, CAT_DGRAD, true, false, T * B, in, 4 * H, da, 4 * H, sg.w[l].Wi, in, dx, in, false));
   }
   return 0;
 }
+static int lstm_layers_backward(nvqa_model* m, int T, const int32_t* len, const float* const* dh0, const float* const* dc0, int ld0) {
+  LstmSeg sg;
+  sg.T = T; sg.w = m->lw; sg.g = m->lg;
+  Drop none = make_drop(m, nullptr, 0);
+  none.mode = 0;
+  return lstm_layers_backward(m, sg, len, dh0, dc0, ld0, nullptr, none, false);
+}
 
 static int backward_lstm(nvqa_model* m) {
+  if (m->cfg.arch == 3) return backward_lstm_arch3(m);
   const int H = m->cfg.H, L = m->cfg.L;
   const float *dh0[4], *dc0[4];
   if (m->cfg.arch == 2) {   // only the top layer's final h receives a gradient (Encoder_lstm.lua:238-239)
@@ -755,6 +956,7 @@ static int backward_lstm(nvqa_model* m) {
 }
 
 static int backward_embed(nvqa_model* m) {
+  if (m->cfg.arch == 3) return backward_embed_arch3(m);
   if (m->cfg.arch == 2) return backward_embed_arch2(m);
   const nvqa_config& c = m->cfg;
   cudaStream_t s = m->stream;
@@ -766,7 +968,11 @@ static int backward_embed(nvqa_model* m) {
 }
 
 extern "C" int nvqa_backward(nvqa_model* m, int phase) {
-  NVQA_CHECK(m && m->fwd_done && m->labels, "nvqa_backward: forward with labels has not run");
+  NVQA_CHECK(m && m->fwd_done && (m->labels || m->cfg.arch == 3), "nvqa_backward: forward with labels has not run");
+  if (m->cfg.arch == 3 && (phase == NVQA_PHASE_HEAD || phase == NVQA_PHASE_ALL)) {
+    NVQA_CHECK(m->logp_valid, "nvqa_backward: the log-probs of this forward were already consumed (they are differentiated in place)");
+    m->logp_valid = false;
+  }
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   if (phase == NVQA_PHASE_HEAD || phase == NVQA_PHASE_ALL) NVQA_TRY(backward_head(m));
   if (phase == NVQA_PHASE_LSTM || phase == NVQA_PHASE_ALL) NVQA_TRY(backward_lstm(m));
@@ -781,6 +987,26 @@ extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps
   umma_workspace_invalidate(m->ws);     // the weights change: their cached bf16 planes are stale
   ProfScope ps(m, CAT_OPT, 0);
   return clamp_rmsprop(m->stream, m->params, m->grads, m->rms, m->P, lr, alpha, eps, wd, clamp, gscale);
+}
+
+extern "C" int nvqa_adam_step(nvqa_model* m, float lr, float beta1, float beta2, float eps, float wd, float clamp, float gscale) {
+  NVQA_CHECK(m && m->cfg.arch == 3 && m->adam_m, "nvqa_adam_step applies to arch 3 (text autoencoder) models");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  umma_workspace_invalidate(m->ws);
+  ProfScope ps(m, CAT_OPT, 0);
+  ++m->adam_t;
+  return clamp_adam(m->stream, m->params, m->grads, m->adam_m, m->rms, m->P, lr, beta1, beta2, eps, wd, clamp, gscale, m->adam_t);
+}
+
+extern "C" int nvqa_logprobs_get(nvqa_model* m, int32_t step, float* dst) {
+  NVQA_CHECK(m && dst && m->cfg.arch == 3 && m->fwd_done && m->logp_valid,
+             "nvqa_logprobs_get: arch 3 forward has not run (or backward consumed the log-probs)");
+  NVQA_CHECK(step >= 0 && step <= m->steps, "decoder step out of range");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_CUDA(cudaMemcpy2DAsync(dst, (size_t)(m->cfg.V + 1) * 4, m->logits + (int64_t)step * m->B * m->ldl, (size_t)m->ldl * 4,
+                              (size_t)(m->cfg.V + 1) * 4, m->B, cudaMemcpyDeviceToHost, m->stream));
+  NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
 }
 
 // ---- results -------------------------------------------------------------------------------------
@@ -806,10 +1032,17 @@ extern "C" int nvqa_state_get(nvqa_model* m, float* dst) {
 // ---- fused convenience -----------------------------------------------------------------------------
 extern "C" int nvqa_train_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
                                     const int32_t* labels, int32_t B, float lr, uint64_t seed, float* loss_out) {
-  NVQA_CHECK(labels, "labels required");
+  NVQA_CHECK(m, "null model");
+  NVQA_CHECK(labels || m->cfg.arch == 3, "labels required");
   NVQA_TRY(nvqa_set_batch_host(m, q, len, fc7, labels, B));
   NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
   NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
+  if (m->cfg.arch == 3) {
+    // grad_clip 0.1, weight_decay 1e-6, adam(alpha .8, beta .999, eps 1e-8)  (001_train_arch1_text_autoencoder.lua:35,40-45,237-243)
+    NVQA_TRY(nvqa_adam_step(m, lr, 0.8f, 0.999f, 1e-8f, 1e-6f, 0.1f, 1.f));
+    if (loss_out) NVQA_TRY(nvqa_loss(m, loss_out));
+    return 0;
+  }
   // clamp(-10,10) (:329) and optim.rmsprop defaults alpha=.99, eps=1e-8 (:408)
   // arch2 trains with optimize.weightDecay = 1e-4 (003_train_vqa_arch2/002_train_baseline.lua:197)
   NVQA_TRY(nvqa_rmsprop_step(m, lr, 0.99f, 1e-8f, m->cfg.arch == 2 ? 1e-4f : 0.f, 10.f, 1.f));

@@ -41,4 +41,20 @@ int mask_copy(cudaStream_t s, const float* src, int ld, float* raw, float* dst, 
 int clamp_rmsprop(cudaStream_t s, float* x, float* g, float* m, int64_t n, float lr, float alpha, float eps,
                   float wd, float clamp, float gscale);
 
+
+// ---- text autoencoder (ae_kernels.cu; 001_train_autoencoder/misc/AutoEncoder_text_nostart.lua) ----
+// rows [0, tmax*B) = encoder steps, rows [tmax*B, (2 tmax+1)*B) = decoder steps; seq [B x T] zero-padded right
+int ae_embed_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* y, Drop denc, Drop ddec, int B, int T, int E,
+                 int V, int tmax);
+int ae_embed_bwd(cudaStream_t s, const int32_t* seq, const float* y, const float* dx, float* dtable, Drop denc, Drop ddec,
+                 int B, int T, int E, int V, int tmax);
+// nn.LanguageModelCriterion (:414-455): targets [(T+1) x B] (0 = none), n_pred = number of predictions
+int lm_targets(cudaStream_t s, const int32_t* seq, int32_t* targets, int32_t* n_pred, int B, int T, int V);
+int logsoftmax_lm(cudaStream_t s, float* x, int rows, int ld, int ncols, const int32_t* targets, float* rowloss);
+int lm_loss_reduce(cudaStream_t s, const float* rowloss, int rows, const int32_t* n_pred, float* loss);
+int lm_grad(cudaStream_t s, float* lp, int rows, int ld, int ncols, const int32_t* targets, const int32_t* n_pred, float gscale);
+// clamp -> += wd * x -> adam (001_train_arch1_text_autoencoder.lua:237-243, misc/optim_updates.lua:78-111); t = step count (1-based)
+int clamp_adam(cudaStream_t s, float* x, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+               float eps, float wd, float clamp, float gscale, int64_t t);
+
 }  // namespace nvqa
