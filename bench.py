@@ -138,7 +138,10 @@ def run_ours(args):
     B = args.batch
     stream = torch.cuda.Stream(device=local)
     nv._lib.check(model.lib.nvqa_set_stream(model.handle, ctypes.c_void_p(stream.cuda_stream)))
-    views = dp.grad_bucket_views(model, local) if world > 1 else None
+    fused = world > 1 and args.dp == "fused"
+    views = dp.grad_bucket_views(model, local) if (world > 1 and not fused) else None
+    if fused:
+        dp.connect_fused(model, dist, rank, world)
     dq, dl, df, dy = (nv.DeviceBuffer(model, a) for a in (q, ln, fc7, lab))
 
     def barrier():
@@ -173,8 +176,14 @@ def run_ours(args):
     # ---- device-resident throughput ("value") ----
     model.set_batch_device(dq, dl, df, dy, B)
 
+    def train_step(lr, seed):
+        if fused:
+            dp.fused_train_step(model, lr, seed)
+        else:
+            dp.train_step(model, views, dist, world, lr, seed)
+
     def step_resident(i):
-        dp.train_step(model, views, dist, world, lr0 * (nv.DECAY_FACTOR ** i), 1000 + i)
+        train_step(lr0 * (nv.DECAY_FACTOR ** i), 1000 + i)
 
     sampler = ClockSampler(local)
     with torch.cuda.stream(stream):
@@ -205,7 +214,7 @@ def run_ours(args):
                                                          lr, 5000 + i, ctypes.byref(lossbox)))
         else:
             nv._lib.check(model.lib.nvqa_set_batch_host(model.handle, pinned[0], pinned[1], pinned[2], pinned[3], B))
-            dp.train_step(model, views, dist, world, lr, 5000 + i)
+            train_step(lr, 5000 + i)
             nv._lib.check(model.lib.nvqa_loss(model.handle, ctypes.byref(lossbox)))
         losses.append(lossbox.value)
 
@@ -221,7 +230,7 @@ def run_ours(args):
     nprof = 3
     with torch.cuda.stream(stream):
         for i in range(nprof):
-            dp.train_step(model, views, dist, world, lr0, 9000 + i)
+            train_step(lr0, 9000 + i)
     buf = ctypes.create_string_buffer(8192)
     nv._lib.check(model.lib.nvqa_profile_report(model.handle, buf, 8192))
     nv._lib.check(model.lib.nvqa_profile(model.handle, 0))
@@ -316,7 +325,10 @@ def run_ours(args):
                 "config": {"workload": "arch1 baseline training step, batch 500 per GPU, qlen 26, 4096-d fc7, 1000 "
                                        "answers, V=14773 E=200 H=512 L=2 C=1024 (BASELINE.json configs[1])",
                            "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision,
-                           "parallelism": f"dp{world}", "dropout": "in-kernel counter hash, p=0.5",
+                           "parallelism": f"dp{world}",
+                           "collective": ("none" if world == 1 else "fused NVLink reduce-scatter + RMSprop + all-gather kernel "
+                                          "over CUDA-IPC peer memory (csrc/dp_fused.cu)" if fused else
+                                          "NCCL all-reduce, 3 buckets overlapped with backward"), "dropout": "in-kernel counter hash, p=0.5",
                            "l2": "working set (params+grads+rms 166 MB, activations > 600 MB) exceeds the 126 MB L2; "
                                  "no explicit flush"},
                 "clocks": clocks,
@@ -339,6 +351,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("NVQA_PRECISION", DEFAULT_PRECISION), choices=sorted(PREC_NAMES))
     ap.add_argument("--batch", type=int, default=500)
+    ap.add_argument("--dp", default=os.environ.get("NVQA_DP", "fused"), choices=["fused", "nccl"],
+                    help="N > 1: gradient exchange = fused peer-memory kernel (default) or NCCL bucketed all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

@@ -159,6 +159,18 @@ int nvqa_rmsprop_vector(nvqa_model* m, float* x, const float* g, float* state_m,
 int nvqa_cross_entropy(nvqa_model* m, const float* scores, const int32_t* labels, int32_t n,
                        float* loss_host, float* dscores);
 
+/* ---- data-parallel update fused with its collective over NVLink peer memory (new functionality; the reference is
+ * single-GPU).  One process per GPU.  Every rank calls nvqa_dp_export, the host exchanges the blobs (any transport,
+ * e.g. torch.distributed all_gather), every rank calls nvqa_dp_connect with all blobs in rank order.  Then, instead of
+ * "all-reduce ; nvqa_rmsprop_step", each step calls nvqa_dp_rmsprop_step after nvqa_backward: ONE kernel reduce-scatters
+ * the gradient over NVLink (fixed rank order), applies scale 1/world -> clamp -> optim.rmsprop
+ * (002_train_baseline.lua:329,408) to this rank's shard and stores the updated shard into every rank's parameters. */
+int nvqa_dp_blob_size(void);
+int nvqa_dp_export(nvqa_model* m, void* blob_out);
+int nvqa_dp_connect(nvqa_model* m, int32_t rank, int32_t world, const void* blobs);
+int nvqa_dp_disconnect(nvqa_model* m);
+int nvqa_dp_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps, float wd, float clamp);
+
 /* ---- utilities ------------------------------------------------------------------------------ */
 int nvqa_host_alloc(void** p, int64_t bytes);     /* pinned host memory */
 int nvqa_host_free(void* p);

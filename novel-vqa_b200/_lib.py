@@ -60,6 +60,11 @@ SIGNATURES = {
     "nvqa_axb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "nvqa_rmsprop_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_float] * 6),
     "nvqa_cross_entropy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, c_f32p, C.c_void_p]),
+    "nvqa_dp_blob_size": (C.c_int, []),
+    "nvqa_dp_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nvqa_dp_connect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "nvqa_dp_disconnect": (C.c_int, [C.c_void_p]),
+    "nvqa_dp_rmsprop_step": (C.c_int, [C.c_void_p] + [C.c_float] * 5),
     "nvqa_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "nvqa_host_free": (C.c_int, [C.c_void_p]),
     "nvqa_device_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

@@ -1,0 +1,96 @@
+// Internal state of a libnvqa model (shared by model.cu and dp_fused.cu).  Not part of the C ABI.
+#pragma once
+#include <vector>
+
+#include "../../include/nvqa.h"
+#include "lstm_persistent.cuh"
+#include "pointwise.cuh"
+
+using namespace nvqa;
+
+struct LayerPtrs { float *Wi, *bi, *Wh, *bh; };
+
+// live per-kernel-class timing with CUDA events on the model's stream (bench.py's roofline leg)
+enum GemmCat { CAT_INPROJ = 0, CAT_REC_FWD, CAT_HEAD_FWD, CAT_HEAD_BWD, CAT_REC_BWD, CAT_WGRAD, CAT_DGRAD, CAT_OTHER,
+               CAT_PW_FWD, CAT_PW_BWD, CAT_OPT, CAT_COUNT };
+static const char* const kCatName[CAT_COUNT] = {"lstm_inproj_gemm", "lstm_recurrent_fwd", "head_fwd_gemm", "head_bwd_gemm",
+                                          "lstm_recurrent_bwd", "lstm_wgrad_gemm", "lstm_dgrad_gemm", "other_gemm",
+                                          "pointwise_fwd", "pointwise_bwd", "clamp_rmsprop"};
+struct ProfCat {
+  double ms = 0, flops = 0;
+  int64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct nvqa_model {
+  nvqa_config cfg;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int S = 0;
+  int64_t n_blk[3] = {0, 0, 0};
+  int64_t off_blk[4] = {0, 0, 0, 0};
+  int64_t P = 0;
+  float *params = nullptr, *grads = nullptr, *rms = nullptr;
+  LayerPtrs lw[4], lg[4];
+  float *WeT, *be, *gWeT, *gbe;
+  float *Wq, *bq, *Wv, *bv, *Wc, *bc, *gWq, *gbq, *gWv, *gbv, *gWc, *gbc;
+  // activations (sized for cfg.B rows)
+  float* y = nullptr;
+  float *pre[4] = {}, *c[4] = {}, *h[4] = {}, *xdrop[4] = {};
+  float *state = nullptr, *qd = nullptr, *vd = nullptr, *qc = nullptr, *ic = nullptr, *zd = nullptr;
+  float *scores = nullptr, *dscores = nullptr, *rowloss = nullptr, *loss = nullptr;
+  int32_t* argmax = nullptr;
+  float *dzd = nullptr, *dqpre = nullptr, *dipre = nullptr, *dqd = nullptr;
+  float *da = nullptr, *dxbuf = nullptr, *dh_carry = nullptr, *dc_carry = nullptr;
+  __nv_bfloat16* hp[4] = {};        // bf16 planes of h per layer [P][(T+1)B][H] (persistent recurrent kernels)
+  __nv_bfloat16* dap = nullptr;     // bf16 planes of da [P][T*B][4H] (persistent backward kernel)
+  float* dhbuf = nullptr;           // [2][4][B][H] split-K partials of dh
+  unsigned int* grid_counter = nullptr;
+  int planes = 0;                   // bf16 planes per operand of the tensor-core modes (0 = SIMT)
+  bool use_persistent = true;
+  // arch2 (003_train_vqa_arch2): image projection, LookupTable, head on the top-layer h
+  int TS = 0;                       // time-step capacity of the activation buffers (T for arch1, T + 2 for arch2)
+  int steps = 0;                    // arch2: executed steps tmax = 2 + longest question of the batch
+  float *Wcnn = nullptr, *bcnn = nullptr, *gWcnn = nullptr, *gbcnn = nullptr, *lookup = nullptr, *glookup = nullptr;
+  float* zeros = nullptr;           // [B x H] zeros (initial dc / dh of the arch2 backward)
+  // arch3 (001_train_autoencoder text autoencoder): encoder core = lw/lg, decoder core = lw2/lg2, decoder projection, lookup
+  LayerPtrs lw2[4], lg2[4];
+  float *Wd = nullptr, *bd = nullptr, *gWd = nullptr, *gbd = nullptr;
+  float *logits = nullptr;          // [(T+1) B x ldl] logits -> log-probs -> d logits, in place
+  int ldl = 0;                      // row pitch of logits: V+1 rounded up to 4
+  float *hd = nullptr, *dhd = nullptr;   // Dropout(top h) of the decoder steps and its gradient [(T+1) B x H]
+  float *dh_init = nullptr, *dc_init = nullptr;   // d(decoder initial state) = d(encoder final state) [B x H]
+  int32_t *targets = nullptr, *n_pred = nullptr;
+  float *adam_m = nullptr;          // Adam first moment (second moment lives in rms)
+  int64_t adam_t = 0;
+  bool logp_valid = false;          // logits holds this forward's log-probs (backward overwrites them with d logits)
+  bool hp_valid[4] = {false, false, false, false};   // hp[l] holds this step's h planes (persistent forward ran)
+  bool dap_valid = false;                            // dap holds the current layer's da planes
+  // batch
+  const int32_t *q = nullptr, *len = nullptr, *labels = nullptr;
+  const float* fc7 = nullptr;
+  int B = 0;
+  int32_t *q_stage = nullptr, *len_stage = nullptr, *lab_stage = nullptr;
+  float* fc7_stage = nullptr;
+  float* loss_host = nullptr;      // pinned
+  int32_t* ans_host = nullptr;     // pinned
+  // dropout
+  const float *mk_emb = nullptr, *mk_lstm = nullptr, *mk_q = nullptr, *mk_i = nullptr, *mk_z = nullptr;
+  int mode = NVQA_MODE_EVAL;
+  uint64_t seed = 0;
+  bool fwd_done = false;
+  UmmaWorkspace* ws = nullptr;
+  std::vector<void*> allocs;
+  // fused data-parallel update over NVLink peer memory (dp_fused.cu)
+  int dp_rank = 0, dp_world = 0;
+  float* dp_peer_grads[16] = {};     // every rank's flat gradient vector (own entry = grads)
+  float* dp_peer_params[16] = {};    // every rank's flat parameter vector
+  unsigned int* dp_flags = nullptr;  // [2][16] counters written by the peers: [0][r] = rank r's grads ready, [1][r] = rank r done
+  unsigned int* dp_peer_flags[16] = {};
+  unsigned int* dp_done = nullptr;   // CTA completion counter of the fused kernel
+  unsigned int dp_step = 0;
+  std::vector<void*> dp_opened;      // cudaIpcOpenMemHandle mappings to close
+  bool profiling = false;
+  ProfCat prof[CAT_COUNT];
+};
+

@@ -47,10 +47,39 @@ def backward_allreduce(model, views, dist, world):
 
 
 def train_step(model, views, dist, world, lr, seed):
-    """JdJ + all-reduce + clamp + RMSprop on an already-set batch."""
+    """JdJ + all-reduce + clamp + RMSprop on an already-set batch (NCCL path: bucketed all-reduce overlapped with the
+    backward phases, then the replicated optimizer kernel)."""
     model.forward(api.MODE_TRAIN, seed)
     backward_allreduce(model, views, dist, world)
     model.rmsprop_step(lr, grad_scale=1.0 / world)
+
+
+def connect_fused(model, dist, rank, world):
+    """Exchange the CUDA-IPC blobs of every rank's gradient / parameter / flag buffers (plumbing: torch.distributed
+    all_gather_object) and map them, so that fused_train_step can run the collective inside the optimizer kernel."""
+    import ctypes as C
+    from . import _lib
+    n = model.lib.nvqa_dp_blob_size()
+    mine = C.create_string_buffer(n)
+    _lib.check(model.lib.nvqa_dp_export(model.handle, mine))
+    blobs = [None] * world
+    if world > 1:
+        dist.all_gather_object(blobs, bytes(mine.raw))
+    else:
+        blobs[0] = bytes(mine.raw)
+    allb = C.create_string_buffer(b"".join(blobs), n * world)
+    _lib.check(model.lib.nvqa_dp_connect(model.handle, rank, world, allb))
+    if world > 1:
+        dist.barrier()                 # nobody starts stepping before every rank has mapped its peers
+
+
+def fused_train_step(model, lr, seed, alpha=0.99, eps=1e-8, wd=0.0, clamp=10.0):
+    """JdJ, then ONE kernel per rank: reduce-scatter over NVLink peer memory -> 1/world -> clamp -> RMSprop on the
+    rank's shard -> all-gather of the updated parameters (csrc/dp_fused.cu).  No NCCL call on the step."""
+    from . import _lib
+    model.forward(api.MODE_TRAIN, seed)
+    model.backward(api.PHASE_ALL)
+    _lib.check(model.lib.nvqa_dp_rmsprop_step(model.handle, lr, alpha, eps, wd, clamp))
 
 
 def average_then_update_reference(grads_per_rank, clamp=10.0):
