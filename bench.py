@@ -21,6 +21,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout: keep stdout to the ONE JSON line
 
 METRIC = "arch1_train_samples_per_s"
 UNIT = "samples/s"
