@@ -371,7 +371,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap mapH, const __gri
 //   grid = (H/64 column tiles of dh) x (4 K-splits = the four gate blocks of da) x (ceil(B/128) batch tiles)
 //   per step t = T-1 .. 0, two phases separated by grid barriers:
 //     A. element-wise, spread over all epilogue threads of the grid: da_t = f(dh_t, dc_t, gates_t, c_{t-1}, c_t),
-//        written as fp32 and as bf16 planes (the TMA / wgrad / dgrad operand); dc carry; zero the dh accumulator
+//        written as bf16 planes (the TMA / wgrad / dgrad operand); dc carry and the per-row sum over t of da (bias
+//        gradients) stay in registers
 //     B. dh_{t-1} += da_t[:, gate block] . W_hh[gate block, :]   with the CTA's [512 x 64] slice of W_hh RESIDENT
 //        in shared memory (MN-major B operand: no transposed weight copy); the four split-K partials go to a
 //        double-buffered [4][B][H] scratch and are summed (fixed order, deterministic) by the next phase A.
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
                            const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ dh0,
                            const float* __restrict__ dc0, int ld0, const float* __restrict__ dh_above, Drop drop,
-                           float* __restrict__ da, __nv_bfloat16* __restrict__ dap, long long dap_plane,
+                           float* __restrict__ dasum, __nv_bfloat16* __restrict__ dap, long long dap_plane,
                            float* __restrict__ dhbuf, float* __restrict__ dc_init, const int32_t* __restrict__ len, int T,
                            int B, int H, int KB, int S, unsigned int* counter, long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
@@ -506,8 +507,12 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
     bool valid[NI];
     int bq[NI], ucol[NI], first_t[NI];
     float4 gi[NI], gf[NI], go[NI], gg[NI], cp[NI], cn[NI], dcr[NI];
+    // sum over all steps of this thread's da elements: the bias gradients (both biases receive sum(da))
+    // need only the column sums of da, so fp32 da never goes to HBM -- just these [B][4H] per-row partial sums at the end
+    float4 bsi[NI], bsf[NI], bso[NI], bsg[NI];
 #pragma unroll
     for (int n = 0; n < NI; ++n) {
+      bsi[n] = bsf[n] = bso[n] = bsg[n] = z;
       const long long i = (long long)cta * LP_EPI_THREADS + et + (long long)n * gthreads;
       valid[n] = i < items;
       bq[n] = valid[n] ? (int)(i / H4) : 0;
@@ -572,6 +577,9 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
             dcr[n].kk = dct * gf[n].kk; }
           LB(x) LB(y) LB(z) LB(w)
 #undef LB
+#define ACC4(a, b) a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          ACC4(bsi[n], dai[n]) ACC4(bsf[n], daf[n]) ACC4(bso[n], dao[n]) ACC4(bsg[n], dag[n])
+#undef ACC4
         }
         // (1) what phase B consumes through TMA: da_t as bf16 planes
         const float4 gsrc[4] = {dai[n], daf[n], dao[n], dag[n]};
@@ -598,15 +606,10 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       if (et == 0) { LP_STAMP(t, 3); grid_arrive(counter); LP_STAMP(t, 4); }
       named_bar_sync(3, LP_EPI_THREADS);          // keep the SM's memory pipeline clear until the release is out
       if (t >= tlast) mbar_wait(gobar, k & 1u);      // ... and until the producer has seen da_t complete and issued its loads
-      // (3) off the critical path: fp32 da_t (bias column sums), and the prefetch of step t-1's gates / cell states
+      // (3) off the critical path: the prefetch of step t-1's gates / cell states
 #pragma unroll
       for (int n = 0; n < NI; ++n) {
         if (!valid[n]) continue;
-        float* dr = da + row[n] * 4 * H + ucol[n];
-        *reinterpret_cast<float4*>(dr) = dai[n];
-        *reinterpret_cast<float4*>(dr + H) = daf[n];
-        *reinterpret_cast<float4*>(dr + 2 * H) = dao[n];
-        *reinterpret_cast<float4*>(dr + 3 * H) = dag[n];
         if (t == 0 && dc_init) *reinterpret_cast<float4*>(dc_init + (size_t)bq[n] * H + ucol[n]) = dcr[n];
         if (t > 0) {
           cn[n] = cp[n];                                               // c_{t-1} becomes the "new" cell of step t-1
@@ -636,6 +639,15 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap mapDA, const __gr
       tc_fence_before();
       named_bar_sync(1, LP_EPI_THREADS);
       if (et == 0) { LP_STAMP(t, 6); grid_arrive(counter); LP_STAMP(t, 7); }      // barrier 2k+2
+    }
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      if (!valid[n]) continue;
+      float* dr = dasum + (size_t)bq[n] * 4 * H + ucol[n];
+      *reinterpret_cast<float4*>(dr) = bsi[n];
+      *reinterpret_cast<float4*>(dr + H) = bsf[n];
+      *reinterpret_cast<float4*>(dr + 2 * H) = bso[n];
+      *reinterpret_cast<float4*>(dr + 3 * H) = bsg[n];
     }
   }
   tc_fence_before();
@@ -691,7 +703,7 @@ __global__ void __launch_bounds__(256) sum4_kernel(const float* __restrict__ par
 }
 
 int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
-                        const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* da,
+                        const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* dasum,
                         __nv_bfloat16* dap, long long dap_plane_rows, float* dhbuf, float* dh_init, float* dc_init,
                         const int32_t* len, int T, int B, int H, unsigned int* counter) {
   if ((dh_init == nullptr) != (dc_init == nullptr)) return -1;
@@ -726,7 +738,7 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
     NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbg), (size_t)T * 8 * sizeof(long long)));
     NVQA_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(long long), s));
   }
-  void* args[] = {&mapDA, &mapW, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &da, &dap, &dap_plane, &dhbuf, &dc_init,
+  void* args[] = {&mapDA, &mapW, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dhbuf, &dc_init,
                   &len, &T, &B, &H, &KBv, &Sv, &counter, &dbg};
   const void* fn = nullptr;
 #define LP_PICK(P_, CL_) if (P == P_ && CL == CL_) fn = (const void*)lstm_bwd_persistent_kernel<P_, CL_>
@@ -738,7 +750,7 @@ int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
   if (le != cudaSuccess && CL > 1) {          // clusters could not be made co-resident: fall back to unicast loads
     (void)cudaGetLastError();
     g_cluster = 1;
-    return lstm_bwd_persistent(s, ws, P, Wh, gates, c, dh0, dc0, ld0, dh_above, d, da, dap, dap_plane_rows, dhbuf, dh_init,
+    return lstm_bwd_persistent(s, ws, P, Wh, gates, c, dh0, dc0, ld0, dh_above, d, dasum, dap, dap_plane_rows, dhbuf, dh_init,
                                dc_init, len, T, B, H, counter);
   }
   NVQA_CUDA(le);

@@ -20,10 +20,11 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
 // All T steps of one layer's backward recurrence (see lstm_persistent.cu).
 //   gates [T][B][4H] post-activation, c [(T+1)][B][H]; dh0/dc0 (leading dim ld0): d(final state) of this layer;
 //   dh_above [T][B][H]: dX of the layer above (masked by its input Dropout) or nullptr;
-//   out: da [T*B][4H] fp32 and dap [P][T*B][4H] bf16 planes (dap_plane_rows rows between planes, 0: T*B);
+//   out: dap [P][T*B][4H] bf16 planes of da (dap_plane_rows rows between planes, 0: T*B) and dasum [B][4H] fp32 =
+//   sum over t of da_t per batch row (its column sums are the bias gradients);
 //   scratch dhbuf [2][4][B][H]; dh_init / dc_init [B][H] (both or neither): gradient w.r.t. the initial state.
 int lstm_bwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
-                        const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* da,
+                        const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* dasum,
                         __nv_bfloat16* dap, long long dap_plane_rows, float* dhbuf, float* dh_init, float* dc_init,
                         const int32_t* len, int T, int B, int H, unsigned int* counter);
 

@@ -849,7 +849,8 @@ static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t*
     }
     {
       ProfScope ps(m, CAT_PW_BWD, 0);
-      NVQA_TRY(colsum(s, da, T * B, 4 * H, 4 * H, sg.g[l].bi, sg.g[l].bh));
+      // persistent kernel: da (here) holds the per-row sums over t [B x 4H]; fallback: da_t of every step [T*B x 4H]
+      NVQA_TRY(colsum(s, da, m->dap_valid ? B : T * B, 4 * H, 4 * H, sg.g[l].bi, sg.g[l].bh));
     }
     // dX = da . Wi  (layer l-1's dh contribution, or the embedding gradient for l = 0)
     if (m->dap_valid)
