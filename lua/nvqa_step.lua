@@ -61,4 +61,36 @@ function Model:predict(q, len, fv_im)
   return ans:long()
 end
 
-return {create = create}
+-- ---------------------------------------------------------------------------------------------------------------
+-- Text autoencoder (001_train_autoencoder/001_train_arch1_text_autoencoder.lua): replaces protos.ae / protos.crit
+-- construction (:95-108), lossFun (:208-249) and the adam call (:334).
+--   local ae = step.create_ae(opt, loader:getVocabSize(), loader:getSeqLength())
+--   ae:set_params{encoder = ..., decoder = ..., lookup_table = ...}
+--   local loss = ae:train_step(data.labels:t():int():contiguous(), lengths, learning_rate, opt.seed + iter)
+local AE_BLOCKS = {encoder = 0, decoder = 1, lookup_table = 2}
+local AE = setmetatable({}, {__index = Model})
+AE.__index = AE
+
+local function create_ae(opt, vocab_size, seq_length)
+  local cfg = ffi.new('nvqa_config', {arch = 3, V = vocab_size, E = opt.input_encoding_size, H = opt.rnn_size,
+    L = opt.num_layers, I = 4, C = 0, O = 4, T = seq_length, B = opt.batch_size, precision = 3, img_norm = 0,
+    device = opt.gpuid, dropout = opt.drop_prob_ae})
+  local h = ffi.new('nvqa_model*[1]')
+  nvqa.check(lib.nvqa_model_create(cfg, h))
+  return setmetatable({h = ffi.gc(h[0], lib.nvqa_model_destroy), cfg = cfg}, AE)
+end
+
+function AE:set_params(t)
+  for name, blk in pairs(AE_BLOCKS) do
+    nvqa.check(lib.nvqa_params_set(self.h, blk, t[name]:float():contiguous():data()))
+  end
+end
+
+-- seq: IntTensor [B x T] (data.labels transposed), zero-padded on the right; len: IntTensor [B]
+function AE:train_step(seq, len, lr, seed)
+  local loss = ffi.new('float[1]')
+  nvqa.check(lib.nvqa_train_step_host(self.h, seq:data(), len:data(), nil, nil, seq:size(1), lr, seed, loss))
+  return loss[0]
+end
+
+return {create = create, create_ae = create_ae}

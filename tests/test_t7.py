@@ -1,0 +1,98 @@
+"""Torch7 .t7 serialisation (novel-vqa_b200/t7.py): byte layout against a hand-assembled
+file, round trips, strided tensors / shared storages, CudaTensor class names, and the autoencoder -> arch1 converter."""
+import struct
+
+import numpy as np
+
+from novel_vqa_b200 import t7
+
+
+def _s(s):
+    return struct.pack("<i", len(s)) + s.encode()
+
+
+def test_hand_assembled_file_is_read(tmp_path):
+    """{encoder_w_q = FloatTensor{1,2,3}, n = 7, ok = true}: built byte by byte from the published layout."""
+    storage = (struct.pack("<i", 4) + struct.pack("<i", 3) + _s("V 1") + _s("torch.FloatStorage") + struct.pack("<q", 3)
+               + np.array([1, 2, 3], dtype="<f4").tobytes())
+    tensor = (struct.pack("<i", 4) + struct.pack("<i", 2) + _s("V 1") + _s("torch.FloatTensor") + struct.pack("<i", 1)
+              + struct.pack("<q", 3) + struct.pack("<q", 1) + struct.pack("<q", 1) + storage)
+    body = (struct.pack("<i", 3) + struct.pack("<i", 1) + struct.pack("<i", 3)
+            + struct.pack("<i", 2) + _s("encoder_w_q") + tensor
+            + struct.pack("<i", 2) + _s("n") + struct.pack("<i", 1) + struct.pack("<d", 7.0)
+            + struct.pack("<i", 2) + _s("ok") + struct.pack("<i", 5) + struct.pack("<i", 1))
+    p = tmp_path / "hand.t7"
+    p.write_bytes(body)
+    t = t7.load(str(p))
+    assert t["n"] == 7 and t["ok"] is True
+    assert t["encoder_w_q"].dtype == np.float32 and t["encoder_w_q"].tolist() == [1.0, 2.0, 3.0]
+    # and the writer produces the same bytes for the same table
+    q = tmp_path / "again.t7"
+    t7.save(str(q), {"encoder_w_q": np.array([1, 2, 3], dtype=np.float32), "n": 7, "ok": True})
+    assert q.read_bytes() == body
+
+
+def test_round_trip_nested_and_cuda_class(tmp_path):
+    r = np.random.default_rng(0)
+    obj = {"encoder_w_q": r.standard_normal(1000).astype(np.float32), "embedding_w_q": r.standard_normal((7, 5)).astype(np.float32),
+           "meta": {"iter": 2500, "lr": 3e-4, "name": "model", 1: "first", 2: [1.5, None, False]},
+           "idx": np.arange(6, dtype=np.int64).reshape(2, 3)}
+    for cuda in (False, True):
+        p = tmp_path / f"rt{cuda}.t7"
+        t7.save(str(p), obj, cuda=cuda)
+        raw = p.read_bytes()
+        assert (b"torch.CudaTensor" in raw) == cuda and (b"torch.FloatTensor" in raw) != cuda
+        back = t7.load(str(p))
+        assert np.array_equal(back["encoder_w_q"], obj["encoder_w_q"]) and back["encoder_w_q"].dtype == np.float32
+        assert np.array_equal(back["embedding_w_q"], obj["embedding_w_q"])
+        assert np.array_equal(back["idx"], obj["idx"]) and back["idx"].dtype == np.int64
+        assert back["meta"]["iter"] == 2500 and abs(back["meta"]["lr"] - 3e-4) < 1e-18 and back["meta"][1] == "first"
+        assert back["meta"][2] == {1: 1.5, 2: None, 3: False}
+
+
+def test_strided_view_and_shared_storage(tmp_path):
+    """A transposed view (stride (1, 4)) at storage offset 3, and a second tensor referencing the SAME storage object."""
+    data = np.arange(20, dtype="<f4")
+    storage = (struct.pack("<i", 4) + struct.pack("<i", 3) + _s("V 1") + _s("torch.FloatStorage") + struct.pack("<q", 20) + data.tobytes())
+    t_a = (struct.pack("<i", 4) + struct.pack("<i", 2) + _s("V 1") + _s("torch.FloatTensor") + struct.pack("<i", 2)
+           + struct.pack("<qq", 4, 3) + struct.pack("<qq", 1, 4) + struct.pack("<q", 4) + storage)
+    t_b = (struct.pack("<i", 4) + struct.pack("<i", 4) + _s("V 1") + _s("torch.CudaTensor") + struct.pack("<i", 1)
+           + struct.pack("<q", 5) + struct.pack("<q", 1) + struct.pack("<q", 16) + struct.pack("<i", 4) + struct.pack("<i", 3))
+    body = (struct.pack("<i", 3) + struct.pack("<i", 1) + struct.pack("<i", 2) + struct.pack("<i", 2) + _s("a") + t_a
+            + struct.pack("<i", 2) + _s("b") + t_b)
+    p = tmp_path / "strided.t7"
+    p.write_bytes(body)
+    t = t7.load(str(p))
+    assert np.array_equal(t["a"], data[3:3 + 12].reshape(3, 4).T)
+    assert np.array_equal(t["b"], data[15:20])
+
+
+def test_generic_torch_object_fields(tmp_path):
+    """An nn module without a dedicated reader is returned with its fields (how protos.ae.lookup_table is reached)."""
+    w = np.array([[1, 2], [3, 4]], dtype="<f4")
+    storage = (struct.pack("<i", 4) + struct.pack("<i", 4) + _s("V 1") + _s("torch.FloatStorage") + struct.pack("<q", 4) + w.tobytes())
+    tensor = (struct.pack("<i", 4) + struct.pack("<i", 3) + _s("V 1") + _s("torch.FloatTensor") + struct.pack("<i", 2)
+              + struct.pack("<qq", 2, 2) + struct.pack("<qq", 2, 1) + struct.pack("<q", 1) + storage)
+    fields = struct.pack("<i", 3) + struct.pack("<i", 2) + struct.pack("<i", 1) + struct.pack("<i", 2) + _s("weight") + tensor
+    body = struct.pack("<i", 4) + struct.pack("<i", 1) + _s("V 1") + _s("nn.LookupTable") + fields
+    p = tmp_path / "mod.t7"
+    p.write_bytes(body)
+    m = t7.load(str(p))
+    assert m.torch_class == "nn.LookupTable" and np.array_equal(m.weight, w)
+
+
+def test_autoencoder_to_arch1_conversion():
+    """002_convert_text_model_arch1.lua:33-38 then 003_train_ae_based.lua:175-183."""
+    V, E = 11, 4
+    r = np.random.default_rng(1)
+    lut = r.standard_normal((V + 1, E)).astype(np.float32)
+    enc = r.standard_normal(50).astype(np.float32)
+    saved = t7.convert_autoencoder(lut, enc)
+    assert saved["lookup"].shape == (E, V + 1) and np.array_equal(saved["lookup"][:, 3], lut[3])
+    enc_w, emb_w = t7.arch1_blocks_from_autoencoder(saved, V, E)
+    assert np.array_equal(enc_w, enc)
+    W = emb_w[:V * E].reshape(E, V)                     # nn.Linear(V, E).weight
+    assert np.array_equal(W, lut[:V].T) and np.all(emb_w[V * E:] == 0)
+    # one-hot Linear with this weight == LookupTable gather of the first V rows
+    onehot = np.eye(V, dtype=np.float32)[[2, 7]]
+    assert np.allclose(onehot @ W.T, lut[[2, 7]])
