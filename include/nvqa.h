@@ -102,6 +102,10 @@ int nvqa_pack_batch(const int32_t* q_right_aligned, const int32_t* lengths, int3
                     int32_t* words, int32_t* batch_sizes, int32_t* sort_index,
                     int32_t* sort_index_inverse, int32_t* n_words, int32_t* n_steps);
 
+/* multiple-choice answer selection (004_eval_model.lua:257-271): out[i] = the candidate id (1-based, 0 = padding in
+ * mc_ids [n x K]) with the highest score in scores [n x O]; first candidate wins ties; 0 if a row has no candidate */
+int nvqa_mc_select(const float* scores, const int32_t* mc_ids, int32_t n, int32_t O, int32_t K, int32_t* out);
+
 /* ---- one step, piecewise (device pointers; rows in ORIGINAL batch order, no sort needed) --- */
 /* q: [B x T] right-aligned token ids, len: [B], fc7: [B x I], labels: [B] 1-based (may be NULL
  * for eval).  Pointers must stay valid until the step's last kernel has run. */

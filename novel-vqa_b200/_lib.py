@@ -40,6 +40,7 @@ SIGNATURES = {
     "nvqa_device_views": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_i64p]),
     "nvqa_right_align": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p]),
     "nvqa_pack_batch": (C.c_int, [c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
+    "nvqa_mc_select": (C.c_int, [c_f32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p]),
     "nvqa_set_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "nvqa_set_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "nvqa_set_steps": (C.c_int, [C.c_void_p, C.c_int32]),

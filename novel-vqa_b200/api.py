@@ -15,7 +15,7 @@ from ._lib import (PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_BF16X2, BLOCK_EN
                    NvqaError)
 
 __all__ = ["Arch1Config", "Arch1Model", "Arch2Config", "Arch2Model", "synth_params2", "synth_batch2", "BLOCK_CNN",
-           "AEConfig", "AEModel", "synth_params_ae", "synth_batch_ae", "BLOCK_AE_ENCODER", "BLOCK_AE_DECODER", "BLOCK_AE_LOOKUP", "DeviceBuffer", "right_align", "pack_batch", "synth_batch", "synth_params",
+           "AEConfig", "AEModel", "synth_params_ae", "synth_batch_ae", "BLOCK_AE_ENCODER", "BLOCK_AE_DECODER", "BLOCK_AE_LOOKUP", "DeviceBuffer", "right_align", "pack_batch", "mc_select", "synth_batch", "synth_params",
            "device_count", "launch_count", "PREC_FP32_SIMT", "PREC_BF16X3", "PREC_BF16", "PREC_BF16X2",
            "BLOCK_ENCODER", "BLOCK_EMBEDDING", "BLOCK_MULTIMODAL", "MODE_EVAL", "MODE_TRAIN", "PHASE_HEAD",
            "PHASE_LSTM", "PHASE_EMBED", "PHASE_ALL", "NvqaError", "DECAY_FACTOR"]
@@ -109,6 +109,15 @@ def pack_batch(q_ra, lengths):
     _lib.check(_lib.load().nvqa_pack_batch(p(q_ra), p(lengths), B, T, p(words), p(sizes), p(sidx), p(inv),
                                            C.byref(nw), C.byref(ns)))
     return words[:nw.value].copy(), sizes[:ns.value].copy(), sidx, inv
+
+
+def mc_select(scores, mc_ids):
+    """004_eval_model.lua:257-271 through the C ABI: scores [n x O] float32, mc_ids [n x K] int32 (0 = padding)."""
+    scores, mc_ids = _f32(scores), _i32(mc_ids)
+    out = np.empty(scores.shape[0], dtype=np.int32)
+    _lib.check(_lib.load().nvqa_mc_select(scores.ctypes.data_as(_lib.c_f32p), mc_ids.ctypes.data_as(_lib.c_i32p),
+                                          scores.shape[0], scores.shape[1], mc_ids.shape[1], out.ctypes.data_as(_lib.c_i32p)))
+    return out
 
 
 class DeviceBuffer:

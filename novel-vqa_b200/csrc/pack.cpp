@@ -58,3 +58,24 @@ extern "C" int nvqa_pack_batch(const int32_t* q, const int32_t* lengths, int32_t
   if (n_steps) *n_steps = L;
   return 0;
 }
+
+// Multiple-choice answer selection (002_train_vqa_arch1/004_eval_model.lua:257-271): for every question the argmax of
+// its scores restricted to the non-zero candidate answer ids of MC_ans_test (1-based ids, 0 = padding); ties keep the
+// FIRST candidate in list order (torch.max over the gathered values).  Host loop in the reference as well.
+extern "C" int nvqa_mc_select(const float* scores, const int32_t* mc_ids, int32_t n, int32_t O, int32_t K, int32_t* out) {
+  if (!scores || !mc_ids || !out || n < 0 || O <= 0 || K <= 0) { nvqa::set_error("nvqa_mc_select: bad argument"); return 1; }
+  for (int32_t i = 0; i < n; ++i) {
+    const float* s = scores + (int64_t)i * O;
+    const int32_t* c = mc_ids + (int64_t)i * K;
+    int32_t best = 0;
+    float bv = 0.f;
+    for (int32_t j = 0; j < K; ++j) {
+      if (c[j] == 0) continue;
+      if (c[j] < 1 || c[j] > O) { nvqa::set_error("nvqa_mc_select: candidate id out of range"); return 1; }
+      const float v = s[c[j] - 1];
+      if (best == 0 || v > bv) { best = c[j]; bv = v; }
+    }
+    out[i] = best;           // 0 when a question has no candidate (the reference would raise on an empty tensor)
+  }
+  return 0;
+}

@@ -180,3 +180,19 @@ def test_multiple_choice_select():
     s = np.array([0.1, 0.9, 0.3, 0.9])
     assert A.multiple_choice_select(s, [3, 0, 4, 2, 0]) == 4      # first max among candidates in list order
     assert A.argmax_first(np.array([[1.0, 3.0, 3.0]]))[0] == 2
+
+
+def test_multiple_choice_select_c_abi_bit_exact():
+    """nvqa_mc_select (host, 004_eval_model.lua:257-271) against the oracle, incl. ties and padded candidate lists."""
+    import novel_vqa_b200 as nv
+    r = np.random.default_rng(3)
+    n, O, K = 300, 1000, 18
+    scores = r.standard_normal((n, O)).astype(np.float32)
+    scores[:, ::7] = 0.25                                      # plenty of exact ties
+    mc = np.zeros((n, K), dtype=np.int32)
+    for i in range(n):
+        k = r.integers(1, K + 1)
+        mc[i, :k] = r.choice(np.arange(1, O + 1), k, replace=False)
+    got = nv.mc_select(scores, mc)
+    want = [A.multiple_choice_select(scores[i], mc[i]) for i in range(n)]
+    assert got.tolist() == want
