@@ -17,6 +17,12 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
                         __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
                         int B, int H, unsigned int* counter);
 
+// Second generation (lstm_persistent_v2.cu): W_hh slice resident in shared memory (plane 0) AND tensor memory (plane 1),
+// 128 gate rows per CTA, 64-row h tiles; same contract, returns -1 for shapes it does not cover.
+int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
+                           __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
+                           int B, int H, unsigned int* counter);
+
 // All T steps of one layer's backward recurrence (see lstm_persistent.cu).
 //   gates [T][B][4H] post-activation, c [(T+1)][B][H]; dh0/dc0 (leading dim ld0): d(final state) of this layer;
 //   dh_above [T][B][H]: dX of the layer above (masked by its input Dropout) or nullptr;

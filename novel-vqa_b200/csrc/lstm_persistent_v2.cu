@@ -1,0 +1,348 @@
+// Persistent multi-timestep LSTM forward, second generation (sm_100a): the recurrent WEIGHTS are the resident MMA
+// operand in BOTH on-chip memories of the SM -- plane 0 of the CTA's W_hh slice in shared memory (128 KB), plane 1 in
+// TENSOR MEMORY (128 KB = 256 of the 512 TMEM columns) -- so a CTA covers 128 gate rows (32 hidden units x 4 gates)
+// instead of 64 and only has to ingest a 64-row tile of h_{t-1} per step: 128 KB instead of 256 KB.  The per-step time
+// of the first-generation kernel (lstm_persistent.cu) is dominated by that ingest (measured 31 B/clk/SM through TMA,
+// unicast or multicast alike) plus latencies, not by the tensor pipe.
+//
+// Replaces the same reference code as lstm_fwd_persistent_kernel: T x { h2h nn.Linear + gate graph } of
+// 002_train_vqa_arch1/misc/LSTM.lua:42-59 driven by rnn_forward (misc/RNNUtils.lua:128-154).
+//
+//   roles  D[gate row m][batch n] (+)= W[m][k] . h_{t-1}[n][k]      (operands swapped w.r.t. generation 1)
+//          A = W slice, M = 128 rows ordered m = gate * 32 + unit:  plane 0 from SMEM (K-major, SWIZZLE_128B),
+//                                                                    plane 1 from TMEM (lane m, column k/2)
+//          B = h_{t-1} tile, N = 64 batch rows, K-major bf16 planes streamed by TMA through a 4-stage ring
+//          bf16x2: per k16 step  W1.h0 (TS)  +  W0.h1 (SS)  +  W0.h0 (SS), fp32 accumulation in TMEM columns [0, 64)
+//   grid   (H/32 unit slices) x (ceil(B/64) batch tiles), one CTA per SM, all co-resident (cooperative launch);
+//          the CTAs of a batch tile synchronise per step through one counter (release-add / acquire-poll)
+//   epilogue  tcgen05.ld gives a thread ONE gate row x 32 batch columns; the tile is transposed through shared memory
+//          (aliasing the idle B ring) so that a thread owns (batch row, 8 units x 4 gates) -- the gate math, the c
+//          carry in registers and every global access are then those of generation 1, with 4x fewer cache lines per
+//          warp access (4 lanes cover 128 contiguous bytes of a row).
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "lstm_persistent.cuh"
+#include "umma_ptx.cuh"
+
+namespace nvqa {
+
+constexpr int V2_THREADS = 320;          // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+constexpr int V2_EPI = 256;
+constexpr int V2_STAGES = 4;
+constexpr int V2_TPITCH = 132;           // words per row of the transpose tile (128 + 4: conflict-free 128-bit reads)
+
+__device__ __forceinline__ void v2_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void v2_arrive(unsigned int* ctr) {
+  unsigned int old;
+  asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+  if (old == 0xFFFFFFFFu) __trap();
+}
+__device__ __forceinline__ void v2_wait(unsigned int* ctr, unsigned int target) {
+  const long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    asm volatile("atom.acquire.gpu.global.add.u32 %0, [%1], 0;" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= target) break;
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("lstm_persistent_v2: group barrier timed out (block %d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, v, target);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ float v2_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float v2_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+template <int P>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
+                   const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
+                   float* __restrict__ h, __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
+                   const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t W_KB = 128 * 128;                  // one k-block of the W0 slice: 128 rows x 128 B
+  constexpr uint32_t B_PLANE = 64 * 128;                // one plane of one k-block of the h tile: 64 rows x 128 B
+  constexpr uint32_t STAGE = P * B_PLANE;
+  const uint32_t w0 = base;
+  const uint32_t r0 = w0 + (uint32_t)KB * W_KB;         // B ring (the transpose tile aliases its first 33 KB)
+  const uint32_t bar0 = r0 + V2_STAGES * STAGE + (P == 1 ? 2 * STAGE : 0);   // P = 1: ring is 32 KB, the tile needs 33 KB
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * V2_STAGES, wfull = bar0 + 16 * V2_STAGES, tfull = wfull + 8,
+                 gobar = wfull + 16, w1bar = wfull + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * V2_STAGES + 32);
+  float* tbuf = reinterpret_cast<float*>(smem_raw + (r0 - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * 32, m0 = blockIdx.y * 64;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < V2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      mbar_init(wfull, 1);
+      mbar_init(tfull, 1);
+      mbar_init(gobar, 1);
+      mbar_init(w1bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t W1_COL = 256;                      // TMEM columns [256, 512): plane 1 of the W slice
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      // resident W0 slice: smem row (g * 32 + j) of k-block kb <- plane 0, W row g*H + u0 + j
+      mbar_expect_tx(wfull, (uint32_t)KB * W_KB);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int g = 0; g < 4; ++g)
+          tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)g * 4096, &mapW, wfull, kb * 64, g * H + u0, 0);
+      int it = 0;
+      const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
+      for (int t = 0; t < T; ++t) {
+        if (t > 0) {
+          v2_wait(counter + 32 * blockIdx.y, (unsigned int)t * gridDim.x);     // h_{t-1} of this batch tile is complete
+          fence_proxy_async();
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          mbar_expect_tx(full0 + 8 * s, STAGE);
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            tma_load_3d(r0 + (uint32_t)s * STAGE + (uint32_t)p * B_PLANE, &mapH, full0 + 8 * s, kb * 64, t * B + m0, p);
+          if (kb == gokb) mbar_arrive(gobar);      // this step's first loads are out: the epilogue may use the memory pipe
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+      mbar_wait(wfull, 0);
+      if (P >= 2) mbar_wait(w1bar, 0);             // plane 1 of the W slice has been stored to TMEM by the epilogue warps
+      tc_fence_after();
+      int it = 0;
+      for (int t = 0; t < T; ++t) {
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dw = make_kmajor_sw128_desc(w0 + (uint32_t)kb * W_KB + k * 32);
+            const uint64_t dh0 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + k * 32);
+            if (P >= 2) {
+              const uint64_t dh1 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + B_PLANE + k * 32);
+              umma_f16_ts(tmem_base, tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8), dh0, idesc, acc); acc = 1;
+              umma_f16(tmem_base, dw, dh1, idesc, acc);
+            }
+            umma_f16(tmem_base, dw, dh0, idesc, acc); acc = 1;
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else {
+    // ===== 8 epilogue warps =====
+    const int q = warp & 3;                       // TMEM lane quarter of this warp = gate index (m = gate * 32 + unit)
+    const int ch = (warp - 2) >> 2;               // which 32 batch columns of the accumulator this warp drains
+    const int et = threadIdx.x - 64;              // 0..255: after the transpose, thread = (batch row n, unit group ug)
+    const int n = et >> 2, ug = et & 3;
+    const int b = m0 + n;
+    const bool rowok = b < B;
+    const int mylen = rowok ? (len ? len[b] : T) : 0;
+    const int uo = u0 + 8 * ug;
+    if (P >= 2) {
+      // plane 1 of the W slice -> TMEM lane (32 q + lane), columns W1_COL + [128 ch, 128 ch + 128): k in [256 ch, 256 ch + 256)
+      const __nv_bfloat16* src = w1 + (size_t)(q * H + u0 + lane) * w_pitch + 256 * ch;
+#pragma unroll 1
+      for (int blk = 0; blk < 4; ++blk) {
+        uint32_t wv[32];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const uint4 x = *reinterpret_cast<const uint4*>(src + blk * 64 + v * 8);
+          wv[4 * v] = x.x; wv[4 * v + 1] = x.y; wv[4 * v + 2] = x.z; wv[4 * v + 3] = x.w;
+        }
+        tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + W1_COL + (uint32_t)(128 * ch + 32 * blk), wv);
+      }
+      tc_fence_before();
+    }
+    v2_bar_sync(1, V2_EPI);
+    if (P >= 2 && threadIdx.x == 64) mbar_arrive(w1bar);      // hand the TMEM-resident operand to the MMA thread
+    float ccarry[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ccarry[j] = 0.f;
+    if (rowok) {
+      const float4 c0a = *reinterpret_cast<const float4*>(c + (size_t)b * H + uo);
+      const float4 c0b = *reinterpret_cast<const float4*>(c + (size_t)b * H + uo + 4);
+      ccarry[0] = c0a.x; ccarry[1] = c0a.y; ccarry[2] = c0a.z; ccarry[3] = c0a.w;
+      ccarry[4] = c0b.x; ccarry[5] = c0b.y; ccarry[6] = c0b.z; ccarry[7] = c0b.w;
+    }
+    for (int t = 0; t < T; ++t) {
+      const bool active = rowok && (t >= T - mylen);
+      const size_t rin = (size_t)t * B + b, rout = (size_t)(t + 1) * B + b;
+      float4 pv[4][2];
+      if (active) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float* src = pre + rin * 4 * H + (size_t)g * H + uo;
+          pv[g][0] = *reinterpret_cast<const float4*>(src);
+          pv[g][1] = *reinterpret_cast<const float4*>(src + 4);
+        }
+      }
+      mbar_wait(tfull, (uint32_t)t & 1u);
+      tc_fence_after();
+      {
+        // accumulator -> shared memory, transposed: tbuf[n][m]   (the B ring is idle between tfull and our arrive)
+        float acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), acc);
+        float* dst = tbuf + (size_t)(ch * 32) * V2_TPITCH + q * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[(size_t)j * V2_TPITCH] = acc[j];
+      }
+      tc_fence_before();
+      v2_bar_sync(2, V2_EPI);
+      float gi[8], gf[8], go[8], gg[8], cn[8], hn[8];
+      if (active) {
+        const float* row = tbuf + (size_t)n * V2_TPITCH + 8 * ug;
+        float a[4][8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 x0 = *reinterpret_cast<const float4*>(row + g * 32), x1 = *reinterpret_cast<const float4*>(row + g * 32 + 4);
+          a[g][0] = x0.x; a[g][1] = x0.y; a[g][2] = x0.z; a[g][3] = x0.w; a[g][4] = x1.x; a[g][5] = x1.y; a[g][6] = x1.z; a[g][7] = x1.w;
+        }
+        const float* pi = reinterpret_cast<const float*>(&pv[0][0]);
+        const float* pf = reinterpret_cast<const float*>(&pv[1][0]);
+        const float* po = reinterpret_cast<const float*>(&pv[2][0]);
+        const float* pg = reinterpret_cast<const float*>(&pv[3][0]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          gi[j] = v2_sigmoid(a[0][j] + pi[j]);
+          gf[j] = v2_sigmoid(a[1][j] + pf[j]);
+          go[j] = v2_sigmoid(a[2][j] + po[j]);
+          gg[j] = v2_tanh(a[3][j] + pg[j]);
+          cn[j] = gf[j] * ccarry[j] + gi[j] * gg[j];
+          hn[j] = go[j] * v2_tanh(cn[j]);
+          ccarry[j] = cn[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gi[j] = gf[j] = go[j] = gg[j] = cn[j] = hn[j] = 0.f; }
+      }
+      // (1) the only output the NEXT step depends on: h_t as bf16 planes, row (t+1)*B + b of [P][(T+1)B][H]
+      if (rowok) {
+        __nv_bfloat16 pl[3][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split3(hn[j], pl[0][j], pl[1][j], pl[2][j]);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          uint4 o;
+          o.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+          o.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+          o.z = (uint32_t)__bfloat16_as_ushort(pl[p][4]) | ((uint32_t)__bfloat16_as_ushort(pl[p][5]) << 16);
+          o.w = (uint32_t)__bfloat16_as_ushort(pl[p][6]) | ((uint32_t)__bfloat16_as_ushort(pl[p][7]) << 16);
+          *reinterpret_cast<uint4*>(hp + (size_t)p * hp_plane + rout * H + uo) = o;
+        }
+      }
+      // (2) publish it: generic-proxy writes (global h planes AND the shared-memory tile that the next TMA loads will
+      // overwrite) are ordered before later async-proxy accesses; one thread's gpu-scope release is made cumulative
+      // over the CTA by the barrier
+      fence_proxy_async();
+      v2_bar_sync(1, V2_EPI);
+      if (threadIdx.x == 64) v2_arrive(counter + 32 * blockIdx.y);
+      v2_bar_sync(3, V2_EPI);                      // keep the SM's memory pipeline clear until the release is out ...
+      if (t + 1 < T) mbar_wait(gobar, (uint32_t)(t + 1) & 1u);   // ... and until the next step's first loads are issued
+      // (3) everything only the backward pass needs, off the critical path
+      if (rowok) {
+        float* gdst = pre + rin * 4 * H + uo;
+#define ST8(ptr, a)                                                                          \
+        *reinterpret_cast<float4*>(ptr) = make_float4(a[0], a[1], a[2], a[3]);               \
+        *reinterpret_cast<float4*>((ptr) + 4) = make_float4(a[4], a[5], a[6], a[7]);
+        ST8(gdst, gi) ST8(gdst + H, gf) ST8(gdst + 2 * H, go) ST8(gdst + 3 * H, gg)
+        ST8(c + rout * H + uo, cn) ST8(h + rout * H + uo, hn)
+        if (xdrop) {
+          float xd[8];
+          const uint64_t mi = (uint64_t)rin * H + uo;
+          float4 ma = drop_at4(drop, mi), mb = drop_at4(drop, mi + 4);
+          xd[0] = hn[0] * ma.x; xd[1] = hn[1] * ma.y; xd[2] = hn[2] * ma.z; xd[3] = hn[3] * ma.w;
+          xd[4] = hn[4] * mb.x; xd[5] = hn[5] * mb.y; xd[6] = hn[6] * mb.z; xd[7] = hn[7] * mb.w;
+          ST8(xdrop + rin * H + uo, xd)
+        }
+#undef ST8
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static bool v2_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("NVQA_LSTM_V2"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+
+// Same contract as lstm_fwd_persistent (lstm_persistent.cuh).  Returns -1 when the shape is not supported by this
+// generation (the caller then tries generation 1, then the per-step kernels).
+int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
+                           __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
+                           int B, int H, unsigned int* counter) {
+  if (!v2_enabled()) return -1;
+  if (P < 1 || P > 2) return -1;
+  if (H % 64 != 0 || H != 512) return -1;          // the W slice (plane 0: SMEM, plane 1: 256 TMEM columns) is sized for K = 512
+  static int num_sms = 0, max_smem = 0;
+  if (!num_sms) {
+    int dev = 0;
+    NVQA_CUDA(cudaGetDevice(&dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  const int KB = H / 64;
+  dim3 grid(H / 32, ceil_div(B, 64));
+  if ((int)(grid.x * grid.y) > num_sms) return -1;
+  const size_t ring = (size_t)V2_STAGES * P * 8192 + (P == 1 ? 2 * 8192 : 0);
+  const size_t smem = (size_t)KB * 16384 + ring + 1024 + 256;
+  if (ring < (size_t)64 * V2_TPITCH * 4 || smem > (size_t)max_smem) return -1;
+
+  __nv_bfloat16* wp = nullptr;
+  int pitch = 0;
+  NVQA_TRY(prepare_planes(ws, s, P, Wh, 4 * H, H, H, true, &wp, &pitch));
+  CUtensorMap mapW, mapH;
+  NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 32, &mapW));
+  if (hp_plane_rows <= 0) hp_plane_rows = (long long)(T + 1) * B;
+  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 64, &mapH, hp_plane_rows * H));
+  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
+  long long hp_plane = hp_plane_rows * H;
+  const __nv_bfloat16* w1 = wp + (size_t)4 * H * pitch;            // plane 1
+  int KBv = KB;
+  void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter};
+  const void* fn = P == 2 ? (const void*)lstm_fwd_v2_kernel<2> : (const void*)lstm_fwd_v2_kernel<1>;
+  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeCooperative; attr.val.cooperative = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  NVQA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+  ++g_launches;
+  return 0;
+}
+
+}  // namespace nvqa

@@ -533,8 +533,11 @@ static int lstm_layers_forward(nvqa_model* m, const LstmSeg& sg, const int32_t* 
     if (m->planes && m->use_persistent) {
       // K4: all T steps in one persistent cooperative kernel (W_hh slice resident in shared memory)
       ProfScope ps(m, CAT_REC_FWD, 2.0 * (T - (sg.has_init ? 0 : 1)) * B * 4.0 * H * H);
-      int rc = lstm_fwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
-                                   (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter);
+      int rc = lstm_fwd_persistent_v2(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
+                                      (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter);
+      if (rc < 0)
+        rc = lstm_fwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
+                                 (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter);
       if (rc > 0) return rc;
       m->hp_valid[l] = rc == 0;
       if (rc == 0) continue;
