@@ -23,6 +23,11 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
                            __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
                            int B, int H, unsigned int* counter);
 
+int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
+                           const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* dasum,
+                           __nv_bfloat16* dap, long long dap_plane_rows, float* dhbuf, float* dh_init, float* dc_init,
+                           const int32_t* len, int T, int B, int H, unsigned int* counter);
+
 // All T steps of one layer's backward recurrence (see lstm_persistent.cu).
 //   gates [T][B][4H] post-activation, c [(T+1)][B][H]; dh0/dc0 (leading dim ld0): d(final state) of this layer;
 //   dh_above [T][B][H]: dX of the layer above (masked by its input Dropout) or nullptr;

@@ -293,6 +293,329 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, generation 2: all T steps of rnn_backward for one layer (misc/RNNUtils.lua:181-210; cell math SURVEY App. A).
+// Same two-phase structure as lstm_bwd_persistent_kernel (phase A: element-wise cell backward spread over the whole
+// grid, phase B: dh_{t-1} partial = da_t[:, gate block] . W_hh[gate block, :], split-K over the four gate blocks), with
+// the roles of phase B swapped as in the forward kernel:
+//     D[dh column m][batch n] = sum_k W_hh[k_base + k][c0 + m] . da_t[n][k_base + k]
+//     A = W_hh^T slice, M = 128 dh columns, K = H rows of one gate block: plane 0 in SMEM as an MN-major operand (the
+//         weight matrix is read as stored, no transposed copy), plane 1 in TMEM (lane m, column k/2)
+//     B = da_t tile, N = 64 batch rows, K-major planes streamed by TMA: 128 KB per step instead of 256 KB
+//   grid = (H/128 column tiles) x (4 K-splits) x (ceil(B/64) batch tiles)
+constexpr int V2_BPITCH = 144;           // transpose-tile pitch of the backward epilogue (conflict-free 128-bit reads)
+
+__device__ __forceinline__ void v2_grid_wait(unsigned int* counter, unsigned int target) { v2_wait(counter, target); }
+
+template <int P>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+lstm_bwd_v2_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
+                   const __nv_bfloat16* __restrict__ w1, int w_pitch, const float* __restrict__ gates,
+                   const float* __restrict__ c, const float* __restrict__ dh0, const float* __restrict__ dc0, int ld0,
+                   const float* __restrict__ dh_above, Drop drop, float* __restrict__ dasum,
+                   __nv_bfloat16* __restrict__ dap, long long dap_plane, float* __restrict__ dhbuf,
+                   float* __restrict__ dc_init, const int32_t* __restrict__ len, int T, int B, int H, int KB,
+                   unsigned int* counter) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t W_KB = 128 * 128;                  // one k-block of the W0 slice: two [64 k x 64 m] boxes
+  constexpr uint32_t B_PLANE = 64 * 128;
+  constexpr uint32_t STAGE = P * B_PLANE;
+  constexpr uint32_t RING = V2_STAGES * STAGE < 64 * V2_BPITCH * 4 ? 64 * V2_BPITCH * 4 + 1024 - (64 * V2_BPITCH * 4) % 1024
+                                                                  : V2_STAGES * STAGE;
+  const uint32_t w0 = base;
+  const uint32_t r0 = w0 + (uint32_t)KB * W_KB;
+  const uint32_t bar0 = r0 + RING;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * V2_STAGES, wfull = bar0 + 16 * V2_STAGES, tfull = wfull + 8,
+                 gobar = wfull + 16, w1bar = wfull + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * V2_STAGES + 32);
+  float* tbuf = reinterpret_cast<float*>(smem_raw + (r0 - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 128, ks = blockIdx.y, m0 = blockIdx.z * 64;
+  const unsigned int G = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int k_base = ks * H;
+  const int tlast = dc_init ? 0 : 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapDA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < V2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      mbar_init(wfull, 1);
+      mbar_init(tfull, 1);
+      mbar_init(gobar, 1);
+      mbar_init(w1bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t W1_COL = 256;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      // W0 slice, MN-major: per k-block two boxes [64 k-rows x 64 columns] (columns c0 + 64 cc)
+      mbar_expect_tx(wfull, (uint32_t)KB * W_KB);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int cc = 0; cc < 2; ++cc)
+          tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)cc * 8192, &mapW, wfull, c0 + 64 * cc, k_base + kb * 64, 0);
+      int it = 0;
+      const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
+      for (int t = T - 1; t >= tlast; --t) {
+        const unsigned int k = (unsigned int)(T - 1 - t);
+        v2_grid_wait(counter, (2 * k + 1) * G);             // da_t is complete everywhere
+        fence_proxy_async();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          mbar_expect_tx(full0 + 8 * s, STAGE);
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            tma_load_3d(r0 + (uint32_t)s * STAGE + (uint32_t)p * B_PLANE, &mapDA, full0 + 8 * s, k_base + kb * 64, t * B + m0, p);
+          if (kb == gokb) mbar_arrive(gobar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, false);       // A = W_hh^T slice in SMEM, MN-major
+      constexpr uint32_t idesc_ts = make_idesc_bf16(128, 64, false, false);   // A from TMEM is K-major by construction
+      mbar_wait(wfull, 0);
+      if (P >= 2) mbar_wait(w1bar, 0);
+      tc_fence_after();
+      int it = 0;
+      for (int t = T - 1; t >= tlast; --t) {
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dw = make_mnmajor_sw128_desc(w0 + (uint32_t)kb * W_KB + k * 2048);
+            const uint64_t d0 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + k * 32);
+            if (P >= 2) {
+              const uint64_t d1 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + B_PLANE + k * 32);
+              umma_f16_ts(tmem_base, tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8), d0, idesc_ts, acc); acc = 1;
+              umma_f16(tmem_base, dw, d1, idesc, acc);
+            }
+            umma_f16(tmem_base, dw, d0, idesc, acc); acc = 1;
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else {
+    // ===== 8 element-wise / epilogue warps =====
+    const int et = threadIdx.x - 64;                         // 0..255
+    const int q = warp & 3, ch = (warp - 2) >> 2;
+    const int H4 = H >> 2;
+    const long long items = (long long)B * H4;
+    const long long gthreads = (long long)G * V2_EPI;
+    if (P >= 2) {
+      // plane 1 of the W_hh^T slice -> TMEM lane m = 32 q + lane (dh column c0 + m), columns W1_COL + k/2,
+      // k in [256 ch, 256 ch + 256): element (m, k) = W1[k_base + k][c0 + m]
+      const __nv_bfloat16* src = w1 + (size_t)(k_base + 256 * ch) * w_pitch + c0 + q * 32 + lane;
+#pragma unroll 1
+      for (int blk = 0; blk < 4; ++blk) {
+        uint32_t wv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t lo = __bfloat16_as_ushort(src[(size_t)(blk * 64 + 2 * j) * w_pitch]);
+          const uint32_t hi = __bfloat16_as_ushort(src[(size_t)(blk * 64 + 2 * j + 1) * w_pitch]);
+          wv[j] = lo | (hi << 16);
+        }
+        tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + W1_COL + (uint32_t)(128 * ch + 32 * blk), wv);
+      }
+      tc_fence_before();
+    }
+    v2_bar_sync(1, V2_EPI);
+    if (P >= 2 && et == 0) mbar_arrive(w1bar);
+    constexpr int NI = 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool valid[NI];
+    int bq[NI], ucol[NI], first_t[NI];
+    float4 gi[NI], gf[NI], go[NI], gg[NI], cp[NI], cn[NI], dcr[NI];
+    float4 bsi[NI], bsf[NI], bso[NI], bsg[NI];
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      bsi[n] = bsf[n] = bso[n] = bsg[n] = z;
+      const long long i = (long long)cta * V2_EPI + et + (long long)n * gthreads;
+      valid[n] = i < items;
+      bq[n] = valid[n] ? (int)(i / H4) : 0;
+      ucol[n] = valid[n] ? (int)(i % H4) * 4 : 0;
+      first_t[n] = valid[n] ? (len ? T - len[bq[n]] : 0) : T;
+      gi[n] = gf[n] = go[n] = gg[n] = cp[n] = cn[n] = dcr[n] = z;
+      if (T - 1 >= first_t[n]) {
+        const size_t row = (size_t)(T - 1) * B + bq[n];
+        const float* g = gates + row * 4 * H + ucol[n];
+        gi[n] = *reinterpret_cast<const float4*>(g);
+        gf[n] = *reinterpret_cast<const float4*>(g + H);
+        go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+        gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+        cp[n] = *reinterpret_cast<const float4*>(c + row * H + ucol[n]);
+        cn[n] = *reinterpret_cast<const float4*>(c + (row + B) * H + ucol[n]);
+        dcr[n] = *reinterpret_cast<const float4*>(dc0 + (size_t)bq[n] * ld0 + ucol[n]);
+      }
+    }
+    const size_t BHs = (size_t)B * H;
+    for (int t = T - 1; t >= 0; --t) {
+      const unsigned int k = (unsigned int)(T - 1 - t);
+      if (t < T - 1) {                                       // dh_t (split-K sums of step t+1) complete everywhere
+        if (et == 0) v2_grid_wait(counter, (2 * k) * G);
+        v2_bar_sync(2, V2_EPI);
+      }
+      // ---- phase A: cell backward, element-wise ----
+      const float* dh_src = dhbuf + (size_t)((t + 1) & 1) * 4 * BHs;
+      float* dh_part = dhbuf + ((size_t)(t & 1) * 4 + ks) * BHs;
+      float4 dai[NI], daf[NI], dao[NI], dag[NI];
+      size_t row[NI];
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        row[n] = (size_t)t * B + bq[n];
+        dai[n] = daf[n] = dao[n] = dag[n] = z;
+        if (!valid[n]) continue;
+        if (t >= first_t[n]) {
+          const size_t o = (size_t)bq[n] * H + ucol[n];
+          float4 dh;
+          if (t == T - 1) {
+            dh = *reinterpret_cast<const float4*>(dh0 + (size_t)bq[n] * ld0 + ucol[n]);
+          } else {
+            const float* ds = dh_src + o;
+            float4 d0 = *reinterpret_cast<const float4*>(ds), d1 = *reinterpret_cast<const float4*>(ds + BHs),
+                   d2 = *reinterpret_cast<const float4*>(ds + 2 * BHs), d3 = *reinterpret_cast<const float4*>(ds + 3 * BHs);
+            dh = make_float4((d0.x + d1.x) + (d2.x + d3.x), (d0.y + d1.y) + (d2.y + d3.y), (d0.z + d1.z) + (d2.z + d3.z),
+                             (d0.w + d1.w) + (d2.w + d3.w));
+          }
+          if (dh_above) {
+            float4 ua = *reinterpret_cast<const float4*>(dh_above + row[n] * H + ucol[n]);
+            float4 mk = drop_at4(drop, (uint64_t)row[n] * H + ucol[n]);
+            dh.x += ua.x * mk.x; dh.y += ua.y * mk.y; dh.z += ua.z * mk.z; dh.w += ua.w * mk.w;
+          }
+#define LB(kk)                                                                     \
+          { float tc = v2_tanh(cn[n].kk);                                            \
+            float dct = dcr[n].kk + dh.kk * go[n].kk * (1.0f - tc * tc);             \
+            dao[n].kk = dh.kk * tc * go[n].kk * (1.0f - go[n].kk);                   \
+            dai[n].kk = dct * gg[n].kk * gi[n].kk * (1.0f - gi[n].kk);               \
+            daf[n].kk = dct * cp[n].kk * gf[n].kk * (1.0f - gf[n].kk);               \
+            dag[n].kk = dct * gi[n].kk * (1.0f - gg[n].kk * gg[n].kk);               \
+            dcr[n].kk = dct * gf[n].kk; }
+          LB(x) LB(y) LB(z) LB(w)
+#undef LB
+#define ACC4(a, b) a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          ACC4(bsi[n], dai[n]) ACC4(bsf[n], daf[n]) ACC4(bso[n], dao[n]) ACC4(bsg[n], dag[n])
+#undef ACC4
+        }
+        // (1) what phase B consumes through TMA: da_t as bf16 planes
+        const float4 gsrc[4] = {dai[n], daf[n], dao[n], dag[n]};
+#pragma unroll
+        for (int gI = 0; gI < 4; ++gI) {
+          __nv_bfloat16 pl[3][4];
+          split3(gsrc[gI].x, pl[0][0], pl[1][0], pl[2][0]);
+          split3(gsrc[gI].y, pl[0][1], pl[1][1], pl[2][1]);
+          split3(gsrc[gI].z, pl[0][2], pl[1][2], pl[2][2]);
+          split3(gsrc[gI].w, pl[0][3], pl[1][3], pl[2][3]);
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            uint2 ov;
+            ov.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+            ov.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+            *reinterpret_cast<uint2*>(dap + (size_t)p * dap_plane + row[n] * 4 * H + (size_t)gI * H + ucol[n]) = ov;
+          }
+        }
+      }
+      // (2) publish da_t (barrier 2k+1)
+      fence_proxy_async();
+      v2_bar_sync(1, V2_EPI);
+      if (et == 0) v2_arrive(counter);
+      v2_bar_sync(3, V2_EPI);
+      if (t >= tlast) mbar_wait(gobar, k & 1u);
+      // (3) off the critical path: the prefetch of step t-1's gates / cell states
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        if (!valid[n]) continue;
+        if (t == 0 && dc_init) *reinterpret_cast<float4*>(dc_init + (size_t)bq[n] * H + ucol[n]) = dcr[n];
+        if (t > 0) {
+          cn[n] = cp[n];
+          if (t - 1 >= first_t[n]) {
+            const size_t rp = row[n] - B;
+            const float* g = gates + rp * 4 * H + ucol[n];
+            gi[n] = *reinterpret_cast<const float4*>(g);
+            gf[n] = *reinterpret_cast<const float4*>(g + H);
+            go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+            gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+            cp[n] = *reinterpret_cast<const float4*>(c + rp * H + ucol[n]);
+          }
+        }
+      }
+      if (t < tlast) break;
+      // ---- phase B epilogue: split-K partial of dh_{t-1}, transposed through shared memory (the ring is idle) ----
+      mbar_wait(tfull, k & 1u);
+      tc_fence_after();
+      {
+        float acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), acc);
+        float* dst = tbuf + (size_t)(ch * 32) * V2_BPITCH + q * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[(size_t)j * V2_BPITCH] = acc[j];
+      }
+      tc_fence_before();
+      v2_bar_sync(2, V2_EPI);
+      {
+        const int n = et >> 2, ug = et & 3;                  // batch row of the tile, interleaved 16-byte chunks ug + 4 i
+        const int brow = m0 + n;
+        if (brow < B) {
+          const float* src = tbuf + (size_t)n * V2_BPITCH;
+          float* dst = dh_part + (size_t)brow * H + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int cidx = (ug + 4 * i) * 4;
+            *reinterpret_cast<float4*>(dst + cidx) = *reinterpret_cast<const float4*>(src + cidx);
+          }
+        }
+      }
+      fence_proxy_async();                                   // the tile is overwritten by the next step's TMA loads
+      v2_bar_sync(1, V2_EPI);
+      if (et == 0) v2_arrive(counter);                       // barrier 2k+2
+    }
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      if (!valid[n]) continue;
+      float* dr = dasum + (size_t)bq[n] * 4 * H + ucol[n];
+      *reinterpret_cast<float4*>(dr) = bsi[n];
+      *reinterpret_cast<float4*>(dr + H) = bsf[n];
+      *reinterpret_cast<float4*>(dr + 2 * H) = bso[n];
+      *reinterpret_cast<float4*>(dr + 3 * H) = bsg[n];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void __launch_bounds__(256) v2_sum4_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4* p = reinterpret_cast<const float4*>(part);
+  float4 a = p[i], b = p[i + n4], c = p[i + 2 * n4], d = p[i + 3 * n4];
+  reinterpret_cast<float4*>(out)[i] = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z),
+                                                  (a.w + b.w) + (c.w + d.w));
+}
+
 static bool v2_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("NVQA_LSTM_V2"); on = e ? atoi(e) : 1; }
@@ -342,6 +665,65 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   cfg.attrs = &attr; cfg.numAttrs = 1;
   NVQA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ++g_launches;
+  return 0;
+}
+
+}  // namespace nvqa
+
+namespace nvqa {
+
+// Same contract as lstm_bwd_persistent (lstm_persistent.cuh); -1 when the shape is not covered by this generation.
+int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
+                           const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* dasum,
+                           __nv_bfloat16* dap, long long dap_plane_rows, float* dhbuf, float* dh_init, float* dc_init,
+                           const int32_t* len, int T, int B, int H, unsigned int* counter) {
+  if (!v2_enabled()) return -1;
+  if ((dh_init == nullptr) != (dc_init == nullptr)) return -1;
+  if (P < 1 || P > 2) return -1;
+  if (H != 512) return -1;
+  static int num_sms = 0, max_smem = 0;
+  if (!num_sms) {
+    int dev = 0;
+    NVQA_CUDA(cudaGetDevice(&dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  const int KB = H / 64;
+  dim3 grid(H / 128, 4, ceil_div(B, 64));
+  if ((int)(grid.x * grid.y * grid.z) > num_sms) return -1;
+  const size_t tile = (size_t)64 * V2_BPITCH * 4;
+  size_t ring = (size_t)V2_STAGES * P * 8192;
+  if (ring < tile) ring = tile + 1024 - tile % 1024;
+  const size_t smem = (size_t)KB * 16384 + ring + 1024 + 256;
+  if (smem > (size_t)max_smem) return -1;
+
+  __nv_bfloat16* wp = nullptr;
+  int pitch = 0;
+  NVQA_TRY(prepare_planes(ws, s, P, Wh, 4 * H, H, H, true, &wp, &pitch));
+  CUtensorMap mapW, mapDA;
+  NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 64, &mapW));              // MN-major A: boxes of 64 k-rows x 64 columns
+  if (dap_plane_rows <= 0) dap_plane_rows = (long long)T * B;
+  NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 64, &mapDA, dap_plane_rows * 4 * H));
+  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+  long long dap_plane = dap_plane_rows * 4 * H;
+  const __nv_bfloat16* w1 = wp + (size_t)4 * H * pitch;
+  int KBv = KB;
+  void* args[] = {&mapDA, &mapW, &w1, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dhbuf,
+                  &dc_init, &len, &T, &B, &H, &KBv, &counter};
+  const void* fn = P == 2 ? (const void*)lstm_bwd_v2_kernel<2> : (const void*)lstm_bwd_v2_kernel<1>;
+  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeCooperative; attr.val.cooperative = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  NVQA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+  ++g_launches;
+  if (dh_init) {
+    const long long n4 = (long long)B * H / 4;
+    v2_sum4_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(dhbuf, dh_init, n4);
+    NVQA_LAUNCHED();
+  }
   return 0;
 }
 

@@ -816,9 +816,13 @@ static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t*
     if (m->planes && m->use_persistent) {
       // K9: the whole backward recurrence of this layer in one persistent cooperative kernel
       ProfScope ps(m, CAT_REC_BWD, 2.0 * (T - (want_init ? 0 : 1)) * B * 4.0 * H * H);
-      rc = lstm_bwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, gates, cb, dh_in, dc_in, ld, dh_above, dabove, da,
-                               m->dap + r0 * 4 * H, (long long)m->TS * c.B, m->dhbuf, want_init ? m->dh_init : nullptr,
-                               want_init ? m->dc_init : nullptr, len, T, B, H, m->grid_counter);
+      rc = lstm_bwd_persistent_v2(s, m->ws, m->planes, sg.w[l].Wh, gates, cb, dh_in, dc_in, ld, dh_above, dabove, da,
+                                  m->dap + r0 * 4 * H, (long long)m->TS * c.B, m->dhbuf, want_init ? m->dh_init : nullptr,
+                                  want_init ? m->dc_init : nullptr, len, T, B, H, m->grid_counter);
+      if (rc < 0)
+        rc = lstm_bwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, gates, cb, dh_in, dc_in, ld, dh_above, dabove, da,
+                                 m->dap + r0 * 4 * H, (long long)m->TS * c.B, m->dhbuf, want_init ? m->dh_init : nullptr,
+                                 want_init ? m->dc_init : nullptr, len, T, B, H, m->grid_counter);
       if (rc > 0) return rc;
     }
     m->dap_valid = rc == 0;
