@@ -607,6 +607,358 @@ lstm_bwd_v2_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, generation 3: generation 2 plus a 4-CTA thread-block CLUSTER over the K-splits.  The four CTAs that hold
+// the four gate blocks of one (column tile, batch tile) keep their split-K partials of dh_{t-1} in SHARED memory and
+// reduce them through distributed shared memory (fixed rank order -> deterministic): the partials never go to global
+// memory, the second grid barrier of every step disappears, and the cell backward (phase A) of the summed tile is
+// done by those same four CTAs (16 of the 64 batch rows each), so dh stays in registers between the reduction and
+// the element-wise math.  One global exchange per step remains: da_t as bf16 planes (TMA operand of phase B, and the
+// wgrad / dgrad operand afterwards), guarded by one counter per batch-tile group (16 CTAs).
+//   step t:  [t < T-1]  tfull -> tcgen05.ld -> tbuf (own partial, transposed) -> mbarrier arrive on all 4 CTAs
+//                        -> wait -> 4 x ld.shared::cluster -> dh_t
+//            phase A (dh_t, dc carry, gates_t, c_t, c_{t-1}) -> da_t planes -> release-add on the group counter
+//            producer: acquire-poll the counter -> TMA da_t tile -> tcgen05.mma (W_hh^T slice: SMEM plane 0 + TMEM plane 1)
+__device__ __forceinline__ uint32_t v3_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 v3_ld_dsmem4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void v3_arrive_remote(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void v3_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) { printf("lstm_bwd_v3: cluster barrier timed out\n"); __trap(); }
+  }
+}
+#define V3_STAMP(slot) do { if (dbg && cta == 0 && blockIdx.z == 0 && t >= 8 && t < 12) stamps[(t - 8) * 8 + (slot)] = clock64(); } while (0)
+
+template <int P>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
+                   const __nv_bfloat16* __restrict__ w1, int w_pitch, const float* __restrict__ gates,
+                   const float* __restrict__ c, const float* __restrict__ dh0, const float* __restrict__ dc0, int ld0,
+                   const float* __restrict__ dh_above, Drop drop, float* __restrict__ dasum,
+                   __nv_bfloat16* __restrict__ dap, long long dap_plane, float* __restrict__ dh_init,
+                   float* __restrict__ dc_init, const int32_t* __restrict__ len, int T, int B, int H, int KB,
+                   unsigned int* counter, int dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ long long stamps[32];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t W_KB = 128 * 128;
+  constexpr uint32_t B_PLANE = 64 * 128;
+  constexpr uint32_t STAGE = P * B_PLANE;
+  constexpr uint32_t TILE = 64 * V2_BPITCH * 4;                                  // 36,864 B
+  constexpr uint32_t RING = V2_STAGES * STAGE < TILE ? TILE + 1024 - TILE % 1024 : V2_STAGES * STAGE;
+  const uint32_t w0 = base;
+  const uint32_t r0 = w0 + (uint32_t)KB * W_KB;
+  const uint32_t bar0 = r0 + RING;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * V2_STAGES, wfull = bar0 + 16 * V2_STAGES, tfull = wfull + 8,
+                 gobar = wfull + 16, w1bar = wfull + 24, pfull = wfull + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * V2_STAGES + 48);
+  float* tbuf = reinterpret_cast<float*>(smem_raw + (r0 - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 128, ks = blockIdx.y, m0 = blockIdx.z * 64;
+  const unsigned int G = gridDim.x * gridDim.y;                          // CTAs of one batch-tile group
+  const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  counter += 32 * blockIdx.z;                                            // one 128-byte line per group
+  const int k_base = ks * H;
+  const int tlast = dc_init ? 0 : 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapDA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < V2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      mbar_init(wfull, 1);
+      mbar_init(tfull, 1);
+      mbar_init(gobar, 1);
+      mbar_init(w1bar, 1);
+      mbar_init(pfull, 4);                          // one arrival per CTA of the cluster and reduction round
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // the peers' mbarriers exist before anybody signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t W1_COL = 256;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(wfull, (uint32_t)KB * W_KB);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int cc = 0; cc < 2; ++cc)
+          tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)cc * 8192, &mapW, wfull, c0 + 64 * cc, k_base + kb * 64, 0);
+      int it = 0;
+      const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
+      for (int t = T - 1; t >= tlast; --t) {
+        const unsigned int k = (unsigned int)(T - 1 - t);
+        v2_wait(counter, (k + 1) * G);                      // da_t of this batch tile is complete
+        fence_proxy_async();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          mbar_expect_tx(full0 + 8 * s, STAGE);
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            tma_load_3d(r0 + (uint32_t)s * STAGE + (uint32_t)p * B_PLANE, &mapDA, full0 + 8 * s, k_base + kb * 64, t * B + m0, p);
+          if (kb == gokb) mbar_arrive(gobar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, false);       // A = W_hh^T slice in SMEM, MN-major
+      constexpr uint32_t idesc_ts = make_idesc_bf16(128, 64, false, false);   // A from TMEM is K-major by construction
+      mbar_wait(wfull, 0);
+      if (P >= 2) mbar_wait(w1bar, 0);
+      tc_fence_after();
+      int it = 0;
+      for (int t = T - 1; t >= tlast; --t) {
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dw = make_mnmajor_sw128_desc(w0 + (uint32_t)kb * W_KB + k * 2048);
+            const uint64_t d0 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + k * 32);
+            if (P >= 2) {
+              const uint64_t d1 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + B_PLANE + k * 32);
+              umma_f16_ts(tmem_base, tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8), d0, idesc_ts, acc); acc = 1;
+              umma_f16(tmem_base, dw, d1, idesc, acc);
+            }
+            umma_f16(tmem_base, dw, d0, idesc, acc); acc = 1;
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else {
+    // ===== 8 element-wise / epilogue warps =====
+    const int et = threadIdx.x - 64;                         // 0..255
+    const int q = warp & 3, ch = (warp - 2) >> 2;
+    if (P >= 2) {
+      const __nv_bfloat16* src = w1 + (size_t)(k_base + 256 * ch) * w_pitch + c0 + q * 32 + lane;
+#pragma unroll 1
+      for (int blk = 0; blk < 4; ++blk) {
+        uint32_t wv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t lo = __bfloat16_as_ushort(src[(size_t)(blk * 64 + 2 * j) * w_pitch]);
+          const uint32_t hi = __bfloat16_as_ushort(src[(size_t)(blk * 64 + 2 * j + 1) * w_pitch]);
+          wv[j] = lo | (hi << 16);
+        }
+        tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + W1_COL + (uint32_t)(128 * ch + 32 * blk), wv);
+      }
+      tc_fence_before();
+    }
+    v2_bar_sync(1, V2_EPI);
+    if (P >= 2 && et == 0) mbar_arrive(w1bar);
+    // This CTA's share of the cluster's [64 rows x 128 columns] tile: rows 16 ks .. 16 ks + 15, all 128 columns;
+    // thread item n: row 16 ks + (et + 256 n) / 32, columns c0 + 4 ((et + 256 n) % 32) .. + 3.  Fixed for all steps:
+    // dc carry, bias sums and the prefetched operands live in registers.
+    constexpr int NI = 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool valid[NI];
+    int bq[NI], ucol[NI], first_t[NI];
+    uint32_t toff[NI];                                       // byte offset of the item inside a CTA's partial tile
+    float4 gi[NI], gf[NI], go[NI], gg[NI], cp[NI], cn[NI], dcr[NI], dab[NI];
+    float4 bsi[NI], bsf[NI], bso[NI], bsg[NI];
+    uint32_t peer_tbuf[4], peer_pfull[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { peer_tbuf[r] = v3_mapa(r0, (uint32_t)r); peer_pfull[r] = v3_mapa(pfull, (uint32_t)r); }
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      bsi[n] = bsf[n] = bso[n] = bsg[n] = dab[n] = z;
+      const int li = et + 256 * n, rl = 16 * ks + (li >> 5), cl = (li & 31) * 4;
+      toff[n] = (uint32_t)(rl * V2_BPITCH + cl) * 4u;
+      bq[n] = m0 + rl;
+      valid[n] = bq[n] < B;
+      if (!valid[n]) bq[n] = 0;
+      ucol[n] = c0 + cl;
+      first_t[n] = valid[n] ? (len ? T - len[bq[n]] : 0) : T;
+      gi[n] = gf[n] = go[n] = gg[n] = cp[n] = cn[n] = dcr[n] = z;
+      if (T - 1 >= first_t[n]) {
+        const size_t row = (size_t)(T - 1) * B + bq[n];
+        const float* g = gates + row * 4 * H + ucol[n];
+        gi[n] = *reinterpret_cast<const float4*>(g);
+        gf[n] = *reinterpret_cast<const float4*>(g + H);
+        go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+        gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+        cp[n] = *reinterpret_cast<const float4*>(c + row * H + ucol[n]);
+        cn[n] = *reinterpret_cast<const float4*>(c + (row + B) * H + ucol[n]);
+        dcr[n] = *reinterpret_cast<const float4*>(dc0 + (size_t)bq[n] * ld0 + ucol[n]);
+        if (dh_above) {
+          const float4 ua = *reinterpret_cast<const float4*>(dh_above + row * H + ucol[n]);
+          const float4 mk = drop_at4(drop, (uint64_t)row * H + ucol[n]);
+          dab[n] = make_float4(ua.x * mk.x, ua.y * mk.y, ua.z * mk.z, ua.w * mk.w);
+        }
+      }
+    }
+    unsigned int red = 0;                                    // reduction rounds done so far (parity of pfull / tfull)
+    // the sum of the cluster's four split-K partials of the tile, for this thread's items (fixed rank order)
+    auto reduce_partials = [&](float4* out) {
+      mbar_wait(tfull, red & 1u);
+      tc_fence_after();
+      {
+        float acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), acc);
+        float* dst = tbuf + (size_t)(ch * 32) * V2_BPITCH + q * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[(size_t)j * V2_BPITCH] = acc[j];
+      }
+      tc_fence_before();
+      v2_bar_sync(2, V2_EPI);                                // the whole partial tile of this CTA is in shared memory
+      if (et < 4) v3_arrive_remote(peer_pfull[et]);          // release.cluster, cumulative over the CTA through the barrier
+      v3_wait_cluster(pfull, red & 1u);                      // all four partial tiles are complete
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        const float4 a = v3_ld_dsmem4(peer_tbuf[0] + toff[n]), b = v3_ld_dsmem4(peer_tbuf[1] + toff[n]),
+                     cc4 = v3_ld_dsmem4(peer_tbuf[2] + toff[n]), d = v3_ld_dsmem4(peer_tbuf[3] + toff[n]);
+        out[n] = make_float4((a.x + b.x) + (cc4.x + d.x), (a.y + b.y) + (cc4.y + d.y), (a.z + b.z) + (cc4.z + d.z),
+                             (a.w + b.w) + (cc4.w + d.w));
+      }
+      ++red;
+    };
+    for (int t = T - 1; t >= 0; --t) {
+      const unsigned int k = (unsigned int)(T - 1 - t);
+      if (et == 0) V3_STAMP(0);
+      float4 dhs[NI];
+      if (t < T - 1) reduce_partials(dhs);                   // dh_t from the MMAs of step t+1
+      if (et == 0) V3_STAMP(1);
+      // ---- phase A: cell backward, element-wise ----
+      float4 dai[NI], daf[NI], dao[NI], dag[NI];
+      size_t row[NI];
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        row[n] = (size_t)t * B + bq[n];
+        dai[n] = daf[n] = dao[n] = dag[n] = z;
+        if (!valid[n]) continue;
+        if (t >= first_t[n]) {
+          float4 dh = t == T - 1 ? *reinterpret_cast<const float4*>(dh0 + (size_t)bq[n] * ld0 + ucol[n]) : dhs[n];
+          dh.x += dab[n].x; dh.y += dab[n].y; dh.z += dab[n].z; dh.w += dab[n].w;
+#define LB(kk)                                                                     \
+          { float tc = v2_tanh(cn[n].kk);                                            \
+            float dct = dcr[n].kk + dh.kk * go[n].kk * (1.0f - tc * tc);             \
+            dao[n].kk = dh.kk * tc * go[n].kk * (1.0f - go[n].kk);                   \
+            dai[n].kk = dct * gg[n].kk * gi[n].kk * (1.0f - gi[n].kk);               \
+            daf[n].kk = dct * cp[n].kk * gf[n].kk * (1.0f - gf[n].kk);               \
+            dag[n].kk = dct * gi[n].kk * (1.0f - gg[n].kk * gg[n].kk);               \
+            dcr[n].kk = dct * gf[n].kk; }
+          LB(x) LB(y) LB(z) LB(w)
+#undef LB
+#define ACC4(a, b) a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          ACC4(bsi[n], dai[n]) ACC4(bsf[n], daf[n]) ACC4(bso[n], dao[n]) ACC4(bsg[n], dag[n])
+#undef ACC4
+        }
+        const float4 gsrc[4] = {dai[n], daf[n], dao[n], dag[n]};
+#pragma unroll
+        for (int gI = 0; gI < 4; ++gI) {
+          __nv_bfloat16 pl[3][4];
+          split3(gsrc[gI].x, pl[0][0], pl[1][0], pl[2][0]);
+          split3(gsrc[gI].y, pl[0][1], pl[1][1], pl[2][1]);
+          split3(gsrc[gI].z, pl[0][2], pl[1][2], pl[2][2]);
+          split3(gsrc[gI].w, pl[0][3], pl[1][3], pl[2][3]);
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            uint2 ov;
+            ov.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+            ov.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+            *reinterpret_cast<uint2*>(dap + (size_t)p * dap_plane + row[n] * 4 * H + (size_t)gI * H + ucol[n]) = ov;
+          }
+        }
+      }
+      // publish da_t: the one global exchange of the step
+      if (et == 0) V3_STAMP(2);
+      fence_proxy_async();
+      v2_bar_sync(1, V2_EPI);
+      if (et == 0) { V3_STAMP(3); v2_arrive(counter); V3_STAMP(4); }
+      v2_bar_sync(3, V2_EPI);
+      if (t >= tlast) mbar_wait(gobar, k & 1u);
+      // off the critical path: the operands of step t-1
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        if (!valid[n]) continue;
+        if (t == 0 && dc_init) *reinterpret_cast<float4*>(dc_init + (size_t)bq[n] * H + ucol[n]) = dcr[n];
+        if (t > 0) {
+          cn[n] = cp[n];
+          if (t - 1 >= first_t[n]) {
+            const size_t rp = row[n] - B;
+            const float* g = gates + rp * 4 * H + ucol[n];
+            gi[n] = *reinterpret_cast<const float4*>(g);
+            gf[n] = *reinterpret_cast<const float4*>(g + H);
+            go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+            gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+            cp[n] = *reinterpret_cast<const float4*>(c + rp * H + ucol[n]);
+            if (dh_above) {
+              const float4 ua = *reinterpret_cast<const float4*>(dh_above + rp * H + ucol[n]);
+              const float4 mk = drop_at4(drop, (uint64_t)rp * H + ucol[n]);
+              dab[n] = make_float4(ua.x * mk.x, ua.y * mk.y, ua.z * mk.z, ua.w * mk.w);
+            }
+          }
+        }
+      }
+    }
+    if (dh_init) {                                           // d h_{-1}: the reduction of the MMAs of step 0
+      float4 dhs[NI];
+      reduce_partials(dhs);
+#pragma unroll
+      for (int n = 0; n < NI; ++n)
+        if (valid[n]) *reinterpret_cast<float4*>(dh_init + (size_t)bq[n] * H + ucol[n]) = dhs[n];
+    }
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      if (!valid[n]) continue;
+      float* dr = dasum + (size_t)bq[n] * 4 * H + ucol[n];
+      *reinterpret_cast<float4*>(dr) = bsi[n];
+      *reinterpret_cast<float4*>(dr + H) = bsf[n];
+      *reinterpret_cast<float4*>(dr + 2 * H) = bso[n];
+      *reinterpret_cast<float4*>(dr + 3 * H) = bsg[n];
+    }
+    if (dbg && cta == 0 && blockIdx.z == 0 && et == 0) {
+      printf("lstm_bwd_v3 timeline (cycles from step start): t | reduced phaseA_done A_alldone A_arrived | step\n");
+      for (int i = 3; i >= 1; --i) {
+        const long long* e = stamps + i * 8;
+        printf("%2d | %6lld %6lld %6lld %6lld | %6lld\n", 8 + i, e[1] - e[0], e[2] - e[0], e[3] - e[0], e[4] - e[0],
+               stamps[(i - 1) * 8] - e[0]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // nobody leaves while a peer may still read its partial tile
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 __global__ void __launch_bounds__(256) v2_sum4_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -657,7 +1009,7 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   int KBv = KB;
   void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter};
   const void* fn = P == 2 ? (const void*)lstm_fwd_v2_kernel<2> : (const void*)lstm_fwd_v2_kernel<1>;
-  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr;
@@ -710,8 +1062,32 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   int KBv = KB;
   void* args[] = {&mapDA, &mapW, &w1, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dhbuf,
                   &dc_init, &len, &T, &B, &H, &KBv, &counter};
+  static int use_v3 = -1;
+  if (use_v3 < 0) { const char* e = getenv("NVQA_LSTM_V3"); use_v3 = e ? atoi(e) : 1; }
+  if (use_v3) {
+    // generation 3: 4-CTA clusters over the K-splits, split-K reduction through distributed shared memory
+    NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.z, s));
+    static const int dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
+    int dbgv = dbg;
+    void* a3[] = {&mapDA, &mapW, &w1, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dh_init,
+                  &dc_init, &len, &T, &B, &H, &KBv, &counter, &dbgv};
+    const void* f3 = P == 2 ? (const void*)lstm_bwd_v3_kernel<2> : (const void*)lstm_bwd_v3_kernel<1>;
+    NVQA_CUDA(cudaFuncSetAttribute(f3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg3 = {};
+    cfg3.gridDim = grid; cfg3.blockDim = dim3(V2_THREADS); cfg3.dynamicSmemBytes = smem; cfg3.stream = s;
+    cudaLaunchAttribute at3[2];
+    at3[0].id = cudaLaunchAttributeCooperative; at3[0].val.cooperative = 1;
+    at3[1].id = cudaLaunchAttributeClusterDimension;
+    at3[1].val.clusterDim.x = 1; at3[1].val.clusterDim.y = 4; at3[1].val.clusterDim.z = 1;
+    cfg3.attrs = at3; cfg3.numAttrs = 2;
+    cudaError_t le = cudaLaunchKernelExC(&cfg3, f3, a3);
+    if (le == cudaSuccess) { ++g_launches; return 0; }
+    (void)cudaGetLastError();                     // the clusters could not be made co-resident: generation 2 below
+    use_v3 = 0;
+    NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+  }
   const void* fn = P == 2 ? (const void*)lstm_bwd_v2_kernel<2> : (const void*)lstm_bwd_v2_kernel<1>;
-  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr;
