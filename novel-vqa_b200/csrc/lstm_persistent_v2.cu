@@ -55,7 +55,13 @@ __device__ __forceinline__ void v2_wait(unsigned int* ctr, unsigned int target) 
 __device__ __forceinline__ float v2_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float v2_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
-template <int P>
+// CL = true: the 16 CTAs of a batch tile are ONE thread-block cluster (non-portable size 16, one GPC) and the per-step
+// synchronisation is the hardware cluster barrier (arrive.release / wait.acquire by every thread) instead of a
+// release-add / acquire-poll on a global counter; no inter-cluster dependency exists, so no cooperative launch either.
+__device__ __forceinline__ void v2_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void v2_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int P, bool CL>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
@@ -108,16 +114,20 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       for (int kb = 0; kb < KB; ++kb)
         for (int g = 0; g < 4; ++g)
           tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)g * 4096, &mapW, wfull, kb * 64, g * H + u0, 0);
-      int it = 0;
-      const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
-      for (int t = 0; t < T; ++t) {
+    }
+    int it = 0;
+    const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
+    for (int t = 0; t < T; ++t) {
+      if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }    // phase t: h_{t-1} published by all 16 CTAs
+      if (lane == 0) {
         if (t > 0) {
-          v2_wait(counter + 32 * blockIdx.y, (unsigned int)t * gridDim.x);     // h_{t-1} of this batch tile is complete
+          if (!CL) v2_wait(counter + 32 * blockIdx.y, (unsigned int)t * gridDim.x);     // h_{t-1} of this batch tile is complete
           fence_proxy_async();
         }
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % V2_STAGES;
-          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+        for (int kb = 0; kb < KB; ++kb) {
+          const int itk = it + kb;
+          const int s = itk % V2_STAGES;
+          const uint32_t ph = (uint32_t)(itk / V2_STAGES) & 1u;
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           mbar_expect_tx(full0 + 8 * s, STAGE);
 #pragma unroll
@@ -126,16 +136,20 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           if (kb == gokb) mbar_arrive(gobar);      // this step's first loads are out: the epilogue may use the memory pipe
         }
       }
+      it += KB;
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
       mbar_wait(wfull, 0);
       if (P >= 2) mbar_wait(w1bar, 0);             // plane 1 of the W slice has been stored to TMEM by the epilogue warps
       tc_fence_after();
-      int it = 0;
-      for (int t = 0; t < T; ++t) {
+    }
+    int it = 0;
+    for (int t = 0; t < T; ++t) {
+      if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }
+      if (lane == 0) {
         uint32_t acc = 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % V2_STAGES;
@@ -156,6 +170,8 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           umma_commit(empty0 + 8 * s);
         }
         umma_commit(tfull);
+      } else {
+        it += KB;
       }
     }
   } else {
@@ -264,9 +280,13 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       // overwrite) are ordered before later async-proxy accesses; one thread's gpu-scope release is made cumulative
       // over the CTA by the barrier
       fence_proxy_async();
-      v2_bar_sync(1, V2_EPI);
-      if (threadIdx.x == 64) v2_arrive(counter + 32 * blockIdx.y);
-      v2_bar_sync(3, V2_EPI);                      // keep the SM's memory pipeline clear until the release is out ...
+      if (CL) {
+        if (t + 1 < T) { __syncwarp(); v2_cluster_arrive(); }     // every thread releases its own stores to the cluster
+      } else {
+        v2_bar_sync(1, V2_EPI);
+        if (threadIdx.x == 64) v2_arrive(counter + 32 * blockIdx.y);
+        v2_bar_sync(3, V2_EPI);                    // keep the SM's memory pipeline clear until the release is out ...
+      }
       if (t + 1 < T) mbar_wait(gobar, (uint32_t)(t + 1) & 1u);   // ... and until the next step's first loads are issued
       // (3) everything only the backward pass needs, off the critical path
       if (rowok) {
@@ -286,6 +306,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         }
 #undef ST8
       }
+      if (CL && t + 1 < T) { __syncwarp(); v2_cluster_wait(); }   // pairs with the arrive above (complete long ago)
     }
   }
   tc_fence_before();
@@ -826,9 +847,10 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     }
     unsigned int red = 0;                                    // reduction rounds done so far (parity of pfull / tfull)
     // the sum of the cluster's four split-K partials of the tile, for this thread's items (fixed rank order)
-    auto reduce_partials = [&](float4* out) {
+    auto reduce_partials = [&](float4* out, int t) {
       mbar_wait(tfull, red & 1u);
       tc_fence_after();
+      if (et == 0) V3_STAMP(5);
       {
         float acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), acc);
@@ -840,6 +862,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       v2_bar_sync(2, V2_EPI);                                // the whole partial tile of this CTA is in shared memory
       if (et < 4) v3_arrive_remote(peer_pfull[et]);          // release.cluster, cumulative over the CTA through the barrier
       v3_wait_cluster(pfull, red & 1u);                      // all four partial tiles are complete
+      if (et == 0) V3_STAMP(6);
 #pragma unroll
       for (int n = 0; n < NI; ++n) {
         const float4 a = v3_ld_dsmem4(peer_tbuf[0] + toff[n]), b = v3_ld_dsmem4(peer_tbuf[1] + toff[n]),
@@ -853,7 +876,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       const unsigned int k = (unsigned int)(T - 1 - t);
       if (et == 0) V3_STAMP(0);
       float4 dhs[NI];
-      if (t < T - 1) reduce_partials(dhs);                   // dh_t from the MMAs of step t+1
+      if (t < T - 1) reduce_partials(dhs, t);                   // dh_t from the MMAs of step t+1
       if (et == 0) V3_STAMP(1);
       // ---- phase A: cell backward, element-wise ----
       float4 dai[NI], daf[NI], dao[NI], dag[NI];
@@ -930,7 +953,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     }
     if (dh_init) {                                           // d h_{-1}: the reduction of the MMAs of step 0
       float4 dhs[NI];
-      reduce_partials(dhs);
+      reduce_partials(dhs, -1);
 #pragma unroll
       for (int n = 0; n < NI; ++n)
         if (valid[n]) *reinterpret_cast<float4*>(dh_init + (size_t)bq[n] * H + ucol[n]) = dhs[n];
@@ -945,11 +968,11 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       *reinterpret_cast<float4*>(dr + 3 * H) = bsg[n];
     }
     if (dbg && cta == 0 && blockIdx.z == 0 && et == 0) {
-      printf("lstm_bwd_v3 timeline (cycles from step start): t | reduced phaseA_done A_alldone A_arrived | step\n");
+      printf("lstm_bwd_v3 timeline (cycles from step start): t | mma_done cluster_synced reduced phaseA_done A_alldone A_arrived | step\n");
       for (int i = 3; i >= 1; --i) {
         const long long* e = stamps + i * 8;
-        printf("%2d | %6lld %6lld %6lld %6lld | %6lld\n", 8 + i, e[1] - e[0], e[2] - e[0], e[3] - e[0], e[4] - e[0],
-               stamps[(i - 1) * 8] - e[0]);
+        printf("%2d | %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", 8 + i, e[5] - e[0], e[6] - e[0], e[1] - e[0], e[2] - e[0],
+               e[3] - e[0], e[4] - e[0], stamps[(i - 1) * 8] - e[0]);
       }
     }
   }
@@ -1008,7 +1031,25 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   const __nv_bfloat16* w1 = wp + (size_t)4 * H * pitch;            // plane 1
   int KBv = KB;
   void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter};
-  const void* fn = P == 2 ? (const void*)lstm_fwd_v2_kernel<2> : (const void*)lstm_fwd_v2_kernel<1>;
+  static int use_cl = -1;
+  if (use_cl < 0) { const char* e = getenv("NVQA_LSTM_CLUSTER16"); use_cl = e ? atoi(e) : 0; }   // measured on B200: only part of the 8 clusters of 16 is co-resident (0.82 ms vs 0.48 ms)
+  if (use_cl && grid.x == 16) {
+    // one 16-CTA cluster per batch tile: hardware cluster barrier per step, plain (non-cooperative) launch
+    const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true> : (const void*)lstm_fwd_v2_kernel<1, true>;
+    NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cc = {};
+    cc.gridDim = grid; cc.blockDim = dim3(V2_THREADS); cc.dynamicSmemBytes = smem; cc.stream = s;
+    cudaLaunchAttribute ca;
+    ca.id = cudaLaunchAttributeClusterDimension;
+    ca.val.clusterDim.x = 16; ca.val.clusterDim.y = 1; ca.val.clusterDim.z = 1;
+    cc.attrs = &ca; cc.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelExC(&cc, fc, args);
+    if (le == cudaSuccess) { ++g_launches; return 0; }
+    (void)cudaGetLastError();
+    use_cl = 0;                                   // 16-CTA clusters are not schedulable here: counter barrier below
+  }
+  const void* fn = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, false> : (const void*)lstm_fwd_v2_kernel<1, false>;
   NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
