@@ -112,11 +112,13 @@ int simt_gemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K,
 
 // ---- tcgen05 GEMM engine (umma_gemm.cu) -------------------------------------------------------
 struct UmmaWorkspace;   // bf16 operand planes + tensor maps
-// a_static / b_static: the operand is a weight whose bf16 planes may be cached until umma_workspace_invalidate()
+// a_static / b_static: cache class of the operand's bf16 planes -- 0 none, 1 weight (until umma_workspace_invalidate()),
+// 2 activation written once per forward (until umma_workspace_new_forward())
 int umma_gemm(cudaStream_t s, int planes, bool a_kmajor, bool b_kmajor, int M, int N, int K, const float* A,
               int lda, const float* B, int ldb, float* C, int ldc, bool beta, const float* bias0,
-              const float* bias1, UmmaWorkspace* ws, bool a_static, bool b_static);
-int umma_workspace_create(UmmaWorkspace** ws, size_t transient_bytes, size_t static_bytes);
+              const float* bias1, UmmaWorkspace* ws, int a_static, int b_static);
+int umma_workspace_create(UmmaWorkspace** ws, size_t transient_bytes, size_t static_bytes, size_t act_bytes = 0);
+void umma_workspace_new_forward(UmmaWorkspace* ws);
 void umma_workspace_destroy(UmmaWorkspace* ws);
 void umma_workspace_invalidate(UmmaWorkspace* ws);
 

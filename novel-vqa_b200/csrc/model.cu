@@ -52,6 +52,14 @@ static Drop make_drop(const nvqa_model* m, const float* mask, uint32_t stream) {
 
 static int gemm_raw(nvqa_model* m, bool ak, bool bk, int M, int N, int K, const float* A, int lda, const float* B,
                     int ldb, float* C, int ldc, bool beta, const float* b0, const float* b1);
+// cache class of a GEMM operand's bf16 planes: 1 = weight (inside the flat parameter vector: cached for the whole step),
+// 2 = forward activation that is written once per forward and read again by the backward GEMMs, 0 = transient
+static int cache_class(const nvqa_model* m, const float* p) {
+  if (p >= m->params && p < m->params + m->P) return 1;
+  for (const auto& r : m->act_ranges)
+    if (p >= r.first && p < r.second) return 2;
+  return 0;
+}
 
 // event bracket around any stretch of work on the model's stream (no-ops unless profiling)
 struct ProfScope {
@@ -87,8 +95,7 @@ static int gemm(nvqa_model* m, int cat, bool ak, bool bk, int M, int N, int K, c
 
 static int gemm_raw(nvqa_model* m, bool ak, bool bk, int M, int N, int K, const float* A, int lda, const float* B,
                     int ldb, float* C, int ldc, bool beta, const float* b0, const float* b1) {
-  // weights (anything inside the flat parameter vector) keep their bf16 planes cached for the whole step
-  const bool as = A >= m->params && A < m->params + m->P, bs = B >= m->params && B < m->params + m->P;
+  const int as = cache_class(m, A), bs = cache_class(m, B);
   switch (m->cfg.precision) {
     case NVQA_PREC_FP32_SIMT:
       return simt_gemm(m->stream, ak, bk, M, N, K, A, lda, B, ldb, C, ldc, beta, b0, b1);
@@ -112,7 +119,7 @@ static int gemm_ops(nvqa_model* m, int cat, const UmmaOperand& A, const UmmaOper
 static UmmaOperand op_f32(const nvqa_model* m, const float* src, int ld, bool kmajor) {
   UmmaOperand o;
   o.src = src; o.ld = ld; o.kmajor = kmajor;
-  o.is_static = src >= m->params && src < m->params + m->P;
+  o.is_static = cache_class(m, src);
   return o;
 }
 static UmmaOperand op_planes(const __nv_bfloat16* planes, int plane_rows, int pitch, int row_offset, bool kmajor) {
@@ -351,7 +358,14 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
     size_t elems = (size_t)(N + 64) * 4 * H + (size_t)(N + 64) * (H > E ? H : E) + (size_t)(B + 64) * (I + S + 2 * C2);
     if (a3) elems = std::max(elems, (size_t)((T + 1) * (size_t)B + 64) * (m->ldl + 8 + H + 8));   // d logits + hd planes
     size_t stat = (size_t)(n_enc + m->n_blk[2] + (a2 ? m->n_blk[0] : 0) + (a3 ? m->n_blk[1] : 0)) * 2 * 6 + (16 << 20);
-    NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (96 << 20), stat));
+    // per-forward activation planes (inputs of the forward GEMMs that the wgrad GEMMs read again)
+    size_t act = 0;
+    auto reg = [&](const float* p, size_t n) { if (p) { m->act_ranges.emplace_back(p, p + n); act += n * 2 * m->planes + 4096; } };
+    reg(m->y, (size_t)N * E);
+    for (int l = 1; l < L; ++l) reg(m->xdrop[l], (size_t)N * H);
+    reg(m->qd, (size_t)B * S); reg(m->vd, (size_t)B * I); reg(m->zd, (size_t)B * C2);
+    if (a3) reg(m->hd, (size_t)(T + 1) * B * H);
+    NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (96 << 20), stat, act + (act >> 3) + (1 << 20)));
   }
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
   return 0;
@@ -648,6 +662,7 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   NVQA_CHECK(mode == NVQA_MODE_EVAL || mode == NVQA_MODE_TRAIN, "bad mode");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   m->mode = mode; m->seed = seed;
+  umma_workspace_new_forward(m->ws);        // this forward rewrites the activations: their cached planes are stale
   if (m->cfg.arch == 3) return forward_arch3(m);
   if (m->cfg.arch == 2) return forward_arch2(m);
   const nvqa_config& c = m->cfg;

@@ -81,6 +81,7 @@ struct nvqa_model {
   bool fwd_done = false;
   UmmaWorkspace* ws = nullptr;
   std::vector<void*> allocs;
+  std::vector<std::pair<const float*, const float*>> act_ranges;   // forward activations whose bf16 planes are cached per forward
   // fused data-parallel update over NVLink peer memory (dp_fused.cu)
   int dp_rank = 0, dp_world = 0;
   float* dp_peer_grads[16] = {};     // every rank's flat gradient vector (own entry = grads)

@@ -4,6 +4,8 @@
 // t >= T - len[b] (questions are right-aligned, misc/RNNUtils.lua:54-61).  Inactive rows keep the
 // zero initial state and produce zero gradients, which reproduces the reference's length-sorted
 // packed recurrence (misc/RNNUtils.lua:128-211) without sorting.
+#include <algorithm>
+
 #include "pointwise.cuh"
 
 namespace nvqa {
@@ -327,8 +329,18 @@ colsum_kernel(const float* __restrict__ A, int rows, int cols, int lda, int rows
   int ry = threadIdx.x >> 5;
   int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
   float acc = 0.f;
-  if (c < cols)
-    for (int r = r0 + ry; r < r1; r += 8) acc += A[(int64_t)r * lda + c];
+  if (c < cols) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // four independent chains: the loop is latency-bound
+    int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {
+      a0 += A[(int64_t)r * lda + c];
+      a1 += A[(int64_t)(r + 8) * lda + c];
+      a2 += A[(int64_t)(r + 16) * lda + c];
+      a3 += A[(int64_t)(r + 24) * lda + c];
+    }
+    for (; r < r1; r += 8) a0 += A[(int64_t)r * lda + c];
+    acc = (a0 + a1) + (a2 + a3);
+  }
   red[ry][threadIdx.x & 31] = acc;
   __syncthreads();
   if (ry == 0 && c < cols) {
@@ -341,7 +353,7 @@ colsum_kernel(const float* __restrict__ A, int rows, int cols, int lda, int rows
 }
 
 int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* out0, float* out1) {
-  int chunks = rows >= 2048 ? 16 : 1;
+  int chunks = rows >= 2048 ? 16 : rows >= 128 ? std::min(16, rows / 64) : 1;   // enough CTAs to hide the load latency
   int rpc = ceil_div(rows, chunks);
   dim3 grid(ceil_div(cols, 32), chunks);
   colsum_kernel<<<grid, 256, 0, s>>>(A, rows, cols, lda, rpc, out0, out1);

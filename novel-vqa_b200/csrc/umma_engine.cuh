@@ -43,15 +43,21 @@ struct UmmaWorkspace {
   size_t bytes = 0;
   size_t static_bytes = 0;      // [0, static_bytes): cached planes of static operands (weights)
   size_t static_top = 0;
-  size_t trans_top = 0;         // transient planes live in [static_bytes, bytes), reset per GEMM
+  size_t act_bytes = 0;         // [static_bytes, static_bytes + act_bytes): planes of this forward's activations, so
+  size_t act_top = 0;           // that the backward GEMMs (wgrad operands) reuse them instead of splitting again
+  size_t trans_top = 0;         // transient planes live in [static_bytes + act_bytes, bytes), reset per GEMM
   std::unordered_map<PlaneKey, __nv_bfloat16*, PlaneKeyHash> cache;
+  std::unordered_map<PlaneKey, __nv_bfloat16*, PlaneKeyHash> act_cache;
   std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
 };
 
 
 // fp32 row-major [rows x cols] (ld) -> bf16 planes [P][rows][pitch], pitch = cols rounded up to 8
+// cache_class: 0 = transient, 1 = weight (cached until umma_workspace_invalidate), 2 = activation written once per
+// forward (cached until umma_workspace_new_forward)
 int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int cols, int ld,
-                   bool is_static, __nv_bfloat16** out, int* pitch_out);
+                   int cache_class, __nv_bfloat16** out, int* pitch_out);
+void umma_workspace_new_forward(UmmaWorkspace* ws);
 // tensor map over planes [P][rows][pitch]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
 // (rows = bound of the row coordinate; plane_stride in elements, 0 = rows * pitch)
 int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int pitch, int P, int box_rows, CUtensorMap* out,
@@ -61,7 +67,7 @@ int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int pitch,
 struct UmmaOperand {
   const float* src = nullptr;             // fp32 [rows x cols], leading dimension ld
   int ld = 0;
-  bool is_static = false;                 // weight: cache the planes until umma_workspace_invalidate()
+  int is_static = 0;                      // cache class of the planes: 0 none, 1 weight, 2 activation of this forward
   const __nv_bfloat16* planes = nullptr;  // ready-made planes [P][plane_rows][pitch] ...
   int plane_rows = 0, pitch = 0;
   int row_offset = 0;                     // ... of which this operand starts at row row_offset

@@ -261,10 +261,11 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int umma_workspace_create(UmmaWorkspace** out, size_t transient_bytes, size_t static_bytes) {
+int umma_workspace_create(UmmaWorkspace** out, size_t transient_bytes, size_t static_bytes, size_t act_bytes) {
   UmmaWorkspace* ws = new UmmaWorkspace();
   ws->static_bytes = (static_bytes + 1023) & ~(size_t)1023;
-  ws->bytes = ws->static_bytes + transient_bytes;
+  ws->act_bytes = (act_bytes + 1023) & ~(size_t)1023;
+  ws->bytes = ws->static_bytes + ws->act_bytes + transient_bytes;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws->base), ws->bytes);
   if (e != cudaSuccess) {
     set_error(std::string("umma workspace cudaMalloc: ") + cudaGetErrorString(e));
@@ -285,27 +286,41 @@ void umma_workspace_invalidate(UmmaWorkspace* ws) {
   ws->cache.clear();
   ws->static_top = 0;
 }
+// a new forward pass overwrites the activations: drop their cached planes
+void umma_workspace_new_forward(UmmaWorkspace* ws) {
+  if (!ws) return;
+  ws->act_cache.clear();
+  ws->act_top = 0;
+}
 
 // fp32 row-major [rows x cols] (ld) -> bf16 planes [P][rows][colsp]; no transposition: an MN-major operand is
 // consumed as such through MN-major shared-memory descriptors
 int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int K,
-                          int ld, bool is_static, __nv_bfloat16** out, int* Kp_out) {
+                          int ld, int is_static, __nv_bfloat16** out, int* Kp_out) {
   const int Kp = (K + 7) & ~7;
   *Kp_out = Kp;
   PlaneKey key{src, rows, K, ld, 1, P};
-  if (is_static) {
+  if (is_static == 1) {
     auto it = ws->cache.find(key);
     if (it != ws->cache.end()) { *out = it->second; return 0; }
+  } else if (is_static == 2) {
+    auto it = ws->act_cache.find(key);
+    if (it != ws->act_cache.end()) { *out = it->second; return 0; }
   }
   const size_t need = ((size_t)P * rows * Kp * 2 + 1023) & ~(size_t)1023;
+  const size_t trans0 = ws->static_bytes + ws->act_bytes;
   __nv_bfloat16* dst;
-  if (is_static && ws->static_top + need <= ws->static_bytes) {
+  if (is_static == 1 && ws->static_top + need <= ws->static_bytes) {
     dst = reinterpret_cast<__nv_bfloat16*>(ws->base + ws->static_top);
     ws->static_top += need;
     ws->cache[key] = dst;
+  } else if (is_static == 2 && ws->act_top + need <= ws->act_bytes) {
+    dst = reinterpret_cast<__nv_bfloat16*>(ws->base + ws->static_bytes + ws->act_top);
+    ws->act_top += need;
+    ws->act_cache[key] = dst;
   } else {
-    NVQA_CHECK(ws->static_bytes + ws->trans_top + need <= ws->bytes, "umma workspace too small");
-    dst = reinterpret_cast<__nv_bfloat16*>(ws->base + ws->static_bytes + ws->trans_top);
+    NVQA_CHECK(trans0 + ws->trans_top + need <= ws->bytes, "umma workspace too small");
+    dst = reinterpret_cast<__nv_bfloat16*>(ws->base + trans0 + ws->trans_top);
     ws->trans_top += need;
   }
   int64_t n = (int64_t)rows * (Kp / 4);
@@ -447,8 +462,8 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
     splits = ceil_div(nkb, L.kb_per_split);                       // no empty split
     L.splits = splits;
     const size_t need = (size_t)splits * M * N * sizeof(float);
-    NVQA_CHECK(ws->static_bytes + ws->trans_top + need <= ws->bytes, "umma workspace too small for split-K partials");
-    Cout = reinterpret_cast<float*>(ws->base + ws->static_bytes + ws->trans_top);
+    NVQA_CHECK(ws->static_bytes + ws->act_bytes + ws->trans_top + need <= ws->bytes, "umma workspace too small for split-K partials");
+    Cout = reinterpret_cast<float*>(ws->base + ws->static_bytes + ws->act_bytes + ws->trans_top);
     ws->trans_top += (need + 1023) & ~(size_t)1023;
     ldo = N;
     L.c_split_stride = (long long)M * N;
@@ -479,7 +494,7 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
 
 int umma_gemm(cudaStream_t s, int planes, bool a_kmajor, bool b_kmajor, int M, int N, int K, const float* A, int lda,
               const float* B, int ldb, float* C, int ldc, bool beta, const float* bias0, const float* bias1,
-              UmmaWorkspace* ws, bool a_static, bool b_static) {
+              UmmaWorkspace* ws, int a_static, int b_static) {
   UmmaOperand a, b;
   a.src = A; a.ld = lda; a.kmajor = a_kmajor; a.is_static = a_static;
   b.src = B; b.ld = ldb; b.kmajor = b_kmajor; b.is_static = b_static;
