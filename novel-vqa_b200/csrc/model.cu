@@ -170,6 +170,9 @@ extern "C" int nvqa_model_destroy(nvqa_model* m) {
   if (m->ans_host) cudaFreeHost(m->ans_host);
   if (m->ws) umma_workspace_destroy(m->ws);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->fc7_ready) cudaEventDestroy(m->fc7_ready);
+  if (m->fc7_consumed) cudaEventDestroy(m->fc7_consumed);
   delete m;
   return 0;
 }
@@ -194,6 +197,9 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_TRY(require_device(cfg->device));
   NVQA_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
+  NVQA_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  NVQA_CUDA(cudaEventCreateWithFlags(&m->fc7_ready, cudaEventDisableTiming));
+  NVQA_CUDA(cudaEventCreateWithFlags(&m->fc7_consumed, cudaEventDisableTiming));
   const int S = (a2 && !a3) ? H : 2 * L * H;
   m->S = S;
   m->TS = a3 ? 2 * T + 1 : a2 ? T + 2 : T;
@@ -397,6 +403,7 @@ extern "C" int nvqa_sync(nvqa_model* m) {
   NVQA_CHECK(m, "null model");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->copy_stream) NVQA_CUDA(cudaStreamSynchronize(m->copy_stream));   // an fc7 copy of nvqa_set_batch_host may be in flight
   return 0;
 }
 
@@ -464,6 +471,7 @@ extern "C" int nvqa_set_batch(nvqa_model* m, const int32_t* q, const int32_t* le
   NVQA_CHECK(B > 0 && B <= m->cfg.B, "batch size out of range");
   m->q = q; m->len = len; m->fc7 = fc7; m->labels = labels; m->B = B;
   m->fwd_done = false;
+  m->fc7_pending = false;
   m->steps = m->cfg.arch == 3 ? m->cfg.T : m->TS;
   return 0;
 }
@@ -483,9 +491,16 @@ extern "C" int nvqa_set_batch_host(nvqa_model* m, const int32_t* q, const int32_
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   NVQA_CUDA(cudaMemcpyAsync(m->q_stage, q, (size_t)B * m->cfg.T * 4, cudaMemcpyHostToDevice, m->stream));
   NVQA_CUDA(cudaMemcpyAsync(m->len_stage, len, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
-  if (m->cfg.arch != 3) NVQA_CUDA(cudaMemcpyAsync(m->fc7_stage, fc7, (size_t)B * m->cfg.I * 4, cudaMemcpyHostToDevice, m->stream));
   if (labels) NVQA_CUDA(cudaMemcpyAsync(m->lab_stage, labels, (size_t)B * 4, cudaMemcpyHostToDevice, m->stream));
   NVQA_TRY(nvqa_set_batch(m, m->q_stage, m->len_stage, m->fc7_stage, labels ? m->lab_stage : nullptr, B));
+  if (m->cfg.arch != 3) {
+    // the 8 MB feature copy overlaps the embedding and the LSTM forward: it runs on the copy stream (after the previous
+    // step's last read of the staging buffer) and the compute stream joins it only in front of the image branch
+    NVQA_CUDA(cudaStreamWaitEvent(m->copy_stream, m->fc7_consumed, 0));
+    NVQA_CUDA(cudaMemcpyAsync(m->fc7_stage, fc7, (size_t)B * m->cfg.I * 4, cudaMemcpyHostToDevice, m->copy_stream));
+    NVQA_CUDA(cudaEventRecord(m->fc7_ready, m->copy_stream));
+    m->fc7_pending = true;
+  }
   if (m->cfg.arch == 2) {   // executed steps tmax = image + START + longest question (Encoder_lstm.lua:185-189,219)
     int mx = 0;
     for (int b = 0; b < B; ++b) mx = len[b] > mx ? len[b] : mx;
@@ -509,6 +524,14 @@ extern "C" int nvqa_set_masks(nvqa_model* m, const float* emb, const float* lstm
 }
 
 // ---- forward -------------------------------------------------------------------------------------
+// the compute stream waits for the asynchronous fc7 host-to-device copy of nvqa_set_batch_host (if one is in flight)
+static int join_fc7_copy(nvqa_model* m) {
+  if (m->fc7_pending) {
+    NVQA_CUDA(cudaStreamWaitEvent(m->stream, m->fc7_ready, 0));
+    m->fc7_pending = false;
+  }
+  return 0;
+}
 
 static Drop lstm_drop(const nvqa_model* m, int l /* between layer l and l+1 */) {
   const int64_t per = (int64_t)(m->cfg.arch == 2 ? m->steps : m->cfg.T) * m->B * m->cfg.H;
@@ -583,8 +606,10 @@ static int forward_arch2(nvqa_model* m) {
   none.mode = 0;
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
-    NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, none, B, c.I, c.img_norm));
     NVQA_TRY(lookup_fwd(s, m->q, m->lookup, m->y, B, T, E, c.V, steps));
+    NVQA_TRY(join_fc7_copy(m));
+    NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, none, B, c.I, c.img_norm));
+    NVQA_CUDA(cudaEventRecord(m->fc7_consumed, s));
   }
   // step 1: cnn_projection = Linear(I, E) on the (normalised) image feature, written as rows [0, B) of the LSTM input
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, E, c.I, m->vd, c.I, m->Wcnn, c.I, m->y, E, false, m->bcnn));
@@ -683,7 +708,9 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L));
+    NVQA_TRY(join_fc7_copy(m));
     NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), B, c.I, c.img_norm));
+    NVQA_CUDA(cudaEventRecord(m->fc7_consumed, s));
   }
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));

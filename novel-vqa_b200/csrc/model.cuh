@@ -26,6 +26,10 @@ struct nvqa_model {
   nvqa_config cfg;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  // host-buffer batches: the large fc7 copy runs on its own stream and is joined only where the head first reads it
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t fc7_ready = nullptr, fc7_consumed = nullptr;
+  bool fc7_pending = false;
   int S = 0;
   int64_t n_blk[3] = {0, 0, 0};
   int64_t off_blk[4] = {0, 0, 0, 0};
