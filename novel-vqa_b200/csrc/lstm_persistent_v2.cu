@@ -30,7 +30,7 @@ namespace nvqa {
 
 constexpr int V2_THREADS = 320;          // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 constexpr int V2_EPI = 256;
-constexpr int V2_STAGES = 4;
+constexpr int V2_STAGES = 6;           // bytes in flight set the load rate (latency-bound: 64 KB -> 17 B/clk, 96 KB -> ~26 B/clk)
 constexpr int V2_TPITCH = 132;           // words per row of the transpose tile (128 + 4: conflict-free 128-bit reads)
 
 __device__ __forceinline__ void v2_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -66,8 +66,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
                    float* __restrict__ h, __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
-                   const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter) {
+                   const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ long long fst[32];
+#define F_STAMP(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && t >= 8 && t < 12) fst[(t - 8) * 8 + (slot)] = clock64(); } while (0)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   constexpr uint32_t W_KB = 128 * 128;                  // one k-block of the W0 slice: 128 rows x 128 B
@@ -113,30 +115,30 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       mbar_expect_tx(wfull, (uint32_t)KB * W_KB);
       for (int kb = 0; kb < KB; ++kb)
         for (int g = 0; g < 4; ++g)
-          tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)g * 4096, &mapW, wfull, kb * 64, g * H + u0, 0);
+          tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)g * 4096, &mapW, wfull, kb * 64, g * H + u0, P >= 2 ? 1 : 0);
     }
     int it = 0;
     const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
+    // warp-uniform loop, one elected lane issues (see elect_one_sync): a TMA issue under `if (lane == 0)` costs ~300 cycles
     for (int t = 0; t < T; ++t) {
       if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }    // phase t: h_{t-1} published by all 16 CTAs
-      if (lane == 0) {
-        if (t > 0) {
-          if (!CL) v2_wait(counter + 32 * blockIdx.y, (unsigned int)t * gridDim.x);     // h_{t-1} of this batch tile is complete
-          fence_proxy_async();
-        }
-        for (int kb = 0; kb < KB; ++kb) {
-          const int itk = it + kb;
-          const int s = itk % V2_STAGES;
-          const uint32_t ph = (uint32_t)(itk / V2_STAGES) & 1u;
-          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      if (t > 0) {
+        if (!CL && lane == 0) v2_wait(counter + 32 * blockIdx.y, (unsigned int)t * gridDim.x);   // h_{t-1} of this batch tile is complete
+        __syncwarp();
+        fence_proxy_async();
+      }
+      if (lane == 0) F_STAMP(0);
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % V2_STAGES;
+        const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        if (elect_one_sync()) {
           mbar_expect_tx(full0 + 8 * s, STAGE);
-#pragma unroll
-          for (int p = 0; p < P; ++p)
-            tma_load_3d(r0 + (uint32_t)s * STAGE + (uint32_t)p * B_PLANE, &mapH, full0 + 8 * s, kb * 64, t * B + m0, p);
+          tma_load_3d(r0 + (uint32_t)s * STAGE, &mapH, full0 + 8 * s, kb * 64, t * B + m0, 0);   // all P planes in one box
           if (kb == gokb) mbar_arrive(gobar);      // this step's first loads are out: the epilogue may use the memory pipe
         }
+        __syncwarp();
       }
-      it += KB;
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -146,32 +148,43 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       if (P >= 2) mbar_wait(w1bar, 0);             // plane 1 of the W slice has been stored to TMEM by the epilogue warps
       tc_fence_after();
     }
+    // the whole warp walks the loop (warp-uniform control flow and descriptors); one elected lane issues
+    if (lane == 0) { /* wfull / w1bar were waited above by lane 0 */ }
+    __syncwarp();
     int it = 0;
+    const uint64_t dw_base = make_kmajor_sw128_desc(w0), dr_base = make_kmajor_sw128_desc(r0);
     for (int t = 0; t < T; ++t) {
       if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }
-      if (lane == 0) {
-        uint32_t acc = 0;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % V2_STAGES;
-          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
-          mbar_wait(full0 + 8 * s, ph);
-          tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % V2_STAGES;
+        const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          // descriptor start-address field is in 16-byte units: advancing by bytes/16 is a plain 64-bit add
+          const uint64_t dwk = dw_base + (uint64_t)(((uint32_t)kb * W_KB) >> 4);
+          const uint64_t dhk = dr_base + (uint64_t)(((uint32_t)s * STAGE) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t dw = make_kmajor_sw128_desc(w0 + (uint32_t)kb * W_KB + k * 32);
-            const uint64_t dh0 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + k * 32);
+            const uint64_t dw = dwk + (uint64_t)(k * 2), dh0 = dhk + (uint64_t)(k * 2);
+            const uint32_t accf = (kb | k) ? 1u : 0u;
             if (P >= 2) {
-              const uint64_t dh1 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + B_PLANE + k * 32);
-              umma_f16_ts(tmem_base, tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8), dh0, idesc, acc); acc = 1;
-              umma_f16(tmem_base, dw, dh1, idesc, acc);
+              // TMEM holds plane 0 of W (two of the three products read it: no shared-memory traffic for their A
+              // operand -- an SS MMA of this shape needs (128 + 64) x 32 B from shared memory, 48 cycles at 128 B/clk,
+              // more than its 32 tensor cycles); shared memory holds plane 1 (one product)
+              const uint64_t dh1 = dh0 + (uint64_t)(B_PLANE >> 4);
+              const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8);
+              umma_f16(tmem_base, dw, dh0, idesc, accf);          // W1 . h0   (A from shared memory)
+              umma_f16_ts(tmem_base, wt, dh1, idesc, 1u);         // W0 . h1   (A from tensor memory)
+              umma_f16_ts(tmem_base, wt, dh0, idesc, 1u);         // W0 . h0
+            } else {
+              umma_f16(tmem_base, dw, dh0, idesc, accf);
             }
-            umma_f16(tmem_base, dw, dh0, idesc, acc); acc = 1;
           }
           umma_commit(empty0 + 8 * s);
+          if (kb == KB - 1) umma_commit(tfull);
         }
-        umma_commit(tfull);
-      } else {
-        it += KB;
+        __syncwarp();
       }
     }
   } else {
@@ -224,6 +237,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       }
       mbar_wait(tfull, (uint32_t)t & 1u);
       tc_fence_after();
+      if (threadIdx.x == 64) F_STAMP(1);
       {
         // accumulator -> shared memory, transposed: tbuf[n][m]   (the B ring is idle between tfull and our arrive)
         float acc[32];
@@ -234,6 +248,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       }
       tc_fence_before();
       v2_bar_sync(2, V2_EPI);
+      if (threadIdx.x == 64) F_STAMP(2);
       float gi[8], gf[8], go[8], gg[8], cn[8], hn[8];
       if (active) {
         const float* row = tbuf + (size_t)n * V2_TPITCH + 8 * ug;
@@ -279,15 +294,17 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       // (2) publish it: generic-proxy writes (global h planes AND the shared-memory tile that the next TMA loads will
       // overwrite) are ordered before later async-proxy accesses; one thread's gpu-scope release is made cumulative
       // over the CTA by the barrier
+      if (threadIdx.x == 64) F_STAMP(3);
       fence_proxy_async();
       if (CL) {
         if (t + 1 < T) { __syncwarp(); v2_cluster_arrive(); }     // every thread releases its own stores to the cluster
       } else {
         v2_bar_sync(1, V2_EPI);
-        if (threadIdx.x == 64) v2_arrive(counter + 32 * blockIdx.y);
+        if (threadIdx.x == 64) { F_STAMP(4); v2_arrive(counter + 32 * blockIdx.y); F_STAMP(5); }
         v2_bar_sync(3, V2_EPI);                    // keep the SM's memory pipeline clear until the release is out ...
       }
       if (t + 1 < T) mbar_wait(gobar, (uint32_t)(t + 1) & 1u);   // ... and until the next step's first loads are issued
+      if (threadIdx.x == 64) F_STAMP(6);
       // (3) everything only the backward pass needs, off the critical path
       if (rowok) {
         float* gdst = pre + rin * 4 * H + uo;
@@ -307,6 +324,15 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
 #undef ST8
       }
       if (CL && t + 1 < T) { __syncwarp(); v2_cluster_wait(); }   // pairs with the arrive above (complete long ago)
+      if (threadIdx.x == 64) F_STAMP(7);
+    }
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) {
+      printf("lstm_fwd_v2 timeline (cycles after the barrier opened): t | mma_done transposed math+stores_done all_done arrived go deferred_issued | step\n");
+      for (int i = 1; i < 4; ++i) {
+        const long long* e = fst + i * 8;
+        printf("%2d | %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", 8 + i, e[1] - e[0], e[2] - e[0], e[3] - e[0], e[4] - e[0], e[5] - e[0],
+               e[6] - e[0], e[7] - e[0], e[0] - fst[(i - 1) * 8]);
+      }
     }
   }
   tc_fence_before();
@@ -727,60 +753,73 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
   constexpr uint32_t W1_COL = 256;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: warp-uniform loop, one elected lane issues =====
     if (lane == 0) {
       mbar_expect_tx(wfull, (uint32_t)KB * W_KB);
       for (int kb = 0; kb < KB; ++kb)
         for (int cc = 0; cc < 2; ++cc)
-          tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)cc * 8192, &mapW, wfull, c0 + 64 * cc, k_base + kb * 64, 0);
-      int it = 0;
-      const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
-      for (int t = T - 1; t >= tlast; --t) {
-        const unsigned int k = (unsigned int)(T - 1 - t);
-        v2_wait(counter, (k + 1) * G);                      // da_t of this batch tile is complete
-        fence_proxy_async();
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % V2_STAGES;
-          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
-          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)cc * 8192, &mapW, wfull, c0 + 64 * cc, k_base + kb * 64, P >= 2 ? 1 : 0);
+    }
+    __syncwarp();
+    int it = 0;
+    const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
+    for (int t = T - 1; t >= tlast; --t) {
+      const unsigned int k = (unsigned int)(T - 1 - t);
+      if (lane == 0) v2_wait(counter, (k + 1) * G);         // da_t of this batch tile is complete
+      __syncwarp();
+      fence_proxy_async();
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % V2_STAGES;
+        const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        if (elect_one_sync()) {
           mbar_expect_tx(full0 + 8 * s, STAGE);
-#pragma unroll
-          for (int p = 0; p < P; ++p)
-            tma_load_3d(r0 + (uint32_t)s * STAGE + (uint32_t)p * B_PLANE, &mapDA, full0 + 8 * s, k_base + kb * 64, t * B + m0, p);
+          tma_load_3d(r0 + (uint32_t)s * STAGE, &mapDA, full0 + 8 * s, k_base + kb * 64, t * B + m0, 0);   // all P planes in one box
           if (kb == gokb) mbar_arrive(gobar);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (descriptors stay in uniform registers) =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, false);       // A = W_hh^T slice in SMEM, MN-major
+    constexpr uint32_t idesc_ts = make_idesc_bf16(128, 64, false, false);   // A from TMEM is K-major by construction
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, false);       // A = W_hh^T slice in SMEM, MN-major
-      constexpr uint32_t idesc_ts = make_idesc_bf16(128, 64, false, false);   // A from TMEM is K-major by construction
       mbar_wait(wfull, 0);
       if (P >= 2) mbar_wait(w1bar, 0);
-      tc_fence_after();
-      int it = 0;
-      for (int t = T - 1; t >= tlast; --t) {
-        uint32_t acc = 0;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % V2_STAGES;
-          const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
-          mbar_wait(full0 + 8 * s, ph);
-          tc_fence_after();
+    }
+    __syncwarp();
+    tc_fence_after();
+    const uint64_t dw_base = make_mnmajor_sw128_desc(w0), dr_base = make_kmajor_sw128_desc(r0);
+    int it = 0;
+    for (int t = T - 1; t >= tlast; --t) {
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % V2_STAGES;
+        const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t dwk = dw_base + (uint64_t)(((uint32_t)kb * W_KB) >> 4);
+          const uint64_t ddk = dr_base + (uint64_t)(((uint32_t)s * STAGE) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t dw = make_mnmajor_sw128_desc(w0 + (uint32_t)kb * W_KB + k * 2048);
-            const uint64_t d0 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + k * 32);
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t dw = dwk + (uint64_t)(kk * (2048 >> 4)), d0 = ddk + (uint64_t)(kk * 2);
+            const uint32_t accf = (kb | kk) ? 1u : 0u;
             if (P >= 2) {
-              const uint64_t d1 = make_kmajor_sw128_desc(r0 + (uint32_t)s * STAGE + B_PLANE + k * 32);
-              umma_f16_ts(tmem_base, tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8), d0, idesc_ts, acc); acc = 1;
-              umma_f16(tmem_base, dw, d1, idesc, acc);
+              // TMEM holds plane 0 of the W_hh^T slice (two of the three products), shared memory plane 1
+              const uint64_t d1 = d0 + (uint64_t)(B_PLANE >> 4);
+              const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + kk * 8);
+              umma_f16(tmem_base, dw, d0, idesc, accf);            // W1 . da0
+              umma_f16_ts(tmem_base, wt, d1, idesc_ts, 1u);        // W0 . da1
+              umma_f16_ts(tmem_base, wt, d0, idesc_ts, 1u);        // W0 . da0
+            } else {
+              umma_f16(tmem_base, dw, d0, idesc, accf);
             }
-            umma_f16(tmem_base, dw, d0, idesc, acc); acc = 1;
           }
           umma_commit(empty0 + 8 * s);
+          if (kb == KB - 1) umma_commit(tfull);
         }
-        umma_commit(tfull);
+        __syncwarp();
       }
     }
   } else {
@@ -1025,12 +1064,14 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   CUtensorMap mapW, mapH;
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 32, &mapW));
   if (hp_plane_rows <= 0) hp_plane_rows = (long long)(T + 1) * B;
-  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 64, &mapH, hp_plane_rows * H));
+  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 64, &mapH, hp_plane_rows * H, P));
   NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
   long long hp_plane = hp_plane_rows * H;
-  const __nv_bfloat16* w1 = wp + (size_t)4 * H * pitch;            // plane 1
+  const __nv_bfloat16* w1 = wp;                                    // the TMEM-resident plane: plane 0 (plane 1 goes to SMEM)
   int KBv = KB;
-  void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter};
+  static const int dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
+  int dbgv = dbg;
+  void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter, &dbgv};
   static int use_cl = -1;
   if (use_cl < 0) { const char* e = getenv("NVQA_LSTM_CLUSTER16"); use_cl = e ? atoi(e) : 0; }   // measured on B200: only part of the 8 clusters of 16 is co-resident (0.82 ms vs 0.48 ms)
   if (use_cl && grid.x == 16) {
@@ -1110,7 +1151,10 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.z, s));
     static const int dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
     int dbgv = dbg;
-    void* a3[] = {&mapDA, &mapW, &w1, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dh_init,
+    CUtensorMap mapDA3;                            // both planes of a da tile in one TMA box
+    NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 64, &mapDA3, dap_plane_rows * 4 * H, P));
+    const __nv_bfloat16* wt = wp;                  // generation 3 keeps plane 0 in TMEM and plane 1 in shared memory
+    void* a3[] = {&mapDA3, &mapW, &wt, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dh_init,
                   &dc_init, &len, &T, &B, &H, &KBv, &counter, &dbgv};
     const void* f3 = P == 2 ? (const void*)lstm_bwd_v3_kernel<2> : (const void*)lstm_bwd_v3_kernel<1>;
     NVQA_CUDA(cudaFuncSetAttribute(f3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

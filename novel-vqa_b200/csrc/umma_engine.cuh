@@ -25,15 +25,16 @@ struct PlaneKeyHash {
   }
 };
 struct MapKey {
-  const void* planes; int rows, Kp, P, box; long long plane_stride;
+  const void* planes; int rows, Kp, P, box; long long plane_stride; int box_planes;
   bool operator==(const MapKey& o) const {
-    return planes == o.planes && rows == o.rows && Kp == o.Kp && P == o.P && box == o.box && plane_stride == o.plane_stride;
+    return planes == o.planes && rows == o.rows && Kp == o.Kp && P == o.P && box == o.box && plane_stride == o.plane_stride &&
+           box_planes == o.box_planes;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.planes);
-    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.Kp; h = h * 1000003u ^ (size_t)(k.P * 1024 + k.box);
+    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.Kp; h = h * 1000003u ^ (size_t)(k.P * 1024 + k.box + k.box_planes * 65536);
     return h;
   }
 };
@@ -60,8 +61,10 @@ int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, i
 void umma_workspace_new_forward(UmmaWorkspace* ws);
 // tensor map over planes [P][rows][pitch]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
 // (rows = bound of the row coordinate; plane_stride in elements, 0 = rows * pitch)
+// box_planes > 1: one TMA instruction fetches the same [box_rows x 64] tile of that many consecutive planes (they land
+// back to back in shared memory)
 int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int pitch, int P, int box_rows, CUtensorMap* out,
-            long long plane_stride = 0);
+            long long plane_stride = 0, int box_planes = 1);
 
 // A GEMM operand: either an fp32 row-major source (split into planes by the engine) or planes made upstream.
 struct UmmaOperand {

@@ -334,16 +334,16 @@ int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, i
 
 // tensor map over planes [P][rows][colsp]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
 int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, int P, int box_rows, CUtensorMap* out,
-            long long plane_stride) {
+            long long plane_stride, int box_planes) {
   if (plane_stride <= 0) plane_stride = (long long)rows * Kp;
-  MapKey key{planes, rows, Kp, P, box_rows, plane_stride};
+  MapKey key{planes, rows, Kp, P, box_rows, plane_stride, box_planes};
   auto it = ws->maps.find(key);
   if (it != ws->maps.end()) { *out = it->second; return 0; }
   EncodeTiledFn enc = get_encode();
   NVQA_CHECK(enc, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)P};
   cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)plane_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)UG_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)UG_BK, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(planes), dims, strides, box, estr,
