@@ -692,6 +692,8 @@ __device__ __forceinline__ void v3_wait_cluster(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) { printf("lstm_bwd_v3: cluster barrier timed out\n"); __trap(); }
   }
 }
+__device__ long long g_v3dbg[16 * 4];           // (debug) per-CTA wall-clock stamps of batch-tile group 0 at one step
+__device__ __forceinline__ long long v3_gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define V3_STAMP(slot) do { if (dbg && cta == 0 && blockIdx.z == 0 && t >= 8 && t < 12) stamps[(t - 8) * 8 + (slot)] = clock64(); } while (0)
 
 template <int P>
@@ -765,7 +767,10 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
     for (int t = T - 1; t >= tlast; --t) {
       const unsigned int k = (unsigned int)(T - 1 - t);
-      if (lane == 0) v2_wait(counter, (k + 1) * G);         // da_t of this batch tile is complete
+      if (lane == 0) {
+        v2_wait(counter, (k + 1) * G);         // da_t of this batch tile is complete
+        if (dbg && blockIdx.z == 0 && t == 10) g_v3dbg[cta * 4 + 1] = v3_gtimer();
+      }
       __syncwarp();
       fence_proxy_async();
       for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -889,7 +894,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     auto reduce_partials = [&](float4* out, int t) {
       mbar_wait(tfull, red & 1u);
       tc_fence_after();
-      if (et == 0) V3_STAMP(5);
+      if (et == 0) { V3_STAMP(5); if (dbg && blockIdx.z == 0 && t == 10) g_v3dbg[cta * 4 + 3] = v3_gtimer(); }
       {
         float acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), acc);
@@ -963,7 +968,13 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       if (et == 0) V3_STAMP(2);
       fence_proxy_async();
       v2_bar_sync(1, V2_EPI);
-      if (et == 0) { V3_STAMP(3); v2_arrive(counter); V3_STAMP(4); }
+      if (et == 0) {
+        V3_STAMP(3);
+        if (dbg && blockIdx.z == 0 && t == 10) g_v3dbg[cta * 4 + 2] = v3_gtimer();
+        v2_arrive(counter);
+        V3_STAMP(4);
+        if (dbg && blockIdx.z == 0 && t == 10) g_v3dbg[cta * 4 + 0] = v3_gtimer();
+      }
       v2_bar_sync(3, V2_EPI);
       if (t >= tlast) mbar_wait(gobar, k & 1u);
       // off the critical path: the operands of step t-1
@@ -1169,6 +1180,17 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     static const bool nocoop = getenv("NVQA_LSTM_NOCOOP") != nullptr;
     cfg3.attrs = at3; cfg3.numAttrs = nocoop ? 1 : 2;
     cudaError_t le = cudaLaunchKernelExC(&cfg3, f3, a3);
+    if (le == cudaSuccess && dbg) {
+      long long hb[64];
+      NVQA_CUDA(cudaStreamSynchronize(s));
+      NVQA_CUDA(cudaMemcpyFromSymbol(hb, g_v3dbg, sizeof(hb)));
+      long long base = hb[3];
+      for (int i = 0; i < 16; ++i) base = std::min(base, hb[i * 4 + 3]);
+      fprintf(stderr, "lstm_bwd_v3 group 0, step t=10 (ns after the first CTA's mma_done): cta(col,ks) | mma_done phaseA_alldone arrived open(for t=9)\n");
+      for (int i = 0; i < 16; ++i)
+        fprintf(stderr, "  %2d (%d,%d) | %6lld %6lld %6lld %6lld\n", i, i % 4, i / 4, hb[i * 4 + 3] - base, hb[i * 4 + 2] - base, hb[i * 4 + 0] - base,
+                hb[i * 4 + 1] - base);
+    }
     if (le == cudaSuccess) { ++g_launches; return 0; }
     (void)cudaGetLastError();                     // the clusters could not be made co-resident: generation 2 below
     use_v3 = 0;
