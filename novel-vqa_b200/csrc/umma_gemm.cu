@@ -96,12 +96,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+    // ===== TMA producer: warp-uniform loop, one elected lane issues (see elect_one_sync in umma_ptx.cuh) =====
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % Cfg::STAGES;
+      const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+      mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      if (elect_one_sync()) {
         mbar_expect_tx(full0 + 8 * s, Cfg::STAGE);
         const uint32_t sa = base + s * Cfg::STAGE;
         const uint32_t sb = sa + P * Cfg::A_PLANE;
@@ -128,17 +128,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN, AMN, BMN);
-      uint32_t acc = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-        mbar_wait(full0 + 8 * s, ph);
-        tc_fence_after();
+    // ===== MMA issuer: the whole warp walks the loop (uniform control flow and descriptors), one elected lane issues;
+    // under `if (lane == 0)` every UTCHMMA was wrapped in an ELECT / R2UR / BRA.U.ANY loop (~80 cycles per MMA) =====
+    constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN, AMN, BMN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % Cfg::STAGES;
+      const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        uint32_t acc = kb > 0 ? 1u : 0u;
         const uint32_t sa = base + s * Cfg::STAGE;
         const uint32_t sb = sa + P * Cfg::A_PLANE;
 #pragma unroll
@@ -166,8 +168,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           umma_f16(tmem_base, da[0], db[0], idesc, acc); acc = 1;
         }
         umma_commit(empty0 + 8 * s);          // smem slot free once these MMAs have read it
+        if (kb == nkb - 1) umma_commit(tfull);  // accumulator complete
       }
-      umma_commit(tfull);                     // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
