@@ -44,6 +44,8 @@ enum {
 
 enum { NVQA_BLOCK_ENCODER = 0, NVQA_BLOCK_EMBEDDING = 1, NVQA_BLOCK_MULTIMODAL = 2 };
 enum { NVQA_MODE_EVAL = 0, NVQA_MODE_TRAIN = 1 };
+/* fusion block of the arch 1 trainers: netdef.AxB (misc/netdef.lua:6-14) or netdef.AskipB (:16-25, 003_train_ae_based_wp.lua:151) */
+enum { NVQA_FUSION_AXB = 0, NVQA_FUSION_ASKIPB = 1 };
 /* backward phases, in gradient-readiness order (what the data-parallel host overlaps with NCCL) */
 enum { NVQA_PHASE_HEAD = 0, NVQA_PHASE_LSTM = 1, NVQA_PHASE_EMBED = 2, NVQA_PHASE_ALL = 3 };
 
@@ -136,6 +138,11 @@ int nvqa_adam_step(nvqa_model* m, float lr, float beta1, float beta2, float eps,
 /* arch 3: log-probabilities [B x (V+1)] of decoder step `step` (0-based; self.output_dec[step+1],
  * AutoEncoder_text_nostart.lua:334); valid after nvqa_forward until nvqa_backward consumes them in place */
 int nvqa_logprobs_get(nvqa_model* m, int32_t step, float* host_dst);
+/* arch 1 trainer variants (002_train_vqa_arch1/003_train_ae_based*.lua): fusion = NVQA_FUSION_*; lr_scale multiplies the
+ * encoder and embedding gradients before the clamp (-lr_scale, 003_train_ae_based_wp.lua:30,344; not applied by
+ * nvqa_dp_rmsprop_step); norm_split > 0: with img_norm = 1 the feature columns [0, norm_split) and [norm_split, I) are
+ * L2-normalised separately (early fusion of two CNN features, 003_train_ae_based_ef.lua:74,116-124). */
+int nvqa_set_variant(nvqa_model* m, int32_t fusion, float lr_scale, int32_t norm_split);
 int nvqa_scores_get(nvqa_model* m, float* host_dst);             /* [B x O]                       */
 int nvqa_argmax_get(nvqa_model* m, int32_t* host_dst);           /* torch.max(scores,2), 1-based  */
 int nvqa_state_get(nvqa_model* m, float* host_dst);              /* final LSTM state tv_q [B x 2LH] */

@@ -20,6 +20,7 @@ class nvqa_config(C.Structure):
 PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_BF16X2 = 0, 1, 2, 3
 BLOCK_ENCODER, BLOCK_EMBEDDING, BLOCK_MULTIMODAL = 0, 1, 2
 MODE_EVAL, MODE_TRAIN = 0, 1
+FUSION_AXB, FUSION_ASKIPB = 0, 1
 PHASE_HEAD, PHASE_LSTM, PHASE_EMBED, PHASE_ALL = 0, 1, 2, 3
 
 # name -> (restype, argtypes); must list every symbol include/nvqa.h declares (tests/test_abi.py checks)
@@ -51,6 +52,7 @@ SIGNATURES = {
     "nvqa_rmsprop_step": (C.c_int, [C.c_void_p] + [C.c_float] * 6),
     "nvqa_adam_step": (C.c_int, [C.c_void_p] + [C.c_float] * 7),
     "nvqa_logprobs_get": (C.c_int, [C.c_void_p, C.c_int32, c_f32p]),
+    "nvqa_set_variant": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_int32]),
     "nvqa_scores_get": (C.c_int, [C.c_void_p, c_f32p]),
     "nvqa_argmax_get": (C.c_int, [C.c_void_p, c_i32p]),
     "nvqa_state_get": (C.c_int, [C.c_void_p, c_f32p]),

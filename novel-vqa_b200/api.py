@@ -10,12 +10,13 @@ from dataclasses import dataclass, asdict
 import numpy as np
 
 from . import _lib
+from ._lib import FUSION_AXB, FUSION_ASKIPB  # noqa: F401
 from ._lib import (PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_BF16X2, BLOCK_ENCODER, BLOCK_EMBEDDING,  # noqa: F401
                    BLOCK_MULTIMODAL, MODE_EVAL, MODE_TRAIN, PHASE_HEAD, PHASE_LSTM, PHASE_EMBED, PHASE_ALL,
                    NvqaError)
 
 __all__ = ["Arch1Config", "Arch1Model", "Arch2Config", "Arch2Model", "synth_params2", "synth_batch2", "BLOCK_CNN",
-           "AEConfig", "AEModel", "synth_params_ae", "synth_batch_ae", "BLOCK_AE_ENCODER", "BLOCK_AE_DECODER", "BLOCK_AE_LOOKUP", "DeviceBuffer", "right_align", "pack_batch", "mc_select", "synth_batch", "synth_params",
+           "AEConfig", "AEModel", "synth_params_ae", "synth_batch_ae", "BLOCK_AE_ENCODER", "BLOCK_AE_DECODER", "BLOCK_AE_LOOKUP", "DeviceBuffer", "right_align", "pack_batch", "mc_select", "FUSION_AXB", "FUSION_ASKIPB", "synth_batch", "synth_params",
            "device_count", "launch_count", "PREC_FP32_SIMT", "PREC_BF16X3", "PREC_BF16", "PREC_BF16X2",
            "BLOCK_ENCODER", "BLOCK_EMBEDDING", "BLOCK_MULTIMODAL", "MODE_EVAL", "MODE_TRAIN", "PHASE_HEAD",
            "PHASE_LSTM", "PHASE_EMBED", "PHASE_ALL", "NvqaError", "DECAY_FACTOR"]
@@ -237,6 +238,10 @@ class Arch1Model:
 
     def backward(self, phase=PHASE_ALL):
         _lib.check(self.lib.nvqa_backward(self.handle, phase))
+
+    def set_variant(self, fusion=0, lr_scale=1.0, norm_split=0):
+        """003_train_ae_based_wp.lua (AskipB, -lr_scale) / 003_train_ae_based_ef.lua (two-block image norm)."""
+        _lib.check(self.lib.nvqa_set_variant(self.handle, fusion, lr_scale, norm_split))
 
     def rmsprop_step(self, lr, alpha=0.99, eps=1e-8, wd=0.0, clamp=10.0, grad_scale=1.0):
         _lib.check(self.lib.nvqa_rmsprop_step(self.handle, lr, alpha, eps, wd, clamp, grad_scale))

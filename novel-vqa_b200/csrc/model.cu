@@ -709,14 +709,14 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L));
     NVQA_TRY(join_fc7_copy(m));
-    NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), B, c.I, c.img_norm));
+    NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), B, c.I, c.img_norm, m->norm_split));
     NVQA_CUDA(cudaEventRecord(m->fc7_consumed, s));
   }
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
-    NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C));
+    NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C, m->fusion_skip));
   }
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.O, c.C, m->zd, c.C, m->Wc, c.C, m->scores, c.O, false, m->bc));
   // criterion forward/backward (:308-310) + torch.max (004_eval_model.lua:233)
@@ -821,7 +821,7 @@ static int backward_head(nvqa_model* m) {
   NVQA_TRY(colsum(s, m->dscores, B, O, O, m->gbc, nullptr));
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, C, O, m->dscores, O, m->Wc, C, m->dzd, C, false));
   // Dropout, CMulTable, Tanh backward
-  NVQA_TRY(fuse_bwd(s, m->dzd, m->qc, m->ic, m->dqpre, m->dipre, make_drop(m, m->mk_z, STREAM_HEAD), B, C));
+  NVQA_TRY(fuse_bwd(s, m->dzd, m->qc, m->ic, m->dqpre, m->dipre, make_drop(m, m->mk_z, STREAM_HEAD), B, C, m->fusion_skip));
   // AxB Linear backward (no d fc7)
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, S, B, m->dqpre, C, m->qd, S, m->gWq, S, false));
   NVQA_TRY(colsum(s, m->dqpre, B, C, C, m->gbq, nullptr));
@@ -962,7 +962,25 @@ extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   umma_workspace_invalidate(m->ws);     // the weights change: their cached bf16 planes are stale
   ProfScope ps(m, CAT_OPT, 0);
+  if (m->cfg.arch == 1 && m->lr_scale != 1.0f) {
+    // gradients = join{encoder_dw * lr_scale, embedding_dw * lr_scale, multimodal_dw}, then clamp, then rmsprop
+    // (003_train_ae_based_wp.lua:344-346): the scale is folded into the pre-clamp gradient scale of blocks 0 and 1
+    const int64_t n01 = m->off_blk[2];
+    NVQA_TRY(clamp_rmsprop(m->stream, m->params, m->grads, m->rms, n01, lr, alpha, eps, wd, clamp, gscale * m->lr_scale));
+    return clamp_rmsprop(m->stream, m->params + n01, m->grads + n01, m->rms + n01, m->P - n01, lr, alpha, eps, wd, clamp, gscale);
+  }
   return clamp_rmsprop(m->stream, m->params, m->grads, m->rms, m->P, lr, alpha, eps, wd, clamp, gscale);
+}
+
+extern "C" int nvqa_set_variant(nvqa_model* m, int32_t fusion, float lr_scale, int32_t norm_split) {
+  NVQA_CHECK(m && m->cfg.arch == 1, "nvqa_set_variant applies to arch 1 models");
+  NVQA_CHECK(fusion == NVQA_FUSION_AXB || fusion == NVQA_FUSION_ASKIPB, "unknown fusion");
+  NVQA_CHECK(norm_split >= 0 && norm_split < m->cfg.I && norm_split % 4 == 0, "norm_split must be a multiple of 4 inside [0, I)");
+  NVQA_CHECK(lr_scale > 0.f, "lr_scale must be positive");
+  m->fusion_skip = fusion == NVQA_FUSION_ASKIPB;
+  m->lr_scale = lr_scale;
+  m->norm_split = norm_split;
+  return 0;
 }
 
 extern "C" int nvqa_adam_step(nvqa_model* m, float lr, float beta1, float beta2, float eps, float wd, float clamp, float gscale) {
@@ -1082,7 +1100,7 @@ extern "C" int nvqa_axb_forward(nvqa_model* m, const float* q, const float* i, c
   NVQA_TRY(mask_copy(s, i, c.I, nullptr, m->vd, di, n, c.I));
   NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
   NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
-  NVQA_TRY(fuse_fwd(s, m->qc, m->ic, out, none, n, c.C));
+  NVQA_TRY(fuse_fwd(s, m->qc, m->ic, out, none, n, c.C, m->fusion_skip));
   return 0;
 }
 

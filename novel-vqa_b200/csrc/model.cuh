@@ -67,6 +67,10 @@ struct nvqa_model {
   int32_t *targets = nullptr, *n_pred = nullptr;
   float *adam_m = nullptr;          // Adam first moment (second moment lives in rms)
   int64_t adam_t = 0;
+  // trainer variants of 002_train_vqa_arch1 (nvqa_set_variant): AskipB fusion, lr_scale on encoder + embedding gradients,
+  // two-block image norm (early fusion)
+  int fusion_skip = 0, norm_split = 0;
+  float lr_scale = 1.0f;
   bool logp_valid = false;          // logits holds this forward's log-probs (backward overwrites them with d logits)
   bool hp_valid[4] = {false, false, false, false};   // hp[l] holds this step's h planes (persistent forward ran)
   bool dap_valid = false;                            // dap holds the current layer's da planes

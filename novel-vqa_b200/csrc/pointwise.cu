@@ -49,35 +49,41 @@ int embed_fwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float*
 // ------------------------------------------------------------------------------------------------
 // one CTA per image row: sum of squares by warp shuffles, then scale + dropout
 __global__ void __launch_bounds__(256)
-imgnorm_drop_kernel(const float* __restrict__ fc7, float* __restrict__ vd, Drop d, int I, int img_norm) {
-  __shared__ float red[8];
+imgnorm_drop_kernel(const float* __restrict__ fc7, float* __restrict__ vd, Drop d, int I, int img_norm, int split) {
+  // split > 0: columns [0, split) and [split, I) are two feature blocks normalised separately
+  // (early fusion, 003_train_ae_based_ef.lua:116-124); split is a multiple of 4
+  __shared__ float red[2][8];
   const int b = blockIdx.x;
   const float* row = fc7 + (int64_t)b * I;
-  float inv = 1.0f;
+  float inv0 = 1.0f, inv1 = 1.0f;
+  const int cut = split > 0 ? split : I;
   if (img_norm) {
-    float ss = 0.f;
+    float s0 = 0.f, s1 = 0.f;
     for (int j = threadIdx.x * 4; j < I; j += 256 * 4) {
       float4 v = LD4(row + j);
-      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      const float q = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      if (j < cut) s0 += q; else s1 += q;
     }
-    ss = warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
     __syncthreads();
-    float tot = 0.f;
+    float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[w];
-    inv = 1.0f / sqrtf(tot);          // no epsilon, as in the reference (:118-119)
+    for (int w = 0; w < 8; ++w) { t0 += red[0][w]; t1 += red[1][w]; }
+    inv0 = 1.0f / sqrtf(t0);          // no epsilon, as in the reference (:118-119)
+    inv1 = split > 0 ? 1.0f / sqrtf(t1) : inv0;
   }
   for (int j = threadIdx.x * 4; j < I; j += 256 * 4) {
     float4 v = LD4(row + j);
     float4 m = drop_at4(d, (uint64_t)b * I + j);
+    const float inv = j < cut ? inv0 : inv1;
     v.x = v.x * inv * m.x; v.y = v.y * inv * m.y; v.z = v.z * inv * m.z; v.w = v.w * inv * m.w;
     ST4(vd + (int64_t)b * I + j, v);
   }
 }
 
-int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm) {
-  imgnorm_drop_kernel<<<B, 256, 0, s>>>(fc7, vd, d, I, img_norm);
+int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm, int split) {
+  imgnorm_drop_kernel<<<B, 256, 0, s>>>(fc7, vd, d, I, img_norm, split);
   NVQA_LAUNCHED();
   return 0;
 }
@@ -147,7 +153,7 @@ int qvec_fwd(cudaStream_t s, const float* const* c_fin, const float* const* h_fi
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-fuse_fwd_kernel(float* __restrict__ qc, float* __restrict__ ic, float* __restrict__ zd, Drop d, int64_t n4) {
+fuse_fwd_kernel(float* __restrict__ qc, float* __restrict__ ic, float* __restrict__ zd, Drop d, int64_t n4, int skip) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 a = LD4(qc + i * 4), b = LD4(ic + i * 4);
@@ -155,12 +161,15 @@ fuse_fwd_kernel(float* __restrict__ qc, float* __restrict__ ic, float* __restric
   b.x = tanhf(b.x); b.y = tanhf(b.y); b.z = tanhf(b.z); b.w = tanhf(b.w);
   float4 m = drop_at4(d, (uint64_t)i * 4);
   ST4(qc + i * 4, a); ST4(ic + i * 4, b);
+  if (skip) {   // netdef.AskipB (misc/netdef.lua:16-25): output = qc + qc * ic
+    b.x += 1.0f; b.y += 1.0f; b.z += 1.0f; b.w += 1.0f;
+  }
   ST4(zd + i * 4, make_float4(a.x * b.x * m.x, a.y * b.y * m.y, a.z * b.z * m.z, a.w * b.w * m.w));
 }
 
-int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C) {
+int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C, int skip) {
   int64_t n4 = (int64_t)B * C / 4;
-  fuse_fwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(qc, ic, zd, d, n4);
+  fuse_fwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(qc, ic, zd, d, n4, skip);
   NVQA_LAUNCHED();
   return 0;
 }
@@ -235,14 +244,14 @@ int loss_reduce(cudaStream_t s, const float* rowloss, float* loss, int n) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fuse_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ qc, const float* __restrict__ ic,
-                float* __restrict__ dqpre, float* __restrict__ dipre, Drop d, int64_t n4) {
+                float* __restrict__ dqpre, float* __restrict__ dipre, Drop d, int64_t n4, int skip) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 g = LD4(dzd + i * 4), a = LD4(qc + i * 4), b = LD4(ic + i * 4), m = drop_at4(d, (uint64_t)i * 4);
   float4 dq, di;
 #define FB(k)                                   \
-  { float dz = g.k * m.k;                       \
-    dq.k = dz * b.k * (1.0f - a.k * a.k);       \
+  { float dz = g.k * m.k;                                          \
+    dq.k = dz * (skip ? b.k + 1.0f : b.k) * (1.0f - a.k * a.k);    \
     di.k = dz * a.k * (1.0f - b.k * b.k); }
   FB(x) FB(y) FB(z) FB(w)
 #undef FB
@@ -250,9 +259,9 @@ fuse_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ qc, con
 }
 
 int fuse_bwd(cudaStream_t s, const float* dzd, const float* qc, const float* ic, float* dqpre, float* dipre,
-             Drop d, int B, int C) {
+             Drop d, int B, int C, int skip) {
   int64_t n4 = (int64_t)B * C / 4;
-  fuse_bwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(dzd, qc, ic, dqpre, dipre, d, n4);
+  fuse_bwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(dzd, qc, ic, dqpre, dipre, d, n4, skip);
   NVQA_LAUNCHED();
   return 0;
 }

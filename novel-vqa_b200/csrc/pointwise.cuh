@@ -8,7 +8,8 @@ namespace nvqa {
 int embed_fwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* WeT, const float* be, float* y,
               Drop d, int B, int T, int E, int V);
 // fc7 L2 row norm (002_train_baseline.lua:117-123) fused with AxB's Dropout on i (misc/netdef.lua:11)
-int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm);
+// split > 0: [0, split) and [split, I) normalised separately (early fusion, 003_train_ae_based_ef.lua:116-124)
+int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm, int split = 0);
 // gate math + cell update of one LSTM layer at time t (misc/LSTM.lua:45-59); pre -> gates in place
 int lstm_gates_fwd(cudaStream_t s, float* pre_t, const float* c_prev, int ldp, float* c_new, float* h_new, int ldn,
                    float* xdrop_next_t, const int32_t* len, Drop d, int t, int T, int B, int H);
@@ -16,13 +17,14 @@ int lstm_gates_fwd(cudaStream_t s, float* pre_t, const float* c_prev, int ldp, f
 int qvec_fwd(cudaStream_t s, const float* const* c_fin, const float* const* h_fin, float* state, float* qd,
              Drop d, int B, int H, int L);
 // qc = tanh(qpre), ic = tanh(ipre) (in place), zd = mz * qc * ic   (misc/netdef.lua:10-12, 002_train_baseline.lua:153)
-int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C);
+// skip = 1: netdef.AskipB (misc/netdef.lua:16-25), output = qc + qc * ic
+int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C, int skip = 0);
 // nn.CrossEntropyCriterion fwd+bwd + torch.max argmax (002_train_baseline.lua:308-310, 004_eval_model.lua:233)
 int softmax_ce(cudaStream_t s, const float* scores, const int32_t* labels, float* dscores, float* rowloss,
                int32_t* argmax, int n, int O, float inv_n);
 int loss_reduce(cudaStream_t s, const float* rowloss, float* loss, int n);
 int fuse_bwd(cudaStream_t s, const float* dzd, const float* qc, const float* ic, float* dqpre, float* dipre,
-             Drop d, int B, int C);
+             Drop d, int B, int C, int skip = 0);
 int mask_inplace(cudaStream_t s, float* x, Drop d, int64_t n);
 // cell backward at time t: writes da_t [B x 4H] and the dc carry
 int lstm_gates_bwd(cudaStream_t s, const float* gates_t, const float* c_prev, const float* c_new,

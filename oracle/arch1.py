@@ -28,6 +28,7 @@ class Arch1Config:
     O: int = 1000       # num_output               :38
     T: int = 26         # buffer_size_q = question matrix width   :136
     p: float = 0.5      # every Dropout on the path uses 0.5      :143,147,152,153
+    fusion_skip: bool = False   # netdef.AskipB instead of netdef.AxB (003_train_ae_based_wp.lua:151)
 
     @property
     def S(self):        # width of the packed LSTM state [c1 h1 c2 h2 ...]  misc/LSTM.lua:21-22,70
@@ -123,8 +124,11 @@ def sort_encoding_right_align(q_ra, lengths):
     return words.astype(np.int64), batch_sizes, sort_index.astype(np.int64), inv.astype(np.int64)
 
 
-def l2_normalize_rows(x):
-    """002_train_baseline.lua:117-123: x / sqrt(sum(x*x, 2)), no epsilon."""
+def l2_normalize_rows(x, split=0):
+    """002_train_baseline.lua:117-123: x / sqrt(sum(x*x, 2)), no epsilon.  split > 0: the column blocks [0, split) and
+    [split, I) are normalised separately (early fusion, 003_train_ae_based_ef.lua:116-124)."""
+    if split:
+        return np.concatenate([l2_normalize_rows(x[:, :split]), l2_normalize_rows(x[:, split:])], axis=1)
     nm = np.sqrt(np.sum(x * x, axis=1, keepdims=True))
     return (x / nm).astype(x.dtype)
 
@@ -253,6 +257,8 @@ def multimodal_forward(cfg, mm, tv_q, fv_im, masks):
     qc = np.tanh(qd @ mm["Wq"].T + mm["bq"])
     ic = np.tanh(vd @ mm["Wv"].T + mm["bv"])
     z = qc * ic
+    if getattr(cfg, "fusion_skip", False):      # netdef.AskipB (misc/netdef.lua:16-25): CAddTable({qc, qc * ic})
+        z = qc + z
     zd = z if masks is None else z * masks["z"]
     scores = zd @ mm["Wc"].T + mm["bc"]
     return scores, (qd, vd, qc, ic, zd)
@@ -265,7 +271,10 @@ def multimodal_backward(cfg, mm, mm_grad, cache, dscores, masks):
     dz = dscores @ mm["Wc"]
     if masks is not None:
         dz = dz * masks["z"]
-    dqpre = dz * ic * (1.0 - qc * qc)
+    dqc = dz * ic
+    if getattr(cfg, "fusion_skip", False):
+        dqc = dqc + dz
+    dqpre = dqc * (1.0 - qc * qc)
     dipre = dz * qc * (1.0 - ic * ic)
     mm_grad["Wq"] += dqpre.T @ qd
     mm_grad["bq"] += dqpre.sum(axis=0)
@@ -362,7 +371,7 @@ def forward(cfg, enc_w, emb_w, mm_w, q_ra, lengths, fv_im, seed=None, dtype=np.f
 
 
 def jdj(cfg, enc_w, emb_w, mm_w, q_ra, lengths, fv_im, labels, seed=None, dtype=np.float32,
-        grad_scale=1.0, clamp=10.0, masks=None):
+        grad_scale=1.0, clamp=10.0, masks=None, lr_scale=1.0):
     """f, gradients of 002_train_baseline.lua:272-335.  Gradients are returned as the three flat
     blocks in the optimiser's order (encoder, embedding, multimodal) (:328), clamped to +-10 (:329).
     ``grad_scale`` (default 1) is the 1/n_ranks factor of the data-parallel extension, applied
@@ -383,6 +392,8 @@ def jdj(cfg, enc_w, emb_w, mm_w, q_ra, lengths, fv_im, labels, seed=None, dtype=
     dy = np.concatenate(dinputs, axis=0)                                                # join_vector :319
     embedding_backward(emb_grad, ctx["words"], ctx["y"], dy, None if masks is None else masks["emb"])  # :320
     grads = [g_enc, g_emb, g_mm]
+    if lr_scale != 1.0:     # join_vector({encoder_adw_q * lr_scale, embedding_dw_q * lr_scale, multimodal_dw})  003_train_ae_based_wp.lua:344
+        grads = [g_enc * dtype(lr_scale), g_emb * dtype(lr_scale), g_mm]
     if grad_scale != 1.0:
         grads = [g * dtype(grad_scale) for g in grads]
     if clamp is not None:

@@ -196,3 +196,31 @@ def test_multiple_choice_select_c_abi_bit_exact():
     got = nv.mc_select(scores, mc)
     want = [A.multiple_choice_select(scores[i], mc[i]) for i in range(n)]
     assert got.tolist() == want
+
+
+def test_trainer_variants_finite_differences_fp64():
+    """AskipB fusion (misc/netdef.lua:16-25) and the lr_scale / two-block-norm variants of 003_train_ae_based_{wp,ef}.lua."""
+    cfg = A.Arch1Config(V=40, E=8, H=8, L=1, I=12, C=8, O=6, T=5, fusion_skip=True)
+    r = np.random.RandomState(0)
+    enc, emb, mm = (r.uniform(-.4, .4, n) for n in (cfg.n_enc, cfg.n_emb, cfg.n_mm))
+    B = 5
+    lens = np.array([5, 3, 1, 4, 2])
+    q = np.zeros((B, cfg.T), dtype=np.int64)
+    for b in range(B):
+        q[b, cfg.T - lens[b]:] = r.randint(1, cfg.V + 1, lens[b])
+    fv = A.l2_normalize_rows(np.abs(r.randn(B, cfg.I)), split=4)
+    assert np.allclose((fv[:, :4] ** 2).sum(1), 1) and np.allclose((fv[:, 4:] ** 2).sum(1), 1)
+    lab = r.randint(1, cfg.O + 1, B)
+    f, g, _, _ = A.jdj(cfg, enc, emb, mm, q, lens, fv, lab, seed=3, dtype=np.float64, clamp=None)
+    eps = 1e-6
+    for w, gw in ((enc, g[0]), (mm, g[2])):
+        for i in r.choice(len(w), 8, replace=False):
+            w[i] += eps
+            fp = A.jdj(cfg, enc, emb, mm, q, lens, fv, lab, seed=3, dtype=np.float64, clamp=None)[0]
+            w[i] -= 2 * eps
+            fm = A.jdj(cfg, enc, emb, mm, q, lens, fv, lab, seed=3, dtype=np.float64, clamp=None)[0]
+            w[i] += eps
+            assert abs((fp - fm) / (2 * eps) - gw[i]) <= 1e-6 + 1e-4 * abs(gw[i])
+    # lr_scale multiplies the encoder and embedding blocks before the clamp, not the multimodal block
+    _, gs, _, _ = A.jdj(cfg, enc, emb, mm, q, lens, fv, lab, seed=3, dtype=np.float64, clamp=None, lr_scale=0.1)
+    assert np.allclose(gs[0], 0.1 * g[0]) and np.allclose(gs[1], 0.1 * g[1]) and np.allclose(gs[2], g[2], rtol=1e-12, atol=0)

@@ -363,3 +363,37 @@ def test_eval_100k_questions_properties():
                                      np.ascontiguousarray(fc7_all[img_list[sl]]))
     assert np.array_equal(again, answers[:1000])
     m.close()
+
+
+@pytest.mark.parametrize("name,prec,tol", [("fp32_simt", 0, FP32_TOL), ("bf16x2", 3, FP32_TOL)])
+def test_trainer_variants_askipb_lrscale_two_block_norm(name, prec, tol):
+    """003_train_ae_based_wp.lua (AskipB, -lr_scale) and 003_train_ae_based_ef.lua (6144-d two-block norm, 1-layer
+    E = 512 LSTM as in the AE-initialised trainers): one training step + update against the oracle."""
+    nvm = nv()
+    cfg = nvm.Arch1Config(V=500, E=64, H=128, L=1, I=96, C=64, O=50, T=9, B=150)
+    oc = ocfg(cfg)
+    oc.fusion_skip = True
+    enc, emb, mm = nvm.synth_params(cfg, seed=11)
+    q, ln, fc7, lab = nvm.synth_batch(cfg, 137, seed=12, min_len=1)
+    fc7 = fc7 + 0.01                                                    # no all-zero feature block
+    split, lr_scale, lr = 32, 0.1, 3e-4
+    f, grads, scores, _ = A.jdj(oc, enc, emb, mm, q, ln, A.l2_normalize_rows(fc7, split=split), lab, seed=5, lr_scale=lr_scale)
+    m = make_model(nvm, cfg, enc, emb, mm, prec)
+    m.set_variant(fusion=nvm.FUSION_ASKIPB, lr_scale=lr_scale, norm_split=split)
+    m.set_batch_host(q, ln, fc7, lab)
+    m.forward(nvm.MODE_TRAIN, 5)
+    assert_close(m.scores(137), scores, tol, "scores (AskipB, two-block norm)")
+    assert abs(m.loss() - f) <= tol * abs(f)
+    m.backward()
+    raw = [m.get_grads(b) for b in (nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL)]
+    for got, want, sc, what in zip(raw, grads, (lr_scale, lr_scale, 1.0), ("encoder", "embedding", "multimodal")):
+        assert_close(np.clip(got * np.float32(sc), -10, 10), want, tol, f"{what} gradient")
+    want_p = []
+    for w, g in zip((enc, emb, mm), grads):
+        w = w.copy()
+        A.rmsprop_update(w, g, np.zeros_like(w), lr)
+        want_p.append(w)
+    m.rmsprop_step(lr)
+    for blk, w0, w1 in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), (enc, emb, mm), want_p):
+        assert_close(m.get_params(blk) - w0, w1 - w0, 50 * tol, "parameter update with lr_scale")
+    m.close()

@@ -96,3 +96,29 @@ def test_autoencoder_to_arch1_conversion():
     # one-hot Linear with this weight == LookupTable gather of the first V rows
     onehot = np.eye(V, dtype=np.float32)[[2, 7]]
     assert np.allclose(onehot @ W.T, lut[[2, 7]])
+
+
+def test_result_json_emission(tmp_path):
+    """004_eval_model.lua:248-273: OpenEnded / MultipleChoice result files; 004_eval_model_lf.lua late fusion."""
+    import json
+
+    from novel_vqa_b200 import results
+    r = np.random.default_rng(0)
+    n, O = 20, 30
+    scores = r.standard_normal((n, O)).astype(np.float32)
+    scores[3, 5] = scores[3, 9] = scores[3].max() + 1           # tie: the first maximum wins (torch.max)
+    ix_to_ans = {str(i): f"ans{i}" for i in range(1, O + 1)}
+    mc = np.zeros((n, 18), dtype=np.int32)
+    for i in range(n):
+        mc[i, :4] = r.choice(np.arange(1, O + 1), 4, replace=False)
+    qids = np.arange(1000, 1000 + n)
+    oe, mcp = tmp_path / "oe.json", tmp_path / "mc.json"
+    results.write_results(str(oe), str(mcp), qids, scores, ix_to_ans, mc_ids=mc)
+    a = json.load(open(oe))
+    assert a[3] == {"question_id": 1003, "answer": "ans6"} and len(a) == n
+    b = json.load(open(mcp))
+    for i in range(n):
+        cand = [c for c in mc[i] if c]
+        assert b[i]["answer"] == f"ans{cand[int(np.argmax([scores[i, c - 1] for c in cand]))]}"
+    lf = results.late_fusion_scores(scores, 2 * scores, 0.25, 0.75)
+    assert lf.dtype == np.float64 and np.allclose(lf, 1.75 * scores, rtol=1e-6)
