@@ -66,7 +66,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
                    float* __restrict__ h, __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
-                   const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg) {
+                   const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg,
+                   int b0, int bend) {
+  // this launch covers batch rows [b0, bend) (row stride of all buffers stays B): batches of more than 8 tiles are
+  // processed as consecutive windows, each a full persistent launch
   extern __shared__ uint8_t smem_raw[];
   __shared__ long long fst[32];
 #define F_STAMP(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && t >= 8 && t < 12) fst[(t - 8) * 8 + (slot)] = clock64(); } while (0)
@@ -84,7 +87,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
   float* tbuf = reinterpret_cast<float*>(smem_raw + (r0 - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u0 = blockIdx.x * 32, m0 = blockIdx.y * 64;
+  const int u0 = blockIdx.x * 32, m0 = b0 + blockIdx.y * 64;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
@@ -194,7 +197,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
     const int et = threadIdx.x - 64;              // 0..255: after the transpose, thread = (batch row n, unit group ug)
     const int n = et >> 2, ug = et & 3;
     const int b = m0 + n;
-    const bool rowok = b < B;
+    const bool rowok = b < bend;
     const int mylen = rowok ? (len ? len[b] : T) : 0;
     const int uo = u0 + 8 * ug;
     if (P >= 2) {
@@ -704,7 +707,8 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
                    const float* __restrict__ dh_above, Drop drop, float* __restrict__ dasum,
                    __nv_bfloat16* __restrict__ dap, long long dap_plane, float* __restrict__ dh_init,
                    float* __restrict__ dc_init, const int32_t* __restrict__ len, int T, int B, int H, int KB,
-                   unsigned int* counter, int dbg) {
+                   unsigned int* counter, int dbg, int b0, int bend) {
+  // this launch covers batch rows [b0, bend) (row stride of all buffers stays B)
   extern __shared__ uint8_t smem_raw[];
   __shared__ long long stamps[32];
   const uint32_t raw = smem_u32(smem_raw);
@@ -723,7 +727,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
   float* tbuf = reinterpret_cast<float*>(smem_raw + (r0 - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = blockIdx.x * 128, ks = blockIdx.y, m0 = blockIdx.z * 64;
+  const int c0 = blockIdx.x * 128, ks = blockIdx.y, m0 = b0 + blockIdx.z * 64;
   const unsigned int G = gridDim.x * gridDim.y;                          // CTAs of one batch-tile group
   const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
   counter += 32 * blockIdx.z;                                            // one 128-byte line per group
@@ -867,7 +871,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       const int li = et + 256 * n, rl = 16 * ks + (li >> 5), cl = (li & 31) * 4;
       toff[n] = (uint32_t)(rl * V2_BPITCH + cl) * 4u;
       bq[n] = m0 + rl;
-      valid[n] = bq[n] < B;
+      valid[n] = bq[n] < bend;
       if (!valid[n]) bq[n] = 0;
       ucol[n] = c0 + cl;
       first_t[n] = valid[n] ? (len ? T - len[bq[n]] : 0) : T;
@@ -1063,8 +1067,8 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     NVQA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   }
   const int KB = H / 64;
-  dim3 grid(H / 32, ceil_div(B, 64));
-  if ((int)(grid.x * grid.y) > num_sms) return -1;
+  const int tiles = ceil_div(B, 64), max_tiles = std::min(8, num_sms / (H / 32));
+  if (max_tiles < 1) return -1;
   const size_t ring = (size_t)V2_STAGES * P * 8192 + (P == 1 ? 2 * 8192 : 0);
   const size_t smem = (size_t)KB * 16384 + ring + 1024 + 256;
   if (ring < (size_t)64 * V2_TPITCH * 4 || smem > (size_t)max_smem) return -1;
@@ -1076,40 +1080,46 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 32, &mapW));
   if (hp_plane_rows <= 0) hp_plane_rows = (long long)(T + 1) * B;
   NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 64, &mapH, hp_plane_rows * H, P));
-  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
   long long hp_plane = hp_plane_rows * H;
   const __nv_bfloat16* w1 = wp;                                    // the TMEM-resident plane: plane 0 (plane 1 goes to SMEM)
   int KBv = KB;
   static const int dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
   int dbgv = dbg;
-  void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter, &dbgv};
   static int use_cl = -1;
   if (use_cl < 0) { const char* e = getenv("NVQA_LSTM_CLUSTER16"); use_cl = e ? atoi(e) : 0; }   // measured on B200: only part of the 8 clusters of 16 is co-resident (0.82 ms vs 0.48 ms)
-  if (use_cl && grid.x == 16) {
-    // one 16-CTA cluster per batch tile: hardware cluster barrier per step, plain (non-cooperative) launch
-    const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true> : (const void*)lstm_fwd_v2_kernel<1, true>;
-    NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    cudaLaunchConfig_t cc = {};
-    cc.gridDim = grid; cc.blockDim = dim3(V2_THREADS); cc.dynamicSmemBytes = smem; cc.stream = s;
-    cudaLaunchAttribute ca;
-    ca.id = cudaLaunchAttributeClusterDimension;
-    ca.val.clusterDim.x = 16; ca.val.clusterDim.y = 1; ca.val.clusterDim.z = 1;
-    cc.attrs = &ca; cc.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelExC(&cc, fc, args);
-    if (le == cudaSuccess) { ++g_launches; return 0; }
-    (void)cudaGetLastError();
-    use_cl = 0;                                   // 16-CTA clusters are not schedulable here: counter barrier below
+  // batches of more than 8 tiles (512 rows) run as consecutive windows of the batch, each a full persistent launch
+  for (int tile0 = 0; tile0 < tiles; tile0 += max_tiles) {
+    int b0 = tile0 * 64, bend = std::min(B, (tile0 + max_tiles) * 64);
+    dim3 grid(H / 32, ceil_div(bend - b0, 64));
+    NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
+    void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter, &dbgv,
+                    &b0, &bend};
+    if (use_cl && grid.x == 16) {
+      // one 16-CTA cluster per batch tile: hardware cluster barrier per step, plain (non-cooperative) launch
+      const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true> : (const void*)lstm_fwd_v2_kernel<1, true>;
+      NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cudaLaunchConfig_t cc = {};
+      cc.gridDim = grid; cc.blockDim = dim3(V2_THREADS); cc.dynamicSmemBytes = smem; cc.stream = s;
+      cudaLaunchAttribute ca;
+      ca.id = cudaLaunchAttributeClusterDimension;
+      ca.val.clusterDim.x = 16; ca.val.clusterDim.y = 1; ca.val.clusterDim.z = 1;
+      cc.attrs = &ca; cc.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelExC(&cc, fc, args);
+      if (le == cudaSuccess) { ++g_launches; continue; }
+      (void)cudaGetLastError();
+      use_cl = 0;                                   // 16-CTA clusters are not schedulable here: counter barrier below
+    }
+    const void* fn = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, false> : (const void*)lstm_fwd_v2_kernel<1, false>;
+    NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeCooperative; attr.val.cooperative = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    NVQA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    ++g_launches;
   }
-  const void* fn = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, false> : (const void*)lstm_fwd_v2_kernel<1, false>;
-  NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeCooperative; attr.val.cooperative = 1;
-  cfg.attrs = &attr; cfg.numAttrs = 1;
-  NVQA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
-  ++g_launches;
   return 0;
 }
 
@@ -1134,8 +1144,8 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     NVQA_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   }
   const int KB = H / 64;
-  dim3 grid(H / 128, 4, ceil_div(B, 64));
-  if ((int)(grid.x * grid.y * grid.z) > num_sms) return -1;
+  const int tiles = ceil_div(B, 64), max_tiles = std::min(8, num_sms / (4 * (H / 128)));
+  if (max_tiles < 1) return -1;
   const size_t tile = (size_t)64 * V2_BPITCH * 4;
   size_t ring = (size_t)V2_STAGES * P * 8192;
   if (ring < tile) ring = tile + 1024 - tile % 1024;
@@ -1149,53 +1159,67 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 64, &mapW));              // MN-major A: boxes of 64 k-rows x 64 columns
   if (dap_plane_rows <= 0) dap_plane_rows = (long long)T * B;
   NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 64, &mapDA, dap_plane_rows * 4 * H));
-  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
   long long dap_plane = dap_plane_rows * 4 * H;
   const __nv_bfloat16* w1 = wp + (size_t)4 * H * pitch;
   int KBv = KB;
-  void* args[] = {&mapDA, &mapW, &w1, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dhbuf,
-                  &dc_init, &len, &T, &B, &H, &KBv, &counter};
   static int use_v3 = -1;
   if (use_v3 < 0) { const char* e = getenv("NVQA_LSTM_V3"); use_v3 = e ? atoi(e) : 1; }
   if (use_v3) {
-    // generation 3: 4-CTA clusters over the K-splits, split-K reduction through distributed shared memory
-    NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.z, s));
+    // generation 3: 4-CTA clusters over the K-splits, split-K reduction through distributed shared memory;
+    // batches of more than 8 tiles (512 rows) run as consecutive windows, each a full persistent launch
     static const int dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
     int dbgv = dbg;
     CUtensorMap mapDA3;                            // both planes of a da tile in one TMA box
     NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 64, &mapDA3, dap_plane_rows * 4 * H, P));
     const __nv_bfloat16* wt = wp;                  // generation 3 keeps plane 0 in TMEM and plane 1 in shared memory
-    void* a3[] = {&mapDA3, &mapW, &wt, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dh_init,
-                  &dc_init, &len, &T, &B, &H, &KBv, &counter, &dbgv};
     const void* f3 = P == 2 ? (const void*)lstm_bwd_v3_kernel<2> : (const void*)lstm_bwd_v3_kernel<1>;
     NVQA_CUDA(cudaFuncSetAttribute(f3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg3 = {};
-    cfg3.gridDim = grid; cfg3.blockDim = dim3(V2_THREADS); cfg3.dynamicSmemBytes = smem; cfg3.stream = s;
-    cudaLaunchAttribute at3[2];
-    at3[0].id = cudaLaunchAttributeClusterDimension;
-    at3[0].val.clusterDim.x = 1; at3[0].val.clusterDim.y = 4; at3[0].val.clusterDim.z = 1;
-    at3[1].id = cudaLaunchAttributeCooperative; at3[1].val.cooperative = 1;
-    // Nsight Compute cannot replay a launch that is both cooperative and clustered (driver: LaunchFailed): profiling runs
-    // set NVQA_LSTM_NOCOOP=1, which drops only the co-residency CHECK (the grid is 128 CTAs on 148 idle SMs either way)
     static const bool nocoop = getenv("NVQA_LSTM_NOCOOP") != nullptr;
-    cfg3.attrs = at3; cfg3.numAttrs = nocoop ? 1 : 2;
-    cudaError_t le = cudaLaunchKernelExC(&cfg3, f3, a3);
-    if (le == cudaSuccess && dbg) {
-      long long hb[64];
-      NVQA_CUDA(cudaStreamSynchronize(s));
-      NVQA_CUDA(cudaMemcpyFromSymbol(hb, g_v3dbg, sizeof(hb)));
-      long long base = hb[3];
-      for (int i = 0; i < 16; ++i) base = std::min(base, hb[i * 4 + 3]);
-      fprintf(stderr, "lstm_bwd_v3 group 0, step t=10 (ns after the first CTA's mma_done): cta(col,ks) | mma_done phaseA_alldone arrived open(for t=9)\n");
-      for (int i = 0; i < 16; ++i)
-        fprintf(stderr, "  %2d (%d,%d) | %6lld %6lld %6lld %6lld\n", i, i % 4, i / 4, hb[i * 4 + 3] - base, hb[i * 4 + 2] - base, hb[i * 4 + 0] - base,
-                hb[i * 4 + 1] - base);
+    bool ok = true;
+    for (int tile0 = 0; tile0 < tiles && ok; tile0 += max_tiles) {
+      int b0 = tile0 * 64, bend = std::min(B, (tile0 + max_tiles) * 64);
+      dim3 grid(H / 128, 4, ceil_div(bend - b0, 64));
+      NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.z, s));
+      void* a3[] = {&mapDA3, &mapW, &wt, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dh_init,
+                    &dc_init, &len, &T, &B, &H, &KBv, &counter, &dbgv, &b0, &bend};
+      cudaLaunchConfig_t cfg3 = {};
+      cfg3.gridDim = grid; cfg3.blockDim = dim3(V2_THREADS); cfg3.dynamicSmemBytes = smem; cfg3.stream = s;
+      cudaLaunchAttribute at3[2];
+      at3[0].id = cudaLaunchAttributeClusterDimension;
+      at3[0].val.clusterDim.x = 1; at3[0].val.clusterDim.y = 4; at3[0].val.clusterDim.z = 1;
+      at3[1].id = cudaLaunchAttributeCooperative; at3[1].val.cooperative = 1;
+      // Nsight Compute cannot replay a launch that is both cooperative and clustered (driver: LaunchFailed): profiling
+      // runs set NVQA_LSTM_NOCOOP=1, which drops only the co-residency CHECK (128 CTAs on 148 idle SMs either way)
+      cfg3.attrs = at3; cfg3.numAttrs = nocoop ? 1 : 2;
+      cudaError_t le = cudaLaunchKernelExC(&cfg3, f3, a3);
+      if (le != cudaSuccess) {
+        (void)cudaGetLastError();                   // the clusters could not be made co-resident: generation 2 below
+        if (tile0 > 0) { set_error("lstm_bwd_v3: cluster launch failed in the middle of a batch"); return 1; }
+        ok = false;
+        break;
+      }
+      ++g_launches;
+      if (dbg && tile0 == 0) {
+        long long hb[64];
+        NVQA_CUDA(cudaStreamSynchronize(s));
+        NVQA_CUDA(cudaMemcpyFromSymbol(hb, g_v3dbg, sizeof(hb)));
+        long long base = hb[3];
+        for (int i = 0; i < 16; ++i) base = std::min(base, hb[i * 4 + 3]);
+        fprintf(stderr, "lstm_bwd_v3 group 0, step t=10 (ns after the first CTA's mma_done): cta(col,ks) | mma_done phaseA_alldone arrived open(for t=9)\n");
+        for (int i = 0; i < 16; ++i)
+          fprintf(stderr, "  %2d (%d,%d) | %6lld %6lld %6lld %6lld\n", i, i % 4, i / 4, hb[i * 4 + 3] - base, hb[i * 4 + 2] - base,
+                  hb[i * 4 + 0] - base, hb[i * 4 + 1] - base);
+      }
     }
-    if (le == cudaSuccess) { ++g_launches; return 0; }
-    (void)cudaGetLastError();                     // the clusters could not be made co-resident: generation 2 below
+    if (ok) return 0;
     use_v3 = 0;
-    NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
   }
+  // generation 2 (no clusters): only for batches that fit one launch
+  dim3 grid(H / 128, 4, tiles);
+  if ((int)(grid.x * grid.y * grid.z) > num_sms) return -1;
+  NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+  void* args[] = {&mapDA, &mapW, &w1, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dhbuf,
+                  &dc_init, &len, &T, &B, &H, &KBv, &counter};
   const void* fn = P == 2 ? (const void*)lstm_bwd_v2_kernel<2> : (const void*)lstm_bwd_v2_kernel<1>;
   NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
