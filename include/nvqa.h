@@ -143,6 +143,11 @@ int nvqa_logprobs_get(nvqa_model* m, int32_t step, float* host_dst);
  * nvqa_dp_rmsprop_step); norm_split > 0: with img_norm = 1 the feature columns [0, norm_split) and [norm_split, I) are
  * L2-normalised separately (early fusion of two CNN features, 003_train_ae_based_ef.lua:74,116-124). */
 int nvqa_set_variant(nvqa_model* m, int32_t fusion, float lr_scale, int32_t norm_split);
+/* arch 2 / 3: on = 1 reproduces the literal reference, whose per-step lookup-table clones share `weight` but not
+ * `gradWeight` with the module that parameters() exposes (misc/AutoEncoder_text_nostart.lua:64-66,
+ * misc/Encoder_lstm.lua:53): the LookupTable block of the gradient is zeroed before the optimizer (it then only sees
+ * weight decay).  Default 0 = the evident intent (gradient accumulated over all steps). */
+int nvqa_set_lookup_grad_literal(nvqa_model* m, int32_t on);
 int nvqa_scores_get(nvqa_model* m, float* host_dst);             /* [B x O]                       */
 int nvqa_argmax_get(nvqa_model* m, int32_t* host_dst);           /* torch.max(scores,2), 1-based  */
 int nvqa_state_get(nvqa_model* m, float* host_dst);              /* final LSTM state tv_q [B x 2LH] */

@@ -288,6 +288,9 @@ class Arch2Model(Arch1Model):
     def set_steps(self, steps):
         _lib.check(self.lib.nvqa_set_steps(self.handle, steps))
 
+    def set_lookup_grad_literal(self, on=True):
+        _lib.check(self.lib.nvqa_set_lookup_grad_literal(self.handle, 1 if on else 0))
+
     def set_masks(self, lstm=None, z=None):
         super().set_masks(emb=None, lstm=lstm, q=None, i=None, z=z)
 
@@ -331,6 +334,9 @@ class AEModel(Arch1Model):
         self._keep = [seq]
         _lib.check(self.lib.nvqa_set_batch(self.handle, seq.ptr, None, None, None, B))
         _lib.check(self.lib.nvqa_set_steps(self.handle, tmax))
+
+    def set_lookup_grad_literal(self, on=True):
+        _lib.check(self.lib.nvqa_set_lookup_grad_literal(self.handle, 1 if on else 0))
 
     def adam_step(self, lr=1e-5, beta1=0.8, beta2=0.999, eps=1e-8, wd=1e-6, clamp=0.1, grad_scale=1.0):
         _lib.check(self.lib.nvqa_adam_step(self.handle, lr, beta1, beta2, eps, wd, clamp, grad_scale))

@@ -54,6 +54,7 @@ static int gemm_raw(nvqa_model* m, bool ak, bool bk, int M, int N, int K, const 
                     int ldb, float* C, int ldc, bool beta, const float* b0, const float* b1);
 // cache class of a GEMM operand's bf16 planes: 1 = weight (inside the flat parameter vector: cached for the whole step),
 // 2 = forward activation that is written once per forward and read again by the backward GEMMs, 0 = transient
+static int drop_lookup_grad(nvqa_model* m);
 static int cache_class(const nvqa_model* m, const float* p) {
   if (p >= m->params && p < m->params + m->P) return 1;
   for (const auto& r : m->act_ranges)
@@ -962,6 +963,7 @@ extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   umma_workspace_invalidate(m->ws);     // the weights change: their cached bf16 planes are stale
   ProfScope ps(m, CAT_OPT, 0);
+  NVQA_TRY(drop_lookup_grad(m));
   if (m->cfg.arch == 1 && m->lr_scale != 1.0f) {
     // gradients = join{encoder_dw * lr_scale, embedding_dw * lr_scale, multimodal_dw}, then clamp, then rmsprop
     // (003_train_ae_based_wp.lua:344-346): the scale is folded into the pre-clamp gradient scale of blocks 0 and 1
@@ -970,6 +972,19 @@ extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps
     return clamp_rmsprop(m->stream, m->params + n01, m->grads + n01, m->rms + n01, m->P - n01, lr, alpha, eps, wd, clamp, gscale);
   }
   return clamp_rmsprop(m->stream, m->params, m->grads, m->rms, m->P, lr, alpha, eps, wd, clamp, gscale);
+}
+
+// The reference's createClones shares the LookupTable weight, but not its gradWeight, with the module whose gradient
+// parameters() returns (AutoEncoder_text_nostart.lua:64-66, Encoder_lstm.lua:53): literally, that gradient block stays zero.
+extern "C" int nvqa_set_lookup_grad_literal(nvqa_model* m, int32_t on) {
+  NVQA_CHECK(m && (m->cfg.arch == 2 || m->cfg.arch == 3), "nvqa_set_lookup_grad_literal applies to arch 2 / 3 models");
+  m->lookup_grad_literal = on != 0;
+  return 0;
+}
+static int drop_lookup_grad(nvqa_model* m) {
+  if (m->lookup_grad_literal && m->glookup)
+    NVQA_CUDA(cudaMemsetAsync(m->glookup, 0, (size_t)(m->cfg.V + 1) * m->cfg.E * 4, m->stream));
+  return 0;
 }
 
 extern "C" int nvqa_set_variant(nvqa_model* m, int32_t fusion, float lr_scale, int32_t norm_split) {
@@ -988,6 +1003,7 @@ extern "C" int nvqa_adam_step(nvqa_model* m, float lr, float beta1, float beta2,
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   umma_workspace_invalidate(m->ws);
   ProfScope ps(m, CAT_OPT, 0);
+  NVQA_TRY(drop_lookup_grad(m));
   ++m->adam_t;
   return clamp_adam(m->stream, m->params, m->grads, m->adam_m, m->rms, m->P, lr, beta1, beta2, eps, wd, clamp, gscale, m->adam_t);
 }

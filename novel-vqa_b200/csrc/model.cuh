@@ -71,6 +71,7 @@ struct nvqa_model {
   // two-block image norm (early fusion)
   int fusion_skip = 0, norm_split = 0;
   float lr_scale = 1.0f;
+  bool lookup_grad_literal = false;   // arch 2 / 3: drop the LookupTable gradient like the literal reference
   bool logp_valid = false;          // logits holds this forward's log-probs (backward overwrites them with d logits)
   bool hp_valid[4] = {false, false, false, false};   // hp[l] holds this step's h planes (persistent forward ran)
   bool dap_valid = false;                            // dap holds the current layer's da planes

@@ -138,3 +138,26 @@ def test_full_size_config5_step():
     m.adam_step()
     m.sync()
     m.close()
+
+
+def test_literal_lookup_gradient_mode():
+    """nvqa_set_lookup_grad_literal(1): the LookupTable only sees the weight-decay term (the literal reference, whose
+    clones do not share gradWeight with the module parameters() exposes); encoder / decoder updates are unchanged."""
+    nvm = nv()
+    g = np.load(GOLD)
+    ocfg = AE.AEConfig(**{k: int(g["cfg_" + k]) for k in ("V", "E", "H", "L", "T")})
+    B = g["seq"].shape[0]
+    e2, d2, l2 = g["enc"].copy(), g["dec"].copy(), g["lut"].copy()
+    AE.train_step(ocfg, e2, d2, l2, [{}, {}, {}], g["seq"], lr=1e-3, seed=int(g["seed"]), literal_lookup_grad=True)
+    m = make(nvm, nvm.AEConfig(V=ocfg.V, E=ocfg.E, H=ocfg.H, L=ocfg.L, T=ocfg.T, B=B), g["enc"], g["dec"], g["lut"], 3)
+    m.set_lookup_grad_literal(True)
+    m.set_batch_host(g["seq"], g["lengths"])
+    m.forward(nvm.MODE_TRAIN, int(g["seed"]))
+    m.backward()
+    m.adam_step(lr=1e-3)
+    for blk, key, want in ((nvm.BLOCK_AE_ENCODER, "enc", e2), (nvm.BLOCK_AE_DECODER, "dec", d2), (nvm.BLOCK_AE_LOOKUP, "lut", l2)):
+        # the first Adam step is lr * g / (|g| + eps'): ill-conditioned element-wise where |g| is tiny, so the update is
+        # checked in rel-L2 (1e-3) with a loose element-wise bound
+        e2, em = rel_err(m.get_params(blk) - g[key], want - g[key])
+        assert e2 <= 1e-3 and em <= 2e-2, f"{key} update (literal lookup gradient): rel-l2 {e2:.3e}, rel-max {em:.3e}"
+    m.close()

@@ -399,3 +399,30 @@ def test_trainer_variants_askipb_lrscale_two_block_norm(name, prec, tol):
         big = np.abs(g) > 1e-5
         assert_close((m.get_params(blk) - w0)[big], (w1 - w0)[big], 50 * tol, "parameter update with lr_scale")
     m.close()
+
+
+@pytest.mark.parametrize("lens", [[1], [26], [26, 1], [3, 1, 2]])
+def test_edge_batches_single_row_and_single_token(lens):
+    """B = 1 and one-token questions (the shortest inputs the reference's packed recurrence accepts)."""
+    nvm = nv()
+    B = len(lens)
+    cfg = nvm.Arch1Config(V=300, E=24, H=64, L=2, I=96, C=64, O=50, T=26, B=4)
+    oc = ocfg(cfg)
+    enc, emb, mm = nvm.synth_params(cfg, seed=21)
+    q, _, fc7, lab = nvm.synth_batch(cfg, B, seed=22)
+    ln = np.array(lens, dtype=np.int32)
+    q = nvm.right_align(np.where(np.arange(cfg.T)[None, :] < ln[:, None], q, 0).astype(np.int32), ln)
+    words, sizes, si, inv = A.sort_encoding_right_align(q, ln)
+    pw, ps, psi, pinv = nvm.pack_batch(q, ln)
+    assert np.array_equal(pw, words) and np.array_equal(ps, sizes) and np.array_equal(psi, si + 1) and np.array_equal(pinv, inv + 1)
+    f, grads, scores, _ = A.jdj(oc, enc, emb, mm, q, ln, A.l2_normalize_rows(fc7), lab, seed=9)
+    for prec, tol in ((nvm.PREC_FP32_SIMT, FP32_TOL), (nvm.PREC_BF16X2, FP32_TOL)):
+        m = make_model(nvm, cfg, enc, emb, mm, prec)
+        m.set_batch_host(q, ln, fc7, lab)
+        m.forward(nvm.MODE_TRAIN, 9)
+        assert_close(m.scores(B), scores, tol, "scores")
+        assert np.array_equal(m.argmax(B), A.argmax_first(scores))
+        m.backward()
+        for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
+            assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, "gradient")
+        m.close()
