@@ -371,6 +371,8 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
     reg(m->y, (size_t)N * E);
     for (int l = 1; l < L; ++l) reg(m->xdrop[l], (size_t)N * H);
     reg(m->qd, (size_t)B * S); reg(m->vd, (size_t)B * I); reg(m->zd, (size_t)B * C2);
+    // written once per step before their GEMMs and read by two of them (weight gradient and input gradient)
+    if (!a2) { reg(m->dscores, (size_t)B * O); reg(m->dqpre, (size_t)B * C2); }
     if (a3) reg(m->hd, (size_t)(T + 1) * B * H);
     NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (96 << 20), stat, act + (act >> 3) + (1 << 20)));
   }
@@ -683,12 +685,31 @@ static int forward_arch3(nvqa_model* m) {
   return 0;
 }
 
+// Every weight matrix a training / eval step multiplies with, for the one-launch plane split at the start of a forward.
+static int presplit_step_weights(nvqa_model* m) {
+  if (!m->planes || !m->ws) return 0;
+  const nvqa_config& c = m->cfg;
+  const float* src[16]; int rows[16], K[16], n = 0;
+  auto add = [&](const float* p, int r, int k) { if (p && n < 16) { src[n] = p; rows[n] = r; K[n] = k; ++n; } };
+  for (int l = 0; l < c.L; ++l) { add(m->lw[l].Wi, 4 * c.H, l == 0 ? c.E : c.H); add(m->lw[l].Wh, 4 * c.H, c.H); }
+  if (c.arch == 3) {
+    for (int l = 0; l < c.L; ++l) { add(m->lw2[l].Wi, 4 * c.H, l == 0 ? c.E : c.H); add(m->lw2[l].Wh, 4 * c.H, c.H); }
+    add(m->Wd, c.V + 1, c.H);
+  } else if (c.arch == 2) {
+    add(m->Wcnn, c.E, c.I); add(m->Wc, c.O, c.H);
+  } else {
+    add(m->Wq, c.C, m->S); add(m->Wv, c.C, c.I); add(m->Wc, c.O, c.C);
+  }
+  return presplit_weights(m->ws, m->stream, m->planes, src, rows, K, n);
+}
+
 extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   NVQA_CHECK(m && m->q, "nvqa_forward: no batch set");
   NVQA_CHECK(mode == NVQA_MODE_EVAL || mode == NVQA_MODE_TRAIN, "bad mode");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   m->mode = mode; m->seed = seed;
   umma_workspace_new_forward(m->ws);        // this forward rewrites the activations: their cached planes are stale
+  NVQA_TRY(presplit_step_weights(m));       // all weight matrices -> bf16 planes in one launch (no-op while they are cached)
   if (m->cfg.arch == 3) return forward_arch3(m);
   if (m->cfg.arch == 2) return forward_arch2(m);
   const nvqa_config& c = m->cfg;

@@ -19,6 +19,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <algorithm>
+
 #include "umma_engine.cuh"
 #include "umma_ptx.cuh"
 
@@ -245,6 +247,40 @@ split_planes_kernel(const float* __restrict__ src, int rows, int K, int ld, int 
   }
 }
 
+// several matrices in ONE launch (all weight matrices of a step): blockIdx.y selects the job
+struct SplitJob { const float* src; __nv_bfloat16* dst; int rows, K, ld, Kp; };
+struct SplitJobs { SplitJob j[16]; };
+template <int P>
+__global__ void __launch_bounds__(256) split_planes_batched_kernel(SplitJobs jobs) {
+  const SplitJob jb = jobs.j[blockIdx.y];
+  const int K4 = jb.Kp >> 2;
+  const int64_t total = (int64_t)jb.rows * K4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K4) * 4;
+    const int64_t row = i / K4;
+    const float* s = jb.src + row * jb.ld + k;
+    float x[4];
+    if (k + 3 < jb.K && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+      float4 t = *reinterpret_cast<const float4*>(s);
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = (k + j < jb.K) ? s[j] : 0.f;
+    }
+    __nv_bfloat16 p[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split3(x[j], p[0][j], p[1][j], p[2][j]);
+    const int64_t plane = (int64_t)jb.rows * jb.Kp;
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      uint2 o;
+      o.x = (uint32_t)__bfloat16_as_ushort(p[q][0]) | ((uint32_t)__bfloat16_as_ushort(p[q][1]) << 16);
+      o.y = (uint32_t)__bfloat16_as_ushort(p[q][2]) | ((uint32_t)__bfloat16_as_ushort(p[q][3]) << 16);
+      *reinterpret_cast<uint2*>(jb.dst + q * plane + row * jb.Kp + k) = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -332,6 +368,34 @@ int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, i
   else split_planes_kernel<3><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
   NVQA_LAUNCHED();
   *out = dst;
+  return 0;
+}
+
+// Pre-split up to 16 weight matrices (row-major fp32 [rows x K], leading dimension K) into cached planes with ONE launch;
+// matrices already cached are skipped.  Called at the start of a forward pass: the per-GEMM prepare_planes then hits.
+int presplit_weights(UmmaWorkspace* ws, cudaStream_t s, int P, const float* const* src, const int* rows, const int* K, int n) {
+  SplitJobs jobs;
+  int nj = 0;
+  int64_t most = 0;
+  for (int i = 0; i < n && nj < 16; ++i) {
+    if (!src[i]) continue;
+    PlaneKey key{src[i], rows[i], K[i], K[i], 1, P};
+    if (ws->cache.find(key) != ws->cache.end()) continue;
+    const int Kp = (K[i] + 7) & ~7;
+    const size_t need = ((size_t)P * rows[i] * Kp * 2 + 1023) & ~(size_t)1023;
+    if (ws->static_top + need > ws->static_bytes) continue;           // no room: split per GEMM as before
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ws->base + ws->static_top);
+    ws->static_top += need;
+    ws->cache[key] = dst;
+    jobs.j[nj++] = SplitJob{src[i], dst, rows[i], K[i], K[i], Kp};
+    most = std::max<int64_t>(most, (int64_t)rows[i] * (Kp / 4));
+  }
+  if (!nj) return 0;
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(most, 256), 2048), nj);
+  if (P == 1) split_planes_batched_kernel<1><<<grid, 256, 0, s>>>(jobs);
+  else if (P == 2) split_planes_batched_kernel<2><<<grid, 256, 0, s>>>(jobs);
+  else split_planes_batched_kernel<3><<<grid, 256, 0, s>>>(jobs);
+  NVQA_LAUNCHED();
   return 0;
 }
 
