@@ -243,14 +243,19 @@ def run_ours(args):
         top = max(gate, key=lambda c: c["ms"])
         ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
         gate_ach = sum(c["flops"] for c in gate) / (sum(c["ms"] for c in gate) * 1e-3) / 1e12
-        traffic = None
+        traffic, ncu_tensor = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top["kernel"])
+            tj = json.load(open(tpath))
+            traffic = tj.get(top["kernel"])
+            ncu_tensor = tj.get("_tensor_pipe_pct_of_elapsed", {}).get(top["kernel"])
+        issued = {"bf16x2": 3, "bf16x3": 6, "bf16": 1, "fp32_simt": 1}[args.precision]
         roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": ach, "peak": pk["tf_sustained"],
                 "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic,
                 "peak_source": f"bf16 dense cuBLAS, sustained, {pk['source']} (MEASURED_PEAKS.json)",
                 "launch_ms": top["ms"] / top["launches"], "launches_per_step": top["launches"] // nprof,
+                "mma_per_algorithmic_product": issued, "frac_issued": ach * issued / pk["tf_sustained"],
+                "ncu_tensor_pipe_pct_of_elapsed": ncu_tensor,
                 "all_gate_gemms": {"achieved": gate_ach, "frac": gate_ach / pk["tf_sustained"]},
                 "gemm_ms_per_step": gemm_ms_per_step,
                 "classes": [{"kernel": c["kernel"], "ms_per_step": c["ms"] / nprof,

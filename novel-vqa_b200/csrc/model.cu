@@ -373,7 +373,10 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
     reg(m->qd, (size_t)B * S); reg(m->vd, (size_t)B * I); reg(m->zd, (size_t)B * C2);
     // written once per step before their GEMMs and read by two of them (weight gradient and input gradient)
     if (!a2) { reg(m->dscores, (size_t)B * O); reg(m->dqpre, (size_t)B * C2); }
-    if (a3) reg(m->hd, (size_t)(T + 1) * B * H);
+    if (a3) {
+      reg(m->hd, (size_t)(T + 1) * B * H);
+      reg(m->logits, (size_t)(T + 1) * B * m->ldl);     // d logits: operand of both the wgrad and the dgrad vocabulary GEMM
+    }
     NVQA_TRY(umma_workspace_create(&m->ws, elems * 6 + (96 << 20), stat, act + (act >> 3) + (1 << 20)));
   }
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
