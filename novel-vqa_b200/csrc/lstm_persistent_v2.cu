@@ -32,6 +32,7 @@ constexpr int V2_THREADS = 320;          // warp 0: TMA, warp 1: MMA, warps 2-9:
 constexpr int V2_EPI = 256;
 constexpr int V2_STAGES = 6;           // bytes in flight set the load rate (latency-bound: 64 KB -> 17 B/clk, 96 KB -> ~26 B/clk)
 constexpr int V2_TPITCH = 132;           // words per row of the transpose tile (128 + 4: conflict-free 128-bit reads)
+constexpr int V2_SPLIT_STAGES = 8;       // NS = 2: ring of 8 stages x 8 KB = one whole half tile in flight
 
 __device__ __forceinline__ void v2_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void v2_arrive(unsigned int* ctr) {
@@ -61,7 +62,15 @@ __device__ __forceinline__ float v2_tanh(float x) { return 1.0f - __fdividef(2.0
 __device__ __forceinline__ void v2_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void v2_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-template <int P, bool CL>
+// NS = 2 ("split"): the 64-row batch tile is processed as TWO independent 32-row sub-tiles, software-pipelined: the
+// recurrences of different batch rows do not depend on each other, so each sub-tile has its own step counter, its own
+// accumulator (TMEM columns [32 sub, 32 sub + 32)), its own mbarriers and its own 4 epilogue warps, and the single TMA /
+// MMA warps serve the work items (t, sub) in the fixed order (0,0) (0,1) (1,0) (1,1) ...  While sub-tile 0 runs its
+// epilogue and waits for its group barrier (half of a step's critical path: ~7,000 cycles of latency), sub-tile 1's
+// h_{t-1} tile is loaded and multiplied, and vice versa.  The transpose tile cannot alias the (now busy) ring: it gets
+// its own 33 KB, the ring shrinks to 8 x 8 KB.  Cost: twice as many tcgen05.mma (N = 32), each ~52-80 cycles whatever
+// its N (tools/probes/probe_mma_rate.cu), so the MMA warp becomes the bound: measured 0.486 -> 0.432 ms per step pair.
+template <int P, bool CL, int NS>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
@@ -71,20 +80,31 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B): batches of more than 8 tiles are
   // processed as consecutive windows, each a full persistent launch
   extern __shared__ uint8_t smem_raw[];
-  __shared__ long long fst[32];
-#define F_STAMP(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && t >= 8 && t < 12) fst[(t - 8) * 8 + (slot)] = clock64(); } while (0)
+  __shared__ long long fst[64];
+  // dbg bits (NVQA_LSTM_DEBUG, timing experiments only -- bits 2..32 change the results): 1 = timeline stamps,
+  // 2 = skip the deferred stores, 4 = skip the pre-activation loads, 8 = always load the h tile of step 0 (static data),
+  // 16 = issue no MMAs (commits only: pure TMA rate), 32 = issue no TMA loads (plain arrives: pure MMA rate)
+#define F_STAMP(slot) do { if ((dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && t >= 8 && t < 12) fst[(t - 8) * 16 + (slot)] = clock64(); } while (0)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   constexpr uint32_t W_KB = 128 * 128;                  // one k-block of the W0 slice: 128 rows x 128 B
-  constexpr uint32_t B_PLANE = 64 * 128;                // one plane of one k-block of the h tile: 64 rows x 128 B
+  static_assert(NS == 1 || (NS == 2 && !CL), "sub-tile pipelining uses the counter barrier");
+  constexpr int SUBN = 64 / NS;                         // batch rows per sub-tile (the N of one MMA)
+  constexpr int NST = NS == 1 ? V2_STAGES : V2_SPLIT_STAGES;
+  constexpr int EPG = V2_EPI / NS;                      // epilogue threads per sub-tile
+  constexpr uint32_t B_PLANE = SUBN * 128;              // one plane of one k-block of the h (sub-)tile: SUBN rows x 128 B
   constexpr uint32_t STAGE = P * B_PLANE;
+  constexpr uint32_t RING = NST * STAGE + (NS == 1 && P == 1 ? 2 * STAGE : 0);   // NS = 1, P = 1: ring is 32 KB, the tile needs 33 KB
+  constexpr uint32_t TB_BYTES = NS == 1 ? 0u : (uint32_t)(64 * V2_TPITCH * 4);   // NS = 1: the transpose tile aliases the idle ring
+  static_assert(TB_BYTES % 1024 == 0, "barriers stay 8-byte aligned");
   const uint32_t w0 = base;
-  const uint32_t r0 = w0 + (uint32_t)KB * W_KB;         // B ring (the transpose tile aliases its first 33 KB)
-  const uint32_t bar0 = r0 + V2_STAGES * STAGE + (P == 1 ? 2 * STAGE : 0);   // P = 1: ring is 32 KB, the tile needs 33 KB
-  const uint32_t full0 = bar0, empty0 = bar0 + 8 * V2_STAGES, wfull = bar0 + 16 * V2_STAGES, tfull = wfull + 8,
-                 gobar = wfull + 16, w1bar = wfull + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * V2_STAGES + 32);
-  float* tbuf = reinterpret_cast<float*>(smem_raw + (r0 - raw));
+  const uint32_t r0 = w0 + (uint32_t)KB * W_KB;         // B ring
+  const uint32_t tb0 = NS == 1 ? r0 : r0 + RING;
+  const uint32_t bar0 = r0 + RING + TB_BYTES;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * NST, wfull = bar0 + 16 * NST, tfull = wfull + 8 /* x2 */,
+                 gobar = wfull + 24 /* x2 */, w1bar = wfull + 40;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * NST + 48);
+  float* tbuf = reinterpret_cast<float*>(smem_raw + (tb0 - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * 32, m0 = b0 + blockIdx.y * 64;
@@ -95,10 +115,9 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < V2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      for (int s = 0; s < NST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
       mbar_init(wfull, 1);
-      mbar_init(tfull, 1);
-      mbar_init(gobar, 1);
+      for (int i = 0; i < NS; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(gobar + 8 * i, 1); }
       mbar_init(w1bar, 1);
       fence_barrier_init();
     }
@@ -121,54 +140,67 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)g * 4096, &mapW, wfull, kb * 64, g * H + u0, P >= 2 ? 1 : 0);
     }
     int it = 0;
-    const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
+    const int gokb = (NST < KB ? NST : KB) - 1;
     // warp-uniform loop, one elected lane issues (see elect_one_sync): a TMA issue under `if (lane == 0)` costs ~300 cycles
     for (int t = 0; t < T; ++t) {
       if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }    // phase t: h_{t-1} published by all 16 CTAs
-      if (t > 0) {
-        if (!CL && lane == 0) v2_wait(counter + 32 * blockIdx.y, (unsigned int)t * gridDim.x);   // h_{t-1} of this batch tile is complete
-        __syncwarp();
-        fence_proxy_async();
-      }
-      if (lane == 0) F_STAMP(0);
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % V2_STAGES;
-        const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        if (elect_one_sync()) {
-          mbar_expect_tx(full0 + 8 * s, STAGE);
-          tma_load_3d(r0 + (uint32_t)s * STAGE, &mapH, full0 + 8 * s, kb * 64, t * B + m0, 0);   // all P planes in one box
-          if (kb == gokb) mbar_arrive(gobar);      // this step's first loads are out: the epilogue may use the memory pipe
+#pragma unroll 1
+      for (int sub = 0; sub < NS; ++sub) {
+        if (t > 0) {
+          // h_{t-1} of this batch (sub-)tile is complete
+          if (!CL && lane == 0) v2_wait(counter + 32 * blockIdx.y + 16 * sub, (unsigned int)t * gridDim.x);
+          __syncwarp();
+          fence_proxy_async();
         }
-        __syncwarp();
+        if (lane == 0) F_STAMP(sub == 0 ? 0 : 8);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % NST;
+          const uint32_t ph = (uint32_t)(it / NST) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          if (elect_one_sync()) {
+            if (dbg & 32) mbar_arrive(full0 + 8 * s);
+            else {
+              mbar_expect_tx(full0 + 8 * s, STAGE);
+              tma_load_3d(r0 + (uint32_t)s * STAGE, &mapH, full0 + 8 * s, kb * 64, ((dbg & 8) ? 0 : t * B) + m0 + sub * SUBN, 0);   // all P planes in one box
+            }
+            if (kb == gokb) mbar_arrive(gobar + 8 * sub);   // this step's first loads are out: the epilogue may use the memory pipe
+            if (kb == KB - 1) F_STAMP(sub == 0 ? 9 : 10);   // all loads of this work item issued
+          }
+          __syncwarp();
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc = make_idesc_bf16(128, SUBN, false, false);
     if (lane == 0) {
       mbar_wait(wfull, 0);
       if (P >= 2) mbar_wait(w1bar, 0);             // plane 1 of the W slice has been stored to TMEM by the epilogue warps
       tc_fence_after();
     }
     // the whole warp walks the loop (warp-uniform control flow and descriptors); one elected lane issues
-    if (lane == 0) { /* wfull / w1bar were waited above by lane 0 */ }
     __syncwarp();
     int it = 0;
     const uint64_t dw_base = make_kmajor_sw128_desc(w0), dr_base = make_kmajor_sw128_desc(r0);
     for (int t = 0; t < T; ++t) {
       if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }
+#pragma unroll 1
+      for (int sub = 0; sub < NS; ++sub) {
+      const uint32_t tacc = tmem_base + (uint32_t)(sub * SUBN);       // this sub-tile's accumulator columns
       for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % V2_STAGES;
-        const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
+        const int s = it % NST;
+        const uint32_t ph = (uint32_t)(it / NST) & 1u;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
+        if (lane == 0 && kb == 0) F_STAMP(sub == 0 ? 11 : 13);          // first / last k-block of the tile has landed
+        if (lane == 0 && kb == KB - 1) F_STAMP(sub == 0 ? 12 : 14);
         if (elect_one_sync()) {
           // descriptor start-address field is in 16-byte units: advancing by bytes/16 is a plain 64-bit add
           const uint64_t dwk = dw_base + (uint64_t)(((uint32_t)kb * W_KB) >> 4);
           const uint64_t dhk = dr_base + (uint64_t)(((uint32_t)s * STAGE) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            if (dbg & 16) break;
             const uint64_t dw = dwk + (uint64_t)(k * 2), dh0 = dhk + (uint64_t)(k * 2);
             const uint32_t accf = (kb | k) ? 1u : 0u;
             if (P >= 2) {
@@ -177,17 +209,21 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
               // more than its 32 tensor cycles); shared memory holds plane 1 (one product)
               const uint64_t dh1 = dh0 + (uint64_t)(B_PLANE >> 4);
               const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8);
-              umma_f16(tmem_base, dw, dh0, idesc, accf);          // W1 . h0   (A from shared memory)
-              umma_f16_ts(tmem_base, wt, dh1, idesc, 1u);         // W0 . h1   (A from tensor memory)
-              umma_f16_ts(tmem_base, wt, dh0, idesc, 1u);         // W0 . h0
+              umma_f16(tacc, dw, dh0, idesc, accf);               // W1 . h0   (A from shared memory)
+              umma_f16_ts(tacc, wt, dh1, idesc, 1u);              // W0 . h1   (A from tensor memory)
+              umma_f16_ts(tacc, wt, dh0, idesc, 1u);              // W0 . h0
+              // (stacking W0 . [h0 ; h1] into one N = 2 SUBN instruction was measured: 2 % slower -- in the real step the
+              // tile's landing, slowed by the other traffic of the SM, bounds the front half, and the epilogue pays a
+              // second tcgen05.ld)
             } else {
-              umma_f16(tmem_base, dw, dh0, idesc, accf);
+              umma_f16(tacc, dw, dh0, idesc, accf);
             }
           }
           umma_commit(empty0 + 8 * s);
-          if (kb == KB - 1) umma_commit(tfull);
+          if (kb == KB - 1) umma_commit(tfull + 8 * sub);
         }
         __syncwarp();
+      }
       }
     }
   } else {
@@ -196,6 +232,12 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
     const int ch = (warp - 2) >> 2;               // which 32 batch columns of the accumulator this warp drains
     const int et = threadIdx.x - 64;              // 0..255: after the transpose, thread = (batch row n, unit group ug)
     const int n = et >> 2, ug = et & 3;
+    // NS = 2: warps 2-5 (ch = 0) own sub-tile 0 = batch rows 0..31 of the tile, warps 6-9 sub-tile 1 -- both before
+    // the transpose (accumulator columns) and after it (rows n), so the two groups never exchange data
+    const int sub = NS == 1 ? 0 : ch;
+    const int bid = NS == 1 ? 0 : 1 + 3 * sub;    // named barriers bid + {1,2,3} with EPG threads (id 1 with all 256: start-up)
+    const bool leader = (et & (EPG - 1)) == 0;
+    unsigned int* const myctr = counter + 32 * blockIdx.y + 16 * sub;
     const int b = m0 + n;
     const bool rowok = b < bend;
     const int mylen = rowok ? (len ? len[b] : T) : 0;
@@ -230,7 +272,10 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       const bool active = rowok && (t >= T - mylen);
       const size_t rin = (size_t)t * B + b, rout = (size_t)(t + 1) * B + b;
       float4 pv[4][2];
-      if (active) {
+      if (dbg & 4) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pv[g][0] = pv[g][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (active) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const float* src = pre + rin * 4 * H + (size_t)g * H + uo;
@@ -238,9 +283,10 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           pv[g][1] = *reinterpret_cast<const float4*>(src + 4);
         }
       }
-      mbar_wait(tfull, (uint32_t)t & 1u);
+      mbar_wait(tfull + 8 * sub, (uint32_t)t & 1u);
       tc_fence_after();
       if (threadIdx.x == 64) F_STAMP(1);
+      if (NS > 1 && threadIdx.x == 64 + EPG) F_STAMP(15);
       {
         // accumulator -> shared memory, transposed: tbuf[n][m]   (the B ring is idle between tfull and our arrive)
         float acc[32];
@@ -250,7 +296,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         for (int j = 0; j < 32; ++j) dst[(size_t)j * V2_TPITCH] = acc[j];
       }
       tc_fence_before();
-      v2_bar_sync(2, V2_EPI);
+      v2_bar_sync(bid + 2, EPG);
       if (threadIdx.x == 64) F_STAMP(2);
       float gi[8], gf[8], go[8], gg[8], cn[8], hn[8];
       if (active) {
@@ -302,14 +348,14 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       if (CL) {
         if (t + 1 < T) { __syncwarp(); v2_cluster_arrive(); }     // every thread releases its own stores to the cluster
       } else {
-        v2_bar_sync(1, V2_EPI);
-        if (threadIdx.x == 64) { F_STAMP(4); v2_arrive(counter + 32 * blockIdx.y); F_STAMP(5); }
-        v2_bar_sync(3, V2_EPI);                    // keep the SM's memory pipeline clear until the release is out ...
+        v2_bar_sync(bid + 1, EPG);
+        if (leader) { if (threadIdx.x == 64) F_STAMP(4); v2_arrive(myctr); if (threadIdx.x == 64) F_STAMP(5); }
+        v2_bar_sync(bid + 3, EPG);                 // keep the SM's memory pipeline clear until the release is out ...
       }
-      if (t + 1 < T) mbar_wait(gobar, (uint32_t)(t + 1) & 1u);   // ... and until the next step's first loads are issued
+      if (t + 1 < T) mbar_wait(gobar + 8 * sub, (uint32_t)(t + 1) & 1u);   // ... and until the next step's first loads are issued
       if (threadIdx.x == 64) F_STAMP(6);
       // (3) everything only the backward pass needs, off the critical path
-      if (rowok) {
+      if (rowok && !(dbg & 2)) {
         float* gdst = pre + rin * 4 * H + uo;
 #define ST8(ptr, a)                                                                          \
         *reinterpret_cast<float4*>(ptr) = make_float4(a[0], a[1], a[2], a[3]);               \
@@ -329,12 +375,17 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       if (CL && t + 1 < T) { __syncwarp(); v2_cluster_wait(); }   // pairs with the arrive above (complete long ago)
       if (threadIdx.x == 64) F_STAMP(7);
     }
-    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) {
+    if ((dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) {
       printf("lstm_fwd_v2 timeline (cycles after the barrier opened): t | mma_done transposed math+stores_done all_done arrived go deferred_issued | step\n");
       for (int i = 1; i < 4; ++i) {
-        const long long* e = fst + i * 8;
+        const long long* e = fst + i * 16;
         printf("%2d | %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", 8 + i, e[1] - e[0], e[2] - e[0], e[3] - e[0], e[4] - e[0], e[5] - e[0],
-               e[6] - e[0], e[7] - e[0], e[0] - fst[(i - 1) * 8]);
+               e[6] - e[0], e[7] - e[0], e[0] - fst[(i - 1) * 16]);
+        printf("   sub0: loads issued %6lld first kb landed %6lld last kb landed %6lld", e[9] - e[0], e[11] - e[0], e[12] - e[0]);
+        if (NS > 1)
+          printf(" | sub1: open %6lld loads issued %6lld first landed %6lld last landed %6lld mma_done %6lld", e[8] - e[0], e[10] - e[0],
+                 e[13] - e[0], e[14] - e[0], e[15] - e[0]);
+        printf("\n");
       }
     }
   }
@@ -1069,9 +1120,13 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   const int KB = H / 64;
   const int tiles = ceil_div(B, 64), max_tiles = std::min(8, num_sms / (H / 32));
   if (max_tiles < 1) return -1;
-  const size_t ring = (size_t)V2_STAGES * P * 8192 + (P == 1 ? 2 * 8192 : 0);
-  const size_t smem = (size_t)KB * 16384 + ring + 1024 + 256;
-  if (ring < (size_t)64 * V2_TPITCH * 4 || smem > (size_t)max_smem) return -1;
+  // NVQA_LSTM_FWD_SPLIT=0: one 64-row tile per CTA (template NS = 1) instead of two software-pipelined 32-row sub-tiles
+  static int split = -1;
+  if (split < 0) { const char* e = getenv("NVQA_LSTM_FWD_SPLIT"); split = e ? atoi(e) : 1; }
+  const size_t ring = split ? (size_t)V2_SPLIT_STAGES * P * 4096 : (size_t)V2_STAGES * P * 8192 + (P == 1 ? 2 * 8192 : 0);
+  const size_t tile = (size_t)64 * V2_TPITCH * 4;
+  const size_t smem = (size_t)KB * 16384 + ring + (split ? tile : 0) + 1024 + 256;
+  if ((!split && ring < tile) || smem > (size_t)max_smem) return -1;
 
   __nv_bfloat16* wp = nullptr;
   int pitch = 0;
@@ -1079,11 +1134,11 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   CUtensorMap mapW, mapH;
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 32, &mapW));
   if (hp_plane_rows <= 0) hp_plane_rows = (long long)(T + 1) * B;
-  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, 64, &mapH, hp_plane_rows * H, P));
+  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, split ? 32 : 64, &mapH, hp_plane_rows * H, P));
   long long hp_plane = hp_plane_rows * H;
   const __nv_bfloat16* w1 = wp;                                    // the TMEM-resident plane: plane 0 (plane 1 goes to SMEM)
   int KBv = KB;
-  static const int dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
+  static const int dbg = getenv("NVQA_LSTM_DEBUG") ? std::max(1, atoi(getenv("NVQA_LSTM_DEBUG"))) : 0;
   int dbgv = dbg;
   static int use_cl = -1;
   if (use_cl < 0) { const char* e = getenv("NVQA_LSTM_CLUSTER16"); use_cl = e ? atoi(e) : 0; }   // measured on B200: only part of the 8 clusters of 16 is co-resident (0.82 ms vs 0.48 ms)
@@ -1094,9 +1149,9 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
     void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter, &dbgv,
                     &b0, &bend};
-    if (use_cl && grid.x == 16) {
+    if (use_cl && !split && grid.x == 16) {
       // one 16-CTA cluster per batch tile: hardware cluster barrier per step, plain (non-cooperative) launch
-      const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true> : (const void*)lstm_fwd_v2_kernel<1, true>;
+      const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true, 1> : (const void*)lstm_fwd_v2_kernel<1, true, 1>;
       NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       cudaLaunchConfig_t cc = {};
@@ -1110,7 +1165,8 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
       (void)cudaGetLastError();
       use_cl = 0;                                   // 16-CTA clusters are not schedulable here: counter barrier below
     }
-    const void* fn = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, false> : (const void*)lstm_fwd_v2_kernel<1, false>;
+    const void* fn = split ? (P == 2 ? (const void*)lstm_fwd_v2_kernel<2, false, 2> : (const void*)lstm_fwd_v2_kernel<1, false, 2>)
+                           : (P == 2 ? (const void*)lstm_fwd_v2_kernel<2, false, 1> : (const void*)lstm_fwd_v2_kernel<1, false, 1>);
     NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
