@@ -192,7 +192,13 @@ def run_ours(args):
         for i in range(args.warmup):
             step_resident(i)
     sampler.start()
+    prof_range = os.environ.get("NVQA_PROFILE_RANGE") == "1"      # ncu --profile-from-start off: only the timed steps
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ms, launches = timed(step_resident, args.steps, 0)
+    if prof_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     sampler.stop_flag = True
     sampler.join(timeout=2)
     value = world * B * args.steps / (ms / 1e3)

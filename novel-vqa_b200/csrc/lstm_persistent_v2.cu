@@ -70,13 +70,18 @@ __device__ __forceinline__ void v2_cluster_wait() { asm volatile("barrier.cluste
 // h_{t-1} tile is loaded and multiplied, and vice versa.  The transpose tile cannot alias the (now busy) ring: it gets
 // its own 33 KB, the ring shrinks to 8 x 8 KB.  Cost: twice as many tcgen05.mma (N = 32), each ~52-80 cycles whatever
 // its N (tools/probes/probe_mma_rate.cu), so the MMA warp becomes the bound: measured 0.486 -> 0.432 ms per step pair.
-template <int P, bool CL, int NS>
+// STK: W0 . h0 and W0 . h1 as ONE instruction with N = 2 SUBN (the two planes of a stage are contiguous [SUBN rows x 128 B]
+// blocks = one K-major B tile of 2 SUBN rows); accumulator columns [0, SUBN) then hold W0 . h0 + W1 . h0, [SUBN, 2 SUBN)
+// W0 . h1, summed by the epilogue.  DBG: the timing-experiment instantiation (NVQA_LSTM_DEBUG); the production one
+// compiles every `dbg` test away (a `lane == 0` stamp inside the MMA loop alone costs 10 % of the kernel).
+template <int P, bool CL, int NS, bool STK, bool DBG>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
                    float* __restrict__ h, __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
-                   const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg,
+                   const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg_arg,
                    int b0, int bend) {
+  const int dbg = DBG ? dbg_arg : 0;
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B): batches of more than 8 tiles are
   // processed as consecutive windows, each a full persistent launch
   extern __shared__ uint8_t smem_raw[];
@@ -173,6 +178,8 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc_bf16(128, SUBN, false, false);
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, 2 * SUBN, false, false);
+    constexpr int ACCW = (P >= 2 && STK) ? 2 * SUBN : SUBN;           // accumulator columns per sub-tile
     if (lane == 0) {
       mbar_wait(wfull, 0);
       if (P >= 2) mbar_wait(w1bar, 0);             // plane 1 of the W slice has been stored to TMEM by the epilogue warps
@@ -186,21 +193,24 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }
 #pragma unroll 1
       for (int sub = 0; sub < NS; ++sub) {
-      const uint32_t tacc = tmem_base + (uint32_t)(sub * SUBN);       // this sub-tile's accumulator columns
+      const uint32_t tacc = tmem_base + (uint32_t)(sub * ACCW);       // this sub-tile's accumulator columns
       for (int kb = 0; kb < KB; ++kb, ++it) {
         const int s = it % NST;
         const uint32_t ph = (uint32_t)(it / NST) & 1u;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
-        if (lane == 0 && kb == 0) F_STAMP(sub == 0 ? 11 : 13);          // first / last k-block of the tile has landed
-        if (lane == 0 && kb == KB - 1) F_STAMP(sub == 0 ? 12 : 14);
+        if (DBG) {
+          if (lane == 0 && kb == 0) F_STAMP(sub == 0 ? 11 : 13);          // first / last k-block of the tile has landed
+          if (lane == 0 && kb == KB - 1) F_STAMP(sub == 0 ? 12 : 14);
+          __syncwarp();
+        }
         if (elect_one_sync()) {
           // descriptor start-address field is in 16-byte units: advancing by bytes/16 is a plain 64-bit add
           const uint64_t dwk = dw_base + (uint64_t)(((uint32_t)kb * W_KB) >> 4);
           const uint64_t dhk = dr_base + (uint64_t)(((uint32_t)s * STAGE) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (dbg & 16) break;
+            if (DBG && (dbg & 16)) break;
             const uint64_t dw = dwk + (uint64_t)(k * 2), dh0 = dhk + (uint64_t)(k * 2);
             const uint32_t accf = (kb | k) ? 1u : 0u;
             if (P >= 2) {
@@ -209,12 +219,14 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
               // more than its 32 tensor cycles); shared memory holds plane 1 (one product)
               const uint64_t dh1 = dh0 + (uint64_t)(B_PLANE >> 4);
               const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8);
-              umma_f16(tacc, dw, dh0, idesc, accf);               // W1 . h0   (A from shared memory)
-              umma_f16_ts(tacc, wt, dh1, idesc, 1u);              // W0 . h1   (A from tensor memory)
-              umma_f16_ts(tacc, wt, dh0, idesc, 1u);              // W0 . h0
-              // (stacking W0 . [h0 ; h1] into one N = 2 SUBN instruction was measured: 2 % slower -- in the real step the
-              // tile's landing, slowed by the other traffic of the SM, bounds the front half, and the epilogue pays a
-              // second tcgen05.ld)
+              if (STK) {
+                umma_f16_ts(tacc, wt, dh0, idesc2, accf);         // W0 . [h0 ; h1]  (A from tensor memory, N = 2 SUBN)
+                umma_f16(tacc, dw, dh0, idesc, 1u);               // W1 . h0         (A from shared memory) += columns [0, SUBN)
+              } else {
+                umma_f16(tacc, dw, dh0, idesc, accf);             // W1 . h0   (A from shared memory)
+                umma_f16_ts(tacc, wt, dh1, idesc, 1u);            // W0 . h1   (A from tensor memory)
+                umma_f16_ts(tacc, wt, dh0, idesc, 1u);            // W0 . h0
+              }
             } else {
               umma_f16(tacc, dw, dh0, idesc, accf);
             }
@@ -290,7 +302,15 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       {
         // accumulator -> shared memory, transposed: tbuf[n][m]   (the B ring is idle between tfull and our arrive)
         float acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), acc);
+        constexpr bool STACKED = P >= 2 && STK;
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(STACKED && NS == 2 ? ch * 64 : ch * 32);
+        tmem_ld32(tcol, acc);
+        if (STACKED) {
+          float a1[32];                           // the W0 . h1 half of the stacked product
+          tmem_ld32(tcol + SUBN, a1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += a1[j];
+        }
         float* dst = tbuf + (size_t)(ch * 32) * V2_TPITCH + q * 32 + lane;
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[(size_t)j * V2_TPITCH] = acc[j];
@@ -750,7 +770,7 @@ __device__ long long g_v3dbg[16 * 4];           // (debug) per-CTA wall-clock st
 __device__ __forceinline__ long long v3_gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define V3_STAMP(slot) do { if (dbg && cta == 0 && blockIdx.z == 0 && t >= 8 && t < 12) stamps[(t - 8) * 8 + (slot)] = clock64(); } while (0)
 
-template <int P>
+template <int P, bool STK, bool DBG>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, const float* __restrict__ gates,
@@ -758,8 +778,9 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
                    const float* __restrict__ dh_above, Drop drop, float* __restrict__ dasum,
                    __nv_bfloat16* __restrict__ dap, long long dap_plane, float* __restrict__ dh_init,
                    float* __restrict__ dc_init, const int32_t* __restrict__ len, int T, int B, int H, int KB,
-                   unsigned int* counter, int dbg, int b0, int bend) {
+                   unsigned int* counter, int dbg_arg, int b0, int bend) {
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B)
+  const int dbg = DBG ? dbg_arg : 0;                // the production instantiation compiles the stamps away
   extern __shared__ uint8_t smem_raw[];
   __shared__ long long stamps[32];
   const uint32_t raw = smem_u32(smem_raw);
@@ -844,6 +865,9 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     // ===== MMA issuer: warp-uniform loop, one elected lane issues (descriptors stay in uniform registers) =====
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, false);       // A = W_hh^T slice in SMEM, MN-major
     constexpr uint32_t idesc_ts = make_idesc_bf16(128, 64, false, false);   // A from TMEM is K-major by construction
+    // STK: the two planes of a da stage are one contiguous 128-row B tile, so W0 . da0 and W0 . da1 are a single N = 128
+    // instruction (accumulator columns [0, 64) and [64, 128), summed by the epilogue)
+    constexpr uint32_t idesc_ts2 = make_idesc_bf16(128, 128, false, false);
     if (lane == 0) {
       mbar_wait(wfull, 0);
       if (P >= 2) mbar_wait(w1bar, 0);
@@ -869,9 +893,14 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
               // TMEM holds plane 0 of the W_hh^T slice (two of the three products), shared memory plane 1
               const uint64_t d1 = d0 + (uint64_t)(B_PLANE >> 4);
               const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + kk * 8);
-              umma_f16(tmem_base, dw, d0, idesc, accf);            // W1 . da0
-              umma_f16_ts(tmem_base, wt, d1, idesc_ts, 1u);        // W0 . da1
-              umma_f16_ts(tmem_base, wt, d0, idesc_ts, 1u);        // W0 . da0
+              if (STK) {
+                umma_f16_ts(tmem_base, wt, d0, idesc_ts2, accf);   // W0 . [da0 ; da1]
+                umma_f16(tmem_base, dw, d0, idesc, 1u);            // W1 . da0  += columns [0, 64)
+              } else {
+                umma_f16(tmem_base, dw, d0, idesc, accf);          // W1 . da0
+                umma_f16_ts(tmem_base, wt, d1, idesc_ts, 1u);      // W0 . da1
+                umma_f16_ts(tmem_base, wt, d0, idesc_ts, 1u);      // W0 . da0
+              }
             } else {
               umma_f16(tmem_base, dw, d0, idesc, accf);
             }
@@ -953,6 +982,12 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       {
         float acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), acc);
+        if (P >= 2 && STK) {
+          float a1[32];                                      // the W0 . da1 half of the stacked product
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 + ch * 32), a1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += a1[j];
+        }
         float* dst = tbuf + (size_t)(ch * 32) * V2_BPITCH + q * 32 + lane;
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[(size_t)j * V2_BPITCH] = acc[j];
@@ -1151,7 +1186,7 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
                     &b0, &bend};
     if (use_cl && !split && grid.x == 16) {
       // one 16-CTA cluster per batch tile: hardware cluster barrier per step, plain (non-cooperative) launch
-      const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true, 1> : (const void*)lstm_fwd_v2_kernel<1, true, 1>;
+      const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true, 1, false, false> : (const void*)lstm_fwd_v2_kernel<1, true, 1, false, false>;
       NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       NVQA_CUDA(cudaFuncSetAttribute(fc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       cudaLaunchConfig_t cc = {};
@@ -1165,8 +1200,16 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
       (void)cudaGetLastError();
       use_cl = 0;                                   // 16-CTA clusters are not schedulable here: counter barrier below
     }
-    const void* fn = split ? (P == 2 ? (const void*)lstm_fwd_v2_kernel<2, false, 2> : (const void*)lstm_fwd_v2_kernel<1, false, 2>)
-                           : (P == 2 ? (const void*)lstm_fwd_v2_kernel<2, false, 1> : (const void*)lstm_fwd_v2_kernel<1, false, 1>);
+    static int stack = -1;
+    if (stack < 0) { const char* e = getenv("NVQA_LSTM_STACK"); stack = e ? atoi(e) : 0; }
+    const void* fn;
+#define NVQA_FWD(P_, NS_, STK_, DBG_) (const void*)lstm_fwd_v2_kernel<P_, false, NS_, STK_, DBG_>
+    if (dbg) fn = split ? (P == 2 ? NVQA_FWD(2, 2, false, true) : NVQA_FWD(1, 2, false, true))
+                        : (P == 2 ? NVQA_FWD(2, 1, false, true) : NVQA_FWD(1, 1, false, true));
+    else if (P == 2 && stack) fn = split ? NVQA_FWD(2, 2, true, false) : NVQA_FWD(2, 1, true, false);
+    else fn = split ? (P == 2 ? NVQA_FWD(2, 2, false, false) : NVQA_FWD(1, 2, false, false))
+                    : (P == 2 ? NVQA_FWD(2, 1, false, false) : NVQA_FWD(1, 1, false, false));
+#undef NVQA_FWD
     NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -1228,7 +1271,11 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     CUtensorMap mapDA3;                            // both planes of a da tile in one TMA box
     NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 64, &mapDA3, dap_plane_rows * 4 * H, P));
     const __nv_bfloat16* wt = wp;                  // generation 3 keeps plane 0 in TMEM and plane 1 in shared memory
-    const void* f3 = P == 2 ? (const void*)lstm_bwd_v3_kernel<2> : (const void*)lstm_bwd_v3_kernel<1>;
+    static int stack3 = -1;
+    if (stack3 < 0) { const char* e = getenv("NVQA_LSTM_STACK"); stack3 = e ? atoi(e) : 0; }
+    const void* f3 = dbg ? (P == 2 ? (const void*)lstm_bwd_v3_kernel<2, false, true> : (const void*)lstm_bwd_v3_kernel<1, false, true>)
+                         : P == 2 ? (stack3 ? (const void*)lstm_bwd_v3_kernel<2, true, false> : (const void*)lstm_bwd_v3_kernel<2, false, false>)
+                                  : (const void*)lstm_bwd_v3_kernel<1, false, false>;
     NVQA_CUDA(cudaFuncSetAttribute(f3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const bool nocoop = getenv("NVQA_LSTM_NOCOOP") != nullptr;
     bool ok = true;
