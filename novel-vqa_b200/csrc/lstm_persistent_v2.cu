@@ -82,6 +82,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                    const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg_arg,
                    int b0, int bend) {
   const int dbg = DBG ? dbg_arg : 0;
+  const long long t_entry = DBG ? clock64() : 0;
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B): batches of more than 8 tiles are
   // processed as consecutive windows, each a full persistent launch
   extern __shared__ uint8_t smem_raw[];
@@ -271,6 +272,8 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
     }
     v2_bar_sync(1, V2_EPI);
     if (P >= 2 && threadIdx.x == 64) mbar_arrive(w1bar);      // hand the TMEM-resident operand to the MMA thread
+    const long long t_prologue = DBG ? clock64() : 0;          // W planes resident (this thread's share), barriers up
+    long long t_step0 = 0;
     float ccarry[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) ccarry[j] = 0.f;
@@ -297,6 +300,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       }
       mbar_wait(tfull + 8 * sub, (uint32_t)t & 1u);
       tc_fence_after();
+      if (DBG && t == 0) t_step0 = clock64();                  // first accumulator complete: W0 landed, first tile multiplied
       if (threadIdx.x == 64) F_STAMP(1);
       if (NS > 1 && threadIdx.x == 64 + EPG) F_STAMP(15);
       {
@@ -396,6 +400,8 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       if (threadIdx.x == 64) F_STAMP(7);
     }
     if ((dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) {
+      printf("lstm_fwd_v2 kernel (cycles from entry): prologue done %lld, first accumulator %lld, last step done %lld\n",
+             t_prologue - t_entry, t_step0 - t_entry, clock64() - t_entry);
       printf("lstm_fwd_v2 timeline (cycles after the barrier opened): t | mma_done transposed math+stores_done all_done arrived go deferred_issued | step\n");
       for (int i = 1; i < 4; ++i) {
         const long long* e = fst + i * 16;
