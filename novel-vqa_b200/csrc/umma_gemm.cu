@@ -11,11 +11,14 @@
 // This is the "fp32 parity on tensor cores" mode of the arch1 step: the reference's nn.Linear GEMMs
 // (misc/LSTM.lua:41-42, misc/netdef.lua:10-11, 002_train_baseline.lua:154) are fp32 SGEMMs.
 //
-// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0   : TMA producer   - cp.async.bulk.tensor.3d (SWIZZLE_128B boxes of 64 bf16 x rows x 1 plane)
+// Kernel anatomy (PERSISTENT: one CTA per SM walks the 128 x BN output tiles tile = blockIdx.x, + gridDim.x, ...; 192 threads):
+//   warp 0   : TMA producer   - cp.async.bulk.tensor.3d (SWIZZLE_128B boxes of 64 bf16 x rows x 1 plane), one ring across tiles
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
 //   warps 2-5: epilogue       - tcgen05.ld (32 lanes x 32 columns per warp), bias / beta, fp32 stores
 // smem: STAGES x { P A-planes [128 x 64] , P B-planes [BN x 64] } ring with full/empty mbarriers.
+// TMEM: TWO accumulator stages of BN columns (tfull / tempty mbarriers): the epilogue of tile i (128 KB of stores at
+// BN = 256) overlaps the main loop of tile i + 1 -- for the short-K products of the step (input projections K = 200 / 512,
+// vocabulary projection K = 512) the epilogue was a third of a tile's time.
 #include <unordered_map>
 #include <vector>
 
@@ -38,10 +41,10 @@ struct UgCfg {
   static constexpr int A_PLANE = UG_BM * UG_BK * 2;           // 16 KB
   static constexpr int B_PLANE = BN * UG_BK * 2;
   static constexpr int STAGE = P * (A_PLANE + B_PLANE);
-  static constexpr int MAX_STAGES = (227 * 1024 - 2048) / STAGE;
+  static constexpr int MAX_STAGES = (227 * 1024 - 4096) / STAGE;
   static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias tile*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * 1024 /*two bias tiles*/;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator stages (a power of two >= 32)
   static_assert(STAGES >= 2, "pipeline needs two stages");
 };
 
@@ -49,7 +52,8 @@ template <int BN, int P, bool AMN, bool BMN>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N,
                  int K, float* __restrict__ C, int ldc, int beta, const float* __restrict__ bias0,
-                 const float* __restrict__ bias1, int a_row0, int b_row0, int kb_per_split, long long c_split_stride) {
+                 const float* __restrict__ bias1, int a_row0, int b_row0, int kb_per_split, long long c_split_stride,
+                 int tiles_n, int tiles_m, int splits) {
   using Cfg = UgCfg<BN, P>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -58,35 +62,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(gen + Cfg::STAGES * Cfg::STAGE);
   const uint32_t full0 = base + Cfg::STAGES * Cfg::STAGE;            // full[s]  at full0 + 8 s
   const uint32_t empty0 = full0 + 8 * Cfg::STAGES;                   // empty[s]
-  const uint32_t tfull = empty0 + 8 * Cfg::STAGES;                   // accumulator ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
-  float* bias_s = reinterpret_cast<float*>(gen + Cfg::STAGES * Cfg::STAGE + 256);      // bias0 + bias1 of this tile
+  const uint32_t tfull = empty0 + 8 * Cfg::STAGES;                   // accumulator stage a ready   (tfull + 8 a)
+  const uint32_t tempty = tfull + 16;                                 // accumulator stage a drained (tempty + 8 a)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  float* bias_all = reinterpret_cast<float*>(gen + Cfg::STAGES * Cfg::STAGE + 256);    // bias0 + bias1 of the tile, per stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * UG_BM, n0 = blockIdx.x * BN;
   const int nkb_all = (K + UG_BK - 1) / UG_BK;
-  const int kb0 = blockIdx.z * kb_per_split;                          // split-K: this CTA's k-block range
-  const int nkb = min(nkb_all, kb0 + kb_per_split) - kb0;
-  C += (size_t)blockIdx.z * c_split_stride;
+  const int total_tiles = tiles_n * tiles_m * splits;                 // tile = (z * tiles_m + y) * tiles_n + x
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
   }
-  if (warp >= 2) {      // stage the tile's bias row once (the epilogue then reads it as a shared-memory broadcast)
-    for (int j = threadIdx.x - 64; j < BN; j += 128) {
-      float bsum = 0.f;
-      if (n0 + j < N) {
-        if (bias0) bsum += __ldg(bias0 + n0 + j);
-        if (bias1) bsum += __ldg(bias1 + n0 + j);
-      }
-      bias_s[j] = bsum;
-    }
-  }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-      mbar_init(tfull, 1);
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull + 8 * a, 1); mbar_init(tempty + 8 * a, 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -99,9 +91,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   if (warp == 0) {
     // ===== TMA producer: warp-uniform loop, one elected lane issues (see elect_one_sync in umma_ptx.cuh) =====
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % Cfg::STAGES;
-      const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tz = tile / (tiles_n * tiles_m), ty = (tile / tiles_n) % tiles_m, tx = tile % tiles_n;
+    const int m0 = ty * UG_BM, n0 = tx * BN;
+    const int kb0 = tz * kb_per_split;                                // split-K: this tile's k-block range
+    const int nkb = min(nkb_all, kb0 + kb_per_split) - kb0;
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
       mbar_wait(empty0 + 8 * s, ph ^ 1u);
       if (elect_one_sync()) {
         mbar_expect_tx(full0 + 8 * s, Cfg::STAGE);
@@ -132,13 +130,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       __syncwarp();
     }
+    }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the loop (uniform control flow and descriptors), one elected lane issues;
     // under `if (lane == 0)` every UTCHMMA was wrapped in an ELECT / R2UR / BRA.U.ANY loop (~80 cycles per MMA) =====
     constexpr uint32_t idesc = make_idesc_bf16(UG_BM, BN, AMN, BMN);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % Cfg::STAGES;
-      const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+    int it = 0, li = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+    const int tz = tile / (tiles_n * tiles_m);
+    const int kb0 = tz * kb_per_split;
+    const int nkb = min(nkb_all, kb0 + kb_per_split) - kb0;
+    const int as = li & 1;                                            // accumulator stage of this tile
+    const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+    mbar_wait(tempty + 8 * as, (((uint32_t)li >> 1) & 1u) ^ 1u);      // the epilogue has drained the tile two tiles back
+    tc_fence_after();
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
       mbar_wait(full0 + 8 * s, ph);
       tc_fence_after();
       if (elect_one_sync()) {
@@ -159,32 +167,53 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
           // smallest terms first
           if (P == 3) {
-            umma_f16(tmem_base, da[0], db[2], idesc, acc); acc = 1;
-            umma_f16(tmem_base, da[2], db[0], idesc, acc);
-            umma_f16(tmem_base, da[1], db[1], idesc, acc);
+            umma_f16(tacc, da[0], db[2], idesc, acc); acc = 1;
+            umma_f16(tacc, da[2], db[0], idesc, acc);
+            umma_f16(tacc, da[1], db[1], idesc, acc);
           }
           if (P >= 2) {
-            umma_f16(tmem_base, da[0], db[1], idesc, acc); acc = 1;
-            umma_f16(tmem_base, da[1], db[0], idesc, acc);
+            umma_f16(tacc, da[0], db[1], idesc, acc); acc = 1;
+            umma_f16(tacc, da[1], db[0], idesc, acc);
           }
-          umma_f16(tmem_base, da[0], db[0], idesc, acc); acc = 1;
+          umma_f16(tacc, da[0], db[0], idesc, acc); acc = 1;
         }
         umma_commit(empty0 + 8 * s);          // smem slot free once these MMAs have read it
-        if (kb == nkb - 1) umma_commit(tfull);  // accumulator complete
+        if (kb == nkb - 1) umma_commit(tfull + 8 * as);  // accumulator complete
       }
       __syncwarp();
     }
+    }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
-    mbar_wait(tfull, 0);
-    tc_fence_after();
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
     const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    float* const C0 = C;
+    int li = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+    const int tz = tile / (tiles_n * tiles_m), ty = (tile / tiles_n) % tiles_m, tx = tile % tiles_n;
+    const int m0 = ty * UG_BM, n0 = tx * BN;
+    const int as = li & 1;
+    C = C0 + (size_t)tz * c_split_stride;
+    float* bias_s = bias_all + as * 256;
+    // stage the tile's bias row (read below as a shared-memory broadcast); the named barrier also orders the reuse of
+    // the stage: nobody passes it before all four warps have finished the tile before
+    for (int j = threadIdx.x - 64; j < BN; j += 128) {
+      float bsum = 0.f;
+      if (n0 + j < N) {
+        if (bias0) bsum += __ldg(bias0 + n0 + j);
+        if (bias1) bsum += __ldg(bias1 + n0 + j);
+      }
+      bias_s[j] = bsum;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(tfull + 8 * as, ((uint32_t)li >> 1) & 1u);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+      tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
       if (row < M) {
         float* crow = C + (size_t)row * ldc;
 #pragma unroll
@@ -206,6 +235,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
       }
+    }
+    tc_fence_before();                          // this warp's tcgen05.ld of the stage are complete (wait::ld inside tmem_ld32)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty + 8 * as);
     }
   }
   tc_fence_before();
@@ -441,10 +474,20 @@ static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap&
                                    Cfg::SMEM));
     attr_set = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, UG_BM), L.splits);
+  static int num_sms = 0, persist = -1;
+  if (!num_sms) {
+    int dev = 0;
+    NVQA_CUDA(cudaGetDevice(&dev));
+    NVQA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (persist < 0) { const char* e = getenv("NVQA_GEMM_PERSIST"); persist = e ? atoi(e) : 1; }   // 0: one tile per CTA
+  const int tn = ceil_div(N, BN), tm = ceil_div(M, UG_BM);
+  const long long total = (long long)tn * tm * L.splits;
+  NVQA_CHECK(total < (1ll << 31), "umma_gemm: too many tiles");
+  dim3 grid((unsigned)(persist ? std::min<long long>(total, num_sms) : total));
   umma_gemm_kernel<BN, P, AMN, BMN><<<grid, UG_THREADS, Cfg::SMEM, s>>>(ma, mb, M, N, K, C, ldc, beta ? 1 : 0, b0, b1,
                                                                         L.a_row0, L.b_row0, L.kb_per_split,
-                                                                        L.c_split_stride);
+                                                                        L.c_split_stride, tn, tm, L.splits);
   NVQA_LAUNCHED();
   return 0;
 }
