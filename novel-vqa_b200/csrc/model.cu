@@ -476,6 +476,21 @@ extern "C" int nvqa_set_batch(nvqa_model* m, const int32_t* q, const int32_t* le
   NVQA_CHECK(m && q && (m->cfg.arch == 3 || (len && fc7)), "null argument");
   NVQA_CHECK(B > 0 && B <= m->cfg.B, "batch size out of range");
   m->q = q; m->len = len; m->fc7 = fc7; m->labels = labels; m->B = B;
+  if (B != m->B_layout) {
+    // A time slot is B rows, so slot 0 -- the zero initial state (c, h and the h planes), which no kernel ever writes --
+    // now covers rows that were LATER slots of the previous, differently sized batch (e.g. the short last batch of a
+    // validation pass followed by full training batches): make it zero again.
+    NVQA_CUDA(cudaSetDevice(m->cfg.device));
+    const size_t n = (size_t)B * m->cfg.H;
+    const size_t plane = (size_t)(m->TS + 1) * m->cfg.B * m->cfg.H;
+    for (int l = 0; l < m->cfg.L; ++l) {
+      NVQA_CUDA(cudaMemsetAsync(m->c[l], 0, n * 4, m->stream));
+      NVQA_CUDA(cudaMemsetAsync(m->h[l], 0, n * 4, m->stream));
+      if (m->planes && m->hp[l])
+        for (int p = 0; p < m->planes; ++p) NVQA_CUDA(cudaMemsetAsync(m->hp[l] + p * plane, 0, n * 2, m->stream));
+    }
+    m->B_layout = B;
+  }
   m->fwd_done = false;
   m->fc7_pending = false;
   m->steps = m->cfg.arch == 3 ? m->cfg.T : m->TS;

@@ -79,6 +79,7 @@ struct nvqa_model {
   const int32_t *q = nullptr, *len = nullptr, *labels = nullptr;
   const float* fc7 = nullptr;
   int B = 0;
+  int B_layout = 0;                // batch size the time-major buffers were last laid out for (row stride of a time slot)
   int32_t *q_stage = nullptr, *len_stage = nullptr, *lab_stage = nullptr;
   float* fc7_stage = nullptr;
   float* loss_host = nullptr;      // pinned

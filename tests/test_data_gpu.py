@@ -7,7 +7,7 @@ import json
 import numpy as np
 import pytest
 
-from conftest import assert_close
+from conftest import assert_close, rel_err
 from oracle import arch1 as A
 
 pytestmark = pytest.mark.gpu
@@ -43,8 +43,15 @@ def test_train_validate_and_emit_answers_from_hdf5(tmp_path):
             g = np.clip(grads[k], -10, 10).astype(np.float32)
             rms[k] = (0.99 * rms[k] + 0.01 * g * g).astype(np.float32)
             w[k] = (w[k] - lr * g / (np.sqrt(rms[k]) + 1e-8)).astype(np.float32)
-    for blk, want in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), w):
-        assert_close(m.get_params(blk), want, 1e-4, f"params {blk} after two iterations")
+    # RMSprop's first steps move every weight by ~10 lr whatever its gradient: compare the weights in rel-L2 and the
+    # *updates* separately (as test_training_trajectory_against_golden does)
+    for blk, w0, want in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), (enc, emb, mm), w):
+        got = m.get_params(blk)
+        e2, _ = rel_err(got, want)
+        assert e2 <= 1e-4, f"params {blk} after two iterations: rel-l2 {e2:.3e}"
+        u2, _ = rel_err(got.astype(np.float64) - w0, want.astype(np.float64) - w0)
+        assert u2 <= 5e-3, f"update {blk}: rel-l2 {u2:.3e}"
+    w = [m.get_params(b) for b in (nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL)]   # oracle continues from the device weights
 
     # ---- validation pass: consecutive batches, last one short ----
     count, losses = 0, []

@@ -426,3 +426,30 @@ def test_edge_batches_single_row_and_single_token(lens):
         for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
             assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, "gradient")
         m.close()
+
+
+@pytest.mark.parametrize("H", [64, 512])
+@pytest.mark.parametrize("name,prec,tol", [PRECISIONS[0], PRECISIONS[1]])
+def test_batch_size_change_keeps_zero_initial_state(name, prec, tol, H):
+    """A time slot of the activation buffers is B rows: after a SHORT batch (the last batch of a validation pass,
+    002_train_baseline.lua:231-233) slot 0 -- the zero initial state of rnn_forward (misc/RNNUtils.lua:131), never
+    written by any kernel -- of a following full batch covers rows the short batch used for later steps.  Short
+    questions (inactive first steps) then started from stale state.  H = 512 runs the persistent kernels, H = 64 the
+    first-generation / per-step path."""
+    nvm = nv()
+    cfg = nvm.Arch1Config(V=300, E=24, H=H, L=2, I=40, C=48, O=10, T=6, B=96)
+    oc = ocfg(cfg)
+    enc, emb, mm = nvm.synth_params(cfg, seed=2)
+    enc, emb, mm = enc * 3, emb * 3, mm * 3
+    m = make_model(nvm, cfg, enc, emb, mm, prec)
+    for i, B in enumerate((96, 40, 96, 7, 50)):
+        q, ln, fc7, lab = nvm.synth_batch(cfg, B, seed=20 + i, min_len=1)
+        m.set_batch_host(q, ln, fc7, lab)
+        m.forward(nvm.MODE_EVAL, 0)
+        f, grads, scores, ctx = A.jdj(oc, enc, emb, mm, q, ln, A.l2_normalize_rows(fc7), lab, seed=None)
+        assert_close(m.state(B), ctx["tv_q"], tol, f"{name} H={H} batch {i} (B={B}) state")
+        assert_close(m.scores(B), scores, tol, f"{name} H={H} batch {i} (B={B}) scores")
+        m.backward()
+        for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
+            assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, f"{name} H={H} batch {i} (B={B}) grads {blk}")
+    m.close()
