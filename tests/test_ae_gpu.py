@@ -161,3 +161,31 @@ def test_literal_lookup_gradient_mode():
         e2, em = rel_err(m.get_params(blk) - g[key], want - g[key])
         assert e2 <= 1e-3 and em <= 2e-2, f"{key} update (literal lookup gradient): rel-l2 {e2:.3e}, rel-max {em:.3e}"
     m.close()
+
+
+@pytest.mark.parametrize("name,prec,tol", [("fp32_simt", 0, 1e-4), ("bf16x2", 3, 1e-4)])
+@pytest.mark.parametrize("H", [128, 512])
+def test_batch_size_and_tmax_changes_between_batches(name, prec, tol, H):
+    """One handle, batches of different sizes and different longest sequences (encoder steps tmax, decoder tmax + 1;
+    the decoder's slot 0 is the encoder's last slot): nothing of an earlier batch may leak into a later one.
+    H = 512 runs the persistent kernels."""
+    nvm = nv()
+    cfg = nvm.AEConfig(V=203, E=H, H=H, L=1, T=8, B=96) if H == 512 else nvm.AEConfig(V=203, E=64, H=H, L=1, T=8, B=96)
+    ocfg = AE.AEConfig(V=cfg.V, E=cfg.E, H=cfg.H, L=1, T=cfg.T)
+    enc, dec, lut = nvm.synth_params_ae(cfg, seed=5)
+    m = make(nvm, cfg, enc, dec, lut, prec)
+    for i, (B, longest) in enumerate(((96, 8), (30, 3), (96, 8), (7, 8), (50, 5))):
+        seq, lens = nvm.synth_batch_ae(cfg, B, seed=40 + i, min_len=1)
+        seq[:, longest:] = 0
+        lens = np.minimum(lens, longest).astype(np.int32)
+        seq[0, :longest] = np.maximum(seq[0, :longest], 1)
+        lens[0] = longest
+        f, grads, ctx = AE.loss_and_grads(ocfg, enc, dec, lut, seq, seed=None, grad_clip=None, weight_decay=0)
+        assert ctx["tmax"] == longest
+        m.set_batch_host(seq, lens)
+        m.forward(nvm.MODE_EVAL, 0)
+        assert abs(m.loss() - f) <= tol * abs(f), f"batch {i} (B={B}, longest {longest}) loss {m.loss()} vs {f}"
+        m.backward()
+        for got, want, what in zip(raw_grads(nvm, m), grads, ("encoder", "decoder", "lookup")):
+            assert_close(got, want, tol, f"batch {i} (B={B}, longest {longest}) {what} gradient")
+    m.close()

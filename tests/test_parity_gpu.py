@@ -453,3 +453,31 @@ def test_batch_size_change_keeps_zero_initial_state(name, prec, tol, H):
         for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
             assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, f"{name} H={H} batch {i} (B={B}) grads {blk}")
     m.close()
+
+
+@pytest.mark.parametrize("name,prec,tol", [PRECISIONS[0], PRECISIONS[1]])
+def test_arch2_batch_size_and_length_changes_between_batches(name, prec, tol):
+    """arch2 on one handle over batches of different sizes AND different longest questions (tmax = longest + 2 steps,
+    Encoder_lstm.lua:152-227): nothing of an earlier batch may leak into a later one."""
+    from oracle import arch2 as A2
+    nvm = nv()
+    cfg = nvm.Arch2Config(V=200, E=64, H=64, L=1, I=40, O=31, T=9, B=64)
+    oc = ocfg2(cfg)
+    cnn, enc, mm = nvm.synth_params2(cfg, seed=5)
+    cnn, enc, mm = cnn * 3, enc * 3, mm * 3
+    m = make_model2(nvm, cfg, cnn, enc, mm, prec)
+    for i, (B, longest) in enumerate(((64, 9), (20, 4), (64, 9), (5, 9), (33, 6))):
+        q, ln, fc7, lab = nvm.synth_batch2(cfg, B, seed=30 + i, min_len=1)
+        ln[:] = np.minimum(ln, longest)
+        q[:, longest:] = 0
+        ln[0] = longest
+        q[0, :longest] = np.maximum(q[0, :longest], 1)
+        m.set_batch_host(q, ln, fc7, lab)
+        f, grads, scores, ctx = A2.jdj(oc, cnn, enc, mm, q, A.l2_normalize_rows(fc7), lab, seed=None)
+        m.forward(nvm.MODE_EVAL, 0)
+        assert_close(m.scores(B), scores, tol, f"{name} arch2 batch {i} (B={B}, longest {longest}) scores")
+        assert abs(m.loss() - f) <= tol * abs(f)
+        m.backward()
+        for blk, gw in zip((nvm.BLOCK_CNN, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
+            assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, f"{name} arch2 batch {i} grads {blk}")
+    m.close()
