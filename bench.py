@@ -21,8 +21,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout: keep stdout to the ONE JSON line
+# stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 from C (NCCL prints its
+# "NCCL version ..." banner there at every debug level from VERSION up, WARN included) are sent to stderr, and the JSON
+# line is written to the saved descriptor
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 METRIC = "arch1_train_samples_per_s"
 UNIT = "samples/s"
@@ -111,7 +114,7 @@ def run_reference(args):
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def run_ours(args):
@@ -381,7 +384,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "tflops_algorithmic": value * FLOPS_PER_SAMPLE / 1e12,
                 "roofline": roof, "cpu_baseline": cpu, "extras": extras}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
