@@ -1,12 +1,13 @@
 """Prints the end-to-end error of every precision mode of the CUDA path against the fp32/fp64 CPU oracle on
-BASELINE config 1 (B=500).  Run on the GPU box:  python tools/precision_study.py [--f64]"""
+BASELINE config 1 (B=500).  Run on the GPU box:  python tests/tools/precision_study.py [--f64]
+(lives under tests/: it calls the oracle, which only test code may do)"""
 import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import novel_vqa_b200 as nv  # noqa: E402
 from oracle import arch1 as A  # noqa: E402
 
