@@ -74,7 +74,61 @@ __device__ __forceinline__ void v2_cluster_wait() { asm volatile("barrier.cluste
 // blocks = one K-major B tile of 2 SUBN rows); accumulator columns [0, SUBN) then hold W0 . h0 + W1 . h0, [SUBN, 2 SUBN)
 // W0 . h1, summed by the epilogue.  DBG: the timing-experiment instantiation (NVQA_LSTM_DEBUG); the production one
 // compiles every `dbg` test away (a `lane == 0` stamp inside the MMA loop alone costs 10 % of the kernel).
-template <int P, bool CL, int NS, bool STK, bool DBG>
+__device__ long long g_fwddbg[16 * 8];           // (DBG) per-CTA wall-clock stamps of batch tile 0 at step 10: [cta][sub * 4 + slot]
+__device__ __forceinline__ long long fwd_gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// ---- CTA-pair (cta_group::2) helpers of the PAIR instantiation ----
+__device__ __forceinline__ uint32_t p2_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void p2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t p2_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA load of this CTA's half of a pair's B tile: the bytes are counted on the mbarrier `bar`, a shared::cluster address
+// that may belong to the peer (the pair's leader)
+__device__ __forceinline__ void p2_tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void p2_umma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void p2_umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+// arrives on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair once all MMAs issued so far are done
+__device__ __forceinline__ void p2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void p2_arrive_remote(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void p2_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) { printf("lstm_fwd_v2 (pair): peer handshake timed out\n"); __trap(); }
+  }
+}
+
+// PAIR: two adjacent unit slices of one batch tile form a cta_group::2 pair (cluster 2 x 1): every CTA keeps its own 128
+// gate rows of W_hh (the A operand: M = 256 per pair), the h sub-tile is the pair's shared B operand of which each CTA
+// loads only HALF (16 rows; its TMA bytes are counted on the LEADER's `full` barrier), the leader issues
+// tcgen05.mma.cta_group::2 for both and its commits arrive on `empty` / `tfull` of both CTAs.  Measured basis
+// (tools/probes/probe_mma_rate2.cu): a pair-mode TS instruction with N = 32 costs 29.6 cycles instead of 51.8, an SS one
+// 62.6 instead of 80 -- and the per-SM tile ingest halves.
+template <int P, bool CL, int NS, bool STK, bool DBG, bool PAIR = false>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
@@ -86,19 +140,22 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B): batches of more than 8 tiles are
   // processed as consecutive windows, each a full persistent launch
   extern __shared__ uint8_t smem_raw[];
-  __shared__ long long fst[64];
+  __shared__ unsigned int fst[64];                      // (DBG) low 32 bits of clock64: differences only
+  __shared__ unsigned int wst[4][6];                    // (DBG) per-warp stamps of sub-tile 0's epilogue warps at step 10
   // dbg bits (NVQA_LSTM_DEBUG, timing experiments only -- bits 2..32 change the results): 1 = timeline stamps,
   // 2 = skip the deferred stores, 4 = skip the pre-activation loads, 8 = always load the h tile of step 0 (static data),
   // 16 = issue no MMAs (commits only: pure TMA rate), 32 = issue no TMA loads (plain arrives: pure MMA rate)
-#define F_STAMP(slot) do { if ((dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && t >= 8 && t < 12) fst[(t - 8) * 16 + (slot)] = clock64(); } while (0)
+#define F_STAMP(slot) do { if ((dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && t >= 8 && t < 12) fst[(t - 8) * 16 + (slot)] = (unsigned int)clock64(); } while (0)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   constexpr uint32_t W_KB = 128 * 128;                  // one k-block of the W0 slice: 128 rows x 128 B
   static_assert(NS == 1 || (NS == 2 && !CL), "sub-tile pipelining uses the counter barrier");
+  static_assert(!PAIR || (NS == 2 && P == 2 && !STK), "the pair instantiation is the bf16x2 sub-tile kernel");
   constexpr int SUBN = 64 / NS;                         // batch rows per sub-tile (the N of one MMA)
-  constexpr int NST = NS == 1 ? V2_STAGES : V2_SPLIT_STAGES;
+  constexpr int LOADN = PAIR ? SUBN / 2 : SUBN;         // ... of which this CTA loads LOADN (a pair shares the B operand)
+  constexpr int NST = PAIR ? 2 * V2_SPLIT_STAGES : NS == 1 ? V2_STAGES : V2_SPLIT_STAGES;   // PAIR: both sub-tiles in flight
   constexpr int EPG = V2_EPI / NS;                      // epilogue threads per sub-tile
-  constexpr uint32_t B_PLANE = SUBN * 128;              // one plane of one k-block of the h (sub-)tile: SUBN rows x 128 B
+  constexpr uint32_t B_PLANE = LOADN * 128;             // one plane of one k-block of the h (sub-)tile: LOADN rows x 128 B
   constexpr uint32_t STAGE = P * B_PLANE;
   constexpr uint32_t RING = NST * STAGE + (NS == 1 && P == 1 ? 2 * STAGE : 0);   // NS = 1, P = 1: ring is 32 KB, the tile needs 33 KB
   constexpr uint32_t TB_BYTES = NS == 1 ? 0u : (uint32_t)(64 * V2_TPITCH * 4);   // NS = 1: the transpose tile aliases the idle ring
@@ -108,12 +165,13 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
   const uint32_t tb0 = NS == 1 ? r0 : r0 + RING;
   const uint32_t bar0 = r0 + RING + TB_BYTES;
   const uint32_t full0 = bar0, empty0 = bar0 + 8 * NST, wfull = bar0 + 16 * NST, tfull = wfull + 8 /* x2 */,
-                 gobar = wfull + 24 /* x2 */, w1bar = wfull + 40;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * NST + 48);
+                 gobar = wfull + 24 /* x2 */, w1bar = wfull + 40, pairbar = wfull + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * NST + 56);
   float* tbuf = reinterpret_cast<float*>(smem_raw + (tb0 - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * 32, m0 = b0 + blockIdx.y * 64;
+  const uint32_t prank = PAIR ? p2_rank() : 0u;         // 0 = the pair's leader (issues the MMAs)
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapH) : "memory");
@@ -125,10 +183,18 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       mbar_init(wfull, 1);
       for (int i = 0; i < NS; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(gobar + 8 * i, 1); }
       mbar_init(w1bar, 1);
+      mbar_init(pairbar, 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), 512);
+    if (!PAIR) tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  if (PAIR) {
+    p2_cluster_sync();                                  // both CTAs' mbarriers exist; both are ready to allocate
+    if (warp == 1) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -159,12 +225,18 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           fence_proxy_async();
         }
         if (lane == 0) F_STAMP(sub == 0 ? 0 : 8);
+        if (DBG && (dbg & 1) && lane == 0 && blockIdx.y == 0 && t == 10 && blockIdx.x < 16) g_fwddbg[blockIdx.x * 8 + sub * 4 + 0] = fwd_gtimer();
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % NST;
           const uint32_t ph = (uint32_t)(it / NST) & 1u;
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           if (elect_one_sync()) {
-            if (dbg & 32) mbar_arrive(full0 + 8 * s);
+            if (PAIR) {
+              // both halves of the pair's B tile are counted on the leader's barrier
+              if (prank == 0) mbar_expect_tx(full0 + 8 * s, 2 * STAGE);
+              p2_tma_load_3d(r0 + (uint32_t)s * STAGE, &mapH, p2_mapa(full0 + 8 * s, 0), kb * 64,
+                             t * B + m0 + sub * SUBN + (int)prank * LOADN, 0);
+            } else if (dbg & 32) mbar_arrive(full0 + 8 * s);
             else {
               mbar_expect_tx(full0 + 8 * s, STAGE);
               tma_load_3d(r0 + (uint32_t)s * STAGE, &mapH, full0 + 8 * s, kb * 64, ((dbg & 8) ? 0 : t * B) + m0 + sub * SUBN, 0);   // all P planes in one box
@@ -178,19 +250,24 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_bf16(128, SUBN, false, false);
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, SUBN, false, false);
     constexpr uint32_t idesc2 = make_idesc_bf16(128, 2 * SUBN, false, false);
     constexpr int ACCW = (P >= 2 && STK) ? 2 * SUBN : SUBN;           // accumulator columns per sub-tile
     if (lane == 0) {
       mbar_wait(wfull, 0);
       if (P >= 2) mbar_wait(w1bar, 0);             // plane 1 of the W slice has been stored to TMEM by the epilogue warps
       tc_fence_after();
+      if (PAIR) {
+        // the leader multiplies with the peer's resident weights too: the peer reports them ready
+        if (prank != 0) p2_arrive_remote(p2_mapa(pairbar, 0));
+        else { p2_wait_cluster(pairbar, 0); tc_fence_after(); }
+      }
     }
     // the whole warp walks the loop (warp-uniform control flow and descriptors); one elected lane issues
     __syncwarp();
     int it = 0;
     const uint64_t dw_base = make_kmajor_sw128_desc(w0), dr_base = make_kmajor_sw128_desc(r0);
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < (PAIR && prank != 0 ? 0 : T); ++t) {
       if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }
 #pragma unroll 1
       for (int sub = 0; sub < NS; ++sub) {
@@ -220,7 +297,11 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
               // more than its 32 tensor cycles); shared memory holds plane 1 (one product)
               const uint64_t dh1 = dh0 + (uint64_t)(B_PLANE >> 4);
               const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8);
-              if (STK) {
+              if (PAIR) {
+                p2_umma_f16(tacc, dw, dh0, idesc, accf);          // [W1 ; W1'] . h0   (A: each CTA's own shared memory)
+                p2_umma_f16_ts(tacc, wt, dh1, idesc, 1u);         // [W0 ; W0'] . h1   (A: each CTA's own tensor memory)
+                p2_umma_f16_ts(tacc, wt, dh0, idesc, 1u);         // [W0 ; W0'] . h0
+              } else if (STK) {
                 umma_f16_ts(tacc, wt, dh0, idesc2, accf);         // W0 . [h0 ; h1]  (A from tensor memory, N = 2 SUBN)
                 umma_f16(tacc, dw, dh0, idesc, 1u);               // W1 . h0         (A from shared memory) += columns [0, SUBN)
               } else {
@@ -232,8 +313,13 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
               umma_f16(tacc, dw, dh0, idesc, accf);
             }
           }
-          umma_commit(empty0 + 8 * s);
-          if (kb == KB - 1) umma_commit(tfull + 8 * sub);
+          if (PAIR) {
+            p2_commit(empty0 + 8 * s);
+            if (kb == KB - 1) p2_commit(tfull + 8 * sub);
+          } else {
+            umma_commit(empty0 + 8 * s);
+            if (kb == KB - 1) umma_commit(tfull + 8 * sub);
+          }
         }
         __syncwarp();
       }
@@ -300,6 +386,9 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       }
       mbar_wait(tfull + 8 * sub, (uint32_t)t & 1u);
       tc_fence_after();
+#define W_STAMP(slot) do { if (DBG && (dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && t == 10 && sub == 0 && lane == 0) wst[warp - 2][slot] = (unsigned int)clock64(); } while (0)
+      W_STAMP(0);
+      if (DBG && (dbg & 1) && leader && blockIdx.y == 0 && t == 10 && blockIdx.x < 16) g_fwddbg[blockIdx.x * 8 + sub * 4 + 1] = fwd_gtimer();
       if (DBG && t == 0) t_step0 = clock64();                  // first accumulator complete: W0 landed, first tile multiplied
       if (threadIdx.x == 64) F_STAMP(1);
       if (NS > 1 && threadIdx.x == 64 + EPG) F_STAMP(15);
@@ -320,7 +409,9 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         for (int j = 0; j < 32; ++j) dst[(size_t)j * V2_TPITCH] = acc[j];
       }
       tc_fence_before();
+      W_STAMP(1);
       v2_bar_sync(bid + 2, EPG);
+      W_STAMP(2);
       if (threadIdx.x == 64) F_STAMP(2);
       float gi[8], gf[8], go[8], gg[8], cn[8], hn[8];
       if (active) {
@@ -350,6 +441,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         for (int j = 0; j < 8; ++j) { gi[j] = gf[j] = go[j] = gg[j] = cn[j] = hn[j] = 0.f; }
       }
       // (1) the only output the NEXT step depends on: h_t as bf16 planes, row (t+1)*B + b of [P][(T+1)B][H]
+      W_STAMP(3);
       if (rowok) {
         __nv_bfloat16 pl[3][8];
 #pragma unroll
@@ -368,12 +460,20 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       // overwrite) are ordered before later async-proxy accesses; one thread's gpu-scope release is made cumulative
       // over the CTA by the barrier
       if (threadIdx.x == 64) F_STAMP(3);
+      W_STAMP(4);
       fence_proxy_async();
       if (CL) {
         if (t + 1 < T) { __syncwarp(); v2_cluster_arrive(); }     // every thread releases its own stores to the cluster
       } else {
         v2_bar_sync(bid + 1, EPG);
-        if (leader) { if (threadIdx.x == 64) F_STAMP(4); v2_arrive(myctr); if (threadIdx.x == 64) F_STAMP(5); }
+        W_STAMP(5);
+        if (leader) {
+          if (threadIdx.x == 64) F_STAMP(4);
+          if (DBG && (dbg & 1) && blockIdx.y == 0 && t == 10 && blockIdx.x < 16) g_fwddbg[blockIdx.x * 8 + sub * 4 + 2] = fwd_gtimer();
+          v2_arrive(myctr);
+          if (DBG && (dbg & 1) && blockIdx.y == 0 && t == 10 && blockIdx.x < 16) g_fwddbg[blockIdx.x * 8 + sub * 4 + 3] = fwd_gtimer();
+          if (threadIdx.x == 64) F_STAMP(5);
+        }
         v2_bar_sync(bid + 3, EPG);                 // keep the SM's memory pipeline clear until the release is out ...
       }
       if (t + 1 < T) mbar_wait(gobar + 8 * sub, (uint32_t)(t + 1) & 1u);   // ... and until the next step's first loads are issued
@@ -403,21 +503,31 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       printf("lstm_fwd_v2 kernel (cycles from entry): prologue done %lld, first accumulator %lld, last step done %lld\n",
              t_prologue - t_entry, t_step0 - t_entry, clock64() - t_entry);
       printf("lstm_fwd_v2 timeline (cycles after the barrier opened): t | mma_done transposed math+stores_done all_done arrived go deferred_issued | step\n");
+      auto df = [](unsigned int a, unsigned int b) { return (int)(a - b); };
       for (int i = 1; i < 4; ++i) {
-        const long long* e = fst + i * 16;
-        printf("%2d | %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", 8 + i, e[1] - e[0], e[2] - e[0], e[3] - e[0], e[4] - e[0], e[5] - e[0],
-               e[6] - e[0], e[7] - e[0], e[0] - fst[(i - 1) * 16]);
-        printf("   sub0: loads issued %6lld first kb landed %6lld last kb landed %6lld", e[9] - e[0], e[11] - e[0], e[12] - e[0]);
+        const unsigned int* e = fst + i * 16;
+        printf("%2d | %6d %6d %6d %6d %6d %6d %6d | %6d\n", 8 + i, df(e[1], e[0]), df(e[2], e[0]), df(e[3], e[0]), df(e[4], e[0]), df(e[5], e[0]),
+               df(e[6], e[0]), df(e[7], e[0]), df(e[0], fst[(i - 1) * 16]));
+        printf("   sub0: loads issued %6d first kb landed %6d last kb landed %6d", df(e[9], e[0]), df(e[11], e[0]), df(e[12], e[0]));
         if (NS > 1)
-          printf(" | sub1: open %6lld loads issued %6lld first landed %6lld last landed %6lld mma_done %6lld", e[8] - e[0], e[10] - e[0],
-                 e[13] - e[0], e[14] - e[0], e[15] - e[0]);
+          printf(" | sub1: open %6d loads issued %6d first landed %6d last landed %6d mma_done %6d", df(e[8], e[0]), df(e[10], e[0]),
+                 df(e[13], e[0]), df(e[14], e[0]), df(e[15], e[0]));
         printf("\n");
+      }
+      if (fst[2 * 16]) {
+        printf("   step 10, sub-tile 0, per epilogue warp (cycles after the barrier opened): accumulator seen | tile stored | transposed-bar | math done | planes stored | all-stored-bar\n");
+        for (int w = 0; w < 4; ++w)
+          printf("   warp %d: %6d %6d %6d %6d %6d %6d\n", w + 2, df(wst[w][0], fst[2 * 16]), df(wst[w][1], fst[2 * 16]), df(wst[w][2], fst[2 * 16]),
+                 df(wst[w][3], fst[2 * 16]), df(wst[w][4], fst[2 * 16]), df(wst[w][5], fst[2 * 16]));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (PAIR) {
+    p2_cluster_sync();                                  // the peer's MMAs (issued by the leader) and its epilogue are done
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  } else if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1162,11 +1272,15 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   const int tiles = ceil_div(B, 64), max_tiles = std::min(8, num_sms / (H / 32));
   if (max_tiles < 1) return -1;
   // NVQA_LSTM_FWD_SPLIT=0: one 64-row tile per CTA (template NS = 1) instead of two software-pipelined 32-row sub-tiles
-  static int split = -1;
+  static int split = -1, pair = -1;
   if (split < 0) { const char* e = getenv("NVQA_LSTM_FWD_SPLIT"); split = e ? atoi(e) : 1; }
-  const size_t ring = split ? (size_t)V2_SPLIT_STAGES * P * 4096 : (size_t)V2_STAGES * P * 8192 + (P == 1 ? 2 * 8192 : 0);
+  // NVQA_LSTM_PAIR=0: no cta_group::2 pairs of unit slices (pairs: sub-tile kernel, bf16x2 only, even number of slices)
+  if (pair < 0) { const char* e = getenv("NVQA_LSTM_PAIR"); pair = e ? atoi(e) : 1; }
+  const bool use_pair = pair && split && P == 2 && (H / 32) % 2 == 0;
+  const size_t ring = use_pair ? (size_t)2 * V2_SPLIT_STAGES * P * 2048
+                    : split ? (size_t)V2_SPLIT_STAGES * P * 4096 : (size_t)V2_STAGES * P * 8192 + (P == 1 ? 2 * 8192 : 0);
   const size_t tile = (size_t)64 * V2_TPITCH * 4;
-  const size_t smem = (size_t)KB * 16384 + ring + (split ? tile : 0) + 1024 + 256;
+  const size_t smem = (size_t)KB * 16384 + ring + (split ? tile : 0) + 1024 + (use_pair ? 512 : 256);   // alignment slack + barriers
   if ((!split && ring < tile) || smem > (size_t)max_smem) return -1;
 
   __nv_bfloat16* wp = nullptr;
@@ -1175,7 +1289,7 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   CUtensorMap mapW, mapH;
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 32, &mapW));
   if (hp_plane_rows <= 0) hp_plane_rows = (long long)(T + 1) * B;
-  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, split ? 32 : 64, &mapH, hp_plane_rows * H, P));
+  NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, use_pair ? 16 : split ? 32 : 64, &mapH, hp_plane_rows * H, P));
   long long hp_plane = hp_plane_rows * H;
   const __nv_bfloat16* w1 = wp;                                    // the TMEM-resident plane: plane 0 (plane 1 goes to SMEM)
   int KBv = KB;
@@ -1210,7 +1324,9 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     if (stack < 0) { const char* e = getenv("NVQA_LSTM_STACK"); stack = e ? atoi(e) : 0; }
     const void* fn;
 #define NVQA_FWD(P_, NS_, STK_, DBG_) (const void*)lstm_fwd_v2_kernel<P_, false, NS_, STK_, DBG_>
-    if (dbg) fn = split ? (P == 2 ? NVQA_FWD(2, 2, false, true) : NVQA_FWD(1, 2, false, true))
+    if (use_pair) fn = dbg ? (const void*)lstm_fwd_v2_kernel<2, false, 2, false, true, true>
+                           : (const void*)lstm_fwd_v2_kernel<2, false, 2, false, false, true>;
+    else if (dbg) fn = split ? (P == 2 ? NVQA_FWD(2, 2, false, true) : NVQA_FWD(1, 2, false, true))
                         : (P == 2 ? NVQA_FWD(2, 1, false, true) : NVQA_FWD(1, 1, false, true));
     else if (P == 2 && stack) fn = split ? NVQA_FWD(2, 2, true, false) : NVQA_FWD(2, 1, true, false);
     else fn = split ? (P == 2 ? NVQA_FWD(2, 2, false, false) : NVQA_FWD(1, 2, false, false))
@@ -1219,11 +1335,27 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeCooperative; attr.val.cooperative = 1;
-    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pair ? 2 : 1;
+    if (use_pair && getenv("NVQA_LSTM_NOCOOP")) { cfg.attrs = attr + 1; cfg.numAttrs = 1; }   // ncu: see lstm_bwd_v3
     NVQA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
     ++g_launches;
+    if (dbg & 1) {
+      long long hst[16 * 8];
+      NVQA_CUDA(cudaStreamSynchronize(s));
+      NVQA_CUDA(cudaMemcpyFromSymbol(hst, g_fwddbg, sizeof(hst)));
+      long long t0 = hst[0];
+      for (int i = 0; i < 16 * 8; ++i) if (hst[i] && hst[i] < t0) t0 = hst[i];
+      printf("lstm_fwd_v2 step 10, batch tile 0, per CTA (ns): sub0 open | accumulator | release issued | released || sub1 open | accumulator | release issued | released\n");
+      for (int cta = 0; cta < 16; ++cta) {
+        printf("   cta %2d:", cta);
+        for (int j = 0; j < 8; ++j) printf(" %6lld%s", hst[cta * 8 + j] - t0, j == 3 ? " ||" : "");
+        printf("\n");
+      }
+    }
   }
   return 0;
 }
