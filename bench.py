@@ -377,7 +377,13 @@ def run_ours(args):
                                           "over CUDA-IPC peer memory (csrc/dp_fused.cu)" if fused else
                                           "NCCL all-reduce, 3 buckets overlapped with backward"), "dropout": "in-kernel counter hash, p=0.5",
                            "l2": "working set (params+grads+rms 166 MB, activations > 600 MB) exceeds the 126 MB L2; "
-                                 "no explicit flush"},
+                                 "no explicit flush",
+                           "kernels": {"lstm_fwd": ("cta_group::2 pairs, " if os.environ.get("NVQA_LSTM_PAIR", "1") != "0" else "")
+                                                   + ("2 pipelined sub-tiles" if os.environ.get("NVQA_LSTM_FWD_SPLIT", "1") != "0"
+                                                      else "one 64-row tile"),
+                                       "lstm_bwd": "4-CTA clusters, DSMEM split-K reduction",
+                                       "gemm": "persistent CTAs, 2 TMEM accumulator stages"
+                                               if os.environ.get("NVQA_GEMM_PERSIST", "1") != "0" else "one tile per CTA"}},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps, "last_loss": losses[-1]},
