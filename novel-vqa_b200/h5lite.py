@@ -22,6 +22,7 @@ writer's output could not be opened with libhdf5 here; it follows the specificat
 
 I/O plumbing only: nothing here is on the timed path.
 """
+import mmap
 import struct
 import zlib
 
@@ -60,7 +61,7 @@ class Dataset:
     def read(self):
         """The whole dataset as a native-endian C-contiguous array (``:all()`` of torch-hdf5, ``[...]`` of h5py)."""
         a = self._f._read_data(self._msgs, self.shape, self.dtype)
-        return np.ascontiguousarray(a.astype(a.dtype.newbyteorder("=")))
+        return np.array(a, dtype=a.dtype.newbyteorder("="), order="C", copy=True)     # ONE copy out of the mapped file
 
 
 class Group:
@@ -90,7 +91,10 @@ class File(Group):
 
     def __init__(self, path):
         with open(path, "rb") as fh:
-            self._b = fh.read()
+            try:                                          # data_img.h5 is gigabytes: map it, copy only what is read
+                self._b = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            except ValueError:                            # empty file
+                self._b = fh.read()
         self.path = path
         b = self._b
         off = 0
@@ -122,6 +126,8 @@ class File(Group):
         Group.__init__(self, self, "/", self._links_of(self._messages(root)))
 
     def close(self):
+        if isinstance(self._b, mmap.mmap):
+            self._b.close()
         self._b = b""
 
     def __enter__(self):
@@ -237,7 +243,7 @@ class File(Group):
             for i in range(n):
                 noff, ohdr = struct.unpack_from("<QQ", b, a + 8 + 40 * i)
                 s = seg + noff
-                links[b[s:b.index(b"\0", s)].decode()] = ohdr
+                links[b[s:b.find(b"\0", s)].decode()] = ohdr
             return
         if b[a:a + 4] != b"TREE" or b[a + 4] != 0:
             raise H5Error("bad group B-tree node")
@@ -312,7 +318,11 @@ class File(Group):
                 raw = d[4:4 + size]
             elif cls == 1:
                 addr, size = struct.unpack_from("<QQ", d, 2)
-                raw = None if addr == UNDEF else self._b[self._base + addr:self._base + addr + nbytes]
+                if addr == UNDEF:
+                    return np.zeros(shape, dtype)
+                if self._base + addr + nbytes > len(self._b):
+                    raise H5Error("dataset extends past the end of the file")
+                return np.frombuffer(self._b, dtype=dtype, count=n, offset=self._base + addr).reshape(shape)   # a view
             elif cls == 2:
                 ndim = d[2]
                 btree = struct.unpack_from("<Q", d, 3)[0]

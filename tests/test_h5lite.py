@@ -138,3 +138,33 @@ def test_loader_reads_compressed_chunked_files_too(tmp_path):
     for s in ("train", "val"):
         for k in a[s].fields:
             assert np.array_equal(a[s][k], b[s][k]), (s, k)
+
+
+def test_round_trip_property(tmp_path):
+    """Random shapes / dtypes / storage layouts (hypothesis): what the writer stores the reader returns bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    dtypes = st.sampled_from(["<u1", "<u2", "<u4", "<u8", "<i1", "<i2", "<i4", "<i8", "<f4", "<f8"])
+    shapes = st.lists(st.integers(0, 7), min_size=1, max_size=3).map(tuple)
+    counter = [0]
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(dtypes, shapes), min_size=1, max_size=6), st.sampled_from([None, 1, 2, 5]),
+           st.booleans(), st.integers(0, 2 ** 31 - 1))
+    def run(specs, chunks, gz, seed):
+        rng = np.random.default_rng(seed)
+        d = {}
+        for i, (dt, shp) in enumerate(specs):
+            a = rng.integers(0, 200, size=shp).astype(dt) if dt[1] in "ui" else rng.standard_normal(shp).astype(dt)
+            d[f"ds_{i}_{'x' * (i * 3)}"] = a                          # names of different lengths (heap padding)
+        counter[0] += 1
+        p = str(tmp_path / f"p{counter[0]}.h5")
+        kw = {} if chunks is None else {"chunks": chunks, "compression": "gzip" if gz else None}
+        h5lite.write(p, d, **kw)
+        with h5lite.File(p) as f:
+            assert sorted(f.keys()) == sorted(d)
+            for k, v in d.items():
+                got = f[k].read()
+                assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v)
+
+    run()
