@@ -40,13 +40,13 @@ __device__ __forceinline__ void v2_arrive(unsigned int* ctr) {
   asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
   if (old == 0xFFFFFFFFu) __trap();
 }
-__device__ __forceinline__ void v2_wait(unsigned int* ctr, unsigned int target) {
+__device__ __forceinline__ void v2_wait(unsigned int* ctr, unsigned int target, unsigned int poll_ns = 64) {
   const long long t0 = clock64();
   while (true) {
     unsigned int v;
     asm volatile("atom.acquire.gpu.global.add.u32 %0, [%1], 0;" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= target) break;
-    __nanosleep(64);
+    __nanosleep(poll_ns);
     if (clock64() - t0 > 4000000000LL) {
       printf("lstm_persistent_v2: group barrier timed out (block %d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, v, target);
       __trap();
@@ -135,7 +135,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                    float* __restrict__ h, __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
                    const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg_arg,
                    int b0, int bend) {
-  const int dbg = DBG ? dbg_arg : 0;
+  const int dbg = DBG ? (dbg_arg & 0xFFFF) : 0;        // the upper half of dbg_arg is the poll interval of the step barrier (ns)
   const long long t_entry = DBG ? clock64() : 0;
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B): batches of more than 8 tiles are
   // processed as consecutive windows, each a full persistent launch
@@ -220,7 +220,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
       for (int sub = 0; sub < NS; ++sub) {
         if (t > 0) {
           // h_{t-1} of this batch (sub-)tile is complete
-          if (!CL && lane == 0) v2_wait(counter + 32 * blockIdx.y + 16 * sub, (unsigned int)t * gridDim.x);
+          if (!CL && lane == 0) v2_wait(counter + 32 * blockIdx.y + 16 * sub, (unsigned int)t * gridDim.x, (unsigned int)dbg_arg >> 16);
           __syncwarp();
           fence_proxy_async();
         }
@@ -896,7 +896,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
                    float* __restrict__ dc_init, const int32_t* __restrict__ len, int T, int B, int H, int KB,
                    unsigned int* counter, int dbg_arg, int b0, int bend) {
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B)
-  const int dbg = DBG ? dbg_arg : 0;                // the production instantiation compiles the stamps away
+  const int dbg = DBG ? (dbg_arg & 0xFFFF) : 0;     // the production instantiation compiles the stamps away
   extern __shared__ uint8_t smem_raw[];
   __shared__ long long stamps[32];
   const uint32_t raw = smem_u32(smem_raw);
@@ -960,7 +960,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     for (int t = T - 1; t >= tlast; --t) {
       const unsigned int k = (unsigned int)(T - 1 - t);
       if (lane == 0) {
-        v2_wait(counter, (k + 1) * G);         // da_t of this batch tile is complete
+        v2_wait(counter, (k + 1) * G, (unsigned int)dbg_arg >> 16);         // da_t of this batch tile is complete
         if (dbg && blockIdx.z == 0 && t == 10) g_v3dbg[cta * 4 + 1] = v3_gtimer();
       }
       __syncwarp();
@@ -1294,7 +1294,9 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   const __nv_bfloat16* w1 = wp;                                    // the TMEM-resident plane: plane 0 (plane 1 goes to SMEM)
   int KBv = KB;
   static const int dbg = getenv("NVQA_LSTM_DEBUG") ? std::max(1, atoi(getenv("NVQA_LSTM_DEBUG"))) : 0;
-  int dbgv = dbg;
+  static int poll_ns = -1;
+  if (poll_ns < 0) { const char* e = getenv("NVQA_LSTM_POLL_NS"); poll_ns = e ? atoi(e) & 0x7FFF : 64; }   // pause between two polls of the step barrier
+  int dbgv = dbg | (poll_ns << 16);
   static int use_cl = -1;
   if (use_cl < 0) { const char* e = getenv("NVQA_LSTM_CLUSTER16"); use_cl = e ? atoi(e) : 0; }   // measured on B200: only part of the 8 clusters of 16 is co-resident (0.82 ms vs 0.48 ms)
   // batches of more than 8 tiles (512 rows) run as consecutive windows of the batch, each a full persistent launch
@@ -1405,7 +1407,9 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     // generation 3: 4-CTA clusters over the K-splits, split-K reduction through distributed shared memory;
     // batches of more than 8 tiles (512 rows) run as consecutive windows, each a full persistent launch
     static const int dbg = getenv("NVQA_LSTM_DEBUG") != nullptr;
-    int dbgv = dbg;
+    static int poll_ns = -1;
+    if (poll_ns < 0) { const char* e = getenv("NVQA_LSTM_POLL_NS"); poll_ns = e ? atoi(e) & 0x7FFF : 64; }
+    int dbgv = dbg | (poll_ns << 16);
     CUtensorMap mapDA3;                            // both planes of a da tile in one TMA box
     NVQA_TRY(get_map(ws, dap, T * B, 4 * H, P, 64, &mapDA3, dap_plane_rows * 4 * H, P));
     const __nv_bfloat16* wt = wp;                  // generation 3 keeps plane 0 in TMEM and plane 1 in shared memory
