@@ -272,3 +272,29 @@ def arch1_blocks_from_autoencoder(saved, V, E):
         raise ValueError(f"lookup has shape {lookup.shape}, expected {(E, V + 1)}")
     emb = np.concatenate([np.ascontiguousarray(lookup[:, :V]).ravel(), np.zeros(E, dtype=np.float32)])
     return np.ascontiguousarray(saved["encoder"], dtype=np.float32).ravel(), emb
+
+
+def arch2_encoder_from_autoencoder(ae_encoder_flat, ae_lookup_flat, V=None, E=None):
+    """003_train_vqa_arch2/003_train_ae_based.lua:150-152,191: ``encoder_model.encoder = modelT.ae.encoder:clone()``,
+    ``encoder_model.lookup_table = modelT.ae.lookup_table:clone()``, then ``encoder_model:getParameters()`` -- the arch2
+    ``encoder_w_q`` block is the autoencoder's encoder LSTM parameters followed by its LookupTable(V+1, E) weight
+    (``misc/Encoder_lstm.lua:66-83``: core first, lookup table second), both taken as they are.  ``cnn_w`` and
+    ``multimodal_w`` stay ``uniform(-0.08, 0.08)`` (``:188-194``).  Inputs: the flat parameter vectors of an autoencoder
+    (``AEModel.get_params(BLOCK_AE_ENCODER)`` / ``(BLOCK_AE_LOOKUP)``, or tensors read with ``t7.load``)."""
+    enc = np.ascontiguousarray(ae_encoder_flat, dtype=np.float32).ravel()
+    lut = np.ascontiguousarray(ae_lookup_flat, dtype=np.float32).ravel()
+    if V is not None and E is not None and lut.size != (V + 1) * E:
+        raise ValueError(f"lookup table has {lut.size} elements, expected (V + 1) x E = {(V + 1) * E}")
+    return np.concatenate([enc, lut])
+
+
+def arch2_cnn_from_linear(weight, bias):
+    """003_train_ae_based_wp_vgg.lua:174 / _wp_inc.lua: ``cnn_projection = nn.Sequential():add(modelT.cnn:get(40):clone())``
+    -- the weakly-paired model's image projection nn.Linear(nhimage, E) becomes the arch2 ``cnn_w`` block
+    (``getParameters()`` order: weight [E x nhimage], then bias [E])."""
+    w = np.ascontiguousarray(weight, dtype=np.float32)
+    b = np.ascontiguousarray(bias, dtype=np.float32).ravel()
+    if w.ndim != 2 or w.shape[0] != b.size:
+        raise ValueError(f"Linear weight {w.shape} and bias {b.shape} do not belong together")
+    return np.concatenate([w.ravel(), b])
+

@@ -3,6 +3,7 @@ file, round trips, strided tensors / shared storages, CudaTensor class names, an
 import struct
 
 import numpy as np
+import pytest
 
 from novel_vqa_b200 import t7
 
@@ -122,3 +123,27 @@ def test_result_json_emission(tmp_path):
         assert b[i]["answer"] == f"ans{cand[int(np.argmax([scores[i, c - 1] for c in cand]))]}"
     lf = results.late_fusion_scores(scores, 2 * scores, 0.25, 0.75)
     assert lf.dtype == np.float64 and np.allclose(lf, 1.75 * scores, rtol=1e-6)
+
+
+def test_autoencoder_to_arch2_conversion():
+    """003_train_vqa_arch2/003_train_ae_based.lua:150-152,191: encoder_w_q = [AE encoder LSTM | AE LookupTable], in the
+    layout the arch2 oracle (and the library) splits it with; cnn_w from a Linear of the weakly-paired model."""
+    from oracle import ae as AE, arch1 as A, arch2 as A2
+    V, E, H = 13, 8, 8
+    acfg = AE.AEConfig(V=V, E=E, H=H, L=1, T=5)
+    r = np.random.default_rng(2)
+    enc = r.standard_normal(acfg.n_enc).astype(np.float32)
+    lut = r.standard_normal(acfg.n_lut).astype(np.float32)
+    blk = t7.arch2_encoder_from_autoencoder(enc, lut, V=V, E=E)
+    c2 = A2.Arch2Config(V=V, E=E, H=H, L=1, I=6, O=3, T=5)
+    assert blk.size == c2.n_enc
+    parts = A.split_flat(blk, c2.enc_layout())
+    ae_parts = A.split_flat(enc, acfg.enc_layout())
+    for k in ("Wi0", "bi0", "Wh0", "bh0"):
+        assert np.array_equal(parts[k], ae_parts[k]), k
+    assert np.array_equal(parts["lookup"], lut.reshape(V + 1, E))
+    with pytest.raises(ValueError):
+        t7.arch2_encoder_from_autoencoder(enc, lut[:-1], V=V, E=E)
+    W, b = r.standard_normal((E, 6)).astype(np.float32), r.standard_normal(E).astype(np.float32)
+    cnn = A.split_flat(t7.arch2_cnn_from_linear(W, b), c2.cnn_layout())
+    assert np.array_equal(cnn["Wcnn"], W) and np.array_equal(cnn["bcnn"], b)
