@@ -1,4 +1,4 @@
-// Probe (written for round 2, not yet run on hardware): what does a cp.async.bulk.tensor box cost the issuing warp, and
+// Probe: what does a cp.async.bulk.tensor box cost the issuing warp, and
 // how long until a half h-tile has landed, as a function of the box shape?  The persistent LSTM kernels measured ~316
 // cycles per issued box whatever its size (8 boxes = 2,500 cycles before the last one is even issued).
 // Variants over the SAME 32 KB of global memory ([2 planes][16 rows][512 bf16], row pitch 1 KB, as the h planes):
