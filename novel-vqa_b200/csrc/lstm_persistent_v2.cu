@@ -95,6 +95,13 @@ __device__ __forceinline__ void p2_tma_load_3d(uint32_t dst, const CUtensorMap* 
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// the same for a 4-D box (64 columns, rows, planes, k-blocks): several k-blocks of the half tile in one instruction
+__device__ __forceinline__ void p2_tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void p2_umma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
@@ -128,13 +135,24 @@ __device__ __forceinline__ void p2_wait_cluster(uint32_t bar, uint32_t parity) {
 // tcgen05.mma.cta_group::2 for both and its commits arrive on `empty` / `tfull` of both CTAs.  Measured basis
 // (tools/probes/probe_mma_rate2.cu): a pair-mode TS instruction with N = 32 costs 29.6 cycles instead of 51.8, an SS one
 // 62.6 instead of 80 -- and the per-SM tile ingest halves.
-template <int P, bool CL, int NS, bool STK, bool DBG, bool PAIR = false>
+// BOX4 / POLL1 (EXPERIMENTAL: written at the end of round 1 from the measurements of DESIGN 5.2, compiled, NOT yet run on
+// hardware -- default off, NVQA_LSTM_BOX4D=1 / NVQA_LSTM_POLL1=1):
+//   BOX4   the CTA's half sub-tile is fetched by TWO 4-D TMA boxes of 4 k-blocks (16 KB) with two `full` / `empty`
+//          barriers instead of eight: 2 instead of 8 try_wait + expect_tx + issue rounds for the TMA warp and 2 instead
+//          of 8 waits for the MMA warp per work item (a lone warp issues such boxes in ~80 cycles each and the data has
+//          landed ~800 cycles later; inside the kernel the eight small boxes take 2,500 cycles to issue)
+//   POLL1  one warp per sub-tile polls `tfull` / `go`, the other three sleep in a named barrier: 2 instead of 8 warps
+//          spinning on the SM's mbarrier unit while the TMA / MMA warps work through theirs
+template <int P, bool CL, int NS, bool STK, bool DBG, bool PAIR = false, bool BOX4 = false, bool POLL1 = false>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
                    float* __restrict__ h, __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
                    const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg_arg,
-                   int b0, int bend) {
+                   int b0, int bend, const __grid_constant__ CUtensorMap mapH4) {
+  static_assert(!BOX4 || PAIR, "4-D boxes are wired into the pair kernel only");
+  static_assert(!POLL1 || NS == 2, "the single-poller barriers are numbered for the sub-tile kernel");
+  constexpr int KBB = 4;                                // BOX4: k-blocks per TMA box (a "big stage" = KBB ring stages)
   const int dbg = DBG ? (dbg_arg & 0xFFFF) : 0;        // the upper half of dbg_arg is the poll interval of the step barrier (ns)
   const long long t_entry = DBG ? clock64() : 0;
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B): batches of more than 8 tiles are
@@ -226,6 +244,22 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         }
         if (lane == 0) F_STAMP(sub == 0 ? 0 : 8);
         if (DBG && (dbg & 1) && lane == 0 && blockIdx.y == 0 && t == 10 && blockIdx.x < 16) g_fwddbg[blockIdx.x * 8 + sub * 4 + 0] = fwd_gtimer();
+        if (BOX4) {
+          // `it` counts big stages here: NST / KBB of them, KB / KBB per work item
+          for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
+            const int bs = it % (NST / KBB);
+            const uint32_t ph = (uint32_t)(it / (NST / KBB)) & 1u;
+            mbar_wait(empty0 + 8 * bs, ph ^ 1u);
+            if (elect_one_sync()) {
+              if (prank == 0) mbar_expect_tx(full0 + 8 * bs, 2 * KBB * STAGE);
+              p2_tma_load_4d(r0 + (uint32_t)bs * KBB * STAGE, &mapH4, p2_mapa(full0 + 8 * bs, 0), 0,
+                             t * B + m0 + sub * SUBN + (int)prank * LOADN, 0, hb * KBB);
+              if (hb == KB / KBB - 1) mbar_arrive(gobar + 8 * sub);
+            }
+            __syncwarp();
+          }
+          continue;
+        }
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % NST;
           const uint32_t ph = (uint32_t)(it / NST) & 1u;
@@ -272,6 +306,34 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
 #pragma unroll 1
       for (int sub = 0; sub < NS; ++sub) {
       const uint32_t tacc = tmem_base + (uint32_t)(sub * ACCW);       // this sub-tile's accumulator columns
+      if (BOX4) {
+        for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
+          const int bs = it % (NST / KBB);
+          const uint32_t ph = (uint32_t)(it / (NST / KBB)) & 1u;
+          mbar_wait(full0 + 8 * bs, ph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int kbl = 0; kbl < KBB; ++kbl) {
+              const int kb = hb * KBB + kbl;
+              const uint64_t dwk = dw_base + (uint64_t)(((uint32_t)kb * W_KB) >> 4);
+              const uint64_t dhk = dr_base + (uint64_t)(((uint32_t)(bs * KBB + kbl) * STAGE) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t dw = dwk + (uint64_t)(k * 2), dh0 = dhk + (uint64_t)(k * 2), dh1 = dh0 + (uint64_t)(B_PLANE >> 4);
+                const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8);
+                p2_umma_f16(tacc, dw, dh0, idesc, (kb | k) ? 1u : 0u);
+                p2_umma_f16_ts(tacc, wt, dh1, idesc, 1u);
+                p2_umma_f16_ts(tacc, wt, dh0, idesc, 1u);
+              }
+            }
+            p2_commit(empty0 + 8 * bs);
+            if (hb == KB / KBB - 1) p2_commit(tfull + 8 * sub);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int kb = 0; kb < KB; ++kb, ++it) {
         const int s = it % NST;
         const uint32_t ph = (uint32_t)(it / NST) & 1u;
@@ -384,7 +446,12 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           pv[g][1] = *reinterpret_cast<const float4*>(src + 4);
         }
       }
-      mbar_wait(tfull + 8 * sub, (uint32_t)t & 1u);
+      if (POLL1) {
+        if ((et & (EPG - 1)) < 32) mbar_wait(tfull + 8 * sub, (uint32_t)t & 1u);    // one warp polls ...
+        v2_bar_sync(8 + sub, EPG);                                                  // ... the others sleep here
+      } else {
+        mbar_wait(tfull + 8 * sub, (uint32_t)t & 1u);
+      }
       tc_fence_after();
 #define W_STAMP(slot) do { if (DBG && (dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && t == 10 && sub == 0 && lane == 0) wst[warp - 2][slot] = (unsigned int)clock64(); } while (0)
       W_STAMP(0);
@@ -476,7 +543,14 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         }
         v2_bar_sync(bid + 3, EPG);                 // keep the SM's memory pipeline clear until the release is out ...
       }
-      if (t + 1 < T) mbar_wait(gobar + 8 * sub, (uint32_t)(t + 1) & 1u);   // ... and until the next step's first loads are issued
+      if (t + 1 < T) {                             // ... and until the next step's first loads are issued
+        if (POLL1) {
+          if ((et & (EPG - 1)) < 32) mbar_wait(gobar + 8 * sub, (uint32_t)(t + 1) & 1u);
+          v2_bar_sync(10 + sub, EPG);
+        } else {
+          mbar_wait(gobar + 8 * sub, (uint32_t)(t + 1) & 1u);
+        }
+      }
       if (threadIdx.x == 64) F_STAMP(6);
       // (3) everything only the backward pass needs, off the critical path
       if (rowok && !(dbg & 2)) {
@@ -1290,6 +1364,12 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 32, &mapW));
   if (hp_plane_rows <= 0) hp_plane_rows = (long long)(T + 1) * B;
   NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, use_pair ? 16 : split ? 32 : 64, &mapH, hp_plane_rows * H, P));
+  // EXPERIMENTAL variants of the pair kernel (see the kernel's header comment): default off
+  static int box4 = -1, poll1 = -1;
+  if (box4 < 0) { const char* e = getenv("NVQA_LSTM_BOX4D"); box4 = e ? atoi(e) : 0; }
+  if (poll1 < 0) { const char* e = getenv("NVQA_LSTM_POLL1"); poll1 = e ? atoi(e) : 0; }
+  CUtensorMap mapH4 = mapH;
+  if (use_pair && box4) NVQA_TRY(get_map_kb(ws, hp, (T + 1) * B, H, P, 16, 4, &mapH4, hp_plane_rows * H));
   long long hp_plane = hp_plane_rows * H;
   const __nv_bfloat16* w1 = wp;                                    // the TMEM-resident plane: plane 0 (plane 1 goes to SMEM)
   int KBv = KB;
@@ -1305,7 +1385,7 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     dim3 grid(H / 32, ceil_div(bend - b0, 64));
     NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
     void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter, &dbgv,
-                    &b0, &bend};
+                    &b0, &bend, &mapH4};
     if (use_cl && !split && grid.x == 16) {
       // one 16-CTA cluster per batch tile: hardware cluster barrier per step, plain (non-cooperative) launch
       const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true, 1, false, false> : (const void*)lstm_fwd_v2_kernel<1, true, 1, false, false>;
@@ -1326,8 +1406,12 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     if (stack < 0) { const char* e = getenv("NVQA_LSTM_STACK"); stack = e ? atoi(e) : 0; }
     const void* fn;
 #define NVQA_FWD(P_, NS_, STK_, DBG_) (const void*)lstm_fwd_v2_kernel<P_, false, NS_, STK_, DBG_>
-    if (use_pair) fn = dbg ? (const void*)lstm_fwd_v2_kernel<2, false, 2, false, true, true>
-                           : (const void*)lstm_fwd_v2_kernel<2, false, 2, false, false, true>;
+    if (use_pair && !dbg && (box4 || poll1))
+      fn = box4 ? (poll1 ? (const void*)lstm_fwd_v2_kernel<2, false, 2, false, false, true, true, true>
+                         : (const void*)lstm_fwd_v2_kernel<2, false, 2, false, false, true, true, false>)
+                : (const void*)lstm_fwd_v2_kernel<2, false, 2, false, false, true, false, true>;
+    else if (use_pair) fn = dbg ? (const void*)lstm_fwd_v2_kernel<2, false, 2, false, true, true>
+                                : (const void*)lstm_fwd_v2_kernel<2, false, 2, false, false, true>;
     else if (dbg) fn = split ? (P == 2 ? NVQA_FWD(2, 2, false, true) : NVQA_FWD(1, 2, false, true))
                         : (P == 2 ? NVQA_FWD(2, 1, false, true) : NVQA_FWD(1, 1, false, true));
     else if (P == 2 && stack) fn = split ? NVQA_FWD(2, 2, true, false) : NVQA_FWD(2, 1, true, false);

@@ -67,6 +67,13 @@ int presplit_weights(UmmaWorkspace* ws, cudaStream_t s, int P, const float* cons
 int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int pitch, int P, int box_rows, CUtensorMap* out,
             long long plane_stride = 0, int box_planes = 1);
 
+// 4-D view (64 columns of a k-block, rows, planes, k-blocks) of the same planes: ONE TMA instruction fetches box_kb
+// consecutive k-blocks of a [box_rows x 64] tile of all P planes; they land as [k-block][plane][row][128 B], i.e. as
+// box_kb consecutive stages of the 3-D boxes above (tools/probes/probe_tma_box.cu: the driver accepts the k-block stride
+// of 128 B and the bytes land identically).  pitch must be a multiple of 64.
+int get_map_kb(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int pitch, int P, int box_rows, int box_kb,
+               CUtensorMap* out, long long plane_stride = 0);
+
 // A GEMM operand: either an fp32 row-major source (split into planes by the engine) or planes made upstream.
 struct UmmaOperand {
   const float* src = nullptr;             // fp32 [rows x cols], leading dimension ld

@@ -459,6 +459,33 @@ int get_map(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, in
   return 0;
 }
 
+int get_map_kb(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp, int P, int box_rows, int box_kb,
+               CUtensorMap* out, long long plane_stride) {
+  NVQA_CHECK(Kp % UG_BK == 0 && box_kb >= 1 && box_kb <= Kp / UG_BK, "get_map_kb: pitch must be a multiple of 64");
+  if (plane_stride <= 0) plane_stride = (long long)rows * Kp;
+  MapKey key{planes, rows, Kp, P, box_rows, plane_stride, P + 256 * box_kb};        // (3-D keys have box_planes <= 3)
+  auto it = ws->maps.find(key);
+  if (it != ws->maps.end()) { *out = it->second; return 0; }
+  EncodeTiledFn enc = get_encode();
+  NVQA_CHECK(enc, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)UG_BK, (cuuint64_t)rows, (cuuint64_t)P, (cuuint64_t)(Kp / UG_BK)};
+  cuuint64_t strides[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)plane_stride * 2, (cuuint64_t)UG_BK * 2};
+  cuuint32_t box[4] = {(cuuint32_t)UG_BK, (cuuint32_t)box_rows, (cuuint32_t)P, (cuuint32_t)box_kb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(planes), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4-D) failed with code " + std::to_string((int)r));
+    return 1;
+  }
+  if (ws->maps.size() > 4096) ws->maps.clear();
+  ws->maps[key] = m;
+  *out = m;
+  return 0;
+}
+
 struct UgLaunch {
   int a_row0 = 0, b_row0 = 0, splits = 1, kb_per_split = 1 << 30;
   long long c_split_stride = 0;
