@@ -43,3 +43,20 @@ def test_bad_arguments_return_errors_not_crashes(lib):
     assert lib.nvqa_right_align(None, None, 1, 1, None) != 0
     assert b"bad argument" in lib.nvqa_last_error()
     assert lib.nvqa_forward(None, 0, 0) != 0
+
+
+def test_header_is_plain_c_after_the_lua_shim_filter(tmp_path):
+    """lua/nvqa_ffi.lua feeds include/nvqa.h to ffi.cdef after dropping preprocessor lines, the extern "C" line and the
+    closing brace: what is left must be plain C declarations (checked with gcc -std=c99 -fsyntax-only; no LuaJIT here)."""
+    import re
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = open(os.path.join(ROOT, "include", "nvqa.h")).read().splitlines()
+    kept = [l for l in src if not re.match(r"^\s*#", l) and 'extern "C"' not in l and not re.match(r"^}\s*$", l)]
+    c = tmp_path / "cdef.c"
+    c.write_text("typedef signed char int8_t; typedef int int32_t; typedef long long int64_t; typedef unsigned long long uint64_t;\n"
+                 + "\n".join(kept) + "\n")
+    p = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", str(c)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
