@@ -446,7 +446,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           pv[g][1] = *reinterpret_cast<const float4*>(src + 4);
         }
       }
-      if (POLL1) {
+      if constexpr (POLL1) {
         if ((et & (EPG - 1)) < 32) mbar_wait(tfull + 8 * sub, (uint32_t)t & 1u);    // one warp polls ...
         v2_bar_sync(8 + sub, EPG);                                                  // ... the others sleep here
       } else {
@@ -544,7 +544,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
         v2_bar_sync(bid + 3, EPG);                 // keep the SM's memory pipeline clear until the release is out ...
       }
       if (t + 1 < T) {                             // ... and until the next step's first loads are issued
-        if (POLL1) {
+        if constexpr (POLL1) {
           if ((et & (EPG - 1)) < 32) mbar_wait(gobar + 8 * sub, (uint32_t)(t + 1) & 1u);
           v2_bar_sync(10 + sub, EPG);
         } else {
@@ -960,7 +960,9 @@ __device__ long long g_v3dbg[16 * 4];           // (debug) per-CTA wall-clock st
 __device__ __forceinline__ long long v3_gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define V3_STAMP(slot) do { if (dbg && cta == 0 && blockIdx.z == 0 && t >= 8 && t < 12) stamps[(t - 8) * 8 + (slot)] = clock64(); } while (0)
 
-template <int P, bool STK, bool DBG>
+// POLL1 (EXPERIMENTAL, default off, NVQA_LSTM_POLL1=1, not yet run on hardware): one warp polls `tfull` / `pfull` / `go`,
+// the other seven epilogue warps sleep in named barriers 4-6 instead of spinning on the SM's mbarrier unit.
+template <int P, bool STK, bool DBG, bool POLL1 = false>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, const float* __restrict__ gates,
@@ -1166,7 +1168,12 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     unsigned int red = 0;                                    // reduction rounds done so far (parity of pfull / tfull)
     // the sum of the cluster's four split-K partials of the tile, for this thread's items (fixed rank order)
     auto reduce_partials = [&](float4* out, int t) {
-      mbar_wait(tfull, red & 1u);
+      if constexpr (POLL1) {                                           // one warp polls, the other seven sleep in a named barrier
+        if (warp == 2) mbar_wait(tfull, red & 1u);
+        v2_bar_sync(4, V2_EPI);
+      } else {
+        mbar_wait(tfull, red & 1u);
+      }
       tc_fence_after();
       if (et == 0) { V3_STAMP(5); if (dbg && blockIdx.z == 0 && t == 10) g_v3dbg[cta * 4 + 3] = v3_gtimer(); }
       {
@@ -1185,7 +1192,12 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       tc_fence_before();
       v2_bar_sync(2, V2_EPI);                                // the whole partial tile of this CTA is in shared memory
       if (et < 4) v3_arrive_remote(peer_pfull[et]);          // release.cluster, cumulative over the CTA through the barrier
-      v3_wait_cluster(pfull, red & 1u);                      // all four partial tiles are complete
+      if constexpr (POLL1) {                                           // all four partial tiles are complete
+        if (warp == 2) v3_wait_cluster(pfull, red & 1u);     // (cluster-scope acquire by one warp, handed on by the barrier)
+        v2_bar_sync(5, V2_EPI);
+      } else {
+        v3_wait_cluster(pfull, red & 1u);
+      }
       if (et == 0) V3_STAMP(6);
 #pragma unroll
       for (int n = 0; n < NI; ++n) {
@@ -1256,7 +1268,14 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
         if (dbg && blockIdx.z == 0 && t == 10) g_v3dbg[cta * 4 + 0] = v3_gtimer();
       }
       v2_bar_sync(3, V2_EPI);
-      if (t >= tlast) mbar_wait(gobar, k & 1u);
+      if (t >= tlast) {
+        if constexpr (POLL1) {
+          if (warp == 2) mbar_wait(gobar, k & 1u);
+          v2_bar_sync(6, V2_EPI);
+        } else {
+          mbar_wait(gobar, k & 1u);
+        }
+      }
       // off the critical path: the operands of step t-1
 #pragma unroll
       for (int n = 0; n < NI; ++n) {
@@ -1499,7 +1518,10 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     const __nv_bfloat16* wt = wp;                  // generation 3 keeps plane 0 in TMEM and plane 1 in shared memory
     static int stack3 = -1;
     if (stack3 < 0) { const char* e = getenv("NVQA_LSTM_STACK"); stack3 = e ? atoi(e) : 0; }
-    const void* f3 = dbg ? (P == 2 ? (const void*)lstm_bwd_v3_kernel<2, false, true> : (const void*)lstm_bwd_v3_kernel<1, false, true>)
+    static int poll1 = -1;
+    if (poll1 < 0) { const char* e = getenv("NVQA_LSTM_POLL1"); poll1 = e ? atoi(e) : 0; }
+    const void* f3 = (poll1 && !dbg && P == 2 && !stack3) ? (const void*)lstm_bwd_v3_kernel<2, false, false, true>
+                   : dbg ? (P == 2 ? (const void*)lstm_bwd_v3_kernel<2, false, true> : (const void*)lstm_bwd_v3_kernel<1, false, true>)
                          : P == 2 ? (stack3 ? (const void*)lstm_bwd_v3_kernel<2, true, false> : (const void*)lstm_bwd_v3_kernel<2, false, false>)
                                   : (const void*)lstm_bwd_v3_kernel<1, false, false>;
     NVQA_CUDA(cudaFuncSetAttribute(f3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
