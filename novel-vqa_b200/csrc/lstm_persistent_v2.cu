@@ -135,8 +135,9 @@ __device__ __forceinline__ void p2_wait_cluster(uint32_t bar, uint32_t parity) {
 // tcgen05.mma.cta_group::2 for both and its commits arrive on `empty` / `tfull` of both CTAs.  Measured basis
 // (tools/probes/probe_mma_rate2.cu): a pair-mode TS instruction with N = 32 costs 29.6 cycles instead of 51.8, an SS one
 // 62.6 instead of 80 -- and the per-SM tile ingest halves.
-// BOX4 / POLL1 (EXPERIMENTAL: written at the end of round 1 from the measurements of DESIGN 5.2, compiled, NOT yet run on
-// hardware -- default off, NVQA_LSTM_BOX4D=1 / NVQA_LSTM_POLL1=1):
+// BOX4 / POLL1 (written at the end of round 1 from the measurements of DESIGN 5.2; first run on B200 in round 2: BOX4
+// 0.424 -> 0.369 ms per step pair = default, NVQA_LSTM_BOX4D=0 disables; POLL1 neutral (0.428 / 0.374 ms) = off,
+// NVQA_LSTM_POLL1=1 enables):
 //   BOX4   the CTA's half sub-tile is fetched by TWO 4-D TMA boxes of 4 k-blocks (16 KB) with two `full` / `empty`
 //          barriers instead of eight: 2 instead of 8 try_wait + expect_tx + issue rounds for the TMA warp and 2 instead
 //          of 8 waits for the MMA warp per work item (a lone warp issues such boxes in ~80 cycles each and the data has
@@ -962,7 +963,10 @@ __device__ __forceinline__ long long v3_gtimer() { long long t; asm volatile("mo
 
 // POLL1 (EXPERIMENTAL, default off, NVQA_LSTM_POLL1=1, not yet run on hardware): one warp polls `tfull` / `pfull` / `go`,
 // the other seven epilogue warps sleep in named barriers 4-6 instead of spinning on the SM's mbarrier unit.
-template <int P, bool STK, bool DBG, bool POLL1 = false>
+// BOX4: the da tile of a step is fetched by KB / 2 4-D TMA boxes of two k-blocks (32 KB, both planes) with one `full` /
+// `empty` barrier pair each instead of KB boxes of one k-block -- half the try_wait + expect_tx + issue rounds of the TMA
+// warp and half the waits of the MMA warp (the forward kernel's BOX4 gave 0.424 -> 0.369 ms on B200, round 2).
+template <int P, bool STK, bool DBG, bool POLL1 = false, bool BOX4 = false>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, const float* __restrict__ gates,
@@ -970,8 +974,10 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
                    const float* __restrict__ dh_above, Drop drop, float* __restrict__ dasum,
                    __nv_bfloat16* __restrict__ dap, long long dap_plane, float* __restrict__ dh_init,
                    float* __restrict__ dc_init, const int32_t* __restrict__ len, int T, int B, int H, int KB,
-                   unsigned int* counter, int dbg_arg, int b0, int bend) {
+                   unsigned int* counter, int dbg_arg, int b0, int bend, const __grid_constant__ CUtensorMap mapDA4) {
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B)
+  constexpr int KBB = 2;                            // BOX4: k-blocks per TMA box (a "big stage" = KBB ring stages)
+  static_assert(V2_STAGES % KBB == 0, "the ring holds whole big stages");
   const int dbg = DBG ? (dbg_arg & 0xFFFF) : 0;     // the production instantiation compiles the stamps away
   extern __shared__ uint8_t smem_raw[];
   __shared__ long long stamps[32];
@@ -1041,6 +1047,21 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       }
       __syncwarp();
       fence_proxy_async();
+      if constexpr (BOX4) {
+        // `it` counts big stages: V2_STAGES / KBB of them in the ring, KB / KBB per step
+        for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
+          const int bs = it % (V2_STAGES / KBB);
+          const uint32_t ph = (uint32_t)(it / (V2_STAGES / KBB)) & 1u;
+          mbar_wait(empty0 + 8 * bs, ph ^ 1u);
+          if (elect_one_sync()) {
+            mbar_expect_tx(full0 + 8 * bs, KBB * STAGE);
+            tma_load_4d(r0 + (uint32_t)bs * KBB * STAGE, &mapDA4, full0 + 8 * bs, 0, t * B + m0, 0, ks * KB + hb * KBB);
+            if (hb == gokb / KBB) mbar_arrive(gobar);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int kb = 0; kb < KB; ++kb, ++it) {
         const int s = it % V2_STAGES;
         const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
@@ -1069,6 +1090,36 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     const uint64_t dw_base = make_mnmajor_sw128_desc(w0), dr_base = make_kmajor_sw128_desc(r0);
     int it = 0;
     for (int t = T - 1; t >= tlast; --t) {
+      if constexpr (BOX4) {
+        static_assert(!BOX4 || (P == 2 && !STK), "4-D boxes are wired into the bf16x2 instantiation");
+        for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
+          const int bs = it % (V2_STAGES / KBB);
+          const uint32_t ph = (uint32_t)(it / (V2_STAGES / KBB)) & 1u;
+          mbar_wait(full0 + 8 * bs, ph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int kbl = 0; kbl < KBB; ++kbl) {
+              const int kb = hb * KBB + kbl;
+              const uint64_t dwk = dw_base + (uint64_t)(((uint32_t)kb * W_KB) >> 4);
+              const uint64_t ddk = dr_base + (uint64_t)(((uint32_t)(bs * KBB + kbl) * STAGE) >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t dw = dwk + (uint64_t)(kk * (2048 >> 4)), d0 = ddk + (uint64_t)(kk * 2);
+                const uint64_t d1 = d0 + (uint64_t)(B_PLANE >> 4);
+                const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + kk * 8);
+                umma_f16(tmem_base, dw, d0, idesc, (kb | kk) ? 1u : 0u);   // W1 . da0
+                umma_f16_ts(tmem_base, wt, d1, idesc_ts, 1u);              // W0 . da1
+                umma_f16_ts(tmem_base, wt, d0, idesc_ts, 1u);              // W0 . da0
+              }
+            }
+            umma_commit(empty0 + 8 * bs);
+            if (hb == KB / KBB - 1) umma_commit(tfull);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int kb = 0; kb < KB; ++kb, ++it) {
         const int s = it % V2_STAGES;
         const uint32_t ph = (uint32_t)(it / V2_STAGES) & 1u;
@@ -1385,7 +1436,7 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   NVQA_TRY(get_map(ws, hp, (T + 1) * B, H, P, use_pair ? 16 : split ? 32 : 64, &mapH, hp_plane_rows * H, P));
   // EXPERIMENTAL variants of the pair kernel (see the kernel's header comment): default off
   static int box4 = -1, poll1 = -1;
-  if (box4 < 0) { const char* e = getenv("NVQA_LSTM_BOX4D"); box4 = e ? atoi(e) : 0; }
+  if (box4 < 0) { const char* e = getenv("NVQA_LSTM_BOX4D"); box4 = e ? atoi(e) : 1; }   // measured on B200 (round 2): 0.424 -> 0.369 ms
   if (poll1 < 0) { const char* e = getenv("NVQA_LSTM_POLL1"); poll1 = e ? atoi(e) : 0; }
   CUtensorMap mapH4 = mapH;
   if (use_pair && box4) NVQA_TRY(get_map_kb(ws, hp, (T + 1) * B, H, P, 16, 4, &mapH4, hp_plane_rows * H));
@@ -1520,7 +1571,14 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     if (stack3 < 0) { const char* e = getenv("NVQA_LSTM_STACK"); stack3 = e ? atoi(e) : 0; }
     static int poll1 = -1;
     if (poll1 < 0) { const char* e = getenv("NVQA_LSTM_POLL1"); poll1 = e ? atoi(e) : 0; }
-    const void* f3 = (poll1 && !dbg && P == 2 && !stack3) ? (const void*)lstm_bwd_v3_kernel<2, false, false, true>
+    // NVQA_LSTM_BOX4D=0: one 3-D TMA box per k-block (round 1) instead of 4-D boxes of two k-blocks
+    static int box4 = -1;
+    if (box4 < 0) { const char* e = getenv("NVQA_LSTM_BOX4D"); box4 = e ? atoi(e) : 1; }
+    const bool use_box4 = box4 && !dbg && P == 2 && !stack3 && !poll1;
+    CUtensorMap mapDA4 = mapDA3;
+    if (use_box4) NVQA_TRY(get_map_kb(ws, dap, T * B, 4 * H, P, 64, 2, &mapDA4, dap_plane_rows * 4 * H));
+    const void* f3 = use_box4 ? (const void*)lstm_bwd_v3_kernel<2, false, false, false, true>
+                   : (poll1 && !dbg && P == 2 && !stack3) ? (const void*)lstm_bwd_v3_kernel<2, false, false, true>
                    : dbg ? (P == 2 ? (const void*)lstm_bwd_v3_kernel<2, false, true> : (const void*)lstm_bwd_v3_kernel<1, false, true>)
                          : P == 2 ? (stack3 ? (const void*)lstm_bwd_v3_kernel<2, true, false> : (const void*)lstm_bwd_v3_kernel<2, false, false>)
                                   : (const void*)lstm_bwd_v3_kernel<1, false, false>;
@@ -1532,7 +1590,7 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
       dim3 grid(H / 128, 4, ceil_div(bend - b0, 64));
       NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.z, s));
       void* a3[] = {&mapDA3, &mapW, &wt, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dh_init,
-                    &dc_init, &len, &T, &B, &H, &KBv, &counter, &dbgv, &b0, &bend};
+                    &dc_init, &len, &T, &B, &H, &KBv, &counter, &dbgv, &b0, &bend, &mapDA4};
       cudaLaunchConfig_t cfg3 = {};
       cfg3.gridDim = grid; cfg3.blockDim = dim3(V2_THREADS); cfg3.dynamicSmemBytes = smem; cfg3.stream = s;
       cudaLaunchAttribute at3[2];

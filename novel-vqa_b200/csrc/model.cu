@@ -1119,6 +1119,7 @@ extern "C" int nvqa_lstm_cell_forward(nvqa_model* m, const float* state, const f
   NVQA_CUDA(cudaSetDevice(c.device));
   const int E = c.E, H = c.H, L = c.L, S = m->S;
   cudaStream_t s = m->stream;
+  umma_workspace_new_forward(m->ws);      // scratch operands are rewritten by every call: no stale cached planes
   float* pre = m->da;                     // scratch [n x 4H]
   float* xin = m->dxbuf;                  // scratch [n x H] (dropped h of the layer below)
   Drop d;
@@ -1147,6 +1148,7 @@ extern "C" int nvqa_axb_forward(nvqa_model* m, const float* q, const float* i, c
   const nvqa_config& c = m->cfg;
   const int S = m->S;
   cudaStream_t s = m->stream;
+  umma_workspace_new_forward(m->ws);       // qd / vd are rewritten here: their cached bf16 planes (class 2) are stale
   Drop dq, di, none;
   dq.mask = masks_q; dq.key = 0; dq.thresh = 0; dq.scale = 1.f; dq.mode = masks_q ? 1 : 0;
   di = dq; di.mask = masks_i; di.mode = masks_i ? 1 : 0;
@@ -1157,6 +1159,181 @@ extern "C" int nvqa_axb_forward(nvqa_model* m, const float* q, const float* i, c
   NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
   NVQA_TRY(fuse_fwd(s, m->qc, m->ic, out, none, n, c.C, m->fusion_skip));
   return 0;
+}
+
+// ---- module-level backward: the reference's nn.Module protocol, one call per module:backward ----------------------
+// Scratch of the module-level calls (allocated on first use; rows <= cfg.B): per layer the gates [n x 4H], c' / h'
+// [n x H] and the (dropped) input of the layer [n x max(E,H)]; da [n x 4H]; dc / dh carries; a dy copy for the embedding.
+static int mod_scratch(nvqa_model* m) {
+  if (m->mod_gates[0]) return 0;
+  const nvqa_config& c = m->cfg;
+  const size_t n = (size_t)c.B, W = (size_t)std::max(c.E, c.H);
+  for (int l = 0; l < c.L; ++l) {
+    NVQA_TRY(dallocT(m, &m->mod_gates[l], n * 4 * c.H));
+    NVQA_TRY(dallocT(m, &m->mod_c[l], n * c.H));
+    NVQA_TRY(dallocT(m, &m->mod_h[l], n * c.H));
+    NVQA_TRY(dallocT(m, &m->mod_x[l], n * W));
+  }
+  NVQA_TRY(dallocT(m, &m->mod_da, n * 4 * c.H));
+  NVQA_TRY(dallocT(m, &m->mod_dx, n * W));
+  NVQA_TRY(dallocT(m, &m->mod_cprev, n * c.H));
+  NVQA_TRY(dallocT(m, &m->mod_dc, n * c.H));
+  NVQA_TRY(dallocT(m, &m->mod_dy, (size_t)c.B * c.T * c.E));
+  return 0;
+}
+static Drop explicit_drop(const float* mask) {
+  Drop d;
+  d.mask = mask; d.key = 0; d.thresh = 0; d.scale = 1.f; d.mode = mask ? 1 : 0;
+  return d;
+}
+
+// zeroGradParameters of one flat block (encoder_dw_q:zero() etc., 002_train_baseline.lua:283-285)
+extern "C" int nvqa_grads_zero(nvqa_model* m, int block) {
+  NVQA_CHECK(m && block >= 0 && block < 3, "bad argument");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_CUDA(cudaMemsetAsync(m->grads + m->off_blk[block], 0, (size_t)m->n_blk[block] * 4, m->stream));
+  return 0;
+}
+
+// embedding_net_q:forward(onehot) (002_train_baseline.lua:141-144,300): Linear(V,E) on one-hot rows + Dropout + Tanh.
+// words [n] = the 1-based column of the 1 in every one-hot row (the packed vector of sort_encoding_onehot_right_align).
+extern "C" int nvqa_embedding_forward(nvqa_model* m, const int32_t* words, const float* mask, int32_t n, float* y) {
+  NVQA_CHECK(m && words && y, "null argument");
+  NVQA_CHECK(m->cfg.arch == 1, "the one-hot embedding Sequential belongs to arch 1");
+  NVQA_CHECK(n > 0 && (int64_t)n <= (int64_t)m->cfg.B * m->cfg.T, "row count out of range");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  return embed_fwd(m->stream, words, nullptr, m->WeT, m->be, y, explicit_drop(mask), n, 1, m->cfg.E, m->cfg.V);
+}
+
+// embedding_net_q:backward(onehot, dy) (:320): Tanh / Dropout backward, then accGradParameters of the one-hot Linear
+// (ACCUMULATES into the embedding gradient block; its gradInput [n x V] is discarded by the reference and not computed)
+extern "C" int nvqa_embedding_backward(nvqa_model* m, const int32_t* words, const float* y, const float* dy, const float* mask,
+                                       int32_t n) {
+  NVQA_CHECK(m && words && y && dy, "null argument");
+  NVQA_CHECK(m->cfg.arch == 1, "the one-hot embedding Sequential belongs to arch 1");
+  NVQA_CHECK(n > 0 && (int64_t)n <= (int64_t)m->cfg.B * m->cfg.T, "row count out of range");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  NVQA_TRY(mod_scratch(m));
+  const int E = m->cfg.E;
+  NVQA_CUDA(cudaMemcpyAsync(m->mod_dy, dy, (size_t)n * E * 4, cudaMemcpyDeviceToDevice, m->stream));
+  NVQA_TRY(embed_bwd(m->stream, words, nullptr, y, m->mod_dy, m->gWeT, explicit_drop(mask), n, 1, E, m->cfg.V));
+  return colsum(m->stream, m->mod_dy, n, E, E, m->gbe, nullptr);
+}
+
+// LSTM.lstm_conventional():backward({state, x}, dstate_out) of one timestep clone (misc/LSTM.lua:12-73; called by
+// rnn_backward, misc/RNNUtils.lua:195-196).  The nngraph clone keeps its forward internals; this entry point is
+// stateless and recomputes them from (state, x, masks).  dstate [n x 2LH] and dx [n x E] are the gradInputs;
+// the parameter gradients are ACCUMULATED into the encoder block (sum over clones, :323-326).
+extern "C" int nvqa_lstm_cell_backward(nvqa_model* m, const float* state, const float* x, const float* masks,
+                                       const float* dstate_out, int32_t n, float* dstate, float* dx) {
+  NVQA_CHECK(m && state && x && dstate_out && dstate && dx, "null argument");
+  const nvqa_config& c = m->cfg;
+  NVQA_CHECK(c.arch == 1, "the module-level cell belongs to arch 1");
+  NVQA_CHECK(n > 0 && n <= c.B, "row count out of range");
+  NVQA_CUDA(cudaSetDevice(c.device));
+  NVQA_TRY(mod_scratch(m));
+  umma_workspace_new_forward(m->ws);       // scratch operands are rewritten by every call: no stale cached planes
+  const int E = c.E, H = c.H, L = c.L, S = m->S;
+  cudaStream_t s = m->stream;
+  // forward internals
+  for (int l = 0; l < L; ++l) {
+    const int in = l == 0 ? E : H;
+    const float* X = l == 0 ? x : m->mod_x[l];
+    NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, 4 * H, in, X, in, m->lw[l].Wi, in, m->mod_gates[l], 4 * H, false, m->lw[l].bi,
+                  m->lw[l].bh));
+    NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, 4 * H, H, state + (2 * l + 1) * H, S, m->lw[l].Wh, H, m->mod_gates[l], 4 * H, true));
+    Drop dl = explicit_drop(masks ? masks + (int64_t)l * n * H : nullptr);
+    NVQA_TRY(lstm_gates_fwd(s, m->mod_gates[l], state + 2 * l * H, S, m->mod_c[l], m->mod_h[l], H,
+                            l + 1 < L ? m->mod_x[l + 1] : nullptr, nullptr, dl, 0, 1, n, H));
+  }
+  // backward, top layer first; h'_l feeds the output state and layer l+1 (gradients summed at the fan-out)
+  for (int l = L - 1; l >= 0; --l) {
+    const int in = l == 0 ? E : H;
+    const float* X = l == 0 ? x : m->mod_x[l];
+    NVQA_CUDA(cudaMemcpy2DAsync(m->mod_cprev, (size_t)H * 4, state + 2 * l * H, (size_t)S * 4, (size_t)H * 4, n,
+                                cudaMemcpyDeviceToDevice, s));
+    const float* dh_above = l + 1 < L ? m->mod_dx : nullptr;
+    Drop dab = explicit_drop(masks && l + 1 < L ? masks + (int64_t)l * n * H : nullptr);
+    NVQA_TRY(lstm_gates_bwd(s, m->mod_gates[l], m->mod_cprev, m->mod_c[l], dstate_out + (2 * l + 1) * H, S, dh_above,
+                            dstate_out + 2 * l * H, S, m->mod_da, m->mod_dc, nullptr, dab, 0, 1, n, H));
+    NVQA_CUDA(cudaMemcpy2DAsync(dstate + 2 * l * H, (size_t)S * 4, m->mod_dc, (size_t)H * 4, (size_t)H * 4, n,
+                                cudaMemcpyDeviceToDevice, s));
+    // accGradParameters: dWi += da^T x, dWh += da^T h_prev, both biases += sum(da)
+    NVQA_TRY(gemm(m, CAT_OTHER, false, false, 4 * H, in, n, m->mod_da, 4 * H, X, in, m->lg[l].Wi, in, true));
+    NVQA_TRY(gemm(m, CAT_OTHER, false, false, 4 * H, H, n, m->mod_da, 4 * H, state + (2 * l + 1) * H, S, m->lg[l].Wh, H, true));
+    NVQA_TRY(colsum(s, m->mod_da, n, 4 * H, 4 * H, m->lg[l].bi, m->lg[l].bh));
+    // gradInputs: dh_prev = da . Wh (into the packed dstate), dx_l = da . Wi
+    NVQA_TRY(gemm(m, CAT_OTHER, true, false, n, H, 4 * H, m->mod_da, 4 * H, m->lw[l].Wh, H, dstate + (2 * l + 1) * H, S, false));
+    NVQA_TRY(gemm(m, CAT_OTHER, true, false, n, in, 4 * H, m->mod_da, 4 * H, m->lw[l].Wi, in, l == 0 ? dx : m->mod_dx, in, false));
+  }
+  return 0;
+}
+
+// netdef.AxB():backward({q, i}, dout) (misc/netdef.lua:6-14): recomputes the forward internals, returns dq [n x 2LH]
+// (and di [n x I] when di != NULL -- the reference computes and discards it, 002_train_baseline.lua:312-313) and
+// ACCUMULATES the gradients of Wq, bq, Wi, bi into the multimodal block.
+extern "C" int nvqa_axb_backward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
+                                 const float* dout, int32_t n, float* dq, float* di) {
+  NVQA_CHECK(m && q && i && dout && dq, "null argument");
+  NVQA_CHECK(m->cfg.arch == 1, "AxB belongs to arch 1");
+  NVQA_CHECK(n > 0 && n <= m->cfg.B, "row count out of range");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  const nvqa_config& c = m->cfg;
+  const int S = m->S, C = c.C, I = c.I;
+  cudaStream_t s = m->stream;
+  umma_workspace_new_forward(m->ws);
+  Drop dq_ = explicit_drop(masks_q), di_ = explicit_drop(masks_i), none = explicit_drop(nullptr);
+  NVQA_TRY(mask_copy(s, q, S, nullptr, m->qd, dq_, n, S));
+  NVQA_TRY(mask_copy(s, i, I, nullptr, m->vd, di_, n, I));
+  NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, C, S, m->qd, S, m->Wq, S, m->qc, C, false, m->bq));
+  NVQA_TRY(gemm(m, CAT_OTHER, true, true, n, C, I, m->vd, I, m->Wv, I, m->ic, C, false, m->bv));
+  NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, none, n, C, m->fusion_skip));
+  // CMulTable / Tanh backward
+  NVQA_TRY(fuse_bwd(s, dout, m->qc, m->ic, m->dqpre, m->dipre, none, n, C, m->fusion_skip));
+  NVQA_TRY(gemm(m, CAT_OTHER, false, false, C, S, n, m->dqpre, C, m->qd, S, m->gWq, S, true));
+  NVQA_TRY(colsum(s, m->dqpre, n, C, C, m->gbq, nullptr));
+  NVQA_TRY(gemm(m, CAT_OTHER, false, false, C, I, n, m->dipre, C, m->vd, I, m->gWv, I, true));
+  NVQA_TRY(colsum(s, m->dipre, n, C, C, m->gbv, nullptr));
+  NVQA_TRY(gemm(m, CAT_OTHER, true, false, n, S, C, m->dqpre, C, m->Wq, S, dq, S, false));
+  NVQA_TRY(mask_inplace(s, dq, dq_, (int64_t)n * S));
+  if (di) {
+    NVQA_TRY(gemm(m, CAT_OTHER, true, false, n, I, C, m->dipre, C, m->Wv, I, di, I, false));
+    NVQA_TRY(mask_inplace(s, di, di_, (int64_t)n * I));
+  }
+  return 0;
+}
+
+// multimodal_net = Sequential{AxB, Dropout, Linear(C, O)} (002_train_baseline.lua:151-154): forward({tv_q, fv_im})
+extern "C" int nvqa_multimodal_forward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
+                                       const float* masks_z, int32_t n, float* scores) {
+  NVQA_CHECK(m && q && i && scores, "null argument");
+  NVQA_CHECK(m->cfg.arch == 1, "multimodal_net belongs to arch 1");
+  NVQA_CHECK(n > 0 && n <= m->cfg.B, "row count out of range");
+  const nvqa_config& c = m->cfg;
+  NVQA_TRY(nvqa_axb_forward(m, q, i, masks_q, masks_i, n, m->zd));
+  NVQA_TRY(mask_inplace(m->stream, m->zd, explicit_drop(masks_z), (int64_t)n * c.C));
+  return gemm(m, CAT_OTHER, true, true, n, c.O, c.C, m->zd, c.C, m->Wc, c.C, scores, c.O, false, m->bc);
+}
+
+// multimodal_net:backward({tv_q, fv_im}, dscores) (:312): dq [n x 2LH] (and di when non-NULL); ACCUMULATES into the whole
+// multimodal gradient block
+extern "C" int nvqa_multimodal_backward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
+                                        const float* masks_z, const float* dscores, int32_t n, float* dq, float* di) {
+  NVQA_CHECK(m && q && i && dscores && dq, "null argument");
+  NVQA_CHECK(m->cfg.arch == 1, "multimodal_net belongs to arch 1");
+  NVQA_CHECK(n > 0 && n <= m->cfg.B, "row count out of range");
+  const nvqa_config& c = m->cfg;
+  const int C = c.C, O = c.O;
+  cudaStream_t s = m->stream;
+  // forward internals up to the classifier input zd
+  NVQA_TRY(nvqa_axb_forward(m, q, i, masks_q, masks_i, n, m->zd));
+  NVQA_TRY(mask_inplace(s, m->zd, explicit_drop(masks_z), (int64_t)n * C));
+  // Linear(C, O) backward
+  NVQA_TRY(gemm(m, CAT_OTHER, false, false, O, C, n, dscores, O, m->zd, C, m->gWc, C, true));
+  NVQA_TRY(colsum(s, dscores, n, O, O, m->gbc, nullptr));
+  NVQA_TRY(gemm(m, CAT_OTHER, true, false, n, C, O, dscores, O, m->Wc, C, m->dzd, C, false));
+  NVQA_TRY(mask_inplace(s, m->dzd, explicit_drop(masks_z), (int64_t)n * C));
+  return nvqa_axb_backward(m, q, i, masks_q, masks_i, m->dzd, n, dq, di);
 }
 
 // optim.rmsprop's update (misc/rmsprop_lrscale.lua:26-34, lrs = 1) on arbitrary device vectors:

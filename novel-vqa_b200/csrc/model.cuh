@@ -75,6 +75,9 @@ struct nvqa_model {
   bool logp_valid = false;          // logits holds this forward's log-probs (backward overwrites them with d logits)
   bool hp_valid[4] = {false, false, false, false};   // hp[l] holds this step's h planes (persistent forward ran)
   bool dap_valid = false;                            // dap holds the current layer's da planes
+  // scratch of the module-level entry points (nvqa_lstm_cell_backward ...), allocated on first use
+  float *mod_gates[4] = {}, *mod_c[4] = {}, *mod_h[4] = {}, *mod_x[4] = {};
+  float *mod_da = nullptr, *mod_dx = nullptr, *mod_cprev = nullptr, *mod_dc = nullptr, *mod_dy = nullptr;
   // batch
   const int32_t *q = nullptr, *len = nullptr, *labels = nullptr;
   const float* fc7 = nullptr;

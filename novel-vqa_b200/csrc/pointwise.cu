@@ -26,7 +26,7 @@ embed_fwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len,
   int b = (int)(n % B), t = (int)(n / B);
   float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
   int w = q[(int64_t)b * T + t];
-  if (t >= T - len[b] && w >= 1 && w <= V) {
+  if ((!len || t >= T - len[b]) && w >= 1 && w <= V) {
     float4 wv = LD4(WeT + (int64_t)(w - 1) * E + e);
     float4 bv = LD4(be + e);
     float4 m = drop_at4(d, (uint64_t)n * E + e);
@@ -383,7 +383,7 @@ embed_bwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len,
   int b = (int)(n % B), t = (int)(n / B);
   int w = q[(int64_t)b * T + t];
   float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (t >= T - len[b] && w >= 1 && w <= V) {
+  if ((!len || t >= T - len[b]) && w >= 1 && w <= V) {
     float4 g = LD4(dx + n * E + e), yy = LD4(y + n * E + e), m = drop_at4(d, (uint64_t)n * E + e);
     dp.x = g.x * (1.0f - yy.x * yy.x) * m.x;
     dp.y = g.y * (1.0f - yy.y * yy.y) * m.y;
