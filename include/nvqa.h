@@ -168,6 +168,32 @@ int nvqa_lstm_cell_forward(nvqa_model* m, const float* state, const float* x, co
 /* netdef.AxB():forward({q, i}) (misc/netdef.lua:6-14): q [n x 2LH], i [n x I] -> out [n x C]; masks NULL = evaluate */
 int nvqa_axb_forward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
                      int32_t n, float* out);
+/* ---- module-level backward: what the reference's JdJ calls on its nn modules (002_train_baseline.lua:283-326).
+ * Every *_backward ACCUMULATES the parameter gradients into the model's gradient block (accGradParameters semantics:
+ * the sum over the unrolled timestep clones of :323-326 falls out of calling it once per clone); nvqa_grads_zero is
+ * module:zeroGradParameters / `encoder_dw_q:zero()` (:283-285); nvqa_grads_get / nvqa_rmsprop_step then see the sums.
+ * The entry points are stateless: they recompute the module's forward internals from the same inputs and masks
+ * (a Torch7 clone keeps them in its own buffers).  rows n <= cfg.B (cell / AxB / multimodal), n <= B*T (embedding). */
+int nvqa_grads_zero(nvqa_model* m, int block);
+/* embedding_net_q = Sequential{Linear(V,E), Dropout, Tanh} on one-hot rows (:141-144,300,320): words [n] = 1-based
+ * column of the 1 in each one-hot row (sort_encoding_onehot_right_align's packed vector); mask [n x E] or NULL;
+ * backward discards the [n x V] gradInput exactly like the reference */
+int nvqa_embedding_forward(nvqa_model* m, const int32_t* words, const float* mask, int32_t n, float* y);
+int nvqa_embedding_backward(nvqa_model* m, const int32_t* words, const float* y, const float* dy, const float* mask,
+                            int32_t n);
+/* clone:backward({state, x}, dstate_out) of LSTM.lstm_conventional (misc/LSTM.lua:12-73, misc/RNNUtils.lua:195-196):
+ * dstate_out, dstate [n x 2LH], dx [n x E] */
+int nvqa_lstm_cell_backward(nvqa_model* m, const float* state, const float* x, const float* masks,
+                            const float* dstate_out, int32_t n, float* dstate, float* dx);
+/* netdef.AxB():backward({q, i}, dout) (misc/netdef.lua:6-14): dq [n x 2LH]; di [n x I] or NULL (the reference computes
+ * and discards it, 002_train_baseline.lua:312-313) */
+int nvqa_axb_backward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
+                      const float* dout, int32_t n, float* dq, float* di);
+/* multimodal_net = Sequential{AxB, Dropout, Linear(C,O)} (002_train_baseline.lua:151-154,307,312); masks_z [n x C] */
+int nvqa_multimodal_forward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
+                            const float* masks_z, int32_t n, float* scores);
+int nvqa_multimodal_backward(nvqa_model* m, const float* q, const float* i, const float* masks_q, const float* masks_i,
+                             const float* masks_z, const float* dscores, int32_t n, float* dq, float* di);
 /* optim.rmsprop update (misc/rmsprop_lrscale.lua:26-34) on arbitrary device vectors of length n */
 int nvqa_rmsprop_vector(nvqa_model* m, float* x, const float* g, float* state_m, int64_t n, float lr, float alpha,
                         float eps, float wd, float clamp, float grad_scale);

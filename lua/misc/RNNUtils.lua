@@ -37,3 +37,47 @@ function split_vector(w, sizes)               -- :25-39
   end
   return t
 end
+
+-- ---- the unrolled-RNN drivers (pure Lua over the module protocol; they run unchanged on the nvqa.LSTMCell shim) --------
+function dupe_rnn(net, times)                 -- :66-81: {clones, their flat weights, their flat gradients}
+  local nets, ws, dws = {}, {}, {}
+  for i = 1, times do
+    local c = net:clone()
+    local w, dw = c:getParameters()
+    nets[i], ws[i], dws[i] = c, w, dw
+  end
+  collectgarbage()
+  return {nets, ws, dws}
+end
+
+-- :128-154, right-aligned batches (sizes non-decreasing): rows that become active start from init_state.  Unlike the
+-- reference (App. C-2 of SURVEY.md) the grown state is a fresh tensor, not a view of init_state.
+function rnn_forward(net_buffer, init_state, inputs, sizes)
+  local N = sizes:size(1)
+  local states = {init_state[{{1, sizes[1]}, {}}]}
+  local outputs = {}
+  for i = 1, N do
+    if i > 1 and sizes[i] > sizes[i - 1] then
+      local grown = init_state[{{1, sizes[i]}, {}}]:clone()
+      grown[{{1, sizes[i - 1]}, {}}] = states[i]
+      states[i] = grown
+    elseif i > 1 and sizes[i] < sizes[i - 1] then
+      error('left-aligned (shrinking) batches are not on the arch1 path')
+    end
+    states[i + 1] = net_buffer[1][i]:forward({states[i], inputs[i]})
+  end
+  return states, outputs
+end
+
+-- :181-210, the branch JdJ takes (doutputs is the dummy output tensor, not a table)
+function rnn_backward(net_buffer, dend_state, doutputs, states, inputs, sizes)
+  local N = sizes:size(1)
+  local dstate = {[N + 1] = dend_state[{{1, sizes[N]}, {}}]}
+  local dinputs = {}
+  for i = N, 1, -1 do
+    local g = net_buffer[1][i]:backward({states[i], inputs[i]}, dstate[i + 1])
+    dstate[i] = (i == 1 or sizes[i] == sizes[i - 1]) and g[1] or g[1][{{1, sizes[i - 1]}, {}}]
+    dinputs[i] = g[2]
+  end
+  return dstate, dinputs
+end

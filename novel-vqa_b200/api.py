@@ -267,11 +267,13 @@ class Arch1Model:
     # ---- fused convenience (host buffers in, scalar out) ----
     def train_step_host(self, q_ra, lengths, fc7, labels, lr, seed):
         out = C.c_float(0)
+        q_ra, lengths, fc7, labels = _i32(q_ra), _i32(lengths), _f32(fc7), _i32(labels)   # no-ops for conforming arrays
         _lib.check(self.lib.nvqa_train_step_host(self.handle, _ptr(q_ra), _ptr(lengths), _ptr(fc7), _ptr(labels),
                                                  q_ra.shape[0], lr, seed, C.byref(out)))
         return out.value
 
     def eval_step_host(self, q_ra, lengths, fc7):
+        q_ra, lengths, fc7 = _i32(q_ra), _i32(lengths), _f32(fc7)
         ans = np.empty(q_ra.shape[0], dtype=np.int32)
         _lib.check(self.lib.nvqa_eval_step_host(self.handle, _ptr(q_ra), _ptr(lengths), _ptr(fc7), q_ra.shape[0],
                                                 _ptr(ans)))

@@ -40,12 +40,20 @@ static int dalloc(nvqa_model* m, void** p, size_t bytes) {
 template <typename T>
 static int dallocT(nvqa_model* m, T** p, size_t count) { return dalloc(m, reinterpret_cast<void**>(p), count * sizeof(T)); }
 
+// The hash generator compares 8 bits per element: the keep probability is quantised to (256 - thresh) / 256, and the
+// multiplier of kept elements is its exact reciprocal, so that E[mask] = 1 for every p (for the reference's p = 0.5:
+// thresh 128, scale 2 = 1/(1-p) exactly; oracle/rng.py keep_scale is the bit-identical twin).
+static void drop_quantise(float p, uint32_t* thresh, float* scale) {
+  uint32_t t = (uint32_t)(p * 256.0f + 0.5f);
+  if (t > 255u) t = 255u;
+  *thresh = t;
+  *scale = 256.0f / (float)(256u - t);
+}
 static Drop make_drop(const nvqa_model* m, const float* mask, uint32_t stream) {
   Drop d;
   d.mask = mask;
   d.key = stream_key(m->seed, stream);
-  d.thresh = (uint32_t)(m->cfg.dropout * 256.0f + 0.5f);
-  d.scale = 1.0f / (1.0f - m->cfg.dropout);
+  drop_quantise(m->cfg.dropout, &d.thresh, &d.scale);
   d.mode = (m->mode == NVQA_MODE_TRAIN && m->cfg.dropout > 0.f) ? (mask ? 1 : 2) : 0;
   return d;
 }
@@ -655,8 +663,7 @@ static int forward_arch2(nvqa_model* m) {
 enum : uint32_t { STREAM_AE_ENC_EMB = 32, STREAM_AE_DEC_EMB = 33, STREAM_AE_OUT = 34 };
 static Drop ae_drop(const nvqa_model* m, uint32_t stream, float p) {
   Drop d = make_drop(m, nullptr, stream);
-  d.thresh = (uint32_t)(p * 256.0f + 0.5f);
-  d.scale = 1.0f / (1.0f - p);
+  drop_quantise(p, &d.thresh, &d.scale);
   d.mode = (m->mode == NVQA_MODE_TRAIN && p > 0.f) ? 2 : 0;
   return d;
 }

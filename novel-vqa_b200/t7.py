@@ -125,7 +125,17 @@ class _Reader:
                 arr = np.zeros([0] * max(nd, 1), dtype=_DTYPES.get(kind, np.float32))
             else:
                 isz = storage.itemsize
-                arr = np.lib.stride_tricks.as_strided(storage[off:], shape=size, strides=[s * isz for s in stride])
+                # a truncated / corrupt / hostile file must raise, not read out of bounds
+                if off < 0 or any(n < 0 for n in size) or any(st < 0 for st in stride):
+                    raise ValueError(f"{cls}: negative size, stride or storage offset")
+                last = off + sum((n - 1) * st for n, st in zip(size, stride)) if all(n > 0 for n in size) else off
+                if all(n > 0 for n in size) and last >= storage.size:
+                    raise ValueError(f"{cls}: size {size} / stride {stride} / offset {off + 1} exceed the storage "
+                                     f"({storage.size} elements)")
+                if any(n == 0 for n in size):
+                    arr = np.zeros(size, dtype=storage.dtype)
+                else:
+                    arr = np.lib.stride_tricks.as_strided(storage[off:], shape=size, strides=[st * isz for st in stride])
             self.objects[idx] = arr
             return arr
         if cls.startswith("torch.") and cls.endswith("Storage"):

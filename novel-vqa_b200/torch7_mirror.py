@@ -13,13 +13,20 @@ in libnvqa.so through the C ABI.  It lets the parity tests read like the referen
 Tensors are NumPy arrays on the host (the mirror copies them to the device for each call -- it is an interface shim,
 the throughput path is Arch1Model.train_step_host / dp.train_step).  Errors surface as NvqaError, the analogue of the
 Lua ``error()`` raised by TH/THNN.
+
+Module protocol (what 002_train_baseline.lua:272-335 calls): ``forward``, ``backward``, ``getParameters`` -> (w, dw),
+``zeroGradParameters``, ``training`` / ``evaluate``, ``clone``; plus ``dupe_rnn`` / ``rnn_forward`` / ``rnn_backward``
+(misc/RNNUtils.lua:66-81,128-211).  ``build_arch1_nets`` creates the four modules of :139-157 over ONE libnvqa model,
+which is what lua/misc/LSTM.lua + lua/misc/netdef.lua do on the Lua side (tests/test_mirror_gpu.py runs the
+reference-shaped JdJ through them).
 """
 import ctypes as C
 
 import numpy as np
 
 from . import _lib
-from .api import Arch1Config, Arch1Model, DeviceBuffer, BLOCK_ENCODER, BLOCK_MULTIMODAL, pack_batch
+from .api import (Arch1Config, Arch1Model, DeviceBuffer, BLOCK_ENCODER, BLOCK_EMBEDDING, BLOCK_MULTIMODAL, pack_batch,
+                  PREC_FP32_SIMT)
 from .api import right_align as _right_align
 
 
@@ -58,22 +65,22 @@ def sort_encoding_onehot_right_align(batch_word_right_align, batch_length, vocab
 
 
 # ---- misc/LSTM.lua ------------------------------------------------------------------------------------------------
-class _LSTMCell:
-    """nngraph gModule returned by LSTM.lstm_conventional: forward({state, x}) -> state' on a packed
-    [c1 h1 c2 h2 ...] state (misc/LSTM.lua:15-72)."""
+class _Module:
+    """What every mirrored nn module shares: a flat (w, dw) pair on the host and ONE block of a libnvqa model."""
+    BLOCK = None
 
-    def __init__(self, input_size, rnn_size, n, dropout, model=None):
-        self.input_size, self.rnn_size, self.n, self.dropout = input_size, rnn_size, n, dropout
-        self.train = True
-        self._model = model or Arch1Model(Arch1Config(E=input_size, H=rnn_size, L=n, V=8, I=4, C=4, O=4, T=8, B=512,
-                                                      dropout=dropout))
-        self._w = np.zeros(self._model.param_count(BLOCK_ENCODER), dtype=np.float32)
+    def _init_params(self, model, w=None):
+        self._model = model
+        self._w = np.zeros(model.param_count(self.BLOCK), dtype=np.float32) if w is None else w
         self._dw = np.zeros_like(self._w)
-        self.masks = None          # explicit Dropout multipliers [(n-1) x rows x H] for training-mode parity
+        self.train = True
 
     def getParameters(self):
-        """flat (w, dw); call .sync() (or forward) after writing into w"""
+        """flat (w, dw): written by the caller (w) / by backward (dw), like Torch's flattened views"""
         return self._w, self._dw
+
+    def parameters(self):
+        return [self._w], [self._dw]
 
     def training(self):
         self.train = True
@@ -81,22 +88,76 @@ class _LSTMCell:
     def evaluate(self):
         self.train = False
 
+    def zeroGradParameters(self):
+        self._dw[...] = 0
+
+    def _push(self):
+        self._model.set_params(self.BLOCK, self._w)
+
+    def _backward_block(self, call):
+        """runs one *_backward entry point on a zeroed device gradient block and accumulates the result into dw
+        (accGradParameters: dw += this call's contribution)"""
+        m = self._model
+        _lib.check(m.lib.nvqa_grads_zero(m.handle, self.BLOCK))
+        call()
+        self._dw += m.get_grads(self.BLOCK)
+
+
+class _LSTMCell(_Module):
+    """nngraph gModule returned by LSTM.lstm_conventional: forward({state, x}) -> state' on a packed
+    [c1 h1 c2 h2 ...] state (misc/LSTM.lua:15-72); backward({state, x}, dstate') -> {dstate, dx}."""
+    BLOCK = BLOCK_ENCODER
+
+    def __init__(self, input_size, rnn_size, n, dropout, model=None, w=None):
+        self.input_size, self.rnn_size, self.n, self.dropout = input_size, rnn_size, n, dropout
+        self._init_params(model or Arch1Model(Arch1Config(E=input_size, H=rnn_size, L=n, V=8, I=4, C=4, O=4, T=8, B=512,
+                                                          dropout=dropout)), w)
+        self.masks = None          # explicit Dropout multipliers [(n-1) x rows x H] for training-mode parity
+
+    def clone(self):
+        """net:clone() as used by dupe_rnn (misc/RNNUtils.lua:66-81): own parameter / gradient storage, same device model"""
+        c = _LSTMCell(self.input_size, self.rnn_size, self.n, self.dropout, self._model, self._w.copy())
+        c.train = self.train
+        return c
+
+    def _check(self, state, x):
+        if state.shape[1] != 2 * self.n * self.rnn_size or x.shape[1] != self.input_size or state.shape[0] != x.shape[0]:
+            raise _lib.NvqaError("size mismatch")                      # what THNN's Linear would raise
+
+    def _mask_buffer(self):
+        if not (self.train and self.dropout > 0 and self.n > 1):
+            return None
+        if self.masks is None:
+            raise _lib.NvqaError("training-mode forward needs explicit .masks (Torch7's RNG is not reproducible)")
+        return DeviceBuffer(self._model, np.ascontiguousarray(self.masks, dtype=np.float32))
+
     def forward(self, inputs):
         state, x = (np.ascontiguousarray(a, dtype=np.float32) for a in inputs)
-        if state.shape[1] != 2 * self.n * self.rnn_size or x.shape[1] != self.input_size:
-            raise _lib.NvqaError("size mismatch")                      # what THNN's Linear would raise
+        self._check(state, x)
         m = self._model
-        m.set_params(BLOCK_ENCODER, self._w)
-        rows = state.shape[0]
-        mk = None
-        if self.train and self.dropout > 0 and self.n > 1:
-            if self.masks is None:
-                raise _lib.NvqaError("training-mode forward needs explicit .masks (Torch7's RNG is not reproducible)")
-            mk = DeviceBuffer(m, np.ascontiguousarray(self.masks, dtype=np.float32))
+        self._push()
+        mk = self._mask_buffer()
         S_, X_, O_ = DeviceBuffer(m, state), DeviceBuffer(m, x), DeviceBuffer(m, np.zeros_like(state))
-        _lib.check(m.lib.nvqa_lstm_cell_forward(m.handle, S_.ptr, X_.ptr, None if mk is None else mk.ptr, rows, O_.ptr))
+        _lib.check(m.lib.nvqa_lstm_cell_forward(m.handle, S_.ptr, X_.ptr, None if mk is None else mk.ptr, state.shape[0], O_.ptr))
         self.output = O_.get()
         return self.output
+
+    def backward(self, inputs, gradOutput):
+        """clone:backward({state, x}, dstate') -> {dstate, dx}; dw += this clone's parameter gradients"""
+        state, x = (np.ascontiguousarray(a, dtype=np.float32) for a in inputs)
+        g = np.ascontiguousarray(gradOutput, dtype=np.float32)
+        self._check(state, x)
+        if g.shape != state.shape:
+            raise _lib.NvqaError("size mismatch")
+        m = self._model
+        self._push()
+        mk = self._mask_buffer()
+        S_, X_, G_ = DeviceBuffer(m, state), DeviceBuffer(m, x), DeviceBuffer(m, g)
+        DS_, DX_ = DeviceBuffer(m, np.zeros_like(state)), DeviceBuffer(m, np.zeros_like(x))
+        self._backward_block(lambda: _lib.check(m.lib.nvqa_lstm_cell_backward(
+            m.handle, S_.ptr, X_.ptr, None if mk is None else mk.ptr, G_.ptr, state.shape[0], DS_.ptr, DX_.ptr)))
+        self.gradInput = [DS_.get(), DX_.get()]
+        return self.gradInput
 
 
 class LSTM:
@@ -106,9 +167,15 @@ class LSTM:
         return _LSTMCell(input_size, rnn_size, n, dropout)
 
 
+def dupe_rnn(net, times):
+    """misc/RNNUtils.lua:66-81: `times` clones of the cell, each with its own flat (w, dw) (the reference deep-copies the
+    prototype; JdJ re-copies encoder_w_q into every clone each iteration, 002_train_baseline.lua:275-280)."""
+    return [[net.clone() for _ in range(times)]]
+
+
 def rnn_forward(net_buffer, init_state, inputs, sizes):
-    """RNNUtils.lua:128-154 for right-aligned (non-decreasing) sizes; net_buffer[0] = list of per-step cells (clones
-    share one parameter vector here).  Returns the T+1 states like the reference."""
+    """RNNUtils.lua:128-154 for right-aligned (non-decreasing) sizes; net_buffer[0] = list of per-step cells.
+    Returns the T+1 states like the reference (states[i] = the state fed to step i, grown to that step's size)."""
     cells = net_buffer[0]
     states = [np.asarray(init_state[:int(sizes[0])], dtype=np.float32)]
     for i in range(len(sizes)):
@@ -122,43 +189,150 @@ def rnn_forward(net_buffer, init_state, inputs, sizes):
     return states
 
 
-# ---- misc/netdef.lua + multimodal head ----------------------------------------------------------------------------
-class _AxB:
-    """netdef.AxB(nhA, nhB, nhcommon, dropout): tanh(Wq drop(q)) (.) tanh(Wi drop(i))   (misc/netdef.lua:6-14)"""
+def rnn_backward(net_buffer, dend_state, doutputs, states, inputs, sizes):
+    """RNNUtils.lua:181-210, the branch JdJ takes (doutputs is the dummy output, not a table): walks the clones
+    backwards, trimming the state gradient to the rows active at the previous step.  Returns (dstate, dinputs)."""
+    cells = net_buffer[0]
+    N = len(sizes)
+    dstate = np.asarray(dend_state[:int(sizes[N - 1])], dtype=np.float32)
+    dinputs = [None] * N
+    for i in reversed(range(N)):
+        dprev, dx = cells[i].backward([states[i], inputs[i]], dstate)
+        dinputs[i] = dx
+        dstate = dprev if (i == 0 or sizes[i] == sizes[i - 1]) else dprev[:int(sizes[i - 1])]
+    return dstate, dinputs
 
-    def __init__(self, nhA, nhB, nhcommon, dropout, H, L):
-        self._model = Arch1Model(Arch1Config(E=4, H=H, L=L, V=8, I=nhB, C=nhcommon, O=4, T=2, B=512, dropout=dropout))
+
+# ---- embedding_net_q (002_train_baseline.lua:141-144) ---------------------------------------------------------------
+class _EmbeddingNet(_Module):
+    """nn.Sequential{Linear(V, E), Dropout(0.5), Tanh}: forward takes element [0] of sort_encoding_onehot_right_align
+    (the packed word ids standing for the one-hot rows); backward(words, dy) accumulates the Linear's gradients."""
+    BLOCK = BLOCK_EMBEDDING
+
+    def __init__(self, model):
+        self._init_params(model)
+        self.masks = None          # explicit Dropout multipliers [n x E]
+
+    def _mask_buffer(self, n):
+        if not (self.train and self._model.cfg.dropout > 0):
+            return None
+        if self.masks is None:
+            raise _lib.NvqaError("training-mode forward needs explicit .masks (Torch7's RNG is not reproducible)")
+        return DeviceBuffer(self._model, np.ascontiguousarray(self.masks, dtype=np.float32).reshape(n, -1))
+
+    def forward(self, words):
+        w = np.ascontiguousarray(words, dtype=np.int32)
+        m = self._model
+        if w.size and (w.min() < 1 or w.max() > m.cfg.V):
+            raise _lib.NvqaError("size mismatch")                      # a one-hot row wider than Linear(V, E)
+        self._push()
+        mk = self._mask_buffer(w.size)
+        W_, Y_ = DeviceBuffer(m, w), DeviceBuffer(m, np.zeros((w.size, m.cfg.E), np.float32))
+        _lib.check(m.lib.nvqa_embedding_forward(m.handle, W_.ptr, None if mk is None else mk.ptr, w.size, Y_.ptr))
+        self.output = Y_.get()
+        return self.output
+
+    def backward(self, words, gradOutput):
+        w = np.ascontiguousarray(words, dtype=np.int32)
+        g = np.ascontiguousarray(gradOutput, dtype=np.float32)
+        m = self._model
+        self._push()
+        mk = self._mask_buffer(w.size)
+        W_, Y_, G_ = DeviceBuffer(m, w), DeviceBuffer(m, self.output), DeviceBuffer(m, g)
+        self._backward_block(lambda: _lib.check(m.lib.nvqa_embedding_backward(
+            m.handle, W_.ptr, Y_.ptr, G_.ptr, None if mk is None else mk.ptr, w.size)))
+        return None                # the [n x V] gradInput is never used by the reference (:320)
+
+
+# ---- misc/netdef.lua + multimodal head ----------------------------------------------------------------------------
+class _AxB(_Module):
+    """netdef.AxB(nhA, nhB, nhcommon, dropout): tanh(Wq drop(q)) (.) tanh(Wi drop(i))   (misc/netdef.lua:6-14).
+    Stand-alone it owns the multimodal block of a private model (the Linear(C,O) tail of the block is unused)."""
+    BLOCK = BLOCK_MULTIMODAL
+
+    def __init__(self, nhA, nhB, nhcommon, dropout, H, L, model=None):
+        self._init_params(model or Arch1Model(Arch1Config(E=4, H=H, L=L, V=8, I=nhB, C=nhcommon, O=4, T=2, B=512,
+                                                          dropout=dropout)))
         assert 2 * H * L == nhA
         self.train = False
-        n = self._model.param_count(BLOCK_MULTIMODAL)
-        self._w = np.zeros(n, dtype=np.float32)
         self.masks = None          # (mask_q, mask_i)
 
-    def getParameters(self):
-        return self._w, np.zeros_like(self._w)
-
-    def training(self):
-        self.train = True
-
-    def evaluate(self):
-        self.train = False
+    def _mask_buffers(self):
+        if not self.train:
+            return None, None
+        if self.masks is None:
+            raise _lib.NvqaError("training-mode forward needs explicit .masks")
+        return tuple(DeviceBuffer(self._model, np.ascontiguousarray(a, dtype=np.float32)) for a in self.masks[:2])
 
     def forward(self, inputs):
         q, i = (np.ascontiguousarray(a, dtype=np.float32) for a in inputs)
         m = self._model
-        m.set_params(BLOCK_MULTIMODAL, self._w)
+        self._push()
         n = q.shape[0]
         Q_, I_ = DeviceBuffer(m, q), DeviceBuffer(m, i)
         O_ = DeviceBuffer(m, np.zeros((n, m.cfg.C), dtype=np.float32))
-        mq = mi = None
-        if self.train:
-            if self.masks is None:
-                raise _lib.NvqaError("training-mode forward needs explicit .masks")
-            mq, mi = (DeviceBuffer(m, np.ascontiguousarray(a, dtype=np.float32)) for a in self.masks)
+        mq, mi = self._mask_buffers()
         _lib.check(m.lib.nvqa_axb_forward(m.handle, Q_.ptr, I_.ptr, None if mq is None else mq.ptr,
                                           None if mi is None else mi.ptr, n, O_.ptr))
         self.output = O_.get()
         return self.output
+
+    def backward(self, inputs, gradOutput):
+        """-> {dq, di}; dw += the gradients of Wq, bq, Wi, bi"""
+        q, i = (np.ascontiguousarray(a, dtype=np.float32) for a in inputs)
+        g = np.ascontiguousarray(gradOutput, dtype=np.float32)
+        m = self._model
+        self._push()
+        n = q.shape[0]
+        Q_, I_, G_ = DeviceBuffer(m, q), DeviceBuffer(m, i), DeviceBuffer(m, g)
+        DQ_, DI_ = DeviceBuffer(m, np.zeros_like(q)), DeviceBuffer(m, np.zeros_like(i))
+        mq, mi = self._mask_buffers()
+        self._backward_block(lambda: _lib.check(m.lib.nvqa_axb_backward(
+            m.handle, Q_.ptr, I_.ptr, None if mq is None else mq.ptr, None if mi is None else mi.ptr, G_.ptr, n,
+            DQ_.ptr, DI_.ptr)))
+        self.gradInput = [DQ_.get(), DI_.get()]
+        return self.gradInput
+
+
+class _MultimodalNet(_AxB):
+    """multimodal_net = nn.Sequential{netdef.AxB(2*H*n, I, C, 0.5), Dropout(0.5), Linear(C, O)}
+    (002_train_baseline.lua:151-154).  masks = (mask_q, mask_i, mask_z)."""
+
+    def __init__(self, model):
+        c = model.cfg
+        _AxB.__init__(self, 2 * c.H * c.L, c.I, c.C, c.dropout, c.H, c.L, model)
+        self.train = True
+
+    def _mask3(self):
+        mq, mi = self._mask_buffers()
+        mz = None if not self.train else DeviceBuffer(self._model, np.ascontiguousarray(self.masks[2], dtype=np.float32))
+        return [None if b is None else b.ptr for b in (mq, mi, mz)], (mq, mi, mz)
+
+    def forward(self, inputs):
+        q, i = (np.ascontiguousarray(a, dtype=np.float32) for a in inputs)
+        m = self._model
+        self._push()
+        n = q.shape[0]
+        Q_, I_ = DeviceBuffer(m, q), DeviceBuffer(m, i)
+        O_ = DeviceBuffer(m, np.zeros((n, m.cfg.O), dtype=np.float32))
+        ptrs, keep = self._mask3()
+        _lib.check(m.lib.nvqa_multimodal_forward(m.handle, Q_.ptr, I_.ptr, *ptrs, n, O_.ptr))
+        self.output = O_.get()
+        return self.output
+
+    def backward(self, inputs, gradOutput):
+        q, i = (np.ascontiguousarray(a, dtype=np.float32) for a in inputs)
+        g = np.ascontiguousarray(gradOutput, dtype=np.float32)
+        m = self._model
+        self._push()
+        n = q.shape[0]
+        Q_, I_, G_ = DeviceBuffer(m, q), DeviceBuffer(m, i), DeviceBuffer(m, g)
+        DQ_, DI_ = DeviceBuffer(m, np.zeros_like(q)), DeviceBuffer(m, np.zeros_like(i))
+        ptrs, keep = self._mask3()
+        self._backward_block(lambda: _lib.check(m.lib.nvqa_multimodal_backward(
+            m.handle, Q_.ptr, I_.ptr, *ptrs, G_.ptr, n, DQ_.ptr, DI_.ptr)))
+        self.gradInput = [DQ_.get(), DI_.get()]
+        return self.gradInput
 
 
 class netdef:
@@ -171,8 +345,8 @@ class netdef:
 class CrossEntropyCriterion:
     """criterion:forward(scores, labels) -> number; criterion:backward(scores, labels) -> dscores (sizeAverage)."""
 
-    def __init__(self, num_output):
-        self._model = Arch1Model(Arch1Config(E=4, H=4, L=1, V=8, I=4, C=4, O=num_output, T=2, B=1024))
+    def __init__(self, num_output, model=None):
+        self._model = model or Arch1Model(Arch1Config(E=4, H=4, L=1, V=8, I=4, C=4, O=num_output, T=2, B=1024))
         self._d = None
 
     def forward(self, scores, labels):
@@ -192,6 +366,14 @@ class CrossEntropyCriterion:
         if self._d is None:
             self.forward(scores, labels)
         return self._d
+
+
+def build_arch1_nets(cfg, precision=PREC_FP32_SIMT):
+    """The model construction of 002_train_baseline.lua:139-157 over ONE libnvqa model:
+    returns (embedding_net_q, encoder_net_q, multimodal_net, criterion, model)."""
+    model = Arch1Model(cfg, precision=precision)
+    return (_EmbeddingNet(model), _LSTMCell(cfg.E, cfg.H, cfg.L, cfg.dropout, model), _MultimodalNet(model),
+            CrossEntropyCriterion(cfg.O, model), model)
 
 
 # ---- optim.rmsprop ------------------------------------------------------------------------------------------------

@@ -7,8 +7,9 @@ or use this stateless hash on both sides.  The CUDA twin is ``nvqa_keep_scale`` 
 ``novel-vqa_b200/csrc/common.cuh``.
 
 One 32-bit hash word yields four 8-bit lanes; element ``idx`` uses lane ``idx & 3`` of word
-``idx >> 2``.  An element is kept iff ``byte >= round(p*256)``; kept elements are scaled by
-``1/(1-p)`` (exactly 2.0 for the reference's p = 0.5 everywhere).
+``idx >> 2``.  An element is kept iff ``byte >= thresh``, ``thresh = min(255, round(p*256))``; kept elements
+are scaled by ``256 / (256 - thresh)``, the exact reciprocal of the quantised keep probability, so E[mask] = 1
+for every p (exactly 2.0 = 1/(1-p) for the reference's p = 0.5 everywhere).
 """
 import numpy as np
 
@@ -60,6 +61,6 @@ def keep_bytes(seed, stream, idx):
 
 def keep_scale(seed, stream, idx, p, dtype=np.float32):
     """Dropout multiplier (0 or 1/(1-p)) for each element index."""
-    thresh = np.uint32(int(round(p * 256.0)))
-    scale = dtype(1.0) / (dtype(1.0) - dtype(p))
+    thresh = np.uint32(min(255, int(np.float32(p) * np.float32(256.0) + np.float32(0.5))))
+    scale = dtype(np.float32(256.0) / np.float32(256 - int(thresh)))
     return np.where(keep_bytes(seed, stream, idx) >= thresh, scale, dtype(0.0)).astype(dtype)

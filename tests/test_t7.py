@@ -147,3 +147,17 @@ def test_autoencoder_to_arch2_conversion():
     W, b = r.standard_normal((E, 6)).astype(np.float32), r.standard_normal(E).astype(np.float32)
     cnn = A.split_flat(t7.arch2_cnn_from_linear(W, b), c2.cnn_layout())
     assert np.array_equal(cnn["Wcnn"], W) and np.array_equal(cnn["bcnn"], b)
+
+
+@pytest.mark.parametrize("size,stride,offset", [((4, 3), (1, 4), 12), ((30,), (1,), 1), ((5,), (-1,), 5), ((5,), (1,), 0)])
+def test_corrupt_tensor_headers_raise_instead_of_reading_out_of_bounds(tmp_path, size, stride, offset):
+    """size / stride / storageOffset fields that reach past the 20-element storage (or are negative) must raise."""
+    data = np.arange(20, dtype="<f4")
+    storage = (struct.pack("<i", 4) + struct.pack("<i", 3) + _s("V 1") + _s("torch.FloatStorage") + struct.pack("<q", 20) + data.tobytes())
+    nd = len(size)
+    t_a = (struct.pack("<i", 4) + struct.pack("<i", 2) + _s("V 1") + _s("torch.FloatTensor") + struct.pack("<i", nd)
+           + struct.pack("<" + "q" * nd, *size) + struct.pack("<" + "q" * nd, *stride) + struct.pack("<q", offset) + storage)
+    p = tmp_path / "bad.t7"
+    p.write_bytes(t_a)
+    with pytest.raises(ValueError):
+        t7.load(str(p))
