@@ -148,6 +148,12 @@ int nvqa_set_variant(nvqa_model* m, int32_t fusion, float lr_scale, int32_t norm
  * misc/Encoder_lstm.lua:53): the LookupTable block of the gradient is zeroed before the optimizer (it then only sees
  * weight decay).  Default 0 = the evident intent (gradient accumulated over all steps). */
 int nvqa_set_lookup_grad_literal(nvqa_model* m, int32_t on);
+/* arch 2: on = 1 reproduces the literal reference's initial state: nn.Encoder:updateGradInput stores
+ * the head's gradInput tensor into self.init_state_enc[num_state] (misc/Encoder_lstm.lua:238-239) and _createInitState
+ * re-zeroes it only when the batch size changes (:37-40), so from the second training step on the top LSTM layer starts
+ * from h0 = the PREVIOUS step's d loss / d h_T (every forward, including validation passes in between).  Default 0 = zero
+ * initial state.  Switching it (either way) restarts from zeros like a freshly built nn.Encoder. */
+int nvqa_set_stale_h0_literal(nvqa_model* m, int32_t on);
 int nvqa_scores_get(nvqa_model* m, float* host_dst);             /* [B x O]                       */
 int nvqa_argmax_get(nvqa_model* m, int32_t* host_dst);           /* torch.max(scores,2), 1-based  */
 int nvqa_state_get(nvqa_model* m, float* host_dst);              /* final LSTM state tv_q [B x 2LH] */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "nvqa_adam_step": (C.c_int, [C.c_void_p] + [C.c_float] * 7),
     "nvqa_logprobs_get": (C.c_int, [C.c_void_p, C.c_int32, c_f32p]),
     "nvqa_set_lookup_grad_literal": (C.c_int, [C.c_void_p, C.c_int32]),
+    "nvqa_set_stale_h0_literal": (C.c_int, [C.c_void_p, C.c_int32]),
     "nvqa_set_variant": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_int32]),
     "nvqa_scores_get": (C.c_int, [C.c_void_p, c_f32p]),
     "nvqa_argmax_get": (C.c_int, [C.c_void_p, c_i32p]),

@@ -293,6 +293,10 @@ class Arch2Model(Arch1Model):
     def set_lookup_grad_literal(self, on=True):
         _lib.check(self.lib.nvqa_set_lookup_grad_literal(self.handle, 1 if on else 0))
 
+    def set_stale_h0_literal(self, on=True):
+        """the literal reference's stale-gradient initial state (misc/Encoder_lstm.lua:238-239)."""
+        _lib.check(self.lib.nvqa_set_stale_h0_literal(self.handle, 1 if on else 0))
+
     def set_masks(self, lstm=None, z=None):
         super().set_masks(emb=None, lstm=lstm, q=None, i=None, z=z)
 

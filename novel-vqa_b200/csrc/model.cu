@@ -313,6 +313,7 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   if (a2) {
     m->Wcnn = w6[0]; m->bcnn = w6[1]; m->gWcnn = g6[0]; m->gbcnn = g6[1];
     m->lookup = m->WeT; m->glookup = m->gWeT;
+    NVQA_TRY(dallocT(m, &m->h0_stale, (size_t)B * H));
     NVQA_TRY(dallocT(m, &m->zeros, (size_t)B * H));
     NVQA_CUDA(cudaMemsetAsync(m->zeros, 0, (size_t)B * H * 4, m->stream));
   }
@@ -642,7 +643,19 @@ static int forward_arch2(nvqa_model* m) {
   }
   // step 1: cnn_projection = Linear(I, E) on the (normalised) image feature, written as rows [0, B) of the LSTM input
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, E, c.I, m->vd, c.I, m->Wcnn, c.I, m->y, E, false, m->bcnn));
-  NVQA_TRY(lstm_layers_forward(m, steps, nullptr));
+  // literal reference (App. C-5): from the second training step on (same batch size), the top layer starts from
+  // h0 = the previous step's d loss / d h_T; otherwise slot 0 is the zero state (restored if a literal step dirtied it)
+  const bool stale = m->stale_h0_literal && m->stale_h0_B == B;
+  if (stale || m->h0_dirty) {
+    const long long plane = (long long)(m->TS + 1) * c.B * H;
+    ProfScope ps(m, CAT_PW_FWD, 0);
+    NVQA_TRY(rows_to_planes(s, stale ? m->h0_stale : m->zeros, m->h[L - 1], m->planes ? m->hp[L - 1] : nullptr, plane, m->planes,
+                            (int64_t)B * H));
+    m->h0_dirty = stale;
+  }
+  LstmSeg sg;
+  sg.T = steps; sg.w = m->lw; sg.g = m->lg; sg.has_init = stale;
+  NVQA_TRY(lstm_layers_forward(m, sg, nullptr));
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(mask_copy(s, m->h[L - 1] + (int64_t)steps * B * H, H, m->state, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, H));
@@ -797,6 +810,10 @@ static int backward_head_arch2(nvqa_model* m) {
   NVQA_TRY(colsum(s, m->dscores, B, O, O, m->gbc, nullptr));
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, H, O, m->dscores, O, m->Wc, H, m->dzd, H, false));
   NVQA_TRY(mask_inplace(s, m->dzd, make_drop(m, m->mk_z, STREAM_HEAD), (int64_t)B * H));
+  if (m->stale_h0_literal) {   // what the literal reference leaves in init_state_enc[num_state] (Encoder_lstm.lua:238-239)
+    NVQA_CUDA(cudaMemcpyAsync(m->h0_stale, m->dzd, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
+    m->stale_h0_B = B;
+  }
   return 0;
 }
 
@@ -1025,6 +1042,12 @@ extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps
 extern "C" int nvqa_set_lookup_grad_literal(nvqa_model* m, int32_t on) {
   NVQA_CHECK(m && (m->cfg.arch == 2 || m->cfg.arch == 3), "nvqa_set_lookup_grad_literal applies to arch 2 / 3 models");
   m->lookup_grad_literal = on != 0;
+  return 0;
+}
+extern "C" int nvqa_set_stale_h0_literal(nvqa_model* m, int32_t on) {
+  NVQA_CHECK(m && m->cfg.arch == 2, "nvqa_set_stale_h0_literal applies to arch 2 models");
+  m->stale_h0_literal = on != 0;
+  m->stale_h0_B = 0;                 // like a freshly constructed nn.Encoder: the first step starts from zeros
   return 0;
 }
 static int drop_lookup_grad(nvqa_model* m) {

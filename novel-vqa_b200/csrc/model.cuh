@@ -71,6 +71,13 @@ struct nvqa_model {
   // two-block image norm (early fusion)
   int fusion_skip = 0, norm_split = 0;
   float lr_scale = 1.0f;
+  // arch 2, literal reference: the top layer's initial h of a training step is the PREVIOUS step's
+  // d loss / d h_T (Encoder_lstm.lua:238-239 stores the head's gradInput into init_state_enc; :37-40 only re-zeroes it on
+  // a batch-size change)
+  bool stale_h0_literal = false;
+  int stale_h0_B = 0;               // batch size of the backward that left its gradInput in h0_stale (0 = none yet)
+  bool h0_dirty = false;            // slot 0 of the top layer currently holds a non-zero initial state
+  float* h0_stale = nullptr;        // [B x H] copy of that gradInput
   bool lookup_grad_literal = false;   // arch 2 / 3: drop the LookupTable gradient like the literal reference
   bool logp_valid = false;          // logits holds this forward's log-probs (backward overwrites them with d logits)
   bool hp_valid[4] = {false, false, false, false};   // hp[l] holds this step's h planes (persistent forward ran)

@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "pointwise.cuh"
+#include "umma_ptx.cuh"
 
 namespace nvqa {
 
@@ -467,6 +468,35 @@ mask_copy_kernel(const float* __restrict__ src, int ld, float* __restrict__ raw,
 
 int mask_copy(cudaStream_t s, const float* src, int ld, float* raw, float* dst, Drop d, int B, int W) {
   mask_copy_kernel<<<ceil_div((int64_t)B * W / 4, 256), 256, 0, s>>>(src, ld, raw, dst, d, B, W);
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+// fp32 rows [n x W] -> the same rows as fp32 (dst32, optional) and as P bf16 planes (planes + p * plane_stride): writes an
+// initial-state slot of the recurrence (h and its planes) from an arbitrary tensor
+__global__ void __launch_bounds__(256)
+rows_to_planes_kernel(const float* __restrict__ src, float* __restrict__ dst32, __nv_bfloat16* __restrict__ planes,
+                      long long plane_stride, int P, int64_t n4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = LD4(src + i * 4);
+  if (dst32) ST4(dst32 + i * 4, v);
+  if (!planes) return;
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 p[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split3(x[j], p[0][j], p[1][j], p[2][j]);
+  for (int q = 0; q < P; ++q) {
+    uint2 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(p[q][0]) | ((uint32_t)__bfloat16_as_ushort(p[q][1]) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(p[q][2]) | ((uint32_t)__bfloat16_as_ushort(p[q][3]) << 16);
+    *reinterpret_cast<uint2*>(planes + (size_t)q * plane_stride + i * 4) = o;
+  }
+}
+
+int rows_to_planes(cudaStream_t s, const float* src, float* dst32, __nv_bfloat16* planes, long long plane_stride, int P,
+                   int64_t n) {
+  rows_to_planes_kernel<<<ceil_div(n / 4, 256), 256, 0, s>>>(src, dst32, planes, plane_stride, P, n / 4);
   NVQA_LAUNCHED();
   return 0;
 }

@@ -1,5 +1,7 @@
 // Launchers of the bandwidth-bound kernels of the arch1 step (pointwise.cu).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace nvqa {
@@ -39,6 +41,9 @@ int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float*
 int lookup_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* x, int B, int T, int E, int V, int steps);
 int lookup_bwd(cudaStream_t s, const int32_t* seq, const float* dx, float* dtable, int B, int T, int E, int V, int steps);
 int mask_copy(cudaStream_t s, const float* src, int ld, float* raw, float* dst, Drop d, int B, int W);
+// n contiguous floats -> a copy (dst32, may be NULL) and P bf16 planes (planes + p * plane_stride, may be NULL)
+int rows_to_planes(cudaStream_t s, const float* src, float* dst32, __nv_bfloat16* planes, long long plane_stride, int P,
+                   int64_t n);
 // gradients*scale -> clamp -> optim.rmsprop, one pass (002_train_baseline.lua:329,408; misc/rmsprop_lrscale.lua:26-34)
 int clamp_rmsprop(cudaStream_t s, float* x, float* g, float* m, int64_t n, float lr, float alpha, float eps,
                   float wd, float clamp, float gscale);

@@ -9,8 +9,13 @@ Sequence fed to the LSTM (Encoder_lstm.lua:170-221): step 1 = image projected by
 (id V+1), steps 3.. = the question words, NOT right-aligned (002_train_baseline.lua:216); zeros are replaced by
 token 1 and processed unmasked (:197); a time row that is all zeros is skipped, so the number of
 executed steps is tmax = 2 + (longest question in the batch).  Output = top-layer h at tmax (:224).
-The first step from a fresh model is restated (zero initial state); the reference's stale-gradient-as-h0 quirk
-(App. C-5) only appears from the second call on and is deliberately NOT replicated.
+Two literal-reference behaviours are flags (default off = the evident intent):
+``literal_lookup_grad`` -- createClones builds the per-step lookup tables from ``self.lookup_table:clone('weight')``
+(Encoder_lstm.lua:53), which shares no gradWeight with the module whose gradient parameters() returns, so the
+LookupTable block of the gradient stays zero (it only sees weight decay); ``h0_top`` -- updateGradInput stores the
+head's gradInput tensor into ``self.init_state_enc[num_state]`` (:238-239) and _createInitState re-zeroes it only on a
+batch-size change (:37-40), so from the second training step on the top layer starts from h0 = the PREVIOUS step's
+d loss / d h_T.  ``train_step(..., literal=True, carry=...)`` threads that tensor through.
 """
 from dataclasses import dataclass
 
@@ -84,8 +89,10 @@ def build_masks(cfg, seed, B, steps, dtype=np.float32):
     return {"lstm": lstm, "z": rng.keep_scale(seed, rng.STREAM_HEAD, b * cfg.H + np.arange(cfg.H)[None, :], cfg.p, dtype)}
 
 
-def jdj(cfg, cnn_w, enc_w, mm_w, seq, fv_im, labels, seed=None, dtype=np.float32, clamp=10.0, grad_scale=1.0):
-    """f, gradients (cnn, encoder, multimodal -- the optimiser's order, :192,326), scores, context."""
+def jdj(cfg, cnn_w, enc_w, mm_w, seq, fv_im, labels, seed=None, dtype=np.float32, clamp=10.0, grad_scale=1.0,
+        literal_lookup_grad=False, h0_top=None):
+    """f, gradients (cnn, encoder, multimodal -- the optimiser's order, :192,326), scores, context.
+    ctx["dz"] is the head's gradInput (what the literal reference leaves in init_state_enc[num_state])."""
     cnn = A.split_flat(cnn_w.astype(dtype), cfg.cnn_layout())
     enc = A.split_flat(enc_w.astype(dtype), cfg.enc_layout())
     mm = A.split_flat(mm_w.astype(dtype), cfg.mm_layout())
@@ -95,6 +102,8 @@ def jdj(cfg, cnn_w, enc_w, mm_w, seq, fv_im, labels, seed=None, dtype=np.float32
     fv = fv_im.astype(dtype)
     x0 = fv @ cnn["Wcnn"].T + cnn["bcnn"]                           # cnn_projection:forward   :308
     state = np.zeros((B, cfg.S), dtype=dtype)
+    if h0_top is not None:                                          # literal reference, 2nd step on (App. C-5)
+        state[:, (2 * cfg.L - 1) * cfg.H:2 * cfg.L * cfg.H] = h0_top
     caches, xs = [], []
     for s in range(tmax):
         x = x0 if s == 0 else enc["lookup"][toks[s] - 1]
@@ -127,18 +136,27 @@ def jdj(cfg, cnn_w, enc_w, mm_w, seq, fv_im, labels, seed=None, dtype=np.float32
             cnn_g["bcnn"] += dx.sum(axis=0)
         else:
             np.add.at(enc_g["lookup"], toks[s] - 1, dx)             # LookupTable accGradParameters   Encoder_lstm.lua:256
+    if literal_lookup_grad:                                         # the clones' gradWeight is not the one parameters() returns
+        enc_g["lookup"][...] = 0
     grads = [g_cnn, g_enc, g_mm]
     if grad_scale != 1.0:
         grads = [g * dtype(grad_scale) for g in grads]
     if clamp is not None:
         grads = [np.clip(g, -clamp, clamp) for g in grads]
-    return f, grads, scores, dict(out=out, tmax=tmax)
+    return f, grads, scores, dict(out=out, tmax=tmax, dz=dz)
 
 
-def train_step(cfg, cnn_w, enc_w, mm_w, m_state, batch, lr, seed=None, dtype=np.float32, wd=1e-4):
-    """optim.rmsprop(JdJ, ...) with optimize.weightDecay = 1e-4 (:197): wd*x is added AFTER the clamp."""
+def train_step(cfg, cnn_w, enc_w, mm_w, m_state, batch, lr, seed=None, dtype=np.float32, wd=1e-4, literal=False, carry=None):
+    """optim.rmsprop(JdJ, ...) with optimize.weightDecay = 1e-4 (:197): wd*x is added AFTER the clamp.
+    literal=True: both literal-reference behaviours; ``carry`` = {} kept by the caller across steps (holds the stale h0
+    and the batch size it belongs to)."""
     seq, fv_im, labels = batch
-    f, grads, _, _ = jdj(cfg, cnn_w, enc_w, mm_w, seq, fv_im, labels, seed, dtype)
+    h0 = None
+    if literal and carry is not None and carry.get("B") == seq.shape[0]:
+        h0 = carry.get("dz")
+    f, grads, _, ctx = jdj(cfg, cnn_w, enc_w, mm_w, seq, fv_im, labels, seed, dtype, literal_lookup_grad=literal, h0_top=h0)
+    if literal and carry is not None:
+        carry["dz"], carry["B"] = ctx["dz"], seq.shape[0]
     for w, g, m in zip((cnn_w, enc_w, mm_w), grads, m_state):
         A.rmsprop_update(w, g.astype(w.dtype), m, lr, wd=wd)
     return f, lr * 0.99997592083

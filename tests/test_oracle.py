@@ -224,3 +224,45 @@ def test_trainer_variants_finite_differences_fp64():
     # lr_scale multiplies the encoder and embedding blocks before the clamp, not the multimodal block
     _, gs, _, _ = A.jdj(cfg, enc, emb, mm, q, lens, fv, lab, seed=3, dtype=np.float64, clamp=None, lr_scale=0.1)
     assert np.allclose(gs[0], 0.1 * g[0]) and np.allclose(gs[1], 0.1 * g[1]) and np.allclose(gs[2], g[2], rtol=1e-12, atol=0)
+
+
+def test_rng_expectation_is_one_for_any_p():
+    """the 8-bit keep threshold quantises the keep probability to k/256; the multiplier is its exact reciprocal,
+    so E[mask] = 1 also for p that is not a multiple of 1/256 (0.3 = the reference's -drop_prob_ae option range), and a p
+    above 255/256 still keeps 1/256 of the elements instead of dropping everything."""
+    idx = np.arange(1 << 18)
+    for p in (0.3, 0.1, 0.75, 0.999):
+        m = rng.keep_scale(7, rng.STREAM_EMB, idx, p)
+        kept = m[m > 0]
+        k = 256 - min(255, int(np.float32(p) * np.float32(256) + np.float32(0.5)))
+        assert kept.size and np.all(kept == np.float32(256.0 / k))
+        assert abs((m > 0).mean() - k / 256) < 0.01
+        assert abs(m.mean() - 1.0) < (0.03 if p < 0.9 else 0.25)
+
+
+@pytest.mark.parametrize("variant", ["faithful", "gather"])
+@pytest.mark.parametrize("seed", [None, 5])
+def test_torch_cpu_port_matches_oracle(variant, seed):
+    """oracle/torch_cpu.py (the timed CPU baseline of bench.py: dense one-hot Linear, un-shared clones, autograd) computes
+    the same loss, scores, clamped gradients and RMSprop update as oracle/arch1.py -- ragged lengths, evaluate and training
+    mode (shared hash masks)."""
+    from oracle import torch_cpu
+    mg = small()
+    cfg = A.Arch1Config(**mg.CFG)
+    g = np.load(GOLD)
+    q, ln, lab = g["q_ra"], g["lengths"], g["labels"]
+    fv = A.l2_normalize_rows(g["fc7"])
+    port = torch_cpu.TorchCpuArch1(cfg, g["enc"], g["emb"], g["mm"], variant)
+    f, grads, scores = port.jdj(q, ln, fv, lab, seed=seed)
+    f_ref, g_ref, s_ref, _ = A.jdj(cfg, g["enc"], g["emb"], g["mm"], q, ln, fv, lab, seed=seed)
+    assert abs(f - f_ref) <= 1e-5 * abs(f_ref)
+    assert_close(scores.numpy(), s_ref, 1e-5, "scores")
+    assert_close(grads.numpy(), np.concatenate(g_ref), 1e-5, "clamped gradients [encoder | embedding | multimodal]")
+    # one optimizer step (the port's 6-pass RMSprop over the joined vector == rmsprop_update per block)
+    port2 = torch_cpu.TorchCpuArch1(cfg, g["enc"], g["emb"], g["mm"], variant)
+    port2.step((q, ln, fv, lab), 3e-4, seed=seed)
+    w = [g["enc"].copy(), g["emb"].copy(), g["mm"].copy()]
+    A.train_step(cfg, w[0], w[1], w[2], [np.zeros_like(x) for x in w], (q, ln, fv, lab), 3e-4, seed=seed)
+    ref_x, x0 = np.concatenate(w), np.concatenate([g["enc"], g["emb"], g["mm"]])
+    big = np.abs(np.concatenate(g_ref)) > 1e-5           # lr * g / (0.1 |g| + eps) is ill-conditioned where |g| ~ eps
+    assert_close((port2.x.numpy() - x0)[big], (ref_x - x0)[big], 5e-3, "RMSprop update")

@@ -114,3 +114,54 @@ def test_train_step_is_rmsprop_with_weight_decay_after_the_clamp():
         tp.grad = torch.tensor(np.clip(gr, -10, 10).astype(np.float32))
         opt.step()
         assert_close(b, tp.detach().numpy(), 1e-6, "rmsprop + weight decay")
+
+
+def test_literal_reference_flags_lookup_gradient_and_stale_h0():
+    """DESIGN 2 / SURVEY App. C-5.  literal_lookup_grad: the LookupTable block of the gradient is zero, everything else
+    unchanged.  h0_top: the forward starts the top layer from the given tensor; checked against torch autograd (the
+    gradient w.r.t. the weights flows through the non-zero initial state, the state itself gets no gradient)."""
+    cfg, cnn, enc, mm, seq, fv, lab = small(seed=4, B=5, T=6, L=1)
+    f0, g0, s0, ctx0 = A2.jdj(cfg, cnn, enc, mm, seq, fv, lab, seed=None, dtype=np.float64, clamp=None)
+    f1, g1, s1, _ = A2.jdj(cfg, cnn, enc, mm, seq, fv, lab, seed=None, dtype=np.float64, clamp=None, literal_lookup_grad=True)
+    n_core = cfg.n_enc - (cfg.V + 1) * cfg.E
+    assert f0 == f1 and np.array_equal(s0, s1)
+    assert np.array_equal(g1[0], g0[0]) and np.array_equal(g1[2], g0[2]) and np.array_equal(g1[1][:n_core], g0[1][:n_core])
+    assert not g1[1][n_core:].any() and g0[1][n_core:].any()
+    # stale h0 = the head's gradInput of the previous step
+    h0 = ctx0["dz"] * 50                                      # scaled up so that it visibly changes the forward
+    f2, g2, s2, _ = A2.jdj(cfg, cnn, enc, mm, seq, fv, lab, seed=None, dtype=np.float64, clamp=None, h0_top=h0)
+    assert np.abs(s2 - s0).max() > 1e-6
+    H, E, V1 = cfg.H, cfg.E, cfg.V + 1
+    tc, te, tm = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (cnn, enc, mm))
+    Wcnn, bcnn = tc[:E * cfg.I].view(E, cfg.I), tc[E * cfg.I:]
+    o, p = 0, []
+    for shape in ((4 * H, E), (4 * H,), (4 * H, H), (4 * H,)):
+        n = int(np.prod(shape))
+        p.append(te[o:o + n].view(*shape))
+        o += n
+    table = te[o:].view(V1, E)
+    Wc, bc = tm[:cfg.O * H].view(cfg.O, H), tm[cfg.O * H:]
+    perm = torch.cat([torch.arange(0, 2 * H), torch.arange(3 * H, 4 * H), torch.arange(2 * H, 3 * H)])
+    B = seq.shape[0]
+    longest = int((seq != 0).sum(1).max())
+    h, c = torch.tensor(h0), torch.zeros(B, H, dtype=torch.float64)
+    tok = torch.tensor(np.where(seq == 0, 1, seq)) - 1
+    for t in range(longest + 2):
+        x = (torch.tensor(fv) @ Wcnn.T + bcnn) if t == 0 else table[torch.full((B,), V1 - 1, dtype=torch.long)] if t == 1 \
+            else torch.nn.functional.embedding(tok[:, t - 2], table)
+        h, c = torch._VF.lstm_cell(x, (h, c), p[0][perm], p[2][perm], p[1][perm], p[3][perm])
+    loss = torch.nn.functional.cross_entropy(h @ Wc.T + bc, torch.tensor(lab) - 1)
+    loss.backward()
+    assert abs(loss.item() - f2) <= 1e-12 * max(1, abs(f2))
+    for a, b, what in ((tc.grad, g2[0], "cnn"), (te.grad, g2[1], "encoder"), (tm.grad, g2[2], "multimodal")):
+        assert_close(b, a.numpy(), 1e-10, what + " with a non-zero initial state")
+    # train_step(literal=True) threads the carry: step 2 differs from a non-literal step 2, and a batch-size change resets
+    w = [a.astype(np.float32) for a in (cnn, enc, mm)]
+    wl = [a.copy() for a in w]
+    ms, msl, carry = [np.zeros_like(a) for a in w], [np.zeros_like(a) for a in w], {}
+    fa = [A2.train_step(cfg, w[0], w[1], w[2], ms, (seq, fv, lab), 3e-4)[0] for _ in range(2)]
+    fl = [A2.train_step(cfg, wl[0], wl[1], wl[2], msl, (seq, fv, lab), 3e-4, literal=True, carry=carry)[0] for _ in range(2)]
+    assert fa[0] == fl[0] and fa[1] != fl[1]
+    assert carry["B"] == B and carry["dz"].shape == (B, H)
+    A2.train_step(cfg, wl[0], wl[1], wl[2], msl, (seq[:3], fv[:3], lab[:3]), 3e-4, literal=True, carry=carry)
+    assert carry["B"] == 3

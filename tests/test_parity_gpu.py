@@ -226,9 +226,13 @@ def test_full_size_config1_step():
         assert abs(m.loss() - f) <= tol * abs(f)
         assert abs(m.loss() - np.log(1000.0)) < 0.05                  # random init: loss ~ ln(O)
         am = m.argmax(500)
-        safe = margin > 1e-5 * np.abs(scores).max()                   # ties below fp32 noise are not pinned
+        # ties below the arithmetic's own noise are not pinned: 1e-6 of the score range for the exact-fp32 path (same
+        # arithmetic as the oracle up to summation order), 1e-5 for the split-bf16 tensor-core modes
+        safe = margin > (1e-6 if prec == 0 else 1e-5) * np.abs(scores).max()
         assert np.array_equal(am[safe], A.argmax_first(scores)[safe])
         assert safe.mean() > 0.99
+        print(f"prec {prec}: argmax pinned on {int(safe.sum())}/500 rows, {int((am[~safe] != A.argmax_first(scores)[~safe]).sum())} "
+              f"of the {int((~safe).sum())} unpinned rows differ")
         m.backward()
         for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
             assert_close(np.clip(m.get_grads(blk), -10, 10), gw, tol, f"prec {prec} grads {blk}")
@@ -239,6 +243,47 @@ def test_full_size_config1_step():
         # eval_step_host == forward + argmax
         assert np.array_equal(m.eval_step_host(q, ln, fc7), am)
         m.close()
+
+
+def test_full_size_config1_training_mode_step():
+    """The configuration bench.py times: BASELINE config 1 (B = 500, T = 26, H = 512, L = 2) in TRAINING mode with the
+    in-kernel seed-hash Dropout (embedding, inter-layer, AxB q / i, head), through the persistent tcgen05 kernels in
+    bf16x2 (the default) and through the exact-fp32 path, against the fp32 oracle with the same seed: scores, loss, final
+    state and the three gradient blocks at 1e-4 (rel-L2 and rel-max); then the fused host-buffer step
+    nvqa_train_step_host reproduces the loss and the RMSprop update."""
+    nvm = nv()
+    cfg = nvm.Arch1Config()
+    oc = ocfg(cfg)
+    enc, emb, mm = nvm.synth_params(cfg, seed=123)
+    q, ln, fc7, lab = nvm.synth_batch(cfg, 500, seed=321, min_len=3)          # ragged lengths 3..26
+    seed = 20261018
+    f, grads, scores, ctx = A.jdj(oc, enc, emb, mm, q, ln, A.l2_normalize_rows(fc7), lab, seed=seed)
+    errs = {}
+    for name, prec in (("bf16x2", nvm.PREC_BF16X2), ("fp32_simt", nvm.PREC_FP32_SIMT)):
+        m = make_model(nvm, cfg, enc, emb, mm, prec)
+        m.set_batch_host(q, ln, fc7, lab)
+        m.forward(nvm.MODE_TRAIN, seed)
+        assert_close(m.scores(500), scores, FP32_TOL, f"{name} training-mode scores")
+        assert_close(m.state(500), ctx["tv_q"], FP32_TOL, f"{name} training-mode final LSTM state")
+        assert abs(m.loss() - f) <= FP32_TOL * abs(f)
+        m.backward()
+        errs[name] = [rel_err(m.scores(500), scores)[0]]
+        for blk, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), grads):
+            got = np.clip(m.get_grads(blk), -10, 10)
+            assert_close(got, gw, FP32_TOL, f"{name} training-mode gradient block {blk}")
+            errs[name].append(rel_err(got, gw)[0])
+        m.close()
+        # the call bench.py's e2e number makes
+        m = make_model(nvm, cfg, enc, emb, mm, prec)
+        f2 = m.train_step_host(q, ln, fc7, lab, 3e-4, seed)
+        assert abs(f2 - f) <= FP32_TOL * abs(f)
+        for blk, w0, gw in zip((nvm.BLOCK_ENCODER, nvm.BLOCK_EMBEDDING, nvm.BLOCK_MULTIMODAL), (enc, emb, mm), grads):
+            w1 = w0.copy()
+            A.rmsprop_update(w1, gw, np.zeros_like(w1), 3e-4)
+            big = np.abs(gw) > 1e-5        # lr * g / (0.1 |g| + eps): ill-conditioned where |g| ~ eps
+            assert_close((m.get_params(blk) - w0)[big], (w1 - w0)[big], 50 * FP32_TOL, f"{name} RMSprop update block {blk}")
+        m.close()
+    print("config-1 training-mode rel-L2 (scores, g_enc, g_emb, g_mm):", {k: ["%.1e" % e for e in v] for k, v in errs.items()})
 
 
 # ------------------------------------------------------------------------------------------------
@@ -325,6 +370,60 @@ def test_arch2_full_size_config4_step_and_update():
         m.close()
 
 
+@pytest.mark.parametrize("name,prec,tol", [PRECISIONS[0], PRECISIONS[1]])
+def test_arch2_literal_reference_mode(name, prec, tol):
+    """The literal reference: LookupTable gradient dropped (Encoder_lstm.lua:53) and, from the
+    second training step on, top-layer h0 = the previous step's d loss / d h_T (:238-239, :37-40: reset only when the batch
+    size changes).  Three training steps + a batch-size change + two more steps, against oracle.arch2.train_step(literal)."""
+    from oracle import arch2 as A2
+    nvm = nv()
+    cfg = nvm.Arch2Config(V=200, E=64, H=512 if prec else 64, L=1, I=40, O=31, T=7, B=48)
+    oc = ocfg2(cfg)
+    cnn, enc, mm = nvm.synth_params2(cfg, seed=5)
+    cnn, enc, mm = cnn * 3, enc * 3, mm * 3
+    m = make_model2(nvm, cfg, cnn, enc, mm, prec)
+    m.set_lookup_grad_literal(True)
+    m.set_stale_h0_literal(True)
+    carry, lr = {}, 3e-4
+    n_core = oc.n_enc - (cfg.V + 1) * cfg.E
+    for i, B in enumerate((48, 48, 48, 20, 20)):
+        q, ln, fc7, lab = nvm.synth_batch2(cfg, B, seed=40 + i, min_len=1)
+        fv = A.l2_normalize_rows(fc7)
+        # the oracle steps from the library's own weights / RMSprop state: RMSprop's first steps amplify 1e-5 gradient
+        # differences into different weights, which is not what this test is about
+        w = [m.get_params(b) for b in (0, 1, 2)]
+        ms = [m.get_rms(b) for b in (0, 1, 2)]
+        h0 = carry.get("dz") if carry.get("B") == B else None
+        f_ref, g_ref, scores, _ = A2.jdj(oc, w[0], w[1], w[2], q, fv, lab, seed=7 + i, literal_lookup_grad=True, h0_top=h0)
+        m.set_batch_host(q, ln, fc7, lab)
+        m.forward(nvm.MODE_TRAIN, 7 + i)
+        assert_close(m.scores(B), scores, tol, f"{name} literal arch2 step {i} scores (stale h0: {h0 is not None})")
+        if i in (1, 2, 4):
+            assert h0 is not None
+            plain = A2.jdj(oc, w[0], w[1], w[2], q, fv, None, seed=7 + i)[2]
+            assert np.abs(plain - scores).max() > 10 * tol * np.abs(scores).max()      # the stale state is visible
+        m.backward()
+        for blk, gw in zip((0, 1, 2), g_ref):
+            got = np.clip(m.get_grads(blk), -10, 10)
+            if blk == 1:
+                assert_close(got[:n_core], gw[:n_core], tol, f"{name} literal arch2 step {i} LSTM-core gradient")
+            else:
+                assert_close(got, gw, tol, f"{name} literal arch2 step {i} gradient block {blk}")
+        m.rmsprop_step(lr, wd=1e-4)
+        A2.train_step(oc, w[0], w[1], w[2], ms, (q, fv, lab), lr, seed=7 + i, literal=True, carry=carry)
+        # the LookupTable only sees weight decay in the literal reference
+        assert_close(m.get_params(1)[n_core:], w[1][n_core:], 1e-6, f"{name} literal arch2 step {i} lookup table after the update")
+    # switching the flag off restores the zero initial state
+    m.forward(nvm.MODE_EVAL, 0)
+    s_stale = m.scores(20)
+    m.set_stale_h0_literal(False)
+    m.forward(nvm.MODE_EVAL, 0)
+    assert np.abs(m.scores(20) - s_stale).max() > 0
+    w = [m.get_params(b) for b in (0, 1, 2)]
+    assert_close(m.scores(20), A2.jdj(oc, w[0], w[1], w[2], q, fv, None)[2], tol, f"{name} zero initial state restored")
+    m.close()
+
+
 def test_eval_100k_questions_properties():
     """BASELINE config 3: forward-only scoring of 100 000 synthetic questions (200 batches of 500, 10 000 distinct fc7
     rows indexed by an img_list), top-1000 argmax.  Oracle-checked on three batches; size-independent properties on
@@ -348,13 +447,32 @@ def test_eval_100k_questions_properties():
         answers[sl] = m.eval_step_host(np.ascontiguousarray(q_ra[sl]), np.ascontiguousarray(lengths[sl]),
                                        np.ascontiguousarray(fc7_all[img_list[sl]]))
     assert answers.min() >= 1 and answers.max() <= cfg.O
-    for s in (0, 49_500, 99_500):                                        # oracle on three batches
+    # Oracle on three batches.  The answer is the argmax of 1000 logits: it is pinned wherever the oracle's top-2 margin
+    # exceeds what the parity bar itself allows the logits to differ by (2 x tol x max|score|, each logit may move by tol);
+    # rows below that margin are reported, not hidden: their count and how many of them differ.  The exact-fp32 mode
+    # (same arithmetic as the oracle up to summation order) must agree on EVERY row whose margin clears 1e-6.
+    m32 = make_model(nvm, cfg, enc, emb, mm, nvm.PREC_FP32_SIMT)
+    excluded = mism_excluded = total = 0
+    for s in (0, 49_500, 99_500):
         sl = slice(s, s + 500)
-        scores, _ = A.forward(oc, enc, emb, mm, q_ra[sl], lengths[sl], A.l2_normalize_rows(fc7_all[img_list[sl]]))
+        fv = np.ascontiguousarray(fc7_all[img_list[sl]])
+        scores, _ = A.forward(oc, enc, emb, mm, q_ra[sl], lengths[sl], A.l2_normalize_rows(fv))
+        want = A.argmax_first(scores)
         srt = np.sort(scores, axis=1)
-        safe = (srt[:, -1] - srt[:, -2]) > 1e-4 * np.abs(scores).max()   # top-2 margin above the fp32-parity noise
+        margin, smax = srt[:, -1] - srt[:, -2], np.abs(scores).max()
+        safe = margin > 2 * FP32_TOL * smax
         assert safe.mean() > 0.9
-        assert np.array_equal(answers[sl][safe], A.argmax_first(scores)[safe])
+        assert np.array_equal(answers[sl][safe], want[safe])
+        total += 500
+        excluded += int((~safe).sum())
+        mism_excluded += int((answers[sl][~safe] != want[~safe]).sum())
+        a32 = m32.eval_step_host(np.ascontiguousarray(q_ra[sl]), np.ascontiguousarray(lengths[sl]), fv)
+        safe32 = margin > 1e-6 * smax
+        assert safe32.mean() > 0.995
+        assert np.array_equal(a32[safe32], want[safe32]), "fp32_simt argmax differs from the oracle above a 1e-6 margin"
+    print(f"eval argmax vs oracle (bf16x2): {total} rows, {excluded} below the 2e-4 margin, {mism_excluded} of those differ")
+    assert mism_excluded <= excluded
+    m32.close()
     again = np.zeros(1000, dtype=np.int32)
     perm = np.r_[np.arange(500, 1000), np.arange(0, 500)]                # second pass, batches swapped
     for k, s in enumerate((500, 0)):
