@@ -43,6 +43,14 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
 
 
+def host_threads():
+    """Host cores this process may use (cgroup / affinity aware)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
 
@@ -55,6 +63,7 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.power = []
         except Exception:
             self.nv = None
 
@@ -69,6 +78,7 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in names.items():
                     if r & bit:
@@ -79,8 +89,11 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(s)}
+        if getattr(self, "power", None):
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 def run_reference(args):
@@ -92,6 +105,8 @@ def run_reference(args):
     import torch
     from oracle import arch1 as A
     from oracle.torch_cpu import time_steps
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the reference arm must still use every host core
+    torch.set_num_threads(host_threads())
     cfg = A.Arch1Config()
     B = args.batch
     probe = time_steps(cfg, B, 1, 1)
@@ -233,6 +248,74 @@ def run_ours(args):
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     assert all(np.isfinite(losses)), "non-finite loss in the e2e run"
 
+    # ---- N > 1: correctness record of the fused NVLink exchange, untimed, after the timed regions --------------------
+    # (a) replicas stay bit-identical: SHA-256 of every rank's parameters after 3 more fused steps; (b) the fused kernels
+    # compute the same update as "NCCL all-reduce(sum) ; clamp ; RMSprop" on the SAME gradients from the SAME state.
+    dp_check = None
+    if fused:
+        import hashlib
+        blocks = (nv.BLOCK_ENCODER, nv.BLOCK_EMBEDDING, nv.BLOCK_MULTIMODAL)
+        model.set_batch_device(dq, dl, df, dy, B)
+        traj = []
+        with torch.cuda.stream(stream):
+            for i in range(3):
+                dp.fused_train_step(model, lr0, 7000 + i)
+                traj.append(model.loss())
+        model.sync()
+        digest = hashlib.sha256(b"".join(model.get_params(b).tobytes() for b in blocks)).hexdigest()
+        digs = [None] * world
+        dist.all_gather_object(digs, digest)
+        # same state, same gradients, two update paths.  The RMSprop state is sharded in the fused path (a rank owns 1/N of
+        # every block), so the comparison is made on THIS rank's shards, in the library's internal flat layout.
+        pptr, _, off = model.device_views()
+
+        def flat_params():
+            out = np.empty(off[3], dtype=np.float32)
+            nv._lib.check(model.lib.nvqa_memcpy_d2h(model.handle, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(pptr),
+                                                    out.nbytes))
+            return out
+
+        mine = np.zeros(off[3], dtype=bool)
+        for k in range(3):
+            b0, b1 = off[k] // 4, off[k + 1] // 4
+            per = (b1 - b0 + world - 1) // world
+            lo = min(b1, b0 + per * rank)
+            mine[4 * lo:4 * min(b1, lo + per)] = True
+        pa = [model.get_params(b) for b in blocks]                # Torch layout, to restore below
+        r0 = [model.get_rms(b) for b in blocks]
+        x0 = flat_params()
+        with torch.cuda.stream(stream):
+            model.forward(nv.MODE_TRAIN, 7100)
+            model.backward(nv.PHASE_ALL)
+            nv._lib.check(model.lib.nvqa_dp_rmsprop_step(model.handle, lr0, 0.99, 1e-8, 0.0, 10.0))
+        model.sync()
+        xa = flat_params()
+        pa_after = [model.get_params(b) for b in blocks]
+        for b, w, r in zip(blocks, pa, r0):
+            model.set_params(b, w)
+            nv._lib.check(model.lib.nvqa_rms_set(model.handle, b, r.ctypes.data_as(nv._lib.c_f32p)))
+        views_chk = dp.grad_bucket_views(model, local)
+        with torch.cuda.stream(stream):
+            for b in blocks:                                      # the gradients are still those of the backward above
+                dist.all_reduce(views_chk[b])
+            model.rmsprop_step(lr0, grad_scale=1.0 / world)
+        model.sync()
+        xb = flat_params()
+        num = float(np.sum((xa[mine].astype(np.float64) - xb[mine]) ** 2))
+        den = float(np.sum((xb[mine].astype(np.float64) - x0[mine]) ** 2))
+        rel = torch.tensor([(num / den) ** 0.5 if den > 0 else 0.0], device=f"cuda:{local}")
+        dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+        dp_check = {"replicas_identical": len(set(digs)) == 1, "fused_steps": 3, "loss_trajectory": traj,
+                    "update_rel_l2_vs_nccl": float(rel.item()),
+                    "what": "3 extra fused steps: SHA-256 of all parameters equal on every rank; then one update computed "
+                            "twice from the same parameters / RMSprop state / local gradients: fused peer-memory kernels vs "
+                            "NCCL all-reduce + clamp_rmsprop (rel-L2 of the parameter updates on each rank's own shards, "
+                            "max over ranks; summation order differs, and RMSprop's early steps are ill-conditioned "
+                            "where |g| ~ eps)"}
+        pa = pa_after
+        for b, w in zip(blocks, pa):                              # leave the replicas identical
+            model.set_params(b, w)
+
     # ---- live per-kernel-class timing for the roofline (separate, profiled pass) ----
     pk = peaks()
     roof = None
@@ -358,7 +441,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import arch1 as A
         from oracle.torch_cpu import time_steps
-        res = time_steps(A.Arch1Config(), B, 3, 1)
+        res = time_steps(A.Arch1Config(), B, 3, 1, threads=host_threads())
         cpu = {"value": res["samples_per_s"], "unit": UNIT, "cores": res["threads"], "kind": "port",
                "sample": f"3 timed steps (+1 warm-up) of the same {B}-sample batch shape",
                "what": "PyTorch-CPU (MKL) op-for-op restatement of the Torch7 CPU path; Torch7 cannot run here",
@@ -390,6 +473,8 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "tflops_algorithmic": value * FLOPS_PER_SAMPLE / 1e12,
                 "roofline": roof, "cpu_baseline": cpu, "extras": extras}
+        if dp_check is not None:
+            line["dp_check"] = dp_check
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if dist is not None:
         dist.barrier()

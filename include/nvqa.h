@@ -139,8 +139,7 @@ int nvqa_adam_step(nvqa_model* m, float lr, float beta1, float beta2, float eps,
  * AutoEncoder_text_nostart.lua:334); valid after nvqa_forward until nvqa_backward consumes them in place */
 int nvqa_logprobs_get(nvqa_model* m, int32_t step, float* host_dst);
 /* arch 1 trainer variants (002_train_vqa_arch1/003_train_ae_based*.lua): fusion = NVQA_FUSION_*; lr_scale multiplies the
- * encoder and embedding gradients before the clamp (-lr_scale, 003_train_ae_based_wp.lua:30,344; not applied by
- * nvqa_dp_rmsprop_step); norm_split > 0: with img_norm = 1 the feature columns [0, norm_split) and [norm_split, I) are
+ * encoder and embedding gradients before the clamp (-lr_scale, 003_train_ae_based_wp.lua:30,344); norm_split > 0: with img_norm = 1 the feature columns [0, norm_split) and [norm_split, I) are
  * L2-normalised separately (early fusion of two CNN features, 003_train_ae_based_ef.lua:74,116-124). */
 int nvqa_set_variant(nvqa_model* m, int32_t fusion, float lr_scale, int32_t norm_split);
 /* arch 2 / 3: on = 1 reproduces the literal reference, whose per-step lookup-table clones share `weight` but not
@@ -218,6 +217,15 @@ int nvqa_dp_export(nvqa_model* m, void* blob_out);
 int nvqa_dp_connect(nvqa_model* m, int32_t rank, int32_t world, const void* blobs);
 int nvqa_dp_disconnect(nvqa_model* m);
 int nvqa_dp_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps, float wd, float clamp);
+/* the whole data-parallel iteration on the batch already set (nvqa_set_batch*): nvqa_forward(TRAIN, seed), nvqa_backward
+ * with the exchange + update of every parameter block started as soon as its gradient is final -- the multimodal block
+ * (53 % of the gradient, final after the head backward) on a side stream beside the LSTM backward, encoder and embedding
+ * after theirs.  Same result as nvqa_forward ; nvqa_backward ; nvqa_dp_rmsprop_step.  -lr_scale (nvqa_set_variant) and the
+ * literal lookup gradient (nvqa_set_lookup_grad_literal) are honoured by both. */
+int nvqa_dp_train_step(nvqa_model* m, float lr, uint64_t seed, float alpha, float eps, float wd, float clamp);
+/* A lagging peer is waited for up to NVQA_DP_TIMEOUT_S seconds (environment, default 600); then the wait gives up and
+ * *timed_out = 1 from here on (nvqa_sync returns an error): the replica's parameters are invalid, the process survives. */
+int nvqa_dp_status(nvqa_model* m, int32_t* timed_out);
 
 /* ---- utilities ------------------------------------------------------------------------------ */
 int nvqa_host_alloc(void** p, int64_t bytes);     /* pinned host memory */

@@ -10,8 +10,9 @@
 //     all-gather     : the updated parameter shard is stored straight into every rank's parameter vector
 //
 // so per step each GPU moves 2 * (N-1)/N * P * 4 bytes over NVLink and the optimizer's HBM traffic drops N-fold.
-// Cross-GPU ordering uses two monotonically increasing flag words per (rank, peer) pair, written remotely with
-// st.release.sys and polled locally with ld.acquire.sys:
+// The exchange runs PER PARAMETER BLOCK (encoder / embedding / multimodal), each as soon as its gradient is final
+// (nvqa_dp_train_step).  Cross-GPU ordering uses two monotonically increasing flag words per (block, rank, peer), written
+// remotely with st.release.sys and polled locally with ld.acquire.sys:
 //     ready[r] >= 2k+1 : rank r's gradients of step k are complete (signalled by a 1-thread kernel that follows the
 //                        backward pass on the stream)
 //     done[r]  >= 2k+2 : rank r has finished reading everybody's gradients and writing its parameter shard everywhere;
@@ -19,13 +20,18 @@
 //                        gradients nor its parameters are touched by a peer once the next kernel on its stream starts.
 #include "model.cuh"
 
+#include <cstdlib>
+
 namespace nvqa {
 
 constexpr int DP_MAX = 8;                       // ranks of one NVSwitch domain
+// Flag page of a rank (128 words): per parameter block k = 0..2  ready[k][16] at 32 k, done[k][16] at 32 k + 16 (both
+// indexed by the WRITER's rank); [96 + k] = CTA completion counter of block k's kernel; [100] = "a wait timed out".
+constexpr int DP_FLAG_WORDS = 128, DP_CTR = 96, DP_ERR = 100;
 struct DpPeers {
   const float* g[DP_MAX];
   float* x[DP_MAX];
-  unsigned int* flags[DP_MAX];                  // [0..15] ready counters, [16..31] done counters, indexed by writer rank
+  unsigned int* flags[DP_MAX];
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -36,13 +42,24 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int target) {
-  const long long t0 = clock64();
+__device__ __forceinline__ unsigned long long dp_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Waits for a peer's flag.  A peer that lags (validation pass, checkpoint, data stall) is waited for up to timeout_ns of
+// WALL-CLOCK time (NVQA_DP_TIMEOUT_S, default 600 s); after that the wait gives up, raises the error word of this rank's
+// flag page -- which nvqa_sync / nvqa_loss turn into an error return -- and the kernel runs to completion instead of
+// trapping (a trap would take the CUDA context, i.e. the whole process, with it).
+__device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int target, unsigned long long timeout_ns,
+                                           unsigned int* err) {
+  const unsigned long long t0 = dp_now_ns();
   while (ld_acquire_sys(p) < target) {
     __nanosleep(100);
-    if (clock64() - t0 > 20000000000LL) {       // ~10 s: a peer died or never launched -> fail loudly instead of hanging
-      printf("nvqa dp: timed out waiting for a peer flag (want %u)\n", target);
-      __trap();
+    if (dp_now_ns() - t0 > timeout_ns) {
+      *err = 1u;
+      __threadfence_system();
+      return;
     }
   }
 }
@@ -53,19 +70,22 @@ __device__ __forceinline__ float4 ld_peer(const float* p) {
   return v;
 }
 
-__global__ void dp_signal_ready_kernel(DpPeers p, int rank, int world, unsigned int value) {
+__global__ void dp_signal_ready_kernel(DpPeers p, int rank, int world, int block, unsigned int value) {
   __threadfence_system();
-  if ((int)threadIdx.x < world) st_release_sys(p.flags[threadIdx.x] + rank, value);
+  if ((int)threadIdx.x < world) st_release_sys(p.flags[threadIdx.x] + 32 * block + rank, value);
 }
 
+// One parameter block's shard [lo4, lo4 + n4) (float4 units of the flat vector) of this rank: grid-stride, so the same
+// kernel runs wide on the main stream or with a handful of CTAs on the side stream beside the 128-CTA LSTM backward.
 __global__ void __launch_bounds__(256)
-dp_fused_rmsprop_kernel(DpPeers p, float* __restrict__ rms, const unsigned int* my_flags, unsigned int* done_ctr, int rank,
-                        int world, long long lo4, long long n4, unsigned int step, float lr, float alpha, float oma, float eps,
-                        float wd, float clampv, float gscale) {
-  if ((int)threadIdx.x < world) spin_until(my_flags + threadIdx.x, 2 * step + 1);
+dp_fused_rmsprop_kernel(DpPeers p, float* __restrict__ rms, unsigned int* my_flags, int block, int rank, int world,
+                        long long lo4, long long n4, unsigned int step, float lr, float alpha, float oma, float eps, float wd,
+                        float clampv, float gscale, unsigned long long timeout_ns) {
+  unsigned int* ready = my_flags + 32 * block;
+  unsigned int* done = ready + 16;
+  if ((int)threadIdx.x < world) spin_until(ready + threadIdx.x, 2 * step + 1, timeout_ns, my_flags + DP_ERR);
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = (lo4 + i) * 4;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -91,12 +111,12 @@ dp_fused_rmsprop_kernel(DpPeers p, float* __restrict__ rms, const unsigned int* 
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(done_ctr, 1u);
+    const unsigned int prev = atomicAdd(my_flags + DP_CTR + block, 1u);
     if (prev == gridDim.x - 1) {                 // last CTA of this rank: everything this rank reads / writes is done
-      *done_ctr = 0;
+      my_flags[DP_CTR + block] = 0;
       __threadfence_system();
-      for (int r = 0; r < world; ++r) st_release_sys(p.flags[r] + 16 + rank, 2 * step + 2);
-      for (int r = 0; r < world; ++r) spin_until(my_flags + 16 + r, 2 * step + 2);
+      for (int r = 0; r < world; ++r) st_release_sys(p.flags[r] + 32 * block + 16 + rank, 2 * step + 2);
+      for (int r = 0; r < world; ++r) spin_until(done + r, 2 * step + 2, timeout_ns, my_flags + DP_ERR);
     }
   }
 }
@@ -117,10 +137,9 @@ extern "C" int nvqa_dp_export(nvqa_model* m, void* blob_out) {
   NVQA_CHECK(m && blob_out, "null argument");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   if (!m->dp_flags) {
-    NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->dp_flags), 64 * sizeof(unsigned int)));
+    NVQA_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->dp_flags), DP_FLAG_WORDS * sizeof(unsigned int)));
     m->allocs.push_back(m->dp_flags);
-    NVQA_CUDA(cudaMemset(m->dp_flags, 0, 64 * sizeof(unsigned int)));
-    m->dp_done = m->dp_flags + 48;
+    NVQA_CUDA(cudaMemset(m->dp_flags, 0, DP_FLAG_WORDS * sizeof(unsigned int)));
   }
   DpBlob b;
   memset(&b, 0, sizeof(b));
@@ -154,16 +173,81 @@ extern "C" int nvqa_dp_connect(nvqa_model* m, int32_t rank, int32_t world, const
     m->dp_peer_params[r] = static_cast<float*>(px);
     m->dp_peer_flags[r] = static_cast<unsigned int*>(pf);
   }
-  m->dp_rank = rank; m->dp_world = world; m->dp_step = 0;
+  if (!m->dp_stream) {
+    NVQA_CUDA(cudaStreamCreateWithFlags(&m->dp_stream, cudaStreamNonBlocking));
+    NVQA_CUDA(cudaEventCreateWithFlags(&m->dp_fork, cudaEventDisableTiming));
+    NVQA_CUDA(cudaEventCreateWithFlags(&m->dp_join, cudaEventDisableTiming));
+  }
+  m->dp_rank = rank; m->dp_world = world;
+  for (int k = 0; k < 3; ++k) m->dp_steps[k] = 0;
   return 0;
 }
 
 extern "C" int nvqa_dp_disconnect(nvqa_model* m) {
   NVQA_CHECK(m, "null model");
   if (m->dp_world) NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  if (m->dp_stream) NVQA_CUDA(cudaStreamSynchronize(m->dp_stream));
   for (void* p : m->dp_opened) cudaIpcCloseMemHandle(p);
   m->dp_opened.clear();
   m->dp_world = 0;
+  return 0;
+}
+
+// Has a peer wait of this rank's fused kernels timed out since the connect?  (blocks: reads one word from the device)
+extern "C" int nvqa_dp_status(nvqa_model* m, int32_t* timed_out) {
+  NVQA_CHECK(m && timed_out, "null argument");
+  *timed_out = 0;
+  if (!m->dp_flags) return 0;
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  unsigned int v = 0;
+  NVQA_CUDA(cudaMemcpy(&v, m->dp_flags + DP_ERR, sizeof(v), cudaMemcpyDeviceToHost));
+  *timed_out = v != 0;
+  return 0;
+}
+
+static unsigned long long dp_timeout_ns() {
+  static unsigned long long ns = 0;
+  if (!ns) {
+    const char* e = getenv("NVQA_DP_TIMEOUT_S");
+    double s = e ? atof(e) : 600.0;
+    if (!(s > 0)) s = 600.0;
+    ns = (unsigned long long)(s * 1e9);
+  }
+  return ns;
+}
+
+// One parameter block: signal "my gradients of this block are final", then the fused reduce-scatter + update + all-gather
+// kernel over this rank's shard of the block.  side = true: on the side stream with few CTAs (beside the LSTM backward).
+static int dp_block(nvqa_model* m, int block, float lr, float alpha, float eps, float wd, float clamp, bool side) {
+  DpPeers p;
+  memset(&p, 0, sizeof(p));
+  for (int r = 0; r < m->dp_world; ++r) { p.g[r] = m->dp_peer_grads[r]; p.x[r] = m->dp_peer_params[r]; p.flags[r] = m->dp_peer_flags[r]; }
+  const long long b0 = m->off_blk[block] / 4, b1 = m->off_blk[block + 1] / 4;            // block offsets are multiples of 4
+  const long long per = (b1 - b0 + m->dp_world - 1) / m->dp_world;
+  const long long lo4 = std::min(b1, b0 + per * m->dp_rank), hi4 = std::min(b1, lo4 + per);
+  const long long n4 = hi4 - lo4;
+  const unsigned int step = m->dp_steps[block]++;
+  // -lr_scale of the arch 1 trainer variants multiplies the encoder and embedding gradients before the clamp
+  // (003_train_ae_based_wp.lua:344-346), exactly as nvqa_rmsprop_step does
+  float gscale = 1.0f / (float)m->dp_world;
+  if (m->cfg.arch == 1 && block != NVQA_BLOCK_MULTIMODAL) gscale *= m->lr_scale;
+  cudaStream_t s = side ? m->dp_stream : m->stream;
+  dp_signal_ready_kernel<<<1, 32, 0, s>>>(p, m->dp_rank, m->dp_world, block, 2 * step + 1);
+  NVQA_LAUNCHED();
+  static int side_ctas = -1;
+  if (side_ctas < 0) { const char* e = getenv("NVQA_DP_SIDE_CTAS"); side_ctas = e ? std::max(1, atoi(e)) : 16; }
+  const int full = std::max(1, std::min(ceil_div(n4, 256), 148 * 8));
+  const int grid = side ? std::min(full, side_ctas) : full;
+  dp_fused_rmsprop_kernel<<<grid, 256, 0, s>>>(p, m->rms, m->dp_flags, block, m->dp_rank, m->dp_world, lo4, n4, step, lr, alpha,
+                                              (float)(1.0 - (double)alpha), eps, wd, clamp, gscale, dp_timeout_ns());
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+static int drop_lookup_grad_dp(nvqa_model* m) {
+  // the literal reference's gradient-less LookupTable (nvqa_set_lookup_grad_literal), as in nvqa_rmsprop_step
+  if (m->lookup_grad_literal && m->glookup)
+    NVQA_CUDA(cudaMemsetAsync(m->glookup, 0, (size_t)(m->cfg.V + 1) * m->cfg.E * 4, m->stream));
   return 0;
 }
 
@@ -172,28 +256,46 @@ extern "C" int nvqa_dp_rmsprop_step(nvqa_model* m, float lr, float alpha, float 
   NVQA_CHECK(m && m->dp_world >= 1, "nvqa_dp_rmsprop_step: not connected (nvqa_dp_export / nvqa_dp_connect)");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   umma_workspace_invalidate(m->ws);
-  DpPeers p;
-  memset(&p, 0, sizeof(p));
-  for (int r = 0; r < m->dp_world; ++r) { p.g[r] = m->dp_peer_grads[r]; p.x[r] = m->dp_peer_params[r]; p.flags[r] = m->dp_peer_flags[r]; }
-  const long long n4_all = m->P / 4, per = (n4_all + m->dp_world - 1) / m->dp_world;
-  const long long lo4 = std::min<long long>(n4_all, per * m->dp_rank), hi4 = std::min<long long>(n4_all, lo4 + per);
-  const long long n4 = hi4 - lo4;
-  const unsigned int step = m->dp_step++;
+  NVQA_TRY(drop_lookup_grad_dp(m));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (m->profiling) {
     NVQA_CUDA(cudaEventCreate(&e0)); NVQA_CUDA(cudaEventCreate(&e1));
     NVQA_CUDA(cudaEventRecord(e0, m->stream));
   }
-  dp_signal_ready_kernel<<<1, 32, 0, m->stream>>>(p, m->dp_rank, m->dp_world, 2 * step + 1);
-  NVQA_LAUNCHED();
-  const int grid = std::max(1, ceil_div(n4, 256));
-  dp_fused_rmsprop_kernel<<<grid, 256, 0, m->stream>>>(p, m->rms, m->dp_flags, m->dp_done, m->dp_rank, m->dp_world, lo4, n4, step, lr,
-                                                      alpha, (float)(1.0 - (double)alpha), eps, wd, clamp, 1.0f / (float)m->dp_world);
-  NVQA_LAUNCHED();
+  for (int k = 0; k < 3; ++k) NVQA_TRY(dp_block(m, k, lr, alpha, eps, wd, clamp, false));
   if (m->profiling) {
     NVQA_CUDA(cudaEventRecord(e1, m->stream));
     m->prof[CAT_OPT].pending.emplace_back(e0, e1);
-    m->prof[CAT_OPT].launches += 2;
+    m->prof[CAT_OPT].launches += 6;
   }
+  return 0;
+}
+
+// One whole data-parallel training step on the batch already set: JdJ with the exchange of each parameter block started as
+// soon as its gradient is final.  arch 1: the multimodal block (53 % of the gradient) is final after the head backward and
+// none of its weights is read again in this step, so its reduce-scatter + update + all-gather runs on a side stream with
+// a few CTAs on the 20 SMs the 128-CTA persistent LSTM backward leaves free; encoder and embedding follow on the main
+// stream after their gradients (the LSTM backward / dgrad GEMMs still read the encoder weights until then).
+extern "C" int nvqa_dp_train_step(nvqa_model* m, float lr, uint64_t seed, float alpha, float eps, float wd, float clamp) {
+  NVQA_CHECK(m && m->dp_world >= 1, "nvqa_dp_train_step: not connected (nvqa_dp_export / nvqa_dp_connect)");
+  NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  static int overlap = -1;
+  if (overlap < 0) { const char* e = getenv("NVQA_DP_OVERLAP"); overlap = e ? atoi(e) : 1; }
+  NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
+  if (m->cfg.arch != 1 || !overlap || m->profiling) {
+    NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
+    return nvqa_dp_rmsprop_step(m, lr, alpha, eps, wd, clamp);
+  }
+  NVQA_TRY(nvqa_backward(m, NVQA_PHASE_HEAD));
+  NVQA_CUDA(cudaEventRecord(m->dp_fork, m->stream));
+  NVQA_CUDA(cudaStreamWaitEvent(m->dp_stream, m->dp_fork, 0));
+  NVQA_TRY(dp_block(m, NVQA_BLOCK_MULTIMODAL, lr, alpha, eps, wd, clamp, true));
+  NVQA_CUDA(cudaEventRecord(m->dp_join, m->dp_stream));
+  NVQA_TRY(nvqa_backward(m, NVQA_PHASE_LSTM));
+  NVQA_TRY(nvqa_backward(m, NVQA_PHASE_EMBED));
+  NVQA_TRY(dp_block(m, NVQA_BLOCK_ENCODER, lr, alpha, eps, wd, clamp, false));
+  NVQA_TRY(dp_block(m, NVQA_BLOCK_EMBEDDING, lr, alpha, eps, wd, clamp, false));
+  NVQA_CUDA(cudaStreamWaitEvent(m->stream, m->dp_join, 0));      // the next forward reads the multimodal weights
+  umma_workspace_invalidate(m->ws);
   return 0;
 }

@@ -1391,6 +1391,20 @@ __global__ void __launch_bounds__(256) v2_sum4_kernel(const float* __restrict__ 
                                                   (a.w + b.w) + (c.w + d.w));
 }
 
+// Nsight Compute cannot replay a launch that is both cooperative and clustered (the driver returns LaunchFailed), which
+// is what the pair forward kernel and the 4-CTA-cluster backward kernel are.  The cooperative attribute only adds the
+// co-residency CHECK (128 CTAs on 148 SMs fit either way), so it is dropped when a profiler is injected into the process
+// (Nsight Compute / CUPTI injection exports these variables into the target) or on request (NVQA_LSTM_NOCOOP=1).
+static bool v2_nocoop() {
+  static int v = -1;
+  if (v < 0) {
+    v = 0;
+    for (const char* name : {"NVQA_LSTM_NOCOOP", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE", "NV_NSIGHT_INJECTION_PORT_BASE",
+                             "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "CUDA_INJECTION64_PATH"})
+      if (getenv(name)) v = 1;
+  }
+  return v != 0;
+}
 static bool v2_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("NVQA_LSTM_V2"); on = e ? atoi(e) : 1; }
@@ -1496,8 +1510,14 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pair ? 2 : 1;
-    if (use_pair && getenv("NVQA_LSTM_NOCOOP")) { cfg.attrs = attr + 1; cfg.numAttrs = 1; }   // ncu: see lstm_bwd_v3
-    NVQA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    if (use_pair && v2_nocoop()) { cfg.attrs = attr + 1; cfg.numAttrs = 1; }   // profilers: see v2_nocoop
+    cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
+    if (le != cudaSuccess && use_pair && cfg.numAttrs == 2) {
+      (void)cudaGetLastError();                     // refused as cooperative + clustered: same grid without the co-residency check
+      cfg.attrs = attr + 1; cfg.numAttrs = 1;
+      le = cudaLaunchKernelExC(&cfg, fn, args);
+    }
+    NVQA_CUDA(le);
     ++g_launches;
     if (dbg & 1) {
       long long hst[16 * 8];
@@ -1583,7 +1603,7 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
                          : P == 2 ? (stack3 ? (const void*)lstm_bwd_v3_kernel<2, true, false> : (const void*)lstm_bwd_v3_kernel<2, false, false>)
                                   : (const void*)lstm_bwd_v3_kernel<1, false, false>;
     NVQA_CUDA(cudaFuncSetAttribute(f3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static const bool nocoop = getenv("NVQA_LSTM_NOCOOP") != nullptr;
+    const bool nocoop = v2_nocoop();
     bool ok = true;
     for (int tile0 = 0; tile0 < tiles && ok; tile0 += max_tiles) {
       int b0 = tile0 * 64, bend = std::min(B, (tile0 + max_tiles) * 64);
@@ -1601,6 +1621,11 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
       // runs set NVQA_LSTM_NOCOOP=1, which drops only the co-residency CHECK (128 CTAs on 148 idle SMs either way)
       cfg3.attrs = at3; cfg3.numAttrs = nocoop ? 1 : 2;
       cudaError_t le = cudaLaunchKernelExC(&cfg3, f3, a3);
+      if (le != cudaSuccess && cfg3.numAttrs == 2) {
+        (void)cudaGetLastError();                   // refused as cooperative + clustered: retry as a plain cluster launch
+        cfg3.numAttrs = 1;
+        le = cudaLaunchKernelExC(&cfg3, f3, a3);
+      }
       if (le != cudaSuccess) {
         (void)cudaGetLastError();                   // the clusters could not be made co-resident: generation 2 below
         if (tile0 > 0) { set_error("lstm_bwd_v3: cluster launch failed in the middle of a batch"); return 1; }

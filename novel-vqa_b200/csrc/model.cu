@@ -173,6 +173,7 @@ extern "C" int nvqa_model_destroy(nvqa_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->dp_stream) cudaStreamSynchronize(m->dp_stream);
   for (void* p : m->dp_opened) cudaIpcCloseMemHandle(p);
   for (void* p : m->allocs) cudaFree(p);
   if (m->loss_host) cudaFreeHost(m->loss_host);
@@ -182,6 +183,9 @@ extern "C" int nvqa_model_destroy(nvqa_model* m) {
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->fc7_ready) cudaEventDestroy(m->fc7_ready);
   if (m->fc7_consumed) cudaEventDestroy(m->fc7_consumed);
+  if (m->dp_stream) cudaStreamDestroy(m->dp_stream);
+  if (m->dp_fork) cudaEventDestroy(m->dp_fork);
+  if (m->dp_join) cudaEventDestroy(m->dp_join);
   delete m;
   return 0;
 }
@@ -419,6 +423,12 @@ extern "C" int nvqa_sync(nvqa_model* m) {
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
   if (m->copy_stream) NVQA_CUDA(cudaStreamSynchronize(m->copy_stream));   // an fc7 copy of nvqa_set_batch_host may be in flight
+  if (m->dp_stream) NVQA_CUDA(cudaStreamSynchronize(m->dp_stream));
+  if (m->dp_world > 0) {
+    int32_t bad = 0;
+    NVQA_TRY(nvqa_dp_status(m, &bad));
+    NVQA_CHECK(!bad, "data-parallel exchange: a peer did not arrive within NVQA_DP_TIMEOUT_S; this replica's parameters are invalid");
+  }
   return 0;
 }
 

@@ -106,10 +106,11 @@ struct nvqa_model {
   int dp_rank = 0, dp_world = 0;
   float* dp_peer_grads[16] = {};     // every rank's flat gradient vector (own entry = grads)
   float* dp_peer_params[16] = {};    // every rank's flat parameter vector
-  unsigned int* dp_flags = nullptr;  // [2][16] counters written by the peers: [0][r] = rank r's grads ready, [1][r] = rank r done
+  unsigned int* dp_flags = nullptr;  // flag page written by the peers (layout: dp_fused.cu)
   unsigned int* dp_peer_flags[16] = {};
-  unsigned int* dp_done = nullptr;   // CTA completion counter of the fused kernel
-  unsigned int dp_step = 0;
+  unsigned int dp_steps[3] = {0, 0, 0};   // exchanges done so far, per parameter block
+  cudaStream_t dp_stream = nullptr;  // side stream of the early (multimodal) block exchange
+  cudaEvent_t dp_fork = nullptr, dp_join = nullptr;
   std::vector<void*> dp_opened;      // cudaIpcOpenMemHandle mappings to close
   bool profiling = false;
   ProfCat prof[CAT_COUNT];

@@ -32,12 +32,31 @@ def grad_bucket_views(model, device):
     return views
 
 
-def backward_allreduce(model, views, dist, world):
+def bind_current_stream(model):
+    """NCCL (through torch.distributed) orders its collectives against torch's CURRENT stream only, while the library
+    enqueues on the model's own stream by default: an all_reduce on the gradient views could then read gradients the
+    backward kernels have not written yet, and the optimizer could start before the all_reduce has finished.  The NCCL path
+    therefore runs the model ON torch's current stream (nvqa_set_stream); called by train_step / backward_allreduce."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    s = torch.cuda.current_stream().cuda_stream
+    if getattr(model, "_bound_stream", None) != s:
+        model.sync()                                   # work already enqueued on the previous stream
+        _lib.check(model.lib.nvqa_set_stream(model.handle, C.c_void_p(s)))
+        model._bound_stream = s
+    return s
+
+
+def backward_allreduce(model, views, dist, world, bind=True):
     """backward in three phases; after each, all-reduce the bucket that just became final.
-    ``dist`` is torch.distributed (or a stand-in with all_reduce(tensor, async_op=True))."""
+    ``dist`` is torch.distributed (or a stand-in with all_reduce(tensor, async_op=True)); bind=False only for such
+    stand-ins (CPU tests), a real NCCL run must order the collectives against the model's stream."""
     if world == 1:
         model.backward(api.PHASE_ALL)
         return
+    if bind:
+        bind_current_stream(model)
     works = []
     for phase, blk in PHASES:
         model.backward(phase)
@@ -46,11 +65,13 @@ def backward_allreduce(model, views, dist, world):
         w.wait()
 
 
-def train_step(model, views, dist, world, lr, seed):
+def train_step(model, views, dist, world, lr, seed, bind=True):
     """JdJ + all-reduce + clamp + RMSprop on an already-set batch (NCCL path: bucketed all-reduce overlapped with the
     backward phases, then the replicated optimizer kernel)."""
+    if world > 1 and bind:
+        bind_current_stream(model)
     model.forward(api.MODE_TRAIN, seed)
-    backward_allreduce(model, views, dist, world)
+    backward_allreduce(model, views, dist, world, bind)
     model.rmsprop_step(lr, grad_scale=1.0 / world)
 
 
@@ -74,12 +95,11 @@ def connect_fused(model, dist, rank, world):
 
 
 def fused_train_step(model, lr, seed, alpha=0.99, eps=1e-8, wd=0.0, clamp=10.0):
-    """JdJ, then ONE kernel per rank: reduce-scatter over NVLink peer memory -> 1/world -> clamp -> RMSprop on the
-    rank's shard -> all-gather of the updated parameters (csrc/dp_fused.cu).  No NCCL call on the step."""
+    """JdJ with, per parameter block and as soon as its gradient is final, ONE kernel per rank: reduce-scatter over NVLink
+    peer memory -> 1/world -> clamp -> RMSprop on the rank's shard -> all-gather of the updated parameters
+    (csrc/dp_fused.cu; the multimodal block's exchange overlaps the LSTM backward).  No NCCL call on the step."""
     from . import _lib
-    model.forward(api.MODE_TRAIN, seed)
-    model.backward(api.PHASE_ALL)
-    _lib.check(model.lib.nvqa_dp_rmsprop_step(model.handle, lr, alpha, eps, wd, clamp))
+    _lib.check(model.lib.nvqa_dp_train_step(model.handle, lr, seed, alpha, eps, wd, clamp))
 
 
 def average_then_update_reference(grads_per_rank, clamp=10.0):

@@ -43,7 +43,7 @@ def _worker(rank, world, port, out):
     half = q_ra.shape[0] // world
     sl = slice(rank * half, (rank + 1) * half)
     model = OracleRankModel(cfg, (enc, emb, mm), (q_ra[sl], lengths[sl], fv[sl], labels[sl]), seed=None)
-    dp.backward_allreduce(model, model.views, dist, world)
+    dp.backward_allreduce(model, model.views, dist, world, bind=False)   # fake CPU model: no CUDA stream to bind
     assert model.phases == [api.PHASE_HEAD, api.PHASE_LSTM, api.PHASE_EMBED]        # readiness order
     # what clamp_rmsprop does with grad_scale = 1/world
     g = [np.clip(model.views[b].numpy() * np.float32(1.0 / world), -10, 10) for b in
