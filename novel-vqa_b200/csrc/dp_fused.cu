@@ -10,11 +10,11 @@
 //     all-gather     : the updated parameter shard is stored straight into every rank's parameter vector
 //
 // so per step each GPU moves 2 * (N-1)/N * P * 4 bytes over NVLink and the optimizer's HBM traffic drops N-fold.
-// The exchange runs PER PARAMETER BLOCK (encoder / embedding / multimodal), each as soon as its gradient is final
-// (nvqa_dp_train_step).  Cross-GPU ordering uses two monotonically increasing flag words per (block, rank, peer), written
+// The exchange runs per RANGE of parameter blocks -- arch 1: {encoder + embedding} and {multimodal} -- each as soon as its
+// gradient is final (nvqa_dp_train_step); a rank owns 1/N of every range.  Cross-GPU ordering uses two monotonically increasing flag words per (block, rank, peer), written
 // remotely with st.release.sys and polled locally with ld.acquire.sys:
-//     ready[r] >= 2k+1 : rank r's gradients of step k are complete (signalled by a 1-thread kernel that follows the
-//                        backward pass on the stream)
+//     ready[r] >= 2k+1 : rank r's gradients of step k are complete (signalled by the first CTA of rank r's kernel, which
+//                        follows the backward pass on the stream)
 //     done[r]  >= 2k+2 : rank r has finished reading everybody's gradients and writing its parameter shard everywhere;
 //                        a rank's kernel does not exit before it has seen done from ALL ranks, so neither its
 //                        gradients nor its parameters are touched by a peer once the next kernel on its stream starts.
@@ -70,11 +70,6 @@ __device__ __forceinline__ float4 ld_peer(const float* p) {
   return v;
 }
 
-__global__ void dp_signal_ready_kernel(DpPeers p, int rank, int world, int block, unsigned int value) {
-  __threadfence_system();
-  if ((int)threadIdx.x < world) st_release_sys(p.flags[threadIdx.x] + 32 * block + rank, value);
-}
-
 // One parameter block's shard [lo4, lo4 + n4) (float4 units of the flat vector) of this rank: grid-stride, so the same
 // kernel runs wide on the main stream or with a handful of CTAs on the side stream beside the 128-CTA LSTM backward.
 __global__ void __launch_bounds__(256)
@@ -83,6 +78,11 @@ dp_fused_rmsprop_kernel(DpPeers p, float* __restrict__ rms, unsigned int* my_fla
                         float clampv, float gscale, unsigned long long timeout_ns) {
   unsigned int* ready = my_flags + 32 * block;
   unsigned int* done = ready + 16;
+  // "my gradients of this range are final": everything earlier on this stream -- the backward kernels -- has completed
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + 32 * block + rank, 2 * step + 1);
+  }
   if ((int)threadIdx.x < world) spin_until(ready + threadIdx.x, 2 * step + 1, timeout_ns, my_flags + DP_ERR);
   __syncthreads();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -173,8 +173,7 @@ extern "C" int nvqa_dp_connect(nvqa_model* m, int32_t rank, int32_t world, const
     m->dp_peer_params[r] = static_cast<float*>(px);
     m->dp_peer_flags[r] = static_cast<unsigned int*>(pf);
   }
-  if (!m->dp_stream) {
-    NVQA_CUDA(cudaStreamCreateWithFlags(&m->dp_stream, cudaStreamNonBlocking));
+  if (!m->dp_fork) {
     NVQA_CUDA(cudaEventCreateWithFlags(&m->dp_fork, cudaEventDisableTiming));
     NVQA_CUDA(cudaEventCreateWithFlags(&m->dp_join, cudaEventDisableTiming));
   }
@@ -186,7 +185,7 @@ extern "C" int nvqa_dp_connect(nvqa_model* m, int32_t rank, int32_t world, const
 extern "C" int nvqa_dp_disconnect(nvqa_model* m) {
   NVQA_CHECK(m, "null model");
   if (m->dp_world) NVQA_CUDA(cudaSetDevice(m->cfg.device));
-  if (m->dp_stream) NVQA_CUDA(cudaStreamSynchronize(m->dp_stream));
+  if (m->aux_stream) NVQA_CUDA(cudaStreamSynchronize(m->aux_stream));
   for (void* p : m->dp_opened) cudaIpcCloseMemHandle(p);
   m->dp_opened.clear();
   m->dp_world = 0;
@@ -216,31 +215,45 @@ static unsigned long long dp_timeout_ns() {
   return ns;
 }
 
-// One parameter block: signal "my gradients of this block are final", then the fused reduce-scatter + update + all-gather
-// kernel over this rank's shard of the block.  side = true: on the side stream with few CTAs (beside the LSTM backward).
-static int dp_block(nvqa_model* m, int block, float lr, float alpha, float eps, float wd, float clamp, bool side) {
+// One exchange = a contiguous range of parameter blocks [blk0, blk1] of the flat vector with one gradient scale (channel =
+// blk0 selects the flag words): the fused reduce-scatter + update + all-gather kernel over this rank's 1/N of the range.
+// side = true: on the side stream with few CTAs (beside the LSTM backward); the unused dynamic shared memory keeps these
+// CTAs off the SMs of the persistent LSTM kernel (which owns all of its SM's shared memory), i.e. on the idle ones.
+static int dp_range(nvqa_model* m, int blk0, int blk1, float lr, float alpha, float eps, float wd, float clamp, bool side) {
   DpPeers p;
   memset(&p, 0, sizeof(p));
   for (int r = 0; r < m->dp_world; ++r) { p.g[r] = m->dp_peer_grads[r]; p.x[r] = m->dp_peer_params[r]; p.flags[r] = m->dp_peer_flags[r]; }
-  const long long b0 = m->off_blk[block] / 4, b1 = m->off_blk[block + 1] / 4;            // block offsets are multiples of 4
+  const long long b0 = m->off_blk[blk0] / 4, b1 = m->off_blk[blk1 + 1] / 4;              // block offsets are multiples of 4
   const long long per = (b1 - b0 + m->dp_world - 1) / m->dp_world;
   const long long lo4 = std::min(b1, b0 + per * m->dp_rank), hi4 = std::min(b1, lo4 + per);
   const long long n4 = hi4 - lo4;
-  const unsigned int step = m->dp_steps[block]++;
+  const unsigned int step = m->dp_steps[blk0]++;
   // -lr_scale of the arch 1 trainer variants multiplies the encoder and embedding gradients before the clamp
   // (003_train_ae_based_wp.lua:344-346), exactly as nvqa_rmsprop_step does
   float gscale = 1.0f / (float)m->dp_world;
-  if (m->cfg.arch == 1 && block != NVQA_BLOCK_MULTIMODAL) gscale *= m->lr_scale;
-  cudaStream_t s = side ? m->dp_stream : m->stream;
-  dp_signal_ready_kernel<<<1, 32, 0, s>>>(p, m->dp_rank, m->dp_world, block, 2 * step + 1);
-  NVQA_LAUNCHED();
+  if (m->cfg.arch == 1 && blk1 < NVQA_BLOCK_MULTIMODAL) gscale *= m->lr_scale;
+  cudaStream_t s = side ? m->aux_stream : m->stream;
   static int side_ctas = -1;
   if (side_ctas < 0) { const char* e = getenv("NVQA_DP_SIDE_CTAS"); side_ctas = e ? std::max(1, atoi(e)) : 16; }
   const int full = std::max(1, std::min(ceil_div(n4, 256), 148 * 8));
   const int grid = side ? std::min(full, side_ctas) : full;
-  dp_fused_rmsprop_kernel<<<grid, 256, 0, s>>>(p, m->rms, m->dp_flags, block, m->dp_rank, m->dp_world, lo4, n4, step, lr, alpha,
-                                              (float)(1.0 - (double)alpha), eps, wd, clamp, gscale, dp_timeout_ns());
+  const size_t smem = side ? 64 * 1024 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NVQA_CUDA(cudaFuncSetAttribute(dp_fused_rmsprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  dp_fused_rmsprop_kernel<<<grid, 256, smem, s>>>(p, m->rms, m->dp_flags, blk0, m->dp_rank, m->dp_world, lo4, n4, step, lr, alpha,
+                                                 (float)(1.0 - (double)alpha), eps, wd, clamp, gscale, dp_timeout_ns());
   NVQA_LAUNCHED();
+  return 0;
+}
+// the exchanges of one step: arch 1 = {encoder + embedding (one range, one lr_scale), multimodal}; other architectures:
+// the whole flat vector at once
+static int dp_tail_ranges(nvqa_model* m, float lr, float alpha, float eps, float wd, float clamp, bool with_multimodal) {
+  if (m->cfg.arch != 1) return dp_range(m, 0, 2, lr, alpha, eps, wd, clamp, false);
+  NVQA_TRY(dp_range(m, NVQA_BLOCK_ENCODER, NVQA_BLOCK_EMBEDDING, lr, alpha, eps, wd, clamp, false));
+  if (with_multimodal) NVQA_TRY(dp_range(m, NVQA_BLOCK_MULTIMODAL, NVQA_BLOCK_MULTIMODAL, lr, alpha, eps, wd, clamp, false));
   return 0;
 }
 
@@ -262,11 +275,11 @@ extern "C" int nvqa_dp_rmsprop_step(nvqa_model* m, float lr, float alpha, float 
     NVQA_CUDA(cudaEventCreate(&e0)); NVQA_CUDA(cudaEventCreate(&e1));
     NVQA_CUDA(cudaEventRecord(e0, m->stream));
   }
-  for (int k = 0; k < 3; ++k) NVQA_TRY(dp_block(m, k, lr, alpha, eps, wd, clamp, false));
+  NVQA_TRY(dp_tail_ranges(m, lr, alpha, eps, wd, clamp, true));
   if (m->profiling) {
     NVQA_CUDA(cudaEventRecord(e1, m->stream));
     m->prof[CAT_OPT].pending.emplace_back(e0, e1);
-    m->prof[CAT_OPT].launches += 6;
+    m->prof[CAT_OPT].launches += m->cfg.arch == 1 ? 2 : 1;
   }
   return 0;
 }
@@ -286,15 +299,19 @@ extern "C" int nvqa_dp_train_step(nvqa_model* m, float lr, uint64_t seed, float 
     NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
     return nvqa_dp_rmsprop_step(m, lr, alpha, eps, wd, clamp);
   }
-  NVQA_TRY(nvqa_backward(m, NVQA_PHASE_HEAD));
-  NVQA_CUDA(cudaEventRecord(m->dp_fork, m->stream));
-  NVQA_CUDA(cudaStreamWaitEvent(m->dp_stream, m->dp_fork, 0));
-  NVQA_TRY(dp_block(m, NVQA_BLOCK_MULTIMODAL, lr, alpha, eps, wd, clamp, true));
-  NVQA_CUDA(cudaEventRecord(m->dp_join, m->dp_stream));
+  // head backward; its two AxB weight-gradient GEMMs are deferred to the side stream (model.cu: aux_launch_bwd), so the
+  // multimodal gradient becomes final ON THE SIDE STREAM and its exchange is enqueued there, behind them; both run beside
+  // the persistent LSTM backward of the main stream
+  m->defer_head = true;
+  const int rc_head = nvqa_backward(m, NVQA_PHASE_HEAD);
+  m->defer_head = false;
+  NVQA_TRY(rc_head);
+  NVQA_TRY(aux_launch_bwd(m, true));
+  NVQA_TRY(dp_range(m, NVQA_BLOCK_MULTIMODAL, NVQA_BLOCK_MULTIMODAL, lr, alpha, eps, wd, clamp, true));
+  NVQA_CUDA(cudaEventRecord(m->dp_join, m->aux_stream));
   NVQA_TRY(nvqa_backward(m, NVQA_PHASE_LSTM));
   NVQA_TRY(nvqa_backward(m, NVQA_PHASE_EMBED));
-  NVQA_TRY(dp_block(m, NVQA_BLOCK_ENCODER, lr, alpha, eps, wd, clamp, false));
-  NVQA_TRY(dp_block(m, NVQA_BLOCK_EMBEDDING, lr, alpha, eps, wd, clamp, false));
+  NVQA_TRY(dp_tail_ranges(m, lr, alpha, eps, wd, clamp, false));
   NVQA_CUDA(cudaStreamWaitEvent(m->stream, m->dp_join, 0));      // the next forward reads the multimodal weights
   umma_workspace_invalidate(m->ws);
   return 0;

@@ -173,7 +173,7 @@ extern "C" int nvqa_model_destroy(nvqa_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->cfg.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
-  if (m->dp_stream) cudaStreamSynchronize(m->dp_stream);
+  if (m->aux_stream) cudaStreamSynchronize(m->aux_stream);
   for (void* p : m->dp_opened) cudaIpcCloseMemHandle(p);
   for (void* p : m->allocs) cudaFree(p);
   if (m->loss_host) cudaFreeHost(m->loss_host);
@@ -183,7 +183,9 @@ extern "C" int nvqa_model_destroy(nvqa_model* m) {
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->fc7_ready) cudaEventDestroy(m->fc7_ready);
   if (m->fc7_consumed) cudaEventDestroy(m->fc7_consumed);
-  if (m->dp_stream) cudaStreamDestroy(m->dp_stream);
+  if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
+  if (m->aux_fork) cudaEventDestroy(m->aux_fork);
+  if (m->aux_join) cudaEventDestroy(m->aux_join);
   if (m->dp_fork) cudaEventDestroy(m->dp_fork);
   if (m->dp_join) cudaEventDestroy(m->dp_join);
   delete m;
@@ -211,6 +213,10 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
   NVQA_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  NVQA_CUDA(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+  NVQA_CUDA(cudaEventCreateWithFlags(&m->aux_fork, cudaEventDisableTiming));
+  NVQA_CUDA(cudaEventCreateWithFlags(&m->aux_join, cudaEventDisableTiming));
+  { const char* e = getenv("NVQA_AUX_STREAM"); m->aux_enabled = e ? atoi(e) : 1; }
   NVQA_CUDA(cudaEventCreateWithFlags(&m->fc7_ready, cudaEventDisableTiming));
   NVQA_CUDA(cudaEventCreateWithFlags(&m->fc7_consumed, cudaEventDisableTiming));
   const int S = (a2 && !a3) ? H : 2 * L * H;
@@ -423,7 +429,7 @@ extern "C" int nvqa_sync(nvqa_model* m) {
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
   if (m->copy_stream) NVQA_CUDA(cudaStreamSynchronize(m->copy_stream));   // an fc7 copy of nvqa_set_batch_host may be in flight
-  if (m->dp_stream) NVQA_CUDA(cudaStreamSynchronize(m->dp_stream));
+  if (m->aux_stream) NVQA_CUDA(cudaStreamSynchronize(m->aux_stream));
   if (m->dp_world > 0) {
     int32_t bad = 0;
     NVQA_TRY(nvqa_dp_status(m, &bad));
@@ -573,6 +579,60 @@ static int join_fc7_copy(nvqa_model* m) {
   return 0;
 }
 
+// ---- side stream (see model.cuh) ---------------------------------------------------------------------------------
+// Routes everything enqueued through m->stream to the side stream for the lifetime of the object; GEMMs then take their
+// transients from the side arena of the workspace and run with a capped persistent grid.
+struct AuxScope {
+  nvqa_model* m; cudaStream_t saved; bool on;
+  AuxScope(nvqa_model* m_, bool on_) : m(m_), saved(m_->stream), on(on_) {
+    if (!on) return;
+    m->stream = m->aux_stream;
+    if (m->ws) {
+      static int cap = -1;
+      if (cap < 0) { const char* e = getenv("NVQA_AUX_CTAS"); cap = e ? atoi(e) : 20; }
+      m->ws->side = true; m->ws->cta_cap = cap;
+    }
+  }
+  ~AuxScope() {
+    if (!on) return;
+    m->stream = saved;
+    if (m->ws) { m->ws->side = false; m->ws->cta_cap = 0; }
+  }
+};
+static bool aux_usable(const nvqa_model* m) { return m->aux_enabled && !m->profiling && m->cfg.arch == 1 && m->planes > 0; }
+
+// forward image branch of arch 1: fc7 L2 norm + AxB's Dropout on i + Linear(I, C) -> ic (pre-tanh).  to_side: called from
+// the hook in front of the first recurrent kernel; otherwise (no persistent kernel ran) inline on the main stream.
+static int aux_launch_fwd(nvqa_model* m, bool to_side) {
+  if (!m->aux_fwd) return 0;
+  m->aux_fwd = false;
+  const nvqa_config& c = m->cfg;
+  const bool side = to_side && aux_usable(m);
+  if (side) {
+    NVQA_CUDA(cudaEventRecord(m->aux_fork, m->stream));
+    NVQA_CUDA(cudaStreamWaitEvent(m->aux_stream, m->aux_fork, 0));
+  }
+  {
+    AuxScope as(m, side);
+    {
+      ProfScope ps(m, CAT_PW_FWD, 0);
+      NVQA_TRY(join_fc7_copy(m));
+      NVQA_TRY(imgnorm_drop(m->stream, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), m->B, c.I, c.img_norm, m->norm_split));
+      NVQA_CUDA(cudaEventRecord(m->fc7_consumed, m->stream));
+    }
+    NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, m->B, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
+    if (side) NVQA_CUDA(cudaEventRecord(m->aux_join, m->stream));
+  }
+  m->aux_fwd_inflight = side;
+  return 0;
+}
+// the main stream waits for side-stream work in flight (forward image branch or backward weight gradients)
+static int aux_join_main(nvqa_model* m) {
+  if (m->aux_fwd_inflight || m->aux_bwd_inflight) NVQA_CUDA(cudaStreamWaitEvent(m->stream, m->aux_join, 0));
+  m->aux_fwd_inflight = m->aux_bwd_inflight = false;
+  return 0;
+}
+
 static Drop lstm_drop(const nvqa_model* m, int l /* between layer l and l+1 */) {
   const int64_t per = (int64_t)(m->cfg.arch == 2 ? m->steps : m->cfg.T) * m->B * m->cfg.H;
   return make_drop(m, m->mk_lstm ? m->mk_lstm + per * l : nullptr, STREAM_LSTM0 + l);
@@ -608,6 +668,7 @@ static int lstm_layers_forward(nvqa_model* m, const LstmSeg& sg, const int32_t* 
     NVQA_TRY(gemm(m, CAT_INPROJ, true, true, T * B, 4 * H, in, X, in, sg.w[l].Wi, in, pre, 4 * H, false, sg.w[l].bi,
                   sg.w[l].bh));
     if (m->planes && m->use_persistent) {
+      if (l == 0) NVQA_TRY(aux_launch_fwd(m, true));     // the image branch runs beside the recurrent kernels
       // K4: all T steps in one persistent cooperative kernel (W_hh slice resident in shared memory)
       ProfScope ps(m, CAT_REC_FWD, 2.0 * (T - (sg.has_init ? 0 : 1)) * B * 4.0 * H * H);
       int rc = lstm_fwd_persistent_v2(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
@@ -769,6 +830,7 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(embed_fwd(s, m->q, m->len, m->WeT, m->be, m->y, make_drop(m, m->mk_emb, STREAM_EMB), B, T, E, c.V));
   }
+  m->aux_fwd = true;                        // the image branch is due: see aux_launch_fwd
   // rnn_forward (:303), layer-major
   NVQA_TRY(lstm_layers_forward(m, T, m->len));
   // tv_q (:306) and multimodal_net:forward (:307)
@@ -778,12 +840,12 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L));
-    NVQA_TRY(join_fc7_copy(m));
-    NVQA_TRY(imgnorm_drop(s, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), B, c.I, c.img_norm, m->norm_split));
-    NVQA_CUDA(cudaEventRecord(m->fc7_consumed, s));
   }
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
-  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
+  // the image branch (fc7 norm + Dropout + Linear(I, C)) was launched on the side stream beside the recurrent kernels
+  // (aux_launch_fwd, hooked in lstm_layers_forward), or runs here if no persistent kernel did
+  NVQA_TRY(aux_launch_fwd(m, false));
+  NVQA_TRY(aux_join_main(m));
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C, m->fusion_skip));
@@ -879,6 +941,7 @@ static int backward_embed_arch3(nvqa_model* m) {
                       m->B, c.T, c.E, c.V, m->steps);
 }
 
+int aux_launch_bwd(nvqa_model* m, bool to_side);
 static int backward_head(nvqa_model* m) {
   if (m->cfg.arch == 3) return backward_head_arch3(m);
   if (m->cfg.arch == 2) return backward_head_arch2(m);
@@ -896,13 +959,49 @@ static int backward_head(nvqa_model* m) {
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, C, O, m->dscores, O, m->Wc, C, m->dzd, C, false));
   // Dropout, CMulTable, Tanh backward
   NVQA_TRY(fuse_bwd(s, m->dzd, m->qc, m->ic, m->dqpre, m->dipre, make_drop(m, m->mk_z, STREAM_HEAD), B, C, m->fusion_skip));
-  // AxB Linear backward (no d fc7)
-  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, S, B, m->dqpre, C, m->qd, S, m->gWq, S, false));
-  NVQA_TRY(colsum(s, m->dqpre, B, C, C, m->gbq, nullptr));
-  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, I, B, m->dipre, C, m->vd, I, m->gWv, I, false));
-  NVQA_TRY(colsum(s, m->dipre, B, C, C, m->gbv, nullptr));
+  // AxB Linear backward (no d fc7): the input gradient the LSTM backward waits for first ...
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, S, C, m->dqpre, C, m->Wq, S, m->dqd, S, false));
   NVQA_TRY(mask_inplace(s, m->dqd, make_drop(m, m->mk_q, STREAM_AXB_Q), (int64_t)B * S));
+  // ... the two weight gradients nobody waits for are due (aux_launch_bwd): beside the recurrent kernels on the side stream
+  // when the LSTM phase follows in the same call (nvqa_backward(ALL), nvqa_dp_train_step), else right here
+  m->aux_bwd = true;
+  (void)I;
+  if (!m->defer_head) NVQA_TRY(aux_launch_bwd(m, false));
+  return 0;
+}
+
+// weight gradients of the two AxB Linears (misc/netdef.lua:10-11): dWq = dqpre^T qd, dWi = dipre^T vd, bias gradients
+int aux_launch_bwd(nvqa_model* m, bool to_side) {
+  const bool side = to_side && aux_usable(m) && m->cfg.arch == 1;
+  if (!m->aux_bwd) {
+    // nothing deferred: a caller that is about to enqueue on the side stream still needs it ordered behind the main stream
+    if (to_side && m->aux_stream) {
+      NVQA_CUDA(cudaEventRecord(m->aux_fork, m->stream));
+      NVQA_CUDA(cudaStreamWaitEvent(m->aux_stream, m->aux_fork, 0));
+    }
+    return 0;
+  }
+  m->aux_bwd = false;
+  const nvqa_config& c = m->cfg;
+  const int B = m->B, S = m->S, C = c.C, I = c.I;
+  if (side || to_side) {
+    NVQA_CUDA(cudaEventRecord(m->aux_fork, m->stream));
+    NVQA_CUDA(cudaStreamWaitEvent(m->aux_stream, m->aux_fork, 0));
+  }
+  {
+    AuxScope as(m, side);
+    NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, S, B, m->dqpre, C, m->qd, S, m->gWq, S, false));
+    NVQA_TRY(colsum(m->stream, m->dqpre, B, C, C, m->gbq, nullptr));
+    NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, I, B, m->dipre, C, m->vd, I, m->gWv, I, false));
+    NVQA_TRY(colsum(m->stream, m->dipre, B, C, C, m->gbv, nullptr));
+    if (side) NVQA_CUDA(cudaEventRecord(m->aux_join, m->stream));
+  }
+  m->aux_bwd_inflight = side;
+  if (!side && to_side) {
+    // ran inline on the main stream although the caller continues on the side stream: order the side stream behind it
+    NVQA_CUDA(cudaEventRecord(m->aux_fork, m->stream));
+    NVQA_CUDA(cudaStreamWaitEvent(m->aux_stream, m->aux_fork, 0));
+  }
   return 0;
 }
 
@@ -1002,7 +1101,9 @@ static int backward_lstm(nvqa_model* m) {
   }
   // arch1: d tv_q = d[c1 h1 c2 h2 ...] (002_train_baseline.lua:306,313)
   for (int l = 0; l < L; ++l) { dh0[l] = m->dqd + (2 * l + 1) * H; dc0[l] = m->dqd + (2 * l) * H; }
-  return lstm_layers_backward(m, m->cfg.T, m->len, dh0, dc0, m->S);
+  NVQA_TRY(aux_launch_bwd(m, m->planes && m->use_persistent));      // the AxB weight gradients run beside the recurrent kernels
+  NVQA_TRY(lstm_layers_backward(m, m->cfg.T, m->len, dh0, dc0, m->S));
+  return aux_join_main(m);
 }
 
 static int backward_embed(nvqa_model* m) {
@@ -1024,7 +1125,14 @@ extern "C" int nvqa_backward(nvqa_model* m, int phase) {
     m->logp_valid = false;
   }
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
-  if (phase == NVQA_PHASE_HEAD || phase == NVQA_PHASE_ALL) NVQA_TRY(backward_head(m));
+  // a head-only call (NCCL bucket overlap, callers reading the gradients between phases) must leave the multimodal block
+  // final: the AxB weight gradients are deferred to the side stream only when the LSTM phase follows in this very call
+  const bool defer_saved = m->defer_head;
+  if (phase == NVQA_PHASE_ALL) m->defer_head = true;
+  int rc = 0;
+  if (phase == NVQA_PHASE_HEAD || phase == NVQA_PHASE_ALL) rc = backward_head(m);
+  m->defer_head = defer_saved;
+  NVQA_TRY(rc);
   if (phase == NVQA_PHASE_LSTM || phase == NVQA_PHASE_ALL) NVQA_TRY(backward_lstm(m));
   if (phase == NVQA_PHASE_EMBED || phase == NVQA_PHASE_ALL) NVQA_TRY(backward_embed(m));
   NVQA_CHECK(phase >= 0 && phase <= 3, "bad phase");

@@ -109,10 +109,22 @@ struct nvqa_model {
   unsigned int* dp_flags = nullptr;  // flag page written by the peers (layout: dp_fused.cu)
   unsigned int* dp_peer_flags[16] = {};
   unsigned int dp_steps[3] = {0, 0, 0};   // exchanges done so far, per parameter block
-  cudaStream_t dp_stream = nullptr;  // side stream of the early (multimodal) block exchange
   cudaEvent_t dp_fork = nullptr, dp_join = nullptr;
+  // Side stream: work that does not depend on the LSTM runs beside the 128-CTA persistent recurrent kernels, on the ~20 SMs
+  // they leave free -- forward: fc7 norm + Dropout + the image Linear of AxB; backward: the weight gradients of the two AxB
+  // Linears; data parallel: the exchange of the multimodal block (dp_fused.cu).  aux_fwd / aux_bwd: that work is due and
+  // is launched by the hook in front of the first recurrent kernel (or inline on the main stream if none follows).
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  bool aux_fwd = false, aux_bwd = false, aux_fwd_inflight = false, aux_bwd_inflight = false;
+  int aux_enabled = -1;              // NVQA_AUX_STREAM (default 1); 0: everything on the main stream
+  bool defer_head = false;           // the head backward may leave the AxB weight gradients to the side stream
   std::vector<void*> dp_opened;      // cudaIpcOpenMemHandle mappings to close
   bool profiling = false;
   ProfCat prof[CAT_COUNT];
 };
 
+
+// Side-stream plumbing (model.cu).  aux_launch_bwd: enqueue the deferred AxB weight-gradient GEMMs of the head backward on
+// the side stream (force_stream: even if nothing is pending, make the side stream wait for the main stream's work so far).
+int aux_launch_bwd(nvqa_model* m, bool force_stream);

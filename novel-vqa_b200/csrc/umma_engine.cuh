@@ -46,7 +46,16 @@ struct UmmaWorkspace {
   size_t static_top = 0;
   size_t act_bytes = 0;         // [static_bytes, static_bytes + act_bytes): planes of this forward's activations, so
   size_t act_top = 0;           // that the backward GEMMs (wgrad operands) reuse them instead of splitting again
-  size_t trans_top = 0;         // transient planes live in [static_bytes + act_bytes, bytes), reset per GEMM
+  size_t trans_top = 0;         // transient planes live in [static_bytes + act_bytes, bytes - side_bytes), reset per GEMM
+  // GEMMs enqueued on a SECOND stream (the image branch beside the persistent LSTM kernels, model.cu) must not share the
+  // transient arena with the main stream's GEMMs: while `side` is set, transients come from [bytes - side_bytes, bytes)
+  // and the persistent grid is capped at cta_cap CTAs (the SMs the 128-CTA recurrent kernel leaves free)
+  size_t side_bytes = 0, side_top = 0;
+  bool side = false;
+  int cta_cap = 0;
+  size_t& ttop() { return side ? side_top : trans_top; }
+  size_t tbase() const { return side ? bytes - side_bytes : static_bytes + act_bytes; }
+  size_t tlimit() const { return side ? bytes : bytes - side_bytes; }
   std::unordered_map<PlaneKey, __nv_bfloat16*, PlaneKeyHash> cache;
   std::unordered_map<PlaneKey, __nv_bfloat16*, PlaneKeyHash> act_cache;
   std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;

@@ -337,7 +337,8 @@ int umma_workspace_create(UmmaWorkspace** out, size_t transient_bytes, size_t st
   UmmaWorkspace* ws = new UmmaWorkspace();
   ws->static_bytes = (static_bytes + 1023) & ~(size_t)1023;
   ws->act_bytes = (act_bytes + 1023) & ~(size_t)1023;
-  ws->bytes = ws->static_bytes + ws->act_bytes + transient_bytes;
+  ws->side_bytes = transient_bytes ? (size_t)48 << 20 : 0;           // split-K partials of the head GEMMs: <= 8 x 500 x 1024 x 4 B
+  ws->bytes = ws->static_bytes + ws->act_bytes + transient_bytes + ws->side_bytes;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws->base), ws->bytes);
   if (e != cudaSuccess) {
     set_error(std::string("umma workspace cudaMalloc: ") + cudaGetErrorString(e));
@@ -380,7 +381,7 @@ int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, i
     if (it != ws->act_cache.end()) { *out = it->second; return 0; }
   }
   const size_t need = ((size_t)P * rows * Kp * 2 + 1023) & ~(size_t)1023;
-  const size_t trans0 = ws->static_bytes + ws->act_bytes;
+  const size_t trans0 = ws->tbase();
   __nv_bfloat16* dst;
   if (is_static == 1 && ws->static_top + need <= ws->static_bytes) {
     dst = reinterpret_cast<__nv_bfloat16*>(ws->base + ws->static_top);
@@ -391,9 +392,9 @@ int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, i
     ws->act_top += need;
     ws->act_cache[key] = dst;
   } else {
-    NVQA_CHECK(trans0 + ws->trans_top + need <= ws->bytes, "umma workspace too small");
-    dst = reinterpret_cast<__nv_bfloat16*>(ws->base + trans0 + ws->trans_top);
-    ws->trans_top += need;
+    NVQA_CHECK(trans0 + ws->ttop() + need <= ws->tlimit(), "umma workspace too small");
+    dst = reinterpret_cast<__nv_bfloat16*>(ws->base + trans0 + ws->ttop());
+    ws->ttop() += need;
   }
   int64_t n = (int64_t)rows * (Kp / 4);
   if (P == 1) split_planes_kernel<1><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
@@ -487,7 +488,7 @@ int get_map_kb(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp,
 }
 
 struct UgLaunch {
-  int a_row0 = 0, b_row0 = 0, splits = 1, kb_per_split = 1 << 30;
+  int a_row0 = 0, b_row0 = 0, splits = 1, kb_per_split = 1 << 30, cta_cap = 0;
   long long c_split_stride = 0;
 };
 
@@ -511,7 +512,7 @@ static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap&
   const int tn = ceil_div(N, BN), tm = ceil_div(M, UG_BM);
   const long long total = (long long)tn * tm * L.splits;
   NVQA_CHECK(total < (1ll << 31), "umma_gemm: too many tiles");
-  dim3 grid((unsigned)(persist ? std::min<long long>(total, num_sms) : total));
+  dim3 grid((unsigned)(persist ? std::min<long long>(total, L.cta_cap > 0 ? std::min(L.cta_cap, num_sms) : num_sms) : total));
   umma_gemm_kernel<BN, P, AMN, BMN><<<grid, UG_THREADS, Cfg::SMEM, s>>>(ma, mb, M, N, K, C, ldc, beta ? 1 : 0, b0, b1,
                                                                         L.a_row0, L.b_row0, L.kb_per_split,
                                                                         L.c_split_stride, tn, tm, L.splits);
@@ -565,7 +566,7 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
   NVQA_CHECK(ws, "umma_gemm: no workspace");
   NVQA_CHECK(planes >= 1 && planes <= 3, "umma_gemm: planes must be 1..3");
   if (M <= 0 || N <= 0) return 0;
-  ws->trans_top = 0;                      // stream order makes the previous GEMM's transient planes reusable
+  ws->ttop() = 0;                         // stream order makes the previous GEMM's transient planes reusable
   // planes keep the source's row-major shape: [M x K] / [N x K] when K-major, [K x M] / [K x N] when MN-major
   const __nv_bfloat16 *pa = nullptr, *pb = nullptr;
   int pitch_a = 0, pitch_b = 0, bound_a = 0, bound_b = 0;
@@ -574,7 +575,9 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
   NVQA_TRY(resolve_operand(ws, s, planes, A, A.kmajor ? M : K, A.kmajor ? K : M, &pa, &pitch_a, &ps_a, &L.a_row0, &bound_a));
   NVQA_TRY(resolve_operand(ws, s, planes, B, B.kmajor ? N : K, B.kmajor ? K : N, &pb, &pitch_b, &ps_b, &L.b_row0, &bound_b));
   // tile shape: the widest N tile that still gives every SM a CTA; split K when the grid would be too small
-  int num_sms = 148;
+  // (a side-stream GEMM owns only cta_cap SMs: shaped as for a machine of that size)
+  int num_sms = ws->side && ws->cta_cap > 0 ? ws->cta_cap : 148;
+  L.cta_cap = ws->side ? ws->cta_cap : 0;
   const int mt = ceil_div(M, UG_BM);
   int BN = 64;
   if (planes <= 2 && N >= 256 && (long)mt * ceil_div(N, 256) >= num_sms / 2) BN = 256;
@@ -599,9 +602,9 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
     splits = ceil_div(nkb, L.kb_per_split);                       // no empty split
     L.splits = splits;
     const size_t need = (size_t)splits * M * N * sizeof(float);
-    NVQA_CHECK(ws->static_bytes + ws->act_bytes + ws->trans_top + need <= ws->bytes, "umma workspace too small for split-K partials");
-    Cout = reinterpret_cast<float*>(ws->base + ws->static_bytes + ws->act_bytes + ws->trans_top);
-    ws->trans_top += (need + 1023) & ~(size_t)1023;
+    NVQA_CHECK(ws->tbase() + ws->ttop() + need <= ws->tlimit(), "umma workspace too small for split-K partials");
+    Cout = reinterpret_cast<float*>(ws->base + ws->tbase() + ws->ttop());
+    ws->ttop() += (need + 1023) & ~(size_t)1023;
     ldo = N;
     L.c_split_stride = (long long)M * N;
     beta_k = false; b0k = b1k = nullptr;

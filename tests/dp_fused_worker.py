@@ -59,6 +59,39 @@ def main():
             ok = False
             print(f"rank {rank} step {step}: replicas diverged {digs}", flush=True)
         # RMSprop state is sharded: this rank owns [lo, hi) of the flat vector; check its own shard
+    # N ranks x B rows against the SINGLE-PROCESS oracle at the global batch N*B.  Dropout masks are
+    # drawn per (local row, local batch size), so this check runs with p = 0 (every other site is covered by the
+    # single-GPU parity tests): mean over the global batch = (1/N) sum over ranks of the per-rank means.
+    if not full:
+        import dataclasses
+        cfg0 = dataclasses.replace(cfg, dropout=0.0)
+        oc = A.Arch1Config(V=cfg.V, E=cfg.E, H=cfg.H, L=cfg.L, I=cfg.I, C=cfg.C, O=cfg.O, T=cfg.T, p=0.0)
+        m0 = nv.Arch1Model(cfg0, precision=nv.PREC_BF16X2, device=local)
+        w0 = list(nv.synth_params(cfg, seed=2))
+        for blk, w in zip(blocks, w0):
+            m0.set_params(blk, w)
+        dp.connect_fused(m0, dist, rank, world)
+        shard = nv.synth_batch(cfg, B, seed=900 + rank, min_len=1)
+        m0.set_batch_host(*shard)
+        dp.fused_train_step(m0, lr, seed=1)
+        m0.sync()
+        shards = [None] * world
+        dist.all_gather_object(shards, shard)
+        gq, gl, gf, gy = (np.concatenate([sh[k] for sh in shards]) for k in range(4))
+        f_ref, g_ref, _, _ = A.jdj(oc, w0[0], w0[1], w0[2], gq, gl, A.l2_normalize_rows(gf), gy, seed=None)
+        for k, blk in enumerate(blocks):
+            want = w0[k].copy()
+            A.rmsprop_update(want, g_ref[k], np.zeros_like(want), lr)
+            got = m0.get_params(blk)
+            big = np.abs(g_ref[k]) > 1e-5       # lr * g / (0.1 |g| + eps) is ill-conditioned where |g| ~ eps
+            du, dw = (got - w0[k])[big].astype(np.float64), (want - w0[k])[big].astype(np.float64)
+            rel = np.linalg.norm(du - dw) / np.linalg.norm(dw)
+            if not rel < 5e-3:
+                ok = False
+                print(f"rank {rank} global-batch oracle check, block {blk}: update rel-l2 {rel:.3e}", flush=True)
+            elif rank == 0:
+                print(f"global batch {world}x{B} vs single-process oracle, block {blk}: update rel-l2 {rel:.2e}", flush=True)
+        m0.close()
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
