@@ -589,7 +589,7 @@ struct AuxScope {
     m->stream = m->aux_stream;
     if (m->ws) {
       static int cap = -1;
-      if (cap < 0) { const char* e = getenv("NVQA_AUX_CTAS"); cap = e ? atoi(e) : 20; }
+      if (cap < 0) { const char* e = getenv("NVQA_AUX_CTAS"); cap = e ? atoi(e) : 16; }   // B200 sweep: 8..18 equal (1.734 ms), 20 collides with the 4-CTA clusters (1.772), 6 too few (1.785)
       m->ws->side = true; m->ws->cta_cap = cap;
     }
   }

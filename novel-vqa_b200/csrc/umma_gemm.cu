@@ -41,9 +41,11 @@ struct UgCfg {
   static constexpr int A_PLANE = UG_BM * UG_BK * 2;           // 16 KB
   static constexpr int B_PLANE = BN * UG_BK * 2;
   static constexpr int STAGE = P * (A_PLANE + B_PLANE);
-  static constexpr int MAX_STAGES = (227 * 1024 - 4096) / STAGE;
+  static constexpr int EPI_PITCH = 36;                        // floats per row of an epilogue staging chunk (32 + 4: conflict-free)
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;    // one [32 rows x 32 columns] chunk per epilogue warp
+  static constexpr int MAX_STAGES = (227 * 1024 - 4096 - EPI_BYTES) / STAGE;
   static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * 1024 /*two bias tiles*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * 1024 /*two bias tiles*/ + EPI_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator stages (a power of two >= 32)
   static_assert(STAGES >= 2, "pipeline needs two stages");
 };
@@ -66,6 +68,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const uint32_t tempty = tfull + 16;                                 // accumulator stage a drained (tempty + 8 a)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
   float* bias_all = reinterpret_cast<float*>(gen + Cfg::STAGES * Cfg::STAGE + 256);    // bias0 + bias1 of the tile, per stage
+  float* epi_all = bias_all + 512;                                                      // per-warp staging chunks of the epilogue
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb_all = (K + UG_BK - 1) / UG_BK;
@@ -208,33 +211,44 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(tfull + 8 * as, ((uint32_t)li >> 1) & 1u);
     tc_fence_after();
-    const int row = m0 + q * 32 + lane;
     const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+    // tcgen05.ld hands a lane one ROW x 32 columns; stored like that, a warp instruction would touch 32 different cache
+    // lines with 16 bytes each (measured: the short-K GEMMs of the step were bound by exactly these stores, 5 B/clk/SM).
+    // Each 32 x 32 chunk therefore goes through a per-warp shared-memory tile and leaves as 4 rows x 128 contiguous bytes
+    // per instruction: full lines.
+    float* stg = epi_all + (warp - 2) * 32 * Cfg::EPI_PITCH;
+    const int sr = lane >> 3, sc = (lane & 7) * 4;              // store phase: lane -> (row within a group of 4, 4 columns)
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
+      if (n0 + cc * 32 >= N) break;
       float v[32];
       tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
-      if (row < M) {
-        float* crow = C + (size_t)row * ldc;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int col = n0 + cc * 32 + j;
-          if (col >= N) break;
-          const float4 bb = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j);
-          float r[4] = {v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w};
-          if (vec && col + 3 < N) {
-            if (beta) {
-              float4 o = *reinterpret_cast<const float4*>(crow + col);
-              r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w;
-            }
-            *reinterpret_cast<float4*>(crow + col) = make_float4(r[0], r[1], r[2], r[3]);
-          } else {
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      const int col = n0 + cc * 32 + sc;
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + cc * 32 + sc);
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (col + t < N) crow[col + t] = (beta ? crow[col + t] : 0.f) + r[t];
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + sr, row = m0 + q * 32 + r;
+        if (row >= M || col >= N) continue;
+        const float4 x = *reinterpret_cast<const float4*>(stg + r * Cfg::EPI_PITCH + sc);
+        float o4[4] = {x.x + bb.x, x.y + bb.y, x.z + bb.z, x.w + bb.w};
+        float* cp = C + (size_t)row * ldc + col;
+        if (vec && col + 3 < N) {
+          if (beta) {
+            const float4 o = *reinterpret_cast<const float4*>(cp);
+            o4[0] += o.x; o4[1] += o.y; o4[2] += o.z; o4[3] += o.w;
           }
+          *reinterpret_cast<float4*>(cp) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (col + t < N) cp[t] = (beta ? cp[t] : 0.f) + o4[t];
         }
       }
+      __syncwarp();                              // the chunk is overwritten by the next one
     }
     tc_fence_before();                          // this warp's tcgen05.ld of the stage are complete (wait::ld inside tmem_ld32)
     __syncwarp();
