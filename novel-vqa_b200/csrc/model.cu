@@ -953,9 +953,7 @@ static int backward_head(nvqa_model* m) {
   NVQA_CUDA(cudaMemsetAsync(m->gbc, 0, (size_t)O * 4, s));
   NVQA_CUDA(cudaMemsetAsync(m->gbq, 0, (size_t)C * 4, s));
   NVQA_CUDA(cudaMemsetAsync(m->gbv, 0, (size_t)C * 4, s));
-  // Linear(C,O) backward
-  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, O, C, B, m->dscores, O, m->zd, C, m->gWc, C, false));
-  NVQA_TRY(colsum(s, m->dscores, B, O, O, m->gbc, nullptr));
+  // Linear(C,O) backward: the input gradient first; the weight gradient joins the deferred ones below
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, C, O, m->dscores, O, m->Wc, C, m->dzd, C, false));
   // Dropout, CMulTable, Tanh backward
   NVQA_TRY(fuse_bwd(s, m->dzd, m->qc, m->ic, m->dqpre, m->dipre, make_drop(m, m->mk_z, STREAM_HEAD), B, C, m->fusion_skip));
@@ -970,7 +968,8 @@ static int backward_head(nvqa_model* m) {
   return 0;
 }
 
-// weight gradients of the two AxB Linears (misc/netdef.lua:10-11): dWq = dqpre^T qd, dWi = dipre^T vd, bias gradients
+// weight gradients of the classifier and of the two AxB Linears (002_train_baseline.lua:154, misc/netdef.lua:10-11):
+// dWc = dscores^T zd, dWq = dqpre^T qd, dWi = dipre^T vd, and the bias gradients
 int aux_launch_bwd(nvqa_model* m, bool to_side) {
   const bool side = to_side && aux_usable(m) && m->cfg.arch == 1;
   if (!m->aux_bwd) {
@@ -990,6 +989,8 @@ int aux_launch_bwd(nvqa_model* m, bool to_side) {
   }
   {
     AuxScope as(m, side);
+    NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, c.O, C, B, m->dscores, c.O, m->zd, C, m->gWc, C, false));
+    NVQA_TRY(colsum(m->stream, m->dscores, B, c.O, c.O, m->gbc, nullptr));
     NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, S, B, m->dqpre, C, m->qd, S, m->gWq, S, false));
     NVQA_TRY(colsum(m->stream, m->dqpre, B, C, C, m->gbq, nullptr));
     NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, I, B, m->dipre, C, m->vd, I, m->gWv, I, false));

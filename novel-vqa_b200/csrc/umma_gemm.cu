@@ -900,15 +900,18 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
   // CTA pairs (cta_group::2, 256 x BN tiles) for the wide tiles of two-plane products: NVQA_GEMM_PAIR=0 disables
   static int pair_on = -1;
   if (pair_on < 0) { const char* e = getenv("NVQA_GEMM_PAIR"); pair_on = e ? atoi(e) : 1; }
-  const bool use_pair = pair_on && planes == 2 && BN >= 128 && M > UG_BM;
+  const bool use_pair = pair_on && BN >= 128 && M > UG_BM;
   CUtensorMap ma, mb;
   NVQA_TRY(get_map(ws, pa, bound_a, pitch_a, planes, A.kmajor ? UG_BM : 64, &ma, ps_a));
   NVQA_TRY(get_map(ws, pb, bound_b, pitch_b, planes, B.kmajor ? (use_pair ? BN / 2 : BN) : 64, &mb, ps_b));
   int rc = 1;
+#define NVQA_UGP(BN_, P_) \
+  rc = launch_umma_pair_major<BN_, P_>(!A.kmajor, !B.kmajor, s, ma, mb, M, N, K, Cout, ldo, beta_k, b0k, b1k, L)
   if (use_pair) {
-    if (BN == 256) rc = launch_umma_pair_major<256, 2>(!A.kmajor, !B.kmajor, s, ma, mb, M, N, K, Cout, ldo, beta_k, b0k, b1k, L);
-    else rc = launch_umma_pair_major<128, 2>(!A.kmajor, !B.kmajor, s, ma, mb, M, N, K, Cout, ldo, beta_k, b0k, b1k, L);
+    if (BN == 256) { if (planes == 1) NVQA_UGP(256, 1); else NVQA_UGP(256, 2); }
+    else { if (planes == 1) NVQA_UGP(128, 1); else if (planes == 2) NVQA_UGP(128, 2); else NVQA_UGP(128, 3); }
   } else
+#undef NVQA_UGP
 #define NVQA_UG(BN_, P_) \
   rc = launch_umma_major<BN_, P_>(!A.kmajor, !B.kmajor, s, ma, mb, M, N, K, Cout, ldo, beta_k, b0k, b1k, L)
   if (BN == 256) {
