@@ -19,9 +19,14 @@ int lstm_fwd_persistent(cudaStream_t s, UmmaWorkspace* ws, int P, const float* W
 
 // Second generation (lstm_persistent_v2.cu): W_hh slice resident in shared memory (plane 0) AND tensor memory (plane 1),
 // 128 gate rows per CTA, 64-row h tiles; same contract, returns -1 for shapes it does not cover.
+// xdrop_planes (optional): Dropout(h_t) for the layer above is written as bf16 planes [P][T*B][H] (xdrop_plane_stride
+// elements between planes) INSTEAD of the fp32 xdrop_next (which must still be non-null to request that output at all).
+// lstm_fwd_v2_supported: will this generation take the shape (so that the caller may reserve the planes beforehand)?
+bool lstm_fwd_v2_supported(int P, int H);
 int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
                            __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
-                           int B, int H, unsigned int* counter);
+                           int B, int H, unsigned int* counter, __nv_bfloat16* xdrop_planes = nullptr,
+                           long long xdrop_plane_stride = 0);
 
 int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, const float* gates, const float* c,
                            const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* dasum,

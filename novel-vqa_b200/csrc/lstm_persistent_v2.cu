@@ -150,7 +150,8 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, float* __restrict__ pre, float* __restrict__ c,
                    float* __restrict__ h, __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
                    const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg_arg,
-                   int b0, int bend, const __grid_constant__ CUtensorMap mapH4) {
+                   int b0, int bend, const __grid_constant__ CUtensorMap mapH4, __nv_bfloat16* __restrict__ xdp,
+                   long long xdp_plane) {
   static_assert(!BOX4 || PAIR, "4-D boxes are wired into the pair kernel only");
   static_assert(!POLL1 || NS == 2, "the single-poller barriers are numbered for the sub-tile kernel");
   constexpr int KBB = 4;                                // BOX4: k-blocks per TMA box (a "big stage" = KBB ring stages)
@@ -567,7 +568,24 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           float4 ma = drop_at4(drop, mi), mb = drop_at4(drop, mi + 4);
           xd[0] = hn[0] * ma.x; xd[1] = hn[1] * ma.y; xd[2] = hn[2] * ma.z; xd[3] = hn[3] * ma.w;
           xd[4] = hn[4] * mb.x; xd[5] = hn[5] * mb.y; xd[6] = hn[6] * mb.z; xd[7] = hn[7] * mb.w;
-          ST8(xdrop + rin * H + uo, xd)
+          if (xdp) {
+            // the layer above consumes Dropout(h_t) only as a GEMM operand: written as bf16 planes [P][T*B][H] (the
+            // place reserve_planes registered for `xdrop`) instead of fp32 -- same bytes, no separate split pass
+            __nv_bfloat16 xl[3][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split3(xd[j], xl[0][j], xl[1][j], xl[2][j]);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              uint4 o;
+              o.x = (uint32_t)__bfloat16_as_ushort(xl[p][0]) | ((uint32_t)__bfloat16_as_ushort(xl[p][1]) << 16);
+              o.y = (uint32_t)__bfloat16_as_ushort(xl[p][2]) | ((uint32_t)__bfloat16_as_ushort(xl[p][3]) << 16);
+              o.z = (uint32_t)__bfloat16_as_ushort(xl[p][4]) | ((uint32_t)__bfloat16_as_ushort(xl[p][5]) << 16);
+              o.w = (uint32_t)__bfloat16_as_ushort(xl[p][6]) | ((uint32_t)__bfloat16_as_ushort(xl[p][7]) << 16);
+              *reinterpret_cast<uint4*>(xdp + (size_t)p * xdp_plane + rin * H + uo) = o;
+            }
+          } else {
+            ST8(xdrop + rin * H + uo, xd)
+          }
         }
 #undef ST8
       }
@@ -1413,9 +1431,11 @@ static bool v2_enabled() {
 
 // Same contract as lstm_fwd_persistent (lstm_persistent.cuh).  Returns -1 when the shape is not supported by this
 // generation (the caller then tries generation 1, then the per-step kernels).
+bool lstm_fwd_v2_supported(int P, int H) { return v2_enabled() && P >= 1 && P <= 2 && H == 512; }
+
 int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
                            __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
-                           int B, int H, unsigned int* counter) {
+                           int B, int H, unsigned int* counter, __nv_bfloat16* xdrop_planes, long long xdrop_plane_stride) {
   if (!v2_enabled()) return -1;
   if (P < 1 || P > 2) return -1;
   if (H % 64 != 0 || H != 512) return -1;          // the W slice (plane 0: SMEM, plane 1: 256 TMEM columns) is sized for K = 512
@@ -1469,7 +1489,7 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     dim3 grid(H / 32, ceil_div(bend - b0, 64));
     NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
     void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter, &dbgv,
-                    &b0, &bend, &mapH4};
+                    &b0, &bend, &mapH4, &xdrop_planes, &xdrop_plane_stride};
     if (use_cl && !split && grid.x == 16) {
       // one 16-CTA cluster per batch tile: hardware cluster barrier per step, plain (non-cooperative) launch
       const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true, 1, false, false> : (const void*)lstm_fwd_v2_kernel<1, true, 1, false, false>;

@@ -391,7 +391,7 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
     for (int l = 1; l < L; ++l) reg(m->xdrop[l], (size_t)N * H);
     reg(m->qd, (size_t)B * S); reg(m->vd, (size_t)B * I); reg(m->zd, (size_t)B * C2);
     // written once per step before their GEMMs and read by two of them (weight gradient and input gradient)
-    if (!a2) { reg(m->dscores, (size_t)B * O); reg(m->dqpre, (size_t)B * C2); }
+    if (!a2) { reg(m->dscores, (size_t)B * O); reg(m->dqpre, (size_t)B * C2); reg(m->dipre, (size_t)B * C2); }
     if (a3) {
       reg(m->hd, (size_t)(T + 1) * B * H);
       reg(m->logits, (size_t)(T + 1) * B * m->ldl);     // d logits: operand of both the wgrad and the dgrad vocabulary GEMM
@@ -579,6 +579,21 @@ static int join_fc7_copy(nvqa_model* m) {
   return 0;
 }
 
+// Planes of an fp32 activation written by its PRODUCER kernel (pointwise.cuh PlaneOut): reserves / registers them in the
+// workspace's per-forward cache so that every GEMM naming `src` [rows x K] (ld = K) as an operand finds them.  Empty (the
+// consumer GEMM splits as before) in the SIMT mode, for K % 8 != 0, or when `src` is not a registered activation.
+static PlaneOut producer_planes(nvqa_model* m, const float* src, int rows, int K) {
+  PlaneOut po;
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("NVQA_PRODUCER_PLANES"); on = e ? atoi(e) : 1; }
+  if (!on || !m->planes || !m->ws || (K & 7) || cache_class(m, src) != 2) return po;
+  __nv_bfloat16* dst = nullptr;
+  int pitch = 0;
+  if (reserve_planes(m->ws, m->planes, src, rows, K, K, 2, &dst, &pitch) != 0 || pitch != K) return po;
+  po.p = dst; po.stride = (long long)rows * K; po.P = m->planes;
+  return po;
+}
+
 // ---- side stream (see model.cuh) ---------------------------------------------------------------------------------
 // Routes everything enqueued through m->stream to the side stream for the lifetime of the object; GEMMs then take their
 // transients from the side arena of the workspace and run with a capped persistent grid.
@@ -617,7 +632,8 @@ static int aux_launch_fwd(nvqa_model* m, bool to_side) {
     {
       ProfScope ps(m, CAT_PW_FWD, 0);
       NVQA_TRY(join_fc7_copy(m));
-      NVQA_TRY(imgnorm_drop(m->stream, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), m->B, c.I, c.img_norm, m->norm_split));
+      NVQA_TRY(imgnorm_drop(m->stream, m->fc7, m->vd, make_drop(m, m->mk_i, STREAM_AXB_I), m->B, c.I, c.img_norm, m->norm_split,
+                            producer_planes(m, m->vd, m->B, c.I)));
       NVQA_CUDA(cudaEventRecord(m->fc7_consumed, m->stream));
     }
     NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, m->B, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
@@ -671,8 +687,12 @@ static int lstm_layers_forward(nvqa_model* m, const LstmSeg& sg, const int32_t* 
       if (l == 0) NVQA_TRY(aux_launch_fwd(m, true));     // the image branch runs beside the recurrent kernels
       // K4: all T steps in one persistent cooperative kernel (W_hh slice resident in shared memory)
       ProfScope ps(m, CAT_REC_FWD, 2.0 * (T - (sg.has_init ? 0 : 1)) * B * 4.0 * H * H);
+      // Dropout(h_t) for the layer above leaves the recurrent kernel as bf16 planes (it is only ever a GEMM operand)
+      PlaneOut xp;
+      if (xnext && lstm_fwd_v2_supported(m->planes, H)) xp = producer_planes(m, xnext, T * B, H);
       int rc = lstm_fwd_persistent_v2(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
-                                      (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter);
+                                      (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter, xp.p,
+                                      xp.stride);
       if (rc < 0)
         rc = lstm_fwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
                                  (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter);
@@ -828,7 +848,8 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   // embedding_net_q:forward   (:300)
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
-    NVQA_TRY(embed_fwd(s, m->q, m->len, m->WeT, m->be, m->y, make_drop(m, m->mk_emb, STREAM_EMB), B, T, E, c.V));
+    NVQA_TRY(embed_fwd(s, m->q, m->len, m->WeT, m->be, m->y, make_drop(m, m->mk_emb, STREAM_EMB), B, T, E, c.V,
+                       producer_planes(m, m->y, T * B, E)));
   }
   m->aux_fwd = true;                        // the image branch is due: see aux_launch_fwd
   // rnn_forward (:303), layer-major
@@ -839,7 +860,7 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   for (int l = 0; l < L; ++l) { cf[l] = m->c[l] + T * BH; hf[l] = m->h[l] + T * BH; }
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
-    NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L));
+    NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L, producer_planes(m, m->qd, B, S)));
   }
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
   // the image branch (fc7 norm + Dropout + Linear(I, C)) was launched on the side stream beside the recurrent kernels
@@ -848,14 +869,15 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   NVQA_TRY(aux_join_main(m));
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
-    NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C, m->fusion_skip));
+    NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C, m->fusion_skip,
+                      producer_planes(m, m->zd, B, c.C)));
   }
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.O, c.C, m->zd, c.C, m->Wc, c.C, m->scores, c.O, false, m->bc));
   // criterion forward/backward (:308-310) + torch.max (004_eval_model.lua:233)
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(softmax_ce(s, m->scores, m->labels, m->labels ? m->dscores : nullptr, m->rowloss, m->argmax, B, c.O,
-                        1.0f / (float)B));
+                        1.0f / (float)B, m->labels ? producer_planes(m, m->dscores, B, c.O) : PlaneOut()));
     if (m->labels) NVQA_TRY(loss_reduce(s, m->rowloss, m->loss, B));
   }
   m->fwd_done = true;
@@ -956,7 +978,8 @@ static int backward_head(nvqa_model* m) {
   // Linear(C,O) backward: the input gradient first; the weight gradient joins the deferred ones below
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, C, O, m->dscores, O, m->Wc, C, m->dzd, C, false));
   // Dropout, CMulTable, Tanh backward
-  NVQA_TRY(fuse_bwd(s, m->dzd, m->qc, m->ic, m->dqpre, m->dipre, make_drop(m, m->mk_z, STREAM_HEAD), B, C, m->fusion_skip));
+  NVQA_TRY(fuse_bwd(s, m->dzd, m->qc, m->ic, m->dqpre, m->dipre, make_drop(m, m->mk_z, STREAM_HEAD), B, C, m->fusion_skip,
+                    producer_planes(m, m->dqpre, B, C), producer_planes(m, m->dipre, B, C)));
   // AxB Linear backward (no d fc7): the input gradient the LSTM backward waits for first ...
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, S, C, m->dqpre, C, m->Wq, S, m->dqd, S, false));
   NVQA_TRY(mask_inplace(s, m->dqd, make_drop(m, m->mk_q, STREAM_AXB_Q), (int64_t)B * S));
@@ -1114,8 +1137,8 @@ static int backward_embed(nvqa_model* m) {
   cudaStream_t s = m->stream;
   ProfScope ps(m, CAT_PW_BWD, 0);
   NVQA_CUDA(cudaMemsetAsync(m->gWeT, 0, (size_t)m->n_blk[1] * 4, s));
-  NVQA_TRY(embed_bwd(s, m->q, m->len, m->y, m->dxbuf, m->gWeT, make_drop(m, m->mk_emb, STREAM_EMB), m->B, c.T, c.E, c.V));
-  NVQA_TRY(colsum(s, m->dxbuf, c.T * m->B, c.E, c.E, m->gbe, nullptr));
+  // (gWeT and the bias gradient gbe are one contiguous block: both were cleared above)
+  NVQA_TRY(embed_bwd(s, m->q, m->len, m->y, m->dxbuf, m->gWeT, make_drop(m, m->mk_emb, STREAM_EMB), m->B, c.T, c.E, c.V, m->gbe));
   return 0;
 }
 
@@ -1269,6 +1292,7 @@ extern "C" int nvqa_lstm_cell_forward(nvqa_model* m, const float* state, const f
   const int E = c.E, H = c.H, L = c.L, S = m->S;
   cudaStream_t s = m->stream;
   umma_workspace_new_forward(m->ws);      // scratch operands are rewritten by every call: no stale cached planes
+  m->fwd_done = false;                    // ... which also drops the planes a pending nvqa_backward would read
   float* pre = m->da;                     // scratch [n x 4H]
   float* xin = m->dxbuf;                  // scratch [n x H] (dropped h of the layer below)
   Drop d;
@@ -1298,6 +1322,7 @@ extern "C" int nvqa_axb_forward(nvqa_model* m, const float* q, const float* i, c
   const int S = m->S;
   cudaStream_t s = m->stream;
   umma_workspace_new_forward(m->ws);       // qd / vd are rewritten here: their cached bf16 planes (class 2) are stale
+  m->fwd_done = false;
   Drop dq, di, none;
   dq.mask = masks_q; dq.key = 0; dq.thresh = 0; dq.scale = 1.f; dq.mode = masks_q ? 1 : 0;
   di = dq; di.mask = masks_i; di.mode = masks_i ? 1 : 0;
@@ -1382,6 +1407,7 @@ extern "C" int nvqa_lstm_cell_backward(nvqa_model* m, const float* state, const 
   NVQA_CUDA(cudaSetDevice(c.device));
   NVQA_TRY(mod_scratch(m));
   umma_workspace_new_forward(m->ws);       // scratch operands are rewritten by every call: no stale cached planes
+  m->fwd_done = false;
   const int E = c.E, H = c.H, L = c.L, S = m->S;
   cudaStream_t s = m->stream;
   // forward internals
@@ -1431,6 +1457,7 @@ extern "C" int nvqa_axb_backward(nvqa_model* m, const float* q, const float* i, 
   const int S = m->S, C = c.C, I = c.I;
   cudaStream_t s = m->stream;
   umma_workspace_new_forward(m->ws);
+  m->fwd_done = false;
   Drop dq_ = explicit_drop(masks_q), di_ = explicit_drop(masks_i), none = explicit_drop(nullptr);
   NVQA_TRY(mask_copy(s, q, S, nullptr, m->qd, dq_, n, S));
   NVQA_TRY(mask_copy(s, i, I, nullptr, m->vd, di_, n, I));

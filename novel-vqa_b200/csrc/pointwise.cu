@@ -14,10 +14,37 @@ namespace nvqa {
 #define LD4(p) (*reinterpret_cast<const float4*>(p))
 #define ST4(p, v) (*reinterpret_cast<float4*>(p) = (v))
 
+// the PlaneOut twin of a store of four consecutive fp32 values at element index idx (idx % 4 == 0) / of one value
+__device__ __forceinline__ void planes_st4(const PlaneOut& po, size_t idx, float4 v) {
+  if (!po.p) return;
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 pl[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split3(x[j], pl[0][j], pl[1][j], pl[2][j]);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (q >= po.P) break;
+    uint2 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(pl[q][0]) | ((uint32_t)__bfloat16_as_ushort(pl[q][1]) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(pl[q][2]) | ((uint32_t)__bfloat16_as_ushort(pl[q][3]) << 16);
+    *reinterpret_cast<uint2*>(po.p + (size_t)q * po.stride + idx) = o;
+  }
+}
+__device__ __forceinline__ void planes_st1(const PlaneOut& po, size_t idx, float v) {
+  if (!po.p) return;
+  __nv_bfloat16 pl[3];
+  split3(v, pl[0], pl[1], pl[2]);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (q >= po.P) break;
+    po.p[(size_t)q * po.stride + idx] = pl[q];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len, const float* __restrict__ WeT,
-                 const float* __restrict__ be, float* __restrict__ y, Drop d, int B, int T, int E, int V) {
+                 const float* __restrict__ be, float* __restrict__ y, Drop d, int B, int T, int E, int V, PlaneOut yp) {
   const int E4 = E >> 2;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)T * B * E4;
@@ -37,12 +64,13 @@ embed_fwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len,
     out.w = tanhf(m.w * (wv.w + bv.w));
   }
   ST4(y + n * E + e, out);
+  planes_st4(yp, (size_t)n * E + e, out);
 }
 
 int embed_fwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* WeT, const float* be, float* y,
-              Drop d, int B, int T, int E, int V) {
+              Drop d, int B, int T, int E, int V, PlaneOut yp) {
   int64_t total = (int64_t)T * B * (E / 4);
-  embed_fwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(q, len, WeT, be, y, d, B, T, E, V);
+  embed_fwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(q, len, WeT, be, y, d, B, T, E, V, yp);
   NVQA_LAUNCHED();
   return 0;
 }
@@ -50,7 +78,8 @@ int embed_fwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float*
 // ------------------------------------------------------------------------------------------------
 // one CTA per image row: sum of squares by warp shuffles, then scale + dropout
 __global__ void __launch_bounds__(256)
-imgnorm_drop_kernel(const float* __restrict__ fc7, float* __restrict__ vd, Drop d, int I, int img_norm, int split) {
+imgnorm_drop_kernel(const float* __restrict__ fc7, float* __restrict__ vd, Drop d, int I, int img_norm, int split,
+                    PlaneOut vp) {
   // split > 0: columns [0, split) and [split, I) are two feature blocks normalised separately
   // (early fusion, 003_train_ae_based_ef.lua:116-124); split is a multiple of 4
   __shared__ float red[2][8];
@@ -80,11 +109,12 @@ imgnorm_drop_kernel(const float* __restrict__ fc7, float* __restrict__ vd, Drop 
     const float inv = j < cut ? inv0 : inv1;
     v.x = v.x * inv * m.x; v.y = v.y * inv * m.y; v.z = v.z * inv * m.z; v.w = v.w * inv * m.w;
     ST4(vd + (int64_t)b * I + j, v);
+    planes_st4(vp, (size_t)b * I + j, v);
   }
 }
 
-int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm, int split) {
-  imgnorm_drop_kernel<<<B, 256, 0, s>>>(fc7, vd, d, I, img_norm, split);
+int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm, int split, PlaneOut vp) {
+  imgnorm_drop_kernel<<<B, 256, 0, s>>>(fc7, vd, d, I, img_norm, split, vp);
   NVQA_LAUNCHED();
   return 0;
 }
@@ -130,7 +160,7 @@ int lstm_gates_fwd(cudaStream_t s, float* pre_t, const float* c_prev, int ldp, f
 struct StatePtrs { const float* c[4]; const float* h[4]; };
 
 __global__ void __launch_bounds__(256)
-qvec_fwd_kernel(StatePtrs sp, float* __restrict__ state, float* __restrict__ qd, Drop d, int B, int H, int L) {
+qvec_fwd_kernel(StatePtrs sp, float* __restrict__ state, float* __restrict__ qd, Drop d, int B, int H, int L, PlaneOut qp) {
   const int S = 2 * L * H, S4 = S >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * S4) return;
@@ -140,21 +170,24 @@ qvec_fwd_kernel(StatePtrs sp, float* __restrict__ state, float* __restrict__ qd,
   float4 v = LD4(src + (int64_t)b * H + jj);
   ST4(state + (int64_t)b * S + j, v);
   float4 m = drop_at4(d, (uint64_t)b * S + j);
-  ST4(qd + (int64_t)b * S + j, make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w));
+  const float4 o = make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w);
+  ST4(qd + (int64_t)b * S + j, o);
+  planes_st4(qp, (size_t)b * S + j, o);
 }
 
 int qvec_fwd(cudaStream_t s, const float* const* c_fin, const float* const* h_fin, float* state, float* qd,
-             Drop d, int B, int H, int L) {
+             Drop d, int B, int H, int L, PlaneOut qp) {
   StatePtrs sp;
   for (int l = 0; l < 4; ++l) { sp.c[l] = l < L ? c_fin[l] : nullptr; sp.h[l] = l < L ? h_fin[l] : nullptr; }
-  qvec_fwd_kernel<<<ceil_div((int64_t)B * 2 * L * H / 4, 256), 256, 0, s>>>(sp, state, qd, d, B, H, L);
+  qvec_fwd_kernel<<<ceil_div((int64_t)B * 2 * L * H / 4, 256), 256, 0, s>>>(sp, state, qd, d, B, H, L, qp);
   NVQA_LAUNCHED();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-fuse_fwd_kernel(float* __restrict__ qc, float* __restrict__ ic, float* __restrict__ zd, Drop d, int64_t n4, int skip) {
+fuse_fwd_kernel(float* __restrict__ qc, float* __restrict__ ic, float* __restrict__ zd, Drop d, int64_t n4, int skip,
+                PlaneOut zp) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 a = LD4(qc + i * 4), b = LD4(ic + i * 4);
@@ -165,12 +198,14 @@ fuse_fwd_kernel(float* __restrict__ qc, float* __restrict__ ic, float* __restric
   if (skip) {   // netdef.AskipB (misc/netdef.lua:16-25): output = qc + qc * ic
     b.x += 1.0f; b.y += 1.0f; b.z += 1.0f; b.w += 1.0f;
   }
-  ST4(zd + i * 4, make_float4(a.x * b.x * m.x, a.y * b.y * m.y, a.z * b.z * m.z, a.w * b.w * m.w));
+  const float4 o = make_float4(a.x * b.x * m.x, a.y * b.y * m.y, a.z * b.z * m.z, a.w * b.w * m.w);
+  ST4(zd + i * 4, o);
+  planes_st4(zp, (size_t)i * 4, o);
 }
 
-int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C, int skip) {
+int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C, int skip, PlaneOut zp) {
   int64_t n4 = (int64_t)B * C / 4;
-  fuse_fwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(qc, ic, zd, d, n4, skip);
+  fuse_fwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(qc, ic, zd, d, n4, skip, zp);
   NVQA_LAUNCHED();
   return 0;
 }
@@ -179,7 +214,7 @@ int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int
 // one warp per row: max / sum by shuffles; first-max argmax (strict '>' scan, torch.max semantics)
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ scores, const int32_t* __restrict__ labels, float* __restrict__ dscores,
-                  float* __restrict__ rowloss, int32_t* __restrict__ argmax, int n, int O, float inv_n) {
+                  float* __restrict__ rowloss, int32_t* __restrict__ argmax, int n, int O, float inv_n, PlaneOut dp) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -207,15 +242,17 @@ softmax_ce_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
     float* dr = dscores + (int64_t)row * O;
     for (int j = lane; j < O; j += 32) {
       float p = expf(sr[j] - mx) * inv;
-      dr[j] = (p - (j == y ? 1.0f : 0.0f)) * inv_n;
+      const float g = (p - (j == y ? 1.0f : 0.0f)) * inv_n;
+      dr[j] = g;
+      planes_st1(dp, (size_t)row * O + j, g);
     }
   }
   if (lane == 0 && rowloss) rowloss[row] = (y >= 0 && y < O) ? -(sr[y] - mx - logf(se)) : 0.f;
 }
 
 int softmax_ce(cudaStream_t s, const float* scores, const int32_t* labels, float* dscores, float* rowloss,
-               int32_t* argmax, int n, int O, float inv_n) {
-  softmax_ce_kernel<<<ceil_div(n, 8), 256, 0, s>>>(scores, labels, dscores, rowloss, argmax, n, O, inv_n);
+               int32_t* argmax, int n, int O, float inv_n, PlaneOut dp) {
+  softmax_ce_kernel<<<ceil_div(n, 8), 256, 0, s>>>(scores, labels, dscores, rowloss, argmax, n, O, inv_n, dp);
   NVQA_LAUNCHED();
   return 0;
 }
@@ -245,7 +282,7 @@ int loss_reduce(cudaStream_t s, const float* rowloss, float* loss, int n) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fuse_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ qc, const float* __restrict__ ic,
-                float* __restrict__ dqpre, float* __restrict__ dipre, Drop d, int64_t n4, int skip) {
+                float* __restrict__ dqpre, float* __restrict__ dipre, Drop d, int64_t n4, int skip, PlaneOut qp, PlaneOut ip) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 g = LD4(dzd + i * 4), a = LD4(qc + i * 4), b = LD4(ic + i * 4), m = drop_at4(d, (uint64_t)i * 4);
@@ -257,12 +294,13 @@ fuse_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ qc, con
   FB(x) FB(y) FB(z) FB(w)
 #undef FB
   ST4(dqpre + i * 4, dq); ST4(dipre + i * 4, di);
+  planes_st4(qp, (size_t)i * 4, dq); planes_st4(ip, (size_t)i * 4, di);
 }
 
 int fuse_bwd(cudaStream_t s, const float* dzd, const float* qc, const float* ic, float* dqpre, float* dipre,
-             Drop d, int B, int C, int skip) {
+             Drop d, int B, int C, int skip, PlaneOut qp, PlaneOut ip) {
   int64_t n4 = (int64_t)B * C / 4;
-  fuse_bwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(dzd, qc, ic, dqpre, dipre, d, n4, skip);
+  fuse_bwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(dzd, qc, ic, dqpre, dipre, d, n4, skip, qp, ip);
   NVQA_LAUNCHED();
   return 0;
 }
@@ -374,32 +412,47 @@ int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* o
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len, const float* __restrict__ y,
-                 float* __restrict__ dx, float* __restrict__ dWeT, Drop d, int B, int T, int E, int V) {
+                 float* __restrict__ dx, float* __restrict__ dWeT, Drop d, int B, int T, int E, int V,
+                 float* __restrict__ dbias) {
+  extern __shared__ float bsum[];                // [E] column sums of this CTA's dpre rows (dbias != nullptr)
+  if (dbias) {
+    for (int j = threadIdx.x; j < E; j += blockDim.x) bsum[j] = 0.f;
+    __syncthreads();
+  }
   const int E4 = E >> 2;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)T * B * E4;
-  if (i >= total) return;
-  int e = (int)(i % E4) * 4;
-  int64_t n = i / E4;
-  int b = (int)(n % B), t = (int)(n / B);
-  int w = q[(int64_t)b * T + t];
-  float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
-  if ((!len || t >= T - len[b]) && w >= 1 && w <= V) {
-    float4 g = LD4(dx + n * E + e), yy = LD4(y + n * E + e), m = drop_at4(d, (uint64_t)n * E + e);
-    dp.x = g.x * (1.0f - yy.x * yy.x) * m.x;
-    dp.y = g.y * (1.0f - yy.y * yy.y) * m.y;
-    dp.z = g.z * (1.0f - yy.z * yy.z) * m.z;
-    dp.w = g.w * (1.0f - yy.w * yy.w) * m.w;
-    float* dst = dWeT + (int64_t)(w - 1) * E + e;
-    atomicAdd(dst + 0, dp.x); atomicAdd(dst + 1, dp.y); atomicAdd(dst + 2, dp.z); atomicAdd(dst + 3, dp.w);
+  if (i < total) {
+    int e = (int)(i % E4) * 4;
+    int64_t n = i / E4;
+    int b = (int)(n % B), t = (int)(n / B);
+    int w = q[(int64_t)b * T + t];
+    float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((!len || t >= T - len[b]) && w >= 1 && w <= V) {
+      float4 g = LD4(dx + n * E + e), yy = LD4(y + n * E + e), m = drop_at4(d, (uint64_t)n * E + e);
+      dp.x = g.x * (1.0f - yy.x * yy.x) * m.x;
+      dp.y = g.y * (1.0f - yy.y * yy.y) * m.y;
+      dp.z = g.z * (1.0f - yy.z * yy.z) * m.z;
+      dp.w = g.w * (1.0f - yy.w * yy.w) * m.w;
+      float* dst = dWeT + (int64_t)(w - 1) * E + e;
+      atomicAdd(dst + 0, dp.x); atomicAdd(dst + 1, dp.y); atomicAdd(dst + 2, dp.z); atomicAdd(dst + 3, dp.w);
+      if (dbias) {
+        atomicAdd(bsum + e, dp.x); atomicAdd(bsum + e + 1, dp.y); atomicAdd(bsum + e + 2, dp.z); atomicAdd(bsum + e + 3, dp.w);
+      }
+    }
+    ST4(dx + n * E + e, dp);    // dpre kept (module-level callers sum the bias gradient from it)
   }
-  ST4(dx + n * E + e, dp);    // dpre kept for the bias column sum
+  if (dbias) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < E; j += blockDim.x)
+      if (bsum[j] != 0.f) atomicAdd(dbias + j, bsum[j]);
+  }
 }
 
 int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* y, float* dx, float* dWeT,
-              Drop d, int B, int T, int E, int V) {
+              Drop d, int B, int T, int E, int V, float* dbias) {
   int64_t total = (int64_t)T * B * (E / 4);
-  embed_bwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(q, len, y, dx, dWeT, d, B, T, E, V);
+  embed_bwd_kernel<<<ceil_div(total, 256), 256, dbias ? (size_t)E * 4 : 0, s>>>(q, len, y, dx, dWeT, d, B, T, E, V, dbias);
   NVQA_LAUNCHED();
   return 0;
 }

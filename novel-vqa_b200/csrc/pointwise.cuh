@@ -6,27 +6,37 @@
 
 namespace nvqa {
 
+// Optional second output of a producer kernel: the same values as bf16 planes [P][rows][K] (K % 8 == 0, no padding), i.e.
+// the operand format of the tcgen05 GEMM engine, at the place reserve_planes (umma_engine.cuh) registered for the fp32
+// matrix -- the separate fp32 -> planes pass (split_planes_kernel) of every consumer GEMM then disappears.
+struct PlaneOut {
+  __nv_bfloat16* p = nullptr;
+  long long stride = 0;        // elements between planes
+  int P = 0;
+};
+
 // K2: one-hot Linear + Dropout + Tanh as a gather (002_train_baseline.lua:141-144).  y [T x B x E]
 int embed_fwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* WeT, const float* be, float* y,
-              Drop d, int B, int T, int E, int V);
+              Drop d, int B, int T, int E, int V, PlaneOut yp = PlaneOut());
 // fc7 L2 row norm (002_train_baseline.lua:117-123) fused with AxB's Dropout on i (misc/netdef.lua:11)
 // split > 0: [0, split) and [split, I) normalised separately (early fusion, 003_train_ae_based_ef.lua:116-124)
-int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm, int split = 0);
+int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm, int split = 0,
+                 PlaneOut vp = PlaneOut());
 // gate math + cell update of one LSTM layer at time t (misc/LSTM.lua:45-59); pre -> gates in place
 int lstm_gates_fwd(cudaStream_t s, float* pre_t, const float* c_prev, int ldp, float* c_new, float* h_new, int ldn,
                    float* xdrop_next_t, const int32_t* len, Drop d, int t, int T, int B, int H);
 // final state -> question vector with AxB's Dropout on q  (002_train_baseline.lua:306, misc/netdef.lua:10)
 int qvec_fwd(cudaStream_t s, const float* const* c_fin, const float* const* h_fin, float* state, float* qd,
-             Drop d, int B, int H, int L);
+             Drop d, int B, int H, int L, PlaneOut qp = PlaneOut());
 // qc = tanh(qpre), ic = tanh(ipre) (in place), zd = mz * qc * ic   (misc/netdef.lua:10-12, 002_train_baseline.lua:153)
 // skip = 1: netdef.AskipB (misc/netdef.lua:16-25), output = qc + qc * ic
-int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C, int skip = 0);
+int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C, int skip = 0, PlaneOut zp = PlaneOut());
 // nn.CrossEntropyCriterion fwd+bwd + torch.max argmax (002_train_baseline.lua:308-310, 004_eval_model.lua:233)
 int softmax_ce(cudaStream_t s, const float* scores, const int32_t* labels, float* dscores, float* rowloss,
-               int32_t* argmax, int n, int O, float inv_n);
+               int32_t* argmax, int n, int O, float inv_n, PlaneOut dp = PlaneOut());
 int loss_reduce(cudaStream_t s, const float* rowloss, float* loss, int n);
 int fuse_bwd(cudaStream_t s, const float* dzd, const float* qc, const float* ic, float* dqpre, float* dipre,
-             Drop d, int B, int C, int skip = 0);
+             Drop d, int B, int C, int skip = 0, PlaneOut qp = PlaneOut(), PlaneOut ip = PlaneOut());
 int mask_inplace(cudaStream_t s, float* x, Drop d, int64_t n);
 // cell backward at time t: writes da_t [B x 4H] and the dc carry
 int lstm_gates_bwd(cudaStream_t s, const float* gates_t, const float* c_prev, const float* c_new,
@@ -35,8 +45,10 @@ int lstm_gates_bwd(cudaStream_t s, const float* gates_t, const float* c_prev, co
 // out0[n] (and out1[n]) = sum_r A[r][n]   (bias gradients)
 int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* out0, float* out1);
 // Tanh/Dropout backward + scatter-add into dWeT [V x E]  (002_train_baseline.lua:320)
+// dbias (optional, zeroed by the caller): += column sums of dpre (the Linear's bias gradient), accumulated per CTA in shared
+// memory and added with one atomic per column and CTA
 int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* y, float* dx, float* dWeT,
-              Drop d, int B, int T, int E, int V);
+              Drop d, int B, int T, int E, int V, float* dbias = nullptr);
 // arch2 LookupTable gather / scatter-add (003_train_vqa_arch2/misc/Encoder_lstm.lua:177-203,256) and head Dropout
 int lookup_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* x, int B, int T, int E, int V, int steps);
 int lookup_bwd(cudaStream_t s, const int32_t* seq, const float* dx, float* dtable, int B, int T, int E, int V, int steps);

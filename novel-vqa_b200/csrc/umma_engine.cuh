@@ -68,6 +68,8 @@ struct UmmaWorkspace {
 int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int cols, int ld,
                    int cache_class, __nv_bfloat16** out, int* pitch_out);
 void umma_workspace_new_forward(UmmaWorkspace* ws);
+int reserve_planes(UmmaWorkspace* ws, int P, const float* src, int rows, int K, int ld, int cache_class, __nv_bfloat16** out,
+                   int* pitch_out);
 int presplit_weights(UmmaWorkspace* ws, cudaStream_t s, int P, const float* const* src, const int* rows, const int* K, int n);
 // tensor map over planes [P][rows][pitch]: box = 64 columns (128 B, SWIZZLE_128B) x box_rows x 1 plane
 // (rows = bound of the row coordinate; plane_stride in elements, 0 = rows * pitch)

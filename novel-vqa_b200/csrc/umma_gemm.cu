@@ -611,8 +611,8 @@ void umma_workspace_new_forward(UmmaWorkspace* ws) {
 
 // fp32 row-major [rows x cols] (ld) -> bf16 planes [P][rows][colsp]; no transposition: an MN-major operand is
 // consumed as such through MN-major shared-memory descriptors
-int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int K,
-                          int ld, int is_static, __nv_bfloat16** out, int* Kp_out) {
+static int prepare_planes_impl(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int K,
+                               int ld, int is_static, __nv_bfloat16** out, int* Kp_out, bool reserve_only) {
   const int Kp = (K + 7) & ~7;
   *Kp_out = Kp;
   PlaneKey key{src, rows, K, ld, 1, P};
@@ -639,6 +639,10 @@ int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, i
     dst = reinterpret_cast<__nv_bfloat16*>(ws->base + trans0 + ws->ttop());
     ws->ttop() += need;
   }
+  if (reserve_only) {             // reserve_planes: the producer kernel of `src` writes the planes itself
+    *out = dst;
+    return 0;
+  }
   int64_t n = (int64_t)rows * (Kp / 4);
   if (P == 1) split_planes_kernel<1><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
   else if (P == 2) split_planes_kernel<2><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
@@ -646,6 +650,19 @@ int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, i
   NVQA_LAUNCHED();
   *out = dst;
   return 0;
+}
+
+// Reserves (and registers in the cache of class 1 / 2) the planes of the fp32 matrix `src` WITHOUT splitting it: the kernel
+// that produces `src` writes the planes too (layout [P][rows][pitch], pitch = K rounded up to 8), so the GEMMs that later
+// name `src` as an operand find them ready.  Returns the existing planes if `src` is already cached.
+int reserve_planes(UmmaWorkspace* ws, int P, const float* src, int rows, int K, int ld, int cache_class, __nv_bfloat16** out,
+                   int* pitch_out) {
+  NVQA_CHECK(cache_class == 1 || cache_class == 2, "reserve_planes: only cached operand classes can be produced upstream");
+  return prepare_planes_impl(ws, nullptr, P, src, rows, K, ld, cache_class, out, pitch_out, true);
+}
+int prepare_planes(UmmaWorkspace* ws, cudaStream_t s, int P, const float* src, int rows, int K, int ld, int is_static,
+                   __nv_bfloat16** out, int* Kp_out) {
+  return prepare_planes_impl(ws, s, P, src, rows, K, ld, is_static, out, Kp_out, false);
 }
 
 // Pre-split up to 16 weight matrices (row-major fp32 [rows x K], leading dimension K) into cached planes with ONE launch;
