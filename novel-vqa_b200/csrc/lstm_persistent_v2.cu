@@ -984,7 +984,17 @@ __device__ __forceinline__ long long v3_gtimer() { long long t; asm volatile("mo
 // BOX4: the da tile of a step is fetched by KB / 2 4-D TMA boxes of two k-blocks (32 KB, both planes) with one `full` /
 // `empty` barrier pair each instead of KB boxes of one k-block -- half the try_wait + expect_tx + issue rounds of the TMA
 // warp and half the waits of the MMA warp (the forward kernel's BOX4 gave 0.424 -> 0.369 ms on B200, round 2).
-template <int P, bool STK, bool DBG, bool POLL1 = false, bool BOX4 = false>
+// PAIR (round 2): the CTAs of two adjacent column tiles (same K-split, same batch tile) form a cta_group::2 pair inside an
+// 8-CTA cluster (2 x 4 x 1): the da tile is the pair's shared B operand of which each CTA loads only HALF (32 rows: the
+// per-SM ingest of a step halves to 64 KB), the leader issues tcgen05.mma.cta_group::2 with M = 256 over both CTAs'
+// resident W_hh^T slices (pair-mode instruction costs, tools/probes/probe_mma_rate2.cu: TS 43.6 instead of 62.9 cycles
+// at N = 64), its multicast commits arrive on `empty` / `tfull` of both.  The split-K reduction through distributed
+// shared memory is unchanged (the four K-split CTAs of a column tile are ranks prank + 2 r of the cluster).
+__device__ __forceinline__ void p2_commit_mask(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+template <int P, bool STK, bool DBG, bool POLL1 = false, bool BOX4 = false, bool PAIR = false>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_constant__ CUtensorMap mapW,
                    const __nv_bfloat16* __restrict__ w1, int w_pitch, const float* __restrict__ gates,
@@ -995,24 +1005,29 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
                    unsigned int* counter, int dbg_arg, int b0, int bend, const __grid_constant__ CUtensorMap mapDA4) {
   // this launch covers batch rows [b0, bend) (row stride of all buffers stays B)
   constexpr int KBB = 2;                            // BOX4: k-blocks per TMA box (a "big stage" = KBB ring stages)
-  static_assert(V2_STAGES % KBB == 0, "the ring holds whole big stages");
+  static_assert(!PAIR || (BOX4 && P == 2 && !STK && !POLL1 && !DBG), "the pair instantiation is the production bf16x2 kernel");
+  constexpr int NSTG = PAIR ? 2 * V2_STAGES : V2_STAGES;   // PAIR: half-size stages, same ring bytes
+  static_assert(NSTG % KBB == 0, "the ring holds whole big stages");
   const int dbg = DBG ? (dbg_arg & 0xFFFF) : 0;     // the production instantiation compiles the stamps away
   extern __shared__ uint8_t smem_raw[];
   __shared__ long long stamps[32];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   constexpr uint32_t W_KB = 128 * 128;
-  constexpr uint32_t B_PLANE = 64 * 128;
+  constexpr int LOADR = PAIR ? 32 : 64;                                         // da rows this CTA loads per step
+  constexpr uint32_t B_PLANE = LOADR * 128;
   constexpr uint32_t STAGE = P * B_PLANE;
   constexpr uint32_t TILE = 64 * V2_BPITCH * 4;                                  // 36,864 B
-  constexpr uint32_t RING = V2_STAGES * STAGE < TILE ? TILE + 1024 - TILE % 1024 : V2_STAGES * STAGE;
+  constexpr uint32_t RING = NSTG * STAGE < TILE ? TILE + 1024 - TILE % 1024 : NSTG * STAGE;
   const uint32_t w0 = base;
   const uint32_t r0 = w0 + (uint32_t)KB * W_KB;
   const uint32_t bar0 = r0 + RING;
-  const uint32_t full0 = bar0, empty0 = bar0 + 8 * V2_STAGES, wfull = bar0 + 16 * V2_STAGES, tfull = wfull + 8,
-                 gobar = wfull + 16, w1bar = wfull + 24, pfull = wfull + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * V2_STAGES + 48);
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * NSTG, wfull = bar0 + 16 * NSTG, tfull = wfull + 8,
+                 gobar = wfull + 16, w1bar = wfull + 24, pfull = wfull + 32, pairbar = wfull + 40;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * NSTG + 56);
   float* tbuf = reinterpret_cast<float*>(smem_raw + (r0 - raw));
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;                          // PAIR: rank = column-tile parity + 2 * ks
+  const uint32_t prank = crank & 1u, lrank = crank & ~1u;                        // 0 = the pair's leader; the leader's cluster rank
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.x * 128, ks = blockIdx.y, m0 = b0 + blockIdx.z * 64;
@@ -1028,16 +1043,24 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < V2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      for (int s = 0; s < NSTG; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
       mbar_init(wfull, 1);
       mbar_init(tfull, 1);
       mbar_init(gobar, 1);
       mbar_init(w1bar, 1);
       mbar_init(pfull, 4);                          // one arrival per CTA of the cluster and reduction round
+      mbar_init(pairbar, 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), 512);
+    if (!PAIR) tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  if (PAIR) {
+    cluster_sync_all();                             // both CTAs' mbarriers exist; both are ready to allocate
+    if (warp == 1) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1056,7 +1079,7 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     }
     __syncwarp();
     int it = 0;
-    const int gokb = (V2_STAGES < KB ? V2_STAGES : KB) - 1;
+    const int gokb = (NSTG < KB ? NSTG : KB) - 1;
     for (int t = T - 1; t >= tlast; --t) {
       const unsigned int k = (unsigned int)(T - 1 - t);
       if (lane == 0) {
@@ -1066,14 +1089,21 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
       __syncwarp();
       fence_proxy_async();
       if constexpr (BOX4) {
-        // `it` counts big stages: V2_STAGES / KBB of them in the ring, KB / KBB per step
+        // `it` counts big stages: NSTG / KBB of them in the ring, KB / KBB per step
         for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
-          const int bs = it % (V2_STAGES / KBB);
-          const uint32_t ph = (uint32_t)(it / (V2_STAGES / KBB)) & 1u;
+          const int bs = it % (NSTG / KBB);
+          const uint32_t ph = (uint32_t)(it / (NSTG / KBB)) & 1u;
           mbar_wait(empty0 + 8 * bs, ph ^ 1u);
           if (elect_one_sync()) {
-            mbar_expect_tx(full0 + 8 * bs, KBB * STAGE);
-            tma_load_4d(r0 + (uint32_t)bs * KBB * STAGE, &mapDA4, full0 + 8 * bs, 0, t * B + m0, 0, ks * KB + hb * KBB);
+            if constexpr (PAIR) {
+              // this CTA's half of the pair's da tile; both halves are counted on the leader's barrier
+              if (prank == 0) mbar_expect_tx(full0 + 8 * bs, 2 * KBB * STAGE);
+              p2_tma_load_4d(r0 + (uint32_t)bs * KBB * STAGE, &mapDA4, v3_mapa(full0 + 8 * bs, lrank), 0,
+                             t * B + m0 + (int)prank * LOADR, 0, ks * KB + hb * KBB);
+            } else {
+              mbar_expect_tx(full0 + 8 * bs, KBB * STAGE);
+              tma_load_4d(r0 + (uint32_t)bs * KBB * STAGE, &mapDA4, full0 + 8 * bs, 0, t * B + m0, 0, ks * KB + hb * KBB);
+            }
             if (hb == gokb / KBB) mbar_arrive(gobar);
           }
           __syncwarp();
@@ -1099,22 +1129,53 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     // STK: the two planes of a da stage are one contiguous 128-row B tile, so W0 . da0 and W0 . da1 are a single N = 128
     // instruction (accumulator columns [0, 64) and [64, 128), summed by the epilogue)
     constexpr uint32_t idesc_ts2 = make_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_p = make_idesc_bf16(256, 64, true, false), idesc_p_ts = make_idesc_bf16(256, 64, false, false);
     if (lane == 0) {
       mbar_wait(wfull, 0);
       if (P >= 2) mbar_wait(w1bar, 0);
+      if (PAIR) {
+        // the leader multiplies with the peer's resident W_hh^T slice too: the peer reports it ready
+        tc_fence_after();
+        if (prank != 0) v3_arrive_remote(v3_mapa(pairbar, lrank));
+        else v3_wait_cluster(pairbar, 0);
+      }
     }
     __syncwarp();
     tc_fence_after();
     const uint64_t dw_base = make_mnmajor_sw128_desc(w0), dr_base = make_kmajor_sw128_desc(r0);
     int it = 0;
-    for (int t = T - 1; t >= tlast; --t) {
+    for (int t = T - 1; t >= (PAIR && prank != 0 ? T : tlast); --t) {
       if constexpr (BOX4) {
         static_assert(!BOX4 || (P == 2 && !STK), "4-D boxes are wired into the bf16x2 instantiation");
         for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
-          const int bs = it % (V2_STAGES / KBB);
-          const uint32_t ph = (uint32_t)(it / (V2_STAGES / KBB)) & 1u;
+          const int bs = it % (NSTG / KBB);
+          const uint32_t ph = (uint32_t)(it / (NSTG / KBB)) & 1u;
           mbar_wait(full0 + 8 * bs, ph);
           tc_fence_after();
+          if constexpr (PAIR) {
+            if (elect_one_sync()) {
+              const uint16_t pmask = (uint16_t)(3u << lrank);
+#pragma unroll
+              for (int kbl = 0; kbl < KBB; ++kbl) {
+                const int kb = hb * KBB + kbl;
+                const uint64_t dwk = dw_base + (uint64_t)(((uint32_t)kb * W_KB) >> 4);
+                const uint64_t ddk = dr_base + (uint64_t)(((uint32_t)(bs * KBB + kbl) * STAGE) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t dw = dwk + (uint64_t)(kk * (2048 >> 4)), d0 = ddk + (uint64_t)(kk * 2);
+                  const uint64_t d1 = d0 + (uint64_t)(B_PLANE >> 4);
+                  const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + kk * 8);
+                  p2_umma_f16(tmem_base, dw, d0, idesc_p, (kb | kk) ? 1u : 0u);   // [W1 ; W1'] . da0
+                  p2_umma_f16_ts(tmem_base, wt, d1, idesc_p_ts, 1u);              // [W0 ; W0'] . da1
+                  p2_umma_f16_ts(tmem_base, wt, d0, idesc_p_ts, 1u);              // [W0 ; W0'] . da0
+                }
+              }
+              p2_commit_mask(empty0 + 8 * bs, pmask);
+              if (hb == KB / KBB - 1) p2_commit_mask(tfull, pmask);
+            }
+            __syncwarp();
+            continue;
+          }
           if (elect_one_sync()) {
 #pragma unroll
             for (int kbl = 0; kbl < KBB; ++kbl) {
@@ -1205,7 +1266,10 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
     float4 bsi[NI], bsf[NI], bso[NI], bsg[NI];
     uint32_t peer_tbuf[4], peer_pfull[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) { peer_tbuf[r] = v3_mapa(r0, (uint32_t)r); peer_pfull[r] = v3_mapa(pfull, (uint32_t)r); }
+    for (int r = 0; r < 4; ++r) {            // the four K-split CTAs of this column tile: cluster ranks r, or prank + 2 r in a pair cluster
+      const uint32_t pr = PAIR ? prank + 2u * (uint32_t)r : (uint32_t)r;
+      peer_tbuf[r] = v3_mapa(r0, pr); peer_pfull[r] = v3_mapa(pfull, pr);
+    }
 #pragma unroll
     for (int n = 0; n < NI; ++n) {
       bsi[n] = bsf[n] = bso[n] = bsg[n] = dab[n] = z;
@@ -1397,7 +1461,10 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                               // nobody leaves while a peer may still read its partial tile
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 __global__ void __launch_bounds__(256) v2_sum4_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4) {
@@ -1615,9 +1682,17 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     static int box4 = -1;
     if (box4 < 0) { const char* e = getenv("NVQA_LSTM_BOX4D"); box4 = e ? atoi(e) : 1; }
     const bool use_box4 = box4 && !dbg && P == 2 && !stack3 && !poll1;
+    // NVQA_LSTM_BWD_PAIR=1: cta_group::2 pairs of column tiles (8-CTA clusters) in the backward kernel.  Correct (parity
+    // suite green) but measured SLOWER on B200: 0.858 instead of 0.490 ms per step pair -- sixteen 8-CTA clusters with one
+    // CTA per SM are not all co-resident (the same effect as the 16-CTA clusters of the forward kernel), so
+    // part of the batch tiles runs as a second wave.  Default off.
+    static int bpair = -1;
+    if (bpair < 0) { const char* e = getenv("NVQA_LSTM_BWD_PAIR"); bpair = e ? atoi(e) : 0; }
+    bool use_pair = bpair && use_box4 && (H / 128) % 2 == 0;
     CUtensorMap mapDA4 = mapDA3;
-    if (use_box4) NVQA_TRY(get_map_kb(ws, dap, T * B, 4 * H, P, 64, 2, &mapDA4, dap_plane_rows * 4 * H));
-    const void* f3 = use_box4 ? (const void*)lstm_bwd_v3_kernel<2, false, false, false, true>
+    if (use_box4) NVQA_TRY(get_map_kb(ws, dap, T * B, 4 * H, P, use_pair ? 32 : 64, 2, &mapDA4, dap_plane_rows * 4 * H));
+    const void* f3 = use_pair ? (const void*)lstm_bwd_v3_kernel<2, false, false, false, true, true>
+                   : use_box4 ? (const void*)lstm_bwd_v3_kernel<2, false, false, false, true>
                    : (poll1 && !dbg && P == 2 && !stack3) ? (const void*)lstm_bwd_v3_kernel<2, false, false, true>
                    : dbg ? (P == 2 ? (const void*)lstm_bwd_v3_kernel<2, false, true> : (const void*)lstm_bwd_v3_kernel<1, false, true>)
                          : P == 2 ? (stack3 ? (const void*)lstm_bwd_v3_kernel<2, true, false> : (const void*)lstm_bwd_v3_kernel<2, false, false>)
@@ -1635,7 +1710,7 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
       cfg3.gridDim = grid; cfg3.blockDim = dim3(V2_THREADS); cfg3.dynamicSmemBytes = smem; cfg3.stream = s;
       cudaLaunchAttribute at3[2];
       at3[0].id = cudaLaunchAttributeClusterDimension;
-      at3[0].val.clusterDim.x = 1; at3[0].val.clusterDim.y = 4; at3[0].val.clusterDim.z = 1;
+      at3[0].val.clusterDim.x = use_pair ? 2 : 1; at3[0].val.clusterDim.y = 4; at3[0].val.clusterDim.z = 1;
       at3[1].id = cudaLaunchAttributeCooperative; at3[1].val.cooperative = 1;
       // Nsight Compute cannot replay a launch that is both cooperative and clustered (driver: LaunchFailed): profiling
       // runs set NVQA_LSTM_NOCOOP=1, which drops only the co-residency CHECK (128 CTAs on 148 idle SMs either way)
@@ -1645,6 +1720,12 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
         (void)cudaGetLastError();                   // refused as cooperative + clustered: retry as a plain cluster launch
         cfg3.numAttrs = 1;
         le = cudaLaunchKernelExC(&cfg3, f3, a3);
+      }
+      if (le != cudaSuccess && use_pair && tile0 == 0) {
+        (void)cudaGetLastError();                   // the 8-CTA pair clusters are not schedulable here: 4-CTA clusters instead
+        bpair = 0;
+        return lstm_bwd_persistent_v2(s, ws, P, Wh, gates, c, dh0, dc0, ld0, dh_above, d, dasum, dap, dap_plane_rows, dhbuf, dh_init,
+                                      dc_init, len, T, B, H, counter);
       }
       if (le != cudaSuccess) {
         (void)cudaGetLastError();                   // the clusters could not be made co-resident: generation 2 below

@@ -410,21 +410,23 @@ int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* o
 }
 
 // ------------------------------------------------------------------------------------------------
+// Grid-stride over (row, 4 columns) items with a CTA of rows_per_cta * E/4 threads: a thread keeps the SAME four columns in
+// every iteration, so the bias gradient (column sums of dpre) accumulates in registers and leaves the CTA as E atomics.
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len, const float* __restrict__ y,
                  float* __restrict__ dx, float* __restrict__ dWeT, Drop d, int B, int T, int E, int V,
                  float* __restrict__ dbias) {
-  extern __shared__ float bsum[];                // [E] column sums of this CTA's dpre rows (dbias != nullptr)
+  extern __shared__ float bsum[];                // [E] column sums of this CTA (dbias != nullptr)
   if (dbias) {
     for (int j = threadIdx.x; j < E; j += blockDim.x) bsum[j] = 0.f;
     __syncthreads();
   }
   const int E4 = E >> 2;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = (int64_t)T * B * E4;
-  if (i < total) {
-    int e = (int)(i % E4) * 4;
-    int64_t n = i / E4;
+  const int e = (int)(threadIdx.x % E4) * 4;     // blockDim.x is a multiple of E/4
+  const int rows_per_cta = blockDim.x / E4;
+  const int64_t rows = (int64_t)T * B;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t n = (int64_t)blockIdx.x * rows_per_cta + threadIdx.x / E4; n < rows; n += (int64_t)gridDim.x * rows_per_cta) {
     int b = (int)(n % B), t = (int)(n / B);
     int w = q[(int64_t)b * T + t];
     float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -436,13 +438,12 @@ embed_bwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len,
       dp.w = g.w * (1.0f - yy.w * yy.w) * m.w;
       float* dst = dWeT + (int64_t)(w - 1) * E + e;
       atomicAdd(dst + 0, dp.x); atomicAdd(dst + 1, dp.y); atomicAdd(dst + 2, dp.z); atomicAdd(dst + 3, dp.w);
-      if (dbias) {
-        atomicAdd(bsum + e, dp.x); atomicAdd(bsum + e + 1, dp.y); atomicAdd(bsum + e + 2, dp.z); atomicAdd(bsum + e + 3, dp.w);
-      }
+      acc.x += dp.x; acc.y += dp.y; acc.z += dp.z; acc.w += dp.w;
     }
     ST4(dx + n * E + e, dp);    // dpre kept (module-level callers sum the bias gradient from it)
   }
   if (dbias) {
+    atomicAdd(bsum + e, acc.x); atomicAdd(bsum + e + 1, acc.y); atomicAdd(bsum + e + 2, acc.z); atomicAdd(bsum + e + 3, acc.w);
     __syncthreads();
     for (int j = threadIdx.x; j < E; j += blockDim.x)
       if (bsum[j] != 0.f) atomicAdd(dbias + j, bsum[j]);
@@ -451,8 +452,14 @@ embed_bwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len,
 
 int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* y, float* dx, float* dWeT,
               Drop d, int B, int T, int E, int V, float* dbias) {
-  int64_t total = (int64_t)T * B * (E / 4);
-  embed_bwd_kernel<<<ceil_div(total, 256), 256, dbias ? (size_t)E * 4 : 0, s>>>(q, len, y, dx, dWeT, d, B, T, E, V, dbias);
+  const int E4 = E / 4;
+  if (E4 > 256) {               // wider than a CTA: plain one-item-per-thread layout is not worth a second code path
+    NVQA_CHECK(E4 <= 256, "embed_bwd: E > 1024 is not supported");
+  }
+  const int threads = (256 / E4) * E4, rows_per_cta = threads / E4;
+  const int64_t rows = (int64_t)T * B;
+  const int grid = (int)std::min<int64_t>(ceil_div(rows, rows_per_cta), 148 * 4);
+  embed_bwd_kernel<<<grid, threads, dbias ? (size_t)E * 4 : 0, s>>>(q, len, y, dx, dWeT, d, B, T, E, V, dbias);
   NVQA_LAUNCHED();
   return 0;
 }
