@@ -1,0 +1,13 @@
+#!/bin/bash
+out=gpurun_out
+run() {
+  name=$1; shift
+  env "$@" timeout 150 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-extras 2>$out/r2i_$name.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+c={x['kernel']:round(x['ms_per_step'],3) for x in d['roofline']['classes']}
+print('$name', round(d['value']), round(d['ms_per_step'],4), 'fwd', c['lstm_recurrent_fwd'], 'bwd', c['lstm_recurrent_bwd'])"
+  tail -2 $out/r2i_$name.err
+}
+for m in 0 1 2 3; do run sync$m NVQA_LSTM_SYNC=$m; done
+run sync0b NVQA_LSTM_SYNC=0
