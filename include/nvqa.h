@@ -81,7 +81,10 @@ int nvqa_device_count(void);
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int nvqa_model_create(const nvqa_config* cfg, nvqa_model** out);
 int nvqa_model_destroy(nvqa_model* m);
-int nvqa_set_stream(nvqa_model* m, void* cuda_stream);      /* cudaStream_t; NULL = own stream  */
+/* cudaStream_t; NULL = the model's own (non-blocking) stream.  To run on the legacy default stream pass cudaStreamLegacy
+ * ((cudaStream_t)0x1), not 0 -- a host that mixes the library with NCCL / torch collectives on the default stream must do
+ * so, or the collectives are not ordered against the library's kernels (novel-vqa_b200/dp.py bind_current_stream). */
+int nvqa_set_stream(nvqa_model* m, void* cuda_stream);
 int nvqa_sync(nvqa_model* m);
 
 /* ---- parameters: module:getParameters() / torch.save table (002_train_baseline.lua:174-181,401) */

@@ -41,6 +41,9 @@ def bind_current_stream(model):
     import torch
     from . import _lib
     s = torch.cuda.current_stream().cuda_stream
+    if s == 0:
+        s = 1          # torch's default stream is the legacy default stream; nvqa_set_stream(NULL) means "the library's own
+        #                stream", so name it explicitly: cudaStreamLegacy == (cudaStream_t)0x1
     if getattr(model, "_bound_stream", None) != s:
         model.sync()                                   # work already enqueued on the previous stream
         _lib.check(model.lib.nvqa_set_stream(model.handle, C.c_void_p(s)))

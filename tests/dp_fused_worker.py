@@ -66,32 +66,44 @@ def main():
         import dataclasses
         cfg0 = dataclasses.replace(cfg, dropout=0.0)
         oc = A.Arch1Config(V=cfg.V, E=cfg.E, H=cfg.H, L=cfg.L, I=cfg.I, C=cfg.C, O=cfg.O, T=cfg.T, p=0.0)
-        m0 = nv.Arch1Model(cfg0, precision=nv.PREC_BF16X2, device=local)
+        # with -lr_scale 0.5 (003_train_ae_based_wp.lua:344: encoder and embedding gradients scaled before the clamp), through
+        # BOTH exchange paths: the fused peer-memory kernels and the NCCL bucketed all-reduce (dp.train_step, which binds the
+        # model to torch's current stream so that NCCL is ordered against the backward kernels -- round-1 ADVICE)
+        lr_scale = 0.5
         w0 = list(nv.synth_params(cfg, seed=2))
-        for blk, w in zip(blocks, w0):
-            m0.set_params(blk, w)
-        dp.connect_fused(m0, dist, rank, world)
         shard = nv.synth_batch(cfg, B, seed=900 + rank, min_len=1)
-        m0.set_batch_host(*shard)
-        dp.fused_train_step(m0, lr, seed=1)
-        m0.sync()
         shards = [None] * world
         dist.all_gather_object(shards, shard)
         gq, gl, gf, gy = (np.concatenate([sh[k] for sh in shards]) for k in range(4))
-        f_ref, g_ref, _, _ = A.jdj(oc, w0[0], w0[1], w0[2], gq, gl, A.l2_normalize_rows(gf), gy, seed=None)
-        for k, blk in enumerate(blocks):
-            want = w0[k].copy()
-            A.rmsprop_update(want, g_ref[k], np.zeros_like(want), lr)
-            got = m0.get_params(blk)
-            big = np.abs(g_ref[k]) > 1e-5       # lr * g / (0.1 |g| + eps) is ill-conditioned where |g| ~ eps
-            du, dw = (got - w0[k])[big].astype(np.float64), (want - w0[k])[big].astype(np.float64)
-            rel = np.linalg.norm(du - dw) / np.linalg.norm(dw)
-            if not rel < 5e-3:
-                ok = False
-                print(f"rank {rank} global-batch oracle check, block {blk}: update rel-l2 {rel:.3e}", flush=True)
-            elif rank == 0:
-                print(f"global batch {world}x{B} vs single-process oracle, block {blk}: update rel-l2 {rel:.2e}", flush=True)
-        m0.close()
+        f_ref, g_ref, _, _ = A.jdj(oc, w0[0], w0[1], w0[2], gq, gl, A.l2_normalize_rows(gf), gy, seed=None, lr_scale=lr_scale)
+        for path in ("fused", "nccl"):
+            m0 = nv.Arch1Model(cfg0, precision=nv.PREC_BF16X2, device=local)
+            m0.set_variant(lr_scale=lr_scale)
+            for blk, w in zip(blocks, w0):
+                m0.set_params(blk, w)
+            m0.set_batch_host(*shard)
+            if path == "fused":
+                dp.connect_fused(m0, dist, rank, world)
+                dp.fused_train_step(m0, lr, seed=1)
+            else:
+                views = dp.grad_bucket_views(m0, local)
+                dp.train_step(m0, views, dist, world, lr, seed=1)
+                torch.cuda.synchronize()
+            m0.sync()
+            for k, blk in enumerate(blocks):
+                want = w0[k].copy()
+                A.rmsprop_update(want, g_ref[k], np.zeros_like(want), lr)
+                got = m0.get_params(blk)
+                big = np.abs(g_ref[k]) > 1e-5       # lr * g / (0.1 |g| + eps) is ill-conditioned where |g| ~ eps
+                du, dw = (got - w0[k])[big].astype(np.float64), (want - w0[k])[big].astype(np.float64)
+                rel = np.linalg.norm(du - dw) / np.linalg.norm(dw)
+                if not rel < 5e-3:
+                    ok = False
+                    print(f"rank {rank} global-batch oracle check ({path}), block {blk}: update rel-l2 {rel:.3e}", flush=True)
+                elif rank == 0:
+                    print(f"global batch {world}x{B} vs single-process oracle ({path}, lr_scale {lr_scale}), block {blk}: "
+                          f"update rel-l2 {rel:.2e}", flush=True)
+            m0.close()
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
