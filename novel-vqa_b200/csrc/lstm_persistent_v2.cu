@@ -1479,6 +1479,339 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, generation 4 = generation 3 (4-CTA clusters over the K-splits, DSMEM reduction, 4-D TMA boxes, bf16x2) with the
+// forward kernel's TWO SOFTWARE-PIPELINED SUB-TILES: the 64-row batch tile of a CTA is processed as two independent 32-row
+// sub-tiles (recurrences of different batch rows never meet), each with its own group counter, accumulator (TMEM columns
+// [32 s, 32 s + 32)), `tfull` / `go` / `pfull` mbarriers, partial tile (16 KB, pitch 128: reads and writes are row-contiguous)
+// and four epilogue warps; the single TMA and MMA warps serve the work items (t, sub) in the fixed order (T-1,0) (T-1,1)
+// (T-2,0) ... through one ring of four 16 KB big stages (= one sub-tile step in flight).  While sub-tile 0 is in its cluster
+// reduction / cell backward / publish / barrier round (two thirds of a step's chain), sub-tile 1's da tile is loaded and
+// multiplied, and vice versa.  Thread items of a sub-tile group (128 threads): rows 8 ks + (lt + 128 n) / 32 of the
+// sub-tile, columns 4 ((lt + 128 n) % 32) .. + 3, n = 0, 1.
+template <int P>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+lstm_bwd_v4_kernel(const __grid_constant__ CUtensorMap mapW, const __nv_bfloat16* __restrict__ w1, int w_pitch,
+                   const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ dh0,
+                   const float* __restrict__ dc0, int ld0, const float* __restrict__ dh_above, Drop drop,
+                   float* __restrict__ dasum, __nv_bfloat16* __restrict__ dap, long long dap_plane,
+                   float* __restrict__ dh_init, float* __restrict__ dc_init, const int32_t* __restrict__ len, int T, int B,
+                   int H, int KB, unsigned int* counter, int poll_ns, int b0, int bend,
+                   const __grid_constant__ CUtensorMap mapDA4) {
+  static_assert(P == 2, "generation 4 is the bf16x2 production kernel");
+  constexpr int KBB = 2, NBS = 4;                   // k-blocks per TMA box; big stages in the ring
+  constexpr int SUBN = 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t W_KB = 128 * 128;
+  constexpr uint32_t B_PLANE = SUBN * 128;          // one plane of one k-block of a da sub-tile: 32 rows x 128 B
+  constexpr uint32_t STAGE = P * B_PLANE;           // 8 KB
+  constexpr uint32_t BIG = KBB * STAGE;             // 16 KB
+  constexpr uint32_t TILE = SUBN * 128 * 4;         // partial tile of a sub-tile: [32 rows][128 columns] fp32 = 16 KB
+  const uint32_t w0 = base;
+  const uint32_t r0 = w0 + (uint32_t)KB * W_KB;
+  const uint32_t tb0 = r0 + NBS * BIG;
+  const uint32_t bar0 = tb0 + 2 * TILE;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * NBS, wfull = bar0 + 16 * NBS, w1bar = wfull + 8, tfull = wfull + 16 /* x2 */,
+                 gobar = wfull + 32 /* x2 */, pfull = wfull + 48 /* x2 */;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - raw) + 16 * NBS + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 128, ks = blockIdx.y, m0 = b0 + blockIdx.z * 64;
+  const unsigned int G = gridDim.x * gridDim.y;                          // CTAs of one batch-tile group
+  counter += 32 * blockIdx.z;                                            // one 128-byte line per group: [0] sub-tile 0, [16] sub-tile 1
+  const int k_base = ks * H;
+  const int tlast = dc_init ? 0 : 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapDA4) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NBS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      mbar_init(wfull, 1);
+      mbar_init(w1bar, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(gobar + 8 * i, 1); mbar_init(pfull + 8 * i, 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // the peers' mbarriers exist before anybody signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t W1_COL = 256;
+
+  if (warp == 0) {
+    // ===== TMA producer: warp-uniform loop, one elected lane issues =====
+    if (lane == 0) {
+      mbar_expect_tx(wfull, (uint32_t)KB * W_KB);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int cc = 0; cc < 2; ++cc)
+          tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)cc * 8192, &mapW, wfull, c0 + 64 * cc, k_base + kb * 64, 1);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int t = T - 1; t >= tlast; --t) {
+      const unsigned int k = (unsigned int)(T - 1 - t);
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        if (lane == 0) v2_wait(counter + 16 * sub, (k + 1) * G, (unsigned int)poll_ns);   // da_t of this sub-tile is complete
+        __syncwarp();
+        fence_proxy_async();
+        for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
+          const int bs = it % NBS;
+          const uint32_t ph = (uint32_t)(it / NBS) & 1u;
+          mbar_wait(empty0 + 8 * bs, ph ^ 1u);
+          if (elect_one_sync()) {
+            mbar_expect_tx(full0 + 8 * bs, BIG);
+            tma_load_4d(r0 + (uint32_t)bs * BIG, &mapDA4, full0 + 8 * bs, 0, t * B + m0 + sub * SUBN, 0, ks * KB + hb * KBB);
+            if (hb == KB / KBB - 1) mbar_arrive(gobar + 8 * sub);   // this work item's loads are out: the epilogue may use the memory pipe
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, SUBN, true, false);       // A = W_hh^T slice in SMEM, MN-major
+    constexpr uint32_t idesc_ts = make_idesc_bf16(128, SUBN, false, false);   // A from TMEM is K-major by construction
+    if (lane == 0) {
+      mbar_wait(wfull, 0);
+      mbar_wait(w1bar, 0);
+    }
+    __syncwarp();
+    tc_fence_after();
+    const uint64_t dw_base = make_mnmajor_sw128_desc(w0), dr_base = make_kmajor_sw128_desc(r0);
+    int it = 0;
+    for (int t = T - 1; t >= tlast; --t) {
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const uint32_t tacc = tmem_base + (uint32_t)(sub * SUBN);
+        for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
+          const int bs = it % NBS;
+          const uint32_t ph = (uint32_t)(it / NBS) & 1u;
+          mbar_wait(full0 + 8 * bs, ph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int kbl = 0; kbl < KBB; ++kbl) {
+              const int kb = hb * KBB + kbl;
+              const uint64_t dwk = dw_base + (uint64_t)(((uint32_t)kb * W_KB) >> 4);
+              const uint64_t ddk = dr_base + (uint64_t)(((uint32_t)(bs * KBB + kbl) * STAGE) >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t dw = dwk + (uint64_t)(kk * (2048 >> 4)), d0 = ddk + (uint64_t)(kk * 2);
+                const uint64_t d1 = d0 + (uint64_t)(B_PLANE >> 4);
+                const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + kk * 8);
+                umma_f16(tacc, dw, d0, idesc, (kb | kk) ? 1u : 0u);   // W1 . da0
+                umma_f16_ts(tacc, wt, d1, idesc_ts, 1u);              // W0 . da1
+                umma_f16_ts(tacc, wt, d0, idesc_ts, 1u);              // W0 . da0
+              }
+            }
+            umma_commit(empty0 + 8 * bs);
+            if (hb == KB / KBB - 1) umma_commit(tfull + 8 * sub);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== 8 element-wise / epilogue warps: warps 2-5 own sub-tile 0, warps 6-9 sub-tile 1 =====
+    const int et = threadIdx.x - 64;                         // 0..255
+    const int q = warp & 3, ch = (warp - 2) >> 2;
+    {
+      // plane 0 of the W_hh^T slice -> TMEM (all eight warps, as in generation 3)
+      const __nv_bfloat16* src = w1 + (size_t)(k_base + 256 * ch) * w_pitch + c0 + q * 32 + lane;
+#pragma unroll 1
+      for (int blk = 0; blk < 4; ++blk) {
+        uint32_t wv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t lo = __bfloat16_as_ushort(src[(size_t)(blk * 64 + 2 * j) * w_pitch]);
+          const uint32_t hi = __bfloat16_as_ushort(src[(size_t)(blk * 64 + 2 * j + 1) * w_pitch]);
+          wv[j] = lo | (hi << 16);
+        }
+        tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + W1_COL + (uint32_t)(128 * ch + 32 * blk), wv);
+      }
+      tc_fence_before();
+    }
+    v2_bar_sync(1, V2_EPI);
+    if (et == 0) mbar_arrive(w1bar);
+    const int sub = ch;                                      // this warp's sub-tile
+    const int lt = et & 127;                                 // thread within the sub-tile group
+    const int bid = 2 + 3 * sub;                             // named barriers bid, bid + 1, bid + 2 (128 threads each)
+    unsigned int* const myctr = counter + 16 * sub;
+    float* const tbuf = reinterpret_cast<float*>(smem_raw + (tb0 - raw) + (uint32_t)sub * TILE);
+    const uint32_t my_tfull = tfull + 8 * sub, my_go = gobar + 8 * sub, my_pfull = pfull + 8 * sub;
+    constexpr int NI = 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool valid[NI];
+    int bq[NI], ucol[NI], first_t[NI];
+    uint32_t toff[NI];
+    float4 gi[NI], gf[NI], go[NI], gg[NI], cp[NI], cn[NI], dcr[NI], dab[NI];
+    float4 bsi[NI], bsf[NI], bso[NI], bsg[NI];
+    uint32_t peer_tbuf[4], peer_pfull[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      peer_tbuf[r] = v3_mapa(tb0 + (uint32_t)sub * TILE, (uint32_t)r);
+      peer_pfull[r] = v3_mapa(my_pfull, (uint32_t)r);
+    }
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      bsi[n] = bsf[n] = bso[n] = bsg[n] = dab[n] = z;
+      const int li = lt + 128 * n, rl = 8 * ks + (li >> 5), cl = (li & 31) * 4;
+      toff[n] = (uint32_t)(rl * 128 + cl) * 4u;
+      bq[n] = m0 + sub * SUBN + rl;
+      valid[n] = bq[n] < bend;
+      if (!valid[n]) bq[n] = 0;
+      ucol[n] = c0 + cl;
+      first_t[n] = valid[n] ? (len ? T - len[bq[n]] : 0) : T;
+      gi[n] = gf[n] = go[n] = gg[n] = cp[n] = cn[n] = dcr[n] = z;
+      if (T - 1 >= first_t[n]) {
+        const size_t row = (size_t)(T - 1) * B + bq[n];
+        const float* g = gates + row * 4 * H + ucol[n];
+        gi[n] = *reinterpret_cast<const float4*>(g);
+        gf[n] = *reinterpret_cast<const float4*>(g + H);
+        go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+        gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+        cp[n] = *reinterpret_cast<const float4*>(c + row * H + ucol[n]);
+        cn[n] = *reinterpret_cast<const float4*>(c + (row + B) * H + ucol[n]);
+        dcr[n] = *reinterpret_cast<const float4*>(dc0 + (size_t)bq[n] * ld0 + ucol[n]);
+        if (dh_above) {
+          const float4 ua = *reinterpret_cast<const float4*>(dh_above + row * H + ucol[n]);
+          const float4 mk = drop_at4(drop, (uint64_t)row * H + ucol[n]);
+          dab[n] = make_float4(ua.x * mk.x, ua.y * mk.y, ua.z * mk.z, ua.w * mk.w);
+        }
+      }
+    }
+    unsigned int red = 0;                                    // reduction rounds done so far (parity of pfull / tfull)
+    auto reduce_partials = [&](float4* out) {
+      mbar_wait(my_tfull, red & 1u);
+      tc_fence_after();
+      {
+        float acc[32];                                       // dh column (32 q + lane) x this sub-tile's 32 batch rows
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * SUBN), acc);
+        float* dst = tbuf + q * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[(size_t)j * 128] = acc[j];
+      }
+      tc_fence_before();
+      v2_bar_sync(bid, 128);                                 // the whole partial tile of this sub-tile is in shared memory
+      if (lt < 4) v3_arrive_remote(peer_pfull[lt]);          // release.cluster, cumulative over the group through the barrier
+      v3_wait_cluster(my_pfull, red & 1u);                   // all four partial tiles are complete
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        const float4 a = v3_ld_dsmem4(peer_tbuf[0] + toff[n]), b = v3_ld_dsmem4(peer_tbuf[1] + toff[n]),
+                     cc4 = v3_ld_dsmem4(peer_tbuf[2] + toff[n]), d = v3_ld_dsmem4(peer_tbuf[3] + toff[n]);
+        out[n] = make_float4((a.x + b.x) + (cc4.x + d.x), (a.y + b.y) + (cc4.y + d.y), (a.z + b.z) + (cc4.z + d.z),
+                             (a.w + b.w) + (cc4.w + d.w));
+      }
+      ++red;
+    };
+    for (int t = T - 1; t >= 0; --t) {
+      const unsigned int k = (unsigned int)(T - 1 - t);
+      float4 dhs[NI];
+      if (t < T - 1) reduce_partials(dhs);                   // dh_t from the MMAs of step t+1
+      // ---- phase A: cell backward, element-wise ----
+      float4 dai[NI], daf[NI], dao[NI], dag[NI];
+      size_t row[NI];
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        row[n] = (size_t)t * B + bq[n];
+        dai[n] = daf[n] = dao[n] = dag[n] = z;
+        if (!valid[n]) continue;
+        if (t >= first_t[n]) {
+          float4 dh = t == T - 1 ? *reinterpret_cast<const float4*>(dh0 + (size_t)bq[n] * ld0 + ucol[n]) : dhs[n];
+          dh.x += dab[n].x; dh.y += dab[n].y; dh.z += dab[n].z; dh.w += dab[n].w;
+#define LB(kk)                                                                     \
+          { float tc = v2_tanh(cn[n].kk);                                            \
+            float dct = dcr[n].kk + dh.kk * go[n].kk * (1.0f - tc * tc);             \
+            dao[n].kk = dh.kk * tc * go[n].kk * (1.0f - go[n].kk);                   \
+            dai[n].kk = dct * gg[n].kk * gi[n].kk * (1.0f - gi[n].kk);               \
+            daf[n].kk = dct * cp[n].kk * gf[n].kk * (1.0f - gf[n].kk);               \
+            dag[n].kk = dct * gi[n].kk * (1.0f - gg[n].kk * gg[n].kk);               \
+            dcr[n].kk = dct * gf[n].kk; }
+          LB(x) LB(y) LB(z) LB(w)
+#undef LB
+#define ACC4(a, b) a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          ACC4(bsi[n], dai[n]) ACC4(bsf[n], daf[n]) ACC4(bso[n], dao[n]) ACC4(bsg[n], dag[n])
+#undef ACC4
+        }
+        const float4 gsrc[4] = {dai[n], daf[n], dao[n], dag[n]};
+#pragma unroll
+        for (int gI = 0; gI < 4; ++gI) {
+          __nv_bfloat16 pl[3][4];
+          split3(gsrc[gI].x, pl[0][0], pl[1][0], pl[2][0]);
+          split3(gsrc[gI].y, pl[0][1], pl[1][1], pl[2][1]);
+          split3(gsrc[gI].z, pl[0][2], pl[1][2], pl[2][2]);
+          split3(gsrc[gI].w, pl[0][3], pl[1][3], pl[2][3]);
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            uint2 ov;
+            ov.x = (uint32_t)__bfloat16_as_ushort(pl[p][0]) | ((uint32_t)__bfloat16_as_ushort(pl[p][1]) << 16);
+            ov.y = (uint32_t)__bfloat16_as_ushort(pl[p][2]) | ((uint32_t)__bfloat16_as_ushort(pl[p][3]) << 16);
+            *reinterpret_cast<uint2*>(dap + (size_t)p * dap_plane + row[n] * 4 * H + (size_t)gI * H + ucol[n]) = ov;
+          }
+        }
+      }
+      // publish da_t of this sub-tile: the one global exchange of the step
+      fence_proxy_async();
+      v2_bar_sync(bid + 1, 128);
+      if (lt == 0) v2_arrive(myctr);
+      v2_bar_sync(bid + 2, 128);
+      if (t >= tlast) mbar_wait(my_go, k & 1u);
+      // off the critical path: the operands of step t-1
+#pragma unroll
+      for (int n = 0; n < NI; ++n) {
+        if (!valid[n]) continue;
+        if (t == 0 && dc_init) *reinterpret_cast<float4*>(dc_init + (size_t)bq[n] * H + ucol[n]) = dcr[n];
+        if (t > 0) {
+          cn[n] = cp[n];
+          if (t - 1 >= first_t[n]) {
+            const size_t rp = row[n] - B;
+            const float* g = gates + rp * 4 * H + ucol[n];
+            gi[n] = *reinterpret_cast<const float4*>(g);
+            gf[n] = *reinterpret_cast<const float4*>(g + H);
+            go[n] = *reinterpret_cast<const float4*>(g + 2 * H);
+            gg[n] = *reinterpret_cast<const float4*>(g + 3 * H);
+            cp[n] = *reinterpret_cast<const float4*>(c + rp * H + ucol[n]);
+            if (dh_above) {
+              const float4 ua = *reinterpret_cast<const float4*>(dh_above + rp * H + ucol[n]);
+              const float4 mk = drop_at4(drop, (uint64_t)rp * H + ucol[n]);
+              dab[n] = make_float4(ua.x * mk.x, ua.y * mk.y, ua.z * mk.z, ua.w * mk.w);
+            }
+          }
+        }
+      }
+    }
+    if (dh_init) {                                           // d h_{-1}: the reduction of the MMAs of step 0
+      float4 dhs[NI];
+      reduce_partials(dhs);
+#pragma unroll
+      for (int n = 0; n < NI; ++n)
+        if (valid[n]) *reinterpret_cast<float4*>(dh_init + (size_t)bq[n] * H + ucol[n]) = dhs[n];
+    }
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+      if (!valid[n]) continue;
+      float* dr = dasum + (size_t)bq[n] * 4 * H + ucol[n];
+      *reinterpret_cast<float4*>(dr) = bsi[n];
+      *reinterpret_cast<float4*>(dr + H) = bsf[n];
+      *reinterpret_cast<float4*>(dr + 2 * H) = bso[n];
+      *reinterpret_cast<float4*>(dr + 3 * H) = bsg[n];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // nobody leaves while a peer may still read its partial tile
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 __global__ void __launch_bounds__(256) v2_sum4_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -1676,6 +2009,49 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   int KBv = KB;
   static int use_v3 = -1;
   if (use_v3 < 0) { const char* e = getenv("NVQA_LSTM_V3"); use_v3 = e ? atoi(e) : 1; }
+  // generation 4 (NVQA_LSTM_BWD_SPLIT, default on): generation 3 + two software-pipelined 32-row sub-tiles per CTA
+  static int use_v4 = -1;
+  if (use_v4 < 0) { const char* e = getenv("NVQA_LSTM_BWD_SPLIT"); use_v4 = e ? atoi(e) : 1; }
+  if (use_v4 && use_v3 && P == 2 && !getenv("NVQA_LSTM_DEBUG") && !getenv("NVQA_LSTM_POLL1") && !getenv("NVQA_LSTM_STACK")) {
+    static int poll_ns4 = -1;
+    if (poll_ns4 < 0) { const char* e = getenv("NVQA_LSTM_POLL_NS"); poll_ns4 = e ? atoi(e) & 0x7FFF : 64; }
+    const size_t smem4 = (size_t)KB * 16384 + 4 * 16384 + 2 * 16384 + 1024 + 256;
+    bool ok4 = smem4 <= (size_t)max_smem;
+    CUtensorMap mapDA4s;
+    if (ok4) NVQA_TRY(get_map_kb(ws, dap, T * B, 4 * H, P, 32, 2, &mapDA4s, dap_plane_rows * 4 * H));
+    const void* f4 = (const void*)lstm_bwd_v4_kernel<2>;
+    if (ok4) NVQA_CUDA(cudaFuncSetAttribute(f4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    const __nv_bfloat16* wt4 = wp;                 // plane 0 in TMEM, plane 1 in shared memory
+    for (int tile0 = 0; tile0 < tiles && ok4; tile0 += max_tiles) {
+      int b0 = tile0 * 64, bend = std::min(B, (tile0 + max_tiles) * 64);
+      dim3 grid(H / 128, 4, ceil_div(bend - b0, 64));
+      NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.z, s));
+      void* a4[] = {&mapW, &wt4, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dh_init, &dc_init,
+                    &len, &T, &B, &H, &KBv, &counter, &poll_ns4, &b0, &bend, &mapDA4s};
+      cudaLaunchConfig_t cfg4 = {};
+      cfg4.gridDim = grid; cfg4.blockDim = dim3(V2_THREADS); cfg4.dynamicSmemBytes = smem4; cfg4.stream = s;
+      cudaLaunchAttribute at4[2];
+      at4[0].id = cudaLaunchAttributeClusterDimension;
+      at4[0].val.clusterDim.x = 1; at4[0].val.clusterDim.y = 4; at4[0].val.clusterDim.z = 1;
+      at4[1].id = cudaLaunchAttributeCooperative; at4[1].val.cooperative = 1;
+      cfg4.attrs = at4; cfg4.numAttrs = v2_nocoop() ? 1 : 2;
+      cudaError_t le = cudaLaunchKernelExC(&cfg4, f4, a4);
+      if (le != cudaSuccess && cfg4.numAttrs == 2) {
+        (void)cudaGetLastError();
+        cfg4.numAttrs = 1;
+        le = cudaLaunchKernelExC(&cfg4, f4, a4);
+      }
+      if (le != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (tile0 > 0) { set_error("lstm_bwd_v4: cluster launch failed in the middle of a batch"); return 1; }
+        ok4 = false;
+        break;
+      }
+      ++g_launches;
+    }
+    if (ok4) return 0;
+    use_v4 = 0;
+  }
   if (use_v3) {
     // generation 3: 4-CTA clusters over the K-splits, split-K reduction through distributed shared memory;
     // batches of more than 8 tiles (512 rows) run as consecutive windows, each a full persistent launch
