@@ -1489,7 +1489,11 @@ lstm_bwd_v3_kernel(const __grid_constant__ CUtensorMap mapDA, const __grid_const
 // reduction / cell backward / publish / barrier round (two thirds of a step's chain), sub-tile 1's da tile is loaded and
 // multiplied, and vice versa.  Thread items of a sub-tile group (128 threads): rows 8 ks + (lt + 128 n) / 32 of the
 // sub-tile, columns 4 ((lt + 128 n) % 32) .. + 3, n = 0, 1.
-template <int P>
+// STK: W0 . da0 and W0 . da1 as ONE instruction with N = 64 (the two planes of a k-block stage are one contiguous K-major B
+// tile of 64 rows); accumulator columns [64 s, 64 s + 32) then hold W0 . da0 + W1 . da0, [64 s + 32, 64 s + 64) W0 . da1,
+// summed by the epilogue.  Two instead of three instructions per k-step: with two sub-tiles the MMA warp is the busiest
+// unit of the kernel (tools/probes/probe_mma_rate.cu: TS N = 64 costs 62.9 cycles, TS N = 32 51.8, SS N = 32 80.0).
+template <int P, bool STK>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 lstm_bwd_v4_kernel(const __grid_constant__ CUtensorMap mapW, const __nv_bfloat16* __restrict__ w1, int w_pitch,
                    const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ dh0,
@@ -1580,6 +1584,8 @@ lstm_bwd_v4_kernel(const __grid_constant__ CUtensorMap mapW, const __nv_bfloat16
     // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
     constexpr uint32_t idesc = make_idesc_bf16(128, SUBN, true, false);       // A = W_hh^T slice in SMEM, MN-major
     constexpr uint32_t idesc_ts = make_idesc_bf16(128, SUBN, false, false);   // A from TMEM is K-major by construction
+    constexpr uint32_t idesc_ts2 = make_idesc_bf16(128, 2 * SUBN, false, false);
+    constexpr int ACCW = STK ? 2 * SUBN : SUBN;                               // accumulator columns per sub-tile
     if (lane == 0) {
       mbar_wait(wfull, 0);
       mbar_wait(w1bar, 0);
@@ -1591,7 +1597,7 @@ lstm_bwd_v4_kernel(const __grid_constant__ CUtensorMap mapW, const __nv_bfloat16
     for (int t = T - 1; t >= tlast; --t) {
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
-        const uint32_t tacc = tmem_base + (uint32_t)(sub * SUBN);
+        const uint32_t tacc = tmem_base + (uint32_t)(sub * ACCW);
         for (int hb = 0; hb < KB / KBB; ++hb, ++it) {
           const int bs = it % NBS;
           const uint32_t ph = (uint32_t)(it / NBS) & 1u;
@@ -1608,9 +1614,14 @@ lstm_bwd_v4_kernel(const __grid_constant__ CUtensorMap mapW, const __nv_bfloat16
                 const uint64_t dw = dwk + (uint64_t)(kk * (2048 >> 4)), d0 = ddk + (uint64_t)(kk * 2);
                 const uint64_t d1 = d0 + (uint64_t)(B_PLANE >> 4);
                 const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + kk * 8);
-                umma_f16(tacc, dw, d0, idesc, (kb | kk) ? 1u : 0u);   // W1 . da0
-                umma_f16_ts(tacc, wt, d1, idesc_ts, 1u);              // W0 . da1
-                umma_f16_ts(tacc, wt, d0, idesc_ts, 1u);              // W0 . da0
+                if (STK) {
+                  umma_f16_ts(tacc, wt, d0, idesc_ts2, (kb | kk) ? 1u : 0u);   // W0 . [da0 ; da1]
+                  umma_f16(tacc, dw, d0, idesc, 1u);                           // W1 . da0  += columns [0, 32)
+                } else {
+                  umma_f16(tacc, dw, d0, idesc, (kb | kk) ? 1u : 0u);   // W1 . da0
+                  umma_f16_ts(tacc, wt, d1, idesc_ts, 1u);              // W0 . da1
+                  umma_f16_ts(tacc, wt, d0, idesc_ts, 1u);              // W0 . da0
+                }
               }
             }
             umma_commit(empty0 + 8 * bs);
@@ -1695,7 +1706,13 @@ lstm_bwd_v4_kernel(const __grid_constant__ CUtensorMap mapW, const __nv_bfloat16
       tc_fence_after();
       {
         float acc[32];                                       // dh column (32 q + lane) x this sub-tile's 32 batch rows
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * SUBN), acc);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * (STK ? 2 * SUBN : SUBN)), acc);
+        if (STK) {
+          float a1[32];                                      // the W0 . da1 half of the stacked product
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 2 * SUBN + SUBN), a1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += a1[j];
+        }
         float* dst = tbuf + q * 32 + lane;
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[(size_t)j * 128] = acc[j];
@@ -2012,14 +2029,19 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   // generation 4 (NVQA_LSTM_BWD_SPLIT, default on): generation 3 + two software-pipelined 32-row sub-tiles per CTA
   static int use_v4 = -1;
   if (use_v4 < 0) { const char* e = getenv("NVQA_LSTM_BWD_SPLIT"); use_v4 = e ? atoi(e) : 1; }
-  if (use_v4 && use_v3 && P == 2 && !getenv("NVQA_LSTM_DEBUG") && !getenv("NVQA_LSTM_POLL1") && !getenv("NVQA_LSTM_STACK")) {
+  if (use_v4 && use_v3 && P == 2 && !getenv("NVQA_LSTM_DEBUG") && !getenv("NVQA_LSTM_POLL1")) {
     static int poll_ns4 = -1;
     if (poll_ns4 < 0) { const char* e = getenv("NVQA_LSTM_POLL_NS"); poll_ns4 = e ? atoi(e) & 0x7FFF : 64; }
     const size_t smem4 = (size_t)KB * 16384 + 4 * 16384 + 2 * 16384 + 1024 + 256;
     bool ok4 = smem4 <= (size_t)max_smem;
     CUtensorMap mapDA4s;
     if (ok4) NVQA_TRY(get_map_kb(ws, dap, T * B, 4 * H, P, 32, 2, &mapDA4s, dap_plane_rows * 4 * H));
-    const void* f4 = (const void*)lstm_bwd_v4_kernel<2>;
+    // NVQA_LSTM_BWD_STACK=1: N-stacked W0 . [da0 ; da1] instructions in generation 4.  Measured on B200 (round 2):
+    // 0.528 instead of 0.430 ms per step pair -- correct, but the N = 64 TS and N = 32 SS instructions into overlapping
+    // accumulator columns run slower than three independent N = 32 instructions.  Default off.
+    static int stack4 = -1;
+    if (stack4 < 0) { const char* e = getenv("NVQA_LSTM_BWD_STACK"); stack4 = e ? atoi(e) : 0; }
+    const void* f4 = stack4 ? (const void*)lstm_bwd_v4_kernel<2, true> : (const void*)lstm_bwd_v4_kernel<2, false>;
     if (ok4) NVQA_CUDA(cudaFuncSetAttribute(f4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
     const __nv_bfloat16* wt4 = wp;                 // plane 0 in TMEM, plane 1 in shared memory
     for (int tile0 = 0; tile0 < tiles && ok4; tile0 += max_tiles) {
