@@ -163,7 +163,10 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
                    float* __restrict__ h, __nv_bfloat16* __restrict__ hp, long long hp_plane, float* __restrict__ xdrop,
                    const int32_t* __restrict__ len, Drop drop, int T, int B, int H, int KB, unsigned int* counter, int dbg_arg,
                    int b0, int bend, const __grid_constant__ CUtensorMap mapH4, __nv_bfloat16* __restrict__ xdp,
-                   long long xdp_plane) {
+                   long long xdp_plane, const __nv_bfloat16* __restrict__ w1b, int kb_tm) {
+  // w1b / kb_tm (pair + 4-D box kernel): the other plane of the W slice (the one that otherwise only lives in shared
+  // memory) ALSO sits in tensor memory for the first kb_tm k-blocks, in the 192 columns the accumulators and plane 0 leave
+  // free ([64, 256)): its product becomes a TS instruction too (pair mode, N = 32: 29.6 instead of 62.6 cycles).
   static_assert(!BOX4 || PAIR, "4-D boxes are wired into the pair kernel only");
   static_assert(!POLL1 || NS == 2, "the single-poller barriers are numbered for the sub-tile kernel");
   constexpr int KBB = 4;                                // BOX4: k-blocks per TMA box (a "big stage" = KBB ring stages)
@@ -336,7 +339,8 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
               for (int k = 0; k < 4; ++k) {
                 const uint64_t dw = dwk + (uint64_t)(k * 2), dh0 = dhk + (uint64_t)(k * 2), dh1 = dh0 + (uint64_t)(B_PLANE >> 4);
                 const uint32_t wt = tmem_base + W1_COL + (uint32_t)(kb * 32 + k * 8);
-                p2_umma_f16(tacc, dw, dh0, idesc, (kb | k) ? 1u : 0u);
+                if (kb < kb_tm) p2_umma_f16_ts(tacc, tmem_base + 64u + (uint32_t)(kb * 32 + k * 8), dh0, idesc, (kb | k) ? 1u : 0u);
+                else p2_umma_f16(tacc, dw, dh0, idesc, (kb | k) ? 1u : 0u);
                 p2_umma_f16_ts(tacc, wt, dh1, idesc, 1u);
                 p2_umma_f16_ts(tacc, wt, dh0, idesc, 1u);
               }
@@ -429,6 +433,22 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
           wv[4 * v] = x.x; wv[4 * v + 1] = x.y; wv[4 * v + 2] = x.z; wv[4 * v + 3] = x.w;
         }
         tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + W1_COL + (uint32_t)(128 * ch + 32 * blk), wv);
+      }
+      if (BOX4 && w1b != nullptr) {
+        // the first kb_tm k-blocks of the other plane -> TMEM columns [64, 64 + 32 kb_tm)
+        const __nv_bfloat16* srcb = w1b + (size_t)(q * H + u0 + lane) * w_pitch + 256 * ch;
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) {
+          const int kbi = 4 * ch + blk;
+          if (kbi >= kb_tm) break;
+          uint32_t wv[32];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const uint4 x = *reinterpret_cast<const uint4*>(srcb + blk * 64 + v * 8);
+            wv[4 * v] = x.x; wv[4 * v + 1] = x.y; wv[4 * v + 2] = x.z; wv[4 * v + 3] = x.w;
+          }
+          tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + 64u + (uint32_t)(32 * kbi), wv);
+        }
       }
       tc_fence_before();
     }
@@ -1917,8 +1937,15 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     int b0 = tile0 * 64, bend = std::min(B, (tile0 + max_tiles) * 64);
     dim3 grid(H / 32, ceil_div(bend - b0, 64));
     NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
+    // NVQA_LSTM_W1TMEM=<n <= 6>: k-blocks of the shared-memory plane that also sit in tensor memory (pair + 4-D box kernel).
+    // Measured on B200 (round 2): 0.384 (6) / 0.387 (4) against 0.376 ms (0) per step pair -- the 24 cheaper instructions of
+    // a step do not shorten its chain (the MMA phase is not what the forward step waits for).  Default 0.
+    static int w1tm = -1;
+    if (w1tm < 0) { const char* e = getenv("NVQA_LSTM_W1TMEM"); w1tm = e ? std::min(6, std::max(0, atoi(e))) : 0; }
+    int kb_tm = (use_pair && box4 && P == 2) ? w1tm : 0;
+    const __nv_bfloat16* w1b = kb_tm > 0 ? wp + (size_t)4 * H * pitch : nullptr;     // plane 1
     void* args[] = {&mapH, &mapW, &w1, &pitch, &pre, &c, &h, &hp, &hp_plane, &xdrop_next, &len, &d, &T, &B, &H, &KBv, &counter, &dbgv,
-                    &b0, &bend, &mapH4, &xdrop_planes, &xdrop_plane_stride};
+                    &b0, &bend, &mapH4, &xdrop_planes, &xdrop_plane_stride, &w1b, &kb_tm};
     if (use_cl && !split && grid.x == 16) {
       // one 16-CTA cluster per batch tile: hardware cluster barrier per step, plain (non-cooperative) launch
       const void* fc = P == 2 ? (const void*)lstm_fwd_v2_kernel<2, true, 1, false, false> : (const void*)lstm_fwd_v2_kernel<1, true, 1, false, false>;
