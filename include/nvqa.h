@@ -164,6 +164,10 @@ int nvqa_state_get(nvqa_model* m, float* host_dst);              /* final LSTM s
 /* JdJ + clamp + rmsprop from HOST buffers: H2D copies, all kernels, D2H of the loss. */
 int nvqa_train_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
                          const int32_t* labels, int32_t B, float lr, uint64_t seed, float* loss_out);
+/* the same on the batch already set (nvqa_set_batch / nvqa_set_batch_host): nvqa_forward(TRAIN, seed) ; nvqa_backward(ALL) ;
+ * clamp + optimizer with the reference's constants.  Knowing lr up front, the multimodal block's update follows its weight
+ * gradients on the side stream beside the LSTM backward (same result as the three separate calls). */
+int nvqa_train_step(nvqa_model* m, float lr, uint64_t seed);
 /* forward() + argmax from HOST buffers */
 int nvqa_eval_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
                         int32_t B, int32_t* answers_out);

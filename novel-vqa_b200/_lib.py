@@ -60,6 +60,7 @@ SIGNATURES = {
     "nvqa_state_get": (C.c_int, [C.c_void_p, c_f32p]),
     "nvqa_train_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_float, C.c_uint64, c_f32p]),
+    "nvqa_train_step": (C.c_int, [C.c_void_p, C.c_float, C.c_uint64]),
     "nvqa_eval_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "nvqa_lstm_cell_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "nvqa_axb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -264,6 +264,10 @@ class Arch1Model:
     def sync(self):
         _lib.check(self.lib.nvqa_sync(self.handle))
 
+    def train_step(self, lr, seed):
+        """JdJ + clamp + optimizer on the batch already set (device-resident twin of train_step_host)."""
+        _lib.check(self.lib.nvqa_train_step(self.handle, lr, seed))
+
     # ---- fused convenience (host buffers in, scalar out) ----
     def train_step_host(self, q_ra, lengths, fc7, labels, lr, seed):
         out = C.c_float(0)

@@ -1018,6 +1018,14 @@ int aux_launch_bwd(nvqa_model* m, bool to_side) {
     NVQA_TRY(colsum(m->stream, m->dqpre, B, C, C, m->gbq, nullptr));
     NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, I, B, m->dipre, C, m->vd, I, m->gWv, I, false));
     NVQA_TRY(colsum(m->stream, m->dipre, B, C, C, m->gbv, nullptr));
+    if (side && m->side_opt.armed) {
+      // the multimodal block is final and its weights are not read again in this step: clamp + RMSprop right here,
+      // beside the LSTM backward (nvqa_train_step)
+      const int64_t o2 = m->off_blk[NVQA_BLOCK_MULTIMODAL], n2 = m->off_blk[3] - o2;
+      NVQA_TRY(clamp_rmsprop(m->stream, m->params + o2, m->grads + o2, m->rms + o2, n2, m->side_opt.lr, m->side_opt.alpha,
+                             m->side_opt.eps, m->side_opt.wd, m->side_opt.clamp, m->side_opt.gscale));
+      m->side_opt_done = true;
+    }
     if (side) NVQA_CUDA(cudaEventRecord(m->aux_join, m->stream));
   }
   m->aux_bwd_inflight = side;
@@ -1169,6 +1177,13 @@ extern "C" int nvqa_rmsprop_step(nvqa_model* m, float lr, float alpha, float eps
   umma_workspace_invalidate(m->ws);     // the weights change: their cached bf16 planes are stale
   ProfScope ps(m, CAT_OPT, 0);
   NVQA_TRY(drop_lookup_grad(m));
+  if (m->side_opt_done) {
+    // nvqa_train_step already updated the multimodal block on the side stream: encoder + embedding remain
+    m->side_opt_done = false;
+    const int64_t n01 = m->off_blk[2];
+    return clamp_rmsprop(m->stream, m->params, m->grads, m->rms, n01, lr, alpha, eps, wd, clamp,
+                         gscale * (m->cfg.arch == 1 ? m->lr_scale : 1.0f));
+  }
   if (m->cfg.arch == 1 && m->lr_scale != 1.0f) {
     // gradients = join{encoder_dw * lr_scale, embedding_dw * lr_scale, multimodal_dw}, then clamp, then rmsprop
     // (003_train_ae_based_wp.lua:344-346): the scale is folded into the pre-clamp gradient scale of blocks 0 and 1
@@ -1251,22 +1266,40 @@ extern "C" int nvqa_state_get(nvqa_model* m, float* dst) {
 }
 
 // ---- fused convenience -----------------------------------------------------------------------------
+// JdJ + clamp + optimizer on the batch already set (nvqa_set_batch*), with the reference's optimizer constants.  Same result
+// as nvqa_forward ; nvqa_backward(ALL) ; nvqa_rmsprop_step -- but knowing the learning rate up front lets the multimodal
+// block's clamp + RMSprop follow its weight gradients on the side stream, beside the LSTM backward.
+extern "C" int nvqa_train_step(nvqa_model* m, float lr, uint64_t seed) {
+  NVQA_CHECK(m, "null model");
+  NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
+  if (m->cfg.arch == 3) {
+    NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
+    // grad_clip 0.1, weight_decay 1e-6, adam(alpha .8, beta .999, eps 1e-8)  (001_train_arch1_text_autoencoder.lua:35,40-45,237-243)
+    return nvqa_adam_step(m, lr, 0.8f, 0.999f, 1e-8f, 1e-6f, 0.1f, 1.f);
+  }
+  // clamp(-10,10) (:329) and optim.rmsprop defaults alpha=.99, eps=1e-8 (:408)
+  // arch2 trains with optimize.weightDecay = 1e-4 (003_train_vqa_arch2/002_train_baseline.lua:197)
+  const float wd = m->cfg.arch == 2 ? 1e-4f : 0.f;
+  static int side_opt = -1;
+  if (side_opt < 0) { const char* e = getenv("NVQA_SIDE_OPT"); side_opt = e ? atoi(e) : 1; }
+  m->side_opt_done = false;
+  if (side_opt && m->cfg.arch == 1 && aux_usable(m) && m->use_persistent) {
+    m->side_opt.armed = true;
+    m->side_opt.lr = lr; m->side_opt.alpha = 0.99f; m->side_opt.eps = 1e-8f; m->side_opt.wd = wd; m->side_opt.clamp = 10.f;
+    m->side_opt.gscale = 1.f;
+  }
+  const int rc = nvqa_backward(m, NVQA_PHASE_ALL);
+  m->side_opt.armed = false;
+  NVQA_TRY(rc);
+  return nvqa_rmsprop_step(m, lr, 0.99f, 1e-8f, wd, 10.f, 1.f);
+}
+
 extern "C" int nvqa_train_step_host(nvqa_model* m, const int32_t* q, const int32_t* len, const float* fc7,
                                     const int32_t* labels, int32_t B, float lr, uint64_t seed, float* loss_out) {
   NVQA_CHECK(m, "null model");
   NVQA_CHECK(labels || m->cfg.arch == 3, "labels required");
   NVQA_TRY(nvqa_set_batch_host(m, q, len, fc7, labels, B));
-  NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
-  NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
-  if (m->cfg.arch == 3) {
-    // grad_clip 0.1, weight_decay 1e-6, adam(alpha .8, beta .999, eps 1e-8)  (001_train_arch1_text_autoencoder.lua:35,40-45,237-243)
-    NVQA_TRY(nvqa_adam_step(m, lr, 0.8f, 0.999f, 1e-8f, 1e-6f, 0.1f, 1.f));
-    if (loss_out) NVQA_TRY(nvqa_loss(m, loss_out));
-    return 0;
-  }
-  // clamp(-10,10) (:329) and optim.rmsprop defaults alpha=.99, eps=1e-8 (:408)
-  // arch2 trains with optimize.weightDecay = 1e-4 (003_train_vqa_arch2/002_train_baseline.lua:197)
-  NVQA_TRY(nvqa_rmsprop_step(m, lr, 0.99f, 1e-8f, m->cfg.arch == 2 ? 1e-4f : 0.f, 10.f, 1.f));
+  NVQA_TRY(nvqa_train_step(m, lr, seed));
   if (loss_out) NVQA_TRY(nvqa_loss(m, loss_out));
   return 0;
 }

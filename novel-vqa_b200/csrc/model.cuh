@@ -119,6 +119,10 @@ struct nvqa_model {
   bool aux_fwd = false, aux_bwd = false, aux_fwd_inflight = false, aux_bwd_inflight = false;
   int aux_enabled = -1;              // NVQA_AUX_STREAM (default 1); 0: everything on the main stream
   bool defer_head = false;           // the head backward may leave the AxB weight gradients to the side stream
+  // nvqa_train_step: the multimodal block's clamp + RMSprop follows its weight gradients on the side stream (none of its
+  // weights is read again in the step); side_opt_done: that happened, nvqa_rmsprop_step skips the block once
+  struct { bool armed = false; float lr = 0, alpha = 0, eps = 0, wd = 0, clamp = 0, gscale = 1; } side_opt;
+  bool side_opt_done = false;
   std::vector<void*> dp_opened;      // cudaIpcOpenMemHandle mappings to close
   bool profiling = false;
   ProfCat prof[CAT_COUNT];

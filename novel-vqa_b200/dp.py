@@ -71,7 +71,10 @@ def backward_allreduce(model, views, dist, world, bind=True):
 def train_step(model, views, dist, world, lr, seed, bind=True):
     """JdJ + all-reduce + clamp + RMSprop on an already-set batch (NCCL path: bucketed all-reduce overlapped with the
     backward phases, then the replicated optimizer kernel)."""
-    if world > 1 and bind:
+    if world == 1:
+        model.train_step(lr, seed)         # single GPU: the library's own fused step (nvqa_train_step)
+        return
+    if bind:
         bind_current_stream(model)
     model.forward(api.MODE_TRAIN, seed)
     backward_allreduce(model, views, dist, world, bind)
