@@ -594,6 +594,8 @@ static PlaneOut producer_planes(nvqa_model* m, const float* src, int rows, int K
   return po;
 }
 
+static int presplit_step_weights(nvqa_model* m, int part = 0);
+
 // ---- side stream (see model.cuh) ---------------------------------------------------------------------------------
 // Routes everything enqueued through m->stream to the side stream for the lifetime of the object; GEMMs then take their
 // transients from the side arena of the workspace and run with a capped persistent grid.
@@ -629,6 +631,7 @@ static int aux_launch_fwd(nvqa_model* m, bool to_side) {
   }
   {
     AuxScope as(m, side);
+    NVQA_TRY(presplit_step_weights(m, 2));     // Wq, Wi, Wc planes: needed by the head only
     {
       ProfScope ps(m, CAT_PW_FWD, 0);
       NVQA_TRY(join_fc7_copy(m));
@@ -815,20 +818,23 @@ static int forward_arch3(nvqa_model* m) {
 }
 
 // Every weight matrix a training / eval step multiplies with, for the one-launch plane split at the start of a forward.
-static int presplit_step_weights(nvqa_model* m) {
+// part: 0 = all, 1 = everything but arch 1's multimodal weights, 2 = only those (arch 1: they are first needed after the
+// LSTM forward, so their split rides on the side stream with the image branch)
+static int presplit_step_weights(nvqa_model* m, int part) {
   if (!m->planes || !m->ws) return 0;
   const nvqa_config& c = m->cfg;
   const float* src[16]; int rows[16], K[16], n = 0;
   auto add = [&](const float* p, int r, int k) { if (p && n < 16) { src[n] = p; rows[n] = r; K[n] = k; ++n; } };
-  for (int l = 0; l < c.L; ++l) { add(m->lw[l].Wi, 4 * c.H, l == 0 ? c.E : c.H); add(m->lw[l].Wh, 4 * c.H, c.H); }
-  if (c.arch == 3) {
-    for (int l = 0; l < c.L; ++l) { add(m->lw2[l].Wi, 4 * c.H, l == 0 ? c.E : c.H); add(m->lw2[l].Wh, 4 * c.H, c.H); }
-    add(m->Wd, c.V + 1, c.H);
-  } else if (c.arch == 2) {
-    add(m->Wcnn, c.E, c.I); add(m->Wc, c.O, c.H);
-  } else {
-    add(m->Wq, c.C, m->S); add(m->Wv, c.C, c.I); add(m->Wc, c.O, c.C);
+  if (part != 2) {
+    for (int l = 0; l < c.L; ++l) { add(m->lw[l].Wi, 4 * c.H, l == 0 ? c.E : c.H); add(m->lw[l].Wh, 4 * c.H, c.H); }
+    if (c.arch == 3) {
+      for (int l = 0; l < c.L; ++l) { add(m->lw2[l].Wi, 4 * c.H, l == 0 ? c.E : c.H); add(m->lw2[l].Wh, 4 * c.H, c.H); }
+      add(m->Wd, c.V + 1, c.H);
+    } else if (c.arch == 2) {
+      add(m->Wcnn, c.E, c.I); add(m->Wc, c.O, c.H);
+    }
   }
+  if (c.arch == 1 && part != 1) { add(m->Wq, c.C, m->S); add(m->Wv, c.C, c.I); add(m->Wc, c.O, c.C); }
   return presplit_weights(m->ws, m->stream, m->planes, src, rows, K, n);
 }
 
@@ -838,7 +844,9 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   m->mode = mode; m->seed = seed;
   umma_workspace_new_forward(m->ws);        // this forward rewrites the activations: their cached planes are stale
-  NVQA_TRY(presplit_step_weights(m));       // all weight matrices -> bf16 planes in one launch (no-op while they are cached)
+  // weight matrices -> bf16 planes in one launch (no-op while they are cached); arch 1's multimodal weights follow on the
+  // side stream (aux_launch_fwd)
+  NVQA_TRY(presplit_step_weights(m, m->cfg.arch == 1 ? 1 : 0));
   if (m->cfg.arch == 3) return forward_arch3(m);
   if (m->cfg.arch == 2) return forward_arch2(m);
   const nvqa_config& c = m->cfg;
@@ -862,11 +870,11 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(qvec_fwd(s, cf, hf, m->state, m->qd, make_drop(m, m->mk_q, STREAM_AXB_Q), B, H, L, producer_planes(m, m->qd, B, S)));
   }
-  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
-  // the image branch (fc7 norm + Dropout + Linear(I, C)) was launched on the side stream beside the recurrent kernels
-  // (aux_launch_fwd, hooked in lstm_layers_forward), or runs here if no persistent kernel did
+  // the image branch (head weight planes, fc7 norm + Dropout + Linear(I, C)) was launched on the side stream beside the
+  // recurrent kernels (aux_launch_fwd, hooked in lstm_layers_forward), or runs here if no persistent kernel did
   NVQA_TRY(aux_launch_fwd(m, false));
   NVQA_TRY(aux_join_main(m));
+  NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, B, c.C, S, m->qd, S, m->Wq, S, m->qc, c.C, false, m->bq));
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(fuse_fwd(s, m->qc, m->ic, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, c.C, m->fusion_skip,
