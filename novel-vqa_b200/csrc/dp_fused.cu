@@ -85,28 +85,47 @@ dp_fused_rmsprop_kernel(DpPeers p, float* __restrict__ rms, unsigned int* my_fla
   }
   if ((int)threadIdx.x < world) spin_until(ready + threadIdx.x, 2 * step + 1, timeout_ns, my_flags + DP_ERR);
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = (lo4 + i) * 4;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  // U items per thread and iteration with all their loads issued before the first use: the side-stream launch has only a
+  // handful of CTAs and every load crosses NVLink (~2 us), so a thread must keep U x world loads in flight (one item per
+  // iteration made the 2-GPU exchange of the multimodal block 224 dependent round trips long: measured +0.1 ms per step)
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+    float4 g[U], xv[U], mv[U];
 #pragma unroll
-    for (int r = 0; r < DP_MAX; ++r) {
-      if (r < world) {
-        const float4 v = ld_peer(p.g[r] + e);
-        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4) {
+        const long long e = (lo4 + i) * 4;
+#pragma unroll
+        for (int r = 0; r < DP_MAX; ++r) {
+          if (r < world) {
+            const float4 v = ld_peer(p.g[r] + e);
+            g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
+          }
+        }
+        xv[u] = *reinterpret_cast<const float4*>(p.x[rank] + e);
+        mv[u] = *reinterpret_cast<const float4*>(rms + e);
       }
     }
-    float4 xv = *reinterpret_cast<const float4*>(p.x[rank] + e), mv = *reinterpret_cast<const float4*>(rms + e);
-#define UP(k)                                                    \
-    { float gg = fminf(fmaxf(g.k * gscale, -clampv), clampv);    \
-      gg += wd * xv.k;                                           \
-      mv.k = alpha * mv.k + oma * gg * gg;                       \
-      xv.k -= lr * (gg / (sqrtf(mv.k) + eps)); }
-    UP(x) UP(y) UP(z) UP(w)
-#undef UP
-    *reinterpret_cast<float4*>(rms + e) = mv;
 #pragma unroll
-    for (int r = 0; r < DP_MAX; ++r)
-      if (r < world) *reinterpret_cast<float4*>(p.x[r] + e) = xv;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n4) continue;
+      const long long e = (lo4 + i) * 4;
+#define UP(k)                                                       \
+      { float gg = fminf(fmaxf(g[u].k * gscale, -clampv), clampv);  \
+        gg += wd * xv[u].k;                                         \
+        mv[u].k = alpha * mv[u].k + oma * gg * gg;                  \
+        xv[u].k -= lr * (gg / (sqrtf(mv[u].k) + eps)); }
+      UP(x) UP(y) UP(z) UP(w)
+#undef UP
+      *reinterpret_cast<float4*>(rms + e) = mv[u];
+#pragma unroll
+      for (int r = 0; r < DP_MAX; ++r)
+        if (r < world) *reinterpret_cast<float4*>(p.x[r] + e) = xv[u];
+    }
   }
   __threadfence_system();
   __syncthreads();
@@ -235,7 +254,9 @@ static int dp_range(nvqa_model* m, int blk0, int blk1, float lr, float alpha, fl
   cudaStream_t s = side ? m->aux_stream : m->stream;
   static int side_ctas = -1;
   if (side_ctas < 0) { const char* e = getenv("NVQA_DP_SIDE_CTAS"); side_ctas = e ? std::max(1, atoi(e)) : 16; }
-  const int full = std::max(1, std::min(ceil_div(n4, 256), 148 * 8));
+  static int main_ctas = -1;
+  if (main_ctas < 0) { const char* e = getenv("NVQA_DP_MAIN_CTAS"); main_ctas = e ? std::max(1, atoi(e)) : 148 * 8; }
+  const int full = std::max(1, std::min(ceil_div(n4, 256), main_ctas));
   const int grid = side ? std::min(full, side_ctas) : full;
   const size_t smem = side ? 64 * 1024 : 0;
   static bool attr_set = false;
@@ -292,8 +313,11 @@ extern "C" int nvqa_dp_rmsprop_step(nvqa_model* m, float lr, float alpha, float 
 extern "C" int nvqa_dp_train_step(nvqa_model* m, float lr, uint64_t seed, float alpha, float eps, float wd, float clamp) {
   NVQA_CHECK(m && m->dp_world >= 1, "nvqa_dp_train_step: not connected (nvqa_dp_export / nvqa_dp_connect)");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
-  static int overlap = -1;
-  if (overlap < 0) { const char* e = getenv("NVQA_DP_OVERLAP"); overlap = e ? atoi(e) : 1; }
+  // overlapping the multimodal exchange pays from 4 ranks on (B200, round 2: 8 ranks 1.777 -> 1.691 ms); with 2 ranks the
+  // 16-CTA side kernel is slower than the tail kernel it saves (1.622 -> 1.645 ms), so the default is by world size
+  static int overlap_env = -2;
+  if (overlap_env == -2) { const char* e = getenv("NVQA_DP_OVERLAP"); overlap_env = e ? atoi(e) : -1; }
+  const int overlap = overlap_env >= 0 ? overlap_env : (m->dp_world >= 4 ? 1 : 0);
   NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
   if (m->cfg.arch != 1 || !overlap || m->profiling) {
     NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
