@@ -5,7 +5,10 @@
 //
 // Row layout of the step buffers: rows [0, tmax*B) are the encoder steps, rows [tmax*B, (2*tmax+1)*B) the decoder steps
 // (time-major [t][b]); seq is [B x T], zero-padded on the right.
+#include <algorithm>
+
 #include "pointwise.cuh"
+#include "umma_ptx.cuh"
 
 namespace nvqa {
 
@@ -63,6 +66,7 @@ ae_embed_bwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ y
   bool dec; int64_t mrow;
   const int tok = ae_token(seq, n, B, T, V, tmax, &dec, &mrow);
   const float4 g = LD4(dx + n * E + e), yy = LD4(y + n * E + e), m = drop_at4(dec ? ddec : denc, (uint64_t)mrow * E + e);
+  if (tok == 1 || tok == V + 1) return;          // the two HOT rows are summed by ae_embed_bwd_hot_kernel
   float* dst = dtable + (int64_t)(tok - 1) * E + e;
   atomicAdd(dst + 0, g.x * (1.0f - yy.x * yy.x) * m.x);
   atomicAdd(dst + 1, g.y * (1.0f - yy.y * yy.y) * m.y);
@@ -70,10 +74,51 @@ ae_embed_bwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ y
   atomicAdd(dst + 3, g.w * (1.0f - yy.w * yy.w) * m.w);
 }
 
+// Token 1 (every null position is fed as token 1, :258-266: ~37 % of the positions of a book-corpus batch) and the START
+// token V + 1 (all B rows of the first decoder step) are the targets of thousands of scatter-adds each: as atomics they
+// serialise on E addresses (measured: the scatter kernel took 570 us at config 5, the rest of the vocabulary ~50 us).  Their
+// gradient rows are column sums over the rows that feed them: CTA = 32 columns x 8 row lanes over a chunk of rows, one
+// atomic per (column, chunk, hot token).
+__global__ void __launch_bounds__(256)
+ae_embed_bwd_hot_kernel(const int32_t* __restrict__ seq, const float* __restrict__ y, const float* __restrict__ dx,
+                        float* __restrict__ dtable, Drop denc, Drop ddec, int B, int T, int E, int V, int tmax,
+                        int rows_per_chunk) {
+  __shared__ float red[2][8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+  const int64_t rows = (int64_t)(2 * tmax + 1) * B;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float a1 = 0.f, as = 0.f;
+  if (c < E) {
+    for (int64_t n = r0 + ry; n < r1; n += 8) {
+      bool dec; int64_t mrow;
+      const int tok = ae_token(seq, n, B, T, V, tmax, &dec, &mrow);
+      if (tok != 1 && tok != V + 1) continue;
+      const float g = dx[n * E + c], yy = y[n * E + c], m = drop_at(dec ? ddec : denc, (uint64_t)mrow * E + c);
+      const float v = g * (1.0f - yy * yy) * m;
+      if (tok == 1) a1 += v; else as += v;
+    }
+  }
+  red[0][ry][threadIdx.x & 31] = a1;
+  red[1][ry][threadIdx.x & 31] = as;
+  __syncthreads();
+  if (ry == 0 && c < E) {
+    float t1 = 0.f, ts = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t1 += red[0][k][threadIdx.x & 31]; ts += red[1][k][threadIdx.x & 31]; }
+    if (t1 != 0.f) atomicAdd(dtable + c, t1);
+    if (ts != 0.f) atomicAdd(dtable + (int64_t)V * E + c, ts);
+  }
+}
+
 int ae_embed_bwd(cudaStream_t s, const int32_t* seq, const float* y, const float* dx, float* dtable, Drop denc, Drop ddec,
                  int B, int T, int E, int V, int tmax) {
   const int64_t total = (int64_t)(2 * tmax + 1) * B * (E / 4);
   ae_embed_bwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(seq, y, dx, dtable, denc, ddec, B, T, E, V, tmax);
+  NVQA_LAUNCHED();
+  const int64_t rows = (int64_t)(2 * tmax + 1) * B;
+  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, rows / 64));
+  dim3 grid(ceil_div(E, 32), chunks);
+  ae_embed_bwd_hot_kernel<<<grid, 256, 0, s>>>(seq, y, dx, dtable, denc, ddec, B, T, E, V, tmax, ceil_div(rows, chunks));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -155,6 +200,141 @@ logsoftmax_lm_kernel(float* __restrict__ x, int ld, int ncols, const int32_t* __
 int logsoftmax_lm(cudaStream_t s, float* x, int rows, int ld, int ncols, const int32_t* targets, float* rowloss) {
   if (rows <= 0) return 0;
   logsoftmax_lm_kernel<<<rows, 256, 0, s>>>(x, ld, ncols, targets, rowloss);
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+// The same WITHOUT rewriting the row (tensor-core modes): lse[row] = log sum exp and the criterion's term; the 1.36 GB of
+// logits stay as they are, log-probs are formed where they are consumed (lm_grad_planes, lm_logprobs).
+__global__ void __launch_bounds__(256)
+lm_row_stats_kernel(const float* __restrict__ x, int ld, int ncols, const int32_t* __restrict__ targets, float* __restrict__ lse_out,
+                    float* __restrict__ rowloss) {
+  __shared__ float red[8];
+  const float* r = x + (int64_t)blockIdx.x * ld;
+  const int n4 = ncols >> 2;
+  // one pass: running max and rescaled sum per thread (online softmax), combined across the CTA
+  float mx = -INFINITY, se = 0.f;
+  for (int j = threadIdx.x; j < n4; j += 256) {
+    const float4 v = LD4(r + 4 * j);
+    const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (m4 > mx) { se *= expf(mx - m4); mx = m4; }
+    se += (expf(v.x - mx) + expf(v.y - mx)) + (expf(v.z - mx) + expf(v.w - mx));
+  }
+  for (int j = 4 * n4 + threadIdx.x; j < ncols; j += 256) {
+    const float v = r[j];
+    if (v > mx) { se *= expf(mx - v); mx = v; }
+    se += expf(v - mx);
+  }
+  const float gmx = block_reduce(mx, true, red);
+  se = mx == -INFINITY ? 0.f : se * expf(mx - gmx);
+  se = block_reduce(se, false, red);
+  const float lse = gmx + logf(se);
+  if (threadIdx.x == 0) {
+    lse_out[blockIdx.x] = lse;
+    const int tg = targets ? targets[blockIdx.x] : 0;
+    if (rowloss) rowloss[blockIdx.x] = (tg >= 1 && tg <= ncols) ? -(r[tg - 1] - lse) : 0.f;
+  }
+}
+
+int lm_row_stats(cudaStream_t s, const float* x, int rows, int ld, int ncols, const int32_t* targets, float* lse, float* rowloss) {
+  if (rows <= 0) return 0;
+  lm_row_stats_kernel<<<rows, 256, 0, s>>>(x, ld, ncols, targets, lse, rowloss);
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+// log-probs of nrows rows (logits - lse) into a dense [nrows x ncols] buffer (nvqa_logprobs_get)
+__global__ void __launch_bounds__(256)
+lm_logprobs_kernel(const float* __restrict__ x, const float* __restrict__ lse, int ld, int ncols, float* __restrict__ out) {
+  const int row = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ncols) out[(int64_t)row * ncols + j] = x[(int64_t)row * ld + j] - lse[row];
+}
+
+int lm_logprobs(cudaStream_t s, const float* x, const float* lse, int nrows, int ld, int ncols, float* out) {
+  if (nrows <= 0) return 0;
+  dim3 grid(ceil_div(ncols, 256), nrows);
+  lm_logprobs_kernel<<<grid, 256, 0, s>>>(x, lse, ld, ncols, out);
+  NVQA_LAUNCHED();
+  return 0;
+}
+
+// criterion + LogSoftMax backward straight into the operand format of the two vocabulary GEMMs of the backward pass:
+// d logits = (softmax - onehot(target)) / n as bf16 PLANES [P][rows][pitch] (pitch = ncols rounded up to 8, zero padded) --
+// the fp32 gradient tensor, its separate split pass and the separate column-sum pass of the bias gradient (3 x 1.36 GB
+// read, 2 x 1.36 GB written at config 5) do not exist.  CTA = 1024 columns x RPC rows: a thread keeps its 4 columns,
+// accumulates their sums over the rows in registers and adds them to gbias with one atomic per column and CTA.
+constexpr int LMG_RPC = 64;
+__global__ void __launch_bounds__(256)
+lm_grad_planes_kernel(const float* __restrict__ x, const float* __restrict__ lse, int rows, int ld, int ncols,
+                      const int32_t* __restrict__ targets, const int32_t* __restrict__ n_pred, float gscale,
+                      __nv_bfloat16* __restrict__ planes, int pitch, long long plane_stride, int P, float* __restrict__ gbias) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j >= pitch) return;
+  const int r0 = blockIdx.y * LMG_RPC, r1 = min(rows, r0 + LMG_RPC);
+  const float inv = gscale / (float)max(*n_pred, 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool full = j + 3 < ncols;
+  constexpr int RU = 4;                                   // rows in flight per thread: the loop is latency-bound otherwise
+  for (int rb = r0; rb < r1; rb += RU) {
+    float4 a[RU];
+    int tg[RU];
+    float l[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int row = rb + u;
+      tg[u] = row < r1 ? targets[row] - 1 : -1;
+      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      l[u] = 0.f;
+      if (tg[u] >= 0) {
+        l[u] = lse[row];
+        const float* r = x + (int64_t)row * ld + j;
+        if (full) a[u] = LD4(r);
+        else {
+          if (j + 0 < ncols) a[u].x = r[0];
+          if (j + 1 < ncols) a[u].y = r[1];
+          if (j + 2 < ncols) a[u].z = r[2];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int row = rb + u;
+      if (row >= r1) break;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tg[u] >= 0) {
+        if (j + 0 < ncols) v.x = (expf(a[u].x - l[u]) - (tg[u] == j + 0 ? 1.f : 0.f)) * inv;
+        if (j + 1 < ncols) v.y = (expf(a[u].y - l[u]) - (tg[u] == j + 1 ? 1.f : 0.f)) * inv;
+        if (j + 2 < ncols) v.z = (expf(a[u].z - l[u]) - (tg[u] == j + 2 ? 1.f : 0.f)) * inv;
+        if (j + 3 < ncols) v.w = (expf(a[u].w - l[u]) - (tg[u] == j + 3 ? 1.f : 0.f)) * inv;
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+      __nv_bfloat16 pl[3][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split3(xs[k], pl[0][k], pl[1][k], pl[2][k]);
+      for (int q = 0; q < P; ++q) {
+        uint2 o;
+        o.x = (uint32_t)__bfloat16_as_ushort(pl[q][0]) | ((uint32_t)__bfloat16_as_ushort(pl[q][1]) << 16);
+        o.y = (uint32_t)__bfloat16_as_ushort(pl[q][2]) | ((uint32_t)__bfloat16_as_ushort(pl[q][3]) << 16);
+        *reinterpret_cast<uint2*>(planes + (size_t)q * plane_stride + (size_t)row * pitch + j) = o;
+      }
+    }
+  }
+  if (gbias) {
+    if (j + 0 < ncols && acc.x != 0.f) atomicAdd(gbias + j + 0, acc.x);
+    if (j + 1 < ncols && acc.y != 0.f) atomicAdd(gbias + j + 1, acc.y);
+    if (j + 2 < ncols && acc.z != 0.f) atomicAdd(gbias + j + 2, acc.z);
+    if (j + 3 < ncols && acc.w != 0.f) atomicAdd(gbias + j + 3, acc.w);
+  }
+}
+
+int lm_grad_planes(cudaStream_t s, const float* x, const float* lse, int rows, int ld, int ncols, const int32_t* targets,
+                   const int32_t* n_pred, float gscale, __nv_bfloat16* planes, int pitch, long long plane_stride, int P,
+                   float* gbias) {
+  if (rows <= 0) return 0;
+  dim3 grid(ceil_div(pitch / 4, 256), ceil_div(rows, LMG_RPC));
+  lm_grad_planes_kernel<<<grid, 256, 0, s>>>(x, lse, rows, ld, ncols, targets, n_pred, gscale, planes, pitch, plane_stride, P, gbias);
   NVQA_LAUNCHED();
   return 0;
 }

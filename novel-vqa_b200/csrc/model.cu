@@ -316,6 +316,7 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
     NVQA_TRY(dallocT(m, &m->dh_init, (size_t)B * H));
     NVQA_TRY(dallocT(m, &m->dc_init, (size_t)B * H));
     NVQA_TRY(dallocT(m, &m->targets, rows));
+    NVQA_TRY(dallocT(m, &m->lse, rows));
     NVQA_TRY(dallocT(m, &m->n_pred, 4));
     NVQA_TRY(dallocT(m, &m->adam_m, m->P));
     NVQA_CUDA(cudaMemsetAsync(m->adam_m, 0, m->P * 4, m->stream));
@@ -809,7 +810,11 @@ static int forward_arch3(nvqa_model* m) {
   NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, rows, V1, H, m->hd, H, m->Wd, H, m->logits, m->ldl, false, m->bd));
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
-    NVQA_TRY(logsoftmax_lm(s, m->logits, rows, m->ldl, V1, m->targets, m->rowloss));
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("NVQA_AE_FUSED"); fused = e ? atoi(e) : 1; }
+    m->lp_raw = fused && m->planes > 0 && m->ws;
+    if (m->lp_raw) NVQA_TRY(lm_row_stats(s, m->logits, rows, m->ldl, V1, m->targets, m->lse, m->rowloss));
+    else NVQA_TRY(logsoftmax_lm(s, m->logits, rows, m->ldl, V1, m->targets, m->rowloss));
     NVQA_TRY(lm_loss_reduce(s, m->rowloss, rows, m->n_pred, m->loss));
   }
   m->fwd_done = true;
@@ -941,9 +946,27 @@ static int backward_head_arch3(nvqa_model* m) {
   cudaStream_t s = m->stream;
   {
     ProfScope ps(m, CAT_PW_BWD, 0);
-    NVQA_TRY(lm_grad(s, m->logits, rows, m->ldl, V1, m->targets, m->n_pred, 1.0f));
     NVQA_CUDA(cudaMemsetAsync(m->gbd, 0, (size_t)V1 * 4, s));
-    NVQA_TRY(colsum(s, m->logits, rows, V1, m->ldl, m->gbd, nullptr));
+    bool done = false;
+    if (m->lp_raw) {
+      // d logits straight as the bf16 planes both vocabulary GEMMs below read (registered under the key they will ask for),
+      // with the bias column sums; no fp32 gradient tensor, no split pass, no column-sum pass
+      __nv_bfloat16* dst = nullptr;
+      int pitch = 0;
+      if (reserve_planes(m->ws, m->planes, m->logits, rows, V1, m->ldl, 2, &dst, &pitch) == 0) {
+        NVQA_TRY(lm_grad_planes(s, m->logits, m->lse, rows, m->ldl, V1, m->targets, m->n_pred, 1.0f, dst, pitch,
+                                (long long)rows * pitch, m->planes, m->gbd));
+        done = true;
+      }
+    }
+    if (!done) {
+      if (m->lp_raw) {   // (no room for the planes: form the log-probs in place first)
+        NVQA_TRY(logsoftmax_lm(s, m->logits, rows, m->ldl, V1, nullptr, nullptr));
+        m->lp_raw = false;
+      }
+      NVQA_TRY(lm_grad(s, m->logits, rows, m->ldl, V1, m->targets, m->n_pred, 1.0f));
+      NVQA_TRY(colsum(s, m->logits, rows, V1, m->ldl, m->gbd, nullptr));
+    }
   }
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, V1, H, rows, m->logits, m->ldl, m->hd, H, m->gWd, H, false));
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, rows, H, V1, m->logits, m->ldl, m->Wd, H, m->dhd, H, false));
@@ -1242,11 +1265,20 @@ extern "C" int nvqa_adam_step(nvqa_model* m, float lr, float beta1, float beta2,
   return clamp_adam(m->stream, m->params, m->grads, m->adam_m, m->rms, m->P, lr, beta1, beta2, eps, wd, clamp, gscale, m->adam_t);
 }
 
+static int d2h(nvqa_model* m, void* dst, const void* src, size_t bytes);
 extern "C" int nvqa_logprobs_get(nvqa_model* m, int32_t step, float* dst) {
   NVQA_CHECK(m && dst && m->cfg.arch == 3 && m->fwd_done && m->logp_valid,
              "nvqa_logprobs_get: arch 3 forward has not run (or backward consumed the log-probs)");
   NVQA_CHECK(step >= 0 && step <= m->steps, "decoder step out of range");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  if (m->lp_raw) {
+    // the logits were not rewritten: log-probs of this step's rows = logits - lse, formed on demand
+    const int V1 = m->cfg.V + 1;
+    if (!m->lp_scratch) NVQA_TRY(dallocT(m, &m->lp_scratch, (size_t)m->cfg.B * V1));
+    NVQA_TRY(lm_logprobs(m->stream, m->logits + (int64_t)step * m->B * m->ldl, m->lse + (int64_t)step * m->B, m->B, m->ldl, V1,
+                         m->lp_scratch));
+    return d2h(m, dst, m->lp_scratch, (size_t)m->B * V1 * 4);
+  }
   NVQA_CUDA(cudaMemcpy2DAsync(dst, (size_t)(m->cfg.V + 1) * 4, m->logits + (int64_t)step * m->B * m->ldl, (size_t)m->ldl * 4,
                               (size_t)(m->cfg.V + 1) * 4, m->B, cudaMemcpyDeviceToHost, m->stream));
   NVQA_CUDA(cudaStreamSynchronize(m->stream));

@@ -65,6 +65,9 @@ struct nvqa_model {
   float *hd = nullptr, *dhd = nullptr;   // Dropout(top h) of the decoder steps and its gradient [(T+1) B x H]
   float *dh_init = nullptr, *dc_init = nullptr;   // d(decoder initial state) = d(encoder final state) [B x H]
   int32_t *targets = nullptr, *n_pred = nullptr;
+  float* lse = nullptr;             // tensor-core modes: per-row log-sum-exp of the logits (they stay raw: ae_kernels.cu)
+  float* lp_scratch = nullptr;      // [B x (V+1)] log-probs of one decoder step for nvqa_logprobs_get (allocated on first use)
+  bool lp_raw = false;              // logits holds raw logits + lse (true) or in-place log-probs (false)
   float *adam_m = nullptr;          // Adam first moment (second moment lives in rms)
   int64_t adam_t = 0;
   // trainer variants of 002_train_vqa_arch1 (nvqa_set_variant): AskipB fusion, lr_scale on encoder + embedding gradients,

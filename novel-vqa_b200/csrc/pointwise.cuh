@@ -71,6 +71,13 @@ int ae_embed_bwd(cudaStream_t s, const int32_t* seq, const float* y, const float
 int lm_targets(cudaStream_t s, const int32_t* seq, int32_t* targets, int32_t* n_pred, int B, int T, int V);
 int logsoftmax_lm(cudaStream_t s, float* x, int rows, int ld, int ncols, const int32_t* targets, float* rowloss);
 int lm_loss_reduce(cudaStream_t s, const float* rowloss, int rows, const int32_t* n_pred, float* loss);
+// tensor-core modes: the logits are never rewritten -- per-row log-sum-exp + criterion term; log-probs on demand; the
+// backward of criterion + LogSoftMax written directly as bf16 planes with the bias column sums (ae_kernels.cu)
+int lm_row_stats(cudaStream_t s, const float* x, int rows, int ld, int ncols, const int32_t* targets, float* lse, float* rowloss);
+int lm_logprobs(cudaStream_t s, const float* x, const float* lse, int nrows, int ld, int ncols, float* out);
+int lm_grad_planes(cudaStream_t s, const float* x, const float* lse, int rows, int ld, int ncols, const int32_t* targets,
+                   const int32_t* n_pred, float gscale, __nv_bfloat16* planes, int pitch, long long plane_stride, int P,
+                   float* gbias);
 int lm_grad(cudaStream_t s, float* lp, int rows, int ld, int ncols, const int32_t* targets, const int32_t* n_pred, float gscale);
 // clamp -> += wd * x -> adam (001_train_arch1_text_autoencoder.lua:237-243, misc/optim_updates.lua:78-111); t = step count (1-based)
 int clamp_adam(cudaStream_t s, float* x, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
