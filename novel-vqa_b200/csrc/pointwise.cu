@@ -501,15 +501,56 @@ lookup_bwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ dx,
   int b = (int)(n % B), t = (int)(n / B);
   int tok = t == 1 ? V + 1 : seq[(int64_t)b * T + (t - 2)];
   if (tok < 1 || tok > V + 1) tok = 1;
+  if (tok == 1 || tok == V + 1) return;          // the two HOT rows are summed by lookup_bwd_hot_kernel
   float4 g = LD4(dx + n * E + e);
   float* dst = dtable + (int64_t)(tok - 1) * E + e;
   atomicAdd(dst + 0, g.x); atomicAdd(dst + 1, g.y); atomicAdd(dst + 2, g.z); atomicAdd(dst + 3, g.w);
+}
+
+// Token 1 (every padded position is fed as token 1 and processed unmasked, Encoder_lstm.lua:197) and the START token V + 1
+// (all B rows of step 2) receive B .. T*B scatter-adds each on the same E addresses; as atomics they serialise (measured on
+// the autoencoder's twin of this kernel: 570 us instead of ~50 us at config 5).  Their gradient rows are column sums:
+// CTA = 32 columns x 8 row lanes over a chunk of rows, one atomic per (column, chunk, hot token).
+__global__ void __launch_bounds__(256)
+lookup_bwd_hot_kernel(const int32_t* __restrict__ seq, const float* __restrict__ dx, float* __restrict__ dtable, int B, int T,
+                      int E, int V, int steps, int rows_per_chunk) {
+  __shared__ float red[2][8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+  const int64_t rows = (int64_t)(steps - 1) * B;                   // rows t*B + b, t >= 1
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float a1 = 0.f, as = 0.f;
+  if (c < E) {
+    for (int64_t k = r0 + ry; k < r1; k += 8) {
+      const int64_t n = k + B;
+      const int b = (int)(n % B), t = (int)(n / B);
+      int tok = t == 1 ? V + 1 : seq[(int64_t)b * T + (t - 2)];
+      if (tok < 1 || tok > V + 1) tok = 1;
+      if (tok != 1 && tok != V + 1) continue;
+      const float g = dx[n * E + c];
+      if (tok == 1) a1 += g; else as += g;
+    }
+  }
+  red[0][ry][threadIdx.x & 31] = a1;
+  red[1][ry][threadIdx.x & 31] = as;
+  __syncthreads();
+  if (ry == 0 && c < E) {
+    float t1 = 0.f, ts = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t1 += red[0][k][threadIdx.x & 31]; ts += red[1][k][threadIdx.x & 31]; }
+    if (t1 != 0.f) atomicAdd(dtable + c, t1);
+    if (ts != 0.f) atomicAdd(dtable + (int64_t)V * E + c, ts);
+  }
 }
 
 int lookup_bwd(cudaStream_t s, const int32_t* seq, const float* dx, float* dtable, int B, int T, int E, int V, int steps) {
   int64_t total = (int64_t)(steps - 1) * B * (E / 4);
   if (total <= 0) return 0;
   lookup_bwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(seq, dx, dtable, B, T, E, V, steps);
+  NVQA_LAUNCHED();
+  const int64_t rows = (int64_t)(steps - 1) * B;
+  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, rows / 64));
+  dim3 grid(ceil_div(E, 32), chunks);
+  lookup_bwd_hot_kernel<<<grid, 256, 0, s>>>(seq, dx, dtable, B, T, E, V, steps, ceil_div(rows, chunks));
   NVQA_LAUNCHED();
   return 0;
 }

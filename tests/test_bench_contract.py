@@ -39,3 +39,18 @@ def test_our_arm_fails_loudly_without_a_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True,
                        text=True, timeout=600, cwd=ROOT)
     assert p.returncode != 0 and p.stdout.strip() == "" and "no CPU fallback" in p.stderr
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the round-1 SCALE ratios at N >= 2 were taken against a
+    single-threaded CPU arm.  The reference arm sets the torch thread count itself."""
+    try:
+        want = len(os.sched_getaffinity(0))
+    except AttributeError:
+        want = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1", "--batch", "20"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["cores"] == want and d["n_gpus"] == 2
