@@ -1120,7 +1120,12 @@ static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t*
     const float* X = (l == 0 ? m->y : m->xdrop[l]) + r0 * in;
     NVQA_CUDA(cudaMemsetAsync(sg.g[l].bi, 0, (size_t)4 * H * 4, s));
     NVQA_CUDA(cudaMemsetAsync(sg.g[l].bh, 0, (size_t)4 * H * 4, s));
-    // sum over timestep clones of accGradParameters (:323-326) as one GEMM over all (t,b) rows
+    // sum over timestep clones of accGradParameters (:323-326) as one GEMM over all (t,b) rows.  Nobody on this stream
+    // waits for these weight gradients: their split-K reductions run on the side stream beside the next GEMM.
+    static int defer_red = -1;
+    if (defer_red < 0) { const char* e = getenv("NVQA_DEFER_REDUCE"); defer_red = e ? atoi(e) : 1; }
+    const bool defer = defer_red && m->ws && aux_usable(m);
+    if (defer) { m->ws->reduce_stream = m->aux_stream; m->aux_reduce_used = true; }
     if (m->dap_valid) {
       // da (and h_prev) already exist as bf16 planes: no split passes, the GEMMs read them through MN-major TMA maps
       UmmaOperand da_mn = op_planes(m->dap, m->TS * c.B, 4 * H, (int)r0, false);
@@ -1132,6 +1137,7 @@ static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t*
       NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, in, T * B, da, 4 * H, X, in, sg.g[l].Wi, in, false));
       NVQA_TRY(gemm(m, CAT_WGRAD, false, false, 4 * H, H, T * B, da, 4 * H, m->h[l] + r0 * H, H, sg.g[l].Wh, H, false));
     }
+    if (m->ws) m->ws->reduce_stream = nullptr;
     {
       ProfScope ps(m, CAT_PW_BWD, 0);
       // persistent kernel: da (here) holds the per-row sums over t [B x 4H]; fallback: da_t of every step [T*B x 4H]
@@ -1166,6 +1172,11 @@ static int backward_lstm(nvqa_model* m) {
   for (int l = 0; l < L; ++l) { dh0[l] = m->dqd + (2 * l + 1) * H; dc0[l] = m->dqd + (2 * l) * H; }
   NVQA_TRY(aux_launch_bwd(m, m->planes && m->use_persistent));      // the AxB weight gradients run beside the recurrent kernels
   NVQA_TRY(lstm_layers_backward(m, m->cfg.T, m->len, dh0, dc0, m->S));
+  if (m->aux_reduce_used) {       // deferred split-K reductions of the weight gradients are the last work on the side stream
+    NVQA_CUDA(cudaEventRecord(m->aux_join, m->aux_stream));
+    m->aux_bwd_inflight = true;
+    m->aux_reduce_used = false;
+  }
   return aux_join_main(m);
 }
 

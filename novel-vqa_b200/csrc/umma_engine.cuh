@@ -53,6 +53,15 @@ struct UmmaWorkspace {
   size_t side_bytes = 0, side_top = 0;
   bool side = false;
   int cta_cap = 0;
+  // Split-K reductions whose result nobody on the launching stream waits for (the weight-gradient GEMMs of the LSTM
+  // layers) can run on a second stream beside the NEXT GEMM: while reduce_stream is set, the partials of such a GEMM go
+  // to one of two dedicated slots at the end of the buffer and the reduction kernel is enqueued on reduce_stream
+  // (event-ordered behind the GEMM; a slot is reused only after its previous reduction has finished).
+  cudaStream_t reduce_stream = nullptr;
+  cudaEvent_t reduce_gemm_done[2] = {nullptr, nullptr}, reduce_done[2] = {nullptr, nullptr};
+  bool reduce_pending[2] = {false, false};
+  int reduce_slot = 0;
+  size_t defer_bytes = 0;       // 2 slots of defer_bytes / 2 in [bytes, bytes + defer_bytes)
   size_t& ttop() { return side ? side_top : trans_top; }
   size_t tbase() const { return side ? bytes - side_bytes : static_bytes + act_bytes; }
   size_t tlimit() const { return side ? bytes : bytes - side_bytes; }

@@ -582,7 +582,14 @@ int umma_workspace_create(UmmaWorkspace** out, size_t transient_bytes, size_t st
   ws->act_bytes = (act_bytes + 1023) & ~(size_t)1023;
   ws->side_bytes = transient_bytes ? (size_t)48 << 20 : 0;           // split-K partials of the head GEMMs: <= 8 x 500 x 1024 x 4 B
   ws->bytes = ws->static_bytes + ws->act_bytes + transient_bytes + ws->side_bytes;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws->base), ws->bytes);
+  ws->defer_bytes = transient_bytes ? (size_t)40 << 20 : 0;          // 2 x 20 MB: 4 splits of a [2048 x 512] fp32 tile set = 16.8 MB
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws->base), ws->bytes + ws->defer_bytes);
+  if (e == cudaSuccess && ws->defer_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEventCreateWithFlags(&ws->reduce_gemm_done[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ws->reduce_done[i], cudaEventDisableTiming);
+    }
+  }
   if (e != cudaSuccess) {
     set_error(std::string("umma workspace cudaMalloc: ") + cudaGetErrorString(e));
     delete ws;
@@ -593,6 +600,10 @@ int umma_workspace_create(UmmaWorkspace** out, size_t transient_bytes, size_t st
 }
 void umma_workspace_destroy(UmmaWorkspace* ws) {
   if (!ws) return;
+  for (int i = 0; i < 2; ++i) {
+    if (ws->reduce_gemm_done[i]) cudaEventDestroy(ws->reduce_gemm_done[i]);
+    if (ws->reduce_done[i]) cudaEventDestroy(ws->reduce_done[i]);
+  }
   cudaFree(ws->base);
   delete ws;
 }
@@ -607,6 +618,7 @@ void umma_workspace_new_forward(UmmaWorkspace* ws) {
   if (!ws) return;
   ws->act_cache.clear();
   ws->act_top = 0;
+  ws->reduce_stream = nullptr;       // a step that failed half-way must not leave the deferral on
 }
 
 // fp32 row-major [rows x cols] (ld) -> bf16 planes [P][rows][colsp]; no transposition: an MN-major operand is
@@ -899,7 +911,7 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
     if (splits < 1) splits = 1;
   }
   float* Cout = C;
-  int ldo = ldc;
+  int ldo = ldc, defer_slot = -1;
   bool beta_k = beta;
   const float *b0k = bias0, *b1k = bias1;
   if (splits > 1) {
@@ -907,9 +919,16 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
     splits = ceil_div(nkb, L.kb_per_split);                       // no empty split
     L.splits = splits;
     const size_t need = (size_t)splits * M * N * sizeof(float);
-    NVQA_CHECK(ws->tbase() + ws->ttop() + need <= ws->tlimit(), "umma workspace too small for split-K partials");
-    Cout = reinterpret_cast<float*>(ws->base + ws->tbase() + ws->ttop());
-    ws->ttop() += (need + 1023) & ~(size_t)1023;
+    defer_slot = (ws->reduce_stream && !ws->side && ws->defer_bytes && need <= ws->defer_bytes / 2) ? ws->reduce_slot : -1;
+    if (defer_slot >= 0) {
+      ws->reduce_slot ^= 1;
+      if (ws->reduce_pending[defer_slot]) NVQA_CUDA(cudaStreamWaitEvent(s, ws->reduce_done[defer_slot], 0));   // slot still being reduced
+      Cout = reinterpret_cast<float*>(ws->base + ws->bytes + (size_t)defer_slot * (ws->defer_bytes / 2));
+    } else {
+      NVQA_CHECK(ws->tbase() + ws->ttop() + need <= ws->tlimit(), "umma workspace too small for split-K partials");
+      Cout = reinterpret_cast<float*>(ws->base + ws->tbase() + ws->ttop());
+      ws->ttop() += (need + 1023) & ~(size_t)1023;
+    }
     ldo = N;
     L.c_split_stride = (long long)M * N;
     beta_k = false; b0k = b1k = nullptr;
@@ -941,9 +960,19 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
 #undef NVQA_UG
   if (rc) return rc;
   if (splits > 1) {
-    splitk_reduce_kernel<<<ceil_div((long long)M * N, 256), 256, 0, s>>>(Cout, splits, L.c_split_stride, M, N, N, C, ldc,
-                                                                        beta ? 1 : 0, bias0, bias1);
+    cudaStream_t rs = s;
+    if (defer_slot >= 0) {
+      rs = ws->reduce_stream;
+      NVQA_CUDA(cudaEventRecord(ws->reduce_gemm_done[defer_slot], s));
+      NVQA_CUDA(cudaStreamWaitEvent(rs, ws->reduce_gemm_done[defer_slot], 0));
+    }
+    splitk_reduce_kernel<<<ceil_div((long long)M * N, 256), 256, 0, rs>>>(Cout, splits, L.c_split_stride, M, N, N, C, ldc,
+                                                                         beta ? 1 : 0, bias0, bias1);
     NVQA_LAUNCHED();
+    if (defer_slot >= 0) {
+      NVQA_CUDA(cudaEventRecord(ws->reduce_done[defer_slot], rs));
+      ws->reduce_pending[defer_slot] = true;
+    }
   }
   return 0;
 }
