@@ -582,7 +582,7 @@ int umma_workspace_create(UmmaWorkspace** out, size_t transient_bytes, size_t st
   ws->act_bytes = (act_bytes + 1023) & ~(size_t)1023;
   ws->side_bytes = transient_bytes ? (size_t)48 << 20 : 0;           // split-K partials of the head GEMMs: <= 8 x 500 x 1024 x 4 B
   ws->bytes = ws->static_bytes + ws->act_bytes + transient_bytes + ws->side_bytes;
-  ws->defer_bytes = transient_bytes ? (size_t)40 << 20 : 0;          // 2 x 20 MB: 4 splits of a [2048 x 512] fp32 tile set = 16.8 MB
+  ws->defer_bytes = transient_bytes ? (size_t)80 << 20 : 0;          // 2 x 40 MB: 9 splits of a [2048 x 512] fp32 tile set = 37.7 MB
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws->base), ws->bytes + ws->defer_bytes);
   if (e == cudaSuccess && ws->defer_bytes) {
     for (int i = 0; i < 2; ++i) {
@@ -896,19 +896,69 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
   int num_sms = ws->side && ws->cta_cap > 0 ? ws->cta_cap : 148;
   L.cta_cap = ws->side ? ws->cta_cap : 0;
   const int mt = ceil_div(M, UG_BM);
+  // CTA pairs (cta_group::2, 256 x BN tiles) for the wide tiles of two-plane products: NVQA_GEMM_PAIR=0 disables
+  static int pair_on = -1, shape_v2 = -1;
+  if (pair_on < 0) { const char* e = getenv("NVQA_GEMM_PAIR"); pair_on = e ? atoi(e) : 1; }
+  if (shape_v2 < 0) { const char* e = getenv("NVQA_GEMM_SHAPE_V2"); shape_v2 = e ? atoi(e) : 1; }
+  const bool pairable = pair_on && M > UG_BM;                      // (and BN >= 128, below)
+  const int slots = pairable ? num_sms / 2 : num_sms;              // work units (pair tiles / tiles) the machine runs at once
+  const int mrows = pairable ? ceil_div(M, 2 * UG_BM) : mt;
   int BN = 64;
-  if (planes <= 2 && N >= 256 && (long)mt * ceil_div(N, 256) >= num_sms / 2) BN = 256;
-  else if ((long)mt * ceil_div(N, 128) >= num_sms / 2) BN = 128;
+  if (planes <= 2 && N >= 256 && (long)mt * ceil_div(N, 256) >= num_sms / 2) {
+    BN = 256;
+    // a persistent grid runs ceil(units / slots) waves: half-width tiles (8 % more operand traffic per flop) win when
+    // they fill the last wave better -- layer-2 dgrad [13000 x 512]: 102 pair tiles on 74 pairs = 2 waves of 256 columns
+    // against 204 = 3 waves of 128 (0.122 -> 0.107 ms for the two dgrad GEMMs of the step)
+    const long w256 = (long)ceil_div(mrows * ceil_div(N, 256), slots) * 256 * 100;
+    const long w128 = (long)ceil_div(mrows * ceil_div(N, 128), slots) * 128 * 108;
+    if (shape_v2 && w128 < w256) BN = 128;
+  } else if ((long)mt * ceil_div(N, 128) >= num_sms / 2) BN = 128;
   else if (planes <= 2 && N >= 256 && K >= 2048) BN = 256;        // few tiles but a long K: wide tiles + split-K
   else if (N >= 128 && K >= 2048) BN = 128;
   const int tiles = mt * ceil_div(N, BN);
   const int nkb = ceil_div(K, UG_BK);
   int splits = 1;
   if (tiles < num_sms / 2 && nkb >= 16) {
-    splits = num_sms / tiles;
-    if (splits > 8) splits = 8;
-    if (splits > nkb / 8) splits = nkb / 8;
-    if (splits < 1) splits = 1;
+    if (shape_v2) {
+      // waves x (k-blocks per split + ~3 k-blocks of prologue / epilogue): more than one wave is allowed when it fills the
+      // machine better -- weight gradients [2048 x 512], K = 13000: 16 pair tiles x 4 splits = 64 of 74 pairs busy for 51
+      // k-blocks against x 9 = 144 units = 2 waves of 23
+      const int units = (BN >= 128 ? mrows : mt) * ceil_div(N, BN), sl = BN >= 128 ? slots : num_sms;
+      long best = -1;
+      for (int sp = 1; sp <= 16 && sp <= (nkb / 8 > 1 ? nkb / 8 : 1); ++sp) {
+        const int kbs = ceil_div(nkb, sp), eff = ceil_div(nkb, kbs);
+        const long cost = (long)ceil_div(units * eff, sl) * (kbs + 3);
+        if (best < 0 || cost < best) { best = cost; splits = eff; }
+      }
+    } else {
+      splits = num_sms / tiles;
+      if (splits > 8) splits = 8;
+      if (splits > nkb / 8) splits = nkb / 8;
+      if (splits < 1) splits = 1;
+    }
+  }
+  // experiments: NVQA_GEMM_OVERRIDE="MxNxK:BN:splits,..." replaces the shape rule for the listed products
+  {
+    struct Ov { int M, N, K, BN, splits; };
+    static std::vector<Ov> ov;
+    static bool parsed = false;
+    if (!parsed) {
+      parsed = true;
+      if (const char* e = getenv("NVQA_GEMM_OVERRIDE")) {
+        Ov o;
+        int used = 0;
+        while (sscanf(e, "%dx%dx%d:%d:%d%n", &o.M, &o.N, &o.K, &o.BN, &o.splits, &used) == 5) {
+          ov.push_back(o);
+          e += used;
+          if (*e == ',') ++e;
+        }
+      }
+    }
+    for (const Ov& o : ov)
+      if (o.M == M && o.N == N && o.K == K && !ws->side && (o.BN == 64 || o.BN == 128 || (o.BN == 256 && planes <= 2))) {
+        BN = o.BN;
+        splits = o.splits < 1 ? 1 : (o.splits > nkb ? nkb : o.splits);
+      }
   }
   float* Cout = C;
   int ldo = ldc, defer_slot = -1;
@@ -917,6 +967,13 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
   if (splits > 1) {
     L.kb_per_split = ceil_div(nkb, splits);
     splits = ceil_div(nkb, L.kb_per_split);                       // no empty split
+    L.splits = splits;
+    const bool can_defer = ws->reduce_stream && !ws->side && ws->defer_bytes;
+    const size_t room = can_defer ? ws->defer_bytes / 2 : ws->tlimit() - ws->tbase() - ws->ttop();
+    while (splits > 2 && (size_t)splits * M * N * sizeof(float) > room) {        // fewer, longer splits if the partials do not fit
+      L.kb_per_split = ceil_div(nkb, splits - 1);
+      splits = ceil_div(nkb, L.kb_per_split);
+    }
     L.splits = splits;
     const size_t need = (size_t)splits * M * N * sizeof(float);
     defer_slot = (ws->reduce_stream && !ws->side && ws->defer_bytes && need <= ws->defer_bytes / 2) ? ws->reduce_slot : -1;
@@ -933,10 +990,7 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
     L.c_split_stride = (long long)M * N;
     beta_k = false; b0k = b1k = nullptr;
   }
-  // CTA pairs (cta_group::2, 256 x BN tiles) for the wide tiles of two-plane products: NVQA_GEMM_PAIR=0 disables
-  static int pair_on = -1;
-  if (pair_on < 0) { const char* e = getenv("NVQA_GEMM_PAIR"); pair_on = e ? atoi(e) : 1; }
-  const bool use_pair = pair_on && BN >= 128 && M > UG_BM;
+  const bool use_pair = pairable && BN >= 128;
   CUtensorMap ma, mb;
   NVQA_TRY(get_map(ws, pa, bound_a, pitch_a, planes, A.kmajor ? UG_BM : 64, &ma, ps_a));
   NVQA_TRY(get_map(ws, pb, bound_b, pitch_b, planes, B.kmajor ? (use_pair ? BN / 2 : BN) : 64, &mb, ps_b));
