@@ -276,34 +276,42 @@ struct UgCfg2 {
   static constexpr int A_PLANE = UG_BM * UG_BK * 2;           // this CTA's 128 rows: 16 KB
   static constexpr int B_PLANE = (BN / 2) * UG_BK * 2;        // this CTA's half of the B tile
   static constexpr int STAGE = P * (A_PLANE + B_PLANE);
-  static constexpr int EPI_PITCH = 36;
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
-  static constexpr int MAX_STAGES = (227 * 1024 - 4096 - EPI_BYTES) / STAGE;
+  static constexpr int EPI_PITCH = 36;                        // padded tile of the st.global fallback (fits the two boxes)
+  static constexpr int EPI_WARP = 2 * 4096;                   // per epilogue warp: two 32 x 32 fp32 boxes (SWIZZLE_128B) in flight
+  static constexpr int EPI_BYTES = 4 * EPI_WARP;
+  static constexpr int TAIL = 256 /*barriers*/ + 2 * 1024 /*two bias tiles*/;
+  static constexpr int MAX_STAGES = (227 * 1024 - TAIL - EPI_BYTES) / STAGE;
   static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + 2 * 1024 + EPI_BYTES;
+  // no alignment slack: the dynamic shared memory is declared __align__(1024) (and the kernel traps if it is not)
+  static constexpr int SMEM = STAGES * STAGE + EPI_BYTES + TAIL;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(STAGES >= 2, "pipeline needs two stages");
+  static_assert(STAGE % 1024 == 0 && SMEM <= 227 * 1024, "shared-memory layout");
+  static_assert(32 * EPI_PITCH * 4 <= EPI_WARP, "fallback tile must fit the warp's staging area");
 };
 
 template <int BN, int P, bool AMN, bool BMN>
 __global__ void __launch_bounds__(UG_THREADS, 1)
-umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N,
+umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                      const __grid_constant__ CUtensorMap mapC, int M, int N,
                       int K, float* __restrict__ C, int ldc, int beta, const float* __restrict__ bias0,
                       const float* __restrict__ bias1, int a_row0, int b_row0, int kb_per_split, long long c_split_stride,
                       int tiles_n, int tiles_m2, int splits) {
   using Cfg = UgCfg2<BN, P>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + Cfg::STAGES * Cfg::STAGE);
-  const uint32_t full0 = base + Cfg::STAGES * Cfg::STAGE;
+  extern __shared__ uint8_t smem_pair_raw[];
+  const uint32_t base = smem_u32(smem_pair_raw);
+  if (base & 1023u) __trap();                                         // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* gen = smem_pair_raw;
+  // [operand stages][epilogue staging 4 warps x 2 boxes][barriers 256 B][two bias tiles]
+  constexpr int BAR_OFF = Cfg::STAGES * Cfg::STAGE + Cfg::EPI_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + BAR_OFF);
+  const uint32_t full0 = base + BAR_OFF;
   const uint32_t empty0 = full0 + 8 * Cfg::STAGES;
   const uint32_t tfull = empty0 + 8 * Cfg::STAGES;
   const uint32_t tempty = tfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
-  float* bias_all = reinterpret_cast<float*>(gen + Cfg::STAGES * Cfg::STAGE + 256);
-  float* epi_all = bias_all + 512;
+  float* bias_all = reinterpret_cast<float*>(gen + BAR_OFF + 256);
+  uint8_t* epi_all = gen + Cfg::STAGES * Cfg::STAGE;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                            // 0 = the pair's leader (issues the MMAs)
@@ -314,6 +322,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -417,43 +426,97 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
     }
   } else {
-    // ===== epilogue (both CTAs): own 128 accumulator rows -> shared-memory chunk -> full-line stores =====
+    // ===== epilogue (both CTAs): own 128 accumulator rows -> 32 x 32 boxes in shared memory -> TMA stores =====
+    // A warp reads its 32 TMEM lanes 32 columns at a time (lane = row), adds the bias, writes the row into a SWIZZLE_128B
+    // box (16-byte chunk j of row r at chunk j ^ (r & 7): conflict-free) and one lane hands the box to the TMA unit, which
+    // clips it at the tensor's bounds; two boxes per warp alternate, the load of chunk cc + 1 is in flight meanwhile.
+    // beta: the box is ADDED to C by the TMA unit (cp.reduce ... .add).  tma_out = 0 (C not 16-byte aligned / tiny
+    // shapes): padded tile + st.global as in round 1.
     const int q = warp & 3;
+    const int tma_out = (beta >> 1) & 1;
+    beta &= 1;
     const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     float* const C0 = C;
     const uint32_t tempty_leader = mapa_u32(tempty, 0);
+    uint8_t* const wst = epi_all + (warp - 2) * Cfg::EPI_WARP;
+    const uint32_t wst_s = smem_u32(wst);
+    const bool has_bias = bias0 != nullptr || bias1 != nullptr;
     int li = 0;
+    uint32_t g = 0;                                   // running box counter of this warp (buffer = g & 1)
     for (int tile = pair; tile < total_tiles; tile += npairs, ++li) {
     const int tz = tile / (tiles_n * tiles_m2), ty = (tile / tiles_n) % tiles_m2, tx = tile % tiles_n;
     const int m0 = ty * 2 * UG_BM + (int)rank * UG_BM, n0 = tx * BN;
     const int as = li & 1;
     C = C0 + (size_t)tz * c_split_stride;
     float* bias_s = bias_all + as * 256;
-    for (int j = threadIdx.x - 64; j < BN; j += 128) {
-      float bsum = 0.f;
-      if (n0 + j < N) {
-        if (bias0) bsum += __ldg(bias0 + n0 + j);
-        if (bias1) bsum += __ldg(bias1 + n0 + j);
+    if (has_bias) {
+      for (int j = threadIdx.x - 64; j < BN; j += 128) {
+        float bsum = 0.f;
+        if (n0 + j < N) {
+          if (bias0) bsum += __ldg(bias0 + n0 + j);
+          if (bias1) bsum += __ldg(bias1 + n0 + j);
+        }
+        bias_s[j] = bsum;
       }
-      bias_s[j] = bsum;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(tfull + 8 * as, ((uint32_t)li >> 1) & 1u);
     tc_fence_after();
-    const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
-    float* stg = epi_all + (warp - 2) * 32 * Cfg::EPI_PITCH;
+    const uint32_t tacc = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(q * 32) << 16);
+    const int nch = min(BN / 32, (N - n0 + 31) / 32);
+    if (tma_out) {
+      const int row0 = m0 + q * 32;
+      float va[32], vb[32];
+      tmem_ld32_nowait(tacc, va);
+#pragma unroll 1
+      for (int cc = 0; cc < nch; cc += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float* v = h ? vb : va;
+          const int c = cc + h;
+          if (c < nch) {
+            tmem_wait_ld(v);
+            if (c + 1 < nch) tmem_ld32_nowait(tacc + (uint32_t)((c + 1) * 32), h ? va : vb);
+            if (has_bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              }
+            }
+            const uint32_t boff = (g & 1u) * 4096u;
+            if (lane == 0) bulk_wait_read<1>();         // the box stored two chunks back has been read out of this buffer
+            __syncwarp();
+            uint8_t* rowp = wst + boff + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < M) {
+              if (beta) tma_reduce_add_3d(&mapC, wst_s + boff, n0 + c * 32, row0, tz);
+              else tma_store_3d(&mapC, wst_s + boff, n0 + c * 32, row0, tz);
+              bulk_commit();
+            }
+            ++g;
+          }
+        }
+      }
+    } else {
+    float* stg = reinterpret_cast<float*>(wst);
     const int sr = lane >> 3, sc = (lane & 7) * 4;
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      if (n0 + cc * 32 >= N) break;
+    for (int cc = 0; cc < nch; ++cc) {
       float v[32];
-      tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+      tmem_ld32(tacc + (uint32_t)(cc * 32), v);
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
       const int col = n0 + cc * 32 + sc;
-      const float4 bb = *reinterpret_cast<const float4*>(bias_s + cc * 32 + sc);
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_bias) bb = *reinterpret_cast<const float4*>(bias_s + cc * 32 + sc);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = 4 * i + sr, row = m0 + q * 32 + r;
@@ -475,6 +538,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       }
       __syncwarp();
     }
+    }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -482,6 +546,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       else mbar_arrive_remote(tempty_leader + 8 * as);
     }
     }
+    if (tma_out && lane == 0) bulk_wait_all();        // the stores are complete (global writes performed) before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -762,7 +827,33 @@ int get_map_kb(UmmaWorkspace* ws, const __nv_bfloat16* planes, int rows, int Kp,
 struct UgLaunch {
   int a_row0 = 0, b_row0 = 0, splits = 1, kb_per_split = 1 << 30, cta_cap = 0;
   long long c_split_stride = 0;
+  const CUtensorMap* mapc = nullptr;       // pair kernel: output tensor map of the TMA-store epilogue (null: st.global)
 };
+
+// tensor map over the fp32 output [splits][M][N] (row pitch ld, split stride in elements): boxes of 32 x 32, SWIZZLE_128B
+static int get_cmap(UmmaWorkspace* ws, float* C, int M, int N, int ld, int splits, long long split_stride, CUtensorMap* out) {
+  if (split_stride <= 0) split_stride = (long long)M * ld;
+  MapKey key{reinterpret_cast<const __nv_bfloat16*>(C), M, ld, splits, N, split_stride, 7777};
+  auto it = ws->maps.find(key);
+  if (it != ws->maps.end()) { *out = it->second; return 0; }
+  EncodeTiledFn enc = get_encode();
+  NVQA_CHECK(enc, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)split_stride * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed with code " + std::to_string((int)r));
+    return 1;
+  }
+  if (ws->maps.size() > 4096) ws->maps.clear();
+  ws->maps[key] = m;
+  *out = m;
+  return 0;
+}
 
 template <int BN, int P, bool AMN, bool BMN>
 static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, float* C,
@@ -821,12 +912,13 @@ static int launch_umma_pair(cudaStream_t s, const CUtensorMap& ma, const CUtenso
   }
   int tn = ceil_div(N, BN), tm2 = ceil_div(M, 2 * UG_BM), splits = L.splits, kbs = L.kb_per_split;
   long long cstride = L.c_split_stride;
-  int a0 = L.a_row0, b0r = L.b_row0, beta_i = beta ? 1 : 0;
+  int a0 = L.a_row0, b0r = L.b_row0, beta_i = (beta ? 1 : 0) | (L.mapc ? 2 : 0);      // bit 1: TMA-store epilogue
   const long long total = (long long)tn * tm2 * splits;
   NVQA_CHECK(total < (1ll << 30), "umma_gemm: too many tiles");
   const int sm_cap = L.cta_cap > 0 ? std::min(L.cta_cap, num_sms) : num_sms;
   const int pairs = (int)std::min<long long>(total, std::max(1, sm_cap / 2));
-  void* args[] = {(void*)&ma, (void*)&mb, &M, &N, &K, &C, &ldc, &beta_i, (void*)&b0, (void*)&b1, &a0, &b0r, &kbs, &cstride, &tn, &tm2, &splits};
+  const CUtensorMap& mc = L.mapc ? *L.mapc : ma;                                       // (unused by the kernel when bit 1 is clear)
+  void* args[] = {(void*)&ma, (void*)&mb, (void*)&mc, &M, &N, &K, &C, &ldc, &beta_i, (void*)&b0, (void*)&b1, &a0, &b0r, &kbs, &cstride, &tn, &tm2, &splits};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(UG_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
   cudaLaunchAttribute attr;
@@ -994,6 +1086,14 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
   CUtensorMap ma, mb;
   NVQA_TRY(get_map(ws, pa, bound_a, pitch_a, planes, A.kmajor ? UG_BM : 64, &ma, ps_a));
   NVQA_TRY(get_map(ws, pb, bound_b, pitch_b, planes, B.kmajor ? (use_pair ? BN / 2 : BN) : 64, &mb, ps_b));
+  CUtensorMap mc;
+  static int tma_epi = -1;
+  if (tma_epi < 0) { const char* e = getenv("NVQA_GEMM_TMA_STORE"); tma_epi = e ? atoi(e) : 1; }
+  if (use_pair && tma_epi && M >= 32 && N >= 32 && (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(Cout) & 15) == 0 &&
+      (L.c_split_stride & 3) == 0) {
+    NVQA_TRY(get_cmap(ws, Cout, M, N, ldo, splits, L.c_split_stride, &mc));
+    L.mapc = &mc;
+  }
   int rc = 1;
 #define NVQA_UGP(BN_, P_) \
   rc = launch_umma_pair_major<BN_, P_>(!A.kmajor, !B.kmajor, s, ma, mb, M, N, K, Cout, ldo, beta_k, b0k, b1k, L)
