@@ -251,6 +251,11 @@ int64_t nvqa_launch_count(void);
  * B stored [N x K] (b_kmajor) or [K x N]; fp32 device pointers; precision = NVQA_PREC_* */
 int nvqa_gemm_test(int precision, int a_kmajor, int b_kmajor, int32_t M, int32_t N, int32_t K,
                    const float* A, const float* B, float* C, void* cuda_stream);
+/* the same with the rest of nn.Linear's contract: C (row pitch ldc >= N) = (beta ? C : 0) + A (.) B + bias0[n] + bias1[n]
+ * (biases nullable) -- accGradParameters accumulates (beta), LSTM.lua:24-25 adds two Linear biases */
+int nvqa_gemm_test_ex(int precision, int a_kmajor, int b_kmajor, int32_t M, int32_t N, int32_t K,
+                      const float* A, const float* B, float* C, int32_t ldc, int beta, const float* bias0,
+                      const float* bias1, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,8 @@ SIGNATURES = {
     "nvqa_launch_count": (C.c_int64, []),
     "nvqa_gemm_test": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "nvqa_gemm_test_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 
 namespace nvqa {
 
@@ -34,6 +35,31 @@ extern int64_t g_launches;                       // kernels launched since load 
     int r__ = (expr);             \
     if (r__ != 0) return r__;     \
   } while (0)
+
+// ---- programmatic dependent launch ------------------------------------------------------------
+// A kernel launched through launch_pdl may be SCHEDULED while its predecessor in the stream is still running (its CTAs
+// become resident as the predecessor's exit, block prologues run, launch latency is hidden); it must not touch memory
+// before pdl_entry(), which waits until the predecessor grid has completed and its writes are visible, and which then lets
+// the next kernel of the stream be scheduled in turn.  pdl_entry() is the FIRST statement of every such kernel (a kernel
+// that returned without it could complete before its own predecessor and break the chain); in a kernel launched without
+// the attribute both instructions are no-ops.  NVQA_PDL=0 launches everything fully serialised.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_wait(); pdl_trigger(); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // launch-error check used after every kernel launch
 #define NVQA_LAUNCHED()                 \

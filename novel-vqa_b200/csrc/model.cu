@@ -25,6 +25,11 @@
 namespace nvqa {
 static thread_local std::string g_err;
 int64_t g_launches = 0;
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("NVQA_PDL"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
 void set_error(const std::string& msg) { g_err = msg; }
 }  // namespace nvqa
 
@@ -1679,21 +1684,27 @@ extern "C" int nvqa_memcpy_d2h(nvqa_model* m, void* dst, const void* src, int64_
   return d2h(m, dst, src, (size_t)bytes);
 }
 
-extern "C" int nvqa_gemm_test(int precision, int a_kmajor, int b_kmajor, int32_t M, int32_t N, int32_t K, const float* A,
-                              const float* B, float* C, void* stream) {
-  NVQA_CHECK(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
+extern "C" int nvqa_gemm_test_ex(int precision, int a_kmajor, int b_kmajor, int32_t M, int32_t N, int32_t K, const float* A,
+                                 const float* B, float* C, int32_t ldc, int beta, const float* bias0, const float* bias1,
+                                 void* stream) {
+  NVQA_CHECK(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N, "bad argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int lda = a_kmajor ? K : M, ldb = b_kmajor ? K : N;
   if (precision == NVQA_PREC_FP32_SIMT) {
-    NVQA_TRY(simt_gemm(s, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, N, false, nullptr, nullptr));
+    NVQA_TRY(simt_gemm(s, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc, beta != 0, bias0, bias1));
     NVQA_CUDA(cudaStreamSynchronize(s));
     return 0;
   }
   int planes = precision == NVQA_PREC_BF16X3 ? 3 : precision == NVQA_PREC_BF16X2 ? 2 : 1;
   UmmaWorkspace* ws = nullptr;
   NVQA_TRY(umma_workspace_create(&ws, ((size_t)(M + 64) * (K + 64) + (size_t)(N + 64) * (K + 64)) * 2 * 3 + (8 << 20), 0));
-  int r = umma_gemm(s, planes, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, N, false, nullptr, nullptr, ws, false, false);
+  int r = umma_gemm(s, planes, a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc, beta != 0, bias0, bias1, ws, false, false);
   cudaStreamSynchronize(s);
   umma_workspace_destroy(ws);
   return r;
+}
+
+extern "C" int nvqa_gemm_test(int precision, int a_kmajor, int b_kmajor, int32_t M, int32_t N, int32_t K, const float* A,
+                              const float* B, float* C, void* stream) {
+  return nvqa_gemm_test_ex(precision, a_kmajor, b_kmajor, M, N, K, A, B, C, N, 0, nullptr, nullptr, stream);
 }

@@ -45,6 +45,7 @@ __device__ __forceinline__ void planes_st1(const PlaneOut& po, size_t idx, float
 __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len, const float* __restrict__ WeT,
                  const float* __restrict__ be, float* __restrict__ y, Drop d, int B, int T, int E, int V, PlaneOut yp) {
+  pdl_entry();
   const int E4 = E >> 2;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)T * B * E4;
@@ -70,7 +71,7 @@ embed_fwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len,
 int embed_fwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float* WeT, const float* be, float* y,
               Drop d, int B, int T, int E, int V, PlaneOut yp) {
   int64_t total = (int64_t)T * B * (E / 4);
-  embed_fwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(q, len, WeT, be, y, d, B, T, E, V, yp);
+  NVQA_CUDA(launch_pdl(embed_fwd_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, s, q, len, WeT, be, y, d, B, T, E, V, yp));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -80,6 +81,7 @@ int embed_fwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float*
 __global__ void __launch_bounds__(256)
 imgnorm_drop_kernel(const float* __restrict__ fc7, float* __restrict__ vd, Drop d, int I, int img_norm, int split,
                     PlaneOut vp) {
+  pdl_entry();
   // split > 0: columns [0, split) and [split, I) are two feature blocks normalised separately
   // (early fusion, 003_train_ae_based_ef.lua:116-124); split is a multiple of 4
   __shared__ float red[2][8];
@@ -114,7 +116,7 @@ imgnorm_drop_kernel(const float* __restrict__ fc7, float* __restrict__ vd, Drop 
 }
 
 int imgnorm_drop(cudaStream_t s, const float* fc7, float* vd, Drop d, int B, int I, int img_norm, int split, PlaneOut vp) {
-  imgnorm_drop_kernel<<<B, 256, 0, s>>>(fc7, vd, d, I, img_norm, split, vp);
+  NVQA_CUDA(launch_pdl(imgnorm_drop_kernel, dim3(B), dim3(256), 0, s, fc7, vd, d, I, img_norm, split, vp));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(256)
 lstm_gates_fwd_kernel(float* __restrict__ pre, const float* __restrict__ c_prev, int ldp, float* __restrict__ c_new,
                       float* __restrict__ h_new, int ldn, float* __restrict__ xdrop, const int32_t* __restrict__ len,
                       Drop d, int t, int T, int B, int H) {
+  pdl_entry();
   const int H4 = H >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H4) return;
@@ -150,8 +153,8 @@ lstm_gates_fwd_kernel(float* __restrict__ pre, const float* __restrict__ c_prev,
 
 int lstm_gates_fwd(cudaStream_t s, float* pre_t, const float* c_prev, int ldp, float* c_new, float* h_new, int ldn,
                    float* xdrop_next_t, const int32_t* len, Drop d, int t, int T, int B, int H) {
-  lstm_gates_fwd_kernel<<<ceil_div((int64_t)B * H / 4, 256), 256, 0, s>>>(pre_t, c_prev, ldp, c_new, h_new, ldn,
-                                                                        xdrop_next_t, len, d, t, T, B, H);
+  NVQA_CUDA(launch_pdl(lstm_gates_fwd_kernel, dim3(ceil_div((int64_t)B * H / 4, 256)), dim3(256), 0, s, pre_t, c_prev, ldp, c_new, h_new, ldn,
+                                                                        xdrop_next_t, len, d, t, T, B, H));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -161,6 +164,7 @@ struct StatePtrs { const float* c[4]; const float* h[4]; };
 
 __global__ void __launch_bounds__(256)
 qvec_fwd_kernel(StatePtrs sp, float* __restrict__ state, float* __restrict__ qd, Drop d, int B, int H, int L, PlaneOut qp) {
+  pdl_entry();
   const int S = 2 * L * H, S4 = S >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * S4) return;
@@ -179,7 +183,7 @@ int qvec_fwd(cudaStream_t s, const float* const* c_fin, const float* const* h_fi
              Drop d, int B, int H, int L, PlaneOut qp) {
   StatePtrs sp;
   for (int l = 0; l < 4; ++l) { sp.c[l] = l < L ? c_fin[l] : nullptr; sp.h[l] = l < L ? h_fin[l] : nullptr; }
-  qvec_fwd_kernel<<<ceil_div((int64_t)B * 2 * L * H / 4, 256), 256, 0, s>>>(sp, state, qd, d, B, H, L, qp);
+  NVQA_CUDA(launch_pdl(qvec_fwd_kernel, dim3(ceil_div((int64_t)B * 2 * L * H / 4, 256)), dim3(256), 0, s, sp, state, qd, d, B, H, L, qp));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -188,6 +192,7 @@ int qvec_fwd(cudaStream_t s, const float* const* c_fin, const float* const* h_fi
 __global__ void __launch_bounds__(256)
 fuse_fwd_kernel(float* __restrict__ qc, float* __restrict__ ic, float* __restrict__ zd, Drop d, int64_t n4, int skip,
                 PlaneOut zp) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 a = LD4(qc + i * 4), b = LD4(ic + i * 4);
@@ -205,7 +210,7 @@ fuse_fwd_kernel(float* __restrict__ qc, float* __restrict__ ic, float* __restric
 
 int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int C, int skip, PlaneOut zp) {
   int64_t n4 = (int64_t)B * C / 4;
-  fuse_fwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(qc, ic, zd, d, n4, skip, zp);
+  NVQA_CUDA(launch_pdl(fuse_fwd_kernel, dim3(ceil_div(n4, 256)), dim3(256), 0, s, qc, ic, zd, d, n4, skip, zp));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -215,6 +220,7 @@ int fuse_fwd(cudaStream_t s, float* qc, float* ic, float* zd, Drop d, int B, int
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ scores, const int32_t* __restrict__ labels, float* __restrict__ dscores,
                   float* __restrict__ rowloss, int32_t* __restrict__ argmax, int n, int O, float inv_n, PlaneOut dp) {
+  pdl_entry();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -252,13 +258,14 @@ softmax_ce_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
 
 int softmax_ce(cudaStream_t s, const float* scores, const int32_t* labels, float* dscores, float* rowloss,
                int32_t* argmax, int n, int O, float inv_n, PlaneOut dp) {
-  softmax_ce_kernel<<<ceil_div(n, 8), 256, 0, s>>>(scores, labels, dscores, rowloss, argmax, n, O, inv_n, dp);
+  NVQA_CUDA(launch_pdl(softmax_ce_kernel, dim3(ceil_div(n, 8)), dim3(256), 0, s, scores, labels, dscores, rowloss, argmax, n, O, inv_n, dp));
   NVQA_LAUNCHED();
   return 0;
 }
 
 // deterministic final reduction: a single CTA walks the rows in a fixed order
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ rowloss, float* __restrict__ loss, int n) {
+  pdl_entry();
   __shared__ float red[8];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) acc += rowloss[i];
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restric
 }
 
 int loss_reduce(cudaStream_t s, const float* rowloss, float* loss, int n) {
-  loss_reduce_kernel<<<1, 256, 0, s>>>(rowloss, loss, n);
+  NVQA_CUDA(launch_pdl(loss_reduce_kernel, dim3(1), dim3(256), 0, s, rowloss, loss, n));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -283,6 +290,7 @@ int loss_reduce(cudaStream_t s, const float* rowloss, float* loss, int n) {
 __global__ void __launch_bounds__(256)
 fuse_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ qc, const float* __restrict__ ic,
                 float* __restrict__ dqpre, float* __restrict__ dipre, Drop d, int64_t n4, int skip, PlaneOut qp, PlaneOut ip) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 g = LD4(dzd + i * 4), a = LD4(qc + i * 4), b = LD4(ic + i * 4), m = drop_at4(d, (uint64_t)i * 4);
@@ -300,12 +308,13 @@ fuse_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ qc, con
 int fuse_bwd(cudaStream_t s, const float* dzd, const float* qc, const float* ic, float* dqpre, float* dipre,
              Drop d, int B, int C, int skip, PlaneOut qp, PlaneOut ip) {
   int64_t n4 = (int64_t)B * C / 4;
-  fuse_bwd_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(dzd, qc, ic, dqpre, dipre, d, n4, skip, qp, ip);
+  NVQA_CUDA(launch_pdl(fuse_bwd_kernel, dim3(ceil_div(n4, 256)), dim3(256), 0, s, dzd, qc, ic, dqpre, dipre, d, n4, skip, qp, ip));
   NVQA_LAUNCHED();
   return 0;
 }
 
 __global__ void __launch_bounds__(256) mask_inplace_kernel(float* __restrict__ x, Drop d, int64_t n4) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 v = LD4(x + i * 4), m = drop_at4(d, (uint64_t)i * 4);
@@ -314,7 +323,7 @@ __global__ void __launch_bounds__(256) mask_inplace_kernel(float* __restrict__ x
 
 int mask_inplace(cudaStream_t s, float* x, Drop d, int64_t n) {
   if (d.mode == 0) return 0;
-  mask_inplace_kernel<<<ceil_div(n / 4, 256), 256, 0, s>>>(x, d, n / 4);
+  NVQA_CUDA(launch_pdl(mask_inplace_kernel, dim3(ceil_div(n / 4, 256)), dim3(256), 0, s, x, d, n / 4));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -325,6 +334,7 @@ lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__
                       const float* __restrict__ dh_in, int dh_ld, const float* __restrict__ dh_above,
                       const float* __restrict__ dc_in, int dc_ld, float* __restrict__ da, float* __restrict__ dc_out,
                       const int32_t* __restrict__ len, Drop d, int t, int T, int B, int H) {
+  pdl_entry();
   const int H4 = H >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H4) return;
@@ -360,8 +370,8 @@ lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__
 int lstm_gates_bwd(cudaStream_t s, const float* gates_t, const float* c_prev, const float* c_new,
                    const float* dh_in, int dh_ld, const float* dh_above_t, const float* dc_in, int dc_ld,
                    float* da_t, float* dc_out, const int32_t* len, Drop d_above, int t, int T, int B, int H) {
-  lstm_gates_bwd_kernel<<<ceil_div((int64_t)B * H / 4, 256), 256, 0, s>>>(
-      gates_t, c_prev, c_new, dh_in, dh_ld, dh_above_t, dc_in, dc_ld, da_t, dc_out, len, d_above, t, T, B, H);
+  NVQA_CUDA(launch_pdl(lstm_gates_bwd_kernel, dim3(ceil_div((int64_t)B * H / 4, 256)), dim3(256), 0, s, 
+      gates_t, c_prev, c_new, dh_in, dh_ld, dh_above_t, dc_in, dc_ld, da_t, dc_out, len, d_above, t, T, B, H));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -372,6 +382,7 @@ int lstm_gates_bwd(cudaStream_t s, const float* gates_t, const float* c_prev, co
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ A, int rows, int cols, int lda, int rows_per_chunk, float* __restrict__ out0,
               float* __restrict__ out1) {
+  pdl_entry();
   __shared__ float red[8][33];
   int c = blockIdx.x * 32 + (threadIdx.x & 31);
   int ry = threadIdx.x >> 5;
@@ -404,7 +415,7 @@ int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* o
   int chunks = rows >= 2048 ? 16 : rows >= 128 ? std::min(16, rows / 64) : 1;   // enough CTAs to hide the load latency
   int rpc = ceil_div(rows, chunks);
   dim3 grid(ceil_div(cols, 32), chunks);
-  colsum_kernel<<<grid, 256, 0, s>>>(A, rows, cols, lda, rpc, out0, out1);
+  NVQA_CUDA(launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, s, A, rows, cols, lda, rpc, out0, out1));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -416,6 +427,7 @@ __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ len, const float* __restrict__ y,
                  float* __restrict__ dx, float* __restrict__ dWeT, Drop d, int B, int T, int E, int V,
                  float* __restrict__ dbias) {
+  pdl_entry();
   extern __shared__ float bsum[];                // [E] column sums of this CTA (dbias != nullptr)
   if (dbias) {
     for (int j = threadIdx.x; j < E; j += blockDim.x) bsum[j] = 0.f;
@@ -459,7 +471,7 @@ int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float*
   const int threads = (256 / E4) * E4, rows_per_cta = threads / E4;
   const int64_t rows = (int64_t)T * B;
   const int grid = (int)std::min<int64_t>(ceil_div(rows, rows_per_cta), 148 * 4);
-  embed_bwd_kernel<<<grid, threads, dbias ? (size_t)E * 4 : 0, s>>>(q, len, y, dx, dWeT, d, B, T, E, V, dbias);
+  NVQA_CUDA(launch_pdl(embed_bwd_kernel, dim3(grid), dim3(threads), dbias ? (size_t)E * 4 : 0, s, q, len, y, dx, dWeT, d, B, T, E, V, dbias));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -470,6 +482,7 @@ int embed_bwd(cudaStream_t s, const int32_t* q, const int32_t* len, const float*
 __global__ void __launch_bounds__(256)
 lookup_fwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ table, float* __restrict__ x, int B, int T,
                   int E, int V, int steps) {
+  pdl_entry();
   const int E4 = E >> 2;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)(steps - 1) * B * E4) return;
@@ -484,7 +497,7 @@ lookup_fwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ tab
 int lookup_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* x, int B, int T, int E, int V, int steps) {
   int64_t total = (int64_t)(steps - 1) * B * (E / 4);
   if (total <= 0) return 0;
-  lookup_fwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(seq, table, x, B, T, E, V, steps);
+  NVQA_CUDA(launch_pdl(lookup_fwd_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, s, seq, table, x, B, T, E, V, steps));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -493,6 +506,7 @@ int lookup_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* x,
 __global__ void __launch_bounds__(256)
 lookup_bwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ dx, float* __restrict__ dtable, int B, int T,
                   int E, int V, int steps) {
+  pdl_entry();
   const int E4 = E >> 2;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)(steps - 1) * B * E4) return;
@@ -514,6 +528,7 @@ lookup_bwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ dx,
 __global__ void __launch_bounds__(256)
 lookup_bwd_hot_kernel(const int32_t* __restrict__ seq, const float* __restrict__ dx, float* __restrict__ dtable, int B, int T,
                       int E, int V, int steps, int rows_per_chunk) {
+  pdl_entry();
   __shared__ float red[2][8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
   const int64_t rows = (int64_t)(steps - 1) * B;                   // rows t*B + b, t >= 1
@@ -545,12 +560,12 @@ lookup_bwd_hot_kernel(const int32_t* __restrict__ seq, const float* __restrict__
 int lookup_bwd(cudaStream_t s, const int32_t* seq, const float* dx, float* dtable, int B, int T, int E, int V, int steps) {
   int64_t total = (int64_t)(steps - 1) * B * (E / 4);
   if (total <= 0) return 0;
-  lookup_bwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(seq, dx, dtable, B, T, E, V, steps);
+  NVQA_CUDA(launch_pdl(lookup_bwd_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, s, seq, dx, dtable, B, T, E, V, steps));
   NVQA_LAUNCHED();
   const int64_t rows = (int64_t)(steps - 1) * B;
   const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, rows / 64));
   dim3 grid(ceil_div(E, 32), chunks);
-  lookup_bwd_hot_kernel<<<grid, 256, 0, s>>>(seq, dx, dtable, B, T, E, V, steps, ceil_div(rows, chunks));
+  NVQA_CUDA(launch_pdl(lookup_bwd_hot_kernel, dim3(grid), dim3(256), 0, s, seq, dx, dtable, B, T, E, V, steps, ceil_div(rows, chunks)));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -558,6 +573,7 @@ int lookup_bwd(cudaStream_t s, const int32_t* seq, const float* dx, float* dtabl
 // dst[b][j] = drop(b*W + j) * src[b*ld + j]   (head Dropout on the encoder output; also saves the raw state)
 __global__ void __launch_bounds__(256)
 mask_copy_kernel(const float* __restrict__ src, int ld, float* __restrict__ raw, float* __restrict__ dst, Drop d, int B, int W) {
+  pdl_entry();
   const int W4 = W >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * W4) return;
@@ -568,7 +584,7 @@ mask_copy_kernel(const float* __restrict__ src, int ld, float* __restrict__ raw,
 }
 
 int mask_copy(cudaStream_t s, const float* src, int ld, float* raw, float* dst, Drop d, int B, int W) {
-  mask_copy_kernel<<<ceil_div((int64_t)B * W / 4, 256), 256, 0, s>>>(src, ld, raw, dst, d, B, W);
+  NVQA_CUDA(launch_pdl(mask_copy_kernel, dim3(ceil_div((int64_t)B * W / 4, 256)), dim3(256), 0, s, src, ld, raw, dst, d, B, W));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -578,6 +594,7 @@ int mask_copy(cudaStream_t s, const float* src, int ld, float* raw, float* dst, 
 __global__ void __launch_bounds__(256)
 rows_to_planes_kernel(const float* __restrict__ src, float* __restrict__ dst32, __nv_bfloat16* __restrict__ planes,
                       long long plane_stride, int P, int64_t n4) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = LD4(src + i * 4);
@@ -597,7 +614,7 @@ rows_to_planes_kernel(const float* __restrict__ src, float* __restrict__ dst32, 
 
 int rows_to_planes(cudaStream_t s, const float* src, float* dst32, __nv_bfloat16* planes, long long plane_stride, int P,
                    int64_t n) {
-  rows_to_planes_kernel<<<ceil_div(n / 4, 256), 256, 0, s>>>(src, dst32, planes, plane_stride, P, n / 4);
+  NVQA_CUDA(launch_pdl(rows_to_planes_kernel, dim3(ceil_div(n / 4, 256)), dim3(256), 0, s, src, dst32, planes, plane_stride, P, n / 4));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -606,6 +623,7 @@ int rows_to_planes(cudaStream_t s, const float* src, float* dst32, __nv_bfloat16
 __global__ void __launch_bounds__(256)
 clamp_rmsprop_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, int64_t n, float lr,
                      float alpha, float oma, float eps, float wd, float clampv, float gscale) {
+  pdl_entry();
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
@@ -632,7 +650,7 @@ clamp_rmsprop_kernel(float* __restrict__ x, const float* __restrict__ g, float* 
 int clamp_rmsprop(cudaStream_t s, float* x, float* g, float* m, int64_t n, float lr, float alpha, float eps,
                   float wd, float clamp, float gscale) {
   float oma = (float)(1.0 - (double)alpha);
-  clamp_rmsprop_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(x, g, m, n, lr, alpha, oma, eps, wd, clamp, gscale);
+  NVQA_CUDA(launch_pdl(clamp_rmsprop_kernel, dim3(ceil_div(ceil_div(n, 4), 256)), dim3(256), 0, s, x, g, m, n, lr, alpha, oma, eps, wd, clamp, gscale));
   NVQA_LAUNCHED();
   return 0;
 }

@@ -91,6 +91,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_entry();                      // everything above touched only this CTA's shared / tensor memory (common.cuh)
 
   if (warp == 0) {
     // ===== TMA producer: warp-uniform loop, one elected lane issues (see elect_one_sync in umma_ptx.cuh) =====
@@ -335,6 +336,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_entry();                      // everything above touched only the pair's shared / tensor memory (common.cuh)
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own A rows + own half of the B tile, bytes counted on the LEADER's full barrier =====
@@ -561,6 +563,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 template <int P>
 __global__ void __launch_bounds__(256)
 split_planes_kernel(const float* __restrict__ src, int rows, int K, int ld, int Kp, __nv_bfloat16* __restrict__ dst) {
+  pdl_entry();
   const int K4 = Kp >> 2;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * K4) return;
@@ -593,6 +596,7 @@ struct SplitJob { const float* src; __nv_bfloat16* dst; int rows, K, ld, Kp; };
 struct SplitJobs { SplitJob j[16]; };
 template <int P>
 __global__ void __launch_bounds__(256) split_planes_batched_kernel(SplitJobs jobs) {
+  pdl_entry();
   const SplitJob jb = jobs.j[blockIdx.y];
   const int K4 = jb.Kp >> 2;
   const int64_t total = (int64_t)jb.rows * K4;
@@ -721,9 +725,10 @@ static int prepare_planes_impl(UmmaWorkspace* ws, cudaStream_t s, int P, const f
     return 0;
   }
   int64_t n = (int64_t)rows * (Kp / 4);
-  if (P == 1) split_planes_kernel<1><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
-  else if (P == 2) split_planes_kernel<2><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
-  else split_planes_kernel<3><<<ceil_div(n, 256), 256, 0, s>>>(src, rows, K, ld, Kp, dst);
+  const dim3 sgrid((unsigned)ceil_div(n, 256));
+  if (P == 1) NVQA_CUDA(launch_pdl(split_planes_kernel<1>, sgrid, dim3(256), 0, s, src, rows, K, ld, Kp, dst));
+  else if (P == 2) NVQA_CUDA(launch_pdl(split_planes_kernel<2>, sgrid, dim3(256), 0, s, src, rows, K, ld, Kp, dst));
+  else NVQA_CUDA(launch_pdl(split_planes_kernel<3>, sgrid, dim3(256), 0, s, src, rows, K, ld, Kp, dst));
   NVQA_LAUNCHED();
   *out = dst;
   return 0;
@@ -763,9 +768,9 @@ int presplit_weights(UmmaWorkspace* ws, cudaStream_t s, int P, const float* cons
   }
   if (!nj) return 0;
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(most, 256), 2048), nj);
-  if (P == 1) split_planes_batched_kernel<1><<<grid, 256, 0, s>>>(jobs);
-  else if (P == 2) split_planes_batched_kernel<2><<<grid, 256, 0, s>>>(jobs);
-  else split_planes_batched_kernel<3><<<grid, 256, 0, s>>>(jobs);
+  if (P == 1) NVQA_CUDA(launch_pdl(split_planes_batched_kernel<1>, grid, dim3(256), 0, s, jobs));
+  else if (P == 2) NVQA_CUDA(launch_pdl(split_planes_batched_kernel<2>, grid, dim3(256), 0, s, jobs));
+  else NVQA_CUDA(launch_pdl(split_planes_batched_kernel<3>, grid, dim3(256), 0, s, jobs));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -876,9 +881,8 @@ static int launch_umma(cudaStream_t s, const CUtensorMap& ma, const CUtensorMap&
   const long long total = (long long)tn * tm * L.splits;
   NVQA_CHECK(total < (1ll << 31), "umma_gemm: too many tiles");
   dim3 grid((unsigned)(persist ? std::min<long long>(total, L.cta_cap > 0 ? std::min(L.cta_cap, num_sms) : num_sms) : total));
-  umma_gemm_kernel<BN, P, AMN, BMN><<<grid, UG_THREADS, Cfg::SMEM, s>>>(ma, mb, M, N, K, C, ldc, beta ? 1 : 0, b0, b1,
-                                                                        L.a_row0, L.b_row0, L.kb_per_split,
-                                                                        L.c_split_stride, tn, tm, L.splits);
+  NVQA_CUDA(launch_pdl(umma_gemm_kernel<BN, P, AMN, BMN>, grid, dim3(UG_THREADS), Cfg::SMEM, s, ma, mb, M, N, K, C, ldc,
+                       beta ? 1 : 0, b0, b1, L.a_row0, L.b_row0, L.kb_per_split, L.c_split_stride, tn, tm, L.splits));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -921,10 +925,12 @@ static int launch_umma_pair(cudaStream_t s, const CUtensorMap& ma, const CUtenso
   void* args[] = {(void*)&ma, (void*)&mb, (void*)&mc, &M, &N, &K, &C, &ldc, &beta_i, (void*)&b0, (void*)&b1, &a0, &b0r, &kbs, &cstride, &tn, &tm2, &splits};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(UG_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr; cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // common.cuh: pdl_entry() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   NVQA_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ++g_launches;
   return 0;
@@ -944,6 +950,7 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, int splits, long long stride, int M, int N, int ldp,
                      float* __restrict__ C, int ldc, int beta, const float* __restrict__ bias0,
                      const float* __restrict__ bias1) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * N) return;
   const int n = (int)(i % N);
@@ -1120,8 +1127,8 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
       NVQA_CUDA(cudaEventRecord(ws->reduce_gemm_done[defer_slot], s));
       NVQA_CUDA(cudaStreamWaitEvent(rs, ws->reduce_gemm_done[defer_slot], 0));
     }
-    splitk_reduce_kernel<<<ceil_div((long long)M * N, 256), 256, 0, rs>>>(Cout, splits, L.c_split_stride, M, N, N, C, ldc,
-                                                                         beta ? 1 : 0, bias0, bias1);
+    NVQA_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)ceil_div((long long)M * N, 256)), dim3(256), 0, rs, Cout, splits,
+                         L.c_split_stride, M, N, N, C, ldc, beta ? 1 : 0, bias0, bias1));
     NVQA_LAUNCHED();
     if (defer_slot >= 0) {
       NVQA_CUDA(cudaEventRecord(ws->reduce_done[defer_slot], rs));

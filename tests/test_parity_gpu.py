@@ -175,6 +175,41 @@ def test_gemm_engines(prec, ak, bk):
     m.close()
 
 
+@pytest.mark.parametrize("prec", [0, 2, 3])
+def test_gemm_engines_accumulate_bias_pitch(prec):
+    """nn.Linear's full contract through every engine path: C (row pitch ldc > N) = C + A.B^T + bias0 + bias1, on shapes that
+    take the CTA-pair kernel with TMA stores / the TMA reduce-add (beta), split-K (+ reduction kernel), the single-CTA
+    kernel, clipped boxes at the M and N edges, and an output pitch that forbids the TMA path (ldc % 4 != 0)."""
+    nvm = nv()
+    lib = nvm._lib.load()
+    m = nvm.Arch1Model(nvm.Arch1Config(V=8, E=4, H=4, L=1, I=4, C=4, O=3, T=2, B=2))
+    r = np.random.default_rng(11)
+    #       M     N     K   ldc  ak bk
+    for (M, N, K, ldc, ak, bk) in ((1300, 520, 192, 528, 1, 1), (1300, 520, 192, 521, 1, 1), (500, 1000, 1024, 1000, 1, 1),
+                                   (2048, 200, 2600, 200, 0, 0), (300, 2048, 512, 2052, 1, 0), (100, 64, 320, 64, 1, 1),
+                                   (13000, 512, 256, 512, 1, 0)):
+        a = r.standard_normal((M, K)).astype(np.float32)
+        b = r.standard_normal((N, K)).astype(np.float32)
+        c0 = r.standard_normal((M, ldc)).astype(np.float32)
+        b0 = r.standard_normal(N).astype(np.float32)
+        b1 = r.standard_normal(N).astype(np.float32)
+        prod = a.astype(np.float64) @ b.astype(np.float64).T
+        A_ = nvm.DeviceBuffer(m, a if ak else a.T.copy())
+        B_ = nvm.DeviceBuffer(m, b if bk else b.T.copy())
+        B0, B1 = nvm.DeviceBuffer(m, b0), nvm.DeviceBuffer(m, b1)
+        for beta, bias in ((1, True), (0, True), (1, False)):
+            C_ = nvm.DeviceBuffer(m, c0)
+            nvm._lib.check(lib.nvqa_gemm_test_ex(prec, ak, bk, M, N, K, A_.ptr, B_.ptr, C_.ptr, ldc, beta,
+                                                 B0.ptr if bias else None, B1.ptr if bias else None, None))
+            got = C_.get().reshape(M, ldc)
+            ref = prod + (c0[:, :N] if beta else 0) + ((b0 + b1) if bias else 0)
+            e2, _ = rel_err(got[:, :N], ref)
+            tol = {0: 2e-6, 2: 6e-3, 3: 1e-5}[prec]
+            assert e2 <= tol, f"prec {prec} {M}x{N}x{K} ldc {ldc} beta {beta} bias {bias}: rel-l2 {e2:.3e}"
+            np.testing.assert_array_equal(got[:, N:], c0[:, N:])      # the pitch padding is never written
+    m.close()
+
+
 def test_module_level_cell_and_criterion():
     """LSTM.lstm_conventional():forward and nn.CrossEntropyCriterion through their C-ABI entry points."""
     nvm = nv()
