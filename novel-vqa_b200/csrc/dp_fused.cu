@@ -318,7 +318,10 @@ extern "C" int nvqa_dp_train_step(nvqa_model* m, float lr, uint64_t seed, float 
   static int overlap_env = -2;
   if (overlap_env == -2) { const char* e = getenv("NVQA_DP_OVERLAP"); overlap_env = e ? atoi(e) : -1; }
   const int overlap = overlap_env >= 0 ? overlap_env : (m->dp_world >= 4 ? 1 : 0);
-  NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
+  m->fused_step = true;            // a backward follows: its gradient slices are cleared beside the forward (model.cu)
+  const int frc = nvqa_forward(m, NVQA_MODE_TRAIN, seed);
+  m->fused_step = false;
+  NVQA_TRY(frc);
   if (m->cfg.arch != 1 || !overlap || m->profiling) {
     NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
     return nvqa_dp_rmsprop_step(m, lr, alpha, eps, wd, clamp);

@@ -248,8 +248,12 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
     }
     int it = 0;
     const int gokb = (NST < KB ? NST : KB) - 1;
+    // programmatic dependent launch (common.cuh): everything above read only this step's weight planes, which are older
+    // than the predecessor kernel; the pre-activations, h_0 and the counters are read from here on
+    pdl_wait();
     // warp-uniform loop, one elected lane issues (see elect_one_sync): a TMA issue under `if (lane == 0)` costs ~300 cycles
     for (int t = 0; t < T; ++t) {
+      if (t == T - 1 && lane == 0) pdl_trigger();     // last step: the next kernel of the stream may become resident
       if (CL && t > 0) { __syncwarp(); v2_cluster_arrive(); v2_cluster_wait(); }    // phase t: h_{t-1} published by all 16 CTAs
 #pragma unroll 1
       for (int sub = 0; sub < NS; ++sub) {
@@ -454,6 +458,7 @@ lstm_fwd_v2_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_consta
     }
     v2_bar_sync(1, V2_EPI);
     if (P >= 2 && threadIdx.x == 64) mbar_arrive(w1bar);      // hand the TMEM-resident operand to the MMA thread
+    pdl_wait();                                                // (see the TMA warp) c_0 and the pre-activations from here on
     const long long t_prologue = DBG ? clock64() : 0;          // W planes resident (this thread's share), barriers up
     long long t_step0 = 0;
     float ccarry[8];
@@ -1579,8 +1584,10 @@ lstm_bwd_v4_kernel(const __grid_constant__ CUtensorMap mapW, const __nv_bfloat16
           tma_load_3d(w0 + (uint32_t)kb * W_KB + (uint32_t)cc * 8192, &mapW, wfull, c0 + 64 * cc, k_base + kb * 64, 1);
     }
     __syncwarp();
+    pdl_wait();                                     // (common.cuh) only the weight planes were read above
     int it = 0;
     for (int t = T - 1; t >= tlast; --t) {
+      if (t == tlast && lane == 0) pdl_trigger();   // last step: the next kernel of the stream may become resident
       const unsigned int k = (unsigned int)(T - 1 - t);
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
@@ -1673,6 +1680,7 @@ lstm_bwd_v4_kernel(const __grid_constant__ CUtensorMap mapW, const __nv_bfloat16
     }
     v2_bar_sync(1, V2_EPI);
     if (et == 0) mbar_arrive(w1bar);
+    pdl_wait();                                              // gates, c, dh0 / dc0, dh_above from here on
     const int sub = ch;                                      // this warp's sub-tile
     const int lt = et & 127;                                 // thread within the sub-tile group
     const int bid = 2 + 3 * sub;                             // named barriers bid, bid + 1, bid + 2 (128 threads each)
@@ -1885,6 +1893,8 @@ bool lstm_fwd_v2_supported(int P, int H) { return v2_enabled() && P >= 1 && P <=
 int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float* Wh, float* pre, float* c, float* h,
                            __nv_bfloat16* hp, long long hp_plane_rows, float* xdrop_next, const int32_t* len, Drop d, int T,
                            int B, int H, unsigned int* counter, __nv_bfloat16* xdrop_planes, long long xdrop_plane_stride) {
+  const bool ctr_zeroed = ws && ws->ctr_zeroed;
+  if (ws) ws->ctr_zeroed = false;
   if (!v2_enabled()) return -1;
   if (P < 1 || P > 2) return -1;
   if (H % 64 != 0 || H != 512) return -1;          // the W slice (plane 0: SMEM, plane 1: 256 TMEM columns) is sized for K = 512
@@ -1912,7 +1922,15 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
 
   __nv_bfloat16* wp = nullptr;
   int pitch = 0;
+  const int64_t launches0 = g_launches;
   NVQA_TRY(prepare_planes(ws, s, P, Wh, 4 * H, H, H, true, &wp, &pitch));
+  // programmatic dependent launch: the kernel's prologue reads the weight planes BEFORE griddepcontrol.wait, so they must
+  // be older than the predecessor kernel (cached since the start of the pass, not split just now); and only a launch that
+  // directly follows a kernel (no counter memset in between) gains anything
+  // Measured on B200 (round 2): 1.365 ms per step with and without -- the cooperative launches gain nothing.  Default off.
+  static int rec_pdl = -1;
+  if (rec_pdl < 0) { const char* e = getenv("NVQA_LSTM_PDL"); rec_pdl = e ? atoi(e) : 0; }
+  const bool w_cached = g_launches == launches0;
   CUtensorMap mapW, mapH;
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 32, &mapW));
   if (hp_plane_rows <= 0) hp_plane_rows = (long long)(T + 1) * B;
@@ -1936,7 +1954,7 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
   for (int tile0 = 0; tile0 < tiles; tile0 += max_tiles) {
     int b0 = tile0 * 64, bend = std::min(B, (tile0 + max_tiles) * 64);
     dim3 grid(H / 32, ceil_div(bend - b0, 64));
-    NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
+    if (!(ctr_zeroed && tile0 == 0)) NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.y, s));
     // NVQA_LSTM_W1TMEM=<n <= 6>: k-blocks of the shared-memory plane that also sit in tensor memory (pair + 4-D box kernel).
     // Measured on B200 (round 2): 0.384 (6) / 0.387 (4) against 0.376 ms (0) per step pair -- the 24 cheaper instructions of
     // a step do not shorten its chain (the MMA phase is not what the forward step waits for).  Default 0.
@@ -1981,16 +1999,33 @@ int lstm_fwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     NVQA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(V2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = use_pair ? 2 : 1;
-    if (use_pair && v2_nocoop()) { cfg.attrs = attr + 1; cfg.numAttrs = 1; }   // profilers: see v2_nocoop
+    // attributes: [cooperative] [cluster 2 x 1 (pairs)] [programmatic stream serialization]
+    cudaLaunchAttribute attr[3];
+    int na = 0;
+    const bool coop = !(use_pair && v2_nocoop());                              // profilers: see v2_nocoop
+    if (coop) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na; }
+    if (use_pair) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    const bool pdl = rec_pdl > 0 && pdl_enabled() && w_cached && ctr_zeroed && tile0 == 0;
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
-    if (le != cudaSuccess && use_pair && cfg.numAttrs == 2) {
+    if (le != cudaSuccess && pdl) {
+      (void)cudaGetLastError();                     // refused with the programmatic attribute: fully serialised from now on
+      rec_pdl = 0;
+      cfg.numAttrs = --na;
+      le = cudaLaunchKernelExC(&cfg, fn, args);
+    }
+    if (le != cudaSuccess && use_pair && coop) {
       (void)cudaGetLastError();                     // refused as cooperative + clustered: same grid without the co-residency check
-      cfg.attrs = attr + 1; cfg.numAttrs = 1;
+      cfg.attrs = attr + 1; cfg.numAttrs = na - 1;
       le = cudaLaunchKernelExC(&cfg, fn, args);
     }
     NVQA_CUDA(le);
@@ -2021,6 +2056,8 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
                            const float* dh0, const float* dc0, int ld0, const float* dh_above, Drop d, float* dasum,
                            __nv_bfloat16* dap, long long dap_plane_rows, float* dhbuf, float* dh_init, float* dc_init,
                            const int32_t* len, int T, int B, int H, unsigned int* counter) {
+  const bool ctr_zeroed = ws && ws->ctr_zeroed;
+  if (ws) ws->ctr_zeroed = false;
   if (!v2_enabled()) return -1;
   if ((dh_init == nullptr) != (dc_init == nullptr)) return -1;
   if (P < 1 || P > 2) return -1;
@@ -2043,7 +2080,11 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
 
   __nv_bfloat16* wp = nullptr;
   int pitch = 0;
+  const int64_t launches0 = g_launches;
   NVQA_TRY(prepare_planes(ws, s, P, Wh, 4 * H, H, H, true, &wp, &pitch));
+  static int rec_pdl = -1;                          // programmatic dependent launch: see lstm_fwd_persistent_v2
+  if (rec_pdl < 0) { const char* e = getenv("NVQA_LSTM_PDL"); rec_pdl = e ? atoi(e) : 0; }
+  const bool w_cached = g_launches == launches0;
   CUtensorMap mapW, mapDA;
   NVQA_TRY(get_map(ws, wp, 4 * H, pitch, P, 64, &mapW));              // MN-major A: boxes of 64 k-rows x 64 columns
   if (dap_plane_rows <= 0) dap_plane_rows = (long long)T * B;
@@ -2074,20 +2115,37 @@ int lstm_bwd_persistent_v2(cudaStream_t s, UmmaWorkspace* ws, int P, const float
     for (int tile0 = 0; tile0 < tiles && ok4; tile0 += max_tiles) {
       int b0 = tile0 * 64, bend = std::min(B, (tile0 + max_tiles) * 64);
       dim3 grid(H / 128, 4, ceil_div(bend - b0, 64));
-      NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.z, s));
+      if (!(ctr_zeroed && tile0 == 0)) NVQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * 32 * grid.z, s));
       void* a4[] = {&mapW, &wt4, &pitch, &gates, &c, &dh0, &dc0, &ld0, &dh_above, &d, &dasum, &dap, &dap_plane, &dh_init, &dc_init,
                     &len, &T, &B, &H, &KBv, &counter, &poll_ns4, &b0, &bend, &mapDA4s};
       cudaLaunchConfig_t cfg4 = {};
       cfg4.gridDim = grid; cfg4.blockDim = dim3(V2_THREADS); cfg4.dynamicSmemBytes = smem4; cfg4.stream = s;
-      cudaLaunchAttribute at4[2];
-      at4[0].id = cudaLaunchAttributeClusterDimension;
-      at4[0].val.clusterDim.x = 1; at4[0].val.clusterDim.y = 4; at4[0].val.clusterDim.z = 1;
-      at4[1].id = cudaLaunchAttributeCooperative; at4[1].val.cooperative = 1;
-      cfg4.attrs = at4; cfg4.numAttrs = v2_nocoop() ? 1 : 2;
+      // attributes: cluster 1 x 4, [programmatic stream serialization], [cooperative] (last: dropped first on refusal)
+      cudaLaunchAttribute at4[3];
+      int na = 0;
+      at4[na].id = cudaLaunchAttributeClusterDimension;
+      at4[na].val.clusterDim.x = 1; at4[na].val.clusterDim.y = 4; at4[na].val.clusterDim.z = 1;
+      ++na;
+      const bool pdl = rec_pdl > 0 && pdl_enabled() && w_cached && ctr_zeroed && tile0 == 0;
+      if (pdl) {
+        at4[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at4[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+      }
+      const bool coop = !v2_nocoop();
+      if (coop) { at4[na].id = cudaLaunchAttributeCooperative; at4[na].val.cooperative = 1; ++na; }
+      cfg4.attrs = at4; cfg4.numAttrs = na;
       cudaError_t le = cudaLaunchKernelExC(&cfg4, f4, a4);
-      if (le != cudaSuccess && cfg4.numAttrs == 2) {
+      if (le != cudaSuccess && pdl) {
+        (void)cudaGetLastError();                   // refused with the programmatic attribute: fully serialised from now on
+        rec_pdl = 0;
+        if (coop) at4[na - 2] = at4[na - 1];
+        cfg4.numAttrs = --na;
+        le = cudaLaunchKernelExC(&cfg4, f4, a4);
+      }
+      if (le != cudaSuccess && coop) {
         (void)cudaGetLastError();
-        cfg4.numAttrs = 1;
+        cfg4.numAttrs = na - 1;
         le = cudaLaunchKernelExC(&cfg4, f4, a4);
       }
       if (le != cudaSuccess) {

@@ -372,7 +372,7 @@ static int model_create_impl(const nvqa_config* cfg, nvqa_model* m) {
   NVQA_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->ans_host), (size_t)B * 4));
   m->planes = cfg->precision == NVQA_PREC_BF16X3 ? 3 : cfg->precision == NVQA_PREC_BF16X2 ? 2
               : cfg->precision == NVQA_PREC_BF16 ? 1 : 0;
-  NVQA_TRY(dallocT(m, &m->grid_counter, 1024));    // per-CTA barrier flags of the persistent kernels
+  NVQA_TRY(dallocT(m, &m->grid_counter, 8 * 512)); // step-barrier counters of the persistent kernels (model.cuh)
   if (m->planes) {
     for (int l = 0; l < L; ++l) {
       NVQA_TRY(dallocT(m, &m->hp[l], (size_t)m->planes * (N + B) * H));
@@ -624,6 +624,24 @@ struct AuxScope {
 };
 static bool aux_usable(const nvqa_model* m) { return m->aux_enabled && !m->profiling && m->cfg.arch == 1 && m->planes > 0; }
 
+// arch 1: everything a backward pass accumulates into with atomics -- the bias gradients (column sums), the embedding
+// scatter -- and the step-barrier counters of its recurrent kernels, cleared by ONE launch on m->stream
+static int backward_prezero(nvqa_model* m) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("NVQA_PREZERO"); on = e ? atoi(e) : 1; }
+  if (!on) return 0;                                  // every phase clears its own slices with cudaMemsetAsync (round 2 start)
+  const nvqa_config& c = m->cfg;
+  ZeroSegs z;
+  z.add(m->gbc, c.O); z.add(m->gbq, c.C); z.add(m->gbv, c.C);
+  for (int l = 0; l < c.L; ++l) { z.add(m->lg[l].bi, 4 * c.H); z.add(m->lg[l].bh, 4 * c.H); }
+  z.add(m->gWeT, m->n_blk[1]);
+  z.add(m->grid_counter + 4 * 512, 4 * 512);
+  NVQA_TRY(zero_segments(m->stream, z));
+  m->prezero_mask = 7u;
+  m->ctr_zero_mask |= 0xF0u;
+  return 0;
+}
+
 // forward image branch of arch 1: fc7 L2 norm + AxB's Dropout on i + Linear(I, C) -> ic (pre-tanh).  to_side: called from
 // the hook in front of the first recurrent kernel; otherwise (no persistent kernel ran) inline on the main stream.
 static int aux_launch_fwd(nvqa_model* m, bool to_side) {
@@ -646,6 +664,9 @@ static int aux_launch_fwd(nvqa_model* m, bool to_side) {
       NVQA_CUDA(cudaEventRecord(m->fc7_consumed, m->stream));
     }
     NVQA_TRY(gemm(m, CAT_HEAD_FWD, true, true, m->B, c.C, c.I, m->vd, c.I, m->Wv, c.I, m->ic, c.C, false, m->bv));
+    // a fused training step: the gradient slices of the coming backward are cleared here, beside the recurrent kernel
+    // (the previous step's optimizer and exchange have finished with the gradient vector: they precede this forward)
+    if (side && m->fused_step && m->mode == NVQA_MODE_TRAIN) NVQA_TRY(backward_prezero(m));
     if (side) NVQA_CUDA(cudaEventRecord(m->aux_join, m->stream));
   }
   m->aux_fwd_inflight = side;
@@ -656,6 +677,13 @@ static int aux_join_main(nvqa_model* m) {
   if (m->aux_fwd_inflight || m->aux_bwd_inflight) NVQA_CUDA(cudaStreamWaitEvent(m->stream, m->aux_join, 0));
   m->aux_fwd_inflight = m->aux_bwd_inflight = false;
   return 0;
+}
+
+// the step-barrier counters of a persistent launch: its own slot, flagged to the launcher if still clear
+static unsigned int* ctr_slot(nvqa_model* m, int slot) {
+  if (m->ws) m->ws->ctr_zeroed = (m->ctr_zero_mask >> slot) & 1u;
+  m->ctr_zero_mask &= ~(1u << slot);
+  return m->grid_counter + 512 * slot;
 }
 
 static Drop lstm_drop(const nvqa_model* m, int l /* between layer l and l+1 */) {
@@ -699,12 +727,13 @@ static int lstm_layers_forward(nvqa_model* m, const LstmSeg& sg, const int32_t* 
       // Dropout(h_t) for the layer above leaves the recurrent kernel as bf16 planes (it is only ever a GEMM operand)
       PlaneOut xp;
       if (xnext && lstm_fwd_v2_supported(m->planes, H)) xp = producer_planes(m, xnext, T * B, H);
+      unsigned int* ctr = ctr_slot(m, l);
       int rc = lstm_fwd_persistent_v2(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
-                                      (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter, xp.p,
+                                      (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, ctr, xp.p,
                                       xp.stride);
       if (rc < 0)
         rc = lstm_fwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, pre, cb, hb, m->hp[l] + r0 * H,
-                                 (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, m->grid_counter);
+                                 (long long)(m->TS + 1) * c.B, xnext, len, lstm_drop(m, l), T, B, H, ctr);
       if (rc > 0) return rc;
       m->hp_valid[l] = rc == 0;
       if (rc == 0) continue;
@@ -854,6 +883,10 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
   m->mode = mode; m->seed = seed;
   umma_workspace_new_forward(m->ws);        // this forward rewrites the activations: their cached planes are stale
+  m->prezero_mask = 0;
+  // step-barrier counters of the forward recurrent kernels: one clear here instead of one in front of every launch
+  NVQA_CUDA(cudaMemsetAsync(m->grid_counter, 0, sizeof(unsigned int) * 4 * 512, m->stream));
+  m->ctr_zero_mask = (m->ctr_zero_mask & ~0xFu) | 0xFu;
   // weight matrices -> bf16 planes in one launch (no-op while they are cached); arch 1's multimodal weights follow on the
   // side stream (aux_launch_fwd)
   NVQA_TRY(presplit_step_weights(m, m->cfg.arch == 1 ? 1 : 0));
@@ -1007,10 +1040,13 @@ static int backward_head(nvqa_model* m) {
   const int B = m->B, S = m->S, C = c.C, O = c.O, I = c.I;
   cudaStream_t s = m->stream;
   // bias gradients and the embedding scatter accumulate with atomics: clear them (weight gradients
-  // are written with beta = 0 by exactly one GEMM each)
-  NVQA_CUDA(cudaMemsetAsync(m->gbc, 0, (size_t)O * 4, s));
-  NVQA_CUDA(cudaMemsetAsync(m->gbq, 0, (size_t)C * 4, s));
-  NVQA_CUDA(cudaMemsetAsync(m->gbv, 0, (size_t)C * 4, s));
+  // are written with beta = 0 by exactly one GEMM each) -- unless backward_prezero already has
+  if (m->prezero_mask & 1u) m->prezero_mask &= ~1u;
+  else {
+    NVQA_CUDA(cudaMemsetAsync(m->gbc, 0, (size_t)O * 4, s));
+    NVQA_CUDA(cudaMemsetAsync(m->gbq, 0, (size_t)C * 4, s));
+    NVQA_CUDA(cudaMemsetAsync(m->gbv, 0, (size_t)C * 4, s));
+  }
   // Linear(C,O) backward: the input gradient first; the weight gradient joins the deferred ones below
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, C, O, m->dscores, O, m->Wc, C, m->dzd, C, false));
   // Dropout, CMulTable, Tanh backward
@@ -1099,13 +1135,14 @@ static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t*
     if (m->planes && m->use_persistent) {
       // K9: the whole backward recurrence of this layer in one persistent cooperative kernel
       ProfScope ps(m, CAT_REC_BWD, 2.0 * (T - (want_init ? 0 : 1)) * B * 4.0 * H * H);
+      unsigned int* ctr = ctr_slot(m, 4 + l);
       rc = lstm_bwd_persistent_v2(s, m->ws, m->planes, sg.w[l].Wh, gates, cb, dh_in, dc_in, ld, dh_above, dabove, da,
                                   m->dap + r0 * 4 * H, (long long)m->TS * c.B, m->dhbuf, want_init ? m->dh_init : nullptr,
-                                  want_init ? m->dc_init : nullptr, len, T, B, H, m->grid_counter);
+                                  want_init ? m->dc_init : nullptr, len, T, B, H, ctr);
       if (rc < 0)
         rc = lstm_bwd_persistent(s, m->ws, m->planes, sg.w[l].Wh, gates, cb, dh_in, dc_in, ld, dh_above, dabove, da,
                                  m->dap + r0 * 4 * H, (long long)m->TS * c.B, m->dhbuf, want_init ? m->dh_init : nullptr,
-                                 want_init ? m->dc_init : nullptr, len, T, B, H, m->grid_counter);
+                                 want_init ? m->dc_init : nullptr, len, T, B, H, ctr);
       if (rc > 0) return rc;
     }
     m->dap_valid = rc == 0;
@@ -1123,8 +1160,10 @@ static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t*
       NVQA_CUDA(cudaMemcpyAsync(m->dc_init, m->dc_carry, (size_t)BH * 4, cudaMemcpyDeviceToDevice, s));
     }
     const float* X = (l == 0 ? m->y : m->xdrop[l]) + r0 * in;
-    NVQA_CUDA(cudaMemsetAsync(sg.g[l].bi, 0, (size_t)4 * H * 4, s));
-    NVQA_CUDA(cudaMemsetAsync(sg.g[l].bh, 0, (size_t)4 * H * 4, s));
+    if (!(m->prezero_mask & 2u)) {
+      NVQA_CUDA(cudaMemsetAsync(sg.g[l].bi, 0, (size_t)4 * H * 4, s));
+      NVQA_CUDA(cudaMemsetAsync(sg.g[l].bh, 0, (size_t)4 * H * 4, s));
+    }
     // sum over timestep clones of accGradParameters (:323-326) as one GEMM over all (t,b) rows.  Nobody on this stream
     // waits for these weight gradients: their split-K reductions run on the side stream beside the next GEMM.
     static int defer_red = -1;
@@ -1177,6 +1216,7 @@ static int backward_lstm(nvqa_model* m) {
   for (int l = 0; l < L; ++l) { dh0[l] = m->dqd + (2 * l + 1) * H; dc0[l] = m->dqd + (2 * l) * H; }
   NVQA_TRY(aux_launch_bwd(m, m->planes && m->use_persistent));      // the AxB weight gradients run beside the recurrent kernels
   NVQA_TRY(lstm_layers_backward(m, m->cfg.T, m->len, dh0, dc0, m->S));
+  m->prezero_mask &= ~2u;
   if (m->aux_reduce_used) {       // deferred split-K reductions of the weight gradients are the last work on the side stream
     NVQA_CUDA(cudaEventRecord(m->aux_join, m->aux_stream));
     m->aux_bwd_inflight = true;
@@ -1191,7 +1231,8 @@ static int backward_embed(nvqa_model* m) {
   const nvqa_config& c = m->cfg;
   cudaStream_t s = m->stream;
   ProfScope ps(m, CAT_PW_BWD, 0);
-  NVQA_CUDA(cudaMemsetAsync(m->gWeT, 0, (size_t)m->n_blk[1] * 4, s));
+  if (m->prezero_mask & 4u) m->prezero_mask &= ~4u;
+  else NVQA_CUDA(cudaMemsetAsync(m->gWeT, 0, (size_t)m->n_blk[1] * 4, s));
   // (gWeT and the bias gradient gbe are one contiguous block: both were cleared above)
   NVQA_TRY(embed_bwd(s, m->q, m->len, m->y, m->dxbuf, m->gWeT, make_drop(m, m->mk_emb, STREAM_EMB), m->B, c.T, c.E, c.V, m->gbe));
   return 0;
@@ -1208,6 +1249,7 @@ extern "C" int nvqa_backward(nvqa_model* m, int phase) {
   // final: the AxB weight gradients are deferred to the side stream only when the LSTM phase follows in this very call
   const bool defer_saved = m->defer_head;
   if (phase == NVQA_PHASE_ALL) m->defer_head = true;
+  if (phase == NVQA_PHASE_ALL && m->cfg.arch == 1 && m->prezero_mask != 7u) NVQA_TRY(backward_prezero(m));
   int rc = 0;
   if (phase == NVQA_PHASE_HEAD || phase == NVQA_PHASE_ALL) rc = backward_head(m);
   m->defer_head = defer_saved;
@@ -1327,7 +1369,10 @@ extern "C" int nvqa_state_get(nvqa_model* m, float* dst) {
 // block's clamp + RMSprop follow its weight gradients on the side stream, beside the LSTM backward.
 extern "C" int nvqa_train_step(nvqa_model* m, float lr, uint64_t seed) {
   NVQA_CHECK(m, "null model");
-  NVQA_TRY(nvqa_forward(m, NVQA_MODE_TRAIN, seed));
+  m->fused_step = true;
+  const int frc = nvqa_forward(m, NVQA_MODE_TRAIN, seed);
+  m->fused_step = false;
+  NVQA_TRY(frc);
   if (m->cfg.arch == 3) {
     NVQA_TRY(nvqa_backward(m, NVQA_PHASE_ALL));
     // grad_clip 0.1, weight_decay 1e-6, adam(alpha .8, beta .999, eps 1e-8)  (001_train_arch1_text_autoencoder.lua:35,40-45,237-243)

@@ -49,7 +49,11 @@ struct nvqa_model {
   __nv_bfloat16* hp[4] = {};        // bf16 planes of h per layer [P][(T+1)B][H] (persistent recurrent kernels)
   __nv_bfloat16* dap = nullptr;     // bf16 planes of da [P][T*B][4H] (persistent backward kernel)
   float* dhbuf = nullptr;           // [2][4][B][H] split-K partials of dh
-  unsigned int* grid_counter = nullptr;
+  unsigned int* grid_counter = nullptr;    // 8 slots of 512 words: forward layer l -> slot l, backward layer l -> slot 4 + l
+  uint32_t ctr_zero_mask = 0;              // slots cleared at the start of the pass and not used since
+  uint32_t prezero_mask = 0;               // backward phases (1 head, 2 LSTM, 4 embedding) whose atomically accumulated gradient
+                                           // slices were already cleared by backward_prezero (one launch instead of 8 memsets)
+  bool fused_step = false;                 // inside nvqa_train_step / nvqa_dp_train_step: a backward follows this forward
   int planes = 0;                   // bf16 planes per operand of the tensor-core modes (0 = SIMT)
   bool use_persistent = true;
   // arch2 (003_train_vqa_arch2): image projection, LookupTable, head on the top-layer h

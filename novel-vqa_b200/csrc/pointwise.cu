@@ -655,4 +655,29 @@ int clamp_rmsprop(cudaStream_t s, float* x, float* g, float* m, int64_t n, float
   return 0;
 }
 
+
+__global__ void __launch_bounds__(256) zero_segments_kernel(ZeroSegs z) {
+  pdl_entry();
+  uint32_t* p = reinterpret_cast<uint32_t*>(z.p[blockIdx.y]);
+  const long long n = z.n[blockIdx.y];
+  const long long head = min(n, (long long)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / 4);   // words up to 16-byte alignment
+  const long long n4 = (n - head) / 4;
+  uint4* p4 = reinterpret_cast<uint4*>(p + head);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    p4[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (blockIdx.x == 0) {
+    for (long long i = threadIdx.x; i < head; i += blockDim.x) p[i] = 0u;
+    for (long long i = head + 4 * n4 + threadIdx.x; i < n; i += blockDim.x) p[i] = 0u;
+  }
+}
+
+int zero_segments(cudaStream_t s, const ZeroSegs& z) {
+  if (z.count == 0) return 0;
+  long long most = 0;
+  for (int i = 0; i < z.count; ++i) most = std::max(most, z.n[i]);
+  dim3 grid((unsigned)std::min<long long>(ceil_div(ceil_div(most, 4), 256), 592), z.count);
+  NVQA_CUDA(launch_pdl(zero_segments_kernel, grid, dim3(256), 0, s, z));
+  NVQA_LAUNCHED();
+  return 0;
+}
 }  // namespace nvqa

@@ -83,4 +83,15 @@ int lm_grad(cudaStream_t s, float* lp, int rows, int ld, int ncols, const int32_
 int clamp_adam(cudaStream_t s, float* x, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                float eps, float wd, float clamp, float gscale, int64_t t);
 
+
+// Clears up to 16 device segments (32-bit words) with ONE launch: the atomically accumulated gradient slices (biases,
+// embedding scatter) and the step-barrier counters of a backward pass, instead of a dozen cudaMemsetAsync nodes that each
+// cost a stream round trip and break the programmatic-launch chain (common.cuh).
+struct ZeroSegs {
+  void* p[16];
+  long long n[16];      // 32-bit words
+  int count = 0;
+  void add(void* ptr, long long words) { if (ptr && words > 0 && count < 16) { p[count] = ptr; n[count] = words; ++count; } }
+};
+int zero_segments(cudaStream_t s, const ZeroSegs& z);
 }  // namespace nvqa

@@ -57,6 +57,9 @@ struct UmmaWorkspace {
   // layers) can run on a second stream beside the NEXT GEMM: while reduce_stream is set, the partials of such a GEMM go
   // to one of two dedicated slots at the end of the buffer and the reduction kernel is enqueued on reduce_stream
   // (event-ordered behind the GEMM; a slot is reused only after its previous reduction has finished).
+  // hint for the persistent LSTM launchers: the step-barrier counters they were handed are already zero (cleared together
+  // with everything else at the start of the pass); consumed (reset) by the launcher, valid for its first batch window
+  bool ctr_zeroed = false;
   cudaStream_t reduce_stream = nullptr;
   cudaEvent_t reduce_gemm_done[2] = {nullptr, nullptr}, reduce_done[2] = {nullptr, nullptr};
   bool reduce_pending[2] = {false, false};

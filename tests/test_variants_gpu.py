@@ -24,6 +24,8 @@ VARIANTS = [
     ("gemm_shape_rule_round1", {"NVQA_GEMM_SHAPE_V2": "0"}),
     ("gemm_st_global_epilogue", {"NVQA_GEMM_TMA_STORE": "0"}),
     ("no_programmatic_dependent_launch", {"NVQA_PDL": "0"}),
+    ("recurrent_kernels_programmatic_launch", {"NVQA_LSTM_PDL": "1"}),
+    ("memset_per_phase", {"NVQA_PREZERO": "0"}),
     ("fwd_no_pairs_no_split", {"NVQA_LSTM_PAIR": "0", "NVQA_LSTM_FWD_SPLIT": "0"}),
     ("bwd_pairs_8cta_clusters", {"NVQA_LSTM_BWD_SPLIT": "0", "NVQA_LSTM_BWD_PAIR": "1"}),
     ("bwd_stacked_mma", {"NVQA_LSTM_BWD_STACK": "1"}),

@@ -6,7 +6,7 @@ NVQA_GEMM_TMA_STORE=$1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cp
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 c={x['kernel']:round(x['ms_per_step'],4) for x in d['roofline']['classes']}
-x=d.get('extras',{})
+x=d.get('extras') or {}
 def g(k):
     v=x.get(k,{})
     return round(v.get('value',0)) if isinstance(v,dict) else v

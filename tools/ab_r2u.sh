@@ -5,7 +5,7 @@ run() {
 NVQA_PDL=$1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-x=d.get('extras',{})
+x=d.get('extras') or {}
 def g(k):
     v=x.get(k,{})
     return round(v.get('value',0)) if isinstance(v,dict) else v
