@@ -929,7 +929,10 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(softmax_ce(s, m->scores, m->labels, m->labels ? m->dscores : nullptr, m->rowloss, m->argmax, B, c.O,
                         1.0f / (float)B, m->labels ? producer_planes(m, m->dscores, B, c.O) : PlaneOut()));
-    if (m->labels) NVQA_TRY(loss_reduce(s, m->rowloss, m->loss, B));
+    // the scalar loss is not an input of the backward: in a fused step its reduction leaves the critical path and rides
+    // with the deferred weight gradients (aux_launch_bwd)
+    m->loss_pending = m->labels && m->fused_step && aux_usable(m) && m->use_persistent;
+    if (m->labels && !m->loss_pending) NVQA_TRY(loss_reduce(s, m->rowloss, m->loss, B));
   }
   m->fwd_done = true;
   return 0;
@@ -938,6 +941,10 @@ extern "C" int nvqa_forward(nvqa_model* m, int mode, uint64_t seed) {
 extern "C" int nvqa_loss(nvqa_model* m, float* out) {
   NVQA_CHECK(m && out && m->fwd_done && (m->labels || m->cfg.arch == 3), "nvqa_loss: forward with labels has not run");
   NVQA_CUDA(cudaSetDevice(m->cfg.device));
+  if (m->loss_pending) {             // a fused forward whose backward never came: reduce the row losses now
+    m->loss_pending = false;
+    NVQA_TRY(loss_reduce(m->stream, m->rowloss, m->loss, m->B));
+  }
   NVQA_CUDA(cudaMemcpyAsync(m->loss_host, m->loss, 4, cudaMemcpyDeviceToHost, m->stream));
   NVQA_CUDA(cudaStreamSynchronize(m->stream));
   *out = m->loss_host[0];
@@ -1084,6 +1091,10 @@ int aux_launch_bwd(nvqa_model* m, bool to_side) {
   }
   {
     AuxScope as(m, side);
+    if (m->loss_pending) {
+      m->loss_pending = false;
+      NVQA_TRY(loss_reduce(m->stream, m->rowloss, m->loss, B));
+    }
     NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, c.O, C, B, m->dscores, c.O, m->zd, C, m->gWc, C, false));
     NVQA_TRY(colsum(m->stream, m->dscores, B, c.O, c.O, m->gbc, nullptr));
     NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, C, S, B, m->dqpre, C, m->qd, S, m->gWq, S, false));

@@ -124,6 +124,7 @@ struct nvqa_model {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   bool aux_fwd = false, aux_bwd = false, aux_fwd_inflight = false, aux_bwd_inflight = false, aux_reduce_used = false;
+  bool loss_pending = false;               // fused step: the batch-mean reduction of the row losses rides with aux_launch_bwd
   int aux_enabled = -1;              // NVQA_AUX_STREAM (default 1); 0: everything on the main stream
   bool defer_head = false;           // the head backward may leave the AxB weight gradients to the side stream
   // nvqa_train_step: the multimodal block's clamp + RMSprop follows its weight gradients on the side stream (none of its

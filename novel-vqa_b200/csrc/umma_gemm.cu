@@ -1023,10 +1023,13 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
       // machine better -- weight gradients [2048 x 512], K = 13000: 16 pair tiles x 4 splits = 64 of 74 pairs busy for 51
       // k-blocks against x 9 = 144 units = 2 waves of 23
       const int units = (BN >= 128 ? mrows : mt) * ceil_div(N, BN), sl = BN >= 128 ? slots : num_sms;
+      // a split product also costs a reduction kernel on the stream (~4 us with its launch), expressed in k-blocks of this
+      // tile width (~6 BN cycles each); free when the reduction is deferred to the side stream
+      const int red_kb = ws->reduce_stream && !ws->side ? 0 : 8000 / (6 * BN);
       long best = -1;
       for (int sp = 1; sp <= 16 && sp <= (nkb / 8 > 1 ? nkb / 8 : 1); ++sp) {
         const int kbs = ceil_div(nkb, sp), eff = ceil_div(nkb, kbs);
-        const long cost = (long)ceil_div(units * eff, sl) * (kbs + 3);
+        const long cost = (long)ceil_div(units * eff, sl) * (kbs + 3) + (eff > 1 ? red_kb : 0);
         if (best < 0 || cost < best) { best = cost; splits = eff; }
       }
     } else {
