@@ -276,7 +276,9 @@ def run_ours(args):
             return out
 
         mine = np.zeros(off[3], dtype=bool)
-        for k0, k1 in ((0, 2), (2, 3)):                           # the exchanged ranges of arch 1 (csrc/dp_fused.cu)
+        whole = ctypes.c_int32(0)
+        nv._lib.check(model.lib.nvqa_dp_layout(model.handle, ctypes.byref(whole)))
+        for k0, k1 in (((0, 3),) if whole.value else ((0, 2), (2, 3))):   # the exchanged ranges of arch 1 (csrc/dp_fused.cu)
             b0, b1 = off[k0] // 4, off[k1] // 4
             per = (b1 - b0 + world - 1) // world
             lo = min(b1, b0 + per * rank)

@@ -233,6 +233,10 @@ int nvqa_dp_train_step(nvqa_model* m, float lr, uint64_t seed, float alpha, floa
 /* A lagging peer is waited for up to NVQA_DP_TIMEOUT_S seconds (environment, default 600); then the wait gives up and
  * *timed_out = 1 from here on (nvqa_sync returns an error): the replica's parameters are invalid, the process survives. */
 int nvqa_dp_status(nvqa_model* m, int32_t* timed_out);
+/* partition of the flat vector among the ranks (it also shards the RMSprop state): *whole_vector = 1: rank r owns the r-th
+ * 1/N of the whole vector; 0: of each of the two ranges {encoder + embedding} and {multimodal}.  Fixed at nvqa_dp_connect
+ * (set -lr_scale before connecting). */
+int nvqa_dp_layout(nvqa_model* m, int32_t* whole_vector);
 
 /* ---- utilities ------------------------------------------------------------------------------ */
 int nvqa_host_alloc(void** p, int64_t bytes);     /* pinned host memory */

@@ -84,6 +84,7 @@ SIGNATURES = {
     "nvqa_dp_rmsprop_step": (C.c_int, [C.c_void_p] + [C.c_float] * 5),
     "nvqa_dp_train_step": (C.c_int, [C.c_void_p, C.c_float, C.c_uint64] + [C.c_float] * 4),
     "nvqa_dp_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "nvqa_dp_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "nvqa_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "nvqa_host_free": (C.c_int, [C.c_void_p]),
     "nvqa_device_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

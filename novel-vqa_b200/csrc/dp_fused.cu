@@ -64,9 +64,14 @@ __device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int t
   }
 }
 // peer memory is read exactly once per step: bypass L1 (lines of a remote GPU must never be served stale)
-__device__ __forceinline__ float4 ld_peer(const float* p) {
+__device__ __forceinline__ float4 ld_peer(const float* p, int mode) {
   float4 v;
-  asm volatile("ld.global.cv.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  if (mode == 0)
+    asm volatile("ld.global.cv.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  else if (mode == 1)
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  else
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 
@@ -75,7 +80,7 @@ __device__ __forceinline__ float4 ld_peer(const float* p) {
 __global__ void __launch_bounds__(256)
 dp_fused_rmsprop_kernel(DpPeers p, float* __restrict__ rms, unsigned int* my_flags, int block, int rank, int world,
                         long long lo4, long long n4, unsigned int step, float lr, float alpha, float oma, float eps, float wd,
-                        float clampv, float gscale, unsigned long long timeout_ns) {
+                        float clampv, float gscale, unsigned long long timeout_ns, int ldmode) {
   unsigned int* ready = my_flags + 32 * block;
   unsigned int* done = ready + 16;
   // "my gradients of this range are final": everything earlier on this stream -- the backward kernels -- has completed
@@ -101,7 +106,7 @@ dp_fused_rmsprop_kernel(DpPeers p, float* __restrict__ rms, unsigned int* my_fla
 #pragma unroll
         for (int r = 0; r < DP_MAX; ++r) {
           if (r < world) {
-            const float4 v = ld_peer(p.g[r] + e);
+            const float4 v = ld_peer(p.g[r] + e, ldmode);
             g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
           }
         }
@@ -132,6 +137,145 @@ dp_fused_rmsprop_kernel(DpPeers p, float* __restrict__ rms, unsigned int* my_fla
   if (threadIdx.x == 0) {
     const unsigned int prev = atomicAdd(my_flags + DP_CTR + block, 1u);
     if (prev == gridDim.x - 1) {                 // last CTA of this rank: everything this rank reads / writes is done
+      my_flags[DP_CTR + block] = 0;
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) st_release_sys(p.flags[r] + 32 * block + 16 + rank, 2 * step + 2);
+      for (int r = 0; r < world; ++r) spin_until(done + r, 2 * step + 2, timeout_ns, my_flags + DP_ERR);
+    }
+  }
+}
+
+// ---- the same exchange with BULK ASYNC COPIES (default; NVQA_DP_BULK=0 restores the ld / st kernel above) ----------------
+// Measured on two B200s (tools/dp_probe.py): the ld.global / st.global kernel moves a rank's 27.7 MB each way in ~70 us per
+// direction-pair -- 190-280 GB/s, whatever its grid size or load flavour -- where the copy engine does 560-750 GB/s.  Here a
+// persistent CTA works through 8 KB chunks of the rank's shard in a ring of stages: ONE thread asks the TMA unit for the
+// chunk of every rank's gradient (peers through NVLink), of the parameters and of the RMSprop state
+// (cp.async.bulk.shared::cluster.global, one mbarrier per stage counts the bytes), 256 threads reduce in the fixed rank
+// order / scale / clamp / update in shared memory, and one thread stores the state back and the updated parameters into
+// EVERY rank's vector (cp.async.bulk.global.shared::cta, bulk groups).  A few CTAs keep megabytes in flight, so the same
+// kernel saturates the links from the 16 side-stream CTAs beside the LSTM backward.  Same flags, same summation order,
+// same arithmetic as the kernel above (replicas stay bit-identical; the two kernels agree bit for bit).
+constexpr int DPB_CHUNK4_DEFAULT = 512;         // float4 per chunk (8 KB); NVQA_DP_CHUNK_KB overrides
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dpb_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dpb_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// false: gave up after timeout_ns of wall-clock time (the error word is raised by the caller)
+__device__ __forceinline__ bool dpb_wait(uint32_t bar, uint32_t parity, unsigned long long timeout_ns) {
+  uint32_t ok = 0;
+  const unsigned long long t0 = dp_now_ns();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+    if (dp_now_ns() - t0 > timeout_ns) return false;
+  }
+}
+
+// 1024 threads: the update is ~60 dependent instructions per element (IEEE sqrt and divide); with 8 warps per CTA it was
+// latency-bound at 2.6 us per 8 KB chunk (72 us for a 27.7 MB shard with no NVLink traffic at all, tools/dp_probe2.sh)
+constexpr int DPB_THREADS = 1024;
+__global__ void __launch_bounds__(DPB_THREADS, 1)
+dp_bulk_rmsprop_kernel(DpPeers p, float* __restrict__ rms, unsigned int* my_flags, int block, int rank, int world,
+                       long long lo4, long long n4, unsigned int step, float lr, float alpha, float oma, float eps, float wd,
+                       float clampv, float gscale, unsigned long long timeout_ns, int stages, int DPB_CHUNK4, int dbg) {
+  extern __shared__ __align__(128) uint8_t dpb_smem[];
+  const uint32_t DPB_CHUNK = (uint32_t)DPB_CHUNK4 * 16u;
+  // stage s: [world gradient chunks][parameter chunk][state chunk]; the `stages` mbarriers follow the last stage
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dpb_smem);
+  const uint32_t stage_bytes = (uint32_t)(world + 2) * DPB_CHUNK;
+  const uint32_t bar0 = sbase + (uint32_t)stages * stage_bytes;
+  unsigned int* ready = my_flags + 32 * block;
+  unsigned int* done = ready + 16;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) dpb_mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + 32 * block + rank, 2 * step + 1);
+  }
+  if ((int)threadIdx.x < world) spin_until(ready + threadIdx.x, 2 * step + 1, timeout_ns, my_flags + DP_ERR);
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");         // the acquired gradients are read through the async proxy below
+
+  const long long nchunks = (n4 + DPB_CHUNK4 - 1) / DPB_CHUNK4;
+  const long long mine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // chunks c = blockIdx.x + k * gridDim.x
+  auto issue_loads = [&](long long k) {                    // thread 0: chunk k of this CTA into stage k % stages
+    const long long c = blockIdx.x + k * gridDim.x;
+    const long long f0 = lo4 + c * DPB_CHUNK4;
+    const uint32_t bytes = (uint32_t)(min((long long)DPB_CHUNK4, n4 - c * DPB_CHUNK4) * 16);
+    const int s = (int)(k % stages);
+    const uint32_t st = sbase + (uint32_t)s * stage_bytes, bar = bar0 + 8 * s;
+    dpb_expect_tx(bar, bytes * (uint32_t)(world + 2));
+    for (int r = 0; r < world; ++r) bulk_g2s(st + (uint32_t)r * DPB_CHUNK, p.g[(dbg & 1) ? rank : r] + f0 * 4, bytes, bar);
+    bulk_g2s(st + (uint32_t)world * DPB_CHUNK, p.x[rank] + f0 * 4, bytes, bar);
+    bulk_g2s(st + (uint32_t)(world + 1) * DPB_CHUNK, rms + f0 * 4, bytes, bar);
+  };
+  if (threadIdx.x == 0)
+    for (long long k = 0; k < mine && k < stages; ++k) issue_loads(k);
+  bool ok = true;       // a wait that gave up raises the error word; the kernel still runs to completion (no divergent exit)
+  for (long long k = 0; k < mine; ++k) {
+    const long long c = blockIdx.x + k * gridDim.x;
+    const int cnt4 = (int)min((long long)DPB_CHUNK4, n4 - c * DPB_CHUNK4);
+    const int s = (int)(k % stages);
+    uint8_t* st = dpb_smem + (size_t)s * stage_bytes;
+    if (!dpb_wait(bar0 + 8 * s, (uint32_t)(k / stages) & 1u, timeout_ns)) ok = false;
+    float4* xs = reinterpret_cast<float4*>(st + (size_t)world * DPB_CHUNK);
+    float4* ms = reinterpret_cast<float4*>(st + (size_t)(world + 1) * DPB_CHUNK);
+    for (int j = threadIdx.x; j < cnt4; j += DPB_THREADS) {
+      {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < world; ++r) {
+          const float4 v = reinterpret_cast<const float4*>(st + (size_t)r * DPB_CHUNK)[j];
+          g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+        }
+        float4 xv = xs[j], mv = ms[j];
+#define UP(q)                                                      \
+        { float gg = fminf(fmaxf(g.q * gscale, -clampv), clampv);  \
+          gg += wd * xv.q;                                         \
+          mv.q = alpha * mv.q + oma * gg * gg;                     \
+          xv.q -= lr * (gg / (sqrtf(mv.q) + eps)); }
+        UP(x) UP(y) UP(z) UP(w)
+#undef UP
+        xs[j] = xv; ms[j] = mv;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the updated chunks are read by the bulk stores
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long long f0 = lo4 + c * DPB_CHUNK4;
+      const uint32_t bytes = (uint32_t)cnt4 * 16u;
+      const uint32_t sx = sbase + (uint32_t)s * stage_bytes + (uint32_t)world * DPB_CHUNK;
+      bulk_s2g(rms + f0 * 4, sx + DPB_CHUNK, bytes);
+      for (int r = 0; r < world; ++r)
+        if (!(dbg & 2) || r == rank) bulk_s2g(p.x[r] + f0 * 4, sx, bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // refill the stage of the PREVIOUS chunk once its stores have read it (one store group stays in flight)
+      if (k >= 1 && k - 1 + stages < mine) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        issue_loads(k - 1 + stages);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");         // every store of this CTA has been performed
+  }
+  if (!ok) my_flags[DP_ERR] = 1u;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(my_flags + DP_CTR + block, 1u);
+    if (prev == gridDim.x - 1) {
       my_flags[DP_CTR + block] = 0;
       __threadfence_system();
       for (int r = 0; r < world; ++r) st_release_sys(p.flags[r] + 32 * block + 16 + rank, 2 * step + 2);
@@ -198,6 +342,14 @@ extern "C" int nvqa_dp_connect(nvqa_model* m, int32_t rank, int32_t world, const
   }
   m->dp_rank = rank; m->dp_world = world;
   for (int k = 0; k < 3; ++k) m->dp_steps[k] = 0;
+  // one exchange kernel for the whole vector when the multimodal block is not exchanged early (see nvqa_dp_train_step) and
+  // one gradient scale covers everything; NVQA_DP_WHOLE=0 keeps the two ranges
+  {
+    const char* eo = getenv("NVQA_DP_OVERLAP");
+    const char* ew = getenv("NVQA_DP_WHOLE");
+    const int overlap = eo ? atoi(eo) : (world >= 4 ? 1 : 0);
+    m->dp_whole_vector = m->cfg.arch == 1 && !overlap && m->lr_scale == 1.0f && !(ew && atoi(ew) == 0);
+  }
   return 0;
 }
 
@@ -208,6 +360,15 @@ extern "C" int nvqa_dp_disconnect(nvqa_model* m) {
   for (void* p : m->dp_opened) cudaIpcCloseMemHandle(p);
   m->dp_opened.clear();
   m->dp_world = 0;
+  return 0;
+}
+
+// How the flat vector is partitioned among the ranks (which also shards the RMSprop state): *whole_vector = 1 -> one range,
+// every rank owns the r-th 1/N of the whole vector; 0 -> two ranges {encoder + embedding}, {multimodal}, a rank owns the
+// r-th 1/N of each (arch 1 with the multimodal exchange overlapped, or with -lr_scale)
+extern "C" int nvqa_dp_layout(nvqa_model* m, int32_t* whole_vector) {
+  NVQA_CHECK(m && whole_vector, "null argument");
+  *whole_vector = (m->dp_whole_vector || m->cfg.arch != 1) ? 1 : 0;
   return 0;
 }
 
@@ -264,8 +425,39 @@ static int dp_range(nvqa_model* m, int blk0, int blk1, float lr, float alpha, fl
     NVQA_CUDA(cudaFuncSetAttribute(dp_fused_rmsprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
+  static int bulk = -1;
+  if (bulk < 0) { const char* e = getenv("NVQA_DP_BULK"); bulk = e ? atoi(e) : 1; }
+  if (bulk) {
+    // persistent CTAs, one per SM (side: side_ctas), ring of 2..6 stages of (world + 2) x 8 KB
+    static int chunk4 = -1;
+    if (chunk4 < 0) { const char* e = getenv("NVQA_DP_CHUNK_KB"); chunk4 = e ? std::max(1, std::min(32, atoi(e))) * 64 : 0; }
+    // default: 16 KB chunks (one float4 per thread) while three stages of (world + 2) chunks fit, else 8 KB
+    const int DPB_CHUNK4 = chunk4 ? chunk4 : ((size_t)(m->dp_world + 2) * 16384 * 3 <= 200 * 1024 ? 1024 : DPB_CHUNK4_DEFAULT);
+    const size_t stage_bytes = (size_t)(m->dp_world + 2) * DPB_CHUNK4 * 16;
+    int stages = (int)std::min<size_t>(8, (200 * 1024) / stage_bytes);
+    if (stages < 2) stages = 2;
+    const size_t bsmem = stages * stage_bytes + 64;
+    static bool battr = false;
+    if (!battr) {
+      NVQA_CUDA(cudaFuncSetAttribute(dp_bulk_rmsprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      battr = true;
+    }
+    static int bulk_ctas = -1;
+    if (bulk_ctas < 0) { const char* e = getenv("NVQA_DP_BULK_CTAS"); bulk_ctas = e ? std::max(1, atoi(e)) : 148; }
+    static int dbgmode = -1;         // timing experiments only (tools/dp_probe.py): 1 no peer loads, 2 no peer stores
+    if (dbgmode < 0) { const char* e = getenv("NVQA_DP_DBG"); dbgmode = e ? atoi(e) : 0; }
+    const long long nchunks = ceil_div(n4, (long long)DPB_CHUNK4);
+    const int bgrid = (int)std::max<long long>(1, std::min<long long>(nchunks, side ? side_ctas : bulk_ctas));
+    dp_bulk_rmsprop_kernel<<<bgrid, DPB_THREADS, bsmem, s>>>(p, m->rms, m->dp_flags, blk0, m->dp_rank, m->dp_world, lo4, n4, step, lr,
+                                                    alpha, (float)(1.0 - (double)alpha), eps, wd, clamp, gscale,
+                                                    dp_timeout_ns(), stages, DPB_CHUNK4, dbgmode);
+    NVQA_LAUNCHED();
+    return 0;
+  }
+  static int ldmode = -1;
+  if (ldmode < 0) { const char* e = getenv("NVQA_DP_LD"); ldmode = e ? atoi(e) : 0; }
   dp_fused_rmsprop_kernel<<<grid, 256, smem, s>>>(p, m->rms, m->dp_flags, blk0, m->dp_rank, m->dp_world, lo4, n4, step, lr, alpha,
-                                                 (float)(1.0 - (double)alpha), eps, wd, clamp, gscale, dp_timeout_ns());
+                                                 (float)(1.0 - (double)alpha), eps, wd, clamp, gscale, dp_timeout_ns(), ldmode);
   NVQA_LAUNCHED();
   return 0;
 }
@@ -273,6 +465,14 @@ static int dp_range(nvqa_model* m, int blk0, int blk1, float lr, float alpha, fl
 // the whole flat vector at once
 static int dp_tail_ranges(nvqa_model* m, float lr, float alpha, float eps, float wd, float clamp, bool with_multimodal) {
   if (m->cfg.arch != 1) return dp_range(m, 0, 2, lr, alpha, eps, wd, clamp, false);
+  // all three blocks are due and share one gradient scale: ONE kernel (one ready / done flag round instead of two).  The
+  // flag channel of a range is its first block, and the per-channel step counters advance independently, so a run may mix
+  // this with the two-range form only if it always uses the same form: decided once per connection
+  if (m->dp_whole_vector) {
+    NVQA_CHECK(with_multimodal, "whole-vector exchange: the multimodal block cannot be exchanged separately");
+    NVQA_CHECK(m->lr_scale == 1.0f, "-lr_scale must be set before nvqa_dp_connect (it splits the exchange into two ranges)");
+    return dp_range(m, 0, 2, lr, alpha, eps, wd, clamp, false);
+  }
   NVQA_TRY(dp_range(m, NVQA_BLOCK_ENCODER, NVQA_BLOCK_EMBEDDING, lr, alpha, eps, wd, clamp, false));
   if (with_multimodal) NVQA_TRY(dp_range(m, NVQA_BLOCK_MULTIMODAL, NVQA_BLOCK_MULTIMODAL, lr, alpha, eps, wd, clamp, false));
   return 0;
@@ -317,7 +517,7 @@ extern "C" int nvqa_dp_train_step(nvqa_model* m, float lr, uint64_t seed, float 
   // 16-CTA side kernel is slower than the tail kernel it saves (1.622 -> 1.645 ms), so the default is by world size
   static int overlap_env = -2;
   if (overlap_env == -2) { const char* e = getenv("NVQA_DP_OVERLAP"); overlap_env = e ? atoi(e) : -1; }
-  const int overlap = overlap_env >= 0 ? overlap_env : (m->dp_world >= 4 ? 1 : 0);
+  const int overlap = m->dp_whole_vector ? 0 : (overlap_env >= 0 ? overlap_env : (m->dp_world >= 4 ? 1 : 0));
   m->fused_step = true;            // a backward follows: its gradient slices are cleared beside the forward (model.cu)
   const int frc = nvqa_forward(m, NVQA_MODE_TRAIN, seed);
   m->fused_step = false;

@@ -117,6 +117,8 @@ struct nvqa_model {
   unsigned int* dp_peer_flags[16] = {};
   unsigned int dp_steps[3] = {0, 0, 0};   // exchanges done so far, per parameter block
   cudaEvent_t dp_fork = nullptr, dp_join = nullptr;
+  bool dp_whole_vector = false;      // the exchange is ONE range (whole flat vector) instead of {encoder + embedding}, {multimodal}:
+                                     // fixed at nvqa_dp_connect, because the partition also shards the RMSprop state
   // Side stream: work that does not depend on the LSTM runs beside the 128-CTA persistent recurrent kernels, on the ~20 SMs
   // they leave free -- forward: fc7 norm + Dropout + the image Linear of AxB; backward: the weight gradients of the two AxB
   // Linears; data parallel: the exchange of the multimodal block (dp_fused.cu).  aux_fwd / aux_bwd: that work is due and
