@@ -533,7 +533,7 @@ def run_ours(args):
                            "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision,
                            "parallelism": f"dp{world}",
                            "collective": ("none" if world == 1 else "fused NVLink reduce-scatter + RMSprop + all-gather kernel "
-                                          "over CUDA-IPC peer memory (csrc/dp_fused.cu)" if fused else
+                                          "over CUDA-IPC peer memory, bulk async copies (csrc/dp_fused.cu)" if fused else
                                           "NCCL all-reduce, 3 buckets overlapped with backward"), "dropout": "in-kernel counter hash, p=0.5",
                            "l2": "working set (params+grads+rms 166 MB, activations > 600 MB) exceeds the 126 MB L2; "
                                  "no explicit flush",
@@ -542,12 +542,19 @@ def run_ours(args):
                                                       else "one 64-row tile")
                                                    + (", 4-D TMA boxes" if os.environ.get("NVQA_LSTM_BOX4D", "1") != "0" else ""),
                                        "lstm_bwd": "4-CTA clusters, DSMEM split-K reduction"
+                                                   + (", 2 pipelined sub-tiles" if os.environ.get("NVQA_LSTM_BWD_SPLIT", "1") != "0" else "")
                                                    + (", 4-D TMA boxes" if os.environ.get("NVQA_LSTM_BOX4D", "1") != "0" else ""),
                                        "gemm": ("cta_group::2 pairs (256 x BN tiles), " if os.environ.get("NVQA_GEMM_PAIR", "1") != "0" else "")
-                                               + ("persistent CTAs, 2 TMEM accumulator stages, full-line epilogue stores"
-                                                  if os.environ.get("NVQA_GEMM_PERSIST", "1") != "0" else "one tile per CTA"),
-                                       "side_stream": "image branch + classifier / AxB weight gradients beside the recurrent kernels"
+                                               + ("persistent CTAs, 2 TMEM accumulator stages, "
+                                                  if os.environ.get("NVQA_GEMM_PERSIST", "1") != "0" else "one tile per CTA, ")
+                                               + ("TMA-store epilogue" if os.environ.get("NVQA_GEMM_TMA_STORE", "1") != "0"
+                                                  else "full-line st.global epilogue")
+                                               + (", wave-aware tile width / split-K" if os.environ.get("NVQA_GEMM_SHAPE_V2", "1") != "0" else ""),
+                                       "side_stream": "image branch, classifier / AxB weight gradients + their optimizer, deferred split-K "
+                                                      "reductions, gradient clearing beside the recurrent kernels"
                                                       if os.environ.get("NVQA_AUX_STREAM", "1") != "0" else "off",
+                                       "launch": "programmatic dependent launch (griddepcontrol) for GEMM / element-wise kernels"
+                                                 if os.environ.get("NVQA_PDL", "1") != "0" else "fully serialised",
                                        "planes": "written by the producer kernels" if os.environ.get("NVQA_PRODUCER_PLANES", "1") != "0"
                                                  else "split pass per GEMM operand"}},
                 "clocks": clocks,
