@@ -34,6 +34,7 @@ __device__ __forceinline__ int ae_token(const int32_t* __restrict__ seq, int64_t
 __global__ void __launch_bounds__(256)
 ae_embed_fwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ table, float* __restrict__ y, Drop denc,
                     Drop ddec, int B, int T, int E, int V, int tmax) {
+  pdl_entry();
   const int E4 = E >> 2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)(2 * tmax + 1) * B * E4) return;
@@ -49,7 +50,7 @@ ae_embed_fwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ t
 int ae_embed_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* y, Drop denc, Drop ddec, int B, int T, int E,
                  int V, int tmax) {
   const int64_t total = (int64_t)(2 * tmax + 1) * B * (E / 4);
-  ae_embed_fwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(seq, table, y, denc, ddec, B, T, E, V, tmax);
+  NVQA_CUDA(launch_pdl(ae_embed_fwd_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, s, seq, table, y, denc, ddec, B, T, E, V, tmax));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -58,6 +59,7 @@ int ae_embed_fwd(cudaStream_t s, const int32_t* seq, const float* table, float* 
 __global__ void __launch_bounds__(256)
 ae_embed_bwd_kernel(const int32_t* __restrict__ seq, const float* __restrict__ y, const float* __restrict__ dx,
                     float* __restrict__ dtable, Drop denc, Drop ddec, int B, int T, int E, int V, int tmax) {
+  pdl_entry();
   const int E4 = E >> 2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)(2 * tmax + 1) * B * E4) return;
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256)
 ae_embed_bwd_hot_kernel(const int32_t* __restrict__ seq, const float* __restrict__ y, const float* __restrict__ dx,
                         float* __restrict__ dtable, Drop denc, Drop ddec, int B, int T, int E, int V, int tmax,
                         int rows_per_chunk) {
+  pdl_entry();
   __shared__ float red[2][8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
   const int64_t rows = (int64_t)(2 * tmax + 1) * B;
@@ -113,12 +116,12 @@ ae_embed_bwd_hot_kernel(const int32_t* __restrict__ seq, const float* __restrict
 int ae_embed_bwd(cudaStream_t s, const int32_t* seq, const float* y, const float* dx, float* dtable, Drop denc, Drop ddec,
                  int B, int T, int E, int V, int tmax) {
   const int64_t total = (int64_t)(2 * tmax + 1) * B * (E / 4);
-  ae_embed_bwd_kernel<<<ceil_div(total, 256), 256, 0, s>>>(seq, y, dx, dtable, denc, ddec, B, T, E, V, tmax);
+  NVQA_CUDA(launch_pdl(ae_embed_bwd_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, s, seq, y, dx, dtable, denc, ddec, B, T, E, V, tmax));
   NVQA_LAUNCHED();
   const int64_t rows = (int64_t)(2 * tmax + 1) * B;
   const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, rows / 64));
   dim3 grid(ceil_div(E, 32), chunks);
-  ae_embed_bwd_hot_kernel<<<grid, 256, 0, s>>>(seq, y, dx, dtable, denc, ddec, B, T, E, V, tmax, ceil_div(rows, chunks));
+  NVQA_CUDA(launch_pdl(ae_embed_bwd_hot_kernel, dim3(grid), dim3(256), 0, s, seq, y, dx, dtable, denc, ddec, B, T, E, V, tmax, ceil_div(rows, chunks)));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -126,6 +129,7 @@ int ae_embed_bwd(cudaStream_t s, const int32_t* seq, const float* y, const float
 // nn.LanguageModelCriterion target selection (:427-447): targets [(T+1) x B] (0 = no prediction), n_pred += count
 __global__ void __launch_bounds__(256)
 lm_targets_kernel(const int32_t* __restrict__ seq, int32_t* __restrict__ targets, int32_t* __restrict__ n_pred, int B, int T, int V) {
+  pdl_entry();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;
   if (b < B) {
@@ -144,7 +148,7 @@ lm_targets_kernel(const int32_t* __restrict__ seq, int32_t* __restrict__ targets
 
 int lm_targets(cudaStream_t s, const int32_t* seq, int32_t* targets, int32_t* n_pred, int B, int T, int V) {
   NVQA_CUDA(cudaMemsetAsync(n_pred, 0, sizeof(int32_t), s));
-  lm_targets_kernel<<<ceil_div(B, 256), 256, 0, s>>>(seq, targets, n_pred, B, T, V);
+  NVQA_CUDA(launch_pdl(lm_targets_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, s, seq, targets, n_pred, B, T, V));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -168,6 +172,7 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) 
 // criterion's term of that row: rowloss = -logp[target] (0 when the row predicts nothing).
 __global__ void __launch_bounds__(256)
 logsoftmax_lm_kernel(float* __restrict__ x, int ld, int ncols, const int32_t* __restrict__ targets, float* __restrict__ rowloss) {
+  pdl_entry();
   __shared__ float red[8];
   float* r = x + (int64_t)blockIdx.x * ld;
   const int n4 = ncols >> 2;
@@ -199,7 +204,7 @@ logsoftmax_lm_kernel(float* __restrict__ x, int ld, int ncols, const int32_t* __
 
 int logsoftmax_lm(cudaStream_t s, float* x, int rows, int ld, int ncols, const int32_t* targets, float* rowloss) {
   if (rows <= 0) return 0;
-  logsoftmax_lm_kernel<<<rows, 256, 0, s>>>(x, ld, ncols, targets, rowloss);
+  NVQA_CUDA(launch_pdl(logsoftmax_lm_kernel, dim3(rows), dim3(256), 0, s, x, ld, ncols, targets, rowloss));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -209,6 +214,7 @@ int logsoftmax_lm(cudaStream_t s, float* x, int rows, int ld, int ncols, const i
 __global__ void __launch_bounds__(256)
 lm_row_stats_kernel(const float* __restrict__ x, int ld, int ncols, const int32_t* __restrict__ targets, float* __restrict__ lse_out,
                     float* __restrict__ rowloss) {
+  pdl_entry();
   __shared__ float red[8];
   const float* r = x + (int64_t)blockIdx.x * ld;
   const int n4 = ncols >> 2;
@@ -238,7 +244,7 @@ lm_row_stats_kernel(const float* __restrict__ x, int ld, int ncols, const int32_
 
 int lm_row_stats(cudaStream_t s, const float* x, int rows, int ld, int ncols, const int32_t* targets, float* lse, float* rowloss) {
   if (rows <= 0) return 0;
-  lm_row_stats_kernel<<<rows, 256, 0, s>>>(x, ld, ncols, targets, lse, rowloss);
+  NVQA_CUDA(launch_pdl(lm_row_stats_kernel, dim3(rows), dim3(256), 0, s, x, ld, ncols, targets, lse, rowloss));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -246,6 +252,7 @@ int lm_row_stats(cudaStream_t s, const float* x, int rows, int ld, int ncols, co
 // log-probs of nrows rows (logits - lse) into a dense [nrows x ncols] buffer (nvqa_logprobs_get)
 __global__ void __launch_bounds__(256)
 lm_logprobs_kernel(const float* __restrict__ x, const float* __restrict__ lse, int ld, int ncols, float* __restrict__ out) {
+  pdl_entry();
   const int row = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < ncols) out[(int64_t)row * ncols + j] = x[(int64_t)row * ld + j] - lse[row];
@@ -254,7 +261,7 @@ lm_logprobs_kernel(const float* __restrict__ x, const float* __restrict__ lse, i
 int lm_logprobs(cudaStream_t s, const float* x, const float* lse, int nrows, int ld, int ncols, float* out) {
   if (nrows <= 0) return 0;
   dim3 grid(ceil_div(ncols, 256), nrows);
-  lm_logprobs_kernel<<<grid, 256, 0, s>>>(x, lse, ld, ncols, out);
+  NVQA_CUDA(launch_pdl(lm_logprobs_kernel, dim3(grid), dim3(256), 0, s, x, lse, ld, ncols, out));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -269,6 +276,7 @@ __global__ void __launch_bounds__(256)
 lm_grad_planes_kernel(const float* __restrict__ x, const float* __restrict__ lse, int rows, int ld, int ncols,
                       const int32_t* __restrict__ targets, const int32_t* __restrict__ n_pred, float gscale,
                       __nv_bfloat16* __restrict__ planes, int pitch, long long plane_stride, int P, float* __restrict__ gbias) {
+  pdl_entry();
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (j >= pitch) return;
   const int r0 = blockIdx.y * LMG_RPC, r1 = min(rows, r0 + LMG_RPC);
@@ -334,7 +342,7 @@ int lm_grad_planes(cudaStream_t s, const float* x, const float* lse, int rows, i
                    float* gbias) {
   if (rows <= 0) return 0;
   dim3 grid(ceil_div(pitch / 4, 256), ceil_div(rows, LMG_RPC));
-  lm_grad_planes_kernel<<<grid, 256, 0, s>>>(x, lse, rows, ld, ncols, targets, n_pred, gscale, planes, pitch, plane_stride, P, gbias);
+  NVQA_CUDA(launch_pdl(lm_grad_planes_kernel, dim3(grid), dim3(256), 0, s, x, lse, rows, ld, ncols, targets, n_pred, gscale, planes, pitch, plane_stride, P, gbias));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -342,6 +350,7 @@ int lm_grad_planes(cudaStream_t s, const float* x, const float* lse, int rows, i
 // loss = sum(rowloss) / n_pred in a fixed order (deterministic)   (:449)
 __global__ void __launch_bounds__(256)
 lm_loss_reduce_kernel(const float* __restrict__ rowloss, int rows, const int32_t* __restrict__ n_pred, float* __restrict__ loss) {
+  pdl_entry();
   __shared__ float red[8];
   float acc = 0.f;
   for (int i = threadIdx.x; i < rows; i += 256) acc += rowloss[i];
@@ -350,7 +359,7 @@ lm_loss_reduce_kernel(const float* __restrict__ rowloss, int rows, const int32_t
 }
 
 int lm_loss_reduce(cudaStream_t s, const float* rowloss, int rows, const int32_t* n_pred, float* loss) {
-  lm_loss_reduce_kernel<<<1, 256, 0, s>>>(rowloss, rows, n_pred, loss);
+  NVQA_CUDA(launch_pdl(lm_loss_reduce_kernel, dim3(1), dim3(256), 0, s, rowloss, rows, n_pred, loss));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -360,6 +369,7 @@ int lm_loss_reduce(cudaStream_t s, const float* rowloss, int rows, const int32_t
 __global__ void __launch_bounds__(256)
 lm_grad_kernel(float* __restrict__ lp, int ld, int ncols, const int32_t* __restrict__ targets, const int32_t* __restrict__ n_pred,
                float gscale) {
+  pdl_entry();
   const int row = blockIdx.y;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (j >= ld) return;
@@ -380,7 +390,7 @@ lm_grad_kernel(float* __restrict__ lp, int ld, int ncols, const int32_t* __restr
 int lm_grad(cudaStream_t s, float* lp, int rows, int ld, int ncols, const int32_t* targets, const int32_t* n_pred, float gscale) {
   if (rows <= 0) return 0;
   dim3 grid(ceil_div(ld / 4, 256), rows);
-  lm_grad_kernel<<<grid, 256, 0, s>>>(lp, ld, ncols, targets, n_pred, gscale);
+  NVQA_CUDA(launch_pdl(lm_grad_kernel, dim3(grid), dim3(256), 0, s, lp, ld, ncols, targets, n_pred, gscale));
   NVQA_LAUNCHED();
   return 0;
 }
@@ -390,6 +400,7 @@ int lm_grad(cudaStream_t s, float* lp, int rows, int ld, int ncols, const int32_
 __global__ void __launch_bounds__(256)
 clamp_adam_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
                   float step, float b1, float omb1, float b2, float omb2, float eps, float wd, float clampv, float gscale) {
+  pdl_entry();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
@@ -418,8 +429,8 @@ int clamp_adam(cudaStream_t s, float* x, const float* g, float* m, float* v, int
                float eps, float wd, float clamp, float gscale, int64_t t) {
   const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
   const float step = (float)((double)lr * sqrt(bc2) / bc1);
-  clamp_adam_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(x, g, m, v, n, step, beta1, (float)(1.0 - (double)beta1), beta2,
-                                                                 (float)(1.0 - (double)beta2), eps, wd, clamp, gscale);
+  NVQA_CUDA(launch_pdl(clamp_adam_kernel, dim3(ceil_div(ceil_div(n, 4), 256)), dim3(256), 0, s, x, g, m, v, n, step, beta1, (float)(1.0 - (double)beta1), beta2,
+                                                                 (float)(1.0 - (double)beta2), eps, wd, clamp, gscale));
   NVQA_LAUNCHED();
   return 0;
 }
