@@ -343,7 +343,11 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     int it = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs) {
     const int tz = tile / (tiles_n * tiles_m2), ty = (tile / tiles_n) % tiles_m2, tx = tile % tiles_n;
-    const int m0 = ty * 2 * UG_BM + (int)rank * UG_BM, n0 = tx * BN + (int)rank * (BN / 2);
+    // the last column tile may be narrow: the pair multiplies N = neff columns only (next multiple of 16 of what is left),
+    // of which each CTA supplies neff / 2 -- so the peer's half starts neff / 2 columns in, not BN / 2
+    const int nrem = N - tx * BN;
+    const int neff = nrem >= BN ? BN : ((nrem + 15) & ~15);
+    const int m0 = ty * 2 * UG_BM + (int)rank * UG_BM, n0 = tx * BN + (int)rank * (neff / 2);
     const int kb0 = tz * kb_per_split;
     const int nkb = min(nkb_all, kb0 + kb_per_split) - kb0;
     for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -381,10 +385,11 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the leader's warp issues for the pair =====
-    constexpr uint32_t idesc = make_idesc_bf16(2 * UG_BM, BN, AMN, BMN);
     int it = 0, li = 0;
     for (int tile = pair; tile < (rank == 0 ? total_tiles : 0); tile += npairs, ++li) {
     const int tz = tile / (tiles_n * tiles_m2);
+    const int nrem = N - (tile % tiles_n) * BN;
+    const uint32_t idesc = make_idesc_bf16(2 * UG_BM, nrem >= BN ? BN : ((nrem + 15) & ~15), AMN, BMN);   // see the producer
     const int kb0 = tz * kb_per_split;
     const int nkb = min(nkb_all, kb0 + kb_per_split) - kb0;
     const int as = li & 1;
@@ -1003,16 +1008,20 @@ int umma_gemm_ops(cudaStream_t s, int planes, const UmmaOperand& A, const UmmaOp
   const int slots = pairable ? num_sms / 2 : num_sms;              // work units (pair tiles / tiles) the machine runs at once
   const int mrows = pairable ? ceil_div(M, 2 * UG_BM) : mt;
   int BN = 64;
-  if (planes <= 2 && N >= 256 && (long)mt * ceil_div(N, 256) >= num_sms / 2) {
+  // the pair kernel multiplies only the next multiple of 16 of the columns a (last) tile really has, so a 256-wide tile
+  // also serves 128 < N < 256 (N = 200, the embedding width: 208 instead of 2 x 128 columns)
+  const int nmin256 = (shape_v2 && pairable) ? 129 : 256;
+  const int n256 = ceil_div(N, 256) == 1 ? ((N + 15) & ~15) : 256;      // effective width of a 256-tile
+  if (planes <= 2 && N >= nmin256 && (long)mt * ceil_div(N, 256) >= num_sms / 2) {
     BN = 256;
     // a persistent grid runs ceil(units / slots) waves: half-width tiles (8 % more operand traffic per flop) win when
     // they fill the last wave better -- layer-2 dgrad [13000 x 512]: 102 pair tiles on 74 pairs = 2 waves of 256 columns
     // against 204 = 3 waves of 128 (0.122 -> 0.107 ms for the two dgrad GEMMs of the step)
-    const long w256 = (long)ceil_div(mrows * ceil_div(N, 256), slots) * 256 * 100;
+    const long w256 = (long)ceil_div(mrows * ceil_div(N, 256), slots) * n256 * 100;
     const long w128 = (long)ceil_div(mrows * ceil_div(N, 128), slots) * 128 * 108;
     if (shape_v2 && w128 < w256) BN = 128;
   } else if ((long)mt * ceil_div(N, 128) >= num_sms / 2) BN = 128;
-  else if (planes <= 2 && N >= 256 && K >= 2048) BN = 256;        // few tiles but a long K: wide tiles + split-K
+  else if (planes <= 2 && N >= nmin256 && K >= 2048) BN = 256;    // few tiles but a long K: wide tiles + split-K
   else if (N >= 128 && K >= 2048) BN = 128;
   const int tiles = mt * ceil_div(N, BN);
   const int nkb = ceil_div(K, UG_BK);

@@ -187,7 +187,10 @@ def test_gemm_engines_accumulate_bias_pitch(prec):
     #       M     N     K   ldc  ak bk
     for (M, N, K, ldc, ak, bk) in ((1300, 520, 192, 528, 1, 1), (1300, 520, 192, 521, 1, 1), (500, 1000, 1024, 1000, 1, 1),
                                    (2048, 200, 2600, 200, 0, 0), (300, 2048, 512, 2052, 1, 0), (100, 64, 320, 64, 1, 1),
-                                   (13000, 512, 256, 512, 1, 0)):
+                                   (13000, 512, 256, 512, 1, 0),
+                                   # narrow last column tile of the pair kernel (N = 208 / 144 of a 256-wide tile), all B layouts
+                                   (2048, 200, 2600, 200, 1, 1), (2048, 200, 2304, 200, 0, 1), (600, 136, 2304, 136, 1, 0),
+                                   (13000, 200, 2048, 200, 1, 0)):
         a = r.standard_normal((M, K)).astype(np.float32)
         b = r.standard_normal((N, K)).astype(np.float32)
         c0 = r.standard_normal((M, ldc)).astype(np.float32)
