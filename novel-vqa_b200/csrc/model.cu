@@ -623,18 +623,29 @@ struct AuxScope {
   }
 };
 static bool aux_usable(const nvqa_model* m) { return m->aux_enabled && !m->profiling && m->cfg.arch == 1 && m->planes > 0; }
+// arch 2 rides the side stream with less: the classifier's weight gradient, the deferred split-K reductions of the LSTM
+// weight gradients and the clearing launch of a fused step
+static bool aux2_usable(const nvqa_model* m) {
+  return m->aux_enabled && !m->profiling && m->cfg.arch == 2 && m->planes > 0 && m->use_persistent;
+}
 
-// arch 1: everything a backward pass accumulates into with atomics -- the bias gradients (column sums), the embedding
-// scatter -- and the step-barrier counters of its recurrent kernels, cleared by ONE launch on m->stream
+// arch 1 / arch 2: everything a backward pass accumulates into with atomics -- the bias gradients (column sums), the
+// embedding / LookupTable scatter -- and the step-barrier counters of its recurrent kernels, cleared by ONE launch on m->stream
 static int backward_prezero(nvqa_model* m) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("NVQA_PREZERO"); on = e ? atoi(e) : 1; }
   if (!on) return 0;                                  // every phase clears its own slices with cudaMemsetAsync (round 2 start)
   const nvqa_config& c = m->cfg;
   ZeroSegs z;
-  z.add(m->gbc, c.O); z.add(m->gbq, c.C); z.add(m->gbv, c.C);
+  z.add(m->gbc, c.O);
   for (int l = 0; l < c.L; ++l) { z.add(m->lg[l].bi, 4 * c.H); z.add(m->lg[l].bh, 4 * c.H); }
-  z.add(m->gWeT, m->n_blk[1]);
+  if (c.arch == 2) {
+    z.add(m->gbcnn, c.E);
+    z.add(m->glookup, (long long)(c.V + 1) * c.E);
+  } else {
+    z.add(m->gbq, c.C); z.add(m->gbv, c.C);
+    z.add(m->gWeT, m->n_blk[1]);
+  }
   z.add(m->grid_counter + 4 * 512, 4 * 512);
   NVQA_TRY(zero_segments(m->stream, z));
   m->prezero_mask = 7u;
@@ -782,9 +793,22 @@ static int forward_arch2(nvqa_model* m) {
                             (int64_t)B * H));
     m->h0_dirty = stale;
   }
+  if (m->fused_step && m->mode == NVQA_MODE_TRAIN && aux2_usable(m)) {
+    // a fused training step: the gradient slices the coming backward accumulates into (30 MB LookupTable gradient, bias
+    // vectors) and its step counters are cleared on the side stream beside the recurrence (see backward_prezero)
+    NVQA_CUDA(cudaEventRecord(m->aux_fork, s));
+    NVQA_CUDA(cudaStreamWaitEvent(m->aux_stream, m->aux_fork, 0));
+    {
+      AuxScope as(m, true);
+      NVQA_TRY(backward_prezero(m));
+      NVQA_CUDA(cudaEventRecord(m->aux_join, m->stream));
+    }
+    m->aux_fwd_inflight = true;
+  }
   LstmSeg sg;
   sg.T = steps; sg.w = m->lw; sg.g = m->lg; sg.has_init = stale;
   NVQA_TRY(lstm_layers_forward(m, sg, nullptr));
+  NVQA_TRY(aux_join_main(m));
   {
     ProfScope ps(m, CAT_PW_FWD, 0);
     NVQA_TRY(mask_copy(s, m->h[L - 1] + (int64_t)steps * B * H, H, m->state, m->zd, make_drop(m, m->mk_z, STREAM_HEAD), B, H));
@@ -957,15 +981,29 @@ static int backward_head_arch2(nvqa_model* m) {
   const nvqa_config& c = m->cfg;
   const int B = m->B, H = c.H, O = c.O;
   cudaStream_t s = m->stream;
-  NVQA_CUDA(cudaMemsetAsync(m->gbc, 0, (size_t)O * 4, s));
-  NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, O, H, B, m->dscores, O, m->zd, H, m->gWc, H, false));
-  NVQA_TRY(colsum(s, m->dscores, B, O, O, m->gbc, nullptr));
+  if (m->prezero_mask & 1u) m->prezero_mask &= ~1u;
+  else NVQA_CUDA(cudaMemsetAsync(m->gbc, 0, (size_t)O * 4, s));
+  // the input gradient the LSTM backward waits for first ...
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, true, false, B, H, O, m->dscores, O, m->Wc, H, m->dzd, H, false));
   NVQA_TRY(mask_inplace(s, m->dzd, make_drop(m, m->mk_z, STREAM_HEAD), (int64_t)B * H));
   if (m->stale_h0_literal) {   // what the literal reference leaves in init_state_enc[num_state] (Encoder_lstm.lua:238-239)
     NVQA_CUDA(cudaMemcpyAsync(m->h0_stale, m->dzd, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
     m->stale_h0_B = B;
   }
+  // ... then the classifier's weight gradient nobody waits for: beside the recurrent kernel when the LSTM phase follows
+  // in the same call (defer_head, nvqa_backward(ALL)), else right here
+  const bool side = m->defer_head && aux2_usable(m);
+  if (side) {
+    NVQA_CUDA(cudaEventRecord(m->aux_fork, s));
+    NVQA_CUDA(cudaStreamWaitEvent(m->aux_stream, m->aux_fork, 0));
+  }
+  {
+    AuxScope as(m, side);
+    NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, O, H, B, m->dscores, O, m->zd, H, m->gWc, H, false));
+    NVQA_TRY(colsum(m->stream, m->dscores, B, O, O, m->gbc, nullptr));
+    if (side) NVQA_CUDA(cudaEventRecord(m->aux_join, m->stream));
+  }
+  if (side) m->aux_bwd_inflight = true;
   return 0;
 }
 
@@ -975,8 +1013,11 @@ static int backward_embed_arch2(nvqa_model* m) {
   const int B = m->B, E = c.E;
   cudaStream_t s = m->stream;
   ProfScope ps(m, CAT_PW_BWD, 0);
-  NVQA_CUDA(cudaMemsetAsync(m->glookup, 0, (size_t)(c.V + 1) * E * 4, s));
-  NVQA_CUDA(cudaMemsetAsync(m->gbcnn, 0, (size_t)E * 4, s));
+  if (m->prezero_mask & 4u) m->prezero_mask &= ~4u;
+  else {
+    NVQA_CUDA(cudaMemsetAsync(m->glookup, 0, (size_t)(c.V + 1) * E * 4, s));
+    NVQA_CUDA(cudaMemsetAsync(m->gbcnn, 0, (size_t)E * 4, s));
+  }
   NVQA_TRY(lookup_bwd(s, m->q, m->dxbuf, m->glookup, B, c.T, E, c.V, m->steps));
   NVQA_TRY(gemm(m, CAT_HEAD_BWD, false, false, E, c.I, B, m->dxbuf, E, m->vd, c.I, m->gWcnn, c.I, false));
   NVQA_TRY(colsum(s, m->dxbuf, B, E, E, m->gbcnn, nullptr));
@@ -1179,7 +1220,7 @@ static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t*
     // waits for these weight gradients: their split-K reductions run on the side stream beside the next GEMM.
     static int defer_red = -1;
     if (defer_red < 0) { const char* e = getenv("NVQA_DEFER_REDUCE"); defer_red = e ? atoi(e) : 1; }
-    const bool defer = defer_red && m->ws && aux_usable(m);
+    const bool defer = defer_red && m->ws && (aux_usable(m) || aux2_usable(m));
     if (defer) { m->ws->reduce_stream = m->aux_stream; m->aux_reduce_used = true; }
     if (m->dap_valid) {
       // da (and h_prev) already exist as bf16 planes: no split passes, the GEMMs read them through MN-major TMA maps
@@ -1221,7 +1262,14 @@ static int backward_lstm(nvqa_model* m) {
   const float *dh0[4], *dc0[4];
   if (m->cfg.arch == 2) {   // only the top layer's final h receives a gradient (Encoder_lstm.lua:238-239)
     for (int l = 0; l < L; ++l) { dh0[l] = l == L - 1 ? m->dzd : m->zeros; dc0[l] = m->zeros; }
-    return lstm_layers_backward(m, m->steps, nullptr, dh0, dc0, H);
+    NVQA_TRY(lstm_layers_backward(m, m->steps, nullptr, dh0, dc0, H));
+    m->prezero_mask &= ~2u;
+    if (m->aux_reduce_used) {     // deferred split-K reductions: the last work on the side stream
+      NVQA_CUDA(cudaEventRecord(m->aux_join, m->aux_stream));
+      m->aux_bwd_inflight = true;
+      m->aux_reduce_used = false;
+    }
+    return aux_join_main(m);
   }
   // arch1: d tv_q = d[c1 h1 c2 h2 ...] (002_train_baseline.lua:306,313)
   for (int l = 0; l < L; ++l) { dh0[l] = m->dqd + (2 * l + 1) * H; dc0[l] = m->dqd + (2 * l) * H; }
@@ -1260,7 +1308,7 @@ extern "C" int nvqa_backward(nvqa_model* m, int phase) {
   // final: the AxB weight gradients are deferred to the side stream only when the LSTM phase follows in this very call
   const bool defer_saved = m->defer_head;
   if (phase == NVQA_PHASE_ALL) m->defer_head = true;
-  if (phase == NVQA_PHASE_ALL && m->cfg.arch == 1 && m->prezero_mask != 7u) NVQA_TRY(backward_prezero(m));
+  if (phase == NVQA_PHASE_ALL && (m->cfg.arch == 1 || m->cfg.arch == 2) && m->prezero_mask != 7u) NVQA_TRY(backward_prezero(m));
   int rc = 0;
   if (phase == NVQA_PHASE_HEAD || phase == NVQA_PHASE_ALL) rc = backward_head(m);
   m->defer_head = defer_saved;
