@@ -1,5 +1,7 @@
 #!/bin/bash
 # where does the pair kernel's epilogue time go?  (timing experiment: results invalid under dbg != 0)
+# NVQA_GEMM_EPI_DBG existed only in the working tree of this experiment (bit 1: no global stores, 2: no shared-memory
+# staging either, 4: first 32-column chunk only); the numbers are in DESIGN 5.1, the rewrite that followed is ab_r2t.sh
 run() {
 NVQA_GEMM_EPI_DBG=$1 timeout 150 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
 import json,sys
