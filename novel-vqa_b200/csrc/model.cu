@@ -628,8 +628,12 @@ static bool aux_usable(const nvqa_model* m) { return m->aux_enabled && !m->profi
 static bool aux2_usable(const nvqa_model* m) {
   return m->aux_enabled && !m->profiling && m->cfg.arch == 2 && m->planes > 0 && m->use_persistent;
 }
+// the autoencoder: only the deferred split-K reductions of its four LSTM weight-gradient GEMMs
+static bool aux3_usable(const nvqa_model* m) {
+  return m->aux_enabled && !m->profiling && m->cfg.arch == 3 && m->planes > 0 && m->use_persistent;
+}
 
-// arch 1 / arch 2: everything a backward pass accumulates into with atomics -- the bias gradients (column sums), the
+// Everything a backward pass accumulates into with atomics -- the bias gradients (column sums), the
 // embedding / LookupTable scatter -- and the step-barrier counters of its recurrent kernels, cleared by ONE launch on m->stream
 static int backward_prezero(nvqa_model* m) {
   static int on = -1;
@@ -637,13 +641,17 @@ static int backward_prezero(nvqa_model* m) {
   if (!on) return 0;                                  // every phase clears its own slices with cudaMemsetAsync (round 2 start)
   const nvqa_config& c = m->cfg;
   ZeroSegs z;
-  z.add(m->gbc, c.O);
   for (int l = 0; l < c.L; ++l) { z.add(m->lg[l].bi, 4 * c.H); z.add(m->lg[l].bh, 4 * c.H); }
-  if (c.arch == 2) {
+  if (c.arch == 3) {            // decoder vocabulary bias, decoder LSTM biases, the shared LookupTable gradient
+    z.add(m->gbd, c.V + 1);
+    for (int l = 0; l < c.L; ++l) { z.add(m->lg2[l].bi, 4 * c.H); z.add(m->lg2[l].bh, 4 * c.H); }
+    z.add(m->glookup, (long long)(c.V + 1) * c.E);
+  } else if (c.arch == 2) {
+    z.add(m->gbc, c.O);
     z.add(m->gbcnn, c.E);
     z.add(m->glookup, (long long)(c.V + 1) * c.E);
   } else {
-    z.add(m->gbq, c.C); z.add(m->gbv, c.C);
+    z.add(m->gbc, c.O); z.add(m->gbq, c.C); z.add(m->gbv, c.C);
     z.add(m->gWeT, m->n_blk[1]);
   }
   z.add(m->grid_counter + 4 * 512, 4 * 512);
@@ -1032,7 +1040,8 @@ static int backward_head_arch3(nvqa_model* m) {
   cudaStream_t s = m->stream;
   {
     ProfScope ps(m, CAT_PW_BWD, 0);
-    NVQA_CUDA(cudaMemsetAsync(m->gbd, 0, (size_t)V1 * 4, s));
+    if (m->prezero_mask & 1u) m->prezero_mask &= ~1u;
+    else NVQA_CUDA(cudaMemsetAsync(m->gbd, 0, (size_t)V1 * 4, s));
     bool done = false;
     if (m->lp_raw) {
       // d logits straight as the bf16 planes both vocabulary GEMMs below read (registered under the key they will ask for),
@@ -1069,13 +1078,21 @@ static int backward_lstm_arch3(nvqa_model* m) {
   NVQA_TRY(lstm_layers_backward(m, dec, nullptr, z, z, H, m->dhd, ae_drop(m, STREAM_AE_OUT, m->cfg.dropout), true));
   const float* dh0[4] = {m->dh_init, nullptr, nullptr, nullptr};
   const float* dc0[4] = {m->dc_init, nullptr, nullptr, nullptr};
-  return lstm_layers_backward(m, enc, nullptr, dh0, dc0, H, nullptr, none, false);
+  NVQA_TRY(lstm_layers_backward(m, enc, nullptr, dh0, dc0, H, nullptr, none, false));
+  m->prezero_mask &= ~2u;
+  if (m->aux_reduce_used) {       // deferred split-K reductions of the weight gradients: the only work on the side stream
+    NVQA_CUDA(cudaEventRecord(m->aux_join, m->aux_stream));
+    m->aux_bwd_inflight = true;
+    m->aux_reduce_used = false;
+  }
+  return aux_join_main(m);
 }
 static int backward_embed_arch3(nvqa_model* m) {
   const nvqa_config& c = m->cfg;
   cudaStream_t s = m->stream;
   ProfScope ps(m, CAT_PW_BWD, 0);
-  NVQA_CUDA(cudaMemsetAsync(m->glookup, 0, (size_t)(c.V + 1) * c.E * 4, s));
+  if (m->prezero_mask & 4u) m->prezero_mask &= ~4u;
+  else NVQA_CUDA(cudaMemsetAsync(m->glookup, 0, (size_t)(c.V + 1) * c.E * 4, s));
   return ae_embed_bwd(s, m->q, m->y, m->dxbuf, m->glookup, ae_drop(m, STREAM_AE_ENC_EMB, 0.5f), ae_drop(m, STREAM_AE_DEC_EMB, 0.5f),
                       m->B, c.T, c.E, c.V, m->steps);
 }
@@ -1220,7 +1237,7 @@ static int lstm_layers_backward(nvqa_model* m, const LstmSeg& sg, const int32_t*
     // waits for these weight gradients: their split-K reductions run on the side stream beside the next GEMM.
     static int defer_red = -1;
     if (defer_red < 0) { const char* e = getenv("NVQA_DEFER_REDUCE"); defer_red = e ? atoi(e) : 1; }
-    const bool defer = defer_red && m->ws && (aux_usable(m) || aux2_usable(m));
+    const bool defer = defer_red && m->ws && (aux_usable(m) || aux2_usable(m) || aux3_usable(m));
     if (defer) { m->ws->reduce_stream = m->aux_stream; m->aux_reduce_used = true; }
     if (m->dap_valid) {
       // da (and h_prev) already exist as bf16 planes: no split passes, the GEMMs read them through MN-major TMA maps
@@ -1308,7 +1325,7 @@ extern "C" int nvqa_backward(nvqa_model* m, int phase) {
   // final: the AxB weight gradients are deferred to the side stream only when the LSTM phase follows in this very call
   const bool defer_saved = m->defer_head;
   if (phase == NVQA_PHASE_ALL) m->defer_head = true;
-  if (phase == NVQA_PHASE_ALL && (m->cfg.arch == 1 || m->cfg.arch == 2) && m->prezero_mask != 7u) NVQA_TRY(backward_prezero(m));
+  if (phase == NVQA_PHASE_ALL && m->prezero_mask != 7u) NVQA_TRY(backward_prezero(m));
   int rc = 0;
   if (phase == NVQA_PHASE_HEAD || phase == NVQA_PHASE_ALL) rc = backward_head(m);
   m->defer_head = defer_saved;
