@@ -275,14 +275,9 @@ def run_ours(args):
                                                     out.nbytes))
             return out
 
-        mine = np.zeros(off[3], dtype=bool)
         whole = ctypes.c_int32(0)
         nv._lib.check(model.lib.nvqa_dp_layout(model.handle, ctypes.byref(whole)))
-        for k0, k1 in (((0, 3),) if whole.value else ((0, 2), (2, 3))):   # the exchanged ranges of arch 1 (csrc/dp_fused.cu)
-            b0, b1 = off[k0] // 4, off[k1] // 4
-            per = (b1 - b0 + world - 1) // world
-            lo = min(b1, b0 + per * rank)
-            mine[4 * lo:4 * min(b1, lo + per)] = True
+        mine = dp.shard_mask(off, rank, world, bool(whole.value))    # the exchanged ranges of arch 1 (csrc/dp_fused.cu)
         pa = [model.get_params(b) for b in blocks]                # Torch layout, to restore below
         r0 = [model.get_rms(b) for b in blocks]
         x0 = flat_params()

@@ -108,6 +108,20 @@ def fused_train_step(model, lr, seed, alpha=0.99, eps=1e-8, wd=0.0, clamp=10.0):
     _lib.check(model.lib.nvqa_dp_train_step(model.handle, lr, seed, alpha, eps, wd, clamp))
 
 
+def shard_mask(off, rank, world, whole_vector):
+    """Which elements of the library's internal flat vector (block offsets ``off`` = nvqa_device_views' off4, in floats)
+    rank ``rank`` of ``world`` reduces, updates and keeps the RMSprop state of -- the partition of csrc/dp_fused.cu
+    (dp_range): every exchanged range [b0, b1) is cut into ``world`` runs of ceil(n / world) float4 units.
+    ``whole_vector`` (nvqa_dp_layout): one range = the whole vector, else {encoder + embedding}, {multimodal}."""
+    mine = np.zeros(int(off[3]), dtype=bool)
+    for k0, k1 in (((0, 3),) if whole_vector else ((0, 2), (2, 3))):
+        b0, b1 = int(off[k0]) // 4, int(off[k1]) // 4
+        per = (b1 - b0 + world - 1) // world
+        lo = min(b1, b0 + per * rank)
+        mine[4 * lo:4 * min(b1, lo + per)] = True
+    return mine
+
+
 def average_then_update_reference(grads_per_rank, clamp=10.0):
     """What the collective + optimizer kernel compute, stated on host arrays (used by the gloo test):
     sum over ranks, scale 1/n, clamp."""

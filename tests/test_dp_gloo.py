@@ -78,3 +78,23 @@ def test_reference_reduction_helper():
     a = np.array([1.0, 30.0, -50.0], dtype=np.float32)
     b = np.array([3.0, 10.0, -10.0], dtype=np.float32)
     np.testing.assert_allclose(dp.average_then_update_reference([a, b]), [2.0, 10.0, -10.0])
+
+
+def test_shard_partition_covers_every_element_once():
+    """dp.shard_mask restates csrc/dp_fused.cu's partition (which also shards the RMSprop state): for every world size the
+    ranks' shards are disjoint and cover the flat vector, in both forms (whole vector / two ranges), also when a range is
+    not a multiple of world x 4 floats."""
+    import importlib
+    dp = importlib.import_module("novel_vqa_b200.dp")
+    for off in ([0, 3563520, 6518320, 13836824], [0, 40, 52, 100], [0, 8, 8, 12]):
+        for world in range(1, 9):
+            for whole in (False, True):
+                masks = [dp.shard_mask(off, r, world, whole) for r in range(world)]
+                total = np.sum(np.stack(masks).astype(np.int32), axis=0)
+                assert total.shape == (off[3],) and (total == 1).all(), (off, world, whole)
+                if not whole:          # no shard straddles the boundary of the two ranges
+                    for mk in masks:
+                        idx = np.flatnonzero(mk)
+                        lo, hi = idx[idx < off[2]], idx[idx >= off[2]]
+                        for part in (lo, hi):
+                            assert part.size == 0 or (np.diff(part) == 1).all()
