@@ -76,3 +76,41 @@ def test_every_environment_switch_is_documented():
     doc = open(os.path.join(root, "DESIGN.md")).read()
     missing = sorted(n for n in names if n not in doc)
     assert len(names) >= 40 and not missing, f"undocumented switches: {missing}"
+
+
+def test_lua_shims_call_only_declared_functions_and_are_balanced():
+    """No Lua runtime exists here, so the drop-in shims under lua/ are checked as far as text allows: every
+    nvqa_* function they call is declared in include/nvqa.h, and block openers / `end`s, parentheses, braces and brackets
+    balance in every file (comments and string literals stripped)."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set(re.findall(r"\b(nvqa_[a-z0-9_]+)\s*\(", open(os.path.join(root, "include", "nvqa.h")).read()))
+    files = sorted(glob.glob(os.path.join(root, "lua", "**", "*.lua"), recursive=True))
+    assert len(files) >= 5
+    for f in files:
+        src = open(f).read()
+        src = re.sub(r"--\[\[.*?\]\]", "", src, flags=re.S)
+        src = re.sub(r"--[^\n]*", "", src)
+        used = set(re.findall(r"\b(nvqa_[a-z0-9_]+)\s*\(", src))
+        assert used <= declared, f"{f}: calls undeclared {sorted(used - declared)}"
+        src = re.sub(r"\[\[.*?\]\]", '""', src, flags=re.S)
+        src = re.sub(r'"(?:\\.|[^"\\])*"', '""', src)
+        src = re.sub(r"'(?:\\.|[^'\\])*'", "''", src)
+        depth = pending_do = 0
+        for t in re.findall(r"\b(function|if|for|while|do|repeat|until|end)\b", src):
+            if t in ("function", "if", "repeat"):
+                depth += 1
+            elif t in ("for", "while"):
+                depth += 1
+                pending_do += 1
+            elif t == "do":
+                if pending_do:
+                    pending_do -= 1
+                else:
+                    depth += 1
+            else:                      # end / until
+                depth -= 1
+            assert depth >= 0, f"{f}: `end` without an opener"
+        assert depth == 0, f"{f}: {depth} unclosed block(s)"
+        for a, b in ("()", "{}", "[]"):
+            assert src.count(a) == src.count(b), f"{f}: unbalanced {a}{b}"
